@@ -1,0 +1,79 @@
+"""The CPU oracle (oracle/hrpose_oracle.py) against golden vectors produced by the reference's own modules
+(oracle/make_golden.py, run in the build container).  This is what pins the oracle."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import hrpose_oracle as O
+from oracle import make_golden as G
+
+GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+
+
+def _load(path):
+    g = np.load(path, allow_pickle=False)
+    cfg, batch, grid, seed = [str(v) for v in g["meta"]]
+    return g, cfg, int(batch), tuple(int(v) for v in grid.split("x")), int(seed)
+
+
+@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p) for p in GOLD])
+def test_forward_loss_grads_decode_match_reference(path):
+    g, cfg, batch, grid, seed = _load(path)
+    torch.set_num_threads(8)
+    x, poses, tgt = G.make_example(cfg, batch, grid, seed)
+    assert abs(float(x.astype(np.float64).sum()) - float(g["x_checksum"])) < 1e-6
+    np.testing.assert_array_equal(poses, g["poses"])
+    for k in ("hm", "ind", "mask", "cat", "anno_pose"):
+        np.testing.assert_array_equal(tgt[k].numpy(), g["tgt_" + k])
+    sd = {k: v.clone().requires_grad_(True) for k, v in O.synth_state_dict(cfg).items()}
+    preds = O.forward(torch.from_numpy(x), sd, cfg)
+    # same ATen kernels on both sides: only summation-order noise is allowed
+    np.testing.assert_allclose(preds["hm"].detach().numpy(), g["hm"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(preds["reg"].detach().numpy(), g["reg"], rtol=1e-4, atol=1e-4)
+    c = O.CONFIGS[cfg]
+    L = O.head_loss(preds, tgt, c["weight"], c["code_weights"])
+    assert abs(float(L["loss"]) - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
+    assert abs(float(L["hm_loss"]) - float(g["hm_loss"])) <= 1e-5 * abs(float(g["hm_loss"]))
+    np.testing.assert_allclose(L["loc_loss_elem"].detach().numpy(), g["loc_loss_elem"], rtol=1e-4, atol=1e-6)
+    assert float(L["num_positive"]) == float(g["num_positive"])
+    L["loss"].backward()
+    names = [str(n) for n in g["grad_names"]]
+    norms = dict(zip(names, g["grad_norms"]))
+    for k, ref in norms.items():
+        got = float(sd[k].grad.norm()) if sd[k].grad is not None else 0.0
+        assert abs(got - ref) <= 2e-3 * max(ref, 1e-6) + 1e-7, (k, got, ref)
+    for k in g.files:
+        if k.startswith("grad::"):
+            np.testing.assert_allclose(sd[k[6:]].grad.numpy(), g[k], rtol=2e-3, atol=2e-5 * float(np.abs(g[k]).max() + 1e-12) + 1e-9)
+    # decode: integer indices exact, coordinates to fp32 round-off
+    kps, idxs = O.decode(preds["hm"].detach(), preds["reg"].detach())
+    for n in range(batch):
+        assert len(kps[n]) == int(g["num_keypoints"][n])
+        ref = g["keypoints"][n][: len(kps[n])]
+        got = np.array(kps[n], dtype=np.float64)
+        np.testing.assert_array_equal(got[:, 0], ref[:, 0])
+        np.testing.assert_allclose(got[:, 1:], ref[:, 1:], rtol=1e-5, atol=1e-5)
+
+
+def test_state_dict_spec_counts():
+    # parameter counts measured on the reference (SURVEY.md §6 / BASELINE.md §2)
+    want = {"hr3d": 2002194, "hr3d_one_hm": 2217006, "hr3d_one_hm_doppler": 2216942,
+            "hr3d_one_hm_doppler_phase": 8297518}
+    for cfg, n in want.items():
+        got = sum(int(np.prod(s)) for _, s in O.state_dict_spec(cfg))
+        assert got == n, (cfg, got, n)
+
+
+def test_ingest_matches_numpy_semantics():
+    rs = np.random.RandomState(0)
+    raw = (rs.uniform(-2, 12, size=(4, 32, 128, 256))).astype(np.float16)
+    out = O.ingest_cube(raw, (0.0, 10.0))
+    assert out.shape == (4, 16, 64, 160) and out.dtype == np.float32
+    ref = (raw.astype(np.float32)[:, 13:29, 32:96, 17:177] - 0.0) / 10.0
+    ref[ref < 0] = 0
+    np.testing.assert_array_equal(out, ref)
+    one = O.ingest_cube(raw[0], (150000.0, 200000.0))
+    assert one.shape == (1, 16, 64, 160)
