@@ -1,0 +1,236 @@
+/* rtpose_b200.h — C ABI of librtpose_b200.so: the B200 (sm_100a) kernels behind the RT-Pose HRRadarPose
+ * forward/backward hot path.
+ *
+ * The reference (ipl-uw/RT-POSE) has no FFI of its own for this path: every op below is, in the reference, a
+ * PyTorch/ATen call made from Python (nn.Conv3d, nn.GroupNorm, F.interpolate, ...), plus one pybind11 module
+ * (det3d/ops/dcn).  Each entry point therefore cites the reference *call site* it replaces (paths relative to
+ * the reference root).  The host side that binds these symbols is rtpose_b200/lib.py (ctypes); the
+ * reference-side stub a maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers unless stated otherwise;
+ *   - `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream);
+ *   - no allocation inside: callers pass outputs and workspaces (`*_workspace_bytes` queries);
+ *   - return 0 on success, a negative value for an argument error, a positive cudaError_t otherwise;
+ *     rtp_last_error() returns a human-readable message for the last failure on the calling thread;
+ *   - re-entrant per stream; nothing here synchronises the device.
+ *
+ * Activation layout "P8" (rtp_p8): bf16, 8-channel blocked, in-plane zero-padded, y fastest:
+ *       T[n][c/8][z][x+1][y+1][c%8],  extents [N][C8][Z][X+2][Y+2][8]
+ *   The pad ring (x=-1, x=X, y=-1, y=Y) is zero and is never written by any kernel, so a 3x3x3 tap is a pure
+ *   linear shift inside a z-plane and zero padding comes for free; `ptr` addresses element (0,0,0,-1,-1,0).
+ *   Buffers must carry >= RTP_GUARD_BYTES of readable memory before and after (tiles read a small halo).
+ */
+#ifndef RTPOSE_B200_H_
+#define RTPOSE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RTP_GUARD_BYTES 8192
+#define RTP_MAX_TAPS 27
+
+typedef struct {
+  void* ptr;        /* bf16 element (n=0, chunk=0, z=0, xp=0, yp=0) */
+  int64_t n_stride; /* elements between samples */
+  int64_t c_stride; /* elements between 8-channel chunks (normally Z*(X+2)*(Y+2)*8) */
+  int32_t N, C8, Z, X, Y;
+} rtp_p8;
+
+const char* rtp_last_error(void);
+int rtp_version(void);
+/* 1 if a device with compute capability 10.x is current, else 0 (kernels are sm_100a-only). */
+int rtp_device_ok(void);
+
+/* ---- layout conversion at the det3d API boundary -------------------------------------------------------
+ * replaces: the NCDHW fp32 tensors that flow between reference modules (radar_pose_net.py:26-46). */
+int rtp_pack_ncdhw(const float* src, rtp_p8 dst, int32_t C, void* stream);                 /* fp32 [N,C,Z,Y,X] -> P8 */
+int rtp_unpack_ncdhw(rtp_p8 src, float* dst, int32_t C, int32_t accumulate, void* stream); /* P8 -> fp32 [N,C,Z,Y,X] */
+
+/* ---- radar-cube ingest -----------------------------------------------------------------------------------
+ * replaces: CRUW_POSE_Dataset.get_cube / get_cube_phase (det3d/datasets/cruw_pose/cruw_pose.py:167-194), the
+ * channel packing in AssignLabelPose(2).__call__ (det3d/datasets/pipelines/pose.py:163-172) and
+ * RadarFeatureNet.forward (det3d/models/readers/radar_encoder.py:15-17).
+ * raw: fp16 [N][D][RZ][RY][RX] (D Doppler bins or 2*D re/im planes, become channels); crops the ROI
+ * z[z0,z0+Z) y[y0,y0+Y) x[x0,x0+X), applies (v - norm_start) / norm_scale, clamps < 0 to 0 (skipped when
+ * normalize == 0), writes P8 bf16.  If dst_f32 != NULL also writes the fp32 [N,D,Z,Y,X] tensor the reference
+ * would hand to the model. */
+int rtp_ingest_pack(const void* raw_f16, int32_t N, int32_t D, int32_t RZ, int32_t RY, int32_t RX, int32_t z0,
+                    int32_t y0, int32_t x0, float norm_start, float norm_scale, int32_t normalize, rtp_p8 dst,
+                    float* dst_f32, void* stream);
+
+/* ---- weights ---------------------------------------------------------------------------------------------
+ * replaces: nothing in the reference (cuDNN consumes [Cout,Cin,kz,ky,kx] fp32 directly); repacks an fp32
+ * nn.Conv3d weight into the bf16 UMMA B-operand tiles.
+ *   mode 0 (forward): dst[tap][KP/8][NP][8],  K = Cin (padded to KP), N = Cout (padded to NP)
+ *   mode 1 (dgrad)  : dst[tap][KP/8][NP][8],  K = Cout (padded to KP), N = Cin (padded to NP)
+ * ci0/ci_n select an input-channel slice of w (used to split the 192->128 final conv per branch). */
+int rtp_weight_pack(const float* w, void* dst_bf16, int32_t Cout, int32_t Cin, int32_t ntaps, int32_t ci0,
+                    int32_t ci_n, int32_t KP, int32_t NP, int32_t mode, void* stream);
+
+/* ---- implicit-GEMM conv3d on tcgen05 tensor cores ---------------------------------------------------------
+ * replaces: nn.Conv3d forward and the cuDNN dgrad of it — call sites hr_util/common.py:40,114;
+ * hr_util/hr3d.py:84,148,169,185,298,324; hrnet3d.py:20; pose_heads/center_head.py:86,91,205 — with the
+ * bias / ReLU / residual-add that follow them (common.py:146-147, center_head.py:88) fused in the epilogue.
+ *
+ * Rows (GEMM M) enumerate a grid (n, rz, rx, ry); for tap t the A row is the input vector at
+ * (rz*IS+tz[t], rx*IS+tx[t], ry*IS+ty[t]) (zero outside), the B tile is packed-weight tap wt[t]; the result
+ * goes to output voxel (rz*OS+oz0, rx*OS+ox0, ry*OS+oy0).  Forward stride-s conv: IS=s, OS=1; dgrad of a
+ * stride-2 conv: IS=1, OS=2, one launch per output parity class. */
+typedef struct {
+  rtp_p8 in, out;
+  rtp_p8 res;        /* optional residual, geometry of `out` (ptr NULL = none) */
+  rtp_p8 mask;       /* optional ReLU mask tensor, geometry of `out`: result *= (mask > 0) */
+  const void* w;     /* packed weights (rtp_weight_pack) */
+  const float* bias; /* [NP] fp32 or NULL */
+  int32_t Cin;       /* K per tap, multiple of 16 (chunks beyond in.C8 read as zero) */
+  int32_t NP;        /* GEMM N, multiple of 16, <= 256 */
+  int32_t out_c8;    /* 8-channel chunks of the result to store (<= NP/8) */
+  int32_t ntaps;
+  int8_t tz[RTP_MAX_TAPS], tx[RTP_MAX_TAPS], ty[RTP_MAX_TAPS], wt[RTP_MAX_TAPS];
+  int32_t RZ, RX, RY;
+  int32_t IS, OS, oz0, ox0, oy0;
+  int32_t relu;       /* apply ReLU last */
+  int32_t accumulate; /* out += result (read-modify-write) */
+} rtp_conv_desc;
+int rtp_conv(const rtp_conv_desc* d, void* stream);
+
+/* Plane-streaming 3x3x3 stride-1 conv (the dominant shape): the z-taps are stacked into GEMM N
+ * (N = 3*NPo), accumulators for all output planes stay resident in TMEM, input planes are streamed once
+ * through shared memory by 1-D bulk async copies; same epilogue options as rtp_conv.
+ * w: packed by rtp_weight_pack_k3s1.  Requires Z*NPo <= 512, Cin % 16 == 0, NPo in {16,32}. */
+int rtp_weight_pack_k3s1(const float* w, void* dst_bf16, int32_t Cout, int32_t Cin, int32_t KP, int32_t NPo,
+                         int32_t transpose_flip, void* stream);
+typedef struct {
+  rtp_p8 in, out, res, mask;
+  const void* w;
+  const float* bias;
+  int32_t Cin, NPo, out_c8;
+  int32_t relu, accumulate;
+  float* gn_sums; /* optional [N][out_c8*8][2] fp32: per-(sample,channel) sum / sum-of-squares of the stored
+                     bf16 result, accumulated with atomics (feeds the next GroupNorm); NULL = off */
+} rtp_conv_k3s1_desc;
+int rtp_conv_k3s1(const rtp_conv_k3s1_desc* d, void* stream);
+int64_t rtp_conv_k3s1_smem_bytes(int32_t Cin, int32_t NPo, int32_t Y);
+
+/* ---- weight gradient ---------------------------------------------------------------------------------------
+ * replaces: cuDNN wgrad inside autograd's convolution_backward for the same call sites.
+ * dW[tap][ci][co] = sum_rows X[row+tap][ci] * dY[row][co]; rows and taps as in rtp_conv_desc (X plays `in`,
+ * dY is indexed by the row grid directly with OS/oz0.. = 1/0).  Split-K over `nsplit` CTAs into a fp32
+ * workspace, then a deterministic reduction writes dW in the reference's [Cout][Cin][taps] fp32 layout. */
+typedef struct {
+  rtp_p8 x, dy;
+  int32_t Cin;   /* multiple of 8 */
+  int32_t NP;    /* dY channels padded to a multiple of 16 (chunks beyond dy.C8 read as zero) */
+  int32_t ntaps;
+  int8_t tz[RTP_MAX_TAPS], tx[RTP_MAX_TAPS], ty[RTP_MAX_TAPS];
+  int32_t RZ, RX, RY, IS;
+  int32_t nsplit;
+  float* workspace;
+} rtp_wgrad_desc;
+int64_t rtp_wgrad_workspace_bytes(int32_t Cin, int32_t NP, int32_t ntaps, int32_t nsplit);
+int rtp_wgrad(const rtp_wgrad_desc* d, void* stream);
+/* dW[co][ci0+ci][tap] (fp32, [co_n][Cin_total][ntaps]) = or += sum over splits of the partial for dY channel
+ * n0+co, input channel ci (co < co_n, ci < ci_n).  Cin8/NP/ntaps/nsplit as given to rtp_wgrad. */
+int rtp_wgrad_reduce(const float* workspace, int32_t nsplit, int32_t Cin8, int32_t NP, int32_t ntaps, float* dW,
+                     int32_t Cin_total, int32_t co_n, int32_t n0, int32_t ci0, int32_t ci_n, int32_t accumulate,
+                     void* stream);
+
+/* ---- GroupNorm ---------------------------------------------------------------------------------------------
+ * replaces: nn.GroupNorm(8, C) forward/backward — hr_util/common.py:57; hr_util/hr3d.py:83,147,168,184,297,323;
+ * center_head.py:85,204.  Statistics are fp32 per (sample, group); eps = 1e-5, biased variance.
+ *   sums : [N][C][2] fp32 per-channel (sum, sum of squares) over real voxels;
+ *   stats: [N][G][2] fp32 (mean, rstd). */
+/* reductions are two-level with a fixed slab count (deterministic); workspace >= rtp_gn_workspace_bytes(N, C8) */
+int64_t rtp_gn_workspace_bytes(int32_t N, int32_t C8);
+int rtp_gn_sums(rtp_p8 x, int32_t C, float* sums, float* workspace, void* stream);
+int rtp_gn_finalize(const float* sums, int32_t N, int32_t C, int32_t G, int64_t voxels, float eps, float* stats,
+                    void* stream);
+/* y = bf16((x - mean) * rstd * gamma + beta), pads stay zero */
+int rtp_gn_apply(rtp_p8 x, int32_t C, int32_t G, const float* stats, const float* gamma, const float* beta, rtp_p8 y,
+                 void* stream);
+/* backward, two steps.  red[N][C][2] = per-channel (sum dy, sum dy*xhat) */
+int rtp_gn_bwd_reduce(rtp_p8 x, rtp_p8 dy, int32_t C, int32_t G, const float* stats, float* red, float* workspace,
+                      void* stream);
+/* dgamma/dbeta (+)= sum_n red; dx (=|+=) rstd*(gamma*dy - (s1 + xhat*s2)/m), optionally times (x > 0) when x is
+ * itself a ReLU output (the gradient of every tensor is kept w.r.t. its pre-ReLU value). */
+int rtp_gn_bwd_apply(rtp_p8 x, rtp_p8 dy, int32_t C, int32_t G, const float* stats, const float* red,
+                     const float* gamma, float* dgamma, float* dbeta, int32_t accumulate_params, rtp_p8 dx,
+                     int32_t accumulate_dx, int32_t relu_mask, void* stream);
+
+/* ---- branch exchange ---------------------------------------------------------------------------------------
+ * replaces: the fuse sum of HighResolutionModule.forward (hr_util/hr3d.py:213-227) and the upsample+cat of
+ * HRNet3D.forward (hrnet3d.py:37-42): out = [relu]( sum_i same[i] + sum_j trilinear_up(low[j]) + bias ),
+ * F.interpolate(mode="trilinear", align_corners=True) semantics; fp32 accumulation, one bf16 store. */
+typedef struct {
+  rtp_p8 out;
+  int32_t C;
+  int32_t n_same, n_low;
+  rtp_p8 same[4];
+  rtp_p8 low[3];
+  const float* bias; /* [C] or NULL */
+  int32_t relu;
+} rtp_fuse_desc;
+int rtp_fuse_sum(const rtp_fuse_desc* d, void* stream);
+/* dlow (=|+=) transpose-of-trilinear-upsample applied to dout (gather form, deterministic) */
+int rtp_upsample_bwd(rtp_p8 dout, rtp_p8 dlow, int32_t C, int32_t accumulate, void* stream);
+/* dst (=|+=) src [* (mask > 0)]   — gradient pass-through of the fuse sum / residual add */
+int rtp_grad_add(rtp_p8 src, rtp_p8 mask, rtp_p8 dst, int32_t C, int32_t accumulate, void* stream);
+/* out[c] = sum over (n, voxels) of x[n][c] (fp32) — bias gradients */
+int rtp_channel_sum(rtp_p8 x, int32_t C, float* out, int32_t accumulate, float* workspace, void* stream);
+
+/* ---- 1 -> C stem (conv1 of layer1 when Cin != Cout; hr_util/common.py:113-116,140) ------------------------
+ * y[c] = w[c] * x + b[c] for single-channel input (x is channel 0 of a P8 tensor). */
+int rtp_stem_fwd(rtp_p8 x, const float* w, const float* b, int32_t C, rtp_p8 y, void* stream);
+int rtp_stem_bwd(rtp_p8 x, rtp_p8 dy, int32_t C, float* dw, float* db, int32_t accumulate, float* workspace,
+                 void* stream);
+
+/* ---- CenterHead loss -----------------------------------------------------------------------------------------
+ * replaces: CenterHead.loss (center_head.py:244-270) -> FastFocalLoss.forward (losses/centernet_loss.py:34-54),
+ * RegLoss.forward (:17-24), _transpose_and_gather_feat (core/utils/center_utils.py:113-117).
+ * hm, reg: raw head outputs (P8).  tgt_hm fp32 [N][ncls][Z][Y][X]; ind int64 [N][M] (flat z*Y*X+y*X+x);
+ * mask uint8 [N][M]; cat int64 [N][M]; anno fp32 [N][M][R].
+ * out (fp32, device): [0]=loss [1]=hm_loss [2]=loc_loss [3]=num_pos [4..4+R)=loc_loss_elem.
+ * d_hm / d_reg (P8, may be NULL): gradients of `loss * grad_scale` w.r.t. the raw outputs. */
+int64_t rtp_head_loss_workspace_bytes(int32_t N, int32_t ncls, int32_t Z, int32_t Y, int32_t X);
+int rtp_head_loss(rtp_p8 hm, rtp_p8 reg, int32_t ncls, int32_t R, const float* tgt_hm, const int64_t* ind,
+                  const uint8_t* mask, const int64_t* cat, const float* anno, int32_t M, float weight,
+                  const float* code_weights, float grad_scale, float* out, rtp_p8 d_hm, rtp_p8 d_reg,
+                  void* workspace, void* stream);
+
+/* ---- keypoint decode -------------------------------------------------------------------------------------------
+ * replaces: CenterHead.predict + post_processing (center_head.py:272-360): per (sample, class) arg-max of
+ * sigmoid(hm) over Z*Y*X (lowest reference flat index wins ties), gather of the regression row, metric
+ * coordinates (idx + reg) * voxel + range.
+ * out_index int32 [N][ncls]; out_score fp32 [N][ncls]; out_xyz fp32 [N][ncls][R] (R = 3 or 45).
+ * voxel_xyz / range_xyz are HOST pointers to 3 floats each (configuration, read at call time). */
+int rtp_decode(rtp_p8 hm, rtp_p8 reg, int32_t ncls, int32_t R, const float* voxel_xyz, const float* range_xyz,
+               int32_t* out_index, float* out_score, float* out_xyz, void* stream);
+
+/* ---- deformable convolution v1 (2-D) ------------------------------------------------------------------------
+ * replaces: deform_conv_forward_cuda / deform_conv_backward_input_cuda / deform_conv_backward_parameters_cuda
+ * (det3d/ops/dcn/src/deform_conv_cuda.cpp:152-488; kernels deform_conv_cuda_kernel.cu:190-465; bound at
+ * deform_conv_cuda.cpp:687-701 and called from det3d/ops/dcn/deform_conv.py:52,77,87).
+ * fp32 NCHW tensors as in the reference op; offset channel order [dg][kh*kw][dy,dx]; groups = 1. */
+int rtp_dcn_fwd(const float* x, const float* offset, const float* w, float* y, int32_t N, int32_t C, int32_t H,
+                int32_t W, int32_t Cout, int32_t kh, int32_t kw, int32_t stride, int32_t pad, int32_t dil,
+                int32_t dg, void* stream);
+int rtp_dcn_bwd_input(const float* x, const float* offset, const float* w, const float* dy, float* dx, float* doffset,
+                      int32_t N, int32_t C, int32_t H, int32_t W, int32_t Cout, int32_t kh, int32_t kw,
+                      int32_t stride, int32_t pad, int32_t dil, int32_t dg, void* stream);
+int rtp_dcn_bwd_weight(const float* x, const float* offset, const float* dy, float* dw, int32_t N, int32_t C,
+                       int32_t H, int32_t W, int32_t Cout, int32_t kh, int32_t kw, int32_t stride, int32_t pad,
+                       int32_t dil, int32_t dg, float scale, void* stream);
+
+/* ---- flat-buffer helpers for the data-parallel step ----------------------------------------------------------
+ * replaces: _allreduce_coalesced's flatten / div_ / copy-back (det3d/core/utils/dist_utils.py:8-28); the
+ * collective itself is ncclAllReduce issued by torch.distributed on the same flat buffer. */
+int rtp_scale_f32(float* buf, int64_t n, float scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RTPOSE_B200_H_ */

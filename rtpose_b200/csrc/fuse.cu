@@ -1,0 +1,227 @@
+// fuse.cu — multi-resolution branch exchange: fused (sum of same-resolution terms + trilinear align_corners
+// upsample of low-resolution terms + bias, ReLU) in one pass, its transpose for the backward pass, and the
+// gradient pass-through of the sum.  HBM-bound; fp32 accumulation, one bf16 store per output vector.
+//
+// Interpolation follows ATen's upsample_trilinear3d (align_corners=True): scale = float(in-1)/float(out-1)
+// (0 when out == 1), src = scale * dst, i0 = int(src), i1 = i0 + (i0 < in-1), w1 = src - i0, w0 = 1 - w1.
+#include "common.cuh"
+
+namespace {
+
+struct Axis {
+  int i0, i1;
+  float w0, w1;
+};
+__device__ __forceinline__ float ac_scale(int in, int out) { return out > 1 ? (float)(in - 1) / (float)(out - 1) : 0.f; }
+__device__ __forceinline__ Axis ac_axis(int d, int in, float scale) {
+  Axis a;
+  const float src = scale * (float)d;
+  a.i0 = (int)src;
+  a.i1 = a.i0 + (a.i0 < in - 1 ? 1 : 0);
+  a.w1 = src - (float)a.i0;
+  a.w0 = 1.f - a.w1;
+  return a;
+}
+
+struct FuseK {
+  P8 out;
+  int C, n_same, n_low, relu;
+  P8 same[4];
+  P8 low[3];
+  const float* bias;
+};
+
+__global__ void __launch_bounds__(256) fuse_sum_kernel(const __grid_constant__ FuseK p) {
+  const int c8 = blockIdx.y, n = blockIdx.z;
+  const P8& o = p.out;
+  const int64_t V = (int64_t)o.Z * o.X * o.Y;
+  float bias[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) bias[i] = (p.bias && c8 * 8 + i < p.C) ? p.bias[c8 * 8 + i] : 0.f;
+  for (int64_t v = blockIdx.x * 256ll + threadIdx.x; v < V; v += (int64_t)gridDim.x * 256) {
+    int64_t q = v;
+    const int y = (int)(q % o.Y); q /= o.Y;
+    const int x = (int)(q % o.X);
+    const int z = (int)(q / o.X);
+    const int64_t off = o.voxel(z, x, y);
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    for (int s = 0; s < p.n_same; ++s) {
+      float f[8];
+      unpack8(ldg16(p.same[s].ptr + n * p.same[s].n_stride + c8 * p.same[s].c_stride + off), f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += f[i];
+    }
+    for (int j = 0; j < p.n_low; ++j) {
+      const P8& l = p.low[j];
+      const Axis az = ac_axis(z, l.Z, ac_scale(l.Z, o.Z));
+      const Axis ax = ac_axis(x, l.X, ac_scale(l.X, o.X));
+      const Axis ay = ac_axis(y, l.Y, ac_scale(l.Y, o.Y));
+      const bf16* lb = l.ptr + n * l.n_stride + c8 * l.c_stride;
+      float up[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) up[i] = 0.f;
+#pragma unroll
+      for (int corner = 0; corner < 8; ++corner) {
+        const int zz = (corner & 4) ? az.i1 : az.i0;
+        const int xx = (corner & 2) ? ax.i1 : ax.i0;
+        const int yy = (corner & 1) ? ay.i1 : ay.i0;
+        const float w = ((corner & 4) ? az.w1 : az.w0) * ((corner & 2) ? ax.w1 : ax.w0) * ((corner & 1) ? ay.w1 : ay.w0);
+        float f[8];
+        unpack8(ldg16(lb + l.voxel(zz, xx, yy)), f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) up[i] = fmaf(w, f[i], up[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += up[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      acc[i] += bias[i];
+      if (p.relu) acc[i] = fmaxf(acc[i], 0.f);
+    }
+    stg16(o.ptr + n * o.n_stride + c8 * o.c_stride + off, pack8(acc));
+  }
+}
+
+// candidate dst range [lo, hi] along one axis whose interpolation touches source index l
+__device__ __forceinline__ void dst_range(int l, int in, int out, float scale, int& lo, int& hi) {
+  if (scale <= 0.f) { lo = 0; hi = out - 1; return; }
+  lo = (int)floorf((float)(l - 1) / scale) - 1;
+  hi = (int)ceilf((float)(l + 1) / scale) + 1;
+  lo = lo < 0 ? 0 : lo;
+  hi = hi > out - 1 ? out - 1 : hi;
+}
+__device__ __forceinline__ float axis_weight(int d, int l, int in, float scale) {
+  const Axis a = ac_axis(d, in, scale);
+  return (a.i0 == l ? a.w0 : 0.f) + (a.i1 == l ? a.w1 : 0.f);
+}
+
+// dlow[l] (=|+=) sum_d W[d -> l] * dout[d]   (gather form of the upsample transpose; deterministic)
+// one warp per low-res voxel-vector; lanes stride over the high-res footprint.
+__global__ void __launch_bounds__(256) upsample_bwd_kernel(P8 dout, P8 dlow, int C8, int accumulate) {
+  const int lane = threadIdx.x & 31;
+  const int64_t VL = (int64_t)dlow.Z * dlow.X * dlow.Y;
+  const int64_t total = VL * C8 * dlow.N;
+  const float sz = ac_scale(dlow.Z, dout.Z), sx = ac_scale(dlow.X, dout.X), sy = ac_scale(dlow.Y, dout.Y);
+  for (int64_t w = (blockIdx.x * 256ll + threadIdx.x) >> 5; w < total; w += ((int64_t)gridDim.x * 256) >> 5) {
+    int64_t q = w;
+    const int yl = (int)(q % dlow.Y); q /= dlow.Y;
+    const int xl = (int)(q % dlow.X); q /= dlow.X;
+    const int zl = (int)(q % dlow.Z); q /= dlow.Z;
+    const int c8 = (int)(q % C8);
+    const int n = (int)(q / C8);
+    int z0, z1, x0, x1, y0, y1;
+    dst_range(zl, dlow.Z, dout.Z, sz, z0, z1);
+    dst_range(xl, dlow.X, dout.X, sx, x0, x1);
+    dst_range(yl, dlow.Y, dout.Y, sy, y0, y1);
+    const int ny = y1 - y0 + 1, nx = x1 - x0 + 1, nz = z1 - z0 + 1;
+    const bf16* db = dout.ptr + n * dout.n_stride + c8 * dout.c_stride;
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    for (int t = lane; t < ny * nx * nz; t += 32) {
+      const int y = y0 + t % ny, x = x0 + (t / ny) % nx, z = z0 + t / (ny * nx);
+      const float wgt = axis_weight(z, zl, dlow.Z, sz) * axis_weight(x, xl, dlow.X, sx) * axis_weight(y, yl, dlow.Y, sy);
+      if (wgt != 0.f) {
+        float f[8];
+        unpack8(ldg16(db + dout.voxel(z, x, y)), f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = fmaf(wgt, f[i], acc[i]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = warp_sum(acc[i]);
+    if (lane == 0) {
+      bf16* dst = dlow.ptr + n * dlow.n_stride + c8 * dlow.c_stride + dlow.voxel(zl, xl, yl);
+      if (accumulate) {
+        float g[8];
+        unpack8(*reinterpret_cast<const uint4*>(dst), g);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] += g[i];
+      }
+      stg16(dst, pack8(acc));
+    }
+  }
+}
+
+// dst (=|+=) src [* (mask > 0)]
+__global__ void __launch_bounds__(256) grad_add_kernel(P8 src, P8 mask, int has_mask, P8 dst, int accumulate) {
+  const int c8 = blockIdx.y, n = blockIdx.z;
+  const int64_t V = (int64_t)dst.Z * dst.X * dst.Y;
+  for (int64_t v = blockIdx.x * 256ll + threadIdx.x; v < V; v += (int64_t)gridDim.x * 256) {
+    int64_t q = v;
+    const int y = (int)(q % dst.Y); q /= dst.Y;
+    const int x = (int)(q % dst.X);
+    const int z = (int)(q / dst.X);
+    const int64_t off = dst.voxel(z, x, y);
+    float f[8];
+    unpack8(ldg16(src.ptr + n * src.n_stride + c8 * src.c_stride + off), f);
+    if (has_mask) {
+      float m[8];
+      unpack8(ldg16(mask.ptr + n * mask.n_stride + c8 * mask.c_stride + off), m);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] = m[i] > 0.f ? f[i] : 0.f;
+    }
+    bf16* d = dst.ptr + n * dst.n_stride + c8 * dst.c_stride + off;
+    if (accumulate) {
+      float g[8];
+      unpack8(*reinterpret_cast<const uint4*>(d), g);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] += g[i];
+    }
+    stg16(d, pack8(f));
+  }
+}
+
+int ew_blocks(int64_t V) {
+  int64_t b = (V + 255) / 256;
+  return (int)(b > 592 ? 592 : (b < 1 ? 1 : b));
+}
+bool same_geom(const rtp_p8& a, const rtp_p8& b) { return a.N == b.N && a.Z == b.Z && a.X == b.X && a.Y == b.Y; }
+
+}  // namespace
+
+extern "C" int rtp_fuse_sum(const rtp_fuse_desc* d, void* stream) {
+  RTP_CHECK_ARG(d && d->out.ptr, "rtp_fuse_sum: null argument");
+  RTP_CHECK_ARG(d->n_same >= 0 && d->n_same <= 4 && d->n_low >= 0 && d->n_low <= 3 && d->n_same + d->n_low >= 1,
+                "rtp_fuse_sum: bad term counts");
+  const int C8 = ceil_div(d->C, 8);
+  RTP_CHECK_ARG(d->C > 0 && C8 <= d->out.C8, "rtp_fuse_sum: bad C");
+  FuseK k;
+  k.out = P8(d->out); k.C = d->C; k.n_same = d->n_same; k.n_low = d->n_low; k.relu = d->relu; k.bias = d->bias;
+  for (int i = 0; i < d->n_same; ++i) {
+    RTP_CHECK_ARG(d->same[i].ptr && same_geom(d->same[i], d->out) && d->same[i].C8 >= C8, "rtp_fuse_sum: same[%d] geometry mismatch", i);
+    k.same[i] = P8(d->same[i]);
+  }
+  for (int i = 0; i < d->n_low; ++i) {
+    RTP_CHECK_ARG(d->low[i].ptr && d->low[i].N == d->out.N && d->low[i].C8 >= C8, "rtp_fuse_sum: low[%d] mismatch", i);
+    k.low[i] = P8(d->low[i]);
+  }
+  const int64_t V = (int64_t)d->out.Z * d->out.X * d->out.Y;
+  fuse_sum_kernel<<<dim3(ew_blocks(V), C8, d->out.N), 256, 0, (cudaStream_t)stream>>>(k);
+  RTP_LAUNCH_CHECK();
+}
+
+extern "C" int rtp_upsample_bwd(rtp_p8 dout, rtp_p8 dlow, int32_t C, int32_t accumulate, void* stream) {
+  RTP_CHECK_ARG(dout.ptr && dlow.ptr && dout.N == dlow.N, "rtp_upsample_bwd: bad tensors");
+  const int C8 = ceil_div(C, 8);
+  RTP_CHECK_ARG(C > 0 && C8 <= dout.C8 && C8 <= dlow.C8, "rtp_upsample_bwd: bad C");
+  const int64_t warps = (int64_t)dlow.Z * dlow.X * dlow.Y * C8 * dlow.N;
+  int64_t blocks = (warps + 7) / 8;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  upsample_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(P8(dout), P8(dlow), C8, accumulate);
+  RTP_LAUNCH_CHECK();
+}
+
+extern "C" int rtp_grad_add(rtp_p8 src, rtp_p8 mask, rtp_p8 dst, int32_t C, int32_t accumulate, void* stream) {
+  RTP_CHECK_ARG(src.ptr && dst.ptr && same_geom(src, dst), "rtp_grad_add: geometry mismatch");
+  const int C8 = ceil_div(C, 8);
+  RTP_CHECK_ARG(C > 0 && C8 <= src.C8 && C8 <= dst.C8, "rtp_grad_add: bad C");
+  if (mask.ptr) RTP_CHECK_ARG(same_geom(mask, dst) && C8 <= mask.C8, "rtp_grad_add: mask geometry mismatch");
+  const int64_t V = (int64_t)dst.Z * dst.X * dst.Y;
+  grad_add_kernel<<<dim3(ew_blocks(V), C8, dst.N), 256, 0, (cudaStream_t)stream>>>(P8(src), P8(mask), mask.ptr != nullptr,
+                                                                                    P8(dst), accumulate);
+  RTP_LAUNCH_CHECK();
+}

@@ -1,0 +1,242 @@
+// layout.cu — error plumbing, NCDHW<->P8 conversion at the det3d API boundary, radar-cube ingest,
+// weight repacking into UMMA B-operand tiles.
+#include <cstdarg>
+#include <cstring>
+#include <cuda_fp16.h>
+#include "common.cuh"
+
+// ---------------------------------------------------------------------------------------------- errors
+static thread_local char g_err[512] = "";
+void rtp_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+extern "C" const char* rtp_last_error(void) { return g_err; }
+extern "C" int rtp_version(void) { return 100; }
+extern "C" int rtp_device_ok(void) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  cudaDeviceProp p;
+  if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) return 0;
+  return p.major == 10 ? 1 : 0;
+}
+
+// ---------------------------------------------------------------------------------------------- pack / unpack
+// One block: (n, chunk, z, 32-wide x tile, 32-wide y tile); 8 channels x 32 y x 32 x staged in smem so that
+// both the NCDHW side (x fastest) and the P8 side (y fastest, 16 B per voxel) are coalesced.
+template <bool kPack>
+__global__ void __launch_bounds__(256) ncdhw_p8_kernel(float* __restrict__ nc, P8 t, int C, int accumulate) {
+  __shared__ float tile[8][32][33];
+  const int xt = blockIdx.x * 32, yt = blockIdx.y * 32;
+  int b = blockIdx.z;
+  const int z = b % t.Z;
+  b /= t.Z;
+  const int ch = b % t.C8, n = b / t.C8;
+  const int tid = threadIdx.x;
+  const int64_t vol = (int64_t)t.Z * t.Y * t.X;
+  bf16* pbase = t.ptr + n * t.n_stride + ch * t.c_stride;
+  if (kPack) {
+    for (int i = tid; i < 8 * 32 * 32; i += 256) {
+      const int xx = i & 31, yy = (i >> 5) & 31, c = i >> 10;
+      const int x = xt + xx, y = yt + yy, cg = ch * 8 + c;
+      float v = 0.f;
+      if (x < t.X && y < t.Y && cg < C) v = nc[((int64_t)n * C + cg) * vol + ((int64_t)z * t.Y + y) * t.X + x];
+      tile[c][yy][xx] = v;
+    }
+    __syncthreads();
+    for (int i = tid; i < 32 * 32; i += 256) {
+      const int yy = i & 31, xx = i >> 5;
+      const int x = xt + xx, y = yt + yy;
+      if (x < t.X && y < t.Y) {
+        float f[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) f[c] = tile[c][yy][xx];
+        stg16(pbase + t.voxel(z, x, y), pack8(f));
+      }
+    }
+  } else {
+    for (int i = tid; i < 32 * 32; i += 256) {
+      const int yy = i & 31, xx = i >> 5;
+      const int x = xt + xx, y = yt + yy;
+      float f[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      if (x < t.X && y < t.Y) unpack8(ldg16(pbase + t.voxel(z, x, y)), f);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) tile[c][yy][xx] = f[c];
+    }
+    __syncthreads();
+    for (int i = tid; i < 8 * 32 * 32; i += 256) {
+      const int xx = i & 31, yy = (i >> 5) & 31, c = i >> 10;
+      const int x = xt + xx, y = yt + yy, cg = ch * 8 + c;
+      if (x < t.X && y < t.Y && cg < C) {
+        float* d = nc + ((int64_t)n * C + cg) * vol + ((int64_t)z * t.Y + y) * t.X + x;
+        *d = accumulate ? (*d + tile[c][yy][xx]) : tile[c][yy][xx];
+      }
+    }
+  }
+}
+
+static int check_p8(const rtp_p8& t, const char* name) {
+  RTP_CHECK_ARG(t.ptr != nullptr, "%s: null pointer", name);
+  RTP_CHECK_ARG(t.N > 0 && t.C8 > 0 && t.Z > 0 && t.X > 0 && t.Y > 0, "%s: bad extents", name);
+  RTP_CHECK_ARG(((uintptr_t)t.ptr & 15) == 0 && (t.n_stride % 8) == 0 && (t.c_stride % 8) == 0,
+                "%s: pointer/strides must be 16-byte aligned", name);
+  return 0;
+}
+
+extern "C" int rtp_pack_ncdhw(const float* src, rtp_p8 dst, int32_t C, void* stream) {
+  if (check_p8(dst, "rtp_pack_ncdhw dst")) return -1;
+  RTP_CHECK_ARG(src && C > 0 && C <= dst.C8 * 8, "rtp_pack_ncdhw: bad C=%d for C8=%d", C, dst.C8);
+  dim3 grid(ceil_div(dst.X, 32), ceil_div(dst.Y, 32), dst.N * dst.C8 * dst.Z);
+  ncdhw_p8_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(const_cast<float*>(src), P8(dst), C, 0);
+  RTP_LAUNCH_CHECK();
+}
+extern "C" int rtp_unpack_ncdhw(rtp_p8 src, float* dst, int32_t C, int32_t accumulate, void* stream) {
+  if (check_p8(src, "rtp_unpack_ncdhw src")) return -1;
+  RTP_CHECK_ARG(dst && C > 0 && C <= src.C8 * 8, "rtp_unpack_ncdhw: bad C=%d for C8=%d", C, src.C8);
+  dim3 grid(ceil_div(src.X, 32), ceil_div(src.Y, 32), src.N * ceil_div(C, 8) * src.Z);
+  P8 t(src);
+  t.C8 = ceil_div(C, 8);
+  ncdhw_p8_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(dst, t, C, accumulate);
+  RTP_LAUNCH_CHECK();
+}
+
+// ---------------------------------------------------------------------------------------------- ingest
+// raw fp16 [N][D][RZ][RY][RX] -> ROI crop -> (v - a) / s -> clamp -> P8 bf16 [N][D/8][Z][X+2][Y+2][8].
+// One block per (n, 8-channel chunk, z, 32x32 (x,y) tile): 8 Doppler planes are read with x fastest
+// (64-byte rows, coalesced) and written as 16-byte channel vectors with y fastest.
+__global__ void __launch_bounds__(256) ingest_kernel(const __half* __restrict__ raw, int D, int RZ, int RY, int RX,
+                                                     int z0, int y0, int x0, float a, float scale, int normalize,
+                                                     P8 t, float* __restrict__ f32) {
+  __shared__ float tile[8][32][33];
+  const int xt = blockIdx.x * 32, yt = blockIdx.y * 32;
+  int b = blockIdx.z;
+  const int z = b % t.Z;
+  b /= t.Z;
+  const int ch = b % t.C8, n = b / t.C8;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 8 * 32 * 32; i += 256) {
+    const int xx = i & 31, yy = (i >> 5) & 31, c = i >> 10;
+    const int x = xt + xx, y = yt + yy, d = ch * 8 + c;
+    float v = 0.f;
+    if (x < t.X && y < t.Y && d < D) {
+      v = __half2float(raw[((((int64_t)n * D + d) * RZ + (z0 + z)) * RY + (y0 + y)) * RX + (x0 + x)]);
+      if (normalize) {
+        // reference arithmetic: (float32(v) - start) / scale ; then clamp (cruw_pose.py:182-183)
+        v = (v - a) / scale;  // IEEE division: bit-identical to numpy's float32 arithmetic
+        v = v < 0.f ? 0.f : v;
+      }
+      if (f32) f32[((((int64_t)n * D + d) * t.Z + z) * t.Y + y) * t.X + x] = v;
+    }
+    tile[c][yy][xx] = v;
+  }
+  __syncthreads();
+  bf16* pbase = t.ptr + n * t.n_stride + ch * t.c_stride;
+  for (int i = tid; i < 32 * 32; i += 256) {
+    const int yy = i & 31, xx = i >> 5;
+    const int x = xt + xx, y = yt + yy;
+    if (x < t.X && y < t.Y) {
+      float f[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) f[c] = tile[c][yy][xx];
+      stg16(pbase + t.voxel(z, x, y), pack8(f));
+    }
+  }
+}
+
+extern "C" int rtp_ingest_pack(const void* raw_f16, int32_t N, int32_t D, int32_t RZ, int32_t RY, int32_t RX,
+                               int32_t z0, int32_t y0, int32_t x0, float norm_start, float norm_scale,
+                               int32_t normalize, rtp_p8 dst, float* dst_f32, void* stream) {
+  if (check_p8(dst, "rtp_ingest_pack dst")) return -1;
+  RTP_CHECK_ARG(raw_f16 && N == dst.N && D <= dst.C8 * 8, "rtp_ingest_pack: N/D mismatch");
+  RTP_CHECK_ARG(z0 >= 0 && y0 >= 0 && x0 >= 0 && z0 + dst.Z <= RZ && y0 + dst.Y <= RY && x0 + dst.X <= RX,
+                "rtp_ingest_pack: ROI outside the raw cube");
+  RTP_CHECK_ARG(!normalize || norm_scale != 0.f, "rtp_ingest_pack: zero normalisation scale");
+  dim3 grid(ceil_div(dst.X, 32), ceil_div(dst.Y, 32), dst.N * dst.C8 * dst.Z);
+  ingest_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)raw_f16, D, RZ, RY, RX, z0, y0, x0, norm_start,
+                                                        normalize ? norm_scale : 1.f, normalize, P8(dst),
+                                                        dst_f32);
+  RTP_LAUNCH_CHECK();
+}
+
+// ---------------------------------------------------------------------------------------------- weights
+// w fp32 [Cout][Cin][ntaps] -> dst bf16 [tap][KP/8][NP][8]
+//   mode 0: k = ci - ci0 (ci in [ci0, ci0+ci_n)), n = co ;  mode 1: k = co, n = ci - ci0
+__global__ void weight_pack_kernel(const float* __restrict__ w, bf16* __restrict__ dst, int Cout, int Cin, int ntaps,
+                                   int ci0, int ci_n, int KP, int NP, int mode) {
+  const int64_t total = (int64_t)ntaps * KP * NP;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int k8 = i & 7;
+    int64_t r = i >> 3;
+    const int n = r % NP;
+    r /= NP;
+    const int kc = r % (KP / 8);
+    const int tap = r / (KP / 8);
+    const int k = kc * 8 + k8;
+    int co, ci;
+    if (mode == 0) { ci = k; co = n; } else { co = k; ci = n; }
+    float v = 0.f;
+    if (co < Cout && ci < ci_n) v = w[((int64_t)co * Cin + (ci0 + ci)) * ntaps + tap];
+    dst[i] = __float2bfloat16(v);
+  }
+}
+extern "C" int rtp_weight_pack(const float* w, void* dst_bf16, int32_t Cout, int32_t Cin, int32_t ntaps, int32_t ci0,
+                               int32_t ci_n, int32_t KP, int32_t NP, int32_t mode, void* stream) {
+  RTP_CHECK_ARG(w && dst_bf16, "rtp_weight_pack: null pointer");
+  RTP_CHECK_ARG(KP % 16 == 0 && NP % 16 == 0 && NP <= 256, "rtp_weight_pack: KP/NP must be multiples of 16");
+  RTP_CHECK_ARG(ci0 >= 0 && ci_n > 0 && ci0 + ci_n <= Cin, "rtp_weight_pack: bad input-channel slice");
+  RTP_CHECK_ARG(mode == 0 ? (ci_n <= KP && Cout <= NP) : (Cout <= KP && ci_n <= NP), "rtp_weight_pack: padding too small");
+  const int64_t total = (int64_t)ntaps * KP * NP;
+  weight_pack_kernel<<<ceil_div(total, 256) > 1024 ? 1024 : ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      w, (bf16*)dst_bf16, Cout, Cin, ntaps, ci0, ci_n, KP, NP, mode);
+  RTP_LAUNCH_CHECK();
+}
+
+// k3s1 plane-streaming pack: dst[(ky,kx) tap 9][KP/8][3*NPo][8]; N index = j*NPo + co with j = 2 - kz
+// (block order [kz=2 | kz=1 | kz=0] so the three TMEM accumulator blocks of output planes z-1, z, z+1 are
+// contiguous).  In-plane tap index t9 = kx*3 + ky (x is the slow in-plane axis of the P8 layout).
+// transpose_flip = 1 builds the dgrad operand: K = Cout, N = Cin, taps mirrored.
+__global__ void weight_pack_k3s1_kernel(const float* __restrict__ w, bf16* __restrict__ dst, int Cout, int Cin, int KP,
+                                        int NPo, int tf) {
+  const int N3 = 3 * NPo;
+  const int64_t total = (int64_t)9 * KP * N3;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int k8 = i & 7;
+    int64_t r = i >> 3;
+    const int n = r % N3;
+    r /= N3;
+    const int kc = r % (KP / 8);
+    const int t9 = r / (KP / 8);
+    const int k = kc * 8 + k8;
+    const int j = n / NPo, nn = n % NPo;
+    int kz = 2 - j, kx = t9 / 3, ky = t9 % 3;
+    int co, ci;
+    if (!tf) { ci = k; co = nn; } else { co = k; ci = nn; kz = 2 - kz; ky = 2 - ky; kx = 2 - kx; }
+    float v = 0.f;
+    if (co < Cout && ci < Cin) v = w[((int64_t)co * Cin + ci) * 27 + (kz * 3 + ky) * 3 + kx];
+    dst[i] = __float2bfloat16(v);
+  }
+}
+extern "C" int rtp_weight_pack_k3s1(const float* w, void* dst_bf16, int32_t Cout, int32_t Cin, int32_t KP, int32_t NPo,
+                                    int32_t transpose_flip, void* stream) {
+  RTP_CHECK_ARG(w && dst_bf16, "rtp_weight_pack_k3s1: null pointer");
+  RTP_CHECK_ARG(KP % 16 == 0 && NPo % 16 == 0 && 3 * NPo <= 256, "rtp_weight_pack_k3s1: bad KP/NPo");
+  RTP_CHECK_ARG(transpose_flip ? (Cout <= KP && Cin <= NPo) : (Cin <= KP && Cout <= NPo),
+                "rtp_weight_pack_k3s1: padding too small");
+  const int64_t total = (int64_t)9 * KP * 3 * NPo;
+  weight_pack_k3s1_kernel<<<ceil_div(total, 256) > 1024 ? 1024 : ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      w, (bf16*)dst_bf16, Cout, Cin, KP, NPo, transpose_flip);
+  RTP_LAUNCH_CHECK();
+}
+
+// ---------------------------------------------------------------------------------------------- misc
+__global__ void scale_kernel(float* __restrict__ b, int64_t n, float s) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) b[i] *= s;
+}
+extern "C" int rtp_scale_f32(float* buf, int64_t n, float scale, void* stream) {
+  RTP_CHECK_ARG(buf && n >= 0, "rtp_scale_f32: bad args");
+  if (n == 0) return 0;
+  scale_kernel<<<ceil_div(n, 1024) > 592 ? 592 : ceil_div(n, 1024), 256, 0, (cudaStream_t)stream>>>(buf, n, scale);
+  RTP_LAUNCH_CHECK();
+}

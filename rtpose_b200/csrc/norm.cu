@@ -1,0 +1,388 @@
+// norm.cu — GroupNorm(G, C) forward / backward on P8 tensors.  HBM-bound elementwise + two-level
+// (deterministic) reductions; statistics fp32, combined in fp64.
+//
+// Algorithmic bytes (bf16): sums 2 B/elem read; apply 2 B read + 2 B write; bwd_reduce 4 B read;
+// bwd_apply 4 B read + 2 B write (+2 B when accumulating).
+#include "common.cuh"
+
+namespace {
+
+constexpr int kSlabs = 32;  // partial reductions per (sample, chunk); fixed => deterministic summation order
+
+// decode a linear real-voxel index v in [0, Z*X*Y) -> element offset (y fastest)
+__device__ __forceinline__ int64_t voxel_off(const P8& t, int64_t v) {
+  const int y = (int)(v % t.Y);
+  v /= t.Y;
+  const int x = (int)(v % t.X);
+  const int z = (int)(v / t.X);
+  return t.voxel(z, x, y);
+}
+
+// block-wide sum of NV values per thread; result valid in thread 0..NV-1 of warp 0 (value index = lane)
+template <int NV>
+__device__ __forceinline__ void block_reduce(float (&acc)[NV], float* sh /* [8][NV] */, float* out) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) acc[i] = warp_sum(acc[i]);
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) sh[warp * NV + i] = acc[i];
+  }
+  __syncthreads();
+  if (threadIdx.x < NV) {
+    float s = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += sh[w * NV + threadIdx.x];
+    out[threadIdx.x] = s;
+  }
+}
+
+// partial[n][c8][slab][16] = (sum x[0..7], sum x^2[0..7])
+__global__ void __launch_bounds__(256) gn_sums_partial_kernel(P8 x, float* __restrict__ partial) {
+  __shared__ float sh[8 * 16];
+  const int slab = blockIdx.x, c8 = blockIdx.y, n = blockIdx.z;
+  const int64_t V = (int64_t)x.Z * x.X * x.Y;
+  const int64_t v0 = V * slab / kSlabs, v1 = V * (slab + 1) / kSlabs;
+  const bf16* base = x.ptr + n * x.n_stride + c8 * x.c_stride;
+  float acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+  for (int64_t v = v0 + threadIdx.x; v < v1; v += 256) {
+    float f[8];
+    unpack8(ldg16(base + voxel_off(x, v)), f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      acc[i] += f[i];
+      acc[8 + i] += f[i] * f[i];
+    }
+  }
+  block_reduce<16>(acc, sh, partial + (((size_t)n * x.C8 + c8) * kSlabs + slab) * 16);
+}
+
+// sums[n][c][2] = sum over slabs (fixed order)
+__global__ void gn_sums_final_kernel(const float* __restrict__ partial, int N, int C8, int C, float* __restrict__ sums) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * C8 * 8) return;
+  const int j = i & 7, c8 = (i >> 3) % C8, n = (i >> 3) / C8;
+  const int c = c8 * 8 + j;
+  if (c >= C) return;
+  const float* p = partial + ((size_t)n * C8 + c8) * kSlabs * 16;
+  double s = 0, q = 0;
+  for (int k = 0; k < kSlabs; ++k) {
+    s += p[k * 16 + j];
+    q += p[k * 16 + 8 + j];
+  }
+  sums[((size_t)n * C + c) * 2] = (float)s;
+  sums[((size_t)n * C + c) * 2 + 1] = (float)q;
+}
+
+// stats[n][g] = (mean, rstd) from per-channel sums
+__global__ void gn_finalize_kernel(const float* __restrict__ sums, int N, int C, int G, double count, float eps,
+                                   float* __restrict__ stats) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * G) return;
+  const int g = i % G, n = i / G, cpg = C / G;
+  double s = 0, q = 0;
+  for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+    s += sums[((size_t)n * C + c) * 2];
+    q += sums[((size_t)n * C + c) * 2 + 1];
+  }
+  const double m = count * cpg;
+  const double mean = s / m;
+  double var = q / m - mean * mean;
+  if (var < 0) var = 0;
+  stats[i * 2] = (float)mean;
+  stats[i * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+}
+
+// y = (x - mean) * rstd * gamma + beta  on real voxels (pads are never written)
+__global__ void __launch_bounds__(256) gn_apply_kernel(P8 x, int C, int G, const float* __restrict__ stats,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                       P8 y) {
+  const int c8 = blockIdx.y, n = blockIdx.z;
+  const int cpg = C / G;
+  float a[8], b[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = c8 * 8 + i;
+    if (c < C) {
+      const int g = c / cpg;
+      const float mean = stats[((size_t)n * G + g) * 2], rstd = stats[((size_t)n * G + g) * 2 + 1];
+      a[i] = rstd * gamma[c];
+      b[i] = beta[c] - mean * a[i];
+    } else {
+      a[i] = 0.f;
+      b[i] = 0.f;
+    }
+  }
+  const int64_t V = (int64_t)x.Z * x.X * x.Y;
+  const bf16* xb = x.ptr + n * x.n_stride + c8 * x.c_stride;
+  bf16* yb = y.ptr + n * y.n_stride + c8 * y.c_stride;
+  for (int64_t v = blockIdx.x * 256ll + threadIdx.x; v < V; v += (int64_t)gridDim.x * 256) {
+    const int64_t off = voxel_off(x, v);
+    float f[8];
+    unpack8(ldg16(xb + off), f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = fmaf(f[i], a[i], b[i]);
+    stg16(yb + off, pack8(f));
+  }
+}
+
+// partial[n][c8][slab][16] = (sum dy[0..7], sum dy*xhat[0..7])
+__global__ void __launch_bounds__(256) gn_bwd_partial_kernel(P8 x, P8 dy, int C, int G, const float* __restrict__ stats,
+                                                             float* __restrict__ partial) {
+  __shared__ float sh[8 * 16];
+  const int slab = blockIdx.x, c8 = blockIdx.y, n = blockIdx.z;
+  const int cpg = C / G;
+  float mean[8], rstd[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = min(c8 * 8 + i, C - 1);
+    const int g = c / cpg;
+    mean[i] = stats[((size_t)n * G + g) * 2];
+    rstd[i] = stats[((size_t)n * G + g) * 2 + 1];
+  }
+  const int64_t V = (int64_t)x.Z * x.X * x.Y;
+  const int64_t v0 = V * slab / kSlabs, v1 = V * (slab + 1) / kSlabs;
+  const bf16* xb = x.ptr + n * x.n_stride + c8 * x.c_stride;
+  const bf16* db = dy.ptr + n * dy.n_stride + c8 * dy.c_stride;
+  float acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+  for (int64_t v = v0 + threadIdx.x; v < v1; v += 256) {
+    const int64_t off = voxel_off(x, v);
+    float f[8], d[8];
+    unpack8(ldg16(xb + off), f);
+    unpack8(ldg16(db + off), d);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      acc[i] += d[i];
+      acc[8 + i] += d[i] * ((f[i] - mean[i]) * rstd[i]);
+    }
+  }
+  block_reduce<16>(acc, sh, partial + (((size_t)n * x.C8 + c8) * kSlabs + slab) * 16);
+}
+
+// dgamma[c] (+)= sum_n red[n][c][1]; dbeta[c] (+)= sum_n red[n][c][0]
+__global__ void gn_param_grad_kernel(const float* __restrict__ red, int N, int C, float* __restrict__ dgamma,
+                                     float* __restrict__ dbeta, int accumulate) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double a = 0, b = 0;
+  for (int n = 0; n < N; ++n) {
+    a += red[((size_t)n * C + c) * 2];
+    b += red[((size_t)n * C + c) * 2 + 1];
+  }
+  dbeta[c] = accumulate ? dbeta[c] + (float)a : (float)a;
+  dgamma[c] = accumulate ? dgamma[c] + (float)b : (float)b;
+}
+
+// dx (=|+=) [x>0] * rstd * (gamma*dy - (s1 + xhat*s2)/m)
+__global__ void __launch_bounds__(256) gn_bwd_apply_kernel(P8 x, P8 dy, int C, int G, const float* __restrict__ stats,
+                                                           const float* __restrict__ red, const float* __restrict__ gamma,
+                                                           P8 dx, int accumulate, int relu_mask) {
+  const int c8 = blockIdx.y, n = blockIdx.z;
+  const int cpg = C / G;
+  const int64_t V = (int64_t)x.Z * x.X * x.Y;
+  const float inv_m = 1.0f / ((float)V * (float)cpg);
+  float mean[8], rstd[8], ga[8], k1[8], k2[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = min(c8 * 8 + i, C - 1);
+    const int g = c / cpg;
+    mean[i] = stats[((size_t)n * G + g) * 2];
+    rstd[i] = stats[((size_t)n * G + g) * 2 + 1];
+    ga[i] = (c8 * 8 + i < C) ? gamma[c] : 0.f;
+    float s1 = 0.f, s2 = 0.f;
+    for (int cc = g * cpg; cc < (g + 1) * cpg; ++cc) {
+      s1 += gamma[cc] * red[((size_t)n * C + cc) * 2];
+      s2 += gamma[cc] * red[((size_t)n * C + cc) * 2 + 1];
+    }
+    k1[i] = s1 * inv_m;
+    k2[i] = s2 * inv_m;
+  }
+  const bf16* xb = x.ptr + n * x.n_stride + c8 * x.c_stride;
+  const bf16* db = dy.ptr + n * dy.n_stride + c8 * dy.c_stride;
+  bf16* ob = dx.ptr + n * dx.n_stride + c8 * dx.c_stride;
+  for (int64_t v = blockIdx.x * 256ll + threadIdx.x; v < V; v += (int64_t)gridDim.x * 256) {
+    const int64_t off = voxel_off(x, v);
+    float f[8], d[8], o[8];
+    unpack8(ldg16(xb + off), f);
+    unpack8(ldg16(db + off), d);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float xh = (f[i] - mean[i]) * rstd[i];
+      o[i] = rstd[i] * (ga[i] * d[i] - k1[i] - xh * k2[i]);
+      if (relu_mask && !(f[i] > 0.f)) o[i] = 0.f;
+    }
+    if (accumulate) {
+      float p[8];
+      unpack8(*reinterpret_cast<const uint4*>(ob + off), p);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] += p[i];
+    }
+    stg16(ob + off, pack8(o));
+  }
+}
+
+int ew_blocks(int64_t V) {
+  int64_t b = (V + 255) / 256;
+  return (int)(b > 592 ? 592 : (b < 1 ? 1 : b));
+}
+
+}  // namespace
+
+extern "C" int64_t rtp_gn_workspace_bytes(int32_t N, int32_t C8) { return (int64_t)N * C8 * kSlabs * 16 * 4; }
+
+extern "C" int rtp_gn_sums(rtp_p8 x, int32_t C, float* sums, float* workspace, void* stream) {
+  RTP_CHECK_ARG(x.ptr && sums && workspace && C > 0 && C <= x.C8 * 8, "rtp_gn_sums: bad args");
+  P8 t(x);
+  t.C8 = ceil_div(C, 8);
+  gn_sums_partial_kernel<<<dim3(kSlabs, t.C8, t.N), 256, 0, (cudaStream_t)stream>>>(t, workspace);
+  gn_sums_final_kernel<<<ceil_div(t.N * t.C8 * 8, 128), 128, 0, (cudaStream_t)stream>>>(workspace, t.N, t.C8, C, sums);
+  RTP_LAUNCH_CHECK();
+}
+
+extern "C" int rtp_gn_finalize(const float* sums, int32_t N, int32_t C, int32_t G, int64_t voxels, float eps, float* stats,
+                               void* stream) {
+  RTP_CHECK_ARG(sums && stats && N > 0 && C > 0 && G > 0 && C % G == 0 && voxels > 0, "rtp_gn_finalize: bad args");
+  gn_finalize_kernel<<<ceil_div(N * G, 64), 64, 0, (cudaStream_t)stream>>>(sums, N, C, G, (double)voxels, eps, stats);
+  RTP_LAUNCH_CHECK();
+}
+
+extern "C" int rtp_gn_apply(rtp_p8 x, int32_t C, int32_t G, const float* stats, const float* gamma, const float* beta,
+                            rtp_p8 y, void* stream) {
+  RTP_CHECK_ARG(x.ptr && y.ptr && stats && gamma && beta, "rtp_gn_apply: null argument");
+  RTP_CHECK_ARG(C > 0 && C % G == 0 && C <= x.C8 * 8 && C <= y.C8 * 8, "rtp_gn_apply: bad C/G");
+  RTP_CHECK_ARG(x.N == y.N && x.Z == y.Z && x.X == y.X && x.Y == y.Y, "rtp_gn_apply: geometry mismatch");
+  P8 tx(x), ty(y);
+  const int64_t V = (int64_t)x.Z * x.X * x.Y;
+  gn_apply_kernel<<<dim3(ew_blocks(V), ceil_div(C, 8), x.N), 256, 0, (cudaStream_t)stream>>>(tx, C, G, stats, gamma, beta, ty);
+  RTP_LAUNCH_CHECK();
+}
+
+extern "C" int rtp_gn_bwd_reduce(rtp_p8 x, rtp_p8 dy, int32_t C, int32_t G, const float* stats, float* red,
+                                 float* workspace, void* stream) {
+  RTP_CHECK_ARG(x.ptr && dy.ptr && stats && red && workspace, "rtp_gn_bwd_reduce: null argument");
+  RTP_CHECK_ARG(C > 0 && C % G == 0 && C <= x.C8 * 8 && C <= dy.C8 * 8, "rtp_gn_bwd_reduce: bad C/G");
+  RTP_CHECK_ARG(x.N == dy.N && x.Z == dy.Z && x.X == dy.X && x.Y == dy.Y, "rtp_gn_bwd_reduce: geometry mismatch");
+  P8 tx(x), td(dy);
+  tx.C8 = ceil_div(C, 8);
+  gn_bwd_partial_kernel<<<dim3(kSlabs, tx.C8, tx.N), 256, 0, (cudaStream_t)stream>>>(tx, td, C, G, stats, workspace);
+  gn_sums_final_kernel<<<ceil_div(tx.N * tx.C8 * 8, 128), 128, 0, (cudaStream_t)stream>>>(workspace, tx.N, tx.C8, C, red);
+  RTP_LAUNCH_CHECK();
+}
+
+extern "C" int rtp_gn_bwd_apply(rtp_p8 x, rtp_p8 dy, int32_t C, int32_t G, const float* stats, const float* red,
+                                const float* gamma, float* dgamma, float* dbeta, int32_t accumulate_params, rtp_p8 dx,
+                                int32_t accumulate_dx, int32_t relu_mask, void* stream) {
+  RTP_CHECK_ARG(x.ptr && dy.ptr && stats && red && gamma, "rtp_gn_bwd_apply: null argument");
+  RTP_CHECK_ARG(C > 0 && C % G == 0 && C <= x.C8 * 8 && C <= dy.C8 * 8, "rtp_gn_bwd_apply: bad C/G");
+  if (dgamma && dbeta)
+    gn_param_grad_kernel<<<ceil_div(C, 64), 64, 0, (cudaStream_t)stream>>>(red, x.N, C, dgamma, dbeta, accumulate_params);
+  if (dx.ptr) {
+    RTP_CHECK_ARG(x.N == dx.N && x.Z == dx.Z && x.X == dx.X && x.Y == dx.Y && C <= dx.C8 * 8, "rtp_gn_bwd_apply: dx geometry mismatch");
+    P8 tx(x), td(dy), to(dx);
+    const int64_t V = (int64_t)x.Z * x.X * x.Y;
+    gn_bwd_apply_kernel<<<dim3(ew_blocks(V), ceil_div(C, 8), x.N), 256, 0, (cudaStream_t)stream>>>(
+        tx, td, C, G, stats, red, gamma, to, accumulate_dx, relu_mask);
+  }
+  RTP_LAUNCH_CHECK();
+}
+
+// ================================================================================================ stem / bias grads
+namespace {
+
+// y[c] = w[c] * x + b[c], x = channel 0 of a P8 tensor (single-channel radar cube)
+__global__ void __launch_bounds__(256) stem_fwd_kernel(P8 x, const float* __restrict__ w, const float* __restrict__ b, int C,
+                                                       P8 y) {
+  const int c8 = blockIdx.y, n = blockIdx.z;
+  float wv[8], bv[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = c8 * 8 + i;
+    wv[i] = c < C ? w[c] : 0.f;
+    bv[i] = c < C ? b[c] : 0.f;
+  }
+  const int64_t V = (int64_t)x.Z * x.X * x.Y;
+  const bf16* xb = x.ptr + n * x.n_stride;
+  bf16* yb = y.ptr + n * y.n_stride + c8 * y.c_stride;
+  for (int64_t v = blockIdx.x * 256ll + threadIdx.x; v < V; v += (int64_t)gridDim.x * 256) {
+    const int64_t off = voxel_off(x, v);
+    const float xv = __bfloat162float(xb[off]);
+    float f[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = fmaf(wv[i], xv, bv[i]);
+    stg16(yb + off, pack8(f));
+  }
+}
+
+// partial[n][c8][slab][16] = (sum dy[0..7], sum dy[0..7] * x)
+__global__ void __launch_bounds__(256) stem_bwd_partial_kernel(P8 x, P8 dy, float* __restrict__ partial) {
+  __shared__ float sh[8 * 16];
+  const int slab = blockIdx.x, c8 = blockIdx.y, n = blockIdx.z;
+  const int64_t V = (int64_t)x.Z * x.X * x.Y;
+  const int64_t v0 = V * slab / kSlabs, v1 = V * (slab + 1) / kSlabs;
+  const bf16* xb = x.ptr + n * x.n_stride;
+  const bf16* db = dy.ptr + n * dy.n_stride + c8 * dy.c_stride;
+  float acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+  for (int64_t v = v0 + threadIdx.x; v < v1; v += 256) {
+    const int64_t off = voxel_off(x, v);
+    const float xv = __bfloat162float(xb[off]);
+    float d[8];
+    unpack8(ldg16(db + off), d);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      acc[i] += d[i];
+      acc[8 + i] += d[i] * xv;
+    }
+  }
+  block_reduce<16>(acc, sh, partial + (((size_t)n * gridDim.y + c8) * kSlabs + slab) * 16);
+}
+
+// out0[c] (+)= sum_{n,slab} partial[..][j], out1[c] (+)= sum partial[..][8+j]  (fixed order)
+__global__ void slab_final_kernel(const float* __restrict__ partial, int N, int C8, int C, float* __restrict__ out0,
+                                  float* __restrict__ out1, int accumulate) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const int c8 = c >> 3, j = c & 7;
+  double a = 0, b = 0;
+  for (int n = 0; n < N; ++n) {
+    const float* p = partial + ((size_t)n * C8 + c8) * kSlabs * 16;
+    for (int k = 0; k < kSlabs; ++k) {
+      a += p[k * 16 + j];
+      b += p[k * 16 + 8 + j];
+    }
+  }
+  if (out0) out0[c] = accumulate ? out0[c] + (float)a : (float)a;
+  if (out1) out1[c] = accumulate ? out1[c] + (float)b : (float)b;
+}
+
+}  // namespace
+
+extern "C" int rtp_stem_fwd(rtp_p8 x, const float* w, const float* b, int32_t C, rtp_p8 y, void* stream) {
+  RTP_CHECK_ARG(x.ptr && y.ptr && w && b && C > 0 && C <= y.C8 * 8, "rtp_stem_fwd: bad args");
+  RTP_CHECK_ARG(x.N == y.N && x.Z == y.Z && x.X == y.X && x.Y == y.Y, "rtp_stem_fwd: geometry mismatch");
+  const int64_t V = (int64_t)x.Z * x.X * x.Y;
+  stem_fwd_kernel<<<dim3(ew_blocks(V), ceil_div(C, 8), x.N), 256, 0, (cudaStream_t)stream>>>(P8(x), w, b, C, P8(y));
+  RTP_LAUNCH_CHECK();
+}
+
+extern "C" int rtp_stem_bwd(rtp_p8 x, rtp_p8 dy, int32_t C, float* dw, float* db, int32_t accumulate, float* workspace,
+                            void* stream) {
+  RTP_CHECK_ARG(x.ptr && dy.ptr && dw && db && workspace && C > 0 && C <= dy.C8 * 8, "rtp_stem_bwd: bad args");
+  const int C8 = ceil_div(C, 8);
+  stem_bwd_partial_kernel<<<dim3(kSlabs, C8, x.N), 256, 0, (cudaStream_t)stream>>>(P8(x), P8(dy), workspace);
+  slab_final_kernel<<<ceil_div(C, 64), 64, 0, (cudaStream_t)stream>>>(workspace, x.N, C8, C, db, dw, accumulate);
+  RTP_LAUNCH_CHECK();
+}
+
+extern "C" int rtp_channel_sum(rtp_p8 x, int32_t C, float* out, int32_t accumulate, float* workspace, void* stream) {
+  RTP_CHECK_ARG(x.ptr && out && workspace && C > 0 && C <= x.C8 * 8, "rtp_channel_sum: bad args");
+  P8 t(x);
+  t.C8 = ceil_div(C, 8);
+  gn_sums_partial_kernel<<<dim3(kSlabs, t.C8, t.N), 256, 0, (cudaStream_t)stream>>>(t, workspace);
+  slab_final_kernel<<<ceil_div(C, 64), 64, 0, (cudaStream_t)stream>>>(workspace, t.N, t.C8, C, out, nullptr, accumulate);
+  RTP_LAUNCH_CHECK();
+}

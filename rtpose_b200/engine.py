@@ -1,0 +1,316 @@
+"""HRRadarPose forward/backward as a straight-line program of C-ABI kernel launches.
+
+This is the host side of the hot path: it mirrors the dataflow of the reference modules
+(det3d/models/backbones/hr_util/{common,hr3d}.py, backbones/hrnet3d.py, pose_heads/center_head.py) but runs
+every op through librtpose_b200.so on P8 tensors and keeps its own tape for the backward pass (the graph is
+static, so no autograd engine is needed; `autograd_bridge.py` exposes it to torch as one Function).
+
+Gradient convention: for a tensor that is the output of a ReLU, `.grad` holds the gradient w.r.t. the *pre-ReLU*
+value; every kernel that writes into such a gradient applies the (t > 0) mask itself.
+"""
+import torch
+
+from . import lib, ops
+from .p8 import P8, _stream
+
+ARCH = {  # det3d/models/backbones/hrnet3D_config.py:85-177 — (input planes, per-branch channels)
+    "hr_tiny_feat32_zyx_l4": (1, [32, 32, 64, 64]),
+    "hr_tiny_feat32_zyx_l4_in32": (32, [32, 32, 64, 64]),
+    "hr_tiny_feat64_zyx_l4_in64": (64, [64, 64, 128, 128]),
+}
+
+
+class Engine:
+    def __init__(self, arch, final_fuse, params, reg_channels, num_classes, loss_weight, code_weights,
+                 prefix_backbone="backbone.", prefix_head="pose_head."):
+        """params: dict name -> fp32 CUDA tensor (the reference's state_dict names)."""
+        if arch not in ARCH:
+            raise KeyError("unknown backbone_cfg %r (supported: %s)" % (arch, sorted(ARCH)))
+        self.in_ch, self.ch = ARCH[arch]
+        self.fuse = final_fuse
+        self.p = params
+        self.pb, self.ph = prefix_backbone, prefix_head
+        self.R, self.ncls = reg_channels, num_classes
+        self.loss_weight = float(loss_weight)
+        self.code_weights = [float(v) for v in code_weights]
+        self.packs = ops.PackedWeights()
+        self.pool = ops.BufferPool()
+        self.tape = []
+        self.grads = None
+        self._touched = set()
+        self._cw = None
+
+    # ------------------------------------------------------------------ helpers
+    def new(self, like, C=None, grid=None):
+        Z, Y, X = grid if grid is not None else like.grid
+        return self.pool.get(like.N, like.C if C is None else C, Z, Y, X, like.buf.device)
+
+    def _grad_of(self, t):
+        """Returns (grad tensor, accumulate flag) for a writer into t.grad."""
+        if t.grad is None:
+            t.grad = self.new(t)
+            return t.grad, False
+        return t.grad, True
+
+    def _pgrad(self, name):
+        """fp32 gradient tensor of parameter `name` and whether to accumulate into it."""
+        g = self.grads[name]
+        acc = name in self._touched
+        self._touched.add(name)
+        return g, acc
+
+    # ------------------------------------------------------------------ ops with backward closures
+    def gn_conv(self, x, gn, conv, k, stride, relu, res=None, train=True, x_needs_grad=True, res_needs_grad=True):
+        """ReLU?( conv_k_stride( GroupNorm(8)(x) ) [+ res] ) — common.py:92-96 'gcr'/'gc' order; hr3d.py fuse/transition
+        Sequentials."""
+        p = self.p
+        gamma, beta, w = p[gn + ".weight"], p[gn + ".bias"], p[conv + ".weight"]
+        G = 8 if x.C >= 8 else 1
+        stats = self.stats_cache.get(id(x))
+        if stats is None:
+            stats = ops.gn_stats(x, G)
+            self.stats_cache[id(x)] = stats
+        xn = ops.gn_apply(x, G, stats, gamma, beta, self.new(x))
+        Zo, Yo, Xo = ops.out_grid(x, stride)
+        y = self.new(x, C=w.shape[0], grid=(Zo, Yo, Xo))
+        ops.conv_forward(self.packs, xn, w, stride, y, relu=relu, res=res)
+        y.relu_out = bool(relu)
+        if train:
+            def bwd():
+                dy = y.grad
+                if dy is None:
+                    return
+                if res is not None and res_needs_grad:
+                    g, acc = self._grad_of(res)
+                    ops.grad_add(dy, g, mask=res if res.relu_out else None, accumulate=acc)
+                gw, accw = self._pgrad(conv + ".weight")
+                ops.conv_wgrad(xn, dy, k, stride, gw, accumulate=accw)
+                dxn = ops.conv_dgrad(self.packs, dy, w, stride, self.new(xn))
+                gg, accg = self._pgrad(gn + ".weight")
+                gb, _ = self._pgrad(gn + ".bias")
+                if x_needs_grad:
+                    gx, accx = self._grad_of(x)
+                else:
+                    gx, accx = None, False
+                ops.gn_backward(x, dxn, G, stats, gamma, gg, gb, accg, gx, accx)
+            self.tape.append(bwd)
+        return y
+
+    def res_block(self, x, prefix, train, x_needs_grad=True):
+        """ResNetBlock.forward (hr_util/common.py:138-148)."""
+        p = self.p
+        if prefix + ".conv1.weight" in p:
+            w1, b1 = p[prefix + ".conv1.weight"], p[prefix + ".conv1.bias"]
+            if w1.shape[1] != 1:
+                raise NotImplementedError("ResNetBlock.conv1 with Cin=%d (only the 1->C stem occurs)" % w1.shape[1])
+            r = self.new(x, C=w1.shape[0])
+            wv = w1.detach().reshape(-1).contiguous()
+            lib.call("rtp_stem_fwd", x.struct(), wv.data_ptr(), b1.data_ptr(), w1.shape[0], r.struct(), _stream())
+            if train:
+                def bwd():
+                    if r.grad is None:
+                        return
+                    gw, acc = self._pgrad(prefix + ".conv1.weight")
+                    gb, _ = self._pgrad(prefix + ".conv1.bias")
+                    lib.call("rtp_stem_bwd", x.struct(), r.grad.struct(), w1.shape[0], gw.data_ptr(), gb.data_ptr(),
+                             int(acc), ops.gn_ws(r).data_ptr(), _stream())
+                self.tape.append(bwd)
+            r_needs_grad = True
+        else:
+            r, r_needs_grad = x, x_needs_grad
+        o = self.gn_conv(r, prefix + ".conv2.groupnorm", prefix + ".conv2.conv", 3, 1, True, train=train,
+                         x_needs_grad=r_needs_grad)
+        out = self.gn_conv(o, prefix + ".conv3.groupnorm", prefix + ".conv3.conv", 3, 1, True,
+                           res=r, train=train, res_needs_grad=r_needs_grad)
+        return out
+
+    def hr_module(self, xs, prefix, nb, train, outputs=None):
+        """HighResolutionModule.forward (hr_util/hr3d.py:205-229)."""
+        xs = [self.res_block(xs[b], "%s.branches.%d.0" % (prefix, b), train) for b in range(nb)]
+        outs = []
+        for i in (range(nb) if outputs is None else outputs):
+            same, low = [], []
+            for j in range(nb):
+                if j == i:
+                    same.append(xs[j])
+                elif j > i:
+                    q = "%s.fuse_layers.%d.%d" % (prefix, i, j)
+                    low.append(self.gn_conv(xs[j], q + ".0", q + ".1", 1, 1, False, train=train))
+                else:
+                    t = xs[j]
+                    for k in range(i - j):
+                        q = "%s.fuse_layers.%d.%d.%d" % (prefix, i, j, k)
+                        t = self.gn_conv(t, q + ".0", q + ".1", 3, 2, k < i - j - 1, train=train)
+                    same.append(t)
+            y = ops.fuse_sum(self.new(xs[i]), same, low, relu=True)
+            y.relu_out = True
+            if train:
+                self.tape.append(self._fuse_bwd(y, same, low))
+            outs.append(y)
+        return outs
+
+    def _fuse_bwd(self, y, same, low):
+        def bwd():
+            g = y.grad
+            if g is None:
+                return
+            for t in same:
+                if t.grad is None and not t.relu_out:
+                    t.grad = g  # single consumer, no mask: alias instead of copying
+                else:
+                    gt, acc = self._grad_of(t)
+                    ops.grad_add(g, gt, mask=t if t.relu_out else None, accumulate=acc)
+            for t in low:
+                gt, acc = self._grad_of(t)
+                ops.upsample_bwd(g, gt, accumulate=acc)
+        return bwd
+
+    # ------------------------------------------------------------------ network
+    def backbone(self, x, train):
+        """HighResolution3DNet.forward (hr_util/hr3d.py:373-399) + HRNet3D.forward (backbones/hrnet3d.py:29-42)."""
+        bb = self.pb + "backbone"
+        x = self.res_block(x, bb + ".layer1", train, x_needs_grad=False)
+        ys = [x]
+        for s in (2, 3, 4):
+            q = "%s.transition%d.%d.0" % (bb, s - 1, s - 1)
+            new = self.gn_conv(ys[-1], q + ".0", q + ".1", 3, 2, True, train=train)
+            outputs = [0] if (s == 4 and self.fuse == "top") else None  # y1..y3 of stage4 are never read ('top')
+            ys = self.hr_module(ys + [new], "%s.stage%d.0" % (bb, s), s, train, outputs)
+        if self.fuse == "top":
+            if (self.pb + "final_conv.weight") in self.p:
+                raise NotImplementedError("final_fuse='top' with a non-identity final_conv")
+            return ys[0]
+        # 'conat_conv': final_conv(cat(x0, up(x1), up(x2), up(x3))) == W0 x0 + sum_j up(Wj xj) + b  (1x1 conv and
+        # trilinear interpolation commute); avoids materialising the concat.
+        w, b = self.p[self.pb + "final_conv.weight"], self.p[self.pb + "final_conv.bias"]
+        terms, c0 = [], 0
+        for y in ys:
+            t = self.new(y, C=w.shape[0])
+            ops.conv_forward(self.packs, y, w, 1, t, ci0=c0, ci_n=y.C)
+            terms.append((y, t, c0))
+            c0 += y.C
+        f = ops.fuse_sum(self.new(ys[0], C=w.shape[0]), [terms[0][1]], [t for _, t, _ in terms[1:]], bias=b)
+        if train:
+            def bwd():
+                g = f.grad
+                if g is None:
+                    return
+                gb, accb = self._pgrad(self.pb + "final_conv.bias")
+                ops.channel_sum(g, gb, accumulate=accb)
+                gw, accw = self._pgrad(self.pb + "final_conv.weight")
+                if not accw:
+                    pass  # every input-channel slice is written below exactly once
+                for i, (y, t, ci0) in enumerate(terms):
+                    if i == 0:
+                        gt = g
+                    else:
+                        gt = self.new(t)
+                        ops.upsample_bwd(g, gt)
+                    ops.conv_wgrad(y, gt, 1, 1, gw, accumulate=accw, ci0=ci0)
+                    gy, acc = self._grad_of(y)
+                    ops.conv_dgrad(self.packs, gt, w, 1, gy, mask=y if y.relu_out else None, accumulate=acc, ci0=ci0,
+                                   ci_n=y.C)
+            self.tape.append(bwd)
+        return f
+
+    def head(self, f, train):
+        """CenterHead.forward + SepHead.forward (pose_heads/center_head.py:232-238, :66-109); reg.0 and hm.0 read the
+        same input and are merged into one N=64 GEMM."""
+        p, ph = self.p, self.ph
+        if ph + "shared_conv.1.weight" in p:
+            f = self.gn_conv(f, ph + "shared_conv.0", ph + "shared_conv.1", 3, 1, True, train=train)
+        q = ph + "tasks.0."
+        w0 = torch.cat([p[q + "reg.0.weight"].detach(), p[q + "hm.0.weight"].detach()], 0).contiguous()
+        b0 = torch.cat([p[q + "reg.0.bias"].detach(), p[q + "hm.0.bias"].detach()], 0).contiguous()
+        hc = p[q + "reg.0.weight"].shape[0]
+        wkey = ("merged_head", p[q + "reg.0.weight"].data_ptr(), p[q + "hm.0.weight"].data_ptr())
+        wver = (p[q + "reg.0.weight"]._version, p[q + "hm.0.weight"]._version)
+        t = self.new(f, C=2 * hc)
+        ops.conv_forward(self.packs, f, w0, 1, t, bias=b0, relu=True, key=wkey, version=wver)
+        t.relu_out = True
+        t_reg, t_hm = t.channels(0, hc), t.channels(hc, hc)
+        reg = self.new(f, C=self.R)
+        hm = self.new(f, C=self.ncls)
+        ops.conv_forward(self.packs, t_reg, p[q + "reg.2.weight"], 1, reg, bias=p[q + "reg.2.bias"])
+        ops.conv_forward(self.packs, t_hm, p[q + "hm.2.weight"], 1, hm, bias=p[q + "hm.2.bias"])
+        if train:
+            def bwd():
+                if hm.grad is None or reg.grad is None:
+                    return
+                tg = self.new(t)
+                for name, tv, o, c0 in (("reg", t_reg, reg, 0), ("hm", t_hm, hm, hc)):
+                    gw, acc = self._pgrad(q + name + ".2.weight")
+                    ops.conv_wgrad(tv, o.grad, 3, 1, gw, accumulate=acc)
+                    gb, accb = self._pgrad(q + name + ".2.bias")
+                    ops.channel_sum(o.grad, gb, accumulate=accb)
+                    ops.conv_dgrad(self.packs, o.grad, p[q + name + ".2.weight"], 1, tg.channels(c0, hc), mask=tv)
+                gw_r, acc_r = self._pgrad(q + "reg.0.weight")
+                gw_h, acc_h = self._pgrad(q + "hm.0.weight")
+                ops.conv_wgrad(f, tg, 3, 1, gw_r, accumulate=acc_r, n0=0, more=((gw_h, acc_h, 0, hc),))
+                gball = torch.empty(2 * hc, dtype=torch.float32, device=f.buf.device)
+                ops.channel_sum(tg, gball)
+                for name, c0 in (("reg", 0), ("hm", hc)):
+                    gb, accb = self._pgrad(q + name + ".0.bias")
+                    if accb:
+                        gb.add_(gball[c0:c0 + hc])
+                    else:
+                        gb.copy_(gball[c0:c0 + hc])
+                gf, accf = self._grad_of(f)
+                ops.conv_dgrad(self.packs, tg, w0, 1, gf, mask=f if f.relu_out else None, accumulate=accf, key=wkey,
+                               version=wver)
+            self.tape.append(bwd)
+        return hm, reg
+
+    # ------------------------------------------------------------------ entry points
+    def begin(self):
+        self.pool.release_all()
+        self.tape = []
+        self.stats_cache = {}
+        self._touched = set()
+
+    def forward(self, x, train):
+        """x: P8 input cube [N, in_ch, Z, Y, X].  Returns (hm, reg) raw head outputs as P8 tensors."""
+        self.begin()
+        f = self.backbone(x, train)
+        return self.head(f, train)
+
+    def loss(self, hm, reg, tgt_hm, ind, mask, cat, anno, with_grad=True, grad_scale=1.0):
+        """CenterHead.loss (center_head.py:244-270).  Returns a device fp32 tensor
+        [loss, hm_loss, loc_loss, num_pos, loc_loss_elem...]; seeds hm.grad / reg.grad when with_grad."""
+        dev = hm.buf.device
+        if self._cw is None or self._cw.device != dev:
+            self._cw = torch.tensor(self.code_weights, dtype=torch.float32, device=dev)
+        out = torch.empty(4 + self.R, dtype=torch.float32, device=dev)
+        ws = ops.workspace(lib.load().rtp_head_loss_workspace_bytes(hm.N, self.ncls, hm.Z, hm.Y, hm.X), dev, "loss")
+        if with_grad:
+            hm.grad, reg.grad = self.new(hm), self.new(reg)
+            dh, dr = hm.grad.struct(), reg.grad.struct()
+        else:
+            dh = dr = lib.NULL_P8
+        M = ind.shape[1]
+        lib.call("rtp_head_loss", hm.struct(), reg.struct(), self.ncls, self.R, tgt_hm.data_ptr(), ind.data_ptr(),
+                 mask.data_ptr(), cat.data_ptr(), anno.data_ptr(), M, self.loss_weight, self._cw.data_ptr(),
+                 float(grad_scale), out.data_ptr(), dh, dr, ws.data_ptr(), _stream())
+        return out
+
+    def backward(self, grads):
+        """Runs the tape in reverse; `grads`: dict name -> fp32 tensor receiving d loss / d param."""
+        self.grads = grads
+        self._touched = set()
+        for fn in reversed(self.tape):
+            fn()
+        self.tape = []
+        return self._touched
+
+    def decode(self, hm, reg, voxel_xyz, range_xyz):
+        """CenterHead.predict + post_processing (center_head.py:272-360) -> (index int32 [N,ncls], score, xyz)."""
+        import ctypes as C
+        dev = hm.buf.device
+        idx = torch.empty((hm.N, self.ncls), dtype=torch.int32, device=dev)
+        score = torch.empty((hm.N, self.ncls), dtype=torch.float32, device=dev)
+        xyz = torch.empty((hm.N, self.ncls, self.R), dtype=torch.float32, device=dev)
+        v = (C.c_float * 3)(*[float(a) for a in voxel_xyz])
+        r = (C.c_float * 3)(*[float(a) for a in range_xyz])
+        lib.call("rtp_decode", hm.struct(), reg.struct(), self.ncls, self.R, v, r, idx.data_ptr(), score.data_ptr(),
+                 xyz.data_ptr(), _stream())
+        return idx, score, xyz

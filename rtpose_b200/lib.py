@@ -1,0 +1,132 @@
+"""ctypes binding of librtpose_b200.so (C ABI declared in include/rtpose_b200.h).
+
+There is deliberately NO fallback: if the shared library is missing, or a compute call is made without an
+sm_100 device, this raises.  (`load()` itself works on a CPU-only box so the symbol table can be checked.)
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "librtpose_b200.so")
+MAX_TAPS = 27
+GUARD_BYTES = 8192
+
+
+class P8Struct(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("n_stride", C.c_int64), ("c_stride", C.c_int64), ("N", C.c_int32),
+                ("C8", C.c_int32), ("Z", C.c_int32), ("X", C.c_int32), ("Y", C.c_int32)]
+
+
+NULL_P8 = P8Struct(None, 0, 0, 0, 0, 0, 0, 0)
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [("inp", P8Struct), ("out", P8Struct), ("res", P8Struct), ("mask", P8Struct), ("w", C.c_void_p),
+                ("bias", C.c_void_p), ("Cin", C.c_int32), ("NP", C.c_int32), ("out_c8", C.c_int32),
+                ("ntaps", C.c_int32), ("tz", C.c_int8 * MAX_TAPS), ("tx", C.c_int8 * MAX_TAPS),
+                ("ty", C.c_int8 * MAX_TAPS), ("wt", C.c_int8 * MAX_TAPS), ("RZ", C.c_int32), ("RX", C.c_int32),
+                ("RY", C.c_int32), ("IS", C.c_int32), ("OS", C.c_int32), ("oz0", C.c_int32), ("ox0", C.c_int32),
+                ("oy0", C.c_int32), ("relu", C.c_int32), ("accumulate", C.c_int32)]
+
+
+class ConvK3S1Desc(C.Structure):
+    _fields_ = [("inp", P8Struct), ("out", P8Struct), ("res", P8Struct), ("mask", P8Struct), ("w", C.c_void_p),
+                ("bias", C.c_void_p), ("Cin", C.c_int32), ("NPo", C.c_int32), ("out_c8", C.c_int32),
+                ("relu", C.c_int32), ("accumulate", C.c_int32), ("gn_sums", C.c_void_p)]
+
+
+class WgradDesc(C.Structure):
+    _fields_ = [("x", P8Struct), ("dy", P8Struct), ("Cin", C.c_int32), ("NP", C.c_int32), ("ntaps", C.c_int32),
+                ("tz", C.c_int8 * MAX_TAPS), ("tx", C.c_int8 * MAX_TAPS), ("ty", C.c_int8 * MAX_TAPS),
+                ("RZ", C.c_int32), ("RX", C.c_int32), ("RY", C.c_int32), ("IS", C.c_int32), ("nsplit", C.c_int32),
+                ("workspace", C.c_void_p)]
+
+
+class FuseDesc(C.Structure):
+    _fields_ = [("out", P8Struct), ("C", C.c_int32), ("n_same", C.c_int32), ("n_low", C.c_int32),
+                ("same", P8Struct * 4), ("low", P8Struct * 3), ("bias", C.c_void_p), ("relu", C.c_int32)]
+
+
+_i32, _i64, _f32, _vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
+
+# name -> (restype, argtypes); every symbol include/rtpose_b200.h declares
+PROTOTYPES = {
+    "rtp_last_error": (C.c_char_p, []),
+    "rtp_version": (C.c_int, []),
+    "rtp_device_ok": (C.c_int, []),
+    "rtp_pack_ncdhw": (C.c_int, [_vp, P8Struct, _i32, _vp]),
+    "rtp_unpack_ncdhw": (C.c_int, [P8Struct, _vp, _i32, _i32, _vp]),
+    "rtp_ingest_pack": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _f32, _i32, P8Struct,
+                                  _vp, _vp]),
+    "rtp_weight_pack": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "rtp_conv": (C.c_int, [C.POINTER(ConvDesc), _vp]),
+    "rtp_weight_pack_k3s1": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
+    # PENDING "rtp_conv_k3s1": (C.c_int, [C.POINTER(ConvK3S1Desc), _vp]),
+    # PENDING "rtp_conv_k3s1_smem_bytes": (C.c_int64, [_i32, _i32, _i32]),
+    "rtp_wgrad_workspace_bytes": (C.c_int64, [_i32, _i32, _i32, _i32]),
+    "rtp_wgrad": (C.c_int, [C.POINTER(WgradDesc), _vp]),
+    "rtp_wgrad_reduce": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "rtp_gn_workspace_bytes": (C.c_int64, [_i32, _i32]),
+    "rtp_gn_sums": (C.c_int, [P8Struct, _i32, _vp, _vp, _vp]),
+    "rtp_gn_finalize": (C.c_int, [_vp, _i32, _i32, _i32, _i64, _f32, _vp, _vp]),
+    "rtp_gn_apply": (C.c_int, [P8Struct, _i32, _i32, _vp, _vp, _vp, P8Struct, _vp]),
+    "rtp_gn_bwd_reduce": (C.c_int, [P8Struct, P8Struct, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "rtp_gn_bwd_apply": (C.c_int, [P8Struct, P8Struct, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _i32, P8Struct, _i32,
+                                   _i32, _vp]),
+    "rtp_fuse_sum": (C.c_int, [C.POINTER(FuseDesc), _vp]),
+    "rtp_upsample_bwd": (C.c_int, [P8Struct, P8Struct, _i32, _i32, _vp]),
+    "rtp_grad_add": (C.c_int, [P8Struct, P8Struct, P8Struct, _i32, _i32, _vp]),
+    "rtp_channel_sum": (C.c_int, [P8Struct, _i32, _vp, _i32, _vp, _vp]),
+    "rtp_stem_fwd": (C.c_int, [P8Struct, _vp, _vp, _i32, P8Struct, _vp]),
+    "rtp_stem_bwd": (C.c_int, [P8Struct, P8Struct, _i32, _vp, _vp, _i32, _vp, _vp]),
+    "rtp_head_loss_workspace_bytes": (C.c_int64, [_i32, _i32, _i32, _i32, _i32]),
+    "rtp_head_loss": (C.c_int, [P8Struct, P8Struct, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _f32, _vp, _f32, _vp,
+                                P8Struct, P8Struct, _vp, _vp]),
+    "rtp_decode": (C.c_int, [P8Struct, P8Struct, _i32, _i32, C.POINTER(_f32), C.POINTER(_f32), _vp, _vp, _vp, _vp]),
+    # PENDING "rtp_dcn_fwd": (C.c_int, [_vp, _vp, _vp, _vp] + [_i32] * 11 + [_vp]),
+    # PENDING "rtp_dcn_bwd_input": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp] + [_i32] * 11 + [_vp]),
+    # PENDING "rtp_dcn_bwd_weight": (C.c_int, [_vp, _vp, _vp, _vp] + [_i32] * 11 + [_f32, _vp]),
+    "rtp_scale_f32": (C.c_int, [_vp, _i64, _f32, _vp]),
+}
+
+_lib = None
+
+
+class RtpError(RuntimeError):
+    pass
+
+
+def load():
+    """dlopen the library and bind every prototype.  Raises if the .so has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RtpError("librtpose_b200.so not built (%s missing): run `python -m rtpose_b200.build`; "
+                       "there is no CPU fallback" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)  # AttributeError here == header/library mismatch
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = load().rtp_last_error()
+        raise RtpError("%s failed (rc=%d): %s" % (what or "rtp call", rc, msg.decode() if msg else "?"))
+
+
+def require_device():
+    import torch
+
+    if not torch.cuda.is_available():
+        raise RtpError("rtpose_b200 needs a CUDA device (sm_100a); no CPU fallback exists")
+    if not load().rtp_device_ok():
+        raise RtpError("rtpose_b200 kernels are built for sm_100a only; current device is not compute capability 10.x")
+
+
+def call(name, *args):
+    check(getattr(load(), name)(*args), name)

@@ -1,0 +1,270 @@
+"""Host-side wrappers of the C-ABI kernels: descriptor construction (tap lists, row grids), weight-pack caching,
+workspace and activation-buffer pooling.  Everything here launches on torch's current CUDA stream.
+"""
+import ctypes as C
+
+import torch
+
+from . import lib
+from .p8 import P8, _stream
+
+
+def ceil_to(v, m):
+    return (v + m - 1) // m * m
+
+
+# ------------------------------------------------------------------------------------------------ pools
+class BufferPool:
+    """Recycles P8 buffers between steps.  Pads are zeroed at first allocation and never written afterwards, and
+    every producer kernel overwrites all real voxels, so recycled buffers need no re-zeroing."""
+
+    def __init__(self):
+        self.free = {}
+        self.live = []
+
+    def get(self, N, Cc, Z, Y, X, device):
+        key = (N, (Cc + 7) // 8, Z, Y, X, str(device))
+        lst = self.free.get(key)
+        if lst:
+            t = lst.pop()
+            t.C = Cc
+            t.relu_out = False
+            t.grad = None
+        else:
+            t = P8(N, Cc, Z, Y, X, device=device)
+        t._keep = key
+        self.live.append(t)
+        return t
+
+    def release_all(self):
+        for t in self.live:
+            t.grad = None
+            self.free.setdefault(t._keep, []).append(t)
+        self.live = []
+
+
+_workspaces = {}
+
+
+def workspace(nbytes, device, tag="ws"):
+    key = (tag, str(device))
+    w = _workspaces.get(key)
+    if w is None or w.numel() < nbytes:
+        w = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+        _workspaces[key] = w
+    return w
+
+
+# ------------------------------------------------------------------------------------------------ tap lists
+def taps_fwd(k):
+    """(tz, tx, ty, wt) for a forward conv; wt = (kz*k + ky)*k + kx indexes the reference weight's taps."""
+    if k == 1:
+        return [(0, 0, 0, 0)]
+    return [(kz - 1, kx - 1, ky - 1, (kz * 3 + ky) * 3 + kx) for kz in range(3) for ky in range(3) for kx in range(3)]
+
+
+def taps_dgrad_s1(k):
+    if k == 1:
+        return [(0, 0, 0, 0)]
+    return [(1 - kz, 1 - kx, 1 - ky, (kz * 3 + ky) * 3 + kx) for kz in range(3) for ky in range(3) for kx in range(3)]
+
+
+def taps_dgrad_s2(pz, px, py):
+    """dgrad of a 3x3x3 stride-2 pad-1 conv for input voxels of parity (pz, px, py): input index i = 2*o + k - 1, so
+    even i pairs with k=1 (o = i/2) and odd i with k=0 (o = (i+1)/2) or k=2 (o = (i-1)/2)."""
+    def dim(p):
+        return [(1, 0)] if p == 0 else [(0, 1), (2, 0)]
+    return [(tz, tx, ty, (kz * 3 + ky) * 3 + kx) for kz, tz in dim(pz) for ky, ty in dim(py) for kx, tx in dim(px)]
+
+
+def _fill_taps(d, taps, with_wt=True):
+    for i, t in enumerate(taps):
+        d.tz[i], d.tx[i], d.ty[i] = t[0], t[1], t[2]
+        if with_wt:
+            d.wt[i] = t[3]
+    d.ntaps = len(taps)
+
+
+# ------------------------------------------------------------------------------------------------ weights
+class PackedWeights:
+    """bf16 UMMA-B packs of an fp32 conv weight, rebuilt when the parameter's version counter changes."""
+
+    def __init__(self):
+        self.cache = {}
+
+    def get(self, w, mode, ci0=0, ci_n=None, key=None, version=None):
+        """`key`/`version` must be given for temporaries (e.g. merged weights) whose address may be recycled."""
+        Cout, Cin = w.shape[0], w.shape[1]
+        ntaps = w.shape[2] * w.shape[3] * w.shape[4]
+        ci_n = Cin if ci_n is None else ci_n
+        key = (key if key is not None else w.data_ptr(), mode, ci0, ci_n, tuple(w.shape))
+        ver = version if version is not None else w._version
+        hit = self.cache.get(key)
+        if hit is not None and hit[0] == ver:
+            return hit[1]
+        if mode == 0:
+            KP, NP = ceil_to(ci_n, 16), ceil_to(Cout, 16)
+        else:
+            KP, NP = ceil_to(Cout, 16), ceil_to(ci_n, 16)
+        dst = hit[1][0] if hit is not None else torch.empty(ntaps * KP * NP, dtype=torch.bfloat16, device=w.device)
+        wc = w.detach().contiguous()
+        lib.call("rtp_weight_pack", wc.data_ptr(), dst.data_ptr(), Cout, Cin, ntaps, ci0, ci_n, KP, NP, mode, _stream())
+        val = (dst, KP, NP)
+        self.cache[key] = (ver, val)
+        return val
+
+
+# ------------------------------------------------------------------------------------------------ conv
+def conv(x, wpack, KP, NP, out, taps, rows, IS=1, OS=1, off=(0, 0, 0), bias=None, res=None, mask=None, relu=False,
+         accumulate=False):
+    """Generic tcgen05 implicit-GEMM conv (rtp_conv).  rows = (RZ, RX, RY)."""
+    d = lib.ConvDesc()
+    d.inp, d.out = x.struct(), out.struct()
+    d.res = res.struct() if res is not None else lib.NULL_P8
+    d.mask = mask.struct() if mask is not None else lib.NULL_P8
+    d.w = wpack.data_ptr()
+    d.bias = bias.data_ptr() if bias is not None else None
+    d.Cin, d.NP, d.out_c8 = KP, NP, out.C8
+    _fill_taps(d, taps)
+    d.RZ, d.RX, d.RY = rows
+    d.IS, d.OS = IS, OS
+    d.oz0, d.ox0, d.oy0 = off
+    d.relu, d.accumulate = int(relu), int(accumulate)
+    lib.call("rtp_conv", C.byref(d), _stream())
+    return out
+
+
+def pad_bias(b, NP):
+    if b is None:
+        return None
+    if b.numel() == NP:
+        return b.detach().float().contiguous()
+    o = torch.zeros(NP, dtype=torch.float32, device=b.device)
+    o[:b.numel()] = b.detach()
+    return o
+
+
+def out_grid(x, stride):
+    return ((x.Z - 1) // stride + 1, (x.Y - 1) // stride + 1, (x.X - 1) // stride + 1) if stride > 1 else x.grid
+
+
+def conv_forward(packs, x, w, stride, out, bias=None, relu=False, res=None, ci0=0, ci_n=None, key=None, version=None):
+    """y = conv3d(x[:, ci0:ci0+ci_n], w[:, ci0:ci0+ci_n], stride, padding=k//2) (+bias)(+res)(relu)."""
+    k = w.shape[2]
+    wp, KP, NP = packs.get(w, 0, ci0, ci_n, key, version)
+    return conv(x, wp, KP, NP, out, taps_fwd(k), (out.Z, out.X, out.Y), IS=stride, bias=pad_bias(bias, NP), res=res,
+                relu=relu)
+
+
+def conv_dgrad(packs, dy, w, stride, dx, mask=None, accumulate=False, ci0=0, ci_n=None, key=None, version=None):
+    """dx (=|+=) conv_transpose(dy, w) [* (mask > 0)]; dx has the forward input's geometry."""
+    k = w.shape[2]
+    wp, KP, NP = packs.get(w, 1, ci0, ci_n, key, version)
+    if stride == 1:
+        return conv(dy, wp, KP, NP, dx, taps_dgrad_s1(k), (dx.Z, dx.X, dx.Y), mask=mask, accumulate=accumulate)
+    assert stride == 2 and k == 3
+    for pz in range(2):
+        for px in range(2):
+            for py in range(2):
+                rows = ((dx.Z - pz + 1) // 2, (dx.X - px + 1) // 2, (dx.Y - py + 1) // 2)
+                if min(rows) <= 0:
+                    continue
+                conv(dy, wp, KP, NP, dx, taps_dgrad_s2(pz, px, py), rows, IS=1, OS=2, off=(pz, px, py), mask=mask,
+                     accumulate=accumulate)
+    return dx
+
+
+_NSM = None
+
+
+def num_sms():
+    global _NSM
+    if _NSM is None:
+        _NSM = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+    return _NSM
+
+
+def conv_wgrad(x, dy, k, stride, dW, accumulate=False, ci0=0, n0=0, more=()):
+    """dW[:, ci0:ci0+x.C] (=|+=) wgrad(x, dy[:, n0:n0+dW.shape[0]]).  x: forward input (P8), dy: P8 gradient.
+    `more`: further (dW, accumulate, ci0, n0) outputs reduced from the same split-K workspace."""
+    ci_n = x.C
+    Cin8 = ceil_to(ci_n, 8)
+    NP = ceil_to(dy.C, 16)
+    taps = taps_fwd(k)
+    d = lib.WgradDesc()
+    d.x, d.dy = x.struct(), dy.struct()
+    d.Cin, d.NP = Cin8, NP
+    _fill_taps(d, taps, with_wt=False)
+    d.RZ, d.RX, d.RY = dy.Z, dy.X, dy.Y
+    d.IS = stride
+    rows = dy.N * dy.voxels
+    ntiles = (rows + 63) // 64
+    npairs = len(taps) * (Cin8 // 8)
+    nblocks = (npairs + 15) // 16
+    per_cta = max(1, 512 // NP)
+    groups = (nblocks + per_cta - 1) // per_cta
+    nsplit = max(1, min(ntiles, (2 * num_sms()) // groups))
+    d.nsplit = nsplit
+    ws = workspace(lib.load().rtp_wgrad_workspace_bytes(Cin8, NP, len(taps), nsplit), x.buf.device, "wgrad")
+    d.workspace = ws.data_ptr()
+    lib.call("rtp_wgrad", C.byref(d), _stream())
+    for gw, acc, c0, nn in ((dW, accumulate, ci0, n0),) + tuple(more):
+        assert gw.is_contiguous()
+        lib.call("rtp_wgrad_reduce", ws.data_ptr(), nsplit, Cin8, NP, len(taps), gw.data_ptr(), gw.shape[1], gw.shape[0],
+                 nn, c0, ci_n, int(acc), _stream())
+
+
+# ------------------------------------------------------------------------------------------------ GroupNorm
+def gn_ws(x):
+    return workspace(lib.load().rtp_gn_workspace_bytes(x.N, x.C8), x.buf.device, "gn")
+
+
+def gn_stats(x, G, eps=1e-5):
+    sums = torch.empty((x.N, x.C, 2), dtype=torch.float32, device=x.buf.device)
+    stats = torch.empty((x.N, G, 2), dtype=torch.float32, device=x.buf.device)
+    lib.call("rtp_gn_sums", x.struct(), x.C, sums.data_ptr(), gn_ws(x).data_ptr(), _stream())
+    lib.call("rtp_gn_finalize", sums.data_ptr(), x.N, x.C, G, x.voxels, eps, stats.data_ptr(), _stream())
+    return stats
+
+
+def gn_apply(x, G, stats, gamma, beta, out):
+    lib.call("rtp_gn_apply", x.struct(), x.C, G, stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), out.struct(),
+             _stream())
+    return out
+
+
+def gn_backward(x, dxn, G, stats, gamma, dgamma, dbeta, acc_params, dx, acc_dx):
+    red = torch.empty((x.N, x.C, 2), dtype=torch.float32, device=x.buf.device)
+    lib.call("rtp_gn_bwd_reduce", x.struct(), dxn.struct(), x.C, G, stats.data_ptr(), red.data_ptr(),
+             gn_ws(x).data_ptr(), _stream())
+    lib.call("rtp_gn_bwd_apply", x.struct(), dxn.struct(), x.C, G, stats.data_ptr(), red.data_ptr(), gamma.data_ptr(),
+             dgamma.data_ptr(), dbeta.data_ptr(), int(acc_params), dx.struct() if dx is not None else lib.NULL_P8,
+             int(acc_dx), int(x.relu_out), _stream())
+
+
+# ------------------------------------------------------------------------------------------------ fuse / misc
+def fuse_sum(out, same, low, bias=None, relu=False):
+    d = lib.FuseDesc()
+    d.out, d.C = out.struct(), out.C
+    d.n_same, d.n_low = len(same), len(low)
+    for i, t in enumerate(same):
+        d.same[i] = t.struct()
+    for i, t in enumerate(low):
+        d.low[i] = t.struct()
+    d.bias = bias.data_ptr() if bias is not None else None
+    d.relu = int(relu)
+    lib.call("rtp_fuse_sum", C.byref(d), _stream())
+    return out
+
+
+def upsample_bwd(dout, dlow, accumulate=False):
+    lib.call("rtp_upsample_bwd", dout.struct(), dlow.struct(), dlow.C, int(accumulate), _stream())
+
+
+def grad_add(src, dst, mask=None, accumulate=False):
+    lib.call("rtp_grad_add", src.struct(), mask.struct() if mask is not None else lib.NULL_P8, dst.struct(), dst.C,
+             int(accumulate), _stream())
+
+
+def channel_sum(x, out, accumulate=False):
+    lib.call("rtp_channel_sum", x.struct(), x.C, out.data_ptr(), int(accumulate), gn_ws(x).data_ptr(), _stream())

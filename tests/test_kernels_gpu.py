@@ -1,0 +1,341 @@
+"""GPU parity tests, kernel level: every C-ABI kernel against the PyTorch (CPU, fp32) op the reference calls at
+that site, on identical bf16-rounded inputs.  Tolerances (SURVEY.md §8c contract (1)):
+  convs / wgrad : |d| <= 2^-7 * max|ref|   (one bf16 ulp of the output range; fp32 accumulation on both sides)
+  fp32 formulas : rel 1e-4 (GroupNorm statistics, loss)
+  indices       : exact
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+BF16_ULP = 2.0 ** -7
+
+
+def bf(x):
+    return x.to(torch.bfloat16).float()
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return bf(torch.randn(*shape, generator=g) * scale)
+
+
+def to_p8(x):
+    from rtpose_b200.p8 import P8
+    return P8.from_ncdhw(x.cuda())
+
+
+def close(got, ref, tol=BF16_ULP, what=""):
+    got, ref = got.detach().cpu().float(), ref.detach().cpu().float()
+    err = (got - ref).abs().max().item()
+    lim = tol * max(ref.abs().max().item(), 1e-6)
+    assert err <= lim, "%s: max abs err %.4g > %.4g (ref max %.4g)" % (what, err, lim, ref.abs().max().item())
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from rtpose_b200 import lib, ops
+    lib.require_device()
+    return ops.PackedWeights()
+
+
+def test_pack_unpack_roundtrip():
+    x = rnd(2, 13, 4, 10, 12, seed=1)
+    t = to_p8(x)
+    y = t.to_ncdhw().cpu()
+    assert torch.equal(y, x)
+    # pads stay zero
+    full = t.buf[t.offset:t.offset + t.N * t.n_stride].view(t.N, t.C8, t.Z, t.X + 2, t.Y + 2, 8).float().cpu()
+    assert full[:, :, :, 0].abs().max() == 0 and full[:, :, :, -1].abs().max() == 0
+    assert full[:, :, :, :, 0].abs().max() == 0 and full[:, :, :, :, -1].abs().max() == 0
+    assert full[:, 1, :, :, :, 5:].abs().max() == 0  # channels 13..15
+
+
+CONV_CASES = [
+    # N, Cin, Cout, grid, k, stride, bias, relu, res
+    (2, 32, 32, (4, 10, 12), 3, 1, False, True, False),
+    (1, 32, 32, (5, 9, 7), 3, 1, False, True, True),
+    (2, 32, 64, (4, 10, 12), 3, 2, False, True, False),
+    (1, 64, 64, (3, 6, 10), 3, 1, False, False, False),
+    (2, 64, 32, (2, 4, 6), 1, 1, False, False, False),
+    (1, 128, 64, (3, 8, 6), 3, 1, True, True, False),
+    (2, 32, 45, (4, 6, 8), 3, 1, True, False, False),
+    (2, 32, 1, (4, 6, 8), 3, 1, True, False, False),
+    (1, 32, 32, (5, 7, 9), 3, 2, False, False, False),
+    (1, 192, 128, (2, 4, 6), 1, 1, True, False, False),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids=[str(c) for c in CONV_CASES])
+def test_conv_forward(ctx, case):
+    from rtpose_b200 import ops
+    from rtpose_b200.p8 import P8
+    N, Cin, Cout, grid, k, stride, use_bias, relu, use_res = case
+    x = rnd(N, Cin, *grid, seed=2)
+    w = rnd(Cout, Cin, k, k, k, seed=3, scale=(Cin * k ** 3) ** -0.5)
+    b = rnd(Cout, seed=4) if use_bias else None
+    ref = F.conv3d(x, w, b, stride=stride, padding=k // 2)
+    res = rnd(*ref.shape, seed=5) if use_res else None
+    if res is not None:
+        ref = ref + res
+    if relu:
+        ref = F.relu(ref)
+    xp = to_p8(x)
+    out = P8(N, Cout, *ref.shape[2:])
+    wc = w.cuda()
+    ops.conv_forward(ctx, xp, wc, stride, out, bias=b.cuda() if use_bias else None, relu=relu,
+                     res=to_p8(res) if use_res else None)
+    torch.cuda.synchronize()
+    close(out.to_ncdhw(), ref, what="conv fwd")
+
+
+DGRAD_CASES = [(2, 32, 32, (4, 10, 12), 3, 1), (1, 32, 64, (4, 10, 12), 3, 2), (1, 64, 64, (5, 7, 9), 3, 2),
+               (2, 64, 32, (2, 4, 6), 1, 1), (1, 128, 64, (3, 8, 6), 3, 1), (1, 32, 45, (3, 6, 8), 3, 1)]
+
+
+@pytest.mark.parametrize("case", DGRAD_CASES, ids=[str(c) for c in DGRAD_CASES])
+def test_conv_dgrad_and_wgrad(ctx, case):
+    from rtpose_b200 import ops
+    from rtpose_b200.p8 import P8
+    N, Cin, Cout, grid, k, stride = case
+    x = rnd(N, Cin, *grid, seed=6).requires_grad_(True)
+    w = rnd(Cout, Cin, k, k, k, seed=7, scale=(Cin * k ** 3) ** -0.5).requires_grad_(True)
+    y = F.conv3d(x, w, None, stride=stride, padding=k // 2)
+    dy = rnd(*y.shape, seed=8)
+    y.backward(dy)
+    # dgrad, with ReLU mask and accumulate variants
+    dyp = to_p8(dy)
+    dx = P8(N, Cin, *grid)
+    ops.conv_dgrad(ctx, dyp, w.detach().cuda(), stride, dx)
+    torch.cuda.synchronize()
+    close(dx.to_ncdhw(), x.grad, what="dgrad")
+    mask = rnd(N, Cin, *grid, seed=9)
+    base = rnd(N, Cin, *grid, seed=10)
+    dx2 = to_p8(base)
+    ops.conv_dgrad(ctx, dyp, w.detach().cuda(), stride, dx2, mask=to_p8(mask), accumulate=True)
+    torch.cuda.synchronize()
+    close(dx2.to_ncdhw(), base + x.grad * (mask > 0), tol=2 * BF16_ULP, what="dgrad mask+acc")
+    # wgrad
+    dW = torch.full(w.shape, 7.0, device="cuda")
+    ops.conv_wgrad(to_p8(x.detach()), dyp, k, stride, dW)
+    torch.cuda.synchronize()
+    close(dW, w.grad, tol=2e-3, what="wgrad")
+    ops.conv_wgrad(to_p8(x.detach()), dyp, k, stride, dW, accumulate=True)
+    torch.cuda.synchronize()
+    close(dW, 2 * w.grad, tol=2e-3, what="wgrad accumulate")
+
+
+def test_wgrad_channel_slices(ctx):
+    """final-conv style input-channel slices and merged-head style output-channel offsets"""
+    from rtpose_b200 import ops
+    x = rnd(2, 32, 3, 6, 8, seed=11)
+    dy = rnd(2, 64, 3, 6, 8, seed=12)
+    w = torch.zeros(64, 32, 3, 3, 3, requires_grad=True)
+    F.conv3d(x, w, padding=1).backward(dy)
+    g_lo = torch.zeros(32, 32, 3, 3, 3, device="cuda")
+    g_hi = torch.zeros(32, 32, 3, 3, 3, device="cuda")
+    ops.conv_wgrad(to_p8(x), to_p8(dy), 3, 1, g_lo, n0=0, more=((g_hi, False, 0, 32),))
+    torch.cuda.synchronize()
+    close(g_lo, w.grad[:32], tol=2e-3, what="wgrad n0=0")
+    close(g_hi, w.grad[32:], tol=2e-3, what="wgrad n0=32")
+    big = torch.zeros(64, 96, 3, 3, 3, device="cuda")
+    ops.conv_wgrad(to_p8(x), to_p8(dy), 3, 1, big, ci0=64)
+    torch.cuda.synchronize()
+    close(big[:, 64:], w.grad, tol=2e-3, what="wgrad ci0")
+    assert big[:, :64].abs().max().item() == 0
+
+
+@pytest.mark.parametrize("C,grid", [(32, (4, 10, 12)), (64, (2, 5, 7)), (128, (2, 4, 6))])
+def test_groupnorm_fwd_bwd(C, grid):
+    from rtpose_b200 import ops
+    from rtpose_b200.p8 import P8
+    N, G = 2, 8
+    x = (rnd(N, C, *grid, seed=13) + 0.5).requires_grad_(True)
+    x.data = bf(x.data)
+    gamma = (1 + 0.2 * torch.randn(C)).requires_grad_(True)
+    beta = (0.1 * torch.randn(C)).requires_grad_(True)
+    y = F.group_norm(x, G, gamma, beta, 1e-5)
+    dy = rnd(*y.shape, seed=14)
+    y.backward(dy)
+    xp = to_p8(x.detach())
+    stats = ops.gn_stats(xp, G)
+    xr = x.detach().reshape(N, G, -1)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(stats[..., 0].cpu().numpy(), xr.mean(-1).numpy(), rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(stats[..., 1].cpu().numpy(), (xr.var(-1, unbiased=False) + 1e-5).rsqrt().numpy(), rtol=1e-4)
+    out = ops.gn_apply(xp, G, stats, gamma.detach().cuda(), beta.detach().cuda(), P8(N, C, *grid))
+    torch.cuda.synchronize()
+    close(out.to_ncdhw(), y, what="gn apply")
+    dg = torch.zeros(C, device="cuda")
+    db = torch.zeros(C, device="cuda")
+    dx = P8(N, C, *grid)
+    ops.gn_backward(xp, to_p8(dy), G, stats, gamma.detach().cuda(), dg, db, False, dx, False)
+    torch.cuda.synchronize()
+    close(dx.to_ncdhw(), x.grad, what="gn dx")
+    close(dg, gamma.grad, tol=1e-3, what="gn dgamma")
+    close(db, beta.grad, tol=1e-3, what="gn dbeta")
+    # relu-masked accumulate variant
+    xp.relu_out = True
+    base = rnd(N, C, *grid, seed=15)
+    dx2 = to_p8(base)
+    ops.gn_backward(xp, to_p8(dy), G, stats, gamma.detach().cuda(), dg, db, True, dx2, True)
+    torch.cuda.synchronize()
+    close(dx2.to_ncdhw(), base + x.grad * (x.detach() > 0), tol=2 * BF16_ULP, what="gn dx mask+acc")
+    close(dg, 2 * gamma.grad, tol=1e-3, what="gn dgamma acc")
+
+
+def test_fuse_sum_and_upsample_bwd():
+    from rtpose_b200 import ops
+    from rtpose_b200.p8 import P8
+    N, C = 2, 32
+    hi, l1, l2 = (8, 16, 24), (4, 8, 12), (1, 2, 3)
+    a, b2 = rnd(N, C, *hi, seed=16), rnd(N, C, *hi, seed=17)
+    u1 = rnd(N, C, *l1, seed=18).requires_grad_(True)
+    u2 = rnd(N, C, *l2, seed=19).requires_grad_(True)
+    bias = rnd(C, seed=20)
+    pre = a + b2 + F.interpolate(u1, size=hi, mode="trilinear", align_corners=True) + \
+        F.interpolate(u2, size=hi, mode="trilinear", align_corners=True) + bias.view(1, C, 1, 1, 1)
+    ref = F.relu(pre)
+    out = ops.fuse_sum(P8(N, C, *hi), [to_p8(a), to_p8(b2)], [to_p8(u1.detach()), to_p8(u2.detach())],
+                       bias=bias.cuda(), relu=True)
+    torch.cuda.synchronize()
+    close(out.to_ncdhw(), ref, what="fuse_sum")
+    g = rnd(N, C, *hi, seed=21)
+    pre.backward(g)
+    gp = to_p8(g)
+    for u, shape in ((u1, l1), (u2, l2)):
+        d = P8(N, C, *shape)
+        ops.upsample_bwd(gp, d)
+        torch.cuda.synchronize()
+        close(d.to_ncdhw(), u.grad, what="upsample bwd %s" % (shape,))
+        ops.upsample_bwd(gp, d, accumulate=True)
+        torch.cuda.synchronize()
+        close(d.to_ncdhw(), 2 * u.grad, tol=2 * BF16_ULP, what="upsample bwd acc")
+
+
+def test_grad_add_channel_sum_stem():
+    from rtpose_b200 import lib, ops
+    from rtpose_b200.p8 import P8, _stream
+    N, C, grid = 2, 32, (3, 6, 8)
+    s, m, d0 = rnd(N, C, *grid, seed=22), rnd(N, C, *grid, seed=23), rnd(N, C, *grid, seed=24)
+    d = to_p8(d0)
+    ops.grad_add(to_p8(s), d, mask=to_p8(m), accumulate=True)
+    out = torch.zeros(C, device="cuda")
+    ops.channel_sum(to_p8(s), out)
+    torch.cuda.synchronize()
+    close(d.to_ncdhw(), d0 + s * (m > 0), what="grad_add")
+    close(out, s.sum((0, 2, 3, 4)), tol=1e-4, what="channel_sum")
+    # 1 -> C stem
+    x = rnd(N, 1, *grid, seed=25)
+    w, b = rnd(C, 1, 1, 1, 1, seed=26).requires_grad_(True), rnd(C, seed=27).requires_grad_(True)
+    y = F.conv3d(x, w, b)
+    dy = rnd(*y.shape, seed=28)
+    y.backward(dy)
+    xp, yp = to_p8(x), P8(N, C, *grid)
+    wd, bd = w.detach().reshape(-1).cuda(), b.detach().cuda()  # keep alive: raw pointers are passed below
+    lib.call("rtp_stem_fwd", xp.struct(), wd.data_ptr(), bd.data_ptr(), C, yp.struct(), _stream())
+    gw, gb = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+    dyp = to_p8(dy)
+    lib.call("rtp_stem_bwd", xp.struct(), dyp.struct(), C, gw.data_ptr(), gb.data_ptr(), 0,
+             ops.gn_ws(yp).data_ptr(), _stream())
+    torch.cuda.synchronize()
+    close(yp.to_ncdhw(), y, what="stem fwd")
+    close(gw, w.grad.reshape(-1), tol=1e-3, what="stem dw")
+    close(gb, b.grad, tol=1e-3, what="stem db")
+
+
+def test_ingest_matches_oracle():
+    from oracle import hrpose_oracle as O
+    from rtpose_b200 import lib
+    from rtpose_b200.p8 import P8, _stream
+    rs = np.random.RandomState(3)
+    raw = rs.uniform(-2, 12, size=(2, 16, 32, 128, 256)).astype(np.float16)
+    ref = np.stack([O.ingest_cube(raw[n], (0.0, 10.0)) for n in range(2)])
+    rawd = torch.from_numpy(raw).cuda()
+    keep = []
+    dst = P8(2, 16, 16, 64, 160)
+    f32 = torch.empty((2, 16, 16, 64, 160), dtype=torch.float32, device="cuda")
+    z0, _, y0, _, x0, _ = O.ROI_IDX
+    lib.call("rtp_ingest_pack", rawd.data_ptr(), 2, 16, 32, 128, 256, z0, y0, x0, 0.0, 10.0, 1, dst.struct(),
+             f32.data_ptr(), _stream())
+    torch.cuda.synchronize()
+    assert np.array_equal(f32.cpu().numpy(), ref), "fp32 side output must be bit-identical to numpy"
+    assert torch.equal(dst.to_ncdhw().cpu(), bf(torch.from_numpy(ref)))
+    # single-channel 'zyx_real' cube and the crop-only phase variant
+    one = rs.uniform(140000, 210000, size=(1, 1, 32, 128, 256)).astype(np.float16)
+    d1 = P8(1, 1, 16, 64, 160)
+    keep.append(torch.from_numpy(one).cuda())
+    lib.call("rtp_ingest_pack", keep[-1].data_ptr(), 1, 1, 32, 128, 256, z0, y0, x0, 150000.0,
+             50000.0, 1, d1.struct(), None, _stream())
+    torch.cuda.synchronize()
+    assert torch.equal(d1.to_ncdhw().cpu(), bf(torch.from_numpy(O.ingest_cube(one[0, 0], (150000.0, 200000.0))[None])))
+    ph = rs.uniform(-1, 1, size=(1, 2, 4, 32, 128, 256)).astype(np.float16)
+    d2 = P8(1, 8, 16, 64, 160)
+    keep.append(torch.from_numpy(ph).cuda())
+    lib.call("rtp_ingest_pack", keep[-1].data_ptr(), 1, 8, 32, 128, 256, z0, y0, x0, 0.0, 1.0, 0,
+             d2.struct(), None, _stream())
+    torch.cuda.synchronize()
+    assert torch.equal(d2.to_ncdhw().cpu(), bf(torch.from_numpy(O.ingest_cube_phase(ph[0])[None])))
+
+
+@pytest.mark.parametrize("one_hm", [True, False])
+def test_head_loss_and_decode(one_hm):
+    from oracle import hrpose_oracle as O
+    from rtpose_b200.engine import Engine
+    grid, N = (8, 16, 24), 3
+    ncls, R = (1, 45) if one_hm else (15, 3)
+    rs = np.random.RandomState(5)
+    poses = [O.synth_pose(rs, grid) for _ in range(N)]
+    tgt = O.batch_targets(poses, grid, one_hm)
+    hm = (rnd(N, ncls, *grid, seed=30) * 0.5 - 2.0).requires_grad_(True)
+    hm.data = bf(hm.data)
+    reg = rnd(N, R, *grid, seed=31).requires_grad_(True)
+    cw = [1.0] * 45 if one_hm else [1.0, 1.5, 2.0]
+    L = O.head_loss({"hm": hm, "reg": reg}, tgt, 0.5, cw)
+    L["loss"].backward()
+    eng = Engine("hr_tiny_feat32_zyx_l4_in32", "top", {}, R, ncls, 0.5, cw)
+    eng.begin()
+    hp, rp = to_p8(hm.detach()), to_p8(reg.detach())
+    out = eng.loss(hp, rp, tgt["hm"].cuda(), tgt["ind"].cuda(), tgt["mask"].cuda(), tgt["cat"].cuda(),
+                   tgt["anno_pose"].cuda())
+    torch.cuda.synchronize()
+    o = out.cpu()
+    assert abs(o[0].item() - L["loss"].item()) <= 1e-4 * abs(L["loss"].item())
+    assert abs(o[1].item() - L["hm_loss"].item()) <= 1e-4 * abs(L["hm_loss"].item())
+    assert abs(o[2].item() - L["loc_loss"].item()) <= 1e-4 * abs(L["loc_loss"].item()) + 1e-6
+    assert o[3].item() == L["num_positive"].item()
+    np.testing.assert_allclose(o[4:].numpy(), L["loc_loss_elem"].detach().numpy(), rtol=1e-4, atol=1e-6)
+    close(hp.grad.to_ncdhw(), hm.grad, tol=2 * BF16_ULP, what="d loss / d hm")
+    close(rp.grad.to_ncdhw(), reg.grad, tol=2 * BF16_ULP, what="d loss / d reg")
+    # decode: indices bit-exact against the oracle run on the same bf16 heatmap / regression maps
+    idx, score, xyz = eng.decode(hp, to_p8(bf(reg.detach())), O.VOXEL_SIZE, O.PC_RANGE)
+    torch.cuda.synchronize()
+    kps, ref_idx = O.decode(hm.detach(), bf(reg.detach()))
+    assert idx.cpu().tolist() == ref_idx
+    for n in range(N):
+        for j, kp in enumerate(kps[n]):
+            c = kp[0] if not one_hm else 0
+            got = xyz[n, c, 3 * (j if one_hm else 0):3 * (j if one_hm else 0) + 3].cpu().numpy()
+            np.testing.assert_allclose(got, np.array(kp[1:4], dtype=np.float32), rtol=1e-6, atol=1e-6)
+            assert abs(score[n, c].item() - kp[4]) <= 1e-6
+
+
+def test_decode_tie_breaks_to_lowest_reference_index():
+    from rtpose_b200.engine import Engine
+    grid, N = (4, 6, 10), 2
+    hm = torch.full((N, 1, *grid), -3.0)
+    Z, Y, X = grid
+    # equal maxima at several voxels: reference flat index z*Y*X + y*X + x must pick the lowest
+    for (z, y, x) in [(3, 1, 2), (1, 5, 9), (1, 2, 7), (2, 0, 0)]:
+        hm[0, 0, z, y, x] = 1.5
+    hm[1, 0, 0, 0, 3] = 0.25
+    hm[1, 0, 0, 0, 4] = 0.25
+    reg = torch.zeros(N, 45, *grid)
+    eng = Engine("hr_tiny_feat32_zyx_l4_in32", "top", {}, 45, 1, 0.5, [1.0] * 45)
+    idx, _, _ = eng.decode(to_p8(hm), to_p8(reg), (1, 1, 1), (0, 0, 0))
+    torch.cuda.synchronize()
+    assert idx.cpu().flatten().tolist() == [1 * Y * X + 2 * X + 7, 3]
+    assert idx.cpu().flatten().tolist() == [int(torch.argmax(torch.sigmoid(hm[n, 0]).flatten())) for n in range(N)]
