@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""bench.py — radar frames/s of the HRRadarPose forward+backward hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--cfg hr3d_one_hm_doppler]
+
+A "step" = one pass of the hot path over one batch of synthetic radar cubes: raw fp16 cube (resident in HBM) ->
+ingest (ROI crop / normalise / clamp / channel pack) -> HRNet3D backbone -> CenterHead -> focal + L1 loss ->
+backward (all parameter gradients) [-> NCCL all-reduce of the flat gradient buffer when N > 1].
+Prints ONE JSON line (rank 0).  See DESIGN.md §Measurement for every field.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+RAW_SHAPE = (32, 128, 256)  # z, y, x of the on-disk cube (cruw_pose.py:38-40)
+ROI0 = (13, 32, 17)         # z0, y0, x0 of roi1 -> 16 x 64 x 160
+GRID = (16, 64, 160)
+CFGS = {
+    # name: (arch, final_in, final_out, fuse, reg, ncls, weight, in_ch, norm(a, b), fwd GFLOP/frame)
+    "hr3d": ("hr_tiny_feat32_zyx_l4", 32, 32, "top", 3, 15, 0.2, 1, (150000.0, 200000.0), 114.92),
+    "hr3d_one_hm": ("hr_tiny_feat32_zyx_l4", 192, 128, "conat_conv", 45, 1, 0.5, 1, (150000.0, 200000.0), 185.25),
+    "hr3d_one_hm_doppler": ("hr_tiny_feat32_zyx_l4_in32", 192, 128, "conat_conv", 45, 1, 0.5, 32, (0.0, 10.0), 185.24),
+    "hr3d_one_hm_doppler_phase": ("hr_tiny_feat64_zyx_l4_in64", 384, 256, "conat_conv", 45, 1, 0.7, 64, None, 556.95),
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d["bf16_tflops"], d.get("bf16_tflops_sustained", d["bf16_tflops"]), d["hbm_gbs"], "measured"
+    return 1590.0, 1400.0, 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi SM clocks / throttle reasons while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                r = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                   capture_output=True, text=True, timeout=5)
+                if r.returncode == 0 and r.stdout.strip():
+                    self.rows.append([c.strip() for c in r.stdout.strip().split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.rows[0][1]) if self.rows[0][1].isdigit() else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def run_reference(args, rank, world):
+    """The reference's own CPU implementation of the path (oracle port: same ATen ops, fp32, all host threads) on a
+    bounded sample: batch 1 forward+backward per step at the full 16x64x160 grid."""
+    if rank != 0:
+        return
+    from oracle import hrpose_oracle as O
+    from oracle import make_golden as G
+    cfg = args.cfg
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    x, poses, tgt = G.make_example(cfg, 1, GRID, seed=1234)
+    sd = {k: v.requires_grad_(True) for k, v in O.synth_state_dict(cfg).items()}
+    xt = torch.from_numpy(x)
+
+    def step():
+        for v in sd.values():
+            v.grad = None
+        L = O.forward_loss(xt, sd, cfg, tgt)
+        L["loss"].backward()
+        return float(L["loss"])
+
+    for _ in range(max(1, min(args.warmup, 1))):
+        step()
+    steps = max(1, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    val = 1.0 / dt
+    line = {"impl": "reference", "metric": "radar frames/sec HRRadarPose fwd+bwd", "value": val, "unit": "frames/s",
+            "n_gpus": args.gpus, "steps": steps, "warmup": 1, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "%s fwd+bwd, batch 1 per step on host cores (bounded sample of the batch-16 workload)" % cfg,
+                       "grid": list(GRID)},
+            "cpu_baseline": {"value": val, "unit": "frames/s", "cores": cores, "kind": "port",
+                             "sample": "%d steps x batch 1, fp32, torch CPU ops (same ATen kernels the reference calls)" % steps},
+            "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def build_params(cfg, device):
+    """Random-init parameters of the named architecture in ONE flat fp32 buffer (+ matching flat grad buffer)."""
+    from rtpose_b200 import spec
+    arch, fin, fout, fuse, reg, ncls, weight, in_ch, norm, gf = CFGS[cfg]
+    entries = [("backbone." + n, s, i) for n, s, i in spec.backbone_spec(arch, fin, fout)]
+    heads = {"reg": (reg, 2), "hm": (ncls, 2)}
+    entries += [("pose_head." + n, s, i) for n, s, i in spec.head_spec(fout if fuse != "top" else 32, fout if fuse != "top" else 32, heads)]
+    total = sum(int(np.prod(s)) for _, s, _ in entries)
+    flat = torch.empty(total, dtype=torch.float32, device=device)
+    gflat = torch.zeros(total, dtype=torch.float32, device=device)
+    params, grads, o = {}, {}, 0
+    torch.manual_seed(0)
+    for name, shape, init in entries:
+        n = int(np.prod(shape))
+        params[name] = flat[o:o + n].view(shape)
+        params[name].copy_(spec.init_tensor(shape, init))
+        grads[name] = gflat[o:o + n].view(shape)
+        o += n
+    return params, grads, flat, gflat
+
+
+def run_ours(args, rank, world, local_rank):
+    from rtpose_b200 import lib, ops, targets
+    from rtpose_b200 import dist as rdist
+    from rtpose_b200.engine import Engine
+    from rtpose_b200.p8 import P8, _stream
+    lib.require_device()
+    cfg = args.cfg
+    arch, fin, fout, fuse, reg, ncls, weight, in_ch, norm, gf_fwd = CFGS[cfg]
+    dev = torch.device("cuda", local_rank)
+    B = args.batch
+    params, grads, flat, gflat = build_params(cfg, dev)
+    if world > 1:
+        rdist.broadcast_params([flat])
+    code_w = [1.0] * 45 if reg == 45 else [1.0, 1.5, 2.0]
+    eng = Engine(arch, fuse, params, reg, ncls, weight, code_w)
+
+    # ---- synthetic inputs, resident in HBM: raw = a + (b-a)*u, u ~ U[-0.2, 1)
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    a, b = norm if norm is not None else (0.0, 1.0)
+    D = in_ch
+    raw = (a + (b - a) * (torch.rand((B, D) + RAW_SHAPE, device=dev, generator=g) * 1.2 - 0.2)).to(torch.float16)
+    rs = np.random.RandomState(99 + rank)
+    tg = targets.assign(targets.random_poses(rs, B, GRID), GRID, one_hm=(ncls == 1), min_radius=2 if ncls == 1 else 1)
+    tgt = {k: torch.from_numpy(v).to(dev) for k, v in tg.items()}
+    xin = P8(B, D, *GRID, device=dev)
+
+    def step():
+        lib.call("rtp_ingest_pack", raw.data_ptr(), B, D, RAW_SHAPE[0], RAW_SHAPE[1], RAW_SHAPE[2], ROI0[0], ROI0[1], ROI0[2],
+                 float(a), float(b - a), 1 if norm is not None else 0, xin.struct(), None, _stream())
+        hm, rg = eng.forward(xin, True)
+        out = eng.loss(hm, rg, tgt["hm"], tgt["ind"], tgt["mask"], tgt["cat"], tgt["anno_pose"])
+        eng.backward(grads)
+        if world > 1:
+            rdist.allreduce_flat(gflat, world)
+        return out
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        out = step()
+    barrier()
+    loss0 = float(out[0])
+    if not np.isfinite(loss0):
+        raise RuntimeError("non-finite loss in warm-up: %r" % loss0)
+
+    # ---- timed region: K steps, CUDA events, max over ranks; L2 (126 MB) is flushed by the working set itself
+    #      (one step streams > 10 GB of activations through HBM) — stated in config.l2
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ops.PROFILE = {"_only": {"conv_generic", "conv_k3s1", "wgrad_generic", "wgrad_k3s1"}}
+    lib.launch_count = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        out = step()
+    e1.record()
+    barrier()
+    launches = lib.launch_count
+    prof, ops.PROFILE = ops.PROFILE, None
+    sampler.stop_flag = True
+    ms = e0.elapsed_time(e1) / args.steps
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms = float(t[0])
+    value = world * B / (ms * 1e-3)
+
+    # ---- roofline of the dominant kernel family (most total time among the profiled conv kernels)
+    pk_burst, pk_sust, hbm, src = peaks()
+    fam = {}
+    for key, evs in prof.items():
+        if key == "_only":
+            continue
+        tms = [s.elapsed_time(e) for s, e, _ in evs]
+        fam[key] = (sum(tms), len(tms), sum(f for _, _, f in evs))
+    roof, top = None, []
+    if fam:
+        for key, (tt, n, fl) in sorted(fam.items(), key=lambda kv: -kv[1][0])[:6]:
+            top.append({"kernel": key[0], "cin": key[1], "cout": key[2], "taps": key[3], "launches": n,
+                        "ms_total": round(tt, 3), "tflops": round(fl / (tt * 1e-3) / 1e12, 1)})
+        key, (tt, n, fl) = max(fam.items(), key=lambda kv: kv[1][0])
+        ach = fl / (tt * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "%s Cin=%d Cout=%d taps=%d" % key[:4], "achieved": ach, "peak": pk_sust,
+                "unit": "TFLOP/s", "frac": ach / pk_sust, "frac_of_burst_peak": ach / pk_burst, "peak_source": src + " (sustained)",
+                "avg_launch_ms": tt / n, "share_of_step": tt / (ms * args.steps), "traffic": None}
+
+    line = {"metric": "radar frames/sec HRRadarPose fwd+bwd", "value": value, "unit": "frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "%s training fwd+bwd, batch %d per GPU, raw fp16 cube [%d,32,128,256] -> ingest -> "
+                                   "HRNet3D -> CenterHead -> loss -> backward" % (cfg, B, D),
+                       "per_gpu_batch": B, "global_batch": B * world, "grid": list(GRID), "parallelism": "dp%d" % world,
+                       "l2": "inputs+activations per step >> 126 MB L2 (no explicit flush needed)",
+                       "optimizer": "not in the metric (fwd+bwd); gradients all-reduced when N>1"},
+            "model_tflops": 3 * gf_fwd * 1e9 * value / 1e12, "model_flops_frac_of_peak": 3 * gf_fwd * 1e9 * value / 1e12 / world / pk_sust,
+            "loss": float(out[0]), "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roof, "top_kernels": top}
+
+    if rank == 0 and world == 1 and not args.no_extras:
+        line["e2e"] = e2e_public_api(args, dev)
+        line["cpu_baseline"] = cpu_baseline(args)
+        try:
+            line["inference"] = inference_bench(args, eng, dev)
+        except Exception as ex:  # extras must never take the headline down
+            line["inference"] = {"error": repr(ex)}
+    elif rank == 0:
+        line["e2e"] = {"value": None, "unit": "frames/s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": None,
+                       "note": "measured at N=1 only"}
+    if rank == 0:
+        print(json.dumps(line))
+
+
+def e2e_public_api(args, dev):
+    """Same metric through the reference-facing API (build_detector -> model(example) -> loss.backward()) with HOST
+    buffers: per step the fp32 rdr_tensor + targets go pinned-host -> device and the loss comes back."""
+    from rtpose_b200 import det3d_compat as D
+    from rtpose_b200 import targets
+    cfg = args.cfg
+    arch, fin, fout, fuse, reg, ncls, weight, in_ch, norm, _ = CFGS[cfg]
+    B = args.batch
+    names = ["Pelvis", "Right_Hip", "Right_Knee", "Right_Ankle", "Left_Hip", "Left_Knee", "Left_Ankle", "Thomx", "Head",
+             "Left_Shoulder", "Left_Elbow", "Left_Wrist", "Right_Shoulder", "Right_Elbow", "Right_Wrist"]
+    head_in = fout if fuse != "top" else 32
+    model_cfg = dict(type="RadarPoseNet", pretrained=None, reader=dict(type="RadarFeatureNet"),
+                     backbone=dict(type="HRNet3D", backbone_cfg=arch, final_conv_in=fin, final_conv_out=fout, final_fuse=fuse, ds_factor=1),
+                     pose_head=dict(type="CenterHead", tasks=[dict(num_class=ncls, class_names=names[:ncls])], in_channels=head_in,
+                                    share_conv_channel=head_in, dataset="cruw_pose", weight=weight,
+                                    code_weights=[1.0] * 45 if reg == 45 else [1.0, 1.5, 2.0], common_heads={"reg": (reg, 2)}, dcn_head=False),
+                     neck=None)
+    torch.manual_seed(0)
+    model = D.build_detector(model_cfg, train_cfg=None, test_cfg=None).to(dev)
+    model.pose_head.sync_free_losses = True
+    rs = np.random.RandomState(7)
+    x_host = torch.from_numpy(np.maximum(rs.uniform(-0.2, 1.0, (B, in_ch) + GRID), 0).astype(np.float32)).pin_memory()
+    tg = targets.assign(targets.random_poses(rs, B, GRID), GRID, one_hm=(ncls == 1), min_radius=2 if ncls == 1 else 1)
+    t_host = {k: torch.from_numpy(v).pin_memory() for k, v in tg.items()}
+    h2d = x_host.numel() * 4 + sum(v.numel() * v.element_size() for v in t_host.values())
+
+    def step():
+        ex = {"rdr": {"rdr_tensor": x_host.to(dev, non_blocking=True)}, "meta": [{}] * B}
+        for k, v in t_host.items():
+            ex["rdr"][k] = [v.to(dev, non_blocking=True)]
+        for p in model.parameters():
+            p.grad = None
+        losses = model(ex, return_loss=True)
+        losses["loss"][0].backward()
+        return float(losses["loss"][0].detach().cpu())  # D2H read of the step's result
+
+    for _ in range(max(3, min(args.warmup, 3))):
+        step()
+    torch.cuda.synchronize()
+    steps = max(3, min(args.steps, 10))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"value": B / (ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
+            "ms_per_step": ms, "api": "det3d_compat.build_detector(...)(example, return_loss=True); loss.backward()"}
+
+
+def cpu_baseline(args):
+    """Oracle port on the box's host cores: bounded sample (batch 1 fwd+bwd, full grid)."""
+    from oracle import hrpose_oracle as O
+    from oracle import make_golden as G
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    x, poses, tgt = G.make_example(args.cfg, 1, GRID, seed=1234)
+    sd = {k: v.requires_grad_(True) for k, v in O.synth_state_dict(args.cfg).items()}
+    xt = torch.from_numpy(x)
+    times = []
+    for i in range(4):
+        for v in sd.values():
+            v.grad = None
+        t0 = time.perf_counter()
+        O.forward_loss(xt, sd, args.cfg, tgt)["loss"].backward()
+        times.append(time.perf_counter() - t0)
+    dt = float(np.median(times[1:]))
+    return {"value": 1.0 / dt, "unit": "frames/s", "cores": cores, "kind": "port",
+            "sample": "batch 1 fwd+bwd at 16x64x160, fp32, 1 warm-up + median of 3 (torch CPU ops, %d threads)" % cores}
+
+
+def inference_bench(args, eng, dev):
+    """BASELINE.json configs[1]: inference batch 32 incl. keypoint decode (reported beside the headline)."""
+    from rtpose_b200 import lib
+    from rtpose_b200.p8 import P8, _stream
+    arch, fin, fout, fuse, reg, ncls, weight, in_ch, norm, _ = CFGS[args.cfg]
+    B = 32
+    g = torch.Generator(device=dev).manual_seed(5)
+    a, b = norm if norm is not None else (0.0, 1.0)
+    raw = (a + (b - a) * (torch.rand((B, in_ch) + RAW_SHAPE, device=dev, generator=g) * 1.2 - 0.2)).to(torch.float16)
+    xin = P8(B, in_ch, *GRID, device=dev)
+
+    def step():
+        lib.call("rtp_ingest_pack", raw.data_ptr(), B, in_ch, RAW_SHAPE[0], RAW_SHAPE[1], RAW_SHAPE[2], ROI0[0], ROI0[1], ROI0[2],
+                 float(a), float(b - a), 1 if norm is not None else 0, xin.struct(), None, _stream())
+        hm, rg = eng.forward(xin, False)
+        return eng.decode(hm, rg, (0.0453125, 0.15703125, 0.3625), (0.7703125, -5.025, -1.0875))
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        idx, score, xyz = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    return {"value": B / (ms * 1e-3), "unit": "frames/s", "batch": B, "ms_per_step": ms, "includes": "ingest + forward + arg-max decode"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cfg", default="hr3d_one_hm_doppler", choices=sorted(CFGS))
+    ap.add_argument("--batch", type=int, default=16, help="frames per GPU per step")
+    ap.add_argument("--no-extras", action="store_true", help="skip e2e / cpu_baseline / inference legs")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -128,5 +128,17 @@ def require_device():
         raise RtpError("rtpose_b200 kernels are built for sm_100a only; current device is not compute capability 10.x")
 
 
+# kernels launched per C-ABI call (for the bench's `gpu_launches` claim)
+LAUNCHES = {"rtp_pack_ncdhw": 1, "rtp_unpack_ncdhw": 1, "rtp_ingest_pack": 1, "rtp_weight_pack": 1,
+            "rtp_weight_pack_k3s1": 1, "rtp_conv": 1, "rtp_conv_k3s1": 1, "rtp_wgrad": 1, "rtp_wgrad_reduce": 1,
+            "rtp_gn_sums": 2, "rtp_gn_finalize": 1, "rtp_gn_apply": 1, "rtp_gn_bwd_reduce": 2, "rtp_gn_bwd_apply": 2,
+            "rtp_fuse_sum": 1, "rtp_upsample_bwd": 1, "rtp_grad_add": 1, "rtp_channel_sum": 2, "rtp_stem_fwd": 1,
+            "rtp_stem_bwd": 2, "rtp_head_loss": 2, "rtp_decode": 1, "rtp_scale_f32": 1, "rtp_dcn_fwd": 1,
+            "rtp_dcn_bwd_input": 1, "rtp_dcn_bwd_weight": 1}
+launch_count = 0
+
+
 def call(name, *args):
+    global launch_count
+    launch_count += LAUNCHES.get(name, 1)
     check(getattr(load(), name)(*args), name)

@@ -114,10 +114,30 @@ class PackedWeights:
         return val
 
 
+# ------------------------------------------------------------------------------------------------ profiling hook
+PROFILE = None  # when a dict: key -> list of (start_event, end_event, algorithmic_flops); used by bench.py
+
+
+def _prof_begin(key):
+    if PROFILE is None or (PROFILE.get("_only") and key[0] not in PROFILE["_only"]):
+        return None
+    ev = torch.cuda.Event(enable_timing=True)
+    ev.record()
+    return ev
+
+
+def _prof_end(key, ev, flops):
+    if ev is None:
+        return
+    end = torch.cuda.Event(enable_timing=True)
+    end.record()
+    PROFILE.setdefault(key, []).append((ev, end, flops))
+
+
 # ------------------------------------------------------------------------------------------------ conv
 def conv(x, wpack, KP, NP, out, taps, rows, IS=1, OS=1, off=(0, 0, 0), bias=None, res=None, mask=None, relu=False,
-         accumulate=False):
-    """Generic tcgen05 implicit-GEMM conv (rtp_conv).  rows = (RZ, RX, RY)."""
+         accumulate=False, real=None):
+    """Generic tcgen05 implicit-GEMM conv (rtp_conv).  rows = (RZ, RX, RY).  real = (Cin, Cout) for FLOP accounting."""
     d = lib.ConvDesc()
     d.inp, d.out = x.struct(), out.struct()
     d.res = res.struct() if res is not None else lib.NULL_P8
@@ -130,7 +150,11 @@ def conv(x, wpack, KP, NP, out, taps, rows, IS=1, OS=1, off=(0, 0, 0), bias=None
     d.IS, d.OS = IS, OS
     d.oz0, d.ox0, d.oy0 = off
     d.relu, d.accumulate = int(relu), int(accumulate)
+    rc = real or (KP, NP)
+    key = ("conv_generic", rc[0], rc[1], len(taps), IS, OS, rows)
+    ev = _prof_begin(key)
     lib.call("rtp_conv", C.byref(d), _stream())
+    _prof_end(key, ev, 2.0 * x.N * rows[0] * rows[1] * rows[2] * rc[0] * rc[1] * len(taps))
     return out
 
 
@@ -153,15 +177,16 @@ def conv_forward(packs, x, w, stride, out, bias=None, relu=False, res=None, ci0=
     k = w.shape[2]
     wp, KP, NP = packs.get(w, 0, ci0, ci_n, key, version)
     return conv(x, wp, KP, NP, out, taps_fwd(k), (out.Z, out.X, out.Y), IS=stride, bias=pad_bias(bias, NP), res=res,
-                relu=relu)
+                relu=relu, real=(ci_n if ci_n is not None else w.shape[1], w.shape[0]))
 
 
 def conv_dgrad(packs, dy, w, stride, dx, mask=None, accumulate=False, ci0=0, ci_n=None, key=None, version=None):
     """dx (=|+=) conv_transpose(dy, w) [* (mask > 0)]; dx has the forward input's geometry."""
     k = w.shape[2]
     wp, KP, NP = packs.get(w, 1, ci0, ci_n, key, version)
+    real = (w.shape[0], ci_n if ci_n is not None else w.shape[1])
     if stride == 1:
-        return conv(dy, wp, KP, NP, dx, taps_dgrad_s1(k), (dx.Z, dx.X, dx.Y), mask=mask, accumulate=accumulate)
+        return conv(dy, wp, KP, NP, dx, taps_dgrad_s1(k), (dx.Z, dx.X, dx.Y), mask=mask, accumulate=accumulate, real=real)
     assert stride == 2 and k == 3
     for pz in range(2):
         for px in range(2):
@@ -170,7 +195,7 @@ def conv_dgrad(packs, dy, w, stride, dx, mask=None, accumulate=False, ci0=0, ci_
                 if min(rows) <= 0:
                     continue
                 conv(dy, wp, KP, NP, dx, taps_dgrad_s2(pz, px, py), rows, IS=1, OS=2, off=(pz, px, py), mask=mask,
-                     accumulate=accumulate)
+                     accumulate=accumulate, real=real)
     return dx
 
 
@@ -207,7 +232,10 @@ def conv_wgrad(x, dy, k, stride, dW, accumulate=False, ci0=0, n0=0, more=()):
     d.nsplit = nsplit
     ws = workspace(lib.load().rtp_wgrad_workspace_bytes(Cin8, NP, len(taps), nsplit), x.buf.device, "wgrad")
     d.workspace = ws.data_ptr()
+    key = ("wgrad_generic", ci_n, dy.C, len(taps), stride, 1, (dy.Z, dy.X, dy.Y))
+    ev = _prof_begin(key)
     lib.call("rtp_wgrad", C.byref(d), _stream())
+    _prof_end(key, ev, 2.0 * rows * ci_n * dy.C * len(taps))
     for gw, acc, c0, nn in ((dW, accumulate, ci0, n0),) + tuple(more):
         assert gw.is_contiguous()
         lib.call("rtp_wgrad_reduce", ws.data_ptr(), nsplit, Cin8, NP, len(taps), gw.data_ptr(), gw.shape[1], gw.shape[0],
