@@ -165,6 +165,7 @@ def run_ours(args, rank, world, local_rank):
     def step():
         lib.call("rtp_ingest_pack", raw.data_ptr(), B, D, RAW_SHAPE[0], RAW_SHAPE[1], RAW_SHAPE[2], ROI0[0], ROI0[1], ROI0[2],
                  float(a), float(b - a), 1 if norm is not None else 0, xin.struct(), None, _stream())
+        eng.packs.invalidate()  # weights change every optimizer step: repack inside the timed region
         hm, rg = eng.forward(xin, True)
         out = eng.loss(hm, rg, tgt["hm"], tgt["ind"], tgt["mask"], tgt["cat"], tgt["anno_pose"])
         eng.backward(grads)

@@ -101,7 +101,8 @@ int rtp_conv(const rtp_conv_desc* d, void* stream);
 /* Plane-streaming 3x3x3 stride-1 conv (the dominant shape): the z-taps are stacked into GEMM N
  * (N = 3*NPo), accumulators for all output planes stay resident in TMEM, input planes are streamed once
  * through shared memory by 1-D bulk async copies; same epilogue options as rtp_conv.
- * w: packed by rtp_weight_pack_k3s1.  Requires Z*NPo <= 512, Cin % 16 == 0, NPo in {16,32}. */
+ * w: packed by rtp_weight_pack_k3s1.  Cin % 16 == 0 (Cin <= 32 or a multiple of 32), NPo in {16..80}; outputs are
+ * processed in z-chunks of 512/NPo planes.  gn_sums is reserved (must be NULL in this version). */
 int rtp_weight_pack_k3s1(const float* w, void* dst_bf16, int32_t Cout, int32_t Cin, int32_t KP, int32_t NPo,
                          int32_t transpose_flip, void* stream);
 typedef struct {
@@ -114,7 +115,9 @@ typedef struct {
                      bf16 result, accumulated with atomics (feeds the next GroupNorm); NULL = off */
 } rtp_conv_k3s1_desc;
 int rtp_conv_k3s1(const rtp_conv_k3s1_desc* d, void* stream);
-int64_t rtp_conv_k3s1_smem_bytes(int32_t Cin, int32_t NPo, int32_t Y);
+/* dynamic shared memory the kernel would use for this shape, or -1 when the shape is not supported (callers
+ * then use rtp_conv) */
+int64_t rtp_conv_k3s1_smem_bytes(int32_t Cin, int32_t NPo, int32_t Z, int32_t X, int32_t Y);
 
 /* ---- weight gradient ---------------------------------------------------------------------------------------
  * replaces: cuDNN wgrad inside autograd's convolution_backward for the same call sites.
@@ -175,8 +178,10 @@ typedef struct {
   int32_t relu;
 } rtp_fuse_desc;
 int rtp_fuse_sum(const rtp_fuse_desc* d, void* stream);
-/* dlow (=|+=) transpose-of-trilinear-upsample applied to dout (gather form, deterministic) */
-int rtp_upsample_bwd(rtp_p8 dout, rtp_p8 dlow, int32_t C, int32_t accumulate, void* stream);
+/* dlow (=|+=) transpose-of-trilinear-upsample applied to dout, as three separable 1-D gather passes (y, x, z;
+ * deterministic); workspace >= rtp_upsample_bwd_workspace_bytes(dout, dlow, C), 16-byte aligned */
+int64_t rtp_upsample_bwd_workspace_bytes(rtp_p8 dout, rtp_p8 dlow, int32_t C);
+int rtp_upsample_bwd(rtp_p8 dout, rtp_p8 dlow, int32_t C, int32_t accumulate, void* workspace, void* stream);
 /* dst (=|+=) src [* (mask > 0)]   — gradient pass-through of the fuse sum / residual add */
 int rtp_grad_add(rtp_p8 src, rtp_p8 mask, rtp_p8 dst, int32_t C, int32_t accumulate, void* stream);
 /* out[c] = sum over (n, voxels) of x[n][c] (fp32) — bias gradients */

@@ -1,0 +1,353 @@
+// conv_k3s1.cu — plane-streaming 3x3x3 stride-1 pad-1 conv3d (forward, and dgrad with flipped weights) on tcgen05.
+//
+// The dominant shape of HRRadarPose (8 full-resolution 32->32 convs = 39-63 % of the forward FLOPs, plus their
+// dgrads).  Design, following the measurements in profiles/r01_umma_probe.txt:
+//
+//  * UMMA reads its SMEM operands at 128 B/clk/SM, so an N=32 GEMM is capped at ~35 % of the tensor peak.  The three
+//    z-taps are therefore stacked into GEMM N:  B = W[(ky,kx,ci), (kz,co)]  (N = 3*Cout = 96 -> 86 % bound), and the
+//    product of input plane z lands in the TMEM accumulator blocks of output planes z-1, z, z+1, which are laid
+//    out contiguously (block b = 32 columns of plane zo0+b; 16 planes x 32 columns = all 512 TMEM columns).
+//  * In the P8 layout an in-plane tap (ky,kx) is a linear shift, so the A operand of every tap is the SAME
+//    shared-memory stage addressed with a start offset of (kx*Yp + ky)*16 B (SWIZZLE_NONE K-major descriptor):
+//    each input plane is fetched ONCE per tile by 1-D bulk async copies (no im2col, no tensor map, zero padding
+//    comes from the layout's zero ring).
+//  * Persistent CTAs (one per SM) walk (sample, 128-position tile, z-chunk) units.  Warp 0 = bulk-copy producer,
+//    warp 1 = MMA issuer, warps 2-9 = two epilogue groups that drain finished planes (tcgen05.ld -> bias /
+//    residual / ReLU / mask / accumulate -> bf16 stores) while the MMAs of later planes and of the next unit run.
+//  * Wide K (the 128-channel head) is processed in passes of KG channels with double-buffered weight slices; the
+//    accumulators stay in TMEM across passes.
+//
+// Roofline: tensor pipe.  Algorithmic FLOPs per launch = 2 * N*Z*Y*X * Cout * Cin * 27.
+#include "common.cuh"
+#include "tc05.cuh"
+
+using namespace tc05;
+
+namespace {
+
+constexpr int kThreads = 320;  // warp 0 producer, warp 1 MMA, warps 2-5 / 6-9 epilogue groups 0 / 1
+constexpr int kMaxBlocks = 32;
+constexpr int kMaxStages = 8;
+
+struct K3 {
+  P8 in, out, res, mask;
+  const bf16* w;
+  const float* bias;
+  int NPo, N3, out_c8, relu, accumulate, has_res, has_mask;
+  int KG, npass;   // channels per pass, passes (KG * npass == K)
+  int PW;          // stage width in positions: 128 + 2*Yp + 2
+  int ntile;       // 128-position tiles per plane
+  int ZC, nzc;     // output planes per z-chunk, z-chunks
+  int nunits;
+  int nstages;
+  uint32_t stage_bytes, wbuf_bytes, wtap_bytes, wtap_stride;  // per-pass weight slice: 9 copies of wtap_bytes
+};
+
+__global__ void __launch_bounds__(kThreads, 1) conv_k3s1_kernel(const __grid_constant__ K3 p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t bar_full[kMaxStages], bar_empty[kMaxStages], bar_wfull[2], bar_wempty[2];
+  __shared__ uint64_t bar_acc_full[kMaxBlocks], bar_acc_empty[kMaxBlocks];
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int S = p.nstages;
+  const int nwbuf = p.npass > 1 ? 2 : 1;
+  uint8_t* wbuf = smem;
+  uint8_t* stages = smem + (size_t)nwbuf * p.wbuf_bytes;
+  const int Yp = p.in.Yp, Z = p.in.Z;
+  const int kch = p.KG >> 3;
+
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&bar_wfull[s], 1); mbar_init(&bar_wempty[s], 1); }
+    for (int b = 0; b < kMaxBlocks; ++b) { mbar_init(&bar_acc_full[b], 1); mbar_init(&bar_acc_empty[b], 128); }
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc<512>(&tmem_base_s);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_base_s;
+
+  auto decode = [&](int u, int& n, int& zc, int& tile) {
+    tile = u % p.ntile;
+    const int r = u / p.ntile;
+    zc = r % p.nzc;
+    n = r / p.nzc;
+  };
+
+  if (warp == 0) {
+    // ============================================================ producer
+    if (lane == 0) {
+      uint32_t it = 0, wit = 0;
+      bool w_loaded = false;
+      for (int u = blockIdx.x; u < p.nunits; u += gridDim.x) {
+        int n, zc, tile;
+        decode(u, n, zc, tile);
+        const int zo0 = zc * p.ZC, zo1 = min(Z, zo0 + p.ZC);
+        const int iz0 = max(0, zo0 - 1), iz1 = min(Z, zo1 + 1);
+        const int64_t qoff = ((int64_t)tile * 128 - 1) * 8;  // first staged position = q0 - Yp - 1, q0 = Yp + tile*128
+        const bf16* in_n = p.in.ptr + (int64_t)n * p.in.n_stride + qoff;
+        for (int g = 0; g < p.npass; ++g) {
+          if (p.npass > 1 || !w_loaded) {
+            const int wb = wit & 1;
+            mbar_wait(&bar_wempty[wb], ((wit >> 1) & 1) ^ 1);
+            mbar_arrive_expect_tx(&bar_wfull[wb], p.wbuf_bytes);
+            for (int t9 = 0; t9 < 9; ++t9)
+              bulk_g2s(wbuf + (size_t)wb * p.wbuf_bytes + (size_t)t9 * p.wtap_bytes,
+                       reinterpret_cast<const uint8_t*>(p.w) + (size_t)t9 * p.wtap_stride + (size_t)g * p.wtap_bytes,
+                       p.wtap_bytes, &bar_wfull[wb]);
+            ++wit;
+            w_loaded = true;
+          }
+          for (int iz = iz0; iz < iz1; ++iz) {
+            const int s = it % S;
+            mbar_wait(&bar_empty[s], ((it / S) & 1) ^ 1);
+            mbar_arrive_expect_tx(&bar_full[s], p.stage_bytes);
+            uint8_t* dst = stages + (size_t)s * p.stage_bytes;
+            for (int c = 0; c < kch; ++c)
+              bulk_g2s(dst + (size_t)c * p.PW * 16,
+                       in_n + (int64_t)(g * kch + c) * p.in.c_stride + (int64_t)iz * p.in.plane_elems(), p.PW * 16,
+                       &bar_full[s]);
+            ++it;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================================================ MMA issuer
+    if (lane == 0) {
+      uint32_t it = 0, wit = 0, fresh_mask = 0;  // bit b: parity of the number of first-writes to block b so far
+      bool w_ready = false;
+      uint32_t wcur = 0;
+      const uint32_t idesc1 = idesc_bf16(128, p.NPo, 0, 0), idesc2 = idesc_bf16(128, 2 * p.NPo, 0, 0),
+                     idesc3 = idesc_bf16(128, 3 * p.NPo, 0, 0);
+      const uint32_t a_lbo = p.PW * 16, b_lbo = p.N3 * 16;
+      for (int u = blockIdx.x; u < p.nunits; u += gridDim.x) {
+        int n, zc, tile;
+        decode(u, n, zc, tile);
+        const int zo0 = zc * p.ZC, zo1 = min(Z, zo0 + p.ZC);
+        const int iz0 = max(0, zo0 - 1), iz1 = min(Z, zo1 + 1);
+        for (int g = 0; g < p.npass; ++g) {
+          if (p.npass > 1 || !w_ready) {
+            wcur = wit & 1;
+            mbar_wait(&bar_wfull[wcur], (wit >> 1) & 1);
+            w_ready = true;
+          }
+          const uint32_t wbase = smem_u32(wbuf + (size_t)wcur * p.wbuf_bytes);
+          for (int iz = iz0; iz < iz1; ++iz) {
+            const int s = it % S;
+            const int lo = max(iz - 1, zo0), hi = min(iz + 1, zo1 - 1);
+            if (g == 0) {  // blocks written for the first time in this unit must have been drained by the epilogue
+              if (iz + 1 <= hi) {
+                const int b = iz + 1 - zo0;
+                mbar_wait(&bar_acc_empty[b], ((fresh_mask >> b) & 1) ^ 1);
+                fresh_mask ^= 1u << b;
+              }
+              if (iz == 0) {
+                mbar_wait(&bar_acc_empty[0], (fresh_mask & 1) ^ 1);
+                fresh_mask ^= 1u;
+              }
+            }
+            mbar_wait(&bar_full[s], (it / S) & 1);
+            fence_after_sync();
+            const uint32_t abase = smem_u32(stages + (size_t)s * p.stage_bytes);
+            const uint32_t dcol = tmem + (uint32_t)(lo - zo0) * p.NPo;
+            const uint32_t boff = (uint32_t)(lo - (iz - 1)) * p.NPo * 16;
+            const int nblk = hi - lo + 1;
+            const uint32_t idesc = nblk == 3 ? idesc3 : (nblk == 2 ? idesc2 : idesc1);
+            for (int t9 = 0; t9 < 9; ++t9) {
+              const uint32_t ashift = (uint32_t)((t9 / 3) * Yp + (t9 % 3)) * 16;
+              for (int k16 = 0; k16 < (p.KG >> 4); ++k16) {
+                const uint32_t aaddr = abase + ashift + k16 * 2 * a_lbo;
+                const uint32_t baddr = wbase + t9 * p.wtap_bytes + k16 * 2 * b_lbo;
+                if (g == 0 && t9 == 0 && k16 == 0) {
+                  // first touch of this input plane: the block of output plane iz+1 (and plane 0 when iz == 0) is
+                  // fresh and must be overwritten, the others accumulate
+                  if (iz == 0 || lo == iz + 1) {
+                    mma_ss(dcol, smem_desc(aaddr, a_lbo, 128), smem_desc(baddr + boff, b_lbo, 128), idesc, 0u);
+                  } else {
+                    const int nacc = min(iz, hi) - lo + 1;  // iz > hi on the halo plane behind a z-chunk
+                    mma_ss(dcol, smem_desc(aaddr, a_lbo, 128), smem_desc(baddr + boff, b_lbo, 128),
+                           nacc == 2 ? idesc2 : idesc1, 1u);
+                    if (iz + 1 <= hi)
+                      mma_ss(tmem + (uint32_t)(iz + 1 - zo0) * p.NPo, smem_desc(aaddr, a_lbo, 128),
+                             smem_desc(baddr + 2 * p.NPo * 16, b_lbo, 128), idesc1, 0u);
+                  }
+                } else {
+                  mma_ss(dcol, smem_desc(aaddr, a_lbo, 128), smem_desc(baddr + boff, b_lbo, 128), idesc, 1u);
+                }
+              }
+            }
+            mma_commit(&bar_empty[s]);
+            if (g == p.npass - 1) {
+              if (iz - 1 >= zo0) mma_commit(&bar_acc_full[iz - 1 - zo0]);
+              if (iz == Z - 1 && iz < zo1) mma_commit(&bar_acc_full[iz - zo0]);
+            }
+            ++it;
+          }
+          if (p.npass > 1) {
+            mma_commit(&bar_wempty[wcur]);
+            ++wit;
+          }
+        }
+      }
+    }
+  } else {
+    // ============================================================ epilogue groups
+    const int eg = (warp - 2) >> 2;                 // 0 / 1: even / odd accumulator blocks
+    const int lane_q = warp & 3;                    // TMEM lane quarter this warp may access
+    const int r = lane_q * 32 + lane;               // GEMM row
+    const uint32_t trow = tmem + ((uint32_t)(lane_q * 32) << 16);
+    uint32_t full_mask = 0;  // bit b: parity of the number of times block b has been drained so far
+    for (int u = blockIdx.x; u < p.nunits; u += gridDim.x) {
+      int n, zc, tile;
+      decode(u, n, zc, tile);
+      const int zo0 = zc * p.ZC, zo1 = min(Z, zo0 + p.ZC);
+      const int q = Yp + tile * 128 + r;            // in-plane linear position (padded coordinates)
+      const int xp = q / Yp, yp = q - xp * Yp;
+      const bool ok = xp >= 1 && xp <= p.out.X && yp >= 1 && yp <= p.out.Y;
+      const int64_t pos = (int64_t)q * 8;
+      for (int oz = zo0 + eg; oz < zo1; oz += 2) {
+        const int b = oz - zo0;
+        mbar_wait(&bar_acc_full[b], (full_mask >> b) & 1);
+        full_mask ^= 1u << b;
+        fence_after_sync();
+        const int64_t plane = (int64_t)oz * p.out.plane_elems() + pos;
+        bf16* out_row = p.out.ptr + (int64_t)n * p.out.n_stride + plane;
+        const bf16* res_row = p.has_res ? p.res.ptr + (int64_t)n * p.res.n_stride + (int64_t)oz * p.res.plane_elems() + pos : nullptr;
+        const bf16* mask_row = p.has_mask ? p.mask.ptr + (int64_t)n * p.mask.n_stride + (int64_t)oz * p.mask.plane_elems() + pos : nullptr;
+        for (int c16 = 0; c16 * 16 < p.NPo; ++c16) {
+          uint32_t v[16];
+          tmem_ld16(trow + b * p.NPo + c16 * 16, v);
+          tmem_ld_wait();
+          if (c16 * 16 + 16 >= p.NPo) {  // last read of this block: hand it back to the MMA warp
+            fence_before_sync();
+            mbar_arrive(&bar_acc_empty[b]);
+          }
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int ch = c16 * 2 + h;
+            if (ch >= p.out_c8 || !ok) continue;
+            float f[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[h * 8 + i]);
+            if (p.bias) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) f[i] += __ldg(p.bias + ch * 8 + i);
+            }
+            if (res_row) {
+              float g[8];
+              unpack8(ldg16(res_row + ch * p.res.c_stride), g);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) f[i] += g[i];
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
+            }
+            if (mask_row) {
+              float g[8];
+              unpack8(ldg16(mask_row + ch * p.mask.c_stride), g);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) f[i] = g[i] > 0.f ? f[i] : 0.f;
+            }
+            bf16* dst = out_row + ch * p.out.c_stride;
+            if (p.accumulate) {
+              float g[8];
+              unpack8(*reinterpret_cast<const uint4*>(dst), g);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) f[i] += g[i];
+            }
+            stg16(dst, pack8(f));
+          }
+        }
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem);
+}
+
+struct Plan {
+  int KG, npass, PW, ntile, ZC, nzc, nstages;
+  uint32_t stage_bytes, wbuf_bytes;
+  size_t smem;
+  bool ok;
+};
+
+Plan make_plan(int K, int NPo, int Z, int X, int Y) {
+  Plan pl{};
+  pl.ok = false;
+  if (K % 16 != 0 || NPo % 16 != 0 || NPo < 16 || 3 * NPo > 256) return pl;
+  const int N3 = 3 * NPo;
+  int KG = (9 * 32 * N3 * 2 <= 56 * 1024) ? 32 : 16;
+  if (K < KG) KG = K;
+  if (K % KG != 0) return pl;
+  pl.KG = KG;
+  pl.npass = K / KG;
+  const int Yp = Y + 2;
+  pl.PW = 128 + 2 * Yp + 2;
+  pl.ntile = (X * Yp + 127) / 128;
+  pl.ZC = 512 / NPo;
+  if (pl.ZC > kMaxBlocks) pl.ZC = kMaxBlocks;
+  if (pl.ZC > Z) pl.ZC = Z;
+  if (pl.ZC < 2 && Z > 1) return pl;
+  pl.nzc = (Z + pl.ZC - 1) / pl.ZC;
+  pl.stage_bytes = (uint32_t)(KG / 8) * pl.PW * 16;
+  pl.wbuf_bytes = (uint32_t)9 * KG * N3 * 2;
+  const size_t wtotal = (size_t)(pl.npass > 1 ? 2 : 1) * pl.wbuf_bytes;
+  const size_t budget = 220 * 1024;
+  if (wtotal + 2 * (size_t)pl.stage_bytes > budget) return pl;
+  int S = (int)((budget - wtotal) / pl.stage_bytes);
+  if (S > kMaxStages) S = kMaxStages;
+  pl.nstages = S;
+  pl.smem = wtotal + (size_t)S * pl.stage_bytes;
+  pl.ok = true;
+  return pl;
+}
+
+}  // namespace
+
+extern "C" int64_t rtp_conv_k3s1_smem_bytes(int32_t Cin, int32_t NPo, int32_t Z, int32_t X, int32_t Y) {
+  Plan pl = make_plan(Cin, NPo, Z, X, Y);
+  return pl.ok ? (int64_t)pl.smem : -1;
+}
+
+extern "C" int rtp_conv_k3s1(const rtp_conv_k3s1_desc* d, void* stream) {
+  RTP_CHECK_ARG(d && d->in.ptr && d->out.ptr && d->w, "rtp_conv_k3s1: null argument");
+  RTP_CHECK_ARG(d->in.N == d->out.N && d->in.Z == d->out.Z && d->in.X == d->out.X && d->in.Y == d->out.Y,
+                "rtp_conv_k3s1: in/out geometry mismatch");
+  RTP_CHECK_ARG(d->in.C8 * 8 >= d->Cin, "rtp_conv_k3s1: input has %d channels, K=%d", d->in.C8 * 8, d->Cin);
+  RTP_CHECK_ARG(d->out_c8 >= 1 && d->out_c8 * 8 <= d->NPo + 7 && d->out_c8 <= d->out.C8, "rtp_conv_k3s1: bad out_c8");
+  RTP_CHECK_ARG(d->in.c_stride == (int64_t)d->in.Z * (d->in.X + 2) * (d->in.Y + 2) * 8,
+                "rtp_conv_k3s1: input planes must be contiguous per channel chunk");
+  Plan pl = make_plan(d->Cin, d->NPo, d->in.Z, d->in.X, d->in.Y);
+  RTP_CHECK_ARG(pl.ok, "rtp_conv_k3s1: unsupported shape K=%d NPo=%d Z=%d X=%d Y=%d", d->Cin, d->NPo, d->in.Z, d->in.X, d->in.Y);
+  K3 k;
+  k.in = P8(d->in); k.out = P8(d->out); k.res = P8(d->res); k.mask = P8(d->mask);
+  k.w = (const bf16*)d->w; k.bias = d->bias;
+  k.NPo = d->NPo; k.N3 = 3 * d->NPo; k.out_c8 = d->out_c8; k.relu = d->relu; k.accumulate = d->accumulate;
+  k.has_res = d->res.ptr != nullptr; k.has_mask = d->mask.ptr != nullptr;
+  k.KG = pl.KG; k.npass = pl.npass; k.PW = pl.PW; k.ntile = pl.ntile; k.ZC = pl.ZC; k.nzc = pl.nzc;
+  k.nunits = d->in.N * pl.ntile * pl.nzc;
+  k.nstages = pl.nstages; k.stage_bytes = pl.stage_bytes; k.wbuf_bytes = pl.wbuf_bytes;
+  k.wtap_bytes = (uint32_t)(pl.KG / 8) * k.N3 * 16;          // one tap's [KG/8][N3][8] slice
+  k.wtap_stride = (uint32_t)(d->Cin / 8) * k.N3 * 16;        // distance between taps in the packed weights
+  static size_t configured = 0;
+  if (pl.smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_k3s1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+    if (e != cudaSuccess) { rtp_set_error("rtp_conv_k3s1: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+    configured = pl.smem;
+  }
+  static int nsm = 0;
+  if (!nsm) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const int grid = k.nunits < nsm ? k.nunits : nsm;
+  conv_k3s1_kernel<<<grid, kThreads, pl.smem, (cudaStream_t)stream>>>(k);
+  RTP_LAUNCH_CHECK();
+}

@@ -61,8 +61,8 @@ PROTOTYPES = {
     "rtp_weight_pack": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "rtp_conv": (C.c_int, [C.POINTER(ConvDesc), _vp]),
     "rtp_weight_pack_k3s1": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
-    # PENDING "rtp_conv_k3s1": (C.c_int, [C.POINTER(ConvK3S1Desc), _vp]),
-    # PENDING "rtp_conv_k3s1_smem_bytes": (C.c_int64, [_i32, _i32, _i32]),
+    "rtp_conv_k3s1": (C.c_int, [C.POINTER(ConvK3S1Desc), _vp]),
+    "rtp_conv_k3s1_smem_bytes": (C.c_int64, [_i32, _i32, _i32, _i32, _i32]),
     "rtp_wgrad_workspace_bytes": (C.c_int64, [_i32, _i32, _i32, _i32]),
     "rtp_wgrad": (C.c_int, [C.POINTER(WgradDesc), _vp]),
     "rtp_wgrad_reduce": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
@@ -74,7 +74,8 @@ PROTOTYPES = {
     "rtp_gn_bwd_apply": (C.c_int, [P8Struct, P8Struct, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _i32, P8Struct, _i32,
                                    _i32, _vp]),
     "rtp_fuse_sum": (C.c_int, [C.POINTER(FuseDesc), _vp]),
-    "rtp_upsample_bwd": (C.c_int, [P8Struct, P8Struct, _i32, _i32, _vp]),
+    "rtp_upsample_bwd_workspace_bytes": (C.c_int64, [P8Struct, P8Struct, _i32]),
+    "rtp_upsample_bwd": (C.c_int, [P8Struct, P8Struct, _i32, _i32, _vp, _vp]),
     "rtp_grad_add": (C.c_int, [P8Struct, P8Struct, P8Struct, _i32, _i32, _vp]),
     "rtp_channel_sum": (C.c_int, [P8Struct, _i32, _vp, _i32, _vp, _vp]),
     "rtp_stem_fwd": (C.c_int, [P8Struct, _vp, _vp, _i32, P8Struct, _vp]),
@@ -132,7 +133,7 @@ def require_device():
 LAUNCHES = {"rtp_pack_ncdhw": 1, "rtp_unpack_ncdhw": 1, "rtp_ingest_pack": 1, "rtp_weight_pack": 1,
             "rtp_weight_pack_k3s1": 1, "rtp_conv": 1, "rtp_conv_k3s1": 1, "rtp_wgrad": 1, "rtp_wgrad_reduce": 1,
             "rtp_gn_sums": 2, "rtp_gn_finalize": 1, "rtp_gn_apply": 1, "rtp_gn_bwd_reduce": 2, "rtp_gn_bwd_apply": 2,
-            "rtp_fuse_sum": 1, "rtp_upsample_bwd": 1, "rtp_grad_add": 1, "rtp_channel_sum": 2, "rtp_stem_fwd": 1,
+            "rtp_fuse_sum": 1, "rtp_upsample_bwd": 3, "rtp_grad_add": 1, "rtp_channel_sum": 2, "rtp_stem_fwd": 1,
             "rtp_stem_bwd": 2, "rtp_head_loss": 2, "rtp_decode": 1, "rtp_scale_f32": 1, "rtp_dcn_fwd": 1,
             "rtp_dcn_bwd_input": 1, "rtp_dcn_bwd_weight": 1}
 launch_count = 0

@@ -113,6 +113,26 @@ class PackedWeights:
         self.cache[key] = (ver, val)
         return val
 
+    def get_k3s1(self, w, K, NPo, transpose_flip, key=None, version=None):
+        """kz-stacked pack for the plane-streaming kernel: [9][K/8][3*NPo][8]."""
+        key = (key if key is not None else w.data_ptr(), "k3s1", bool(transpose_flip), K, NPo, tuple(w.shape))
+        ver = version if version is not None else w._version
+        hit = self.cache.get(key)
+        if hit is not None and hit[0] == ver:
+            return hit[1]
+        dst = hit[1] if hit is not None else torch.empty(9 * K * 3 * NPo, dtype=torch.bfloat16, device=w.device)
+        wc = w.detach().contiguous()
+        lib.call("rtp_weight_pack_k3s1", wc.data_ptr(), dst.data_ptr(), w.shape[0], w.shape[1], K, NPo,
+                 int(bool(transpose_flip)), _stream())
+        self.cache[key] = (ver, dst)
+        return dst
+
+    def invalidate(self):
+        """Forces a repack on next use (weights are repacked once per optimizer step in training)."""
+        for k in list(self.cache):
+            ver, val = self.cache[k]
+            self.cache[k] = (None, val)
+
 
 # ------------------------------------------------------------------------------------------------ profiling hook
 PROFILE = None  # when a dict: key -> list of (start_event, end_event, algorithmic_flops); used by bench.py
@@ -172,9 +192,44 @@ def out_grid(x, stride):
     return ((x.Z - 1) // stride + 1, (x.Y - 1) // stride + 1, (x.X - 1) // stride + 1) if stride > 1 else x.grid
 
 
+USE_K3S1 = True  # route eligible 3x3x3 stride-1 convs through the plane-streaming kernel (rtp_conv_k3s1)
+
+
+def k3s1_eligible(x, K, NPo):
+    if not USE_K3S1 or x.C8 * 8 != K or x.c_stride != x.Z * (x.X + 2) * (x.Y + 2) * 8:
+        return False
+    return lib.load().rtp_conv_k3s1_smem_bytes(K, NPo, x.Z, x.X, x.Y) > 0
+
+
+def conv_k3s1(packs, x, w, out, transpose_flip, bias=None, relu=False, res=None, mask=None, accumulate=False, key=None,
+              version=None):
+    """Plane-streaming 3x3x3 s1 conv (forward: transpose_flip=False; dgrad: True)."""
+    Cout, Cin = w.shape[0], w.shape[1]
+    K, NPo = (ceil_to(Cin, 16), ceil_to(Cout, 16)) if not transpose_flip else (ceil_to(Cout, 16), ceil_to(Cin, 16))
+    wp = packs.get_k3s1(w, K, NPo, transpose_flip, key, version)
+    d = lib.ConvK3S1Desc()
+    d.inp, d.out = x.struct(), out.struct()
+    d.res = res.struct() if res is not None else lib.NULL_P8
+    d.mask = mask.struct() if mask is not None else lib.NULL_P8
+    d.w = wp.data_ptr()
+    b = pad_bias(bias, NPo)
+    d.bias = b.data_ptr() if b is not None else None
+    d.Cin, d.NPo, d.out_c8 = K, NPo, out.C8
+    d.relu, d.accumulate = int(relu), int(accumulate)
+    d.gn_sums = None
+    pkey = ("conv_k3s1", Cin if not transpose_flip else Cout, Cout if not transpose_flip else Cin, 27, 1, 1,
+            (x.Z, x.X, x.Y))
+    ev = _prof_begin(pkey)
+    lib.call("rtp_conv_k3s1", C.byref(d), _stream())
+    _prof_end(pkey, ev, 2.0 * x.N * x.voxels * Cin * Cout * 27)
+    return out
+
+
 def conv_forward(packs, x, w, stride, out, bias=None, relu=False, res=None, ci0=0, ci_n=None, key=None, version=None):
     """y = conv3d(x[:, ci0:ci0+ci_n], w[:, ci0:ci0+ci_n], stride, padding=k//2) (+bias)(+res)(relu)."""
     k = w.shape[2]
+    if k == 3 and stride == 1 and ci0 == 0 and ci_n is None and k3s1_eligible(x, ceil_to(w.shape[1], 16), ceil_to(w.shape[0], 16)):
+        return conv_k3s1(packs, x, w, out, False, bias=bias, relu=relu, res=res, key=key, version=version)
     wp, KP, NP = packs.get(w, 0, ci0, ci_n, key, version)
     return conv(x, wp, KP, NP, out, taps_fwd(k), (out.Z, out.X, out.Y), IS=stride, bias=pad_bias(bias, NP), res=res,
                 relu=relu, real=(ci_n if ci_n is not None else w.shape[1], w.shape[0]))
@@ -183,6 +238,8 @@ def conv_forward(packs, x, w, stride, out, bias=None, relu=False, res=None, ci0=
 def conv_dgrad(packs, dy, w, stride, dx, mask=None, accumulate=False, ci0=0, ci_n=None, key=None, version=None):
     """dx (=|+=) conv_transpose(dy, w) [* (mask > 0)]; dx has the forward input's geometry."""
     k = w.shape[2]
+    if k == 3 and stride == 1 and ci0 == 0 and ci_n is None and k3s1_eligible(dy, ceil_to(w.shape[0], 16), ceil_to(w.shape[1], 16)):
+        return conv_k3s1(packs, dy, w, dx, True, mask=mask, accumulate=accumulate, key=key, version=version)
     wp, KP, NP = packs.get(w, 1, ci0, ci_n, key, version)
     real = (w.shape[0], ci_n if ci_n is not None else w.shape[1])
     if stride == 1:
@@ -286,7 +343,8 @@ def fuse_sum(out, same, low, bias=None, relu=False):
 
 
 def upsample_bwd(dout, dlow, accumulate=False):
-    lib.call("rtp_upsample_bwd", dout.struct(), dlow.struct(), dlow.C, int(accumulate), _stream())
+    ws = workspace(lib.load().rtp_upsample_bwd_workspace_bytes(dout.struct(), dlow.struct(), dlow.C), dout.buf.device, "upbwd")
+    lib.call("rtp_upsample_bwd", dout.struct(), dlow.struct(), dlow.C, int(accumulate), ws.data_ptr(), _stream())
 
 
 def grad_add(src, dst, mask=None, accumulate=False):

@@ -339,3 +339,72 @@ def test_decode_tie_breaks_to_lowest_reference_index():
     torch.cuda.synchronize()
     assert idx.cpu().flatten().tolist() == [1 * Y * X + 2 * X + 7, 3]
     assert idx.cpu().flatten().tolist() == [int(torch.argmax(torch.sigmoid(hm[n, 0]).flatten())) for n in range(N)]
+
+
+# ------------------------------------------------------------------------------------------------ plane-streaming conv
+K3S1_CASES = [
+    # N, Cin, Cout, grid(Z,Y,X), bias, relu, res
+    (2, 32, 32, (16, 30, 20), False, True, True),      # all 16 planes resident, several tiles
+    (1, 32, 32, (16, 64, 160), False, True, False),    # the full-resolution shape (83 tiles)
+    (16, 32, 32, (8, 30, 40), False, False, False),    # 160 units > 148 SMs: persistent loop, block recycling
+    (1, 128, 32, (16, 14, 12), True, True, False),     # wide K: 4 passes, double-buffered weights
+    (2, 32, 45, (16, 10, 12), True, False, False),     # NPo = 48 -> z-chunks of 10 + 6 planes
+    (1, 64, 64, (12, 10, 14), False, False, False),    # NPo = 64 -> z-chunks of 8 + 4
+    (2, 32, 1, (16, 12, 10), True, False, False),      # NPo = 16
+    (1, 16, 32, (3, 9, 7), False, True, False),        # K = 16, odd sizes
+    (1, 64, 32, (1, 8, 8), False, False, False),       # single plane
+]
+
+
+@pytest.mark.parametrize("case", K3S1_CASES, ids=[str(c) for c in K3S1_CASES])
+def test_conv_k3s1_forward_and_dgrad(ctx, case):
+    from rtpose_b200 import ops
+    from rtpose_b200.p8 import P8
+    N, Cin, Cout, grid, use_bias, relu, use_res = case
+    x = rnd(N, Cin, *grid, seed=40).requires_grad_(True)
+    w = rnd(Cout, Cin, 3, 3, 3, seed=41, scale=(Cin * 27) ** -0.5).requires_grad_(True)
+    b = rnd(Cout, seed=42) if use_bias else None
+    pre = F.conv3d(x, w, b, padding=1)
+    res = rnd(*pre.shape, seed=43) if use_res else None
+    ref = pre + res if use_res else pre
+    ref = F.relu(ref) if relu else ref
+    xp = to_p8(x.detach())
+    assert ops.k3s1_eligible(xp, (Cin + 15) // 16 * 16, (Cout + 15) // 16 * 16), "case should take the fast path"
+    out = P8(N, Cout, *grid)
+    wc = w.detach().cuda()
+    ops.conv_forward(ctx, xp, wc, 1, out, bias=b.cuda() if use_bias else None, relu=relu,
+                     res=to_p8(res) if use_res else None)
+    torch.cuda.synchronize()
+    close(out.to_ncdhw(), ref, what="k3s1 fwd")
+    # pads must stay zero
+    full = out.buf[out.offset:out.offset + out.N * out.n_stride].view(out.N, out.C8, out.Z, out.X + 2, out.Y + 2, 8).float()
+    assert full[:, :, :, 0].abs().max().item() == 0 and full[:, :, :, -1].abs().max().item() == 0
+    assert full[:, :, :, :, 0].abs().max().item() == 0 and full[:, :, :, :, -1].abs().max().item() == 0
+    # dgrad through the same kernel (flipped / transposed pack), with mask + accumulate
+    dy = rnd(*pre.shape, seed=44)
+    pre.backward(dy)
+    dyp = to_p8(dy)
+    if ops.k3s1_eligible(dyp, (Cout + 15) // 16 * 16, (Cin + 15) // 16 * 16):
+        dx = P8(N, Cin, *grid)
+        ops.conv_dgrad(ctx, dyp, wc, 1, dx)
+        torch.cuda.synchronize()
+        close(dx.to_ncdhw(), x.grad, what="k3s1 dgrad")
+        mask, base = rnd(N, Cin, *grid, seed=45), rnd(N, Cin, *grid, seed=46)
+        dx2 = to_p8(base)
+        ops.conv_dgrad(ctx, dyp, wc, 1, dx2, mask=to_p8(mask), accumulate=True)
+        torch.cuda.synchronize()
+        close(dx2.to_ncdhw(), base + x.grad * (mask > 0), tol=2 * BF16_ULP, what="k3s1 dgrad mask+acc")
+
+
+def test_generic_path_still_used_when_fast_path_disabled(ctx):
+    from rtpose_b200 import ops
+    from rtpose_b200.p8 import P8
+    x, w = rnd(1, 32, 4, 10, 12, seed=47), rnd(32, 32, 3, 3, 3, seed=48, scale=0.03)
+    ref = F.conv3d(x, w, padding=1)
+    ops.USE_K3S1 = False
+    try:
+        out = ops.conv_forward(ctx, to_p8(x), w.cuda(), 1, P8(1, 32, 4, 10, 12))
+    finally:
+        ops.USE_K3S1 = True
+    torch.cuda.synchronize()
+    close(out.to_ncdhw(), ref, what="generic conv")
