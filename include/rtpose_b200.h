@@ -142,6 +142,19 @@ int rtp_wgrad_reduce(const float* workspace, int32_t nsplit, int32_t Cin8, int32
                      int32_t Cin_total, int32_t co_n, int32_t n0, int32_t ci0, int32_t ci_n, int32_t accumulate,
                      void* stream);
 
+/* Plane-streaming weight gradient for 3x3x3 stride-1 convs with exactly 32 input channels (x: 4 chunks).  The three
+ * z-taps are stacked along GEMM M, the 9 in-plane taps are 9 TMEM-resident accumulators; one persistent CTA per SM
+ * writes an fp32 partial [nsplit][9][128][NP] and rtp_wgrad_k3s1_reduce sums them in a fixed order into
+ * dW[co][ci0+ci][kz][ky][kx] (co < co_n reads dY channel n0+co).  zero_page: >= rtp_wgrad_k3s1_zero_bytes(Y) bytes of
+ * device zeros; workspace: >= rtp_wgrad_k3s1_workspace_bytes(NP, #SMs).  *nsplit_out receives the partial count. */
+int rtp_wgrad_k3s1_supported(int32_t Cin, int32_t NP, int32_t Z, int32_t X, int32_t Y);
+int64_t rtp_wgrad_k3s1_workspace_bytes(int32_t NP, int32_t nsm);
+int64_t rtp_wgrad_k3s1_zero_bytes(int32_t Y);
+int rtp_wgrad_k3s1(rtp_p8 x, rtp_p8 dy, int32_t NP, const void* zero_page, float* workspace, int32_t* nsplit_out,
+                   void* stream);
+int rtp_wgrad_k3s1_reduce(const float* workspace, int32_t nsplit, int32_t NP, float* dW, int32_t Cin_total,
+                          int32_t co_n, int32_t n0, int32_t ci0, int32_t accumulate, void* stream);
+
 /* ---- GroupNorm ---------------------------------------------------------------------------------------------
  * replaces: nn.GroupNorm(8, C) forward/backward — hr_util/common.py:57; hr_util/hr3d.py:83,147,168,184,297,323;
  * center_head.py:85,204.  Statistics are fp32 per (sample, group); eps = 1e-5, biased variance.

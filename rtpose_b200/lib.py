@@ -66,6 +66,11 @@ PROTOTYPES = {
     "rtp_wgrad_workspace_bytes": (C.c_int64, [_i32, _i32, _i32, _i32]),
     "rtp_wgrad": (C.c_int, [C.POINTER(WgradDesc), _vp]),
     "rtp_wgrad_reduce": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "rtp_wgrad_k3s1_supported": (C.c_int, [_i32, _i32, _i32, _i32, _i32]),
+    "rtp_wgrad_k3s1_workspace_bytes": (C.c_int64, [_i32, _i32]),
+    "rtp_wgrad_k3s1_zero_bytes": (C.c_int64, [_i32]),
+    "rtp_wgrad_k3s1": (C.c_int, [P8Struct, P8Struct, _i32, _vp, _vp, C.POINTER(_i32), _vp]),
+    "rtp_wgrad_k3s1_reduce": (C.c_int, [_vp, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "rtp_gn_workspace_bytes": (C.c_int64, [_i32, _i32]),
     "rtp_gn_sums": (C.c_int, [P8Struct, _i32, _vp, _vp, _vp]),
     "rtp_gn_finalize": (C.c_int, [_vp, _i32, _i32, _i32, _i64, _f32, _vp, _vp]),

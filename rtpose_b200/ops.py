@@ -266,9 +266,51 @@ def num_sms():
     return _NSM
 
 
+USE_WGRAD_K3S1 = True
+_zero_pages = {}
+
+
+def _zero_page(nbytes, device):
+    z = _zero_pages.get(str(device))
+    if z is None or z.numel() < nbytes:
+        z = torch.zeros(max(int(nbytes), 16384), dtype=torch.uint8, device=device)
+        _zero_pages[str(device)] = z
+    return z
+
+
+def _wgrad_k3s1(x, dy, outs):
+    """Plane-streaming wgrad: loops 32-channel input groups x (<= 48)-channel dY groups; outs = [(dW, acc, ci0, n0)]."""
+    L = lib.load()
+    dev = x.buf.device
+    zero = _zero_page(L.rtp_wgrad_k3s1_zero_bytes(x.Y), dev)
+    nsplit = C.c_int32(0)
+    for gi in range(x.C // 32):
+        xg = x.channels(gi * 32, 32)
+        for gw, acc, c0, nn in outs:
+            co_total = gw.shape[0]
+            h = 0
+            while h < co_total:
+                hn = (co_total - h) if (co_total - h) <= 48 else 32  # 9 accumulators x NP columns must fit 512
+                dyg = dy.channels(nn + h, hn)
+                NP = ceil_to(hn, 16)
+                ws = workspace(L.rtp_wgrad_k3s1_workspace_bytes(NP, num_sms()), dev, "wgrad3")
+                key = ("wgrad_k3s1", 32, hn, 27, 1, 1, (x.Z, x.X, x.Y))
+                ev = _prof_begin(key)
+                lib.call("rtp_wgrad_k3s1", xg.struct(), dyg.struct(), NP, zero.data_ptr(), ws.data_ptr(), C.byref(nsplit), _stream())
+                _prof_end(key, ev, 2.0 * x.N * x.voxels * 32 * hn * 27)
+                lib.call("rtp_wgrad_k3s1_reduce", ws.data_ptr(), nsplit.value, NP, gw[h:].data_ptr(), gw.shape[1], hn, 0,
+                         c0 + gi * 32, int(acc), _stream())
+                h += hn
+
+
 def conv_wgrad(x, dy, k, stride, dW, accumulate=False, ci0=0, n0=0, more=()):
     """dW[:, ci0:ci0+x.C] (=|+=) wgrad(x, dy[:, n0:n0+dW.shape[0]]).  x: forward input (P8), dy: P8 gradient.
     `more`: further (dW, accumulate, ci0, n0) outputs reduced from the same split-K workspace."""
+    outs = ((dW, accumulate, ci0, n0),) + tuple(more)
+    if (USE_WGRAD_K3S1 and k == 3 and stride == 1 and x.C % 32 == 0 and x.c_stride == x.Z * (x.X + 2) * (x.Y + 2) * 8
+            and dy.c_stride == x.c_stride and all(o[3] % 8 == 0 for o in outs)
+            and lib.load().rtp_wgrad_k3s1_supported(32, 32, x.Z, x.X, x.Y)):
+        return _wgrad_k3s1(x, dy, outs)
     ci_n = x.C
     Cin8 = ceil_to(ci_n, 8)
     NP = ceil_to(dy.C, 16)

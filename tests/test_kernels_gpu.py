@@ -408,3 +408,43 @@ def test_generic_path_still_used_when_fast_path_disabled(ctx):
         ops.USE_K3S1 = True
     torch.cuda.synchronize()
     close(out.to_ncdhw(), ref, what="generic conv")
+
+
+WGRAD3_CASES = [
+    # N, Cin, Cout, grid(Z,Y,X)
+    (2, 32, 32, (16, 30, 20)),
+    (1, 32, 32, (16, 64, 160)),     # full resolution: 83 tiles, last one partial
+    (16, 32, 32, (4, 30, 40)),      # 160 units > 148 SMs
+    (2, 32, 45, (8, 10, 12)),       # NP = 48
+    (2, 32, 1, (8, 12, 10)),        # NP = 16, dY has one chunk
+    (1, 128, 64, (6, 14, 12)),      # 4 input groups x 2 output groups (the merged head conv)
+    (1, 64, 64, (3, 8, 10)),
+]
+
+
+@pytest.mark.parametrize("case", WGRAD3_CASES, ids=[str(c) for c in WGRAD3_CASES])
+def test_wgrad_k3s1(case):
+    from rtpose_b200 import lib, ops
+    N, Cin, Cout, grid = case
+    x = rnd(N, Cin, *grid, seed=50)
+    dy = rnd(N, Cout, *grid, seed=51)
+    w = torch.zeros(Cout, Cin, 3, 3, 3, requires_grad=True)
+    F.conv3d(x, w, padding=1).backward(dy)
+    assert lib.load().rtp_wgrad_k3s1_supported(32, 32, grid[0], grid[2], grid[1])
+    dW = torch.full(w.shape, 3.0, device="cuda")
+    xp, dyp = to_p8(x), to_p8(dy)
+    ops.conv_wgrad(xp, dyp, 3, 1, dW)
+    torch.cuda.synchronize()
+    close(dW, w.grad, tol=2e-3, what="wgrad k3s1")
+    ops.conv_wgrad(xp, dyp, 3, 1, dW, accumulate=True)
+    torch.cuda.synchronize()
+    close(dW, 2 * w.grad, tol=2e-3, what="wgrad k3s1 accumulate")
+    # generic kernel agrees
+    ops.USE_WGRAD_K3S1 = False
+    try:
+        dW2 = torch.zeros_like(dW)
+        ops.conv_wgrad(xp, dyp, 3, 1, dW2)
+    finally:
+        ops.USE_WGRAD_K3S1 = True
+    torch.cuda.synchronize()
+    close(dW2, w.grad, tol=2e-3, what="wgrad generic")
