@@ -218,8 +218,8 @@ def run_ours(args, rank, world, local_rank):
         fam[key] = (sum(tms), len(tms), sum(f for _, _, f in evs))
     roof, top = None, []
     if fam:
-        for key, (tt, n, fl) in sorted(fam.items(), key=lambda kv: -kv[1][0])[:6]:
-            top.append({"kernel": key[0], "cin": key[1], "cout": key[2], "taps": key[3], "launches": n,
+        for key, (tt, n, fl) in sorted(fam.items(), key=lambda kv: -kv[1][0])[:16]:
+            top.append({"kernel": key[0], "cin": key[1], "cout": key[2], "taps": key[3], "is_os": [key[4], key[5]], "rows": list(key[6]), "launches": n,
                         "ms_total": round(tt, 3), "tflops": round(fl / (tt * 1e-3) / 1e12, 1)})
         key, (tt, n, fl) = max(fam.items(), key=lambda kv: kv[1][0])
         ach = fl / (tt * 1e-3) / 1e12

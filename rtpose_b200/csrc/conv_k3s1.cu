@@ -43,6 +43,7 @@ struct K3 {
   uint32_t stage_bytes, wbuf_bytes, wtap_bytes, wtap_stride;  // per-pass weight slice: 9 copies of wtap_bytes
 };
 
+template <int KS>  // KS = KG / 16: k16 steps per tap (1 or 2)
 __global__ void __launch_bounds__(kThreads, 1) conv_k3s1_kernel(const __grid_constant__ K3 p) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t bar_full[kMaxStages], bar_empty[kMaxStages], bar_wfull[2], bar_wempty[2];
@@ -122,7 +123,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_k3s1_kernel(const __grid_con
       uint32_t wcur = 0;
       const uint32_t idesc1 = idesc_bf16(128, p.NPo, 0, 0), idesc2 = idesc_bf16(128, 2 * p.NPo, 0, 0),
                      idesc3 = idesc_bf16(128, 3 * p.NPo, 0, 0);
-      const uint32_t a_lbo = p.PW * 16, b_lbo = p.N3 * 16;
+      // smem descriptor halves (SWIZZLE_NONE, K-major): lo = start>>4 | (LBO>>4)<<16 ; hi = SBO>>4 | version bit
+      const uint32_t a_lo_c = (uint32_t)p.PW << 16, b_lo_c = (uint32_t)p.N3 << 16;
+      const uint32_t a_hi = (128u >> 4) | (1u << 14), b_hi = a_hi;
+      const uint32_t a_k16 = 2u * p.PW, b_k16 = 2u * p.N3, b_tap16 = p.wtap_bytes >> 4;
+      const uint32_t stage0 = smem_u32(stages), wbase0 = smem_u32(wbuf);
+      auto mk_desc = [](uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; };
       for (int u = blockIdx.x; u < p.nunits; u += gridDim.x) {
         int n, zc, tile;
         decode(u, n, zc, tile);
@@ -134,7 +140,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_k3s1_kernel(const __grid_con
             mbar_wait(&bar_wfull[wcur], (wit >> 1) & 1);
             w_ready = true;
           }
-          const uint32_t wbase = smem_u32(wbuf + (size_t)wcur * p.wbuf_bytes);
           for (int iz = iz0; iz < iz1; ++iz) {
             const int s = it % S;
             const int lo = max(iz - 1, zo0), hi = min(iz + 1, zo1 - 1);
@@ -151,32 +156,37 @@ __global__ void __launch_bounds__(kThreads, 1) conv_k3s1_kernel(const __grid_con
             }
             mbar_wait(&bar_full[s], (it / S) & 1);
             fence_after_sync();
-            const uint32_t abase = smem_u32(stages + (size_t)s * p.stage_bytes);
+            // Descriptors are built from precomputed halves: only the 14-bit start-address field (16-byte units) of the
+            // low word changes between MMAs, so one elected thread sustains the issue rate (~10 instructions / MMA).
             const uint32_t dcol = tmem + (uint32_t)(lo - zo0) * p.NPo;
-            const uint32_t boff = (uint32_t)(lo - (iz - 1)) * p.NPo * 16;
+            const uint32_t boff16 = (uint32_t)(lo - (iz - 1)) * p.NPo;  // N-slice offset in 16-byte rows
             const int nblk = hi - lo + 1;
             const uint32_t idesc = nblk == 3 ? idesc3 : (nblk == 2 ? idesc2 : idesc1);
+            const uint32_t a_lo = a_lo_c + ((stage0 + (uint32_t)s * p.stage_bytes) >> 4);
+            const uint32_t b_lo = b_lo_c + ((wbase0 + wcur * p.wbuf_bytes) >> 4);
+            bool first_done = false;
+            if (g == 0) {
+              // first touch of this input plane: the block of output plane iz+1 (and plane 0 when iz == 0) is fresh
+              // and must be overwritten, the others accumulate
+              const uint64_t ad = mk_desc(a_lo, a_hi);
+              if (iz == 0 || lo == iz + 1) {
+                mma_ss(dcol, ad, mk_desc(b_lo + boff16, b_hi), idesc, 0u);
+              } else {
+                const int nacc = min(iz, hi) - lo + 1;  // iz > hi on the halo plane behind a z-chunk
+                mma_ss(dcol, ad, mk_desc(b_lo + boff16, b_hi), nacc == 2 ? idesc2 : idesc1, 1u);
+                if (iz + 1 <= hi)
+                  mma_ss(tmem + (uint32_t)(iz + 1 - zo0) * p.NPo, ad, mk_desc(b_lo + 2 * p.NPo, b_hi), idesc1, 0u);
+              }
+              first_done = true;
+            }
+#pragma unroll
             for (int t9 = 0; t9 < 9; ++t9) {
-              const uint32_t ashift = (uint32_t)((t9 / 3) * Yp + (t9 % 3)) * 16;
-              for (int k16 = 0; k16 < (p.KG >> 4); ++k16) {
-                const uint32_t aaddr = abase + ashift + k16 * 2 * a_lbo;
-                const uint32_t baddr = wbase + t9 * p.wtap_bytes + k16 * 2 * b_lbo;
-                if (g == 0 && t9 == 0 && k16 == 0) {
-                  // first touch of this input plane: the block of output plane iz+1 (and plane 0 when iz == 0) is
-                  // fresh and must be overwritten, the others accumulate
-                  if (iz == 0 || lo == iz + 1) {
-                    mma_ss(dcol, smem_desc(aaddr, a_lbo, 128), smem_desc(baddr + boff, b_lbo, 128), idesc, 0u);
-                  } else {
-                    const int nacc = min(iz, hi) - lo + 1;  // iz > hi on the halo plane behind a z-chunk
-                    mma_ss(dcol, smem_desc(aaddr, a_lbo, 128), smem_desc(baddr + boff, b_lbo, 128),
-                           nacc == 2 ? idesc2 : idesc1, 1u);
-                    if (iz + 1 <= hi)
-                      mma_ss(tmem + (uint32_t)(iz + 1 - zo0) * p.NPo, smem_desc(aaddr, a_lbo, 128),
-                             smem_desc(baddr + 2 * p.NPo * 16, b_lbo, 128), idesc1, 0u);
-                  }
-                } else {
-                  mma_ss(dcol, smem_desc(aaddr, a_lbo, 128), smem_desc(baddr + boff, b_lbo, 128), idesc, 1u);
-                }
+              const uint32_t at = a_lo + (uint32_t)((t9 / 3) * Yp + (t9 % 3));
+              const uint32_t bt = b_lo + boff16 + t9 * b_tap16;
+#pragma unroll
+              for (int k16 = 0; k16 < KS; ++k16) {
+                if (t9 == 0 && k16 == 0 && first_done) continue;
+                mma_ss(dcol, mk_desc(at + k16 * a_k16, a_hi), mk_desc(bt + k16 * b_k16, b_hi), idesc, 1u);
               }
             }
             mma_commit(&bar_empty[s]);
@@ -210,14 +220,28 @@ __global__ void __launch_bounds__(kThreads, 1) conv_k3s1_kernel(const __grid_con
       const int64_t pos = (int64_t)q * 8;
       for (int oz = zo0 + eg; oz < zo1; oz += 2) {
         const int b = oz - zo0;
-        mbar_wait(&bar_acc_full[b], (full_mask >> b) & 1);
-        full_mask ^= 1u << b;
-        fence_after_sync();
         const int64_t plane = (int64_t)oz * p.out.plane_elems() + pos;
         bf16* out_row = p.out.ptr + (int64_t)n * p.out.n_stride + plane;
         const bf16* res_row = p.has_res ? p.res.ptr + (int64_t)n * p.res.n_stride + (int64_t)oz * p.res.plane_elems() + pos : nullptr;
         const bf16* mask_row = p.has_mask ? p.mask.ptr + (int64_t)n * p.mask.n_stride + (int64_t)oz * p.mask.plane_elems() + pos : nullptr;
-        for (int c16 = 0; c16 * 16 < p.NPo; ++c16) {
+        // issue the residual / mask / accumulate loads of the first four chunks BEFORE waiting for the accumulator,
+        // so their latency overlaps the MMAs of this plane
+        uint4 pre_res[4], pre_mask[4], pre_acc[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          pre_res[c] = pre_mask[c] = pre_acc[c] = make_uint4(0, 0, 0, 0);
+          if (ok && c < p.out_c8) {
+            if (res_row) pre_res[c] = ldg16(res_row + c * p.res.c_stride);
+            if (mask_row) pre_mask[c] = ldg16(mask_row + c * p.mask.c_stride);
+            if (p.accumulate) pre_acc[c] = *reinterpret_cast<const uint4*>(out_row + c * p.out.c_stride);
+          }
+        }
+        mbar_wait(&bar_acc_full[b], (full_mask >> b) & 1);
+        full_mask ^= 1u << b;
+        fence_after_sync();
+#pragma unroll
+        for (int c16 = 0; c16 < 5; ++c16) {  // NPo <= 80; unrolled so the prefetched vectors stay in registers
+          if (c16 * 16 >= p.NPo) break;
           uint32_t v[16];
           tmem_ld16(trow + b * p.NPo + c16 * 16, v);
           tmem_ld_wait();
@@ -238,7 +262,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_k3s1_kernel(const __grid_con
             }
             if (res_row) {
               float g[8];
-              unpack8(ldg16(res_row + ch * p.res.c_stride), g);
+              unpack8(ch < 4 ? pre_res[ch & 3] : ldg16(res_row + ch * p.res.c_stride), g);
 #pragma unroll
               for (int i = 0; i < 8; ++i) f[i] += g[i];
             }
@@ -248,14 +272,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_k3s1_kernel(const __grid_con
             }
             if (mask_row) {
               float g[8];
-              unpack8(ldg16(mask_row + ch * p.mask.c_stride), g);
+              unpack8(ch < 4 ? pre_mask[ch & 3] : ldg16(mask_row + ch * p.mask.c_stride), g);
 #pragma unroll
               for (int i = 0; i < 8; ++i) f[i] = g[i] > 0.f ? f[i] : 0.f;
             }
             bf16* dst = out_row + ch * p.out.c_stride;
             if (p.accumulate) {
               float g[8];
-              unpack8(*reinterpret_cast<const uint4*>(dst), g);
+              unpack8(ch < 4 ? pre_acc[ch & 3] : *reinterpret_cast<const uint4*>(dst), g);
 #pragma unroll
               for (int i = 0; i < 8; ++i) f[i] += g[i];
             }
@@ -284,6 +308,7 @@ Plan make_plan(int K, int NPo, int Z, int X, int Y) {
   const int N3 = 3 * NPo;
   int KG = (9 * 32 * N3 * 2 <= 56 * 1024) ? 32 : 16;
   if (K < KG) KG = K;
+  if (K % KG != 0) KG = 16;  // e.g. K = 48 (dgrad of the 45-channel regression conv): three passes of 16
   if (K % KG != 0) return pl;
   pl.KG = KG;
   pl.npass = K / KG;
@@ -335,11 +360,12 @@ extern "C" int rtp_conv_k3s1(const rtp_conv_k3s1_desc* d, void* stream) {
   k.nstages = pl.nstages; k.stage_bytes = pl.stage_bytes; k.wbuf_bytes = pl.wbuf_bytes;
   k.wtap_bytes = (uint32_t)(pl.KG / 8) * k.N3 * 16;          // one tap's [KG/8][N3][8] slice
   k.wtap_stride = (uint32_t)(d->Cin / 8) * k.N3 * 16;        // distance between taps in the packed weights
-  static size_t configured = 0;
-  if (pl.smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_k3s1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+  auto kern = pl.KG == 32 ? conv_k3s1_kernel<2> : conv_k3s1_kernel<1>;
+  static size_t configured[2] = {0, 0};
+  if (pl.smem > configured[pl.KG == 32]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
     if (e != cudaSuccess) { rtp_set_error("rtp_conv_k3s1: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
-    configured = pl.smem;
+    configured[pl.KG == 32] = pl.smem;
   }
   static int nsm = 0;
   if (!nsm) {
@@ -348,6 +374,6 @@ extern "C" int rtp_conv_k3s1(const rtp_conv_k3s1_desc* d, void* stream) {
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
   }
   const int grid = k.nunits < nsm ? k.nunits : nsm;
-  conv_k3s1_kernel<<<grid, kThreads, pl.smem, (cudaStream_t)stream>>>(k);
+  kern<<<grid, kThreads, pl.smem, (cudaStream_t)stream>>>(k);
   RTP_LAUNCH_CHECK();
 }

@@ -39,10 +39,10 @@ __global__ void __launch_bounds__(256) fuse_sum_kernel(const __grid_constant__ F
 #pragma unroll
   for (int i = 0; i < 8; ++i) bias[i] = (p.bias && c8 * 8 + i < p.C) ? p.bias[c8 * 8 + i] : 0.f;
   for (int64_t v = blockIdx.x * 256ll + threadIdx.x; v < V; v += (int64_t)gridDim.x * 256) {
-    int64_t q = v;
-    const int y = (int)(q % o.Y); q /= o.Y;
-    const int x = (int)(q % o.X);
-    const int z = (int)(q / o.X);
+    uint32_t q = (uint32_t)v;  // 32-bit div/mod (Z*X*Y < 2^31)
+    const int y = (int)(q % (uint32_t)o.Y); q /= (uint32_t)o.Y;
+    const int x = (int)(q % (uint32_t)o.X);
+    const int z = (int)(q / (uint32_t)o.X);
     const int64_t off = o.voxel(z, x, y);
     float acc[8];
 #pragma unroll
@@ -109,12 +109,12 @@ __global__ void __launch_bounds__(256) upsample_bwd_axis_kernel(P8 in, P8 out, i
   const int64_t V = (int64_t)out.Z * out.X * out.Y;
   const int64_t total = V * C8 * out.N;
   for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
-    int64_t q = i;
-    const int y = (int)(q % out.Y); q /= out.Y;
-    const int x = (int)(q % out.X); q /= out.X;
-    const int z = (int)(q % out.Z); q /= out.Z;
-    const int c8 = (int)(q % C8);
-    const int n = (int)(q / C8);
+    uint32_t q = (uint32_t)i;  // total < 2^31 vectors
+    const int y = (int)(q % (uint32_t)out.Y); q /= (uint32_t)out.Y;
+    const int x = (int)(q % (uint32_t)out.X); q /= (uint32_t)out.X;
+    const int z = (int)(q % (uint32_t)out.Z); q /= (uint32_t)out.Z;
+    const int c8 = (int)(q % (uint32_t)C8);
+    const int n = (int)(q / (uint32_t)C8);
     const int l = axis == 0 ? z : (axis == 1 ? x : y);
     int lo, hi;
     dst_range(l, out_n, in_n, scale, lo, hi);
@@ -147,10 +147,10 @@ __global__ void __launch_bounds__(256) grad_add_kernel(P8 src, P8 mask, int has_
   const int c8 = blockIdx.y, n = blockIdx.z;
   const int64_t V = (int64_t)dst.Z * dst.X * dst.Y;
   for (int64_t v = blockIdx.x * 256ll + threadIdx.x; v < V; v += (int64_t)gridDim.x * 256) {
-    int64_t q = v;
-    const int y = (int)(q % dst.Y); q /= dst.Y;
-    const int x = (int)(q % dst.X);
-    const int z = (int)(q / dst.X);
+    uint32_t q = (uint32_t)v;
+    const int y = (int)(q % (uint32_t)dst.Y); q /= (uint32_t)dst.Y;
+    const int x = (int)(q % (uint32_t)dst.X);
+    const int z = (int)(q / (uint32_t)dst.X);
     const int64_t off = dst.voxel(z, x, y);
     float f[8];
     unpack8(ldg16(src.ptr + n * src.n_stride + c8 * src.c_stride + off), f);

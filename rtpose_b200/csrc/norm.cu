@@ -11,11 +11,13 @@ constexpr int kSlabs = 32;  // partial reductions per (sample, chunk); fixed => 
 
 // decode a linear real-voxel index v in [0, Z*X*Y) -> element offset (y fastest)
 __device__ __forceinline__ int64_t voxel_off(const P8& t, int64_t v) {
-  const int y = (int)(v % t.Y);
-  v /= t.Y;
-  const int x = (int)(v % t.X);
-  const int z = (int)(v / t.X);
-  return t.voxel(z, x, y);
+  // 32-bit arithmetic on purpose (Z*X*Y < 2^31): 64-bit div/mod costs ~10x more and dominated these kernels
+  uint32_t u = (uint32_t)v;
+  const uint32_t y = u % (uint32_t)t.Y;
+  u /= (uint32_t)t.Y;
+  const uint32_t x = u % (uint32_t)t.X;
+  const uint32_t z = u / (uint32_t)t.X;
+  return t.voxel((int)z, (int)x, (int)y);
 }
 
 // block-wide sum of NV values per thread; result valid in thread 0..NV-1 of warp 0 (value index = lane)

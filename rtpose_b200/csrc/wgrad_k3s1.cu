@@ -90,6 +90,8 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_k3s1_kernel(const __grid_co
       uint32_t it = 0;
       bool first = true;
       const uint32_t idesc = idesc_bf16(128, p.NP, 1, 1);
+      const uint32_t a_hi = (uint32_t)p.PW | (1u << 14), b_hi = 128u | (1u << 14);
+      const uint32_t smem0 = smem_u32(smem);
       for (int u = blockIdx.x; u < p.nunits; u += gridDim.x) {
         const int tile = u % p.ntile;
         int nk16 = (p.valid_pos - tile * 128 + 15) / 16;  // whole 16-position K steps inside the plane
@@ -98,15 +100,18 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_k3s1_kernel(const __grid_co
           const int s = it % S;
           mbar_wait(&bar_full[s], (it / S) & 1);
           fence_after_sync();
-          const uint32_t xbase = smem_u32(smem + (size_t)s * p.stage_bytes);
-          const uint32_t dbase = xbase + 4 * p.xplane_bytes;
+          // descriptor halves (SWIZZLE_NONE, MN-major): lo = start>>4 | (LBO = 128 B)>>4 << 16 ; hi = SBO>>4 | version
+          const uint32_t xbase = smem0 + (uint32_t)s * p.stage_bytes;
+          const uint32_t a_lo = (8u << 16) + (xbase >> 4);
+          const uint32_t b_lo = (8u << 16) + ((xbase + 4 * p.xplane_bytes) >> 4);
+#pragma unroll
           for (int t9 = 0; t9 < 9; ++t9) {
-            const uint32_t shift = (uint32_t)((t9 / 3) * Yp + (t9 % 3));
-            for (int k16 = 0; k16 < nk16; ++k16) {
-              // MN-major operands: LBO = stride between 8-position K groups (128 B), SBO = stride between 8-channel chunks
-              const uint64_t ad = smem_desc(xbase + (shift + k16 * 16) * 16, 128, p.PW * 16);
-              const uint64_t bd = smem_desc(dbase + k16 * 256, 128, 2048);
-              mma_ss(tmem + t9 * p.NP, ad, bd, idesc, (first && k16 == 0) ? 0u : 1u);
+            const uint32_t at = a_lo + (uint32_t)((t9 / 3) * Yp + (t9 % 3));
+#pragma unroll
+            for (int k16 = 0; k16 < 8; ++k16) {
+              if (k16 < nk16)
+                mma_ss(tmem + t9 * p.NP, ((uint64_t)a_hi << 32) | (at + k16 * 16), ((uint64_t)b_hi << 32) | (b_lo + k16 * 16),
+                       idesc, (first && k16 == 0) ? 0u : 1u);
             }
           }
           first = false;

@@ -240,6 +240,15 @@ def conv_dgrad(packs, dy, w, stride, dx, mask=None, accumulate=False, ci0=0, ci_
     k = w.shape[2]
     if k == 3 and stride == 1 and ci0 == 0 and ci_n is None and k3s1_eligible(dy, ceil_to(w.shape[0], 16), ceil_to(w.shape[1], 16)):
         return conv_k3s1(packs, dy, w, dx, True, mask=mask, accumulate=accumulate, key=key, version=version)
+    if (k == 3 and stride == 1 and ci0 == 0 and ci_n is None and w.shape[1] > 80 and w.shape[1] % 32 == 0
+            and k3s1_eligible(dy, ceil_to(w.shape[0], 16), 32)):
+        # wide dX (e.g. the 128-channel head input): one plane-streaming launch per 32-channel group of dX
+        for g in range(w.shape[1] // 32):
+            conv_k3s1(packs, dy, w[:, g * 32:(g + 1) * 32], dx.channels(g * 32, 32), True,
+                      mask=mask.channels(g * 32, 32) if mask is not None else None, accumulate=accumulate,
+                      key=(key if key is not None else w.data_ptr(), "dgrad_group", g),
+                      version=version if version is not None else w._version)
+        return dx
     wp, KP, NP = packs.get(w, 1, ci0, ci_n, key, version)
     real = (w.shape[0], ci_n if ci_n is not None else w.shape[1])
     if stride == 1:
