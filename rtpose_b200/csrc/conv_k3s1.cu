@@ -41,6 +41,7 @@ struct K3 {
   int nunits;
   int nstages;
   uint32_t stage_bytes, wbuf_bytes, wtap_bytes, wtap_stride;  // per-pass weight slice: 9 copies of wtap_bytes
+  long long* dbg;  // optional [grid][8] cycle counters (RTP_K3S1_DEBUG): MMA-warp wait/issue breakdown
 };
 
 template <int KS>  // KS = KG / 16: k16 steps per tap (1 or 2)
@@ -117,8 +118,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_k3s1_kernel(const __grid_con
     }
   } else if (warp == 1) {
     // ============================================================ MMA issuer
-    if (lane == 0) {
+    // Loop control, barrier waits and descriptor arithmetic run warp-uniformly (uniform datapath, no per-MMA
+    // reconvergence); only the tcgen05.mma / commit instructions are predicated on the leader lane.
+    {
+      const bool leader = lane == 0;
       uint32_t it = 0, wit = 0, fresh_mask = 0;  // bit b: parity of the number of first-writes to block b so far
+      long long t_empty = 0, t_full = 0, t_issue = 0, t0 = clock64(), tk = 0;
       bool w_ready = false;
       uint32_t wcur = 0;
       const uint32_t idesc1 = idesc_bf16(128, p.NPo, 0, 0), idesc2 = idesc_bf16(128, 2 * p.NPo, 0, 0),
@@ -143,6 +148,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_k3s1_kernel(const __grid_con
           for (int iz = iz0; iz < iz1; ++iz) {
             const int s = it % S;
             const int lo = max(iz - 1, zo0), hi = min(iz + 1, zo1 - 1);
+            tk = clock64();
             if (g == 0) {  // blocks written for the first time in this unit must have been drained by the epilogue
               if (iz + 1 <= hi) {
                 const int b = iz + 1 - zo0;
@@ -154,8 +160,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_k3s1_kernel(const __grid_con
                 fresh_mask ^= 1u;
               }
             }
+            { const long long t1 = clock64(); t_empty += t1 - tk; tk = t1; }
             mbar_wait(&bar_full[s], (it / S) & 1);
             fence_after_sync();
+            { const long long t1 = clock64(); t_full += t1 - tk; tk = t1; }
             // Descriptors are built from precomputed halves: only the 14-bit start-address field (16-byte units) of the
             // low word changes between MMAs, so one elected thread sustains the issue rate (~10 instructions / MMA).
             const uint32_t dcol = tmem + (uint32_t)(lo - zo0) * p.NPo;
@@ -165,7 +173,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_k3s1_kernel(const __grid_con
             const uint32_t a_lo = a_lo_c + ((stage0 + (uint32_t)s * p.stage_bytes) >> 4);
             const uint32_t b_lo = b_lo_c + ((wbase0 + wcur * p.wbuf_bytes) >> 4);
             bool first_done = false;
-            if (g == 0) {
+            if (g == 0 && elect_one()) {
               // first touch of this input plane: the block of output plane iz+1 (and plane 0 when iz == 0) is fresh
               // and must be overwritten, the others accumulate
               const uint64_t ad = mk_desc(a_lo, a_hi);
@@ -177,30 +185,38 @@ __global__ void __launch_bounds__(kThreads, 1) conv_k3s1_kernel(const __grid_con
                 if (iz + 1 <= hi)
                   mma_ss(tmem + (uint32_t)(iz + 1 - zo0) * p.NPo, ad, mk_desc(b_lo + 2 * p.NPo, b_hi), idesc1, 0u);
               }
-              first_done = true;
             }
+            first_done = (g == 0);
+            if (elect_one()) {  // elect.sync: the compiler knows exactly one lane runs this block (no per-MMA waterfall)
 #pragma unroll
-            for (int t9 = 0; t9 < 9; ++t9) {
-              const uint32_t at = a_lo + (uint32_t)((t9 / 3) * Yp + (t9 % 3));
-              const uint32_t bt = b_lo + boff16 + t9 * b_tap16;
+              for (int t9 = 0; t9 < 9; ++t9) {
+                const uint32_t at = a_lo + (uint32_t)((t9 / 3) * Yp + (t9 % 3));
+                const uint32_t bt = b_lo + boff16 + t9 * b_tap16;
 #pragma unroll
-              for (int k16 = 0; k16 < KS; ++k16) {
-                if (t9 == 0 && k16 == 0 && first_done) continue;
-                mma_ss(dcol, mk_desc(at + k16 * a_k16, a_hi), mk_desc(bt + k16 * b_k16, b_hi), idesc, 1u);
+                for (int k16 = 0; k16 < KS; ++k16) {
+                  if (t9 == 0 && k16 == 0 && first_done) continue;
+                  mma_ss(dcol, mk_desc(at + k16 * a_k16, a_hi), mk_desc(bt + k16 * b_k16, b_hi), idesc, 1u);
+                }
+              }
+              mma_commit(&bar_empty[s]);
+              if (g == p.npass - 1) {
+                if (iz - 1 >= zo0) mma_commit(&bar_acc_full[iz - 1 - zo0]);
+                if (iz == Z - 1 && iz < zo1) mma_commit(&bar_acc_full[iz - zo0]);
               }
             }
-            mma_commit(&bar_empty[s]);
-            if (g == p.npass - 1) {
-              if (iz - 1 >= zo0) mma_commit(&bar_acc_full[iz - 1 - zo0]);
-              if (iz == Z - 1 && iz < zo1) mma_commit(&bar_acc_full[iz - zo0]);
-            }
+            __syncwarp();
+            t_issue += clock64() - tk;
             ++it;
           }
           if (p.npass > 1) {
-            mma_commit(&bar_wempty[wcur]);
+            if (leader) mma_commit(&bar_wempty[wcur]);
             ++wit;
           }
         }
+      }
+      if (p.dbg && leader) {
+        long long* d = p.dbg + (size_t)blockIdx.x * 8;
+        d[0] = clock64() - t0; d[1] = t_empty; d[2] = t_full; d[3] = t_issue; d[4] = it;
       }
     }
   } else {
@@ -360,6 +376,7 @@ extern "C" int rtp_conv_k3s1(const rtp_conv_k3s1_desc* d, void* stream) {
   k.nstages = pl.nstages; k.stage_bytes = pl.stage_bytes; k.wbuf_bytes = pl.wbuf_bytes;
   k.wtap_bytes = (uint32_t)(pl.KG / 8) * k.N3 * 16;          // one tap's [KG/8][N3][8] slice
   k.wtap_stride = (uint32_t)(d->Cin / 8) * k.N3 * 16;        // distance between taps in the packed weights
+  k.dbg = (long long*)d->gn_sums;  // debug builds of the host side pass a counter buffer through the reserved field
   auto kern = pl.KG == 32 ? conv_k3s1_kernel<2> : conv_k3s1_kernel<1>;
   static size_t configured[2] = {0, 0};
   if (pl.smem > configured[pl.KG == 32]) {

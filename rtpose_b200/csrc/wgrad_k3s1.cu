@@ -86,7 +86,8 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_k3s1_kernel(const __grid_co
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {  // warp-uniform control flow; only the MMA / commit instructions are predicated on the leader lane
+      const bool leader = lane == 0;
       uint32_t it = 0;
       bool first = true;
       const uint32_t idesc = idesc_bf16(128, p.NP, 1, 1);
@@ -104,22 +105,25 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_k3s1_kernel(const __grid_co
           const uint32_t xbase = smem0 + (uint32_t)s * p.stage_bytes;
           const uint32_t a_lo = (8u << 16) + (xbase >> 4);
           const uint32_t b_lo = (8u << 16) + ((xbase + 4 * p.xplane_bytes) >> 4);
+          if (elect_one()) {  // elect.sync => no per-MMA waterfall loop in SASS
 #pragma unroll
-          for (int t9 = 0; t9 < 9; ++t9) {
-            const uint32_t at = a_lo + (uint32_t)((t9 / 3) * Yp + (t9 % 3));
+            for (int t9 = 0; t9 < 9; ++t9) {
+              const uint32_t at = a_lo + (uint32_t)((t9 / 3) * Yp + (t9 % 3));
 #pragma unroll
-            for (int k16 = 0; k16 < 8; ++k16) {
-              if (k16 < nk16)
-                mma_ss(tmem + t9 * p.NP, ((uint64_t)a_hi << 32) | (at + k16 * 16), ((uint64_t)b_hi << 32) | (b_lo + k16 * 16),
-                       idesc, (first && k16 == 0) ? 0u : 1u);
+              for (int k16 = 0; k16 < 8; ++k16) {
+                if (k16 < nk16)
+                  mma_ss(tmem + t9 * p.NP, ((uint64_t)a_hi << 32) | (at + k16 * 16), ((uint64_t)b_hi << 32) | (b_lo + k16 * 16),
+                         idesc, (first && k16 == 0) ? 0u : 1u);
+              }
             }
+            mma_commit(&bar_empty[s]);
           }
+          __syncwarp();
           first = false;
-          mma_commit(&bar_empty[s]);
           ++it;
         }
       }
-      if (has_work) mma_commit(&bar_done);
+      if (has_work && leader) mma_commit(&bar_done);
     }
   } else {
     // final epilogue: 9 accumulators -> fp32 partial of this CTA
