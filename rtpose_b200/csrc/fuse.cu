@@ -32,56 +32,74 @@ struct FuseK {
 };
 
 __global__ void __launch_bounds__(256) fuse_sum_kernel(const __grid_constant__ FuseK p) {
+  // rows (fixed z, x) x lanes along y: the z/x interpolation indices and weights are computed once per row
   const int c8 = blockIdx.y, n = blockIdx.z;
   const P8& o = p.out;
-  const int64_t V = (int64_t)o.Z * o.X * o.Y;
   float bias[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) bias[i] = (p.bias && c8 * 8 + i < p.C) ? p.bias[c8 * 8 + i] : 0.f;
-  for (int64_t v = blockIdx.x * 256ll + threadIdx.x; v < V; v += (int64_t)gridDim.x * 256) {
-    uint32_t q = (uint32_t)v;  // 32-bit div/mod (Z*X*Y < 2^31)
-    const int y = (int)(q % (uint32_t)o.Y); q /= (uint32_t)o.Y;
-    const int x = (int)(q % (uint32_t)o.X);
-    const int z = (int)(q / (uint32_t)o.X);
-    const int64_t off = o.voxel(z, x, y);
-    float acc[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-    for (int s = 0; s < p.n_same; ++s) {
-      float f[8];
-      unpack8(ldg16(p.same[s].ptr + n * p.same[s].n_stride + c8 * p.same[s].c_stride + off), f);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] += f[i];
-    }
+  int log2ty = 3;
+  while ((1 << log2ty) < o.Y && log2ty < 6) ++log2ty;
+  const int TY = 1 << log2ty;
+  const int ty = threadIdx.x & (TY - 1), tr = threadIdx.x >> log2ty, rstep = 256 >> log2ty;
+  const int R = o.Z * o.X;
+  const int r0 = (int)((int64_t)R * blockIdx.x / gridDim.x), r1 = (int)((int64_t)R * (blockIdx.x + 1) / gridDim.x);
+  float sz[3], sx[3], sy[3];
+  for (int j = 0; j < p.n_low; ++j) {
+    sz[j] = ac_scale(p.low[j].Z, o.Z);
+    sx[j] = ac_scale(p.low[j].X, o.X);
+    sy[j] = ac_scale(p.low[j].Y, o.Y);
+  }
+  int row = r0 + tr;
+  if (row >= r1) return;
+  int z = row / o.X, x = row - z * o.X;
+  for (; row < r1; row += rstep) {
+    Axis az[3], ax[3];
     for (int j = 0; j < p.n_low; ++j) {
-      const P8& l = p.low[j];
-      const Axis az = ac_axis(z, l.Z, ac_scale(l.Z, o.Z));
-      const Axis ax = ac_axis(x, l.X, ac_scale(l.X, o.X));
-      const Axis ay = ac_axis(y, l.Y, ac_scale(l.Y, o.Y));
-      const bf16* lb = l.ptr + n * l.n_stride + c8 * l.c_stride;
-      float up[8];
+      az[j] = ac_axis(z, p.low[j].Z, sz[j]);
+      ax[j] = ac_axis(x, p.low[j].X, sx[j]);
+    }
+    for (int y = ty; y < o.Y; y += TY) {
+      const int64_t off = o.voxel(z, x, y);
+      float acc[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) up[i] = 0.f;
-#pragma unroll
-      for (int corner = 0; corner < 8; ++corner) {
-        const int zz = (corner & 4) ? az.i1 : az.i0;
-        const int xx = (corner & 2) ? ax.i1 : ax.i0;
-        const int yy = (corner & 1) ? ay.i1 : ay.i0;
-        const float w = ((corner & 4) ? az.w1 : az.w0) * ((corner & 2) ? ax.w1 : ax.w0) * ((corner & 1) ? ay.w1 : ay.w0);
+      for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+      for (int s = 0; s < p.n_same; ++s) {
         float f[8];
-        unpack8(ldg16(lb + l.voxel(zz, xx, yy)), f);
+        unpack8(ldg16(p.same[s].ptr + n * p.same[s].n_stride + c8 * p.same[s].c_stride + off), f);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) up[i] = fmaf(w, f[i], up[i]);
+        for (int i = 0; i < 8; ++i) acc[i] += f[i];
+      }
+      for (int j = 0; j < p.n_low; ++j) {
+        const P8& l = p.low[j];
+        const Axis ay = ac_axis(y, l.Y, sy[j]);
+        const bf16* lb = l.ptr + n * l.n_stride + c8 * l.c_stride;
+        float up[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) up[i] = 0.f;
+#pragma unroll
+        for (int corner = 0; corner < 8; ++corner) {
+          const int zz = (corner & 4) ? az[j].i1 : az[j].i0;
+          const int xx = (corner & 2) ? ax[j].i1 : ax[j].i0;
+          const int yy = (corner & 1) ? ay.i1 : ay.i0;
+          const float w = ((corner & 4) ? az[j].w1 : az[j].w0) * ((corner & 2) ? ax[j].w1 : ax[j].w0) * ((corner & 1) ? ay.w1 : ay.w0);
+          float f[8];
+          unpack8(ldg16(lb + l.voxel(zz, xx, yy)), f);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) up[i] = fmaf(w, f[i], up[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] += up[i];
       }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] += up[i];
+      for (int i = 0; i < 8; ++i) {
+        acc[i] += bias[i];
+        if (p.relu) acc[i] = fmaxf(acc[i], 0.f);
+      }
+      stg16(o.ptr + n * o.n_stride + c8 * o.c_stride + off, pack8(acc));
     }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      acc[i] += bias[i];
-      if (p.relu) acc[i] = fmaxf(acc[i], 0.f);
-    }
-    stg16(o.ptr + n * o.n_stride + c8 * o.c_stride + off, pack8(acc));
+    x += rstep;
+    while (x >= o.X) { x -= o.X; ++z; }
   }
 }
 
@@ -171,8 +189,8 @@ __global__ void __launch_bounds__(256) grad_add_kernel(P8 src, P8 mask, int has_
   }
 }
 
-int ew_blocks(int64_t V) {
-  int64_t b = (V + 255) / 256;
+int ew_blocks(int64_t V) {  // every thread gets >= ~8 vectors
+  int64_t b = (V + 2047) / 2048;
   return (int)(b > 592 ? 592 : (b < 1 ? 1 : b));
 }
 bool same_geom(const rtp_p8& a, const rtp_p8& b) { return a.N == b.N && a.Z == b.Z && a.X == b.X && a.Y == b.Y; }

@@ -20,6 +20,31 @@ __device__ __forceinline__ int64_t voxel_off(const P8& t, int64_t v) {
   return t.voxel((int)z, (int)x, (int)y);
 }
 
+// Row-wise traversal of the real voxels: a row is Y consecutive 16-byte vectors.  Threads are laid out as
+// (TY = 2^log2ty lanes along y) x (blockDim/TY rows); (z, x) advance incrementally, so there is ONE integer
+// division per thread instead of two per vector.  f(element_offset) is called for every assigned vector.
+template <typename F>
+__device__ __forceinline__ void rows_foreach(const P8& t, int row_begin, int row_end, int log2ty, F&& f) {
+  const int TY = 1 << log2ty;
+  const int ty = threadIdx.x & (TY - 1), tr = threadIdx.x >> log2ty;
+  const int rstep = (int)blockDim.x >> log2ty;
+  int row = row_begin + tr;
+  if (row < row_end) {
+    int z = row / t.X, x = row - z * t.X;
+    for (; row < row_end; row += rstep) {
+      const int64_t base = t.voxel(z, x, 0);
+      for (int y = ty; y < t.Y; y += TY) f(base + (int64_t)y * 8);
+      x += rstep;
+      while (x >= t.X) { x -= t.X; ++z; }
+    }
+  }
+}
+__host__ __device__ inline int log2_ty(int Y) {
+  int l = 3;
+  while ((1 << l) < Y && l < 6) ++l;
+  return l;
+}
+
 // block-wide sum of NV values per thread; result valid in thread 0..NV-1 of warp 0 (value index = lane)
 template <int NV>
 __device__ __forceinline__ void block_reduce(float (&acc)[NV], float* sh /* [8][NV] */, float* out) {
@@ -42,21 +67,21 @@ __device__ __forceinline__ void block_reduce(float (&acc)[NV], float* sh /* [8][
 __global__ void __launch_bounds__(256) gn_sums_partial_kernel(P8 x, float* __restrict__ partial) {
   __shared__ float sh[8 * 16];
   const int slab = blockIdx.x, c8 = blockIdx.y, n = blockIdx.z;
-  const int64_t V = (int64_t)x.Z * x.X * x.Y;
-  const int64_t v0 = V * slab / kSlabs, v1 = V * (slab + 1) / kSlabs;
+  const int R = x.Z * x.X;
+  const int r0 = (int)((int64_t)R * slab / kSlabs), r1 = (int)((int64_t)R * (slab + 1) / kSlabs);
   const bf16* base = x.ptr + n * x.n_stride + c8 * x.c_stride;
   float acc[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) acc[i] = 0.f;
-  for (int64_t v = v0 + threadIdx.x; v < v1; v += 256) {
+  rows_foreach(x, r0, r1, log2_ty(x.Y), [&](int64_t off) {
     float f[8];
-    unpack8(ldg16(base + voxel_off(x, v)), f);
+    unpack8(ldg16(base + off), f);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       acc[i] += f[i];
       acc[8 + i] += f[i] * f[i];
     }
-  }
+  });
   block_reduce<16>(acc, sh, partial + (((size_t)n * x.C8 + c8) * kSlabs + slab) * 16);
 }
 
@@ -100,33 +125,36 @@ __global__ void gn_finalize_kernel(const float* __restrict__ sums, int N, int C,
 __global__ void __launch_bounds__(256) gn_apply_kernel(P8 x, int C, int G, const float* __restrict__ stats,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        P8 y) {
+  __shared__ float s_ab[16];
   const int c8 = blockIdx.y, n = blockIdx.z;
   const int cpg = C / G;
-  float a[8], b[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int c = c8 * 8 + i;
+  if (threadIdx.x < 8) {  // per-(sample, chunk) affine coefficients, computed once per block
+    const int c = c8 * 8 + threadIdx.x;
+    float av = 0.f, bv = 0.f;
     if (c < C) {
       const int g = c / cpg;
       const float mean = stats[((size_t)n * G + g) * 2], rstd = stats[((size_t)n * G + g) * 2 + 1];
-      a[i] = rstd * gamma[c];
-      b[i] = beta[c] - mean * a[i];
-    } else {
-      a[i] = 0.f;
-      b[i] = 0.f;
+      av = rstd * gamma[c];
+      bv = beta[c] - mean * av;
     }
+    s_ab[threadIdx.x] = av;
+    s_ab[8 + threadIdx.x] = bv;
   }
-  const int64_t V = (int64_t)x.Z * x.X * x.Y;
+  __syncthreads();
+  float a[8], b[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { a[i] = s_ab[i]; b[i] = s_ab[8 + i]; }
+  const int R = x.Z * x.X;
+  const int r0 = (int)((int64_t)R * blockIdx.x / gridDim.x), r1 = (int)((int64_t)R * (blockIdx.x + 1) / gridDim.x);
   const bf16* xb = x.ptr + n * x.n_stride + c8 * x.c_stride;
   bf16* yb = y.ptr + n * y.n_stride + c8 * y.c_stride;
-  for (int64_t v = blockIdx.x * 256ll + threadIdx.x; v < V; v += (int64_t)gridDim.x * 256) {
-    const int64_t off = voxel_off(x, v);
+  rows_foreach(x, r0, r1, log2_ty(x.Y), [&](int64_t off) {
     float f[8];
     unpack8(ldg16(xb + off), f);
 #pragma unroll
     for (int i = 0; i < 8; ++i) f[i] = fmaf(f[i], a[i], b[i]);
     stg16(yb + off, pack8(f));
-  }
+  });
 }
 
 // partial[n][c8][slab][16] = (sum dy[0..7], sum dy*xhat[0..7])
@@ -143,15 +171,14 @@ __global__ void __launch_bounds__(256) gn_bwd_partial_kernel(P8 x, P8 dy, int C,
     mean[i] = stats[((size_t)n * G + g) * 2];
     rstd[i] = stats[((size_t)n * G + g) * 2 + 1];
   }
-  const int64_t V = (int64_t)x.Z * x.X * x.Y;
-  const int64_t v0 = V * slab / kSlabs, v1 = V * (slab + 1) / kSlabs;
+  const int R = x.Z * x.X;
+  const int r0 = (int)((int64_t)R * slab / kSlabs), r1 = (int)((int64_t)R * (slab + 1) / kSlabs);
   const bf16* xb = x.ptr + n * x.n_stride + c8 * x.c_stride;
   const bf16* db = dy.ptr + n * dy.n_stride + c8 * dy.c_stride;
   float acc[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) acc[i] = 0.f;
-  for (int64_t v = v0 + threadIdx.x; v < v1; v += 256) {
-    const int64_t off = voxel_off(x, v);
+  rows_foreach(x, r0, r1, log2_ty(x.Y), [&](int64_t off) {
     float f[8], d[8];
     unpack8(ldg16(xb + off), f);
     unpack8(ldg16(db + off), d);
@@ -160,7 +187,7 @@ __global__ void __launch_bounds__(256) gn_bwd_partial_kernel(P8 x, P8 dy, int C,
       acc[i] += d[i];
       acc[8 + i] += d[i] * ((f[i] - mean[i]) * rstd[i]);
     }
-  }
+  });
   block_reduce<16>(acc, sh, partial + (((size_t)n * x.C8 + c8) * kSlabs + slab) * 16);
 }
 
@@ -182,31 +209,37 @@ __global__ void gn_param_grad_kernel(const float* __restrict__ red, int N, int C
 __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(P8 x, P8 dy, int C, int G, const float* __restrict__ stats,
                                                            const float* __restrict__ red, const float* __restrict__ gamma,
                                                            P8 dx, int accumulate, int relu_mask) {
+  __shared__ float s_k[5 * 8];
   const int c8 = blockIdx.y, n = blockIdx.z;
   const int cpg = C / G;
-  const int64_t V = (int64_t)x.Z * x.X * x.Y;
-  const float inv_m = 1.0f / ((float)V * (float)cpg);
-  float mean[8], rstd[8], ga[8], k1[8], k2[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int c = min(c8 * 8 + i, C - 1);
+  if (threadIdx.x < 8) {  // per-(sample, chunk) constants, computed once per block
+    const int64_t V = (int64_t)x.Z * x.X * x.Y;
+    const float inv_m = 1.0f / ((float)V * (float)cpg);
+    const int c = min(c8 * 8 + (int)threadIdx.x, C - 1);
     const int g = c / cpg;
-    mean[i] = stats[((size_t)n * G + g) * 2];
-    rstd[i] = stats[((size_t)n * G + g) * 2 + 1];
-    ga[i] = (c8 * 8 + i < C) ? gamma[c] : 0.f;
     float s1 = 0.f, s2 = 0.f;
     for (int cc = g * cpg; cc < (g + 1) * cpg; ++cc) {
       s1 += gamma[cc] * red[((size_t)n * C + cc) * 2];
       s2 += gamma[cc] * red[((size_t)n * C + cc) * 2 + 1];
     }
-    k1[i] = s1 * inv_m;
-    k2[i] = s2 * inv_m;
+    s_k[threadIdx.x] = stats[((size_t)n * G + g) * 2];
+    s_k[8 + threadIdx.x] = stats[((size_t)n * G + g) * 2 + 1];
+    s_k[16 + threadIdx.x] = (c8 * 8 + (int)threadIdx.x < C) ? gamma[c] : 0.f;
+    s_k[24 + threadIdx.x] = s1 * inv_m;
+    s_k[32 + threadIdx.x] = s2 * inv_m;
   }
+  __syncthreads();
+  float mean[8], rstd[8], ga[8], k1[8], k2[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    mean[i] = s_k[i]; rstd[i] = s_k[8 + i]; ga[i] = s_k[16 + i]; k1[i] = s_k[24 + i]; k2[i] = s_k[32 + i];
+  }
+  const int R = x.Z * x.X;
+  const int r0 = (int)((int64_t)R * blockIdx.x / gridDim.x), r1 = (int)((int64_t)R * (blockIdx.x + 1) / gridDim.x);
   const bf16* xb = x.ptr + n * x.n_stride + c8 * x.c_stride;
   const bf16* db = dy.ptr + n * dy.n_stride + c8 * dy.c_stride;
   bf16* ob = dx.ptr + n * dx.n_stride + c8 * dx.c_stride;
-  for (int64_t v = blockIdx.x * 256ll + threadIdx.x; v < V; v += (int64_t)gridDim.x * 256) {
-    const int64_t off = voxel_off(x, v);
+  rows_foreach(x, r0, r1, log2_ty(x.Y), [&](int64_t off) {
     float f[8], d[8], o[8];
     unpack8(ldg16(xb + off), f);
     unpack8(ldg16(db + off), d);
@@ -223,14 +256,14 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(P8 x, P8 dy, int C, i
       for (int i = 0; i < 8; ++i) o[i] += p[i];
     }
     stg16(ob + off, pack8(o));
-  }
+  });
 }
 
+// blocks along the row dimension for the elementwise kernels: every thread gets >= ~8 vectors
 int ew_blocks(int64_t V) {
-  int64_t b = (V + 255) / 256;
+  int64_t b = (V + 2047) / 2048;
   return (int)(b > 592 ? 592 : (b < 1 ? 1 : b));
 }
-
 }  // namespace
 
 extern "C" int64_t rtp_gn_workspace_bytes(int32_t N, int32_t C8) { return (int64_t)N * C8 * kSlabs * 16 * 4; }
