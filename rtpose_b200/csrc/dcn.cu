@@ -1,0 +1,287 @@
+// dcn.cu — deformable convolution v1 (2-D, groups = 1) forward / backward without the reference's `columns`
+// round trip through HBM (det3d/ops/dcn/src/deform_conv_cuda.cpp:196-247 materialises C*kh*kw x N*Ho*Wo fp32).
+//
+// Each CTA owns a tile of 32 output pixels of one sample.  A channel tile of the deformed im2col matrix is sampled
+// straight into shared memory with warp-level bilinear gathers (lanes = consecutive output pixels, so the offset
+// reads and most of the 4-corner reads coalesce) and is consumed in place by the contraction with the weights.
+// fp32 NCHW in and out, exactly the reference op's dtype/layout.  Sampling semantics follow
+// deform_conv_cuda_kernel.cu:84-115 (bilinear, zero outside) and :229 (validity h>-1 && w>-1 && h<H && w<W);
+// offset channel order [dg][kh*kw][dy,dx].
+//
+// Roofline: the gather is L2/HBM-bound, the contraction runs on the fp32 CUDA cores in this version (moving it to
+// tcgen05 is the round-2 item listed in DESIGN.md).
+#include "common.cuh"
+
+namespace {
+
+constexpr int kPix = 32;   // output pixels per CTA
+constexpr int kCT = 8;     // input channels per smem tile
+
+struct Dcn {
+  int N, C, H, W, Cout, kh, kw, stride, pad, dil, dg, Ho, Wo;
+};
+
+struct Sample {
+  float w1, w2, w3, w4;  // corner weights (0 when the corner is outside)
+  int o1, o2, o3, o4;    // corner offsets inside one channel plane
+  float lh, lw;
+  bool valid;
+};
+
+__device__ __forceinline__ Sample make_sample(const Dcn& p, float h, float w) {
+  Sample s;
+  s.valid = h > -1.f && w > -1.f && h < (float)p.H && w < (float)p.W;
+  const int h_low = (int)floorf(h), w_low = (int)floorf(w);
+  const int h_high = h_low + 1, w_high = w_low + 1;
+  s.lh = h - (float)h_low;
+  s.lw = w - (float)w_low;
+  const float hh = 1.f - s.lh, hw = 1.f - s.lw;
+  const bool t = h_low >= 0, b = h_high <= p.H - 1, l = w_low >= 0, r = w_high <= p.W - 1;
+  s.w1 = (s.valid && t && l) ? hh * hw : 0.f;
+  s.w2 = (s.valid && t && r) ? hh * s.lw : 0.f;
+  s.w3 = (s.valid && b && l) ? s.lh * hw : 0.f;
+  s.w4 = (s.valid && b && r) ? s.lh * s.lw : 0.f;
+  s.o1 = (t && l) ? h_low * p.W + w_low : 0;
+  s.o2 = (t && r) ? h_low * p.W + w_high : 0;
+  s.o3 = (b && l) ? h_high * p.W + w_low : 0;
+  s.o4 = (b && r) ? h_high * p.W + w_high : 0;
+  return s;
+}
+
+// sampling position of tap (i, j) at output pixel (ho, wo) for deformable group g
+__device__ __forceinline__ void tap_pos(const Dcn& p, const float* __restrict__ off_n, int g, int t, int ho, int wo, float& h,
+                                        float& w) {
+  const int i = t / p.kw, j = t - i * p.kw;
+  const int K = p.kh * p.kw;
+  const int64_t plane = (int64_t)p.Ho * p.Wo;
+  const float* o = off_n + ((int64_t)(g * K + t) * 2) * plane + (int64_t)ho * p.Wo + wo;
+  h = (float)(ho * p.stride - p.pad + i * p.dil) + __ldg(o);
+  w = (float)(wo * p.stride - p.pad + j * p.dil) + __ldg(o + plane);
+}
+
+// col[ck][px] for channels [c0, c0+kCT): one warp-level gather per (channel, tap) row
+__device__ __forceinline__ void sample_tile(const Dcn& p, const float* __restrict__ x_n, const float* __restrict__ off_n, int c0,
+                                            int pix0, float* col) {
+  const int K = p.kh * p.kw, npix = p.Ho * p.Wo, cpg = p.C / p.dg;
+  for (int i = threadIdx.x; i < kCT * K * kPix; i += blockDim.x) {
+    const int px = i % kPix, ck = i / kPix;
+    const int c = c0 + ck / K, t = ck % K;
+    float v = 0.f;
+    const int pix = pix0 + px;
+    if (c < p.C && pix < npix) {
+      const int ho = pix / p.Wo, wo = pix - ho * p.Wo;
+      float h, w;
+      tap_pos(p, off_n, c / cpg, t, ho, wo, h, w);
+      const Sample s = make_sample(p, h, w);
+      const float* xc = x_n + (int64_t)c * p.H * p.W;
+      v = s.w1 * __ldg(xc + s.o1) + s.w2 * __ldg(xc + s.o2) + s.w3 * __ldg(xc + s.o3) + s.w4 * __ldg(xc + s.o4);
+    }
+    col[ck * kPix + px] = v;
+  }
+}
+
+// y[n, co, pix] = sum_{c,t} w[co, c, t] * col[(c,t), pix]
+__global__ void __launch_bounds__(256) dcn_fwd_kernel(Dcn p, const float* __restrict__ x, const float* __restrict__ off,
+                                                      const float* __restrict__ w, float* __restrict__ y) {
+  extern __shared__ float col[];  // [kCT*K][kPix]
+  const int K = p.kh * p.kw, npix = p.Ho * p.Wo;
+  const int n = blockIdx.y, pix0 = blockIdx.x * kPix, co0 = blockIdx.z * 128;
+  const int px = threadIdx.x & 31, cg = threadIdx.x >> 5;  // 8 warps: warp cg owns output channels co0 + cg + 8*j
+  const float* x_n = x + (int64_t)n * p.C * p.H * p.W;
+  const float* off_n = off + (int64_t)n * p.dg * K * 2 * npix;
+  float acc[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+  for (int c0 = 0; c0 < p.C; c0 += kCT) {
+    __syncthreads();
+    sample_tile(p, x_n, off_n, c0, pix0, col);
+    __syncthreads();
+    const int nck = min(kCT, p.C - c0) * K;
+    for (int ck = 0; ck < nck; ++ck) {
+      const float v = col[ck * kPix + px];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int co = co0 + cg + 8 * j;
+        if (co < p.Cout) acc[j] = fmaf(__ldg(w + ((int64_t)co * p.C + c0) * K + ck), v, acc[j]);
+      }
+    }
+  }
+  if (pix0 + px < npix) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int co = co0 + cg + 8 * j;
+      if (co < p.Cout) y[((int64_t)n * p.Cout + co) * npix + pix0 + px] = acc[j];
+    }
+  }
+}
+
+// dx (atomic scatter) and doffset for one pixel tile
+__global__ void __launch_bounds__(256) dcn_bwd_input_kernel(Dcn p, const float* __restrict__ x, const float* __restrict__ off,
+                                                            const float* __restrict__ w, const float* __restrict__ dy,
+                                                            float* __restrict__ dx, float* __restrict__ doff) {
+  extern __shared__ float sm[];
+  const int K = p.kh * p.kw, npix = p.Ho * p.Wo, cpg = p.C / p.dg;
+  float* dcol = sm;                      // [kCT*K][kPix]
+  float* dys = sm + kCT * K * kPix;      // [Cout][kPix]
+  const int n = blockIdx.y, pix0 = blockIdx.x * kPix;
+  const float* x_n = x + (int64_t)n * p.C * p.H * p.W;
+  const float* off_n = off + (int64_t)n * p.dg * K * 2 * npix;
+  float* dx_n = dx + (int64_t)n * p.C * p.H * p.W;
+  float* doff_n = doff + (int64_t)n * p.dg * K * 2 * npix;
+  for (int i = threadIdx.x; i < p.Cout * kPix; i += blockDim.x) {
+    const int px = i % kPix, co = i / kPix;
+    dys[i] = (pix0 + px < npix) ? dy[((int64_t)n * p.Cout + co) * npix + pix0 + px] : 0.f;
+  }
+  // each thread owns fixed (tap, pixel) pairs across all channel tiles, so its doffset sums need no atomics
+  for (int c0 = 0; c0 < p.C; c0 += kCT) {
+    __syncthreads();
+    // dcol[(c,t), px] = sum_co w[co, c, t] * dy[co, px]
+    for (int i = threadIdx.x; i < kCT * K * kPix; i += blockDim.x) {
+      const int px = i % kPix, ck = i / kPix;
+      float a = 0.f;
+      if (c0 + ck / K < p.C) {
+        const float* wp = w + (int64_t)c0 * K + ck;
+        for (int co = 0; co < p.Cout; ++co) a = fmaf(__ldg(wp + (int64_t)co * p.C * K), dys[co * kPix + px], a);
+      }
+      dcol[i] = a;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < K * kPix; i += blockDim.x) {
+      const int px = i % kPix, t = i / kPix;
+      const int pix = pix0 + px;
+      if (pix >= npix) continue;
+      const int ho = pix / p.Wo, wo = pix - ho * p.Wo;
+      for (int cc = 0; cc < kCT && c0 + cc < p.C; ++cc) {
+        const int c = c0 + cc, g = c / cpg;
+        float h, wv;
+        tap_pos(p, off_n, g, t, ho, wo, h, wv);
+        const Sample s = make_sample(p, h, wv);
+        const float d = dcol[(cc * K + t) * kPix + px];
+        const float* xc = x_n + (int64_t)c * p.H * p.W;
+        float* dxc = dx_n + (int64_t)c * p.H * p.W;
+        if (s.w1 != 0.f) atomicAdd(dxc + s.o1, d * s.w1);
+        if (s.w2 != 0.f) atomicAdd(dxc + s.o2, d * s.w2);
+        if (s.w3 != 0.f) atomicAdd(dxc + s.o3, d * s.w3);
+        if (s.w4 != 0.f) atomicAdd(dxc + s.o4, d * s.w4);
+        if (s.valid) {
+          // d val / d h and d val / d w of the bilinear form (corners outside the image contribute 0)
+          const int h_low = (int)floorf(h), w_low = (int)floorf(wv);
+          const bool tt = h_low >= 0, bb = h_low + 1 <= p.H - 1, ll = w_low >= 0, rr = w_low + 1 <= p.W - 1;
+          const float x1 = (tt && ll) ? __ldg(xc + s.o1) : 0.f, x2 = (tt && rr) ? __ldg(xc + s.o2) : 0.f;
+          const float x3 = (bb && ll) ? __ldg(xc + s.o3) : 0.f, x4 = (bb && rr) ? __ldg(xc + s.o4) : 0.f;
+          const float hw = 1.f - s.lw, hh = 1.f - s.lh;
+          const float gh = -hw * x1 - s.lw * x2 + hw * x3 + s.lw * x4;
+          const float gw = -hh * x1 + hh * x2 - s.lh * x3 + s.lh * x4;
+          const int64_t plane = (int64_t)npix;
+          float* o = doff_n + ((int64_t)(g * K + t) * 2) * plane + pix;
+          o[0] += d * gh;      // this thread is the only writer of (n, g, t, pix) — channels are visited sequentially
+          o[plane] += d * gw;
+        }
+      }
+    }
+  }
+}
+
+// dw[co, c, t] += scale * sum_{pixels of this chunk} dy[co, pix] * col[(c,t), pix]
+__global__ void __launch_bounds__(256) dcn_bwd_weight_kernel(Dcn p, const float* __restrict__ x, const float* __restrict__ off,
+                                                             const float* __restrict__ dy, float* __restrict__ dw, float scale,
+                                                             int tiles_per_block) {
+  extern __shared__ float sm[];
+  const int K = p.kh * p.kw, npix = p.Ho * p.Wo;
+  float* col = sm;                   // [kCT*K][kPix]
+  float* dys = sm + kCT * K * kPix;  // [kPix][64]  (transposed: conflict-free for consecutive co)
+  const int n = blockIdx.y, c0 = blockIdx.z * kCT;
+  const int co_l = threadIdx.x & 63, ckg = threadIdx.x >> 6;  // 4 groups of ck
+  const int nck = kCT * K, per = (nck + 3) / 4;
+  const float* x_n = x + (int64_t)n * p.C * p.H * p.W;
+  const float* off_n = off + (int64_t)n * p.dg * K * 2 * npix;
+  for (int cob = 0; cob < p.Cout; cob += 64) {
+    float acc[18];
+#pragma unroll
+    for (int j = 0; j < 18; ++j) acc[j] = 0.f;
+    for (int tl = 0; tl < tiles_per_block; ++tl) {
+      const int pix0 = (blockIdx.x * tiles_per_block + tl) * kPix;
+      if (pix0 >= npix) break;
+      __syncthreads();
+      sample_tile(p, x_n, off_n, c0, pix0, col);
+      for (int i = threadIdx.x; i < 64 * kPix; i += blockDim.x) {
+        const int px = i % kPix, co = i / kPix;
+        dys[px * 64 + co] = (cob + co < p.Cout && pix0 + px < npix) ? dy[((int64_t)n * p.Cout + cob + co) * npix + pix0 + px] : 0.f;
+      }
+      __syncthreads();
+      for (int px = 0; px < kPix; ++px) {
+        const float a = dys[px * 64 + co_l];
+#pragma unroll
+        for (int j = 0; j < 18; ++j) {
+          const int ck = ckg * per + j;
+          if (j < per && ck < nck) acc[j] = fmaf(a, col[ck * kPix + px], acc[j]);
+        }
+      }
+    }
+    const int co = cob + co_l;
+    if (co < p.Cout) {
+#pragma unroll
+      for (int j = 0; j < 18; ++j) {
+        const int ck = ckg * per + j;
+        if (j < per && ck < nck && c0 + ck / K < p.C) atomicAdd(dw + ((int64_t)co * p.C + c0) * K + ck, scale * acc[j]);
+      }
+    }
+  }
+}
+
+int make(Dcn& d, int N, int C, int H, int W, int Cout, int kh, int kw, int stride, int pad, int dil, int dg, const char* who) {
+  RTP_CHECK_ARG(N > 0 && C > 0 && H > 0 && W > 0 && Cout > 0 && kh > 0 && kw > 0 && stride > 0 && dil > 0 && dg > 0, "%s: bad sizes", who);
+  RTP_CHECK_ARG(C % dg == 0, "%s: input channels %d not divisible by deformable groups %d", who, C, dg);
+  RTP_CHECK_ARG(kh * kw * kCT <= 18 * 4, "%s: kernel %dx%d too large (max 9 taps)", who, kh, kw);
+  d = Dcn{N, C, H, W, Cout, kh, kw, stride, pad, dil, dg, (H + 2 * pad - (dil * (kh - 1) + 1)) / stride + 1,
+          (W + 2 * pad - (dil * (kw - 1) + 1)) / stride + 1};
+  RTP_CHECK_ARG(d.Ho > 0 && d.Wo > 0, "%s: empty output", who);
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int rtp_dcn_fwd(const float* x, const float* offset, const float* w, float* y, int32_t N, int32_t C, int32_t H,
+                           int32_t W, int32_t Cout, int32_t kh, int32_t kw, int32_t stride, int32_t pad, int32_t dil,
+                           int32_t dg, void* stream) {
+  RTP_CHECK_ARG(x && offset && w && y, "rtp_dcn_fwd: null pointer");
+  Dcn d;
+  if (make(d, N, C, H, W, Cout, kh, kw, stride, pad, dil, dg, "rtp_dcn_fwd")) return -1;
+  dim3 grid(ceil_div((int64_t)d.Ho * d.Wo, kPix), N, ceil_div(Cout, 128));
+  dcn_fwd_kernel<<<grid, 256, kCT * kh * kw * kPix * sizeof(float), (cudaStream_t)stream>>>(d, x, offset, w, y);
+  RTP_LAUNCH_CHECK();
+}
+
+extern "C" int rtp_dcn_bwd_input(const float* x, const float* offset, const float* w, const float* dy, float* dx, float* doffset,
+                                 int32_t N, int32_t C, int32_t H, int32_t W, int32_t Cout, int32_t kh, int32_t kw,
+                                 int32_t stride, int32_t pad, int32_t dil, int32_t dg, void* stream) {
+  RTP_CHECK_ARG(x && offset && w && dy && dx && doffset, "rtp_dcn_bwd_input: null pointer");
+  Dcn d;
+  if (make(d, N, C, H, W, Cout, kh, kw, stride, pad, dil, dg, "rtp_dcn_bwd_input")) return -1;
+  const size_t smem = ((size_t)kCT * kh * kw * kPix + (size_t)Cout * kPix) * sizeof(float);
+  RTP_CHECK_ARG(smem <= 200 * 1024, "rtp_dcn_bwd_input: Cout=%d too large", Cout);
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaFuncSetAttribute(dcn_bwd_input_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = smem;
+  }
+  cudaMemsetAsync(dx, 0, (size_t)N * C * H * W * sizeof(float), (cudaStream_t)stream);
+  cudaMemsetAsync(doffset, 0, (size_t)N * dg * kh * kw * 2 * d.Ho * d.Wo * sizeof(float), (cudaStream_t)stream);
+  dim3 grid(ceil_div((int64_t)d.Ho * d.Wo, kPix), N);
+  dcn_bwd_input_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(d, x, offset, w, dy, dx, doffset);
+  RTP_LAUNCH_CHECK();
+}
+
+extern "C" int rtp_dcn_bwd_weight(const float* x, const float* offset, const float* dy, float* dw, int32_t N, int32_t C, int32_t H,
+                                  int32_t W, int32_t Cout, int32_t kh, int32_t kw, int32_t stride, int32_t pad, int32_t dil,
+                                  int32_t dg, float scale, void* stream) {
+  RTP_CHECK_ARG(x && offset && dy && dw, "rtp_dcn_bwd_weight: null pointer");
+  Dcn d;
+  if (make(d, N, C, H, W, Cout, kh, kw, stride, pad, dil, dg, "rtp_dcn_bwd_weight")) return -1;
+  const int tiles = ceil_div((int64_t)d.Ho * d.Wo, kPix);
+  const int tiles_per_block = tiles > 64 ? 16 : 1;
+  const size_t smem = ((size_t)kCT * kh * kw * kPix + 64 * kPix) * sizeof(float);
+  dim3 grid(ceil_div(tiles, tiles_per_block), N, ceil_div(C, kCT));
+  dcn_bwd_weight_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(d, x, offset, dy, dw, scale, tiles_per_block);
+  RTP_LAUNCH_CHECK();
+}

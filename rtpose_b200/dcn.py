@@ -1,0 +1,117 @@
+"""Deformable convolution v1 (2-D) with the reference's Python API.
+
+Mirrors det3d/ops/dcn/deform_conv.py:14-112 (`DeformConvFunction`: forward / backward, 8-argument signature,
+`_output_size`) and :192-255 (`DeformConv` module: no bias, uniform(-1/sqrt(fan_in)) init, small-input padding
+work-around).  The kernels are librtpose_b200.so's rtp_dcn_* (no `columns` buffer, no im2col_step batching — the
+argument is accepted and ignored).  groups must be 1, as in every use the reference makes of the op
+(center_head.py:45-51: DeformConv(C, C, 3, padding=1, deformable_groups=4)).
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+from torch.nn.modules.utils import _pair, _single
+
+from . import lib
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+class DeformConvFunction(Function):
+    @staticmethod
+    def forward(ctx, input, offset, weight, stride=1, padding=0, dilation=1, groups=1, deformable_groups=1, im2col_step=64):
+        if input is not None and input.dim() != 4:
+            raise ValueError("Expected 4D tensor as input, got {}D tensor instead.".format(input.dim()))
+        if not input.is_cuda:
+            raise NotImplementedError  # same as the reference (deform_conv.py:46-47)
+        if groups != 1:
+            raise NotImplementedError("rtpose_b200 DeformConv supports groups=1 only")
+        ctx.stride, ctx.padding, ctx.dilation = _pair(stride), _pair(padding), _pair(dilation)
+        if ctx.stride[0] != ctx.stride[1] or ctx.padding[0] != ctx.padding[1] or ctx.dilation[0] != ctx.dilation[1]:
+            raise NotImplementedError("anisotropic stride/padding/dilation")
+        ctx.groups, ctx.deformable_groups, ctx.im2col_step = groups, deformable_groups, im2col_step
+        input, offset, weight = input.contiguous().float(), offset.contiguous().float(), weight.contiguous().float()
+        ctx.save_for_backward(input, offset, weight)
+        out_size = DeformConvFunction._output_size(input, weight, ctx.padding, ctx.dilation, ctx.stride)
+        N, Cc, H, W = input.shape
+        if offset.shape != (N, deformable_groups * 2 * weight.shape[2] * weight.shape[3], out_size[2], out_size[3]):
+            raise ValueError("invalid offset shape {} for output {}".format(tuple(offset.shape), out_size))
+        output = input.new_empty(out_size)
+        lib.call("rtp_dcn_fwd", input.data_ptr(), offset.data_ptr(), weight.data_ptr(), output.data_ptr(), N, Cc, H, W,
+                 weight.shape[0], weight.shape[2], weight.shape[3], ctx.stride[0], ctx.padding[0], ctx.dilation[0],
+                 deformable_groups, _stream())
+        return output
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        input, offset, weight = ctx.saved_tensors
+        grad_output = grad_output.contiguous().float()
+        N, Cc, H, W = input.shape
+        args = (N, Cc, H, W, weight.shape[0], weight.shape[2], weight.shape[3], ctx.stride[0], ctx.padding[0],
+                ctx.dilation[0], ctx.deformable_groups)
+        grad_input = grad_offset = grad_weight = None
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+            grad_input, grad_offset = torch.empty_like(input), torch.empty_like(offset)
+            lib.call("rtp_dcn_bwd_input", input.data_ptr(), offset.data_ptr(), weight.data_ptr(), grad_output.data_ptr(),
+                     grad_input.data_ptr(), grad_offset.data_ptr(), *args, _stream())
+        if ctx.needs_input_grad[2]:
+            grad_weight = torch.zeros_like(weight)
+            lib.call("rtp_dcn_bwd_weight", input.data_ptr(), offset.data_ptr(), grad_output.data_ptr(), grad_weight.data_ptr(),
+                     *args, 1.0, _stream())
+        return (grad_input, grad_offset, grad_weight, None, None, None, None, None, None)
+
+    @staticmethod
+    def _output_size(input, weight, padding, dilation, stride):
+        channels = weight.size(0)
+        output_size = (input.size(0), channels)
+        for d in range(input.dim() - 2):
+            in_size = input.size(d + 2)
+            pad = padding[d]
+            kernel = dilation[d] * (weight.size(d + 2) - 1) + 1
+            output_size += ((in_size + (2 * pad) - kernel) // stride[d] + 1,)
+        if not all(map(lambda s: s > 0, output_size)):
+            raise ValueError("convolution input is too small (output would be {})".format("x".join(map(str, output_size))))
+        return output_size
+
+
+deform_conv = DeformConvFunction.apply
+
+
+class DeformConv(nn.Module):
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1,
+                 deformable_groups=1, bias=False):
+        super(DeformConv, self).__init__()
+        assert not bias
+        assert in_channels % groups == 0, "in_channels {} cannot be divisible by groups {}".format(in_channels, groups)
+        assert out_channels % groups == 0, "out_channels {} cannot be divisible by groups {}".format(out_channels, groups)
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.kernel_size, self.stride, self.padding, self.dilation = _pair(kernel_size), _pair(stride), _pair(padding), _pair(dilation)
+        self.groups, self.deformable_groups = groups, deformable_groups
+        self.transposed, self.output_padding = False, _single(0)
+        self.weight = nn.Parameter(torch.Tensor(out_channels, in_channels // self.groups, *self.kernel_size))
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        n = self.in_channels
+        for k in self.kernel_size:
+            n *= k
+        stdv = 1.0 / math.sqrt(n)
+        self.weight.data.uniform_(-stdv, stdv)
+
+    def forward(self, x, offset):
+        input_pad = x.size(2) < self.kernel_size[0] or x.size(3) < self.kernel_size[1]
+        if input_pad:
+            pad_h = max(self.kernel_size[0] - x.size(2), 0)
+            pad_w = max(self.kernel_size[1] - x.size(3), 0)
+            x = F.pad(x, (0, pad_w, 0, pad_h), "constant", 0).contiguous()
+            offset = F.pad(offset, (0, pad_w, 0, pad_h), "constant", 0).contiguous()
+        out = deform_conv(x, offset, self.weight, self.stride, self.padding, self.dilation, self.groups, self.deformable_groups)
+        if input_pad:
+            out = out[:, :, :out.size(2) - pad_h, :out.size(3) - pad_w].contiguous()
+        return out

@@ -372,8 +372,7 @@ class CenterHead(nn.Module):
         tgt = (example["hm"][0].to(dev, torch.float32).contiguous(), example["ind"][0].to(dev, torch.int64).contiguous(),
                example["mask"][0].to(dev, torch.uint8).contiguous(), example["cat"][0].to(dev, torch.int64).contiguous(),
                example["anno_pose"][0].to(dev, torch.float32).contiguous())
-        e = self._eng()
-        e.begin()
+        e = self._eng()  # no e.begin() here: the head's forward tape (if any) must survive until backward
         (out,) = _Bridge.apply(_LossJob(e, hm.float().contiguous(), reg.float().contiguous(), tgt, torch.is_grad_enabled()), hm, reg)
         with torch.no_grad():  # the reference's loss() leaves the clamped sigmoid in preds_dict['hm'] (:248)
             preds["hm"] = torch.clamp(hm.detach().sigmoid(), min=1e-4, max=1 - 1e-4)
@@ -407,10 +406,10 @@ class CenterHead(nn.Module):
         hm, reg = P8.from_ncdhw(_cuda_input(preds["hm"], "preds['hm']")), P8.from_ncdhw(preds["reg"])
         return self._predict_p8(hm, reg, test_cfg, example.get("meta") if isinstance(example, dict) else None)
 
-    def _predict_p8(self, hm, reg, test_cfg, metas):
+    def _predict_p8(self, hm, reg, test_cfg, metas, engine=None):
         osf, vs, rng = _get(test_cfg, "out_size_factor"), _get(test_cfg, "voxel_size"), _get(test_cfg, "pc_range")
         voxel = (osf[2] * vs[0], osf[1] * vs[1], osf[0] * vs[2])
-        idx, score, xyz = self._eng().decode(hm, reg, voxel, rng[:3])
+        idx, score, xyz = (engine or self._eng()).decode(hm, reg, voxel, rng[:3])
         return self._keypoints(idx, score, xyz, test_cfg, metas)
 
 
@@ -464,8 +463,7 @@ class RadarPoseNet(nn.Module):
             return self.pose_head._format_losses(out)
         with torch.no_grad():
             hm, reg = e.forward(P8.from_ncdhw(x), False)
-            self.pose_head._engine = self.pose_head._engine or e
-            return self.pose_head._predict_p8(hm, reg, self.test_cfg, ex["meta"])
+            return self.pose_head._predict_p8(hm, reg, self.test_cfg, ex["meta"], engine=e)
 
 
 # ------------------------------------------------------------------------------------------------ det3d aliasing

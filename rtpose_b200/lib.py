@@ -89,9 +89,9 @@ PROTOTYPES = {
     "rtp_head_loss": (C.c_int, [P8Struct, P8Struct, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _f32, _vp, _f32, _vp,
                                 P8Struct, P8Struct, _vp, _vp]),
     "rtp_decode": (C.c_int, [P8Struct, P8Struct, _i32, _i32, C.POINTER(_f32), C.POINTER(_f32), _vp, _vp, _vp, _vp]),
-    # PENDING "rtp_dcn_fwd": (C.c_int, [_vp, _vp, _vp, _vp] + [_i32] * 11 + [_vp]),
-    # PENDING "rtp_dcn_bwd_input": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp] + [_i32] * 11 + [_vp]),
-    # PENDING "rtp_dcn_bwd_weight": (C.c_int, [_vp, _vp, _vp, _vp] + [_i32] * 11 + [_f32, _vp]),
+    "rtp_dcn_fwd": (C.c_int, [_vp, _vp, _vp, _vp] + [_i32] * 11 + [_vp]),
+    "rtp_dcn_bwd_input": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp] + [_i32] * 11 + [_vp]),
+    "rtp_dcn_bwd_weight": (C.c_int, [_vp, _vp, _vp, _vp] + [_i32] * 11 + [_f32, _vp]),
     "rtp_scale_f32": (C.c_int, [_vp, _i64, _f32, _vp]),
 }
 

@@ -1,0 +1,171 @@
+"""CPU-side tests: the C-ABI library loads and exports every symbol include/rtpose_b200.h declares (no compute calls),
+host logic (tap lists, target assignment, config loading, registry/builder, state_dict names) and the
+no-CPU-fallback contract."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import hrpose_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_CFG = "/root/reference/configs/cruw_pose"
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "rtpose_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(rtp_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from rtpose_b200 import build, lib
+    if not os.path.exists(lib.LIB_PATH):
+        build.build()
+    L = lib.load()
+    names = header_symbols()
+    assert len(names) >= 35
+    for n in names:
+        assert hasattr(L, n), "librtpose_b200.so does not export %s" % n
+    missing = [n for n in names if n not in lib.PROTOTYPES]
+    assert not missing, "ctypes prototypes missing for %s" % missing
+    extra = [n for n in lib.PROTOTYPES if n not in names]
+    assert not extra, "prototypes not declared in the header: %s" % extra
+    assert L.rtp_version() >= 100
+    assert isinstance(L.rtp_last_error(), bytes)
+
+
+def test_argument_errors_are_reported_without_a_gpu():
+    """Argument validation runs before any CUDA call, so it can be exercised on the CPU box."""
+    import ctypes as C
+    from rtpose_b200 import lib
+    L = lib.load()
+    d = lib.ConvDesc()  # all-null descriptor
+    assert L.rtp_conv(C.byref(d), None) == -1
+    assert b"null" in L.rtp_last_error() or b"is null" in L.rtp_last_error()
+    assert L.rtp_conv(None, None) == -1
+    assert L.rtp_scale_f32(None, 8, 1.0, None) == -1
+    assert L.rtp_conv_k3s1_smem_bytes(32, 32, 16, 160, 64) > 0
+    assert L.rtp_conv_k3s1_smem_bytes(32, 128, 16, 160, 64) == -1      # 3*NPo > 256
+    assert L.rtp_wgrad_k3s1_supported(32, 32, 16, 160, 64) == 1
+    assert L.rtp_wgrad_k3s1_supported(64, 32, 16, 160, 64) == 0
+
+
+def test_no_cpu_fallback():
+    from rtpose_b200 import det3d_compat as D
+    from rtpose_b200 import lib
+    m = D.HRNet3D(backbone_cfg="hr_tiny_feat32_zyx_l4_in32", final_conv_in=192, final_conv_out=128, final_fuse="conat_conv", ds_factor=1)
+    with pytest.raises(lib.RtpError):
+        m(torch.zeros(1, 32, 8, 16, 16))  # CPU tensor -> loud failure, never a PyTorch-op fallback
+    if not torch.cuda.is_available():
+        with pytest.raises(lib.RtpError):
+            lib.require_device()
+
+
+def test_tap_lists():
+    from rtpose_b200 import ops
+    f = ops.taps_fwd(3)
+    assert len(f) == 27 and f[0] == (-1, -1, -1, 0) and f[13] == (0, 0, 0, 13)
+    # forward tap (kz,ky,kx) -> (tz, tx, ty): x is the slow in-plane axis of the P8 layout
+    assert f[(0 * 3 + 2) * 3 + 1] == (-1, 0, 1, 7)
+    d = ops.taps_dgrad_s1(3)
+    assert all(a[0] == -b[0] and a[1] == -b[1] and a[2] == -b[2] and a[3] == b[3] for a, b in zip(d, f))
+    # stride-2 dgrad: the 8 parity classes partition the 27 taps
+    seen = []
+    for pz in range(2):
+        for px in range(2):
+            for py in range(2):
+                t = ops.taps_dgrad_s2(pz, px, py)
+                assert len(t) == (1 if pz == 0 else 2) * (1 if px == 0 else 2) * (1 if py == 0 else 2)
+                seen += [w for _, _, _, w in t]
+    assert sorted(seen) == list(range(27))
+    # 1-D check of the index relation i = 2*o + k - 1
+    for p in range(2):
+        for k, t in ([(1, 0)] if p == 0 else [(0, 1), (2, 0)]):
+            for ih in range(4):
+                i = 2 * ih + p
+                o = ih + t
+                assert i == 2 * o + k - 1
+
+
+@pytest.mark.parametrize("one_hm", [True, False])
+def test_targets_match_oracle(one_hm):
+    from rtpose_b200 import targets
+    grid = (16, 64, 160)
+    rs = np.random.RandomState(3)
+    poses = targets.random_poses(rs, 5, grid)
+    poses[1, 3] = [-50.0, 0.0, 0.0]  # joint outside the ROI -> skipped in the 15-class assigner
+    got = targets.assign(poses, grid, one_hm, min_radius=2 if one_hm else 1)
+    ref = O.batch_targets(list(poses), grid, one_hm)
+    for k in ("hm", "ind", "mask", "cat", "anno_pose"):
+        np.testing.assert_array_equal(got[k], ref[k].numpy(), err_msg=k)
+    assert got["hm"].max() == 1.0
+
+
+@pytest.mark.parametrize("cfg", sorted(O.CONFIGS))
+def test_state_dict_names_match_reference_spec(cfg):
+    from rtpose_b200 import det3d_compat as D
+    c = O.CONFIGS[cfg]
+    names = G_POSE[:c["ncls"]]
+    model_cfg = dict(type="RadarPoseNet", pretrained=None, reader=dict(type="RadarFeatureNet"),
+                     backbone=dict(type="HRNet3D", backbone_cfg=c["arch"], final_conv_in=c["final_in"], final_conv_out=c["final_out"],
+                                   final_fuse=c["fuse"], ds_factor=1),
+                     pose_head=dict(type="CenterHead", tasks=[dict(num_class=c["ncls"], class_names=names)], in_channels=c["head_in"],
+                                    share_conv_channel=c["share"], dataset="cruw_pose", weight=c["weight"], code_weights=c["code_weights"],
+                                    common_heads={"reg": (c["reg"], 2)}, dcn_head=False),
+                     neck=None)
+    m = D.build_detector(model_cfg, train_cfg=None, test_cfg=None)
+    sd = m.state_dict()
+    spec = dict(O.state_dict_spec(cfg))  # pinned against the reference by load_state_dict(strict=True) in make_golden
+    assert set(sd) == set(spec)
+    for k, shape in spec.items():
+        assert tuple(sd[k].shape) == tuple(shape), k
+    # reference init conventions that matter: hm bias -2.19, GroupNorm gamma 1 / beta 0
+    assert torch.allclose(sd["pose_head.tasks.0.hm.2.bias"], torch.full_like(sd["pose_head.tasks.0.hm.2.bias"], -2.19))
+    assert float(sd["backbone.backbone.layer1.conv2.groupnorm.weight"].min()) == 1.0
+    m.load_state_dict(O.synth_state_dict(cfg), strict=True)
+
+
+G_POSE = ["Pelvis", "Right_Hip", "Right_Knee", "Right_Ankle", "Left_Hip", "Left_Knee", "Left_Ankle", "Thomx", "Head",
+          "Left_Shoulder", "Left_Elbow", "Left_Wrist", "Right_Shoulder", "Right_Elbow", "Right_Wrist"]
+
+
+def test_registry_and_builder_errors():
+    from rtpose_b200 import det3d_compat as D
+    with pytest.raises(KeyError):
+        D.build_detector(dict(type="NoSuchNet"))
+    with pytest.raises(KeyError):
+        D.build_backbone(dict(type="HRNet3D", backbone_cfg="nope", final_conv_in=1, final_conv_out=1, final_fuse="top"))
+    with pytest.raises(TypeError):  # the reference's dcn_head=True is a TypeError too (center_head.py:152)
+        D.build_head(dict(type="CenterHead", in_channels=32, tasks=[dict(num_class=1, class_names=["Pelvis"])],
+                          share_conv_channel=32, common_heads={"reg": (45, 2)}, dcn_head=True))
+    with pytest.raises(KeyError):
+        D.DETECTORS.register_module(D.RadarPoseNet)  # already registered
+    assert set(["RadarPoseNet"]) <= set(D.DETECTORS.module_dict)
+    assert D.install_as_det3d().build_detector is D.build_detector
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_CFG), reason="reference configs not present (GPU box)")
+@pytest.mark.parametrize("name", ["hr3d", "hr3d_one_hm", "hr3d_one_hm_doppler", "hr3d_one_hm_doppler_phase"])
+def test_reference_configs_load_unchanged_and_build(name):
+    from rtpose_b200 import det3d_compat as D
+    from rtpose_b200.config import Config
+    cfg = Config.fromfile(os.path.join(REF_CFG, name + ".py"))
+    assert cfg.model.type == "RadarPoseNet" and cfg.test_cfg.voxel_size == [0.0453125, 0.15703125, 0.3625]
+    m = D.build_detector(cfg.model, train_cfg=cfg.train_cfg, test_cfg=cfg.test_cfg)
+    want = {"hr3d": 2002194, "hr3d_one_hm": 2217006, "hr3d_one_hm_doppler": 2216942, "hr3d_one_hm_doppler_phase": 8297518}
+    assert sum(p.numel() for p in m.parameters()) == want[name]
+    with pytest.raises(AttributeError):
+        cfg.no_such_key
+
+
+def test_shard_frames_partitions_exactly():
+    from rtpose_b200.dist import shard_frames
+    for total in (0, 1, 7, 16, 129):
+        for world in (1, 2, 3, 8):
+            spans = [shard_frames(total, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert max(b - a for a, b in spans) - min(b - a for a, b in spans) <= 1

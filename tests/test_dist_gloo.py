@@ -1,0 +1,58 @@
+"""N > 1 host logic on CPU: two gloo ranks shard frames, average a flat gradient buffer in place and receive the
+rank-0 parameters (what bench.py / a DDP-style trainer does around the hot path)."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from rtpose_b200 import dist as rdist
+        lo, hi = rdist.shard_frames(33, rank, world)
+        flat = torch.arange(10, dtype=torch.float32) * (rank + 1)        # "gradients" of this rank
+        rdist.allreduce_flat(flat, world)
+        params = torch.full((5,), float(rank + 7))
+        rdist.broadcast_params([params])
+        h = rdist.allreduce_flat(torch.ones(3) * rank, world, async_op=True)
+        h.wait()
+        out.put((rank, lo, hi, flat.tolist(), params.tolist()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_allreduce_and_sharding():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (r0, lo0, hi0, f0, p0), (r1, lo1, hi1, f1, p1) = res
+    assert (lo0, hi0, lo1, hi1) == (0, 17, 17, 33)
+    want = [i * 1.5 for i in range(10)]  # mean of 1x and 2x
+    assert f0 == want and f1 == want
+    assert p0 == [7.0] * 5 and p1 == [7.0] * 5
+
+
+def test_single_process_is_a_noop():
+    from rtpose_b200 import dist as rdist
+    t = torch.ones(4)
+    assert rdist.allreduce_flat(t) is None and t.tolist() == [1.0] * 4
