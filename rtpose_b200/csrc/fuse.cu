@@ -31,6 +31,70 @@ struct FuseK {
   const float* bias;
 };
 
+// Warp-per-row variant (all low-resolution rows <= 32 vectors): trilinear interpolation is separable, so the warp first
+// blends the 4 (z, x) corner rows of every low-res term into ONE row held in shared memory (4*Yl loads) and then
+// interpolates along y from there — 4*Yl instead of 8*Y global loads per term and output row.
+__global__ void __launch_bounds__(256) fuse_sum_rows_kernel(const __grid_constant__ FuseK p) {
+  __shared__ float srow[8][3][32][8];
+  const int c8 = blockIdx.y, n = blockIdx.z;
+  const P8& o = p.out;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float bias[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) bias[i] = (p.bias && c8 * 8 + i < p.C) ? p.bias[c8 * 8 + i] : 0.f;
+  const int R = o.Z * o.X;
+  const int r0 = (int)((int64_t)R * blockIdx.x / gridDim.x), r1 = (int)((int64_t)R * (blockIdx.x + 1) / gridDim.x);
+  float sz[3], sx[3], sy[3];
+  for (int j = 0; j < p.n_low; ++j) {
+    sz[j] = ac_scale(p.low[j].Z, o.Z);
+    sx[j] = ac_scale(p.low[j].X, o.X);
+    sy[j] = ac_scale(p.low[j].Y, o.Y);
+  }
+  for (int row = r0 + warp; row < r1; row += 8) {
+    const int z = row / o.X, x = row - z * o.X;
+    for (int j = 0; j < p.n_low; ++j) {
+      const P8& l = p.low[j];
+      const Axis az = ac_axis(z, l.Z, sz[j]), ax = ac_axis(x, l.X, sx[j]);
+      const bf16* lb = l.ptr + n * l.n_stride + c8 * l.c_stride;
+      for (int yl = lane; yl < l.Y; yl += 32) {
+        float f00[8], f01[8], f10[8], f11[8];
+        unpack8(ldg16(lb + l.voxel(az.i0, ax.i0, yl)), f00);
+        unpack8(ldg16(lb + l.voxel(az.i0, ax.i1, yl)), f01);
+        unpack8(ldg16(lb + l.voxel(az.i1, ax.i0, yl)), f10);
+        unpack8(ldg16(lb + l.voxel(az.i1, ax.i1, yl)), f11);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          srow[warp][j][yl][i] = az.w0 * (ax.w0 * f00[i] + ax.w1 * f01[i]) + az.w1 * (ax.w0 * f10[i] + ax.w1 * f11[i]);
+      }
+    }
+    __syncwarp();
+    for (int y = lane; y < o.Y; y += 32) {
+      const int64_t off = o.voxel(z, x, y);
+      float acc[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+      for (int s = 0; s < p.n_same; ++s) {
+        float f[8];
+        unpack8(ldg16(p.same[s].ptr + n * p.same[s].n_stride + c8 * p.same[s].c_stride + off), f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] += f[i];
+      }
+      for (int j = 0; j < p.n_low; ++j) {
+        const Axis ay = ac_axis(y, p.low[j].Y, sy[j]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] += ay.w0 * srow[warp][j][ay.i0][i] + ay.w1 * srow[warp][j][ay.i1][i];
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        acc[i] += bias[i];
+        if (p.relu) acc[i] = fmaxf(acc[i], 0.f);
+      }
+      stg16(o.ptr + n * o.n_stride + c8 * o.c_stride + off, pack8(acc));
+    }
+    __syncwarp();
+  }
+}
+
 __global__ void __launch_bounds__(256) fuse_sum_kernel(const __grid_constant__ FuseK p) {
   // rows (fixed z, x) x lanes along y: the z/x interpolation indices and weights are computed once per row
   const int c8 = blockIdx.y, n = blockIdx.z;
@@ -214,7 +278,12 @@ extern "C" int rtp_fuse_sum(const rtp_fuse_desc* d, void* stream) {
     k.low[i] = P8(d->low[i]);
   }
   const int64_t V = (int64_t)d->out.Z * d->out.X * d->out.Y;
-  fuse_sum_kernel<<<dim3(ew_blocks(V), C8, d->out.N), 256, 0, (cudaStream_t)stream>>>(k);
+  bool rows_ok = d->n_low > 0;
+  for (int i = 0; i < d->n_low; ++i) rows_ok = rows_ok && d->low[i].Y <= 32;
+  if (rows_ok)
+    fuse_sum_rows_kernel<<<dim3(ew_blocks(V), C8, d->out.N), 256, 0, (cudaStream_t)stream>>>(k);
+  else
+    fuse_sum_kernel<<<dim3(ew_blocks(V), C8, d->out.N), 256, 0, (cudaStream_t)stream>>>(k);
   RTP_LAUNCH_CHECK();
 }
 

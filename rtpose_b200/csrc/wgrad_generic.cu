@@ -190,24 +190,40 @@ __global__ void __launch_bounds__(kThreads) wgrad_generic_kernel(const __grid_co
 }
 
 // partial [nsplit][nblocks][128][NP]  ->  dW[co][ci0 + ci][tap] = sum_split partial[..][(tap,ci)][n0 + co]
-__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int nsplit, int Cin8, int NP, int ntaps,
-                                    int nblocks, float* __restrict__ dW, int Cin_total, int co_n, int n0, int ci0,
-                                    int ci_n, int accumulate) {
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, int nsplit, int Cin8, int NP,
+                                                           int ntaps, int nblocks, float* __restrict__ dW, int Cin_total,
+                                                           int co_n, int n0, int ci0, int ci_n, int accumulate) {
+  // 32 outputs x 8 split lanes per block: lane l sums splits l, l+8, ... (independent loads in flight), then the 8
+  // lane sums are combined in a fixed order -> deterministic, and ~8x shorter dependent chains than one thread/output
+  __shared__ float sh[8][33];
   const int kch = Cin8 >> 3;
   const int64_t total = (int64_t)ntaps * ci_n * co_n;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int co = (int)(i % co_n);
-    int64_t r = i / co_n;
-    const int ci = (int)(r % ci_n);
-    const int tap = (int)(r / ci_n);
-    const int pair = tap * kch + (ci >> 3);
-    const int blk = pair >> 4, m = (pair & 15) * 8 + (ci & 7);
-    const size_t off = ((size_t)blk * 128 + m) * NP + n0 + co;
-    const size_t sstride = (size_t)nblocks * 128 * NP;
+  const int o = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  const size_t sstride = (size_t)nblocks * 128 * NP;
+  for (int64_t base = (int64_t)blockIdx.x * 32; base < total; base += (int64_t)gridDim.x * 32) {
+    const int64_t i = base + o;
     float acc = 0.f;
-    for (int s = 0; s < nsplit; ++s) acc += partial[s * sstride + off];
-    float* d = dW + ((int64_t)co * Cin_total + ci0 + ci) * ntaps + tap;
-    *d = accumulate ? *d + acc : acc;
+    int co = 0, ci = 0, tap = 0;
+    if (i < total) {
+      co = (int)(i % co_n);
+      const int64_t r = i / co_n;
+      ci = (int)(r % ci_n);
+      tap = (int)(r / ci_n);
+      const int pair = tap * kch + (ci >> 3);
+      const int blk = pair >> 4, m = (pair & 15) * 8 + (ci & 7);
+      const float* src = partial + ((size_t)blk * 128 + m) * NP + n0 + co;
+      for (int s = sl; s < nsplit; s += 8) acc += src[s * sstride];
+    }
+    sh[sl][o] = acc;
+    __syncthreads();
+    if (sl == 0 && i < total) {
+      float t = 0.f;
+#pragma unroll
+      for (int l = 0; l < 8; ++l) t += sh[l][o];
+      float* d = dW + ((int64_t)co * Cin_total + ci0 + ci) * ntaps + tap;
+      *d = accumulate ? *d + t : t;
+    }
+    __syncthreads();
   }
 }
 
@@ -273,7 +289,7 @@ extern "C" int rtp_wgrad_reduce(const float* workspace, int32_t nsplit, int32_t 
   const int npairs = ntaps * (Cin8 / 8);
   const int nblocks = (npairs + 15) / 16;
   const int64_t total = (int64_t)ntaps * ci_n * co_n;
-  const int blocks = ceil_div(total, 256) > 2048 ? 2048 : ceil_div(total, 256);
+  const int blocks = ceil_div(total, 32) > 4096 ? 4096 : ceil_div(total, 32);
   wgrad_reduce_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(workspace, nsplit, Cin8, NP, ntaps, nblocks, dW, Cin_total,
                                                                co_n, n0, ci0, ci_n, accumulate);
   RTP_LAUNCH_CHECK();

@@ -160,23 +160,39 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_k3s1_kernel(const __grid_co
 }
 
 // partial[split][t9 = kx*3+ky][(kz*4 + c)*8 + ci8][n] -> dW[co][ci0 + ci][kz][ky][kx]
-__global__ void wgrad_k3s1_reduce_kernel(const float* __restrict__ partial, int nsplit, int NP, float* __restrict__ dW,
-                                         int Cin_total, int co_n, int n0, int ci0, int accumulate) {
+__global__ void __launch_bounds__(256) wgrad_k3s1_reduce_kernel(const float* __restrict__ partial, int nsplit, int NP,
+                                                                float* __restrict__ dW, int Cin_total, int co_n, int n0,
+                                                                int ci0, int accumulate) {
+  // 32 outputs x 8 split lanes per block, fixed-order combine (deterministic)
+  __shared__ float sh[8][33];
   const int total = 27 * 32 * co_n;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int co = i % co_n;
-    int r = i / co_n;
-    const int ci = r % 32;
-    const int tap = r / 32;  // (kz*3 + ky)*3 + kx
-    const int kz = tap / 9, ky = (tap / 3) % 3, kx = tap % 3;
-    const int t9 = kx * 3 + ky;
-    const int m = (kz * 4 + (ci >> 3)) * 8 + (ci & 7);
-    const size_t off = ((size_t)t9 * 128 + m) * NP + n0 + co;
-    const size_t sstride = (size_t)9 * 128 * NP;
+  const int o = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  const size_t sstride = (size_t)9 * 128 * NP;
+  for (int base = blockIdx.x * 32; base < total; base += gridDim.x * 32) {
+    const int i = base + o;
     float acc = 0.f;
-    for (int s = 0; s < nsplit; ++s) acc += partial[s * sstride + off];
-    float* d = dW + ((int64_t)co * Cin_total + ci0 + ci) * 27 + tap;
-    *d = accumulate ? *d + acc : acc;
+    int co = 0, ci = 0, tap = 0;
+    if (i < total) {
+      co = i % co_n;
+      const int r = i / co_n;
+      ci = r % 32;
+      tap = r / 32;  // (kz*3 + ky)*3 + kx
+      const int kz = tap / 9, ky = (tap / 3) % 3, kx = tap % 3;
+      const int t9 = kx * 3 + ky;
+      const int m = (kz * 4 + (ci >> 3)) * 8 + (ci & 7);
+      const float* src = partial + ((size_t)t9 * 128 + m) * NP + n0 + co;
+      for (int s = sl; s < nsplit; s += 8) acc += src[s * sstride];
+    }
+    sh[sl][o] = acc;
+    __syncthreads();
+    if (sl == 0 && i < total) {
+      float t = 0.f;
+#pragma unroll
+      for (int l = 0; l < 8; ++l) t += sh[l][o];
+      float* d = dW + ((int64_t)co * Cin_total + ci0 + ci) * 27 + tap;
+      *d = accumulate ? *d + t : t;
+    }
+    __syncthreads();
   }
 }
 
@@ -239,7 +255,7 @@ extern "C" int rtp_wgrad_k3s1_reduce(const float* workspace, int32_t nsplit, int
   RTP_CHECK_ARG(workspace && dW && nsplit >= 1 && co_n >= 1 && n0 >= 0 && n0 + co_n <= NP && ci0 >= 0 && ci0 + 32 <= Cin_total,
                 "rtp_wgrad_k3s1_reduce: bad args");
   const int total = 27 * 32 * co_n;
-  wgrad_k3s1_reduce_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(workspace, nsplit, NP, dW, Cin_total, co_n,
+  wgrad_k3s1_reduce_kernel<<<ceil_div(total, 32), 256, 0, (cudaStream_t)stream>>>(workspace, nsplit, NP, dW, Cin_total, co_n,
                                                                                   n0, ci0, accumulate);
   RTP_LAUNCH_CHECK();
 }

@@ -87,51 +87,74 @@ def _fill_taps(d, taps, with_wt=True):
 
 # ------------------------------------------------------------------------------------------------ weights
 class PackedWeights:
-    """bf16 UMMA-B packs of an fp32 conv weight, rebuilt when the parameter's version counter changes."""
+    """bf16 UMMA-B packs of an fp32 conv weight, rebuilt when the parameter's version counter changes.
+
+    A cache entry is valid only for the SAME tensor object (weak reference) at the same version — a new tensor that
+    happens to reuse a freed tensor's address never hits.  Temporaries (merged / sliced weights) must pass an
+    explicit `key` and `version` derived from the parameters they were built from."""
 
     def __init__(self):
         self.cache = {}
 
+    def _lookup(self, key, w, ver, explicit):
+        hit = self.cache.get(key)
+        if hit is None:
+            return None, None
+        hver, val, ref = hit
+        same = explicit or (ref is not None and ref() is w)
+        return (val if (same and hver == ver and hver is not None) else None), val
+
+    def _store(self, key, w, ver, val, explicit):
+        import weakref
+        ref = None
+        if not explicit:
+            try:
+                ref = weakref.ref(w)
+            except TypeError:
+                ref = None
+        self.cache[key] = (ver, val, ref)
+
     def get(self, w, mode, ci0=0, ci_n=None, key=None, version=None):
-        """`key`/`version` must be given for temporaries (e.g. merged weights) whose address may be recycled."""
         Cout, Cin = w.shape[0], w.shape[1]
         ntaps = w.shape[2] * w.shape[3] * w.shape[4]
         ci_n = Cin if ci_n is None else ci_n
-        key = (key if key is not None else w.data_ptr(), mode, ci0, ci_n, tuple(w.shape))
+        explicit = key is not None
+        key = (key if explicit else w.data_ptr(), mode, ci0, ci_n, tuple(w.shape))
         ver = version if version is not None else w._version
-        hit = self.cache.get(key)
-        if hit is not None and hit[0] == ver:
-            return hit[1]
+        val, old = self._lookup(key, w, ver, explicit)
+        if val is not None:
+            return val
         if mode == 0:
             KP, NP = ceil_to(ci_n, 16), ceil_to(Cout, 16)
         else:
             KP, NP = ceil_to(Cout, 16), ceil_to(ci_n, 16)
-        dst = hit[1][0] if hit is not None else torch.empty(ntaps * KP * NP, dtype=torch.bfloat16, device=w.device)
+        dst = old[0] if old is not None else torch.empty(ntaps * KP * NP, dtype=torch.bfloat16, device=w.device)
         wc = w.detach().contiguous()
         lib.call("rtp_weight_pack", wc.data_ptr(), dst.data_ptr(), Cout, Cin, ntaps, ci0, ci_n, KP, NP, mode, _stream())
         val = (dst, KP, NP)
-        self.cache[key] = (ver, val)
+        self._store(key, w, ver, val, explicit)
         return val
 
     def get_k3s1(self, w, K, NPo, transpose_flip, key=None, version=None):
         """kz-stacked pack for the plane-streaming kernel: [9][K/8][3*NPo][8]."""
-        key = (key if key is not None else w.data_ptr(), "k3s1", bool(transpose_flip), K, NPo, tuple(w.shape))
+        explicit = key is not None
+        key = (key if explicit else w.data_ptr(), "k3s1", bool(transpose_flip), K, NPo, tuple(w.shape))
         ver = version if version is not None else w._version
-        hit = self.cache.get(key)
-        if hit is not None and hit[0] == ver:
-            return hit[1]
-        dst = hit[1] if hit is not None else torch.empty(9 * K * 3 * NPo, dtype=torch.bfloat16, device=w.device)
+        val, old = self._lookup(key, w, ver, explicit)
+        if val is not None:
+            return val
+        dst = old if old is not None else torch.empty(9 * K * 3 * NPo, dtype=torch.bfloat16, device=w.device)
         wc = w.detach().contiguous()
         lib.call("rtp_weight_pack_k3s1", wc.data_ptr(), dst.data_ptr(), w.shape[0], w.shape[1], K, NPo,
                  int(bool(transpose_flip)), _stream())
-        self.cache[key] = (ver, dst)
+        self._store(key, w, ver, dst, explicit)
         return dst
 
     def invalidate(self):
         """Forces a repack on next use (weights are repacked once per optimizer step in training)."""
         for k in list(self.cache):
-            ver, val = self.cache[k]
-            self.cache[k] = (None, val)
+            ver, val, ref = self.cache[k]
+            self.cache[k] = (None, val, ref)
 
 
 # ------------------------------------------------------------------------------------------------ profiling hook
