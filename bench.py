@@ -3,9 +3,10 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--cfg hr3d_one_hm_doppler]
 
-A "step" = one pass of the hot path over one batch of synthetic radar cubes: raw fp16 cube (resident in HBM) ->
-ingest (ROI crop / normalise / clamp / channel pack) -> HRNet3D backbone -> CenterHead -> focal + L1 loss ->
-backward (all parameter gradients) [-> NCCL all-reduce of the flat gradient buffer when N > 1].
+A "step" = one pass of the hot path over one batch of synthetic radar cubes: raw fp16 cube + 3-D skeletons (resident in
+HBM) -> ingest (ROI crop / normalise / clamp / channel pack) + target assignment -> HRNet3D backbone -> CenterHead ->
+focal + L1 loss -> backward (all parameter gradients) [-> NCCL all-reduce of the flat gradient buffer when N > 1] ->
+fused clip + Adam step (weights really change, so the bf16 weight packs are rebuilt every step).
 Prints ONE JSON line (rank 0).  See DESIGN.md §Measurement for every field.
 """
 import argparse
@@ -158,19 +159,26 @@ def run_ours(args, rank, world, local_rank):
     D = in_ch
     raw = (a + (b - a) * (torch.rand((B, D) + RAW_SHAPE, device=dev, generator=g) * 1.2 - 0.2)).to(torch.float16)
     rs = np.random.RandomState(99 + rank)
-    tg = targets.assign(targets.random_poses(rs, B, GRID), GRID, one_hm=(ncls == 1), min_radius=2 if ncls == 1 else 1)
-    tgt = {k: torch.from_numpy(v).to(dev) for k, v in tg.items()}
+    poses = torch.from_numpy(targets.random_poses(rs, B, GRID)).to(dev)  # random 3-D skeletons, fp64 [B,15,3], resident
     xin = P8(B, D, *GRID, device=dev)
+    from rtpose_b200.optim import FlatAdam, one_cycle
+    opt = FlatAdam(flat, gflat, wd=0.01, max_norm=35.0) if not args.no_optimizer else None
+    it = [0]
 
     def step():
         lib.call("rtp_ingest_pack", raw.data_ptr(), B, D, RAW_SHAPE[0], RAW_SHAPE[1], RAW_SHAPE[2], ROI0[0], ROI0[1], ROI0[2],
                  float(a), float(b - a), 1 if norm is not None else 0, xin.struct(), None, _stream())
-        eng.packs.invalidate()  # weights change every optimizer step: repack inside the timed region
+        tgt = targets.assign_device(poses, GRID, one_hm=(ncls == 1), min_radius=2 if ncls == 1 else 1)
+        eng.packs.invalidate()  # the weights changed in the optimizer step: repack inside the timed region
         hm, rg = eng.forward(xin, True)
         out = eng.loss(hm, rg, tgt["hm"], tgt["ind"], tgt["mask"], tgt["cat"], tgt["anno_pose"])
         eng.backward(grads)
         if world > 1:
             rdist.allreduce_flat(gflat, world)
+        if opt is not None:
+            lr, mom = one_cycle(it[0], 1000, lr_max=2e-3)  # configs/cruw_pose/hr3d_one_hm_doppler.py:176-179
+            opt.step(lr, mom)
+        it[0] += 1
         return out
 
     def barrier():
@@ -221,11 +229,26 @@ def run_ours(args, rank, world, local_rank):
         for key, (tt, n, fl) in sorted(fam.items(), key=lambda kv: -kv[1][0])[:16]:
             top.append({"kernel": key[0], "cin": key[1], "cout": key[2], "taps": key[3], "is_os": [key[4], key[5]], "rows": list(key[6]), "launches": n,
                         "ms_total": round(tt, 3), "tflops": round(fl / (tt * 1e-3) / 1e12, 1)})
-        key, (tt, n, fl) = max(fam.items(), key=lambda kv: kv[1][0])
+        # dominant kernel = the kernel FUNCTION with the largest summed time (all its shapes); the per-launch figures
+        # quoted are those of its most time-consuming shape
+        by_kernel = {}
+        for key, (tt, n, fl) in fam.items():
+            a = by_kernel.setdefault(key[0], [0.0, 0, 0.0])
+            a[0] += tt; a[1] += n; a[2] += fl
+        kname = max(by_kernel, key=lambda k: by_kernel[k][0])
+        key, (tt, n, fl) = max(((k, v) for k, v in fam.items() if k[0] == kname), key=lambda kv: kv[1][0])
         ach = fl / (tt * 1e-3) / 1e12
+        traffic = None
+        tj = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+        if os.path.exists(tj) and key[1] == 32 and key[2] == 32 and tuple(key[6]) == (16, 160, 64) and B == 16:
+            traffic = json.load(open(tj)).get(kname, {}).get("traffic_MB")
+            traffic = traffic * 1e6 if traffic else None
         roof = {"bound": "tensor", "kernel": "%s Cin=%d Cout=%d taps=%d" % key[:4], "achieved": ach, "peak": pk_sust,
                 "unit": "TFLOP/s", "frac": ach / pk_sust, "frac_of_burst_peak": ach / pk_burst, "peak_source": src + " (sustained)",
-                "avg_launch_ms": tt / n, "share_of_step": tt / (ms * args.steps), "traffic": None}
+                "avg_launch_ms": tt / n, "share_of_step": by_kernel[kname][0] / (ms * args.steps), "traffic": traffic,
+                "traffic_source": "profiles/r01_ncu_traffic.json (ncu --set full, bytes per launch)" if traffic else None,
+                "other_tensor_kernels": {k: {"tflops": round(v[2] / (v[0] * 1e-3) / 1e12, 1), "frac": round(v[2] / (v[0] * 1e-3) / 1e12 / pk_sust, 3),
+                                             "share_of_step": round(v[0] / (ms * args.steps), 3)} for k, v in by_kernel.items() if k != kname}}
 
     line = {"metric": "radar frames/sec HRRadarPose fwd+bwd", "value": value, "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
@@ -234,7 +257,9 @@ def run_ours(args, rank, world, local_rank):
                                    "HRNet3D -> CenterHead -> loss -> backward" % (cfg, B, D),
                        "per_gpu_batch": B, "global_batch": B * world, "grid": list(GRID), "parallelism": "dp%d" % world,
                        "l2": "inputs+activations per step >> 126 MB L2 (no explicit flush needed)",
-                       "optimizer": "not in the metric (fwd+bwd); gradients all-reduced when N>1"},
+                       "targets": "assigned on the device from resident fp64 skeletons every step (rtp_assign_targets)",
+                       "optimizer": ("fused clip(35) + decoupled wd + Adam, one-cycle lr (rtp_adam_step) inside the timed region"
+                                     if opt is not None else "none (--no-optimizer)")},
             "model_tflops": 3 * gf_fwd * 1e9 * value / 1e12, "model_flops_frac_of_peak": 3 * gf_fwd * 1e9 * value / 1e12 / world / pk_sust,
             "loss": float(out[0]), "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roof, "top_kernels": top}
 
@@ -278,24 +303,41 @@ def e2e_public_api(args, dev):
     t_host = {k: torch.from_numpy(v).pin_memory() for k, v in tg.items()}
     h2d = x_host.numel() * 4 + sum(v.numel() * v.element_size() for v in t_host.values())
 
-    def step():
-        ex = {"rdr": {"rdr_tensor": x_host.to(dev, non_blocking=True)}, "meta": [{}] * B}
-        for k, v in t_host.items():
-            ex["rdr"][k] = [v.to(dev, non_blocking=True)]
+    # Every step copies ITS OWN inputs host -> device; the copy of step i+1 is issued on a side stream while step i
+    # computes (what a prefetching loader does; the reference's trainer has an unused Prefetcher for this, trainer.py:119-140)
+    copy_stream = torch.cuda.Stream(device=dev)
+
+    def fetch():
+        with torch.cuda.stream(copy_stream):
+            ex = {"rdr": {"rdr_tensor": x_host.to(dev, non_blocking=True)}, "meta": [{}] * B}
+            for k, v in t_host.items():
+                ex["rdr"][k] = [v.to(dev, non_blocking=True)]
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return ex, ev
+
+    def step(ex, ev):
+        cur = torch.cuda.current_stream()
+        cur.wait_event(ev)
+        ex["rdr"]["rdr_tensor"].record_stream(cur)
+        for k in t_host:
+            ex["rdr"][k][0].record_stream(cur)
         for p in model.parameters():
             p.grad = None
         losses = model(ex, return_loss=True)
         losses["loss"][0].backward()
-        return float(losses["loss"][0].detach().cpu())  # D2H read of the step's result
+        nxt = fetch()                                        # overlaps with the GPU work just enqueued
+        return float(losses["loss"][0].detach().cpu()), nxt  # D2H read of the step's result
 
+    nxt = fetch()
     for _ in range(max(3, min(args.warmup, 3))):
-        step()
+        _, nxt = step(*nxt)
     torch.cuda.synchronize()
     steps = max(3, min(args.steps, 10))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
-        step()
+        _, nxt = step(*nxt)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
@@ -363,6 +405,7 @@ def main():
     ap.add_argument("--cfg", default="hr3d_one_hm_doppler", choices=sorted(CFGS))
     ap.add_argument("--batch", type=int, default=16, help="frames per GPU per step")
     ap.add_argument("--no-extras", action="store_true", help="skip e2e / cpu_baseline / inference legs")
+    ap.add_argument("--no-optimizer", action="store_true", help="time forward+backward only (no fused clip+Adam step)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

@@ -243,6 +243,24 @@ int rtp_dcn_bwd_weight(const float* x, const float* offset, const float* dy, flo
                        int32_t H, int32_t W, int32_t Cout, int32_t kh, int32_t kw, int32_t stride, int32_t pad,
                        int32_t dil, int32_t dg, float scale, void* stream);
 
+/* ---- "next" rows around the path --------------------------------------------------------------
+ * N2 fused optimizer step on flat fp32 buffers.  replaces: OptimizerHook.clip_grads (clip_grad_norm_, max_norm 35;
+ * det3d/torchie/trainer/hooks/optimizer.py:9-24) + OptimWrapper.step (decoupled weight decay p *= 1 - wd*lr on every
+ * parameter, bn_wd=True; det3d/solver/fastai_optim.py:158-174) + torch.optim.Adam(betas=(mom, 0.99), eps=1e-8).step().
+ * step >= 1 is the Adam time step; max_norm <= 0 disables clipping; workspace >= rtp_adam_workspace_bytes();
+ * grad_norm_out (optional, device) receives the global L2 norm before clipping. */
+int64_t rtp_adam_workspace_bytes(void);
+int rtp_adam_step(float* param, const float* grad, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                  float eps, float wd, int32_t step, float max_norm, float* workspace, float* grad_norm_out, void* stream);
+/* N1 CenterNet target assignment on the device.  replaces: AssignLabelPose / AssignLabelPose2.__call__
+ * (det3d/datasets/pipelines/pose.py:186-255, :385-452) with gaussian3D / draw_gaussian3D
+ * (det3d/core/utils/center_utils.py:67-91).  poses: device fp64 [B][15][3] metres; voxel_xyz (fp64) and range_xyz (fp32)
+ * are HOST pointers to 3 values.  Outputs (device): hm fp32 [B][ncls][Z][Y][X], ind int64 [B][M], mask uint8 [B][M],
+ * cat int64 [B][M], anno fp32 [B][M][R] with (ncls, M, R) = (1, 1, 45) when one_hm else (15, 15, 3). */
+int rtp_assign_targets(const double* poses, int32_t B, int32_t Z, int32_t Y, int32_t X, int32_t one_hm, int32_t radius,
+                       const double* voxel_xyz, const float* range_xyz, float* hm, int64_t* ind, uint8_t* mask,
+                       int64_t* cat, float* anno, void* stream);
+
 /* ---- flat-buffer helpers for the data-parallel step ----------------------------------------------------------
  * replaces: _allreduce_coalesced's flatten / div_ / copy-back (det3d/core/utils/dist_utils.py:8-28); the
  * collective itself is ncclAllReduce issued by torch.distributed on the same flat buffer. */

@@ -93,6 +93,10 @@ PROTOTYPES = {
     "rtp_dcn_bwd_input": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp] + [_i32] * 11 + [_vp]),
     "rtp_dcn_bwd_weight": (C.c_int, [_vp, _vp, _vp, _vp] + [_i32] * 11 + [_f32, _vp]),
     "rtp_scale_f32": (C.c_int, [_vp, _i64, _f32, _vp]),
+    "rtp_adam_workspace_bytes": (C.c_int64, []),
+    "rtp_adam_step": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _i32, _f32, _vp, _vp, _vp]),
+    "rtp_assign_targets": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, C.POINTER(C.c_double), C.POINTER(_f32), _vp,
+                                     _vp, _vp, _vp, _vp, _vp]),
 }
 
 _lib = None

@@ -1,0 +1,50 @@
+"""Fused optimizer step on flat buffers.
+
+Mirrors what the reference does per iteration around the hot path:
+  OptimizerHook.after_train_iter  det3d/torchie/trainer/hooks/optimizer.py:14-24   clip_grad_norm_(max_norm=35, L2)
+  OptimWrapper.step               det3d/solver/fastai_optim.py:158-174             p *= 1 - wd*lr  (true_wd, bn_wd=True)
+  torch.optim.Adam(betas=(mom, 0.99)) built at det3d/torchie/apis/train.py:157-174
+  OneCycle lr / momentum schedule det3d/solver/learning_schedules_fastai.py:53-95   (values passed in per step)
+as ONE pass over (param, grad, m, v) in rtp_adam_step.  Parameters and gradients must live in flat fp32 buffers
+(the engine already produces gradients that way).
+"""
+import math
+
+import torch
+
+from . import lib
+
+
+class FlatAdam:
+    def __init__(self, flat_params, flat_grads, wd=0.01, eps=1e-8, beta2=0.99, max_norm=35.0):
+        assert flat_params.is_cuda and flat_params.dtype == torch.float32 and flat_params.is_contiguous()
+        assert flat_grads.shape == flat_params.shape and flat_grads.dtype == torch.float32
+        self.p, self.g = flat_params, flat_grads
+        self.m, self.v = torch.zeros_like(flat_params), torch.zeros_like(flat_params)
+        self.wd, self.eps, self.beta2, self.max_norm = float(wd), float(eps), float(beta2), float(max_norm)
+        self.t = 0
+        self.ws = torch.empty(lib.load().rtp_adam_workspace_bytes(), dtype=torch.uint8, device=flat_params.device)
+        self.grad_norm = torch.zeros(1, dtype=torch.float32, device=flat_params.device)
+
+    def step(self, lr, mom=0.9):
+        self.t += 1
+        lib.call("rtp_adam_step", self.p.data_ptr(), self.g.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), self.p.numel(),
+                 float(lr), float(mom), self.beta2, self.eps, self.wd, self.t, self.max_norm, self.ws.data_ptr(),
+                 self.grad_norm.data_ptr(), torch.cuda.current_stream().cuda_stream)
+
+
+def one_cycle(step, total_steps, lr_max=2e-3, div_factor=10.0, pct_start=0.4, moms=(0.95, 0.85)):
+    """OneCycle (learning_schedules_fastai.py:53-95): cosine warm-up lr_max/div -> lr_max over pct_start of the run with
+    momentum moms[0] -> moms[1], then cosine annealing to lr_max/div/1e4 and back to moms[0]."""
+    a1 = int(total_steps * pct_start)
+    a2 = total_steps - a1
+    low = lr_max / div_factor
+
+    def cos(start, end, pct):
+        return end + (start - end) / 2 * (math.cos(math.pi * pct) + 1)
+
+    if step < a1:
+        pct = step / max(a1, 1)
+        return cos(low, lr_max, pct), cos(moms[0], moms[1], pct)
+    pct = (step - a1) / max(a2, 1)
+    return cos(lr_max, low / 1e4, pct), cos(moms[1], moms[0], pct)

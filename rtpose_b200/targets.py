@@ -82,3 +82,29 @@ def random_poses(rs, batch, grid_zyx, voxel=VOXEL_SIZE, pc_range=PC_RANGE):
         j[0] = pelvis
         out[b] = np.clip(j, lo + 1e-3, lo + ext - 1e-3)
     return out
+
+
+def assign_device(poses, grid_zyx, one_hm, min_radius, voxel=VOXEL_SIZE, pc_range=PC_RANGE):
+    """Same targets, built on the GPU by rtp_assign_targets: poses is a CUDA float64 tensor
+    [B, 15, 3]; returns CUDA tensors hm, ind, mask, cat, anno_pose with the reference's dtypes and shapes."""
+    import ctypes as C
+
+    import torch
+
+    from . import lib
+    assert poses.is_cuda and poses.dtype == torch.float64 and poses.shape[1:] == (15, 3)
+    poses = poses.contiguous()
+    B = poses.shape[0]
+    Z, Y, X = grid_zyx
+    ncls, M, R = (1, 1, 45) if one_hm else (15, 15, 3)
+    dev = poses.device
+    out = dict(hm=torch.empty((B, ncls, Z, Y, X), dtype=torch.float32, device=dev),
+               ind=torch.empty((B, M), dtype=torch.int64, device=dev), mask=torch.empty((B, M), dtype=torch.uint8, device=dev),
+               cat=torch.empty((B, M), dtype=torch.int64, device=dev), anno_pose=torch.empty((B, M, R), dtype=torch.float32, device=dev))
+    v = (C.c_double * 3)(*[float(a) for a in voxel])
+    r = (C.c_float * 3)(*[float(a) for a in pc_range])
+    radius = min_radius if one_hm else max(min_radius, 1)
+    lib.call("rtp_assign_targets", poses.data_ptr(), B, Z, Y, X, 1 if one_hm else 0, int(radius), v, r, out["hm"].data_ptr(),
+             out["ind"].data_ptr(), out["mask"].data_ptr(), out["cat"].data_ptr(), out["anno_pose"].data_ptr(),
+             torch.cuda.current_stream().cuda_stream)
+    return out
