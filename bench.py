@@ -197,7 +197,7 @@ def run_ours(args, rank, world, local_rank):
     #      (one step streams > 10 GB of activations through HBM) — stated in config.l2
     sampler = ClockSampler(local_rank)
     sampler.start()
-    ops.PROFILE = {"_only": {"conv_generic", "conv_k3s1", "wgrad_generic", "wgrad_k3s1"}}
+    ops.PROFILE = {"_only": {"conv_generic", "conv_k3s1", "conv_pw", "wgrad_generic", "wgrad_k3s1"}}
     lib.launch_count = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()

@@ -119,6 +119,14 @@ int rtp_conv_k3s1(const rtp_conv_k3s1_desc* d, void* stream);
  * then use rtp_conv) */
 int64_t rtp_conv_k3s1_smem_bytes(int32_t Cin, int32_t NPo, int32_t Z, int32_t X, int32_t Y);
 
+/* Pointwise (1x1x1) conv, forward or dgrad (w packed by rtp_weight_pack mode 0 / 1 with ntaps = 1): a streaming GEMM
+ * over the linear positions of the P8 tensor (bulk-copy staging, resident weights, ping-pong TMEM accumulators).
+ * replaces: the fuse-layer 1x1 convs (hr_util/hr3d.py:147-157), final_conv (backbones/hrnet3d.py:20,41) and their
+ * dgrads.  K % 16 == 0 (<= 256), NP % 16 == 0 (<= 256); mask/bias/relu/accumulate as in rtp_conv. */
+int rtp_conv_pw_supported(int32_t K, int32_t NP);
+int rtp_conv_pw(rtp_p8 in, rtp_p8 out, rtp_p8 mask, const void* w, const float* bias, int32_t K, int32_t NP,
+                int32_t out_c8, int32_t relu, int32_t accumulate, void* stream);
+
 /* ---- weight gradient ---------------------------------------------------------------------------------------
  * replaces: cuDNN wgrad inside autograd's convolution_backward for the same call sites.
  * dW[tap][ci][co] = sum_rows X[row+tap][ci] * dY[row][co]; rows and taps as in rtp_conv_desc (X plays `in`,

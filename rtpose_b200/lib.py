@@ -63,6 +63,8 @@ PROTOTYPES = {
     "rtp_weight_pack_k3s1": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "rtp_conv_k3s1": (C.c_int, [C.POINTER(ConvK3S1Desc), _vp]),
     "rtp_conv_k3s1_smem_bytes": (C.c_int64, [_i32, _i32, _i32, _i32, _i32]),
+    "rtp_conv_pw_supported": (C.c_int, [_i32, _i32]),
+    "rtp_conv_pw": (C.c_int, [P8Struct, P8Struct, P8Struct, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "rtp_wgrad_workspace_bytes": (C.c_int64, [_i32, _i32, _i32, _i32]),
     "rtp_wgrad": (C.c_int, [C.POINTER(WgradDesc), _vp]),
     "rtp_wgrad_reduce": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),

@@ -215,6 +215,29 @@ def out_grid(x, stride):
     return ((x.Z - 1) // stride + 1, (x.Y - 1) // stride + 1, (x.X - 1) // stride + 1) if stride > 1 else x.grid
 
 
+USE_PW = True    # route 1x1x1 convs through the streaming pointwise kernel (rtp_conv_pw)
+
+
+def _dense_planes(t):
+    return t.c_stride == t.Z * (t.X + 2) * (t.Y + 2) * 8
+
+
+def pw_eligible(x, out, KP, NP):
+    return (x.C8 * 8 >= KP and _dense_planes(x) and _dense_planes(out) and x.grid == out.grid
+            and lib.load().rtp_conv_pw_supported(KP, NP) == 1)
+
+
+def conv_pw(x, wpack, KP, NP, out, bias=None, mask=None, relu=False, accumulate=False, real=None):
+    """Pointwise conv / dgrad (rtp_conv_pw)."""
+    rc = real or (KP, NP)
+    key = ("conv_pw", rc[0], rc[1], 1, 1, 1, (x.Z, x.X, x.Y))
+    ev = _prof_begin(key)
+    lib.call("rtp_conv_pw", x.struct(), out.struct(), mask.struct() if mask is not None else lib.NULL_P8, wpack.data_ptr(),
+             bias.data_ptr() if bias is not None else None, KP, NP, out.C8, int(relu), int(accumulate), _stream())
+    _prof_end(key, ev, 2.0 * x.N * x.voxels * rc[0] * rc[1])
+    return out
+
+
 USE_K3S1 = True  # route eligible 3x3x3 stride-1 convs through the plane-streaming kernel (rtp_conv_k3s1)
 
 
@@ -253,6 +276,11 @@ def conv_forward(packs, x, w, stride, out, bias=None, relu=False, res=None, ci0=
     k = w.shape[2]
     if k == 3 and stride == 1 and ci0 == 0 and ci_n is None and k3s1_eligible(x, ceil_to(w.shape[1], 16), ceil_to(w.shape[0], 16)):
         return conv_k3s1(packs, x, w, out, False, bias=bias, relu=relu, res=res, key=key, version=version)
+    if k == 1 and stride == 1 and res is None and USE_PW:
+        wp, KP, NP = packs.get(w, 0, ci0, ci_n, key, version)
+        if pw_eligible(x, out, KP, NP):
+            return conv_pw(x, wp, KP, NP, out, bias=pad_bias(bias, NP), relu=relu,
+                           real=(ci_n if ci_n is not None else w.shape[1], w.shape[0]))
     wp, KP, NP = packs.get(w, 0, ci0, ci_n, key, version)
     return conv(x, wp, KP, NP, out, taps_fwd(k), (out.Z, out.X, out.Y), IS=stride, bias=pad_bias(bias, NP), res=res,
                 relu=relu, real=(ci_n if ci_n is not None else w.shape[1], w.shape[0]))
@@ -274,6 +302,8 @@ def conv_dgrad(packs, dy, w, stride, dx, mask=None, accumulate=False, ci0=0, ci_
         return dx
     wp, KP, NP = packs.get(w, 1, ci0, ci_n, key, version)
     real = (w.shape[0], ci_n if ci_n is not None else w.shape[1])
+    if k == 1 and stride == 1 and USE_PW and pw_eligible(dy, dx, KP, NP):
+        return conv_pw(dy, wp, KP, NP, dx, mask=mask, accumulate=accumulate, real=real)
     if stride == 1:
         return conv(dy, wp, KP, NP, dx, taps_dgrad_s1(k), (dx.Z, dx.X, dx.Y), mask=mask, accumulate=accumulate, real=real)
     assert stride == 2 and k == 3
