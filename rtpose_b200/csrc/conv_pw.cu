@@ -14,7 +14,7 @@ using namespace tc05;
 
 namespace {
 
-constexpr int kThreads = 192;  // warp 0 producer, warp 1 MMA, warps 2-5 epilogue
+constexpr int kThreads = 320;  // warp 0 producer, warp 1 MMA, warps 2-5 / 6-9 epilogue groups (one TMEM accumulator each)
 constexpr int kMaxStages = 8;
 
 struct PW {
@@ -51,19 +51,24 @@ __global__ void __launch_bounds__(kThreads, 1) conv_pw_kernel(const __grid_const
   const uint32_t tmem = tmem_base_s;
 
   if (warp == 0) {
+    // lane 0 runs the barrier protocol; the K/8 chunk copies of a tile are issued by K/8 lanes at once (a single
+    // thread issuing 2 KB bulk copies back to back tops out near 8 GB/s per SM, see profiles/r01_bulk_probe.txt)
     if (lane == 0) {
       mbar_arrive_expect_tx(&bar_w, p.w_bytes);
       bulk_g2s(wsm, p.w, p.w_bytes, &bar_w);
-      uint32_t it = 0;
-      for (int u = blockIdx.x; u < p.nunits; u += gridDim.x, ++it) {
-        const int tile = u % p.ntile, n = u / p.ntile;
-        const int s = it % S;
+    }
+    uint32_t it = 0;
+    for (int u = blockIdx.x; u < p.nunits; u += gridDim.x, ++it) {
+      const int tile = u % p.ntile, n = u / p.ntile;
+      const int s = it % S;
+      if (lane == 0) {
         mbar_wait(&bar_empty[s], ((it / S) & 1) ^ 1);
         mbar_arrive_expect_tx(&bar_full[s], p.stage_bytes);
-        const bf16* src = p.in.ptr + (int64_t)n * p.in.n_stride + (int64_t)tile * 128 * 8;
-        uint8_t* dst = stages + (size_t)s * p.stage_bytes;
-        for (int c = 0; c < kch; ++c) bulk_g2s(dst + (size_t)c * 2048, src + (int64_t)c * p.in.c_stride, 2048, &bar_full[s]);
       }
+      __syncwarp();
+      const bf16* src = p.in.ptr + (int64_t)n * p.in.n_stride + (int64_t)tile * 128 * 8;
+      uint8_t* dst = stages + (size_t)s * p.stage_bytes;
+      for (int c = lane; c < kch; c += 32) bulk_g2s(dst + (size_t)c * 2048, src + (int64_t)c * p.in.c_stride, 2048, &bar_full[s]);
     }
   } else if (warp == 1) {
     const uint32_t idesc = idesc_bf16(128, p.NP, 0, 0);
@@ -88,53 +93,68 @@ __global__ void __launch_bounds__(kThreads, 1) conv_pw_kernel(const __grid_const
       __syncwarp();
     }
   } else {
-    const int lane_q = warp & 3;
+    const int lane_q = warp & 3, grp = (warp - 2) >> 2;   // group g drains accumulator g (tiles with it&1 == g)
     const int r = lane_q * 32 + lane;
-    const uint32_t trow = tmem + ((uint32_t)(lane_q * 32) << 16);
+    const uint32_t trow = tmem + ((uint32_t)(lane_q * 32) << 16) + grp * p.NP;
     const int Yp = p.out.Yp, Xp = p.out.Xp;
     uint32_t it = 0;
     for (int u = blockIdx.x; u < p.nunits; u += gridDim.x, ++it) {
-      const int tile = u % p.ntile, n = u / p.ntile, buf = it & 1;
+      if ((int)(it & 1) != grp) continue;
+      const int tile = u % p.ntile, n = u / p.ntile;
       const int q = tile * 128 + r;                        // linear position inside the sample (all planes)
       const int yp = q % Yp, xp = (q / Yp) % Xp;
       const bool ok = q < p.npos && xp >= 1 && xp <= p.out.X && yp >= 1 && yp <= p.out.Y;
       bf16* out_row = p.out.ptr + (int64_t)n * p.out.n_stride + (int64_t)q * 8;
-      const bf16* mask_row = p.has_mask ? p.mask.ptr + (int64_t)n * p.mask.n_stride + (int64_t)q * 8 : nullptr;
-      mbar_wait(&bar_acc_full[buf], (it >> 1) & 1);
-      fence_after_sync();
-      for (int c16 = 0; c16 * 16 < p.NP; ++c16) {
-        uint32_t v[16];
-        tmem_ld16(trow + buf * p.NP + c16 * 16, v);
-        tmem_ld_wait();
-        if (c16 * 16 + 16 >= p.NP) {
-          fence_before_sync();
-          mbar_arrive(&bar_acc_empty[buf]);
-        }
+      const bf16* mask_row = p.mask.ptr + (int64_t)n * p.mask.n_stride + (int64_t)q * 8;
+      // mask / accumulate operands of the first 4 chunks are fetched before the accumulator wait
+      uint4 pm[4], pa[4];
+      const bool pre = ok && p.out_c8 <= 4;
+      if (pre) {
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int ch = c16 * 2 + h;
-          if (ch >= p.out_c8 || !ok) continue;
+        for (int c = 0; c < 4; ++c) {
+          if (c < p.out_c8 && p.has_mask) pm[c] = ldg16(mask_row + c * p.mask.c_stride);
+          if (c < p.out_c8 && p.accumulate) pa[c] = *reinterpret_cast<const uint4*>(out_row + c * p.out.c_stride);
+        }
+      }
+      mbar_wait(&bar_acc_full[grp], (it >> 1) & 1);
+      fence_after_sync();
+      for (int c32 = 0; c32 * 32 < p.NP; ++c32) {
+        uint32_t v[32];
+        const bool wide = c32 * 32 + 32 <= p.NP;
+        if (wide) tmem_ld32(trow + c32 * 32, v); else tmem_ld16(trow + c32 * 32, *reinterpret_cast<uint32_t(*)[16]>(v));
+        tmem_ld_wait();
+        if (c32 * 32 + 32 >= p.NP) {
+          fence_before_sync();
+          mbar_arrive(&bar_acc_empty[grp]);
+        }
+        if (!ok) continue;
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          const int ch = c32 * 4 + h;
+          if (ch >= p.out_c8 || (!wide && h >= 2)) continue;
           float f[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[h * 8 + i]);
           if (p.bias) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) f[i] += __ldg(p.bias + ch * 8 + i);
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + ch * 8));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + ch * 8 + 4));
+            f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+            f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
           }
           if (p.relu) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
           }
-          if (mask_row) {
+          if (p.has_mask) {
             float g[8];
-            unpack8(ldg16(mask_row + ch * p.mask.c_stride), g);
+            unpack8((pre && c32 == 0) ? pm[h] : ldg16(mask_row + ch * p.mask.c_stride), g);
 #pragma unroll
             for (int i = 0; i < 8; ++i) f[i] = g[i] > 0.f ? f[i] : 0.f;
           }
           bf16* dst = out_row + ch * p.out.c_stride;
           if (p.accumulate) {
             float g[8];
-            unpack8(*reinterpret_cast<const uint4*>(dst), g);
+            unpack8((pre && c32 == 0) ? pa[h] : *reinterpret_cast<const uint4*>(dst), g);
 #pragma unroll
             for (int i = 0; i < 8; ++i) f[i] += g[i];
           }

@@ -2,15 +2,23 @@
 //
 //   dW[kz][ky][kx][ci][co] = sum_{n,z,q} X[n, z+kz-1, q + (kx-1)*Yp + (ky-1)][ci] * dY[n, z, q][co]
 //
-// GEMM view: K = in-plane positions q (both operands MN-major straight out of the P8 layout).  A stacks the three
-// X planes z-1, z, z+1 along M ((kz, ci) = 96 rows, padded to the UMMA M = 128), B is the dY plane (N = Cout padded
-// to 16); the 9 in-plane taps are 9 accumulators [128 x NP] resident in TMEM, addressed — like in conv_k3s1.cu — by
-// shifting the A descriptor's start address over ONE staged copy of the input rows.  Each persistent CTA walks
-// (sample, 128-position tile) units over all z planes and writes one fp32 partial at the end; a second kernel sums
-// the per-CTA partials in a fixed order (deterministic) into the reference's [Cout][Cin][3][3][3] layout.
+// GEMM view: K = in-plane positions q, both operands MN-major straight out of the P8 layout.  Each step consumes ONE
+// X plane zx of a 128-position tile:
+//   A (M = 16 groups of 8 rows, group 4c+kx = channel chunk c of the X tile shifted by (kx-1) rows; groups 4c+3 are
+//     padding): the +-1 position shift (ky) is a 16-byte shift of the descriptor start.  When a row is at least 65
+//     positions wide ("span mode") the four groups of a chunk are ONE staged span of 4 rows read at a group stride of
+//     one row (SBO = Yp*16 B), so X is fetched once, in 4 bulk copies per step; narrower planes stage three shifted
+//     copies per chunk (12 copies of 130 positions).  Few, large copies matter: a bulk copy costs ~30 ns + bytes at
+//     ~68 GB/s per SM (tools/bulk_probe.cu).
+//   B (N = (jz, co) = 3*NP columns): the dY planes zx-1, zx, zx+1 (kz = 2-jz), which sit in consecutive slots of a
+//     ring of dY plane tiles.  Every dY plane is fetched once per tile; the first two ring slots are mirrored behind
+//     the last one so a 3-plane window never wraps.  Planes -1 and Z are copies of a zero page.
+// => 3 accumulators [128 x 3*NP] (one per ky) live in TMEM for the whole kernel; an MMA is M128 x N96 x K16
+// (56 issue cycles by the measured operand-bandwidth law, vs 3 x 45 for the N=32 form this replaces).  Each
+// persistent CTA walks (sample, tile) units over all z planes and writes one fp32 partial at the end; a second kernel
+// sums the per-CTA partials in a fixed order (deterministic) into the reference's [Cout][Cin][3][3][3] layout.
 //
-// Roofline: tensor pipe; SMEM operand bandwidth (128 B/clk) caps M=128,N=32 at ~35 % and one of the four stacked
-// plane slots is padding, so the ceiling is ~27 % of the bf16 peak (see DESIGN.md for the N=64 two-role variant).
+// Roofline: tensor pipe.  96 of the 128 M rows are useful, so the ceiling is 75 % of the N=96 issue rate.
 #include "common.cuh"
 #include "tc05.cuh"
 
@@ -20,17 +28,23 @@ namespace {
 
 constexpr int kThreads = 192;  // warp 0 producer, warp 1 MMA, warps 2-5 final epilogue
 constexpr int kMaxStages = 4;
+constexpr int kXW = 130;                       // staged positions per X copy: 128 + the two ky halo positions
+constexpr uint32_t kXCopyStage = 16u * kXW * 16u;  // copy mode: 16 group slots (4 of them unused)
 
 struct WG3 {
   P8 x, dy;
-  const bf16* zero_page;  // >= PW*16*4 bytes of zeros (stands in for the planes z = -1 and z = Z)
+  const bf16* zero_page;  // >= 2048 bytes of zeros (stands in for the dY planes z = -1 and z = Z)
   int NP;                 // dY channels padded to 16
-  int PW;                 // staged positions per plane: 128 + 2*Yp + 2
-  int ntile, nunits, nstages;
+  int ntile, nunits;
+  int nstages;            // X stages (one step each)
+  int R;                  // dY ring slots (+2 mirror slots behind them)
   int valid_pos;          // X*Yp: positions past this in the last tile are skipped in whole k16 steps
-  uint32_t xplane_bytes;  // 4 chunks * PW * 16
-  uint32_t stage_bytes;   // 4 plane slots + dY tile
-  float* partial;         // [gridDim.x][9][128][NP]
+  uint32_t slot_bytes;    // NP/8 chunks x 128 positions x 16 B
+  float* partial;         // [gridDim.x][3 ky][128][3*NP]
+  int span;               // 1: span mode (see header)
+  uint32_t xstage_bytes;  // 16 groups x group stride
+  uint32_t a_sbo;         // A group stride in 16-byte units: Yp (span) or kXW (copies)
+  int dbg;                // tools only: 1 = no X copies, 2 = no MMAs, 4 = no dY copies (results are garbage)
 };
 
 __global__ void __launch_bounds__(kThreads, 1) wgrad_k3s1_kernel(const __grid_constant__ WG3 p) {
@@ -39,8 +53,8 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_k3s1_kernel(const __grid_co
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int S = p.nstages, Z = p.x.Z, Yp = p.x.Yp;
-  const uint32_t dy_bytes = (uint32_t)(p.NP / 8) * 128 * 16;
+  const int S = p.nstages, R = p.R, Z = p.x.Z, Yp = p.x.Yp, ZP = Z + 2;
+  uint8_t* ring = smem + (size_t)S * p.xstage_bytes;
 
   if (tid == 0) {
     for (int s = 0; s < S; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
@@ -55,97 +69,119 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_k3s1_kernel(const __grid_co
   const bool has_work = (int)blockIdx.x < p.nunits;
 
   if (warp == 0) {
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (int u = blockIdx.x; u < p.nunits; u += gridDim.x) {
-        const int tile = u % p.ntile, n = u / p.ntile;
-        const int64_t qoff = ((int64_t)tile * 128 - 1) * 8;      // staged X rows start at q0 - Yp - 1
-        const int64_t q0 = ((int64_t)Yp + (int64_t)tile * 128) * 8;
-        const bf16* xn = p.x.ptr + (int64_t)n * p.x.n_stride + qoff;
-        const bf16* dn = p.dy.ptr + (int64_t)n * p.dy.n_stride + q0;
-        for (int z = 0; z < Z; ++z) {
-          const int s = it % S;
+    // producer warp: lane 0 runs the barrier protocol, then all lanes issue the step's bulk copies in parallel
+    uint32_t it = 0, gbase = 0;  // CTA-local step counter / plane counter at the start of the unit
+    const int nch = p.NP / 8;
+    for (int u = blockIdx.x; u < p.nunits; u += gridDim.x, gbase += ZP) {
+      const int tile = u % p.ntile, n = u / p.ntile;
+      const int64_t q0 = (int64_t)Yp + (int64_t)tile * 128;
+      const bf16* xn = p.x.ptr + (int64_t)n * p.x.n_stride + (q0 - 1 - Yp) * 8;
+      const bf16* dn = p.dy.ptr + (int64_t)n * p.dy.n_stride + q0 * 8;
+      for (int zx = 0; zx < Z; ++zx, ++it) {
+        const int s = it % S;
+        // dY planes fetched with this step: -1, 0, 1 at the start of a unit, zx+1 afterwards
+        const int pz_lo = zx == 0 ? -1 : zx + 1, npl = zx == 0 ? 3 : 1;
+        if (lane == 0) {
           mbar_wait(&bar_empty[s], ((it / S) & 1) ^ 1);
-          mbar_arrive_expect_tx(&bar_full[s], 3 * p.xplane_bytes + dy_bytes);
-          uint8_t* dst = smem + (size_t)s * p.stage_bytes;
-          for (int i = 0; i < 3; ++i) {
-            const int zx = z + i - 1;
-            const bool ok = zx >= 0 && zx < Z;
-            for (int c = 0; c < 4; ++c) {
-              const bf16* src = ok ? xn + (int64_t)c * p.x.c_stride + (int64_t)zx * p.x.plane_elems() : p.zero_page;
-              bulk_g2s(dst + (size_t)(i * 4 + c) * p.PW * 16, src, p.PW * 16, &bar_full[s]);
+          uint32_t bytes = (p.dbg & 1) ? 0u : (p.span ? p.xstage_bytes : 12u * kXW * 16u);
+          for (int i = 0; i < npl; ++i) {
+            const uint32_t g = gbase + pz_lo + i + 1, sl = g % R;
+            if (!(p.dbg & 4)) bytes += p.slot_bytes * (sl < 2 ? 2u : 1u);
+            if (g >= (uint32_t)R) {
+              // the slot's previous plane was last read by step t of this CTA; make sure that step has retired
+              const uint32_t gp = g - R, kprev = gp / ZP;
+              const int pzp = (int)(gp % ZP) - 1;
+              const uint32_t t = kprev * Z + (uint32_t)(pzp + 1 < Z - 1 ? pzp + 1 : Z - 1);
+              if (t + S > it) mbar_wait(&bar_empty[t % S], (t / S) & 1);
             }
           }
-          uint8_t* ddst = dst + 4 * p.xplane_bytes;
-          for (int c = 0; c < p.NP / 8; ++c) {
-            const bf16* src = c < p.dy.C8 ? dn + (int64_t)c * p.dy.c_stride + (int64_t)z * p.dy.plane_elems() : p.zero_page;
-            bulk_g2s(ddst + (size_t)c * 2048, src, 2048, &bar_full[s]);
+          mbar_arrive_expect_tx(&bar_full[s], bytes);
+        }
+        __syncwarp();
+        uint8_t* xdst = smem + (size_t)s * p.xstage_bytes;
+        const bf16* xz = xn + (int64_t)zx * p.x.plane_elems();
+        const int nx = p.span ? 4 : 12;
+        const int ncopy = nx + npl * 2 * nch;
+        for (int i = lane; i < ncopy; i += 32) {
+          if (p.dbg & (i < nx ? 1 : 4)) continue;
+          if (i < nx) {
+            if (p.span) {  // chunk i: 4 rows starting one row above the tile
+              bulk_g2s(xdst + (size_t)i * (p.xstage_bytes >> 2), xz + (int64_t)i * p.x.c_stride, p.xstage_bytes >> 2, &bar_full[s]);
+            } else {       // chunk c shifted by j rows -> group slot 4c + j
+              const int j = i >> 2, c = i & 3;
+              bulk_g2s(xdst + (size_t)(4 * c + j) * (kXW * 16), xz + (int64_t)c * p.x.c_stride + (int64_t)j * Yp * 8, kXW * 16,
+                       &bar_full[s]);
+            }
+          } else {
+            const int d = i - nx, pi = d / (2 * nch), rem = d - pi * 2 * nch, c = rem >> 1, mirror = rem & 1;
+            const int pz = pz_lo + pi;
+            const uint32_t sl = (gbase + pz + 1) % R;
+            if (mirror && sl >= 2) continue;
+            const bool real = pz >= 0 && pz < Z && c < p.dy.C8;
+            const bf16* src = real ? dn + (int64_t)c * p.dy.c_stride + (int64_t)pz * p.dy.plane_elems() : p.zero_page;
+            bulk_g2s(ring + (size_t)(mirror ? R + sl : sl) * p.slot_bytes + (size_t)c * 2048, src, 2048, &bar_full[s]);
           }
-          ++it;
         }
       }
     }
   } else if (warp == 1) {
-    {  // warp-uniform control flow; only the MMA / commit instructions are predicated on the leader lane
-      const bool leader = lane == 0;
-      uint32_t it = 0;
-      bool first = true;
-      const uint32_t idesc = idesc_bf16(128, p.NP, 1, 1);
-      const uint32_t a_hi = (uint32_t)p.PW | (1u << 14), b_hi = 128u | (1u << 14);
-      const uint32_t smem0 = smem_u32(smem);
-      for (int u = blockIdx.x; u < p.nunits; u += gridDim.x) {
-        const int tile = u % p.ntile;
-        int nk16 = (p.valid_pos - tile * 128 + 15) / 16;  // whole 16-position K steps inside the plane
-        nk16 = nk16 > 8 ? 8 : nk16;
-        for (int z = 0; z < Z; ++z) {
-          const int s = it % S;
-          mbar_wait(&bar_full[s], (it / S) & 1);
-          fence_after_sync();
-          // descriptor halves (SWIZZLE_NONE, MN-major): lo = start>>4 | (LBO = 128 B)>>4 << 16 ; hi = SBO>>4 | version
-          const uint32_t xbase = smem0 + (uint32_t)s * p.stage_bytes;
-          const uint32_t a_lo = (8u << 16) + (xbase >> 4);
-          const uint32_t b_lo = (8u << 16) + ((xbase + 4 * p.xplane_bytes) >> 4);
-          if (elect_one()) {  // elect.sync => no per-MMA waterfall loop in SASS
+    // warp-uniform control flow; the MMA / commit instructions sit in elect.sync blocks
+    uint32_t it = 0, gbase = 0;
+    bool first = true;
+    const int N3 = 3 * p.NP;
+    const uint32_t idesc = idesc_bf16(128, N3, 1, 1);
+    const uint32_t a_hi = p.a_sbo | (1u << 14), b_hi = 128u | (1u << 14);
+    const uint32_t smem0 = smem_u32(smem), ring0 = smem_u32(ring);
+    for (int u = blockIdx.x; u < p.nunits; u += gridDim.x, gbase += ZP) {
+      const int tile = u % p.ntile;
+      int nk16 = (p.valid_pos - tile * 128 + 15) / 16;  // whole 16-position K steps inside the plane
+      nk16 = nk16 > 8 ? 8 : nk16;
+      for (int zx = 0; zx < Z; ++zx, ++it) {
+        const int s = it % S;
+        mbar_wait(&bar_full[s], (it / S) & 1);
+        fence_after_sync();
+        // descriptor halves (SWIZZLE_NONE, MN-major): lo = start>>4 | (LBO = 128 B)>>4 << 16 ; hi = SBO>>4 | version
+        const uint32_t a_lo = (8u << 16) + ((smem0 + (uint32_t)s * p.xstage_bytes) >> 4);
+        const uint32_t b_lo = (8u << 16) + ((ring0 + ((gbase + zx) % R) * p.slot_bytes) >> 4);
+        if (elect_one()) {
 #pragma unroll
-            for (int t9 = 0; t9 < 9; ++t9) {
-              const uint32_t at = a_lo + (uint32_t)((t9 / 3) * Yp + (t9 % 3));
+          for (int ky = 0; ky < 3; ++ky) {
 #pragma unroll
-              for (int k16 = 0; k16 < 8; ++k16) {
-                if (k16 < nk16)
-                  mma_ss(tmem + t9 * p.NP, ((uint64_t)a_hi << 32) | (at + k16 * 16), ((uint64_t)b_hi << 32) | (b_lo + k16 * 16),
-                         idesc, (first && k16 == 0) ? 0u : 1u);
-              }
+            for (int k16 = 0; k16 < 8; ++k16) {
+              if (k16 < nk16 && !((p.dbg & 2) && it > 0))
+                mma_ss(tmem + ky * N3, ((uint64_t)a_hi << 32) | (a_lo + ky + k16 * 16), ((uint64_t)b_hi << 32) | (b_lo + k16 * 16),
+                       idesc, (first && k16 == 0) ? 0u : 1u);
             }
-            mma_commit(&bar_empty[s]);
           }
-          __syncwarp();
-          first = false;
-          ++it;
+          mma_commit(&bar_empty[s]);
         }
+        __syncwarp();
+        first = false;
       }
-      if (has_work && leader) mma_commit(&bar_done);
     }
+    if (has_work && lane == 0) mma_commit(&bar_done);
   } else {
-    // final epilogue: 9 accumulators -> fp32 partial of this CTA
+    // final epilogue: 3 accumulators -> fp32 partial of this CTA
     const int lane_q = warp & 3;
     const int r = lane_q * 32 + lane;
+    const int N3 = 3 * p.NP;
     if (has_work) {
       mbar_wait(&bar_done, 0);
       fence_after_sync();
     }
     const uint32_t trow = tmem + ((uint32_t)(lane_q * 32) << 16);
-    for (int t9 = 0; t9 < 9; ++t9) {
-      float* dst = p.partial + (((size_t)blockIdx.x * 9 + t9) * 128 + r) * p.NP;
-      for (int c16 = 0; c16 * 16 < p.NP; ++c16) {
+    for (int ky = 0; ky < 3; ++ky) {
+      float* dst = p.partial + (((size_t)blockIdx.x * 3 + ky) * 128 + r) * N3;
+      for (int c16 = 0; c16 * 16 < N3; ++c16) {
         uint32_t v[16];
         if (has_work) {
-          tmem_ld16(trow + t9 * p.NP + c16 * 16, v);
+          tmem_ld16(trow + ky * N3 + c16 * 16, v);
           tmem_ld_wait();
         } else {
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = 0u;
         }
-        if (r < 96) {
+        if (((r >> 3) & 3) != 3) {
 #pragma unroll
           for (int i = 0; i < 16; i += 4)
             *reinterpret_cast<float4*>(dst + c16 * 16 + i) =
@@ -159,7 +195,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_k3s1_kernel(const __grid_co
   if (warp == 1) tmem_dealloc<512>(tmem);
 }
 
-// partial[split][t9 = kx*3+ky][(kz*4 + c)*8 + ci8][n] -> dW[co][ci0 + ci][kz][ky][kx]
+// partial[split][ky][((ci/8)*4 + kx)*8 + ci%8][(2-kz)*NP + n] -> dW[co][ci0 + ci][kz][ky][kx]
 __global__ void __launch_bounds__(256) wgrad_k3s1_reduce_kernel(const float* __restrict__ partial, int nsplit, int NP,
                                                                 float* __restrict__ dW, int Cin_total, int co_n, int n0,
                                                                 int ci0, int accumulate) {
@@ -178,9 +214,7 @@ __global__ void __launch_bounds__(256) wgrad_k3s1_reduce_kernel(const float* __r
       ci = r % 32;
       tap = r / 32;  // (kz*3 + ky)*3 + kx
       const int kz = tap / 9, ky = (tap / 3) % 3, kx = tap % 3;
-      const int t9 = kx * 3 + ky;
-      const int m = (kz * 4 + (ci >> 3)) * 8 + (ci & 7);
-      const float* src = partial + ((size_t)t9 * 128 + m) * NP + n0 + co;
+      const float* src = partial + ((size_t)ky * 128 + ((ci >> 3) * 4 + kx) * 8 + (ci & 7)) * (3 * NP) + (2 - kz) * NP + n0 + co;
       for (int s = sl; s < nsplit; s += 8) acc += src[s * sstride];
     }
     sh[sl][o] = acc;
@@ -196,24 +230,40 @@ __global__ void __launch_bounds__(256) wgrad_k3s1_reduce_kernel(const float* __r
   }
 }
 
-int plan_stages(int NP, int Y, uint32_t& xplane_bytes, uint32_t& stage_bytes, int& PW) {
-  PW = 128 + 2 * (Y + 2) + 2;
-  xplane_bytes = 4u * PW * 16;
-  stage_bytes = 4 * xplane_bytes + (uint32_t)(NP / 8) * 2048;
-  int S = (int)((220 * 1024) / stage_bytes);
-  return S > kMaxStages ? kMaxStages : S;
+// X stages + dY ring (R slots + 2 mirrors); returns false if even the smallest configuration does not fit
+bool plan(int NP, int Y, int& S, int& R, int& span, uint32_t& xstage, uint32_t& slot_bytes, size_t& smem) {
+  const int Yp = Y + 2;
+  span = (Yp >= 65 && Yp <= kXW) ? 1 : 0;  // 130 + 2*Yp staged positions must fit the 4-row span
+  xstage = span ? 16u * Yp * 16u : kXCopyStage;
+  slot_bytes = (uint32_t)(NP / 8) * 2048;
+  const size_t budget = 220 * 1024;
+  for (S = kMaxStages; S >= 2; --S) {
+    R = (int)((budget - (size_t)S * xstage) / slot_bytes) - 2;
+    if (R > 14) R = 14;
+    if (R >= S + 2) break;
+  }
+  if (S < 2) {
+    S = 2;
+    R = (int)((budget - 2 * (size_t)xstage) / slot_bytes) - 2;
+    if (R < 3) return false;
+  }
+  smem = (size_t)S * xstage + (size_t)(R + 2) * slot_bytes;
+  return true;
 }
 
 }  // namespace
+
+extern "C" { int rtp_wgrad_k3s1_dbg = 0; }  // tools/dbg_wgrad.py only; not part of the ABI
 
 extern "C" int64_t rtp_wgrad_k3s1_workspace_bytes(int32_t NP, int32_t nsm) { return (int64_t)nsm * 9 * 128 * NP * 4; }
 extern "C" int64_t rtp_wgrad_k3s1_zero_bytes(int32_t Y) { return (int64_t)(128 + 2 * (Y + 2) + 2) * 16 + 2048; }
 
 extern "C" int rtp_wgrad_k3s1_supported(int32_t Cin, int32_t NP, int32_t Z, int32_t X, int32_t Y) {
   if (Cin != 32 || NP % 16 != 0 || NP < 16 || 9 * NP > 512 || Y < 6) return 0;
-  uint32_t a, b;
-  int PW;
-  return plan_stages(NP, Y, a, b, PW) >= 2 && Z >= 1 && X >= 1 ? 1 : 0;
+  int S, R, span;
+  uint32_t xs, sb;
+  size_t smem;
+  return plan(NP, Y, S, R, span, xs, sb, smem) && Z >= 1 && X >= 1 ? 1 : 0;
 }
 
 extern "C" int rtp_wgrad_k3s1(rtp_p8 x, rtp_p8 dy, int32_t NP, const void* zero_page, float* workspace, int32_t* nsplit_out,
@@ -224,13 +274,16 @@ extern "C" int rtp_wgrad_k3s1(rtp_p8 x, rtp_p8 dy, int32_t NP, const void* zero_
   RTP_CHECK_ARG(x.c_stride == (int64_t)x.Z * (x.X + 2) * (x.Y + 2) * 8 && dy.c_stride == x.c_stride,
                 "rtp_wgrad_k3s1: planes must be contiguous per channel chunk");
   WG3 k;
+  size_t smem;
   k.x = P8(x); k.dy = P8(dy); k.zero_page = (const bf16*)zero_page; k.NP = NP;
-  k.nstages = plan_stages(NP, x.Y, k.xplane_bytes, k.stage_bytes, k.PW);
+  plan(NP, x.Y, k.nstages, k.R, k.span, k.xstage_bytes, k.slot_bytes, smem);
   const int Yp = x.Y + 2;
+  k.a_sbo = k.span ? (uint32_t)Yp : (uint32_t)kXW;
   k.valid_pos = x.X * Yp;
   k.ntile = (k.valid_pos + 127) / 128;
   k.nunits = x.N * k.ntile;
   k.partial = workspace;
+  k.dbg = rtp_wgrad_k3s1_dbg;
   static int nsm = 0;
   if (!nsm) {
     int dev = 0;
@@ -239,7 +292,6 @@ extern "C" int rtp_wgrad_k3s1(rtp_p8 x, rtp_p8 dy, int32_t NP, const void* zero_
   }
   const int grid = k.nunits < nsm ? k.nunits : nsm;
   *nsplit_out = grid;
-  const size_t smem = (size_t)k.nstages * k.stage_bytes;
   static size_t configured = 0;
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(wgrad_k3s1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -419,6 +419,9 @@ WGRAD3_CASES = [
     (2, 32, 1, (8, 12, 10)),        # NP = 16, dY has one chunk
     (1, 128, 64, (6, 14, 12)),      # 4 input groups x 2 output groups (the merged head conv)
     (1, 64, 64, (3, 8, 10)),
+    (1, 32, 45, (2, 70, 9)),        # span mode (row >= 65 positions), NP = 48, dY ring wraps with two planes
+    (2, 32, 32, (1, 64, 5)),        # span mode, single plane
+    (1, 32, 32, (1, 9, 7)),         # copy mode, single plane
 ]
 
 
