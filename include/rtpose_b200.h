@@ -260,6 +260,11 @@ int rtp_dcn_bwd_weight(const float* x, const float* offset, const float* dy, flo
 int64_t rtp_adam_workspace_bytes(void);
 int rtp_adam_step(float* param, const float* grad, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                   float eps, float wd, int32_t step, float max_norm, float* workspace, float* grad_norm_out, void* stream);
+/* Same step with the hyper-parameters read from DEVICE memory: hyper = {lr, beta1, beta2, eps, wd, 1 - beta1^t,
+ * sqrt(1 - beta2^t), max_norm} (8 floats).  Lets a CUDA graph that captured the whole training step be replayed along
+ * the one-cycle schedule (learning_schedules_fastai.py:53-95) by rewriting 32 bytes between replays. */
+int rtp_adam_step_dev(float* param, const float* grad, float* m, float* v, int64_t n, const float* hyper, float* workspace,
+                      float* grad_norm_out, void* stream);
 /* N1 CenterNet target assignment on the device.  replaces: AssignLabelPose / AssignLabelPose2.__call__
  * (det3d/datasets/pipelines/pose.py:186-255, :385-452) with gaussian3D / draw_gaussian3D
  * (det3d/core/utils/center_utils.py:67-91).  poses: device fp64 [B][15][3] metres; voxel_xyz (fp64) and range_xyz (fp32)

@@ -167,50 +167,60 @@ __global__ void __launch_bounds__(256) fuse_sum_kernel(const __grid_constant__ F
   }
 }
 
-// candidate dst range [lo, hi] along one axis whose interpolation touches source index l
-__device__ __forceinline__ void dst_range(int l, int in, int out, float scale, int& lo, int& hi) {
-  if (scale <= 0.f) { lo = 0; hi = out - 1; return; }
-  lo = (int)floorf((float)(l - 1) / scale) - 1;
-  hi = (int)ceilf((float)(l + 1) / scale) + 1;
-  lo = lo < 0 ? 0 : lo;
-  hi = hi > out - 1 ? out - 1 : hi;
-}
-__device__ __forceinline__ float axis_weight(int d, int l, int in, float scale) {
-  const Axis a = ac_axis(d, in, scale);
-  return (a.i0 == l ? a.w0 : 0.f) + (a.i1 == l ? a.w1 : 0.f);
+// Weight of source index l in the interpolation of destination d (ac_axis): a hat function of src = scale*d around l,
+// written with the same fp32 expressions the forward uses (w0 = 1 - (src - i0), w1 = src - i0).
+__device__ __forceinline__ float hat_weight(int d, int l, float scale) {
+  const float src = scale * (float)d;
+  const float w = src >= (float)l ? 1.f - (src - (float)l) : src - (float)(l - 1);
+  return w > 0.f ? w : 0.f;
 }
 
 // Transpose of the trilinear upsample, applied separably: U^T = Uz^T Ux^T Uy^T.  One launch reduces ONE axis:
 //   out[.., l, ..] (=|+=) sum_d w(d -> l) * in[.., d, ..]      (gather form, deterministic)
 // so the full-resolution gradient is read ~once instead of once per low-res footprint (8x..27x).
-// axis: 0 = z, 1 = x, 2 = y.  `in` and `out` differ only in the extent of `axis`.
+// axis: 0 = z, 1 = x, 2 = y.  `in` and `out` differ only in the extent of `axis`.  The destinations touching l are
+// the d with |scale*d - l| < 1; they are visited four at a time with clamped indices (weight 0 outside the range) so
+// the loads of a group are independent and issue back to back.
 __global__ void __launch_bounds__(256) upsample_bwd_axis_kernel(P8 in, P8 out, int C8, int axis, int accumulate) {
   const int in_n = axis == 0 ? in.Z : (axis == 1 ? in.X : in.Y);
   const int out_n = axis == 0 ? out.Z : (axis == 1 ? out.X : out.Y);
   const float scale = ac_scale(out_n, in_n);  // low-res (out) is the interpolation source, high-res (in) the dest
-  const int64_t V = (int64_t)out.Z * out.X * out.Y;
-  const int64_t total = V * C8 * out.N;
-  for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
-    uint32_t q = (uint32_t)i;  // total < 2^31 vectors
+  const float inv = scale > 0.f ? 1.f / scale : 0.f;
+  const int64_t astride = axis == 0 ? in.plane_elems() : (axis == 1 ? (int64_t)in.Yp * 8 : 8);
+  const uint32_t total = (uint32_t)((int64_t)out.Z * out.X * out.Y * C8 * out.N);  // < 2^31 vectors
+  for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < total; i += gridDim.x * 256u) {
+    uint32_t q = i;
     const int y = (int)(q % (uint32_t)out.Y); q /= (uint32_t)out.Y;
     const int x = (int)(q % (uint32_t)out.X); q /= (uint32_t)out.X;
     const int z = (int)(q % (uint32_t)out.Z); q /= (uint32_t)out.Z;
     const int c8 = (int)(q % (uint32_t)C8);
     const int n = (int)(q / (uint32_t)C8);
     const int l = axis == 0 ? z : (axis == 1 ? x : y);
-    int lo, hi;
-    dst_range(l, out_n, in_n, scale, lo, hi);
-    const bf16* ib = in.ptr + n * in.n_stride + c8 * in.c_stride;
+    int lo = 0, hi = in_n - 1;
+    if (scale > 0.f) {  // one extra candidate on each side absorbs the rounding of the reciprocal
+      lo = max(0, (int)floorf((float)(l - 1) * inv));
+      hi = min(in_n - 1, (int)ceilf((float)(l + 1) * inv));
+    }
+    // voxel of this output with the reduced axis at 0
+    const bf16* ib = in.ptr + n * in.n_stride + c8 * in.c_stride + in.voxel(axis == 0 ? 0 : z, axis == 1 ? 0 : x, axis == 2 ? 0 : y);
     float acc[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) acc[k] = 0.f;
-    for (int d = lo; d <= hi; ++d) {
-      const float w = axis_weight(d, l, out_n, scale);
-      if (w != 0.f) {
-        float f[8];
-        unpack8(ldg16(ib + in.voxel(axis == 0 ? d : z, axis == 1 ? d : x, axis == 2 ? d : y)), f);
+    for (int d0 = lo; d0 <= hi; d0 += 4) {
+      uint4 v[4];
+      float w[4];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) acc[k] = fmaf(w, f[k], acc[k]);
+      for (int u = 0; u < 4; ++u) {
+        const int d = min(d0 + u, hi);
+        v[u] = ldg16(ib + d * astride);
+        w[u] = d0 + u <= hi ? (scale > 0.f ? hat_weight(d, l, scale) : 1.f) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float f[8];
+        unpack8(v[u], f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = fmaf(w[u], f[k], acc[k]);
       }
     }
     bf16* dst = out.ptr + n * out.n_stride + c8 * out.c_stride + out.voxel(z, x, y);

@@ -27,11 +27,18 @@ __global__ void __launch_bounds__(256) sumsq_partial_kernel(const float* __restr
   }
 }
 
+// hyper (optional, device): {lr, beta1, beta2, eps, wd, bias1, bias2_sqrt, max_norm} overriding the by-value arguments,
+// so a captured CUDA graph of the step can be replayed with a new schedule point without re-capturing
 __global__ void __launch_bounds__(256) adam_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                         float* __restrict__ v, int64_t n, float lr, float beta1, float beta2,
                                                         float eps, float wd, float bias1, float bias2_sqrt, float max_norm,
-                                                        const float* __restrict__ partial, float* __restrict__ norm_out) {
+                                                        const float* __restrict__ hyper, const float* __restrict__ partial,
+                                                        float* __restrict__ norm_out) {
   __shared__ float s_coef;
+  if (hyper) {
+    lr = hyper[0]; beta1 = hyper[1]; beta2 = hyper[2]; eps = hyper[3]; wd = hyper[4]; bias1 = hyper[5]; bias2_sqrt = hyper[6];
+    max_norm = hyper[7];
+  }
   if (threadIdx.x == 0) {
     double tot = 0;
     for (int i = 0; i < kNormBlocks; ++i) tot += partial[i];  // fixed order: deterministic
@@ -133,7 +140,17 @@ extern "C" int rtp_adam_step(float* param, const float* grad, float* m, float* v
   const float bias2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
   const int blocks = ceil_div(n, 1024) > 592 ? 592 : ceil_div(n, 1024);
   adam_step_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, m, v, n, lr, beta1, beta2, eps, wd, bias1, bias2_sqrt,
-                                                            max_norm, workspace, grad_norm_out);
+                                                            max_norm, nullptr, workspace, grad_norm_out);
+  RTP_LAUNCH_CHECK();
+}
+
+extern "C" int rtp_adam_step_dev(float* param, const float* grad, float* m, float* v, int64_t n, const float* hyper, float* workspace,
+                                 float* grad_norm_out, void* stream) {
+  RTP_CHECK_ARG(param && grad && m && v && hyper && workspace && n > 0, "rtp_adam_step_dev: bad arguments");
+  sumsq_partial_kernel<<<kNormBlocks, 256, 0, (cudaStream_t)stream>>>(grad, n, workspace);
+  const int blocks = ceil_div(n, 1024) > 592 ? 592 : ceil_div(n, 1024);
+  adam_step_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, m, v, n, 0.f, 0.f, 0.f, 1.f, 0.f, 1.f, 1.f, 0.f, hyper, workspace,
+                                                            grad_norm_out);
   RTP_LAUNCH_CHECK();
 }
 

@@ -84,7 +84,7 @@ class Engine:
                     g, acc = self._grad_of(res)
                     ops.grad_add(dy, g, mask=res if res.relu_out else None, accumulate=acc)
                 gw, accw = self._pgrad(conv + ".weight")
-                ops.conv_wgrad(xn, dy, k, stride, gw, accumulate=accw)
+                ops.conv_wgrad_async(xn, dy, k, stride, gw, accumulate=accw)
                 dxn = ops.conv_dgrad(self.packs, dy, w, stride, self.new(xn))
                 gg, accg = self._pgrad(gn + ".weight")
                 gb, _ = self._pgrad(gn + ".bias")
@@ -206,7 +206,7 @@ class Engine:
                     else:
                         gt = self.new(t)
                         ops.upsample_bwd(g, gt)
-                    ops.conv_wgrad(y, gt, 1, 1, gw, accumulate=accw, ci0=ci0)
+                    ops.conv_wgrad_async(y, gt, 1, 1, gw, accumulate=accw, ci0=ci0)
                     gy, acc = self._grad_of(y)
                     ops.conv_dgrad(self.packs, gt, w, 1, gy, mask=y if y.relu_out else None, accumulate=acc, ci0=ci0,
                                    ci_n=y.C)
@@ -240,13 +240,13 @@ class Engine:
                 tg = self.new(t)
                 for name, tv, o, c0 in (("reg", t_reg, reg, 0), ("hm", t_hm, hm, hc)):
                     gw, acc = self._pgrad(q + name + ".2.weight")
-                    ops.conv_wgrad(tv, o.grad, 3, 1, gw, accumulate=acc)
+                    ops.conv_wgrad_async(tv, o.grad, 3, 1, gw, accumulate=acc)
                     gb, accb = self._pgrad(q + name + ".2.bias")
                     ops.channel_sum(o.grad, gb, accumulate=accb)
                     ops.conv_dgrad(self.packs, o.grad, p[q + name + ".2.weight"], 1, tg.channels(c0, hc), mask=tv)
                 gw_r, acc_r = self._pgrad(q + "reg.0.weight")
                 gw_h, acc_h = self._pgrad(q + "hm.0.weight")
-                ops.conv_wgrad(f, tg, 3, 1, gw_r, accumulate=acc_r, n0=0, more=((gw_h, acc_h, 0, hc),))
+                ops.conv_wgrad_async(f, tg, 3, 1, gw_r, accumulate=acc_r, n0=0, more=((gw_h, acc_h, 0, hc),))
                 gball = torch.empty(2 * hc, dtype=torch.float32, device=f.buf.device)
                 ops.channel_sum(tg, gball)
                 for name, c0 in (("reg", 0), ("hm", hc)):
@@ -300,6 +300,7 @@ class Engine:
         for fn in reversed(self.tape):
             fn()
         self.tape = []
+        ops.join_wgrad()
         return self._touched
 
     def decode(self, hm, reg, voxel_xyz, range_xyz):

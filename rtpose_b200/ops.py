@@ -365,6 +365,41 @@ def _wgrad_k3s1(x, dy, outs):
                 h += hn
 
 
+ASYNC_WGRAD = True  # weight gradients run on a side stream (nothing in backward depends on them); see join_wgrad()
+_side = {}
+
+
+def _side_stream(device):
+    key = str(device)
+    st = _side.get(key)
+    if st is None:
+        st = {"stream": torch.cuda.Stream(device=device), "busy": False, "events": []}
+        _side[key] = st
+    return st
+
+
+def join_wgrad(device=None):
+    """Makes the current stream wait for every weight gradient queued on the side stream(s)."""
+    for key, st in _side.items():
+        if st["busy"] and (device is None or key == str(device)):
+            torch.cuda.current_stream(st["stream"].device).wait_stream(st["stream"])
+            st["busy"] = False
+
+
+def conv_wgrad_async(x, dy, k, stride, dW, accumulate=False, ci0=0, n0=0, more=()):
+    """conv_wgrad queued on a side stream, ordered after everything issued so far on the current stream.  The caller
+    keeps x, dy and dW alive and untouched until join_wgrad() (the engine's buffers live until the end of the step).
+    Falls back to the in-stream call when ASYNC_WGRAD is off."""
+    dev = x.buf.device
+    if not ASYNC_WGRAD:
+        return conv_wgrad(x, dy, k, stride, dW, accumulate, ci0, n0, more)
+    st = _side_stream(dev)
+    st["stream"].wait_stream(torch.cuda.current_stream(dev))
+    st["busy"] = True
+    with torch.cuda.stream(st["stream"]):
+        return conv_wgrad(x, dy, k, stride, dW, accumulate, ci0, n0, more)
+
+
 def conv_wgrad(x, dy, k, stride, dW, accumulate=False, ci0=0, n0=0, more=()):
     """dW[:, ci0:ci0+x.C] (=|+=) wgrad(x, dy[:, n0:n0+dW.shape[0]]).  x: forward input (P8), dy: P8 gradient.
     `more`: further (dW, accumulate, ci0, n0) outputs reduced from the same split-K workspace."""

@@ -10,12 +10,19 @@ as ONE pass over (param, grad, m, v) in rtp_adam_step.  Parameters and gradients
 """
 import math
 
+import numpy as np
 import torch
 
 from . import lib
+from .p8 import _stream
 
 
 class FlatAdam:
+    """step(lr, mom) = set_hyper(lr, mom) + step_dev().  The kernel reads the schedule point from an 8-float DEVICE block
+    (rtp_adam_step_dev), so step_dev() can sit inside a captured CUDA graph while set_hyper() — a 32-byte async copy
+    from a pinned ring — runs before each replay."""
+    RING = 1024  # pinned schedule slots: the host may run this many steps ahead of the device
+
     def __init__(self, flat_params, flat_grads, wd=0.01, eps=1e-8, beta2=0.99, max_norm=35.0):
         assert flat_params.is_cuda and flat_params.dtype == torch.float32 and flat_params.is_contiguous()
         assert flat_grads.shape == flat_params.shape and flat_grads.dtype == torch.float32
@@ -23,14 +30,38 @@ class FlatAdam:
         self.m, self.v = torch.zeros_like(flat_params), torch.zeros_like(flat_params)
         self.wd, self.eps, self.beta2, self.max_norm = float(wd), float(eps), float(beta2), float(max_norm)
         self.t = 0
-        self.ws = torch.empty(lib.load().rtp_adam_workspace_bytes(), dtype=torch.uint8, device=flat_params.device)
-        self.grad_norm = torch.zeros(1, dtype=torch.float32, device=flat_params.device)
+        dev = flat_params.device
+        self.ws = torch.empty(lib.load().rtp_adam_workspace_bytes(), dtype=torch.uint8, device=dev)
+        self.grad_norm = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.hyper = torch.zeros(8, dtype=torch.float32, device=dev)
+        self._ring = torch.zeros((self.RING, 8), dtype=torch.float32).pin_memory()
+
+    def set_hyper(self, lr, mom=0.9):
+        """Advances the Adam time step and uploads {lr, beta1, beta2, eps, wd, 1-beta1^t, sqrt(1-beta2^t), max_norm}."""
+        self.t += 1
+        slot = self._ring[self.t % self.RING]
+        # fp32 like rtp_adam_step: bias1 = 1 - powf(beta1, t), bias2_sqrt = sqrtf(1 - powf(beta2, t))
+        f32 = np.float32
+        slot[0], slot[1], slot[2], slot[3], slot[4] = float(lr), float(mom), self.beta2, self.eps, self.wd
+        slot[5] = float(f32(1) - np.power(f32(mom), f32(self.t)))
+        slot[6] = float(np.sqrt(f32(1) - np.power(f32(self.beta2), f32(self.t))))
+        slot[7] = self.max_norm
+        self.hyper.copy_(slot, non_blocking=True)
+
+    def step_dev(self):
+        lib.call("rtp_adam_step_dev", self.p.data_ptr(), self.g.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), self.p.numel(),
+                 self.hyper.data_ptr(), self.ws.data_ptr(), self.grad_norm.data_ptr(), _stream())
 
     def step(self, lr, mom=0.9):
+        self.set_hyper(lr, mom)
+        self.step_dev()
+
+    def step_by_value(self, lr, mom=0.9):
+        """Same update through rtp_adam_step (hyper-parameters as kernel arguments)."""
         self.t += 1
         lib.call("rtp_adam_step", self.p.data_ptr(), self.g.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), self.p.numel(),
                  float(lr), float(mom), self.beta2, self.eps, self.wd, self.t, self.max_norm, self.ws.data_ptr(),
-                 self.grad_norm.data_ptr(), torch.cuda.current_stream().cuda_stream)
+                 self.grad_norm.data_ptr(), _stream())
 
 
 def one_cycle(step, total_steps, lr_max=2e-3, div_factor=10.0, pct_start=0.4, moms=(0.95, 0.85)):

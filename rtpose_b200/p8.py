@@ -85,5 +85,10 @@ class P8:
         return self
 
 
+_raw_stream = torch._C._cuda_getCurrentRawStream
+_cur_device = torch._C._cuda_getDevice
+
+
 def _stream():
-    return torch.cuda.current_stream().cuda_stream
+    """Raw cudaStream_t of torch's current stream (torch.cuda.current_stream() costs ~10 us of Python per call)."""
+    return _raw_stream(_cur_device())

@@ -65,3 +65,58 @@ def test_fused_adam_matches_reference_optimizer_semantics():
         assert abs(float(fa.grad_norm) - float(total)) <= 1e-4 * float(total)
         ref_flat = torch.cat([t.detach().flatten() for t in ref_params])
         torch.testing.assert_close(p.cpu(), ref_flat, rtol=2e-5, atol=2e-7)
+
+
+def test_adam_by_value_and_device_hyper_agree():
+    from rtpose_b200.optim import FlatAdam
+    g = torch.Generator().manual_seed(3)
+    p0 = torch.randn(100003, generator=g) * 0.1
+    pa, pb = p0.clone().cuda(), p0.clone().cuda()
+    ga, gb = torch.zeros_like(pa), torch.zeros_like(pb)
+    a, b = FlatAdam(pa, ga), FlatAdam(pb, gb)
+    for step in range(3):
+        gr = (torch.randn(100003, generator=g) * (40.0 if step == 1 else 0.3)).cuda()
+        ga.copy_(gr); gb.copy_(gr)
+        a.step(1e-3 * (step + 1), 0.9 - 0.02 * step)            # rtp_adam_step_dev
+        b.step_by_value(1e-3 * (step + 1), 0.9 - 0.02 * step)    # rtp_adam_step
+    torch.cuda.synchronize()
+    torch.testing.assert_close(pa, pb, rtol=1e-6, atol=1e-8)
+    assert float(a.grad_norm) == float(b.grad_norm)
+
+
+def test_step_graph_replay_matches_eager():
+    """wgrad on the side stream + join + Adam with device hyper-parameters, captured once and replayed along a
+    schedule, equals the same steps issued eagerly (rtpose_b200/graph.py)."""
+    from rtpose_b200 import ops
+    from rtpose_b200.graph import StepGraph
+    from rtpose_b200.optim import FlatAdam
+    from rtpose_b200.p8 import P8
+    g = torch.Generator().manual_seed(11)
+    xp = P8.from_ncdhw(torch.randn(2, 32, 4, 12, 10, generator=g).cuda())
+    dyp = P8.from_ncdhw(torch.randn(2, 32, 4, 12, 10, generator=g).cuda())
+    sched = [(1e-3, 0.95), (2e-3, 0.9), (5e-4, 0.85)]
+
+    def make():
+        p = torch.full((32 * 32 * 27,), 0.01, device="cuda")
+        gr = torch.zeros_like(p)
+        opt = FlatAdam(p, gr)
+
+        def body():
+            ops.conv_wgrad_async(xp, dyp, 3, 1, gr.view(32, 32, 3, 3, 3))
+            ops.join_wgrad()
+            opt.step_dev()
+            return opt.grad_norm
+        return p, opt, body
+
+    p_e, opt_e, body_e = make()
+    for lr, mom in sched:
+        opt_e.set_hyper(lr, mom)
+        body_e()
+    p_g, opt_g, body_g = make()
+    sg = StepGraph(body_g, warmup=0)
+    for lr, mom in sched:
+        opt_g.set_hyper(lr, mom)
+        norm = sg()
+    torch.cuda.synchronize()
+    assert float(norm) > 0
+    assert torch.equal(p_e, p_g)
