@@ -343,6 +343,7 @@ def e2e_public_api(args, dev):
     torch.manual_seed(0)
     model = D.build_detector(model_cfg, train_cfg=None, test_cfg=None).to(dev)
     model.pose_head.sync_free_losses = True
+    model.cuda_graph = not args.no_graph  # one replayed graph per training step (det3d_compat._StepJob)
     rs = np.random.RandomState(7)
     x_host = torch.from_numpy(np.maximum(rs.uniform(-0.2, 1.0, (B, in_ch) + GRID), 0).astype(np.float32)).pin_memory()
     tg = targets.assign(targets.random_poses(rs, B, GRID), GRID, one_hm=(ncls == 1), min_radius=2 if ncls == 1 else 1)
@@ -388,7 +389,8 @@ def e2e_public_api(args, dev):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
     return {"value": B / (ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
-            "ms_per_step": ms, "api": "det3d_compat.build_detector(...)(example, return_loss=True); loss.backward()"}
+            "ms_per_step": ms, "cuda_graph": bool(model.cuda_graph),
+            "api": "det3d_compat.build_detector(...)(example, return_loss=True); loss.backward()"}
 
 
 def cpu_baseline(args):

@@ -174,23 +174,66 @@ class _ParamJob:
 
 
 class _StepJob(_ParamJob):
-    """RadarPoseNet training step: input cube -> backbone -> head -> loss (+ gradient seeds) in one go."""
+    """RadarPoseNet training step: input cube -> backbone -> head -> loss (+ gradient seeds) in one go.
 
-    def __init__(self, engine, params, x, example, train, task_id=0):
+    With `graph_state` (RadarPoseNet.cuda_graph = True) the whole step INCLUDING the backward pass is one captured CUDA
+    graph over static input / target / gradient buffers: run_forward copies this iteration's tensors into them and
+    replays; run_backward only hands out (a copy of) the gradients the replay already produced.  The graph is
+    re-captured whenever a parameter, input or target tensor changes shape or a parameter moves in memory."""
+
+    def __init__(self, engine, params, x, example, train, task_id=0, graph_state=None):
         super().__init__(engine, params)
         self.x, self.example, self.train, self.task_id = x, example, train, task_id
+        self.graph_state = graph_state if train else None
+
+    def _targets(self):
+        ex, t, dev = self.example, self.task_id, self.x.device
+        return (ex["hm"][t].to(dev, torch.float32).contiguous(), ex["ind"][t].to(dev, torch.int64).contiguous(),
+                ex["mask"][t].to(dev, torch.uint8).contiguous(), ex["cat"][t].to(dev, torch.int64).contiguous(),
+                ex["anno_pose"][t].to(dev, torch.float32).contiguous())
 
     def run_forward(self):
-        e, ex, t = self.engine, self.example, self.task_id
+        if self.graph_state is not None:
+            return self._run_graphed()
+        e = self.engine
         xp = P8.from_ncdhw(self.x)
         hm, reg = e.forward(xp, self.train)
-        dev = self.x.device
-        out = e.loss(hm, reg, ex["hm"][t].to(dev, torch.float32).contiguous(), ex["ind"][t].to(dev, torch.int64).contiguous(),
-                     ex["mask"][t].to(dev, torch.uint8).contiguous(), ex["cat"][t].to(dev, torch.int64).contiguous(),
-                     ex["anno_pose"][t].to(dev, torch.float32).contiguous(), with_grad=self.train)
-        return out
+        return e.loss(hm, reg, *self._targets(), with_grad=self.train)
+
+    def _run_graphed(self):
+        from .graph import StepGraph
+        st, e, tgt = self.graph_state, self.engine, self._targets()
+        key = (tuple(p.data_ptr() for p in self.params.values()), tuple(self.x.shape), tuple(tuple(t.shape) for t in tgt))
+        if st.get("key") != key:
+            st.clear()
+            st["x"], st["tgt"] = torch.empty_like(self.x), tuple(torch.empty_like(t) for t in tgt)
+            st["flat"], st["views"] = self.grads_buffer()
+
+            def body():
+                e.packs.invalidate()  # the optimizer rewrites the weights between replays: repack inside the graph
+                hm, reg = e.forward(P8.from_ncdhw(st["x"]), True)
+                out = e.loss(hm, reg, *st["tgt"], with_grad=True)
+                st["touched"] = e.backward(st["views"])
+                return out
+            st["x"].copy_(self.x)
+            for d, t in zip(st["tgt"], tgt):
+                d.copy_(t)
+            st["graph"] = StepGraph(body, warmup=1).capture()
+            st["key"] = key
+        st["x"].copy_(self.x)
+        for d, t in zip(st["tgt"], tgt):
+            d.copy_(t)
+        return st["graph"]().clone()
 
     def run_backward(self, gouts):
+        if self.graph_state is not None:
+            st = self.graph_state
+            flat = st["flat"].clone()  # the static buffer is overwritten by the next replay
+            views, o = {}, 0
+            for k, p in self.params.items():
+                views[k] = flat[o:o + p.numel()].view(p.shape)
+                o += p.numel()
+            return self.finish(flat, views, gouts[0][0], st["touched"])
         flat, views = self.grads_buffer()
         touched = self.engine.backward(views)
         # d(out[0]) is the only differentiable element; its incoming gradient rescales everything linearly
@@ -427,6 +470,9 @@ class RadarPoseNet(nn.Module):
         self.pose_head = build_head(pose_head)
         self.train_cfg, self.test_cfg, self.sensor_type = train_cfg, test_cfg, sensor_type
         self._engine = None
+        # opt-in: run each training step (forward + loss + backward) as one replayed CUDA graph; see _StepJob
+        self.cuda_graph = False
+        self._graph_state = {}
         if pretrained is not None:
             try:
                 ckpt = torch.load(pretrained, map_location="cpu")
@@ -459,7 +505,8 @@ class RadarPoseNet(nn.Module):
         params = _named(self)
         e = self._eng(params)
         if return_loss:
-            (out,) = _Bridge.apply(_StepJob(e, params, x, ex, torch.is_grad_enabled()), *params.values())
+            gs = self._graph_state if (self.cuda_graph and torch.is_grad_enabled()) else None
+            (out,) = _Bridge.apply(_StepJob(e, params, x, ex, torch.is_grad_enabled(), graph_state=gs), *params.values())
             return self.pose_head._format_losses(out)
         with torch.no_grad():
             hm, reg = e.forward(P8.from_ncdhw(x), False)

@@ -111,3 +111,32 @@ def test_standalone_backbone_and_head_modules_autograd():
     assert cos > 0.9, cos
     dets = model.pose_head.predict({"meta": [{}]}, [{"hm": hm_raw, "reg": preds[0]["reg"].detach()}], test_cfg)
     assert len(dets) == 1 and len(dets[0]["keypoints"]) == 15
+
+
+def test_graphed_train_step_equals_eager_and_follows_weight_updates():
+    """RadarPoseNet.cuda_graph = True: same losses and gradients as the eager path, for new inputs and after an
+    optimizer update of the weights (the captured graph repacks the weights on every replay)."""
+    cfg, grid, batch = "hr3d_one_hm_doppler", (8, 16, 24), 2
+    eager, _ = build(cfg)
+    graphed, _ = build(cfg)
+    graphed.cuda_graph = True
+    eager.train(); graphed.train()
+    for m in (eager, graphed):
+        m.pose_head.sync_free_losses = True
+    opt_e = torch.optim.SGD(eager.parameters(), lr=1e-3)
+    opt_g = torch.optim.SGD(graphed.parameters(), lr=1e-3)
+    for it in range(3):
+        x, poses, tgt = G.make_example(cfg, batch, grid, seed=40 + it)
+        out = []
+        for m, opt in ((eager, opt_e), (graphed, opt_g)):
+            opt.zero_grad(set_to_none=True)
+            losses = m(example_of(x, tgt, batch), return_loss=True)
+            (sum(losses["loss"]) * 0.5).backward()
+            out.append((float(losses["loss"][0]), {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}))
+            opt.step()
+        (le, ge), (lg, gg) = out
+        assert le == lg, (it, le, lg)
+        assert set(ge) == set(gg)
+        for k in ge:
+            assert torch.equal(ge[k], gg[k]), (it, k)
+    assert graphed._graph_state.get("graph") is not None
