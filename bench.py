@@ -167,6 +167,8 @@ def run_ours(args, rank, world, local_rank):
 
     if args.sync_wgrad:
         ops.ASYNC_WGRAD = False
+    if args.serial_branches:
+        eng.parallel_branches = False
 
     def step_body():
         lib.call("rtp_ingest_pack", raw.data_ptr(), B, D, RAW_SHAPE[0], RAW_SHAPE[1], RAW_SHAPE[2], ROI0[0], ROI0[1], ROI0[2],
@@ -237,8 +239,8 @@ def run_ours(args, rank, world, local_rank):
     # ---- per-kernel durations for the roofline: the same step, issued eagerly with the weight gradients in-stream so
     #      that every CUDA-event pair brackets exactly one kernel running alone (in the timed region kernels of the
     #      wgrad side stream overlap the main stream, and event timing inside a replayed graph is not available)
-    graph, async_was = None, ops.ASYNC_WGRAD
-    ops.ASYNC_WGRAD = False
+    graph, async_was, par_was = None, ops.ASYNC_WGRAD, eng.parallel_branches
+    ops.ASYNC_WGRAD, eng.parallel_branches = False, False
     step()
     ops.PROFILE = {"_only": {"conv_generic", "conv_k3s1", "conv_pw", "wgrad_generic", "wgrad_k3s1"}}
     p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -249,7 +251,7 @@ def run_ours(args, rank, world, local_rank):
     p1.record()
     barrier()
     prof, ops.PROFILE = ops.PROFILE, None
-    ops.ASYNC_WGRAD = async_was
+    ops.ASYNC_WGRAD, eng.parallel_branches = async_was, par_was
     ms_serial = p0.elapsed_time(p1) / nprof
     sampler.stop_flag = True
     if world > 1:
@@ -302,7 +304,7 @@ def run_ours(args, rank, world, local_rank):
                                    "HRNet3D -> CenterHead -> loss -> backward" % (cfg, B, D),
                        "per_gpu_batch": B, "global_batch": B * world, "grid": list(GRID), "parallelism": "dp%d" % world,
                        "l2": "inputs+activations per step >> 126 MB L2 (no explicit flush needed)",
-                       "cuda_graph": use_graph, "wgrad_side_stream": bool(ops.ASYNC_WGRAD),
+                       "cuda_graph": use_graph, "wgrad_side_stream": bool(ops.ASYNC_WGRAD), "branch_streams": bool(eng.parallel_branches),
                        "targets": "assigned on the device from resident fp64 skeletons every step (rtp_assign_targets)",
                        "optimizer": ("fused clip(35) + decoupled wd + Adam, one-cycle lr (rtp_adam_step) inside the timed region"
                                      if opt is not None else "none (--no-optimizer)")},
@@ -453,6 +455,7 @@ def main():
     ap.add_argument("--cfg", default="hr3d_one_hm_doppler", choices=sorted(CFGS))
     ap.add_argument("--batch", type=int, default=16, help="frames per GPU per step")
     ap.add_argument("--no-graph", action="store_true", help="issue every step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--serial-branches", action="store_true", help="run the HR-module branches one after the other on one stream")
     ap.add_argument("--sync-wgrad", action="store_true", help="run weight gradients in-stream (no side stream)")
     ap.add_argument("--no-extras", action="store_true", help="skip e2e / cpu_baseline / inference legs")
     ap.add_argument("--no-optimizer", action="store_true", help="time forward+backward only (no fused clip+Adam step)")

@@ -236,17 +236,18 @@ extern "C" int rtp_conv(const rtp_conv_desc* d, void* stream) {
   k.KC = d->Cin; k.nk = 1;
   while (((size_t)k.KC * 256 + (size_t)k.KC * d->NP * 2) * 2 > 200 * 1024 && k.KC % 32 == 0) { k.KC /= 2; k.nk *= 2; }
   const size_t stage = (size_t)k.KC * 256 + (size_t)k.KC * d->NP * 2;
-  const int stages = 4 * stage <= 200 * 1024 ? 4 : (3 * stage <= 200 * 1024 ? 3 : 2);
+  const int64_t tiles = (k.total_rows + 127) / 128;
+  int stages = 4 * stage <= 200 * 1024 ? 4 : (3 * stage <= 200 * 1024 ? 3 : 2);
   const size_t smem = stages * stage;
   RTP_CHECK_ARG(smem <= 200 * 1024, "rtp_conv: Cin=%d NP=%d needs %zu B of shared memory", d->Cin, d->NP, smem);
-  auto kern = stages == 4 ? conv_generic_kernel<4> : (stages == 3 ? conv_generic_kernel<3> : conv_generic_kernel<2>);
-  static size_t configured[5] = {0, 0, 0, 0, 0};
+  auto kern = stages == 8 ? conv_generic_kernel<8>
+                          : (stages == 4 ? conv_generic_kernel<4> : (stages == 3 ? conv_generic_kernel<3> : conv_generic_kernel<2>));
+  static size_t configured[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   if (smem > configured[stages]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { rtp_set_error("rtp_conv: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
     configured[stages] = smem;
   }
-  const int64_t tiles = (k.total_rows + 127) / 128;
   kern<<<(unsigned)tiles, kThreads, smem, (cudaStream_t)stream>>>(k);
   RTP_LAUNCH_CHECK();
 }

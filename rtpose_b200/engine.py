@@ -39,6 +39,10 @@ class Engine:
         self.grads = None
         self._touched = set()
         self._cw = None
+        # the branches of an HR module are independent between two fuse layers: run branch b >= 1 on its own stream
+        # so the small low-resolution kernels fill the gaps of the full-resolution branch (forward and backward)
+        self.parallel_branches = True
+        self._bstreams = {}
 
     # ------------------------------------------------------------------ helpers
     def new(self, like, C=None, grid=None):
@@ -126,7 +130,7 @@ class Engine:
 
     def hr_module(self, xs, prefix, nb, train, outputs=None):
         """HighResolutionModule.forward (hr_util/hr3d.py:205-229)."""
-        xs = [self.res_block(xs[b], "%s.branches.%d.0" % (prefix, b), train) for b in range(nb)]
+        xs = self._branches(xs, prefix, nb, train)
         outs = []
         for i in (range(nb) if outputs is None else outputs):
             same, low = [], []
@@ -148,6 +152,57 @@ class Engine:
                 self.tape.append(self._fuse_bwd(y, same, low))
             outs.append(y)
         return outs
+
+    def _branch_stream(self, b, device):
+        st = self._bstreams.get((b, str(device)))
+        if st is None:
+            st = torch.cuda.Stream(device=device)
+            self._bstreams[(b, str(device))] = st
+        return st
+
+    def _branches(self, xs, prefix, nb, train):
+        """One res_block per branch.  Branch 0 stays on the current stream; with parallel_branches the others fork onto
+        side streams and join before the fuse layers.  The backward closures a branch records are replayed on the same
+        side stream, bracketed by the mirrored fork / join."""
+        if not self.parallel_branches or nb < 2:
+            return [self.res_block(xs[b], "%s.branches.%d.0" % (prefix, b), train) for b in range(nb)]
+        dev = xs[0].buf.device
+        main = torch.cuda.current_stream(dev)
+        side = [self._branch_stream(b, dev) for b in range(1, nb)]
+        if train:  # runs LAST among this module's branch closures in backward: the current stream joins the sides
+            def join_bwd():
+                cur = torch.cuda.current_stream(dev)
+                for st in side:
+                    cur.wait_stream(st)
+            self.tape.append(join_bwd)
+        outs = [None] * nb
+        for b in range(nb):
+            if b == 0:
+                outs[0] = self.res_block(xs[0], "%s.branches.0.0" % prefix, train)
+                continue
+            st = side[b - 1]
+            st.wait_stream(main)
+            t0 = len(self.tape)
+            with torch.cuda.stream(st):
+                outs[b] = self.res_block(xs[b], "%s.branches.%d.0" % (prefix, b), train)
+            for i in range(t0, len(self.tape)):
+                self.tape[i] = self._on_stream(self.tape[i], st)
+        for st in side:
+            main.wait_stream(st)
+        if train:  # runs FIRST in backward: the sides wait for the fuse-layer gradients produced on the current stream
+            def fork_bwd():
+                cur = torch.cuda.current_stream(dev)
+                for st in side:
+                    st.wait_stream(cur)
+            self.tape.append(fork_bwd)
+        return outs
+
+    @staticmethod
+    def _on_stream(fn, st):
+        def run():
+            with torch.cuda.stream(st):
+                fn()
+        return run
 
     def _fuse_bwd(self, y, same, low):
         def bwd():
@@ -243,7 +298,11 @@ class Engine:
                     ops.conv_wgrad_async(tv, o.grad, 3, 1, gw, accumulate=acc)
                     gb, accb = self._pgrad(q + name + ".2.bias")
                     ops.channel_sum(o.grad, gb, accumulate=accb)
-                    ops.conv_dgrad(self.packs, o.grad, p[q + name + ".2.weight"], 1, tg.channels(c0, hc), mask=tv)
+                    dy = o.grad
+                    if dy.C8 == 1 and dy.n_stride >= 2 * dy.c_stride:  # gradient with a zeroed spare chunk (loss())
+                        dy = P8(dy.N, 16, dy.Z, dy.Y, dy.X, buf=dy.buf, offset=dy.offset, n_stride=dy.n_stride,
+                                c_stride=dy.c_stride)
+                    ops.conv_dgrad(self.packs, dy, p[q + name + ".2.weight"], 1, tg.channels(c0, hc), mask=tv)
                 gw_r, acc_r = self._pgrad(q + "reg.0.weight")
                 gw_h, acc_h = self._pgrad(q + "hm.0.weight")
                 ops.conv_wgrad_async(f, tg, 3, 1, gw_r, accumulate=acc_r, n0=0, more=((gw_h, acc_h, 0, hc),))
@@ -283,7 +342,15 @@ class Engine:
         out = torch.empty(4 + self.R, dtype=torch.float32, device=dev)
         ws = ops.workspace(lib.load().rtp_head_loss_workspace_bytes(hm.N, self.ncls, hm.Z, hm.Y, hm.X), dev, "loss")
         if with_grad:
-            hm.grad, reg.grad = self.new(hm), self.new(reg)
+            if hm.C8 == 1:
+                # one spare, zeroed 8-channel chunk behind the heat-map gradient: the dgrad of hm.2 can then run on the
+                # plane-streaming kernel (K = 16) instead of the generic one (see head.bwd)
+                wide = self.new(hm, C=16)
+                wide.channels(8, 8).zero_()
+                hm.grad = wide.channels(0, hm.C)
+            else:
+                hm.grad = self.new(hm)
+            reg.grad = self.new(reg)
             dh, dr = hm.grad.struct(), reg.grad.struct()
         else:
             dh = dr = lib.NULL_P8

@@ -47,7 +47,8 @@ _workspaces = {}
 
 
 def workspace(nbytes, device, tag="ws"):
-    key = (tag, str(device))
+    """Scratch buffer per (tag, device, current stream): kernels of concurrently running streams never share one."""
+    key = (tag, str(device), _stream())
     w = _workspaces.get(key)
     if w is None or w.numel() < nbytes:
         w = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)

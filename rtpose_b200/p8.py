@@ -79,9 +79,7 @@ class P8:
         if self.n_stride == self.C8 * self.c_stride:
             self.buf[self.offset:self.offset + self.N * self.n_stride].zero_()
         else:
-            for n in range(self.N):
-                o = self.offset + n * self.n_stride
-                self.buf[o:o + self.C8 * self.c_stride].zero_()
+            self.buf.as_strided((self.N, self.C8 * self.c_stride), (self.n_stride, 1), self.offset).zero_()
         return self
 
 
