@@ -174,7 +174,7 @@ def run_ours(args, rank, world, local_rank):
         lib.call("rtp_ingest_pack", raw.data_ptr(), B, D, RAW_SHAPE[0], RAW_SHAPE[1], RAW_SHAPE[2], ROI0[0], ROI0[1], ROI0[2],
                  float(a), float(b - a), 1 if norm is not None else 0, xin.struct(), None, _stream())
         tgt = targets.assign_device(poses, GRID, one_hm=(ncls == 1), min_radius=2 if ncls == 1 else 1)
-        eng.packs.invalidate()  # the weights changed in the optimizer step: repack inside the timed region
+        eng.packs.refresh_async()  # the optimizer rewrote the weights: every pack is rebuilt inside the timed region
         hm, rg = eng.forward(xin, True)
         out = eng.loss(hm, rg, tgt["hm"], tgt["ind"], tgt["mask"], tgt["cat"], tgt["anno_pose"])
         eng.backward(grads)

@@ -111,13 +111,28 @@ typedef struct {
   const float* bias;
   int32_t Cin, NPo, out_c8;
   int32_t relu, accumulate;
-  float* gn_sums; /* optional [N][out_c8*8][2] fp32: per-(sample,channel) sum / sum-of-squares of the stored
-                     bf16 result, accumulated with atomics (feeds the next GroupNorm); NULL = off */
+  /* fused per-(sample, channel) statistics of the result as stored (bf16-rounded), out_c8 <= 4; 0 = off.
+   *   1: sum v, sum v*v          -> mean / rstd of the GroupNorm that consumes `out` (common.py:92-96 'g' layers)
+   *   2: sum v, sum v*stat_aux   -> the two reductions of GroupNorm backward when `out` is dL/d(GN output) and
+   *                                 stat_aux the GN input
+   * Partial sums go to stat_ws (>= rtp_conv_k3s1_stat_ws_bytes(N)); rtp_conv_k3s1_stat_finalize turns them into
+   * `stats` / `red` in a fixed summation order.  Saves one full read of the tensor per GroupNorm (forward and backward). */
+  int32_t stat_mode;
+  rtp_p8 stat_aux;
+  float* stat_ws;
+  void* debug; /* tools only (tools/dbg_k3s1.py): [grid][8] int64 cycle counters of the MMA warp; NULL otherwise */
 } rtp_conv_k3s1_desc;
 int rtp_conv_k3s1(const rtp_conv_k3s1_desc* d, void* stream);
 /* dynamic shared memory the kernel would use for this shape, or -1 when the shape is not supported (callers
  * then use rtp_conv) */
 int64_t rtp_conv_k3s1_smem_bytes(int32_t Cin, int32_t NPo, int32_t Z, int32_t X, int32_t Y);
+/* fused statistics (rtp_conv_k3s1_desc.stat_mode): workspace size, number of CTAs the launch for this shape uses, and
+ * the finalisation: mode 1 -> stats[N][G][2] = (mean, rstd) as rtp_gn_finalize; mode 2 -> red[N][C][2] as
+ * rtp_gn_bwd_reduce (stats_in = the forward statistics of the GroupNorm). */
+int64_t rtp_conv_k3s1_stat_ws_bytes(int32_t N);
+int32_t rtp_conv_k3s1_num_ctas(int32_t Cin, int32_t NPo, int32_t N, int32_t Z, int32_t X, int32_t Y);
+int rtp_conv_k3s1_stat_finalize(const float* stat_ws, int32_t nctas, int32_t mode, int32_t N, int32_t C, int32_t G,
+                                int64_t voxels, float eps, const float* stats_in, float* out, void* stream);
 
 /* Pointwise (1x1x1) conv, forward or dgrad (w packed by rtp_weight_pack mode 0 / 1 with ntaps = 1): a streaming GEMM
  * over the linear positions of the P8 tensor (bulk-copy staging, resident weights, ping-pong TMEM accumulators).

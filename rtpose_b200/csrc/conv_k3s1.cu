@@ -42,9 +42,14 @@ struct K3 {
   int nstages;
   uint32_t stage_bytes, wbuf_bytes, wtap_bytes, wtap_stride;  // per-pass weight slice: 9 copies of wtap_bytes
   long long* dbg;  // optional [grid][8] cycle counters (RTP_K3S1_DEBUG): MMA-warp wait/issue breakdown
+  // fused per-(sample, channel) statistics of the stored result (STAT template argument, out_c8 <= 4):
+  //   1: sum v, sum v*v        (the next GroupNorm's mean / variance)
+  //   2: sum v, sum v*aux      (GroupNorm backward: v = dL/d(normalised x), aux = x)
+  P8 stat_aux;
+  float* stat_ws;  // [grid*8 warp slabs][N][64] then [grid CTA slabs][N][64]
 };
 
-template <int KS>  // KS = KG / 16: k16 steps per tap (1 or 2)
+template <int KS, int STAT>  // KS = KG / 16: k16 steps per tap (1 or 2); STAT: fused statistics mode (0 = off)
 __global__ void __launch_bounds__(kThreads, 1) conv_k3s1_kernel(const __grid_constant__ K3 p) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t bar_full[kMaxStages], bar_empty[kMaxStages], bar_wfull[2], bar_wempty[2];
@@ -226,6 +231,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_k3s1_kernel(const __grid_con
     const int r = lane_q * 32 + lane;               // GEMM row
     const uint32_t trow = tmem + ((uint32_t)(lane_q * 32) << 16);
     uint32_t full_mask = 0;  // bit b: parity of the number of times block b has been drained so far
+    // STAT: per-thread partial sums over the rows this thread stores; folded over the warp at the end of every unit
+    // (fixed butterfly => deterministic) and added to this warp's private [N][64] slab in global memory
+    float st0[STAT ? 32 : 1], st1[STAT ? 32 : 1];
+    float* wslab = nullptr;
+    if constexpr (STAT != 0) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) st0[i] = st1[i] = 0.f;
+      wslab = p.stat_ws + ((size_t)blockIdx.x * 8 + (warp - 2)) * p.out.N * 64;
+      for (int n = 0; n < p.out.N; ++n) reinterpret_cast<float2*>(wslab + n * 64)[lane] = make_float2(0.f, 0.f);
+    }
     for (int u = blockIdx.x; u < p.nunits; u += gridDim.x) {
       int n, zc, tile;
       decode(u, n, zc, tile);
@@ -242,14 +257,28 @@ __global__ void __launch_bounds__(kThreads, 1) conv_k3s1_kernel(const __grid_con
         const bf16* mask_row = p.has_mask ? p.mask.ptr + (int64_t)n * p.mask.n_stride + (int64_t)oz * p.mask.plane_elems() + pos : nullptr;
         // issue the residual / mask / accumulate loads of the first four chunks BEFORE waiting for the accumulator,
         // so their latency overlaps the MMAs of this plane
-        uint4 pre_res[4], pre_mask[4], pre_acc[4];
+        // (the STAT variants drop the operands their call sites never use, to keep the epilogue free of spills:
+        //  1 = forward conv + residual, 2 = plain dgrad)
+        constexpr bool kRes = STAT != 2, kMaskAcc = STAT == 0;
+        uint4 pre_res[kRes ? 4 : 1], pre_mask[kMaskAcc ? 4 : 1], pre_acc[kMaskAcc ? 4 : 1], pre_aux[STAT == 2 ? 4 : 1];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          pre_res[c] = pre_mask[c] = pre_acc[c] = make_uint4(0, 0, 0, 0);
+          if constexpr (kRes) pre_res[c] = make_uint4(0, 0, 0, 0);
+          if constexpr (kMaskAcc) pre_mask[c] = pre_acc[c] = make_uint4(0, 0, 0, 0);
+          if constexpr (STAT == 2) {
+            pre_aux[c] = make_uint4(0, 0, 0, 0);
+            if (ok && c < p.out_c8)
+              pre_aux[c] = ldg16(p.stat_aux.ptr + (int64_t)n * p.stat_aux.n_stride + (int64_t)oz * p.stat_aux.plane_elems() + pos +
+                                 c * p.stat_aux.c_stride);
+          }
           if (ok && c < p.out_c8) {
-            if (res_row) pre_res[c] = ldg16(res_row + c * p.res.c_stride);
-            if (mask_row) pre_mask[c] = ldg16(mask_row + c * p.mask.c_stride);
-            if (p.accumulate) pre_acc[c] = *reinterpret_cast<const uint4*>(out_row + c * p.out.c_stride);
+            if constexpr (kRes) {
+              if (res_row) pre_res[c] = ldg16(res_row + c * p.res.c_stride);
+            }
+            if constexpr (kMaskAcc) {
+              if (mask_row) pre_mask[c] = ldg16(mask_row + c * p.mask.c_stride);
+              if (p.accumulate) pre_acc[c] = *reinterpret_cast<const uint4*>(out_row + c * p.out.c_stride);
+            }
           }
         }
         mbar_wait(&bar_acc_full[b], (full_mask >> b) & 1);
@@ -276,38 +305,131 @@ __global__ void __launch_bounds__(kThreads, 1) conv_k3s1_kernel(const __grid_con
 #pragma unroll
               for (int i = 0; i < 8; ++i) f[i] += __ldg(p.bias + ch * 8 + i);
             }
-            if (res_row) {
-              float g[8];
-              unpack8(ch < 4 ? pre_res[ch & 3] : ldg16(res_row + ch * p.res.c_stride), g);
+            if constexpr (kRes) {
+              if (res_row) {
+                float g[8];
+                unpack8(ch < 4 ? pre_res[ch & 3] : ldg16(res_row + ch * p.res.c_stride), g);
 #pragma unroll
-              for (int i = 0; i < 8; ++i) f[i] += g[i];
+                for (int i = 0; i < 8; ++i) f[i] += g[i];
+              }
             }
             if (p.relu) {
 #pragma unroll
               for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
             }
-            if (mask_row) {
-              float g[8];
-              unpack8(ch < 4 ? pre_mask[ch & 3] : ldg16(mask_row + ch * p.mask.c_stride), g);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) f[i] = g[i] > 0.f ? f[i] : 0.f;
-            }
             bf16* dst = out_row + ch * p.out.c_stride;
-            if (p.accumulate) {
-              float g[8];
-              unpack8(ch < 4 ? pre_acc[ch & 3] : *reinterpret_cast<const uint4*>(dst), g);
+            if constexpr (kMaskAcc) {
+              if (mask_row) {
+                float g[8];
+                unpack8(ch < 4 ? pre_mask[ch & 3] : ldg16(mask_row + ch * p.mask.c_stride), g);
 #pragma unroll
-              for (int i = 0; i < 8; ++i) f[i] += g[i];
+                for (int i = 0; i < 8; ++i) f[i] = g[i] > 0.f ? f[i] : 0.f;
+              }
+              if (p.accumulate) {
+                float g[8];
+                unpack8(ch < 4 ? pre_acc[ch & 3] : *reinterpret_cast<const uint4*>(dst), g);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[i] += g[i];
+              }
             }
-            stg16(dst, pack8(f));
+            const uint4 pk = pack8(f);
+            if constexpr (STAT != 0) {
+              if (ch < 4) {  // statistics of the value as stored (bf16-rounded), like a separate pass over the tensor
+                float r8[8], a8[8];
+                unpack8(pk, r8);
+                if constexpr (STAT == 2) unpack8(pre_aux[ch & 3], a8);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  st0[(ch & 3) * 8 + i] += r8[i];
+                  st1[(ch & 3) * 8 + i] += r8[i] * (STAT == 2 ? a8[i] : r8[i]);
+                }
+              }
+            }
+            stg16(dst, pk);
           }
         }
+      }
+      if constexpr (STAT != 0) {
+        // fold the 64 partial sums over the 32 lanes: after the five exchange rounds lane L holds entries 2L, 2L+1 of
+        // [sum0[0..31], sum1[0..31]]
+        float a[32], b[16], c[8], d[4], e[2];
+        const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4, h2 = lane & 2, h1 = lane & 1;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) a[i] = (h16 ? st1[i] : st0[i]) + __shfl_xor_sync(0xffffffffu, h16 ? st0[i] : st1[i], 16);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) b[i] = (h8 ? a[i + 16] : a[i]) + __shfl_xor_sync(0xffffffffu, h8 ? a[i] : a[i + 16], 8);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) c[i] = (h4 ? b[i + 8] : b[i]) + __shfl_xor_sync(0xffffffffu, h4 ? b[i] : b[i + 8], 4);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) d[i] = (h2 ? c[i + 4] : c[i]) + __shfl_xor_sync(0xffffffffu, h2 ? c[i] : c[i + 4], 2);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) e[i] = (h1 ? d[i + 2] : d[i]) + __shfl_xor_sync(0xffffffffu, h1 ? d[i] : d[i + 2], 1);
+        float2* slot = reinterpret_cast<float2*>(wslab + n * 64) + lane;  // always touched by this lane only
+        float2 o = *slot;
+        o.x += e[0];
+        o.y += e[1];
+        *slot = o;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) st0[i] = st1[i] = 0.f;
       }
     }
   }
   fence_before_sync();
   __syncthreads();
   if (warp == 1) tmem_dealloc<512>(tmem);
+  if constexpr (STAT != 0) {  // the 8 warp slabs of this CTA -> its CTA slab (fixed order)
+    const int per = p.out.N * 64;
+    const float* ws = p.stat_ws + (size_t)blockIdx.x * 8 * per;
+    float* cs = p.stat_ws + (size_t)gridDim.x * 8 * per + (size_t)blockIdx.x * per;
+    for (int i = tid; i < per; i += kThreads) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += ws[(size_t)w * per + i];
+      cs[i] = t;
+    }
+  }
+}
+
+// CTA slabs -> GroupNorm statistics (mode 1) or GroupNorm-backward reductions (mode 2); one block per sample
+__global__ void __launch_bounds__(256) stat_finalize_kernel(const float* __restrict__ ws, int nslab, int N, int C, int G, double count,
+                                                            float eps, const float* __restrict__ stats_in, float* __restrict__ out,
+                                                            int mode) {
+  __shared__ double part[4][64];
+  __shared__ double tot[64];
+  const int n = blockIdx.x, k = threadIdx.x & 63, q = threadIdx.x >> 6;
+  const float* cs = ws + (size_t)nslab * 8 * N * 64 + (size_t)n * 64 + k;
+  double t = 0;
+  int s = q;
+  for (; s + 28 < nslab; s += 32) {  // 8 independent loads in flight
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = cs[(size_t)(s + 4 * j) * N * 64];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t += (double)v[j];
+  }
+  for (; s < nslab; s += 4) t += (double)cs[(size_t)s * N * 64];
+  part[q][k] = t;
+  __syncthreads();
+  if (threadIdx.x < 64) tot[k] = part[0][k] + part[1][k] + part[2][k] + part[3][k];
+  __syncthreads();
+  const int cpg = C / G;
+  if (mode == 1) {
+    if (threadIdx.x < G) {
+      const int g = threadIdx.x;
+      double s = 0, qq = 0;
+      for (int c = g * cpg; c < (g + 1) * cpg; ++c) { s += tot[c]; qq += tot[32 + c]; }
+      const double m = count * cpg, mean = s / m;
+      double var = qq / m - mean * mean;
+      if (var < 0) var = 0;
+      out[((size_t)n * G + g) * 2] = (float)mean;
+      out[((size_t)n * G + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+  } else if (threadIdx.x < C) {
+    const int c = threadIdx.x, g = c / cpg;
+    const double mean = stats_in[((size_t)n * G + g) * 2], rstd = stats_in[((size_t)n * G + g) * 2 + 1];
+    out[((size_t)n * C + c) * 2] = (float)tot[c];                               // sum dy
+    out[((size_t)n * C + c) * 2 + 1] = (float)(rstd * (tot[32 + c] - mean * tot[c]));  // sum dy * xhat
+  }
 }
 
 struct Plan {
@@ -376,13 +498,27 @@ extern "C" int rtp_conv_k3s1(const rtp_conv_k3s1_desc* d, void* stream) {
   k.nstages = pl.nstages; k.stage_bytes = pl.stage_bytes; k.wbuf_bytes = pl.wbuf_bytes;
   k.wtap_bytes = (uint32_t)(pl.KG / 8) * k.N3 * 16;          // one tap's [KG/8][N3][8] slice
   k.wtap_stride = (uint32_t)(d->Cin / 8) * k.N3 * 16;        // distance between taps in the packed weights
-  k.dbg = (long long*)d->gn_sums;  // debug builds of the host side pass a counter buffer through the reserved field
-  auto kern = pl.KG == 32 ? conv_k3s1_kernel<2> : conv_k3s1_kernel<1>;
-  static size_t configured[2] = {0, 0};
-  if (pl.smem > configured[pl.KG == 32]) {
+  k.dbg = (long long*)d->debug;
+  RTP_CHECK_ARG(d->stat_mode >= 0 && d->stat_mode <= 2, "rtp_conv_k3s1: bad stat_mode");
+  if (d->stat_mode) {
+    RTP_CHECK_ARG(d->stat_ws && d->out_c8 <= 4, "rtp_conv_k3s1: fused statistics need a workspace and <= 32 output channels");
+    RTP_CHECK_ARG(!d->mask.ptr && !d->accumulate && (d->stat_mode == 1 || !d->res.ptr),
+                  "rtp_conv_k3s1: stat_mode 1 supports bias/res/relu only, stat_mode 2 bias/relu only");
+    if (d->stat_mode == 2)
+      RTP_CHECK_ARG(d->stat_aux.ptr && d->stat_aux.N == d->out.N && d->stat_aux.Z == d->out.Z && d->stat_aux.X == d->out.X &&
+                        d->stat_aux.Y == d->out.Y && d->stat_aux.C8 >= d->out_c8,
+                    "rtp_conv_k3s1: stat_aux must have the output's geometry");
+  }
+  k.stat_aux = P8(d->stat_aux); k.stat_ws = d->stat_ws;
+  const int ki = (pl.KG == 32 ? 1 : 0) + 2 * d->stat_mode;
+  void (*kerns[6])(const K3) = {conv_k3s1_kernel<1, 0>, conv_k3s1_kernel<2, 0>, conv_k3s1_kernel<1, 1>,
+                                conv_k3s1_kernel<2, 1>, conv_k3s1_kernel<1, 2>, conv_k3s1_kernel<2, 2>};
+  auto kern = kerns[ki];
+  static size_t configured[6] = {0, 0, 0, 0, 0, 0};
+  if (pl.smem > configured[ki]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
     if (e != cudaSuccess) { rtp_set_error("rtp_conv_k3s1: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
-    configured[pl.KG == 32] = pl.smem;
+    configured[ki] = pl.smem;
   }
   static int nsm = 0;
   if (!nsm) {
@@ -392,5 +528,31 @@ extern "C" int rtp_conv_k3s1(const rtp_conv_k3s1_desc* d, void* stream) {
   }
   const int grid = k.nunits < nsm ? k.nunits : nsm;
   kern<<<grid, kThreads, pl.smem, (cudaStream_t)stream>>>(k);
+  RTP_LAUNCH_CHECK();
+}
+
+extern "C" int64_t rtp_conv_k3s1_stat_ws_bytes(int32_t N) {
+  int dev = 0, nsm = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+  return (int64_t)nsm * 9 * N * 64 * 4;
+}
+
+extern "C" int32_t rtp_conv_k3s1_num_ctas(int32_t Cin, int32_t NPo, int32_t N, int32_t Z, int32_t X, int32_t Y) {
+  Plan pl = make_plan(Cin, NPo, Z, X, Y);
+  if (!pl.ok) return -1;
+  int dev = 0, nsm = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+  const int nunits = N * pl.ntile * pl.nzc;
+  return nunits < nsm ? nunits : nsm;
+}
+
+extern "C" int rtp_conv_k3s1_stat_finalize(const float* stat_ws, int32_t nctas, int32_t mode, int32_t N, int32_t C, int32_t G,
+                                           int64_t voxels, float eps, const float* stats_in, float* out, void* stream) {
+  RTP_CHECK_ARG(stat_ws && out && nctas >= 1 && N >= 1 && C >= 1 && C <= 32 && G >= 1 && C % G == 0 && (mode == 1 || mode == 2),
+                "rtp_conv_k3s1_stat_finalize: bad arguments");
+  RTP_CHECK_ARG(mode == 1 || stats_in, "rtp_conv_k3s1_stat_finalize: mode 2 needs the forward statistics");
+  stat_finalize_kernel<<<N, 256, 0, (cudaStream_t)stream>>>(stat_ws, nctas, N, C, G, (double)voxels, eps, stats_in, out, mode);
   RTP_LAUNCH_CHECK();
 }

@@ -210,7 +210,7 @@ class _StepJob(_ParamJob):
             st["flat"], st["views"] = self.grads_buffer()
 
             def body():
-                e.packs.invalidate()  # the optimizer rewrites the weights between replays: repack inside the graph
+                e.packs.refresh_async()  # the optimizer rewrites the weights between replays: repack inside the graph
                 hm, reg = e.forward(P8.from_ncdhw(st["x"]), True)
                 out = e.loss(hm, reg, *st["tgt"], with_grad=True)
                 st["touched"] = e.backward(st["views"])

@@ -64,9 +64,11 @@ class Engine:
         return g, acc
 
     # ------------------------------------------------------------------ ops with backward closures
-    def gn_conv(self, x, gn, conv, k, stride, relu, res=None, train=True, x_needs_grad=True, res_needs_grad=True):
+    def gn_conv(self, x, gn, conv, k, stride, relu, res=None, train=True, x_needs_grad=True, res_needs_grad=True,
+                y_stats=False):
         """ReLU?( conv_k_stride( GroupNorm(8)(x) ) [+ res] ) — common.py:92-96 'gcr'/'gc' order; hr3d.py fuse/transition
-        Sequentials."""
+        Sequentials.  y_stats: the result feeds another GroupNorm, so let the conv's epilogue produce its statistics
+        when the shape allows (ops.stat_fusable); likewise the dgrad's epilogue produces the GroupNorm-backward sums."""
         p = self.p
         gamma, beta, w = p[gn + ".weight"], p[gn + ".bias"], p[conv + ".weight"]
         G = 8 if x.C >= 8 else 1
@@ -77,7 +79,11 @@ class Engine:
         xn = ops.gn_apply(x, G, stats, gamma, beta, self.new(x))
         Zo, Yo, Xo = ops.out_grid(x, stride)
         y = self.new(x, C=w.shape[0], grid=(Zo, Yo, Xo))
-        ops.conv_forward(self.packs, xn, w, stride, y, relu=relu, res=res)
+        if y_stats and stride == 1 and y.C % 8 == 0 and ops.stat_fusable(xn, w, False):
+            _, st = ops.conv_forward(self.packs, xn, w, stride, y, relu=relu, res=res, stat=("stats", 8, 1e-5))
+            self.stats_cache[id(y)] = st
+        else:
+            ops.conv_forward(self.packs, xn, w, stride, y, relu=relu, res=res)
         y.relu_out = bool(relu)
         if train:
             def bwd():
@@ -89,14 +95,18 @@ class Engine:
                     ops.grad_add(dy, g, mask=res if res.relu_out else None, accumulate=acc)
                 gw, accw = self._pgrad(conv + ".weight")
                 ops.conv_wgrad_async(xn, dy, k, stride, gw, accumulate=accw)
-                dxn = ops.conv_dgrad(self.packs, dy, w, stride, self.new(xn))
+                red = None
+                if stride == 1 and x.C % 8 == 0 and ops.stat_fusable(dy, w, True):
+                    dxn, red = ops.conv_dgrad(self.packs, dy, w, stride, self.new(xn), stat=("red", G, x, stats))
+                else:
+                    dxn = ops.conv_dgrad(self.packs, dy, w, stride, self.new(xn))
                 gg, accg = self._pgrad(gn + ".weight")
                 gb, _ = self._pgrad(gn + ".bias")
                 if x_needs_grad:
                     gx, accx = self._grad_of(x)
                 else:
                     gx, accx = None, False
-                ops.gn_backward(x, dxn, G, stats, gamma, gg, gb, accg, gx, accx)
+                ops.gn_backward(x, dxn, G, stats, gamma, gg, gb, accg, gx, accx, red=red)
             self.tape.append(bwd)
         return y
 
@@ -123,9 +133,9 @@ class Engine:
         else:
             r, r_needs_grad = x, x_needs_grad
         o = self.gn_conv(r, prefix + ".conv2.groupnorm", prefix + ".conv2.conv", 3, 1, True, train=train,
-                         x_needs_grad=r_needs_grad)
+                         x_needs_grad=r_needs_grad, y_stats=True)
         out = self.gn_conv(o, prefix + ".conv3.groupnorm", prefix + ".conv3.conv", 3, 1, True,
-                           res=r, train=train, res_needs_grad=r_needs_grad)
+                           res=r, train=train, res_needs_grad=r_needs_grad, y_stats=True)
         return out
 
     def hr_module(self, xs, prefix, nb, train, outputs=None):

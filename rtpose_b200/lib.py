@@ -32,7 +32,8 @@ class ConvDesc(C.Structure):
 class ConvK3S1Desc(C.Structure):
     _fields_ = [("inp", P8Struct), ("out", P8Struct), ("res", P8Struct), ("mask", P8Struct), ("w", C.c_void_p),
                 ("bias", C.c_void_p), ("Cin", C.c_int32), ("NPo", C.c_int32), ("out_c8", C.c_int32),
-                ("relu", C.c_int32), ("accumulate", C.c_int32), ("gn_sums", C.c_void_p)]
+                ("relu", C.c_int32), ("accumulate", C.c_int32), ("stat_mode", C.c_int32), ("stat_aux", P8Struct),
+                ("stat_ws", C.c_void_p), ("debug", C.c_void_p)]
 
 
 class WgradDesc(C.Structure):
@@ -63,6 +64,9 @@ PROTOTYPES = {
     "rtp_weight_pack_k3s1": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "rtp_conv_k3s1": (C.c_int, [C.POINTER(ConvK3S1Desc), _vp]),
     "rtp_conv_k3s1_smem_bytes": (C.c_int64, [_i32, _i32, _i32, _i32, _i32]),
+    "rtp_conv_k3s1_stat_ws_bytes": (C.c_int64, [_i32]),
+    "rtp_conv_k3s1_num_ctas": (C.c_int32, [_i32, _i32, _i32, _i32, _i32, _i32]),
+    "rtp_conv_k3s1_stat_finalize": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i64, _f32, _vp, _vp, _vp]),
     "rtp_conv_pw_supported": (C.c_int, [_i32, _i32]),
     "rtp_conv_pw": (C.c_int, [P8Struct, P8Struct, P8Struct, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "rtp_wgrad_workspace_bytes": (C.c_int64, [_i32, _i32, _i32, _i32]),

@@ -95,17 +95,21 @@ class PackedWeights:
     explicit `key` and `version` derived from the parameters they were built from."""
 
     def __init__(self):
-        self.cache = {}
+        self.cache = {}      # key -> (version, packed value, weakref to the source weight, repack(w) or None)
+        self._side = None    # stream of a refresh_async() still to be joined by the first consumer
 
     def _lookup(self, key, w, ver, explicit):
+        if self._side is not None:  # the first consumer after refresh_async() joins the packing stream
+            torch.cuda.current_stream(w.device).wait_stream(self._side)
+            self._side = None
         hit = self.cache.get(key)
         if hit is None:
             return None, None
-        hver, val, ref = hit
+        hver, val, ref, _ = hit
         same = explicit or (ref is not None and ref() is w)
         return (val if (same and hver == ver and hver is not None) else None), val
 
-    def _store(self, key, w, ver, val, explicit):
+    def _store(self, key, w, ver, val, explicit, repack):
         import weakref
         ref = None
         if not explicit:
@@ -113,7 +117,7 @@ class PackedWeights:
                 ref = weakref.ref(w)
             except TypeError:
                 ref = None
-        self.cache[key] = (ver, val, ref)
+        self.cache[key] = (ver, val, ref, repack if ref is not None else None)
 
     def get(self, w, mode, ci0=0, ci_n=None, key=None, version=None):
         Cout, Cin = w.shape[0], w.shape[1]
@@ -130,10 +134,13 @@ class PackedWeights:
         else:
             KP, NP = ceil_to(Cout, 16), ceil_to(ci_n, 16)
         dst = old[0] if old is not None else torch.empty(ntaps * KP * NP, dtype=torch.bfloat16, device=w.device)
-        wc = w.detach().contiguous()
-        lib.call("rtp_weight_pack", wc.data_ptr(), dst.data_ptr(), Cout, Cin, ntaps, ci0, ci_n, KP, NP, mode, _stream())
+
+        def repack(src):
+            wc = src.detach().contiguous()
+            lib.call("rtp_weight_pack", wc.data_ptr(), dst.data_ptr(), Cout, Cin, ntaps, ci0, ci_n, KP, NP, mode, _stream())
+        repack(w)
         val = (dst, KP, NP)
-        self._store(key, w, ver, val, explicit)
+        self._store(key, w, ver, val, explicit, repack)
         return val
 
     def get_k3s1(self, w, K, NPo, transpose_flip, key=None, version=None):
@@ -145,20 +152,53 @@ class PackedWeights:
         if val is not None:
             return val
         dst = old if old is not None else torch.empty(9 * K * 3 * NPo, dtype=torch.bfloat16, device=w.device)
-        wc = w.detach().contiguous()
-        lib.call("rtp_weight_pack_k3s1", wc.data_ptr(), dst.data_ptr(), w.shape[0], w.shape[1], K, NPo,
-                 int(bool(transpose_flip)), _stream())
-        self._store(key, w, ver, dst, explicit)
+        shape = (w.shape[0], w.shape[1])
+
+        def repack(src):
+            wc = src.detach().contiguous()
+            lib.call("rtp_weight_pack_k3s1", wc.data_ptr(), dst.data_ptr(), shape[0], shape[1], K, NPo,
+                     int(bool(transpose_flip)), _stream())
+        repack(w)
+        self._store(key, w, ver, dst, explicit, repack)
         return dst
+
+    def refresh_async(self):
+        """Training: the optimizer has rewritten the weights in place.  Repacks every cached weight that still has a live
+        source tensor on a side stream (forked after the work queued so far; the first consumer joins it), instead of
+        lazily, one small kernel at a time, in front of each conv.  Entries built from per-step temporaries (explicit
+        keys) are only invalidated."""
+        dev = None
+        for k in list(self.cache):
+            ver, val, ref, repack = self.cache[k]
+            w = ref() if ref is not None else None
+            if repack is None or w is None:
+                if ref is not None and w is None:
+                    del self.cache[k]          # the source tensor is gone
+                else:
+                    self.cache[k] = (None, val, ref, repack)
+                continue
+            if dev is None:
+                dev = w.device
+                global _pack_stream
+                if _pack_stream is None or _pack_stream.device != dev:
+                    _pack_stream = torch.cuda.Stream(device=dev)
+                _pack_stream.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(_pack_stream):
+                repack(w)
+            self.cache[k] = (w._version, val, ref, repack)
+        if dev is not None:
+            self._side = _pack_stream
 
     def invalidate(self):
         """Forces a repack on next use (weights are repacked once per optimizer step in training)."""
         for k in list(self.cache):
-            ver, val, ref = self.cache[k]
-            self.cache[k] = (None, val, ref)
+            ver, val, ref, repack = self.cache[k]
+            self.cache[k] = (None, val, ref, repack)
 
 
-# ------------------------------------------------------------------------------------------------ profiling hook
+_pack_stream = None
+
+
 PROFILE = None  # when a dict: key -> list of (start_event, end_event, algorithmic_flops); used by bench.py
 
 
@@ -248,9 +288,14 @@ def k3s1_eligible(x, K, NPo):
     return lib.load().rtp_conv_k3s1_smem_bytes(K, NPo, x.Z, x.X, x.Y) > 0
 
 
+FUSE_GN_STATS = True  # GroupNorm statistics / backward reductions come out of the producing conv's epilogue
+
+
 def conv_k3s1(packs, x, w, out, transpose_flip, bias=None, relu=False, res=None, mask=None, accumulate=False, key=None,
-              version=None):
-    """Plane-streaming 3x3x3 s1 conv (forward: transpose_flip=False; dgrad: True)."""
+              version=None, stat=None):
+    """Plane-streaming 3x3x3 s1 conv (forward: transpose_flip=False; dgrad: True).
+    stat: None | ("stats", G, eps) -> returns (out, stats[N][G][2]) of the stored result (GroupNorm forward)
+               | ("red", G, x_gn, stats) -> returns (out, red[N][C][2]) (GroupNorm backward reductions, out = dL/dxn)."""
     Cout, Cin = w.shape[0], w.shape[1]
     K, NPo = (ceil_to(Cin, 16), ceil_to(Cout, 16)) if not transpose_flip else (ceil_to(Cout, 16), ceil_to(Cin, 16))
     wp = packs.get_k3s1(w, K, NPo, transpose_flip, key, version)
@@ -263,20 +308,52 @@ def conv_k3s1(packs, x, w, out, transpose_flip, bias=None, relu=False, res=None,
     d.bias = b.data_ptr() if b is not None else None
     d.Cin, d.NPo, d.out_c8 = K, NPo, out.C8
     d.relu, d.accumulate = int(relu), int(accumulate)
-    d.gn_sums = None
+    d.debug = None
+    d.stat_mode, d.stat_ws = 0, None
+    if stat is not None:
+        L = lib.load()
+        sws = workspace(L.rtp_conv_k3s1_stat_ws_bytes(x.N), x.buf.device, "k3stat")
+        d.stat_mode, d.stat_ws = (1 if stat[0] == "stats" else 2), sws.data_ptr()
+        if stat[0] == "red":
+            d.stat_aux = stat[2].struct()
     pkey = ("conv_k3s1", Cin if not transpose_flip else Cout, Cout if not transpose_flip else Cin, 27, 1, 1,
             (x.Z, x.X, x.Y))
     ev = _prof_begin(pkey)
     lib.call("rtp_conv_k3s1", C.byref(d), _stream())
     _prof_end(pkey, ev, 2.0 * x.N * x.voxels * Cin * Cout * 27)
-    return out
+    if stat is None:
+        return out
+    nct = L.rtp_conv_k3s1_num_ctas(K, NPo, x.N, x.Z, x.X, x.Y)
+    Cc, G = out.C, stat[1]
+    if stat[0] == "stats":
+        res_t = torch.empty((x.N, G, 2), dtype=torch.float32, device=x.buf.device)
+        lib.call("rtp_conv_k3s1_stat_finalize", sws.data_ptr(), nct, 1, x.N, Cc, G, out.voxels, float(stat[2]), None,
+                 res_t.data_ptr(), _stream())
+    else:
+        res_t = torch.empty((x.N, Cc, 2), dtype=torch.float32, device=x.buf.device)
+        lib.call("rtp_conv_k3s1_stat_finalize", sws.data_ptr(), nct, 2, x.N, Cc, G, out.voxels, 0.0, stat[3].data_ptr(),
+                 res_t.data_ptr(), _stream())
+    return out, res_t
 
 
-def conv_forward(packs, x, w, stride, out, bias=None, relu=False, res=None, ci0=0, ci_n=None, key=None, version=None):
-    """y = conv3d(x[:, ci0:ci0+ci_n], w[:, ci0:ci0+ci_n], stride, padding=k//2) (+bias)(+res)(relu)."""
+def stat_fusable(x, w, transpose_flip):
+    """True when conv_forward / conv_dgrad of this call goes through the plane-streaming kernel with <= 32 result channels
+    (the shapes whose epilogue can carry the GroupNorm reductions)."""
+    Cout, Cin = w.shape[0], w.shape[1]
+    rc = Cin if transpose_flip else Cout
+    kin = Cout if transpose_flip else Cin
+    return (FUSE_GN_STATS and w.shape[2] == 3 and rc <= 32 and rc % 8 == 0
+            and k3s1_eligible(x, ceil_to(kin, 16), ceil_to(rc, 16)))
+
+
+def conv_forward(packs, x, w, stride, out, bias=None, relu=False, res=None, ci0=0, ci_n=None, key=None, version=None,
+                 stat=None):
+    """y = conv3d(x[:, ci0:ci0+ci_n], w[:, ci0:ci0+ci_n], stride, padding=k//2) (+bias)(+res)(relu).
+    stat (only when stat_fusable(x, w, False) and stride 1): see conv_k3s1; the return value becomes (y, stats)."""
     k = w.shape[2]
     if k == 3 and stride == 1 and ci0 == 0 and ci_n is None and k3s1_eligible(x, ceil_to(w.shape[1], 16), ceil_to(w.shape[0], 16)):
-        return conv_k3s1(packs, x, w, out, False, bias=bias, relu=relu, res=res, key=key, version=version)
+        return conv_k3s1(packs, x, w, out, False, bias=bias, relu=relu, res=res, key=key, version=version, stat=stat)
+    assert stat is None, "fused statistics need the plane-streaming kernel (check stat_fusable first)"
     if k == 1 and stride == 1 and res is None and USE_PW:
         wp, KP, NP = packs.get(w, 0, ci0, ci_n, key, version)
         if pw_eligible(x, out, KP, NP):
@@ -287,11 +364,13 @@ def conv_forward(packs, x, w, stride, out, bias=None, relu=False, res=None, ci0=
                 relu=relu, real=(ci_n if ci_n is not None else w.shape[1], w.shape[0]))
 
 
-def conv_dgrad(packs, dy, w, stride, dx, mask=None, accumulate=False, ci0=0, ci_n=None, key=None, version=None):
-    """dx (=|+=) conv_transpose(dy, w) [* (mask > 0)]; dx has the forward input's geometry."""
+def conv_dgrad(packs, dy, w, stride, dx, mask=None, accumulate=False, ci0=0, ci_n=None, key=None, version=None, stat=None):
+    """dx (=|+=) conv_transpose(dy, w) [* (mask > 0)]; dx has the forward input's geometry.
+    stat (only when stat_fusable(dy, w, True) and stride 1): see conv_k3s1; the return value becomes (dx, red)."""
     k = w.shape[2]
     if k == 3 and stride == 1 and ci0 == 0 and ci_n is None and k3s1_eligible(dy, ceil_to(w.shape[0], 16), ceil_to(w.shape[1], 16)):
-        return conv_k3s1(packs, dy, w, dx, True, mask=mask, accumulate=accumulate, key=key, version=version)
+        return conv_k3s1(packs, dy, w, dx, True, mask=mask, accumulate=accumulate, key=key, version=version, stat=stat)
+    assert stat is None, "fused statistics need the plane-streaming kernel (check stat_fusable first)"
     if (k == 3 and stride == 1 and ci0 == 0 and ci_n is None and w.shape[1] > 80 and w.shape[1] % 32 == 0
             and k3s1_eligible(dy, ceil_to(w.shape[0], 16), 32)):
         # wide dX (e.g. the 128-channel head input): one plane-streaming launch per 32-channel group of dX
@@ -458,10 +537,12 @@ def gn_apply(x, G, stats, gamma, beta, out):
     return out
 
 
-def gn_backward(x, dxn, G, stats, gamma, dgamma, dbeta, acc_params, dx, acc_dx):
-    red = torch.empty((x.N, x.C, 2), dtype=torch.float32, device=x.buf.device)
-    lib.call("rtp_gn_bwd_reduce", x.struct(), dxn.struct(), x.C, G, stats.data_ptr(), red.data_ptr(),
-             gn_ws(x).data_ptr(), _stream())
+def gn_backward(x, dxn, G, stats, gamma, dgamma, dbeta, acc_params, dx, acc_dx, red=None):
+    """red: the [N][C][2] reductions when the conv that produced dxn already computed them (conv_dgrad(stat=...))."""
+    if red is None:
+        red = torch.empty((x.N, x.C, 2), dtype=torch.float32, device=x.buf.device)
+        lib.call("rtp_gn_bwd_reduce", x.struct(), dxn.struct(), x.C, G, stats.data_ptr(), red.data_ptr(),
+                 gn_ws(x).data_ptr(), _stream())
     lib.call("rtp_gn_bwd_apply", x.struct(), dxn.struct(), x.C, G, stats.data_ptr(), red.data_ptr(), gamma.data_ptr(),
              dgamma.data_ptr(), dbeta.data_ptr(), int(acc_params), dx.struct() if dx is not None else lib.NULL_P8,
              int(acc_dx), int(x.relu_out), _stream())

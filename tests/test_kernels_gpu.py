@@ -451,3 +451,53 @@ def test_wgrad_k3s1(case):
         ops.USE_WGRAD_K3S1 = True
     torch.cuda.synchronize()
     close(dW2, w.grad, tol=2e-3, what="wgrad generic")
+
+
+STAT_CASES = [
+    # N, Cin, Cout, grid(Z,Y,X)
+    (2, 32, 32, (16, 30, 20)),
+    (3, 32, 32, (5, 64, 37)),      # several units per CTA across samples, z-chunking
+    (16, 32, 32, (4, 20, 24)),     # more samples than the common case: slab rows for every n
+    (2, 64, 32, (6, 12, 10)),      # two K passes
+    (2, 32, 16, (4, 10, 12)),      # 16 result channels
+]
+
+
+@pytest.mark.parametrize("case", STAT_CASES, ids=[str(c) for c in STAT_CASES])
+def test_conv_k3s1_fused_groupnorm_statistics(ctx, case):
+    """stat_mode 1 / 2 of rtp_conv_k3s1: the statistics that come out of the conv epilogue equal the ones the separate
+    reduction kernels compute from the stored tensor (different summation order: fp32 round-off only)."""
+    from rtpose_b200 import ops
+    from rtpose_b200.p8 import P8
+    N, Cin, Cout, grid = case
+    x = rnd(N, Cin, *grid, seed=70)
+    w = rnd(Cout, Cin, 3, 3, 3, seed=71, scale=0.1).cuda()
+    res = rnd(N, Cout, *grid, seed=72)
+    xp, resp = to_p8(x), to_p8(res)
+    assert ops.stat_fusable(xp, w, False)
+    # forward: y = relu(conv(x) + res), statistics of y
+    y0 = ops.conv_forward(ctx, xp, w, 1, P8(N, Cout, *grid), relu=True, res=resp)
+    G = 8
+    ref_stats = ops.gn_stats(y0, G)
+    y1, stats = ops.conv_forward(ctx, xp, w, 1, P8(N, Cout, *grid), relu=True, res=resp, stat=("stats", G, 1e-5))
+    torch.cuda.synchronize()
+    assert torch.equal(y0.to_ncdhw(), y1.to_ncdhw())
+    torch.testing.assert_close(stats, ref_stats, rtol=2e-5, atol=2e-6)
+    # dgrad: dxn = conv_transpose(dy), reductions against the GroupNorm input xg with its statistics
+    dy = to_p8(rnd(N, Cout, *grid, seed=73))
+    xg = to_p8(rnd(N, Cin, *grid, seed=74) + 0.3)
+    assert ops.stat_fusable(dy, w, True) == (Cin <= 32)
+    Gx = 8
+    st_x = ops.gn_stats(xg, Gx)
+    d0 = ops.conv_dgrad(ctx, dy, w, 1, P8(N, Cin, *grid))
+    red_ref = torch.empty((N, Cin, 2), dtype=torch.float32, device="cuda")
+    from rtpose_b200 import lib
+    from rtpose_b200.p8 import _stream
+    lib.call("rtp_gn_bwd_reduce", xg.struct(), d0.struct(), Cin, Gx, st_x.data_ptr(), red_ref.data_ptr(),
+             ops.gn_ws(xg).data_ptr(), _stream())
+    if Cin <= 32:
+        d1, red = ops.conv_dgrad(ctx, dy, w, 1, P8(N, Cin, *grid), stat=("red", Gx, xg, st_x))
+        torch.cuda.synchronize()
+        assert torch.equal(d0.to_ncdhw(), d1.to_ncdhw())
+        scale = red_ref.abs().max().item()
+        assert (red - red_ref).abs().max().item() <= 2e-5 * scale + 1e-4

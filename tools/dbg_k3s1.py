@@ -14,7 +14,7 @@ d = lib.ConvK3S1Desc()
 d.inp, d.out, d.res, d.mask = x.struct(), out.struct(), lib.NULL_P8, lib.NULL_P8
 d.w, d.bias, d.Cin, d.NPo, d.out_c8, d.relu, d.accumulate = wp.data_ptr(), None, 32, 32, 4, 0, 0
 for i in range(3):
-    d.gn_sums = dbg.data_ptr()
+    d.debug = dbg.data_ptr()
     lib.call("rtp_conv_k3s1", C.byref(d), _stream())
 torch.cuda.synchronize()
 t = dbg.view(148, 8).float()

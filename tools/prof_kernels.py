@@ -48,6 +48,9 @@ if what in ("conv", "all"):
     timeit("conv_k3s1 fwd 32->32", lambda: ops.conv_forward(packs, x, w, 1, out), fl)
     timeit("conv_k3s1 fwd +res+relu", lambda: ops.conv_forward(packs, x, w, 1, out, relu=True, res=dy), fl)
     timeit("conv_k3s1 dgrad", lambda: ops.conv_dgrad(packs, dy, w, 1, out), fl)
+    stx = ops.gn_stats(x, 8)
+    timeit("conv_k3s1 fwd +res+relu +stats", lambda: ops.conv_forward(packs, x, w, 1, out, relu=True, res=dy, stat=("stats", 8, 1e-5)), fl)
+    timeit("conv_k3s1 dgrad +gn-bwd sums", lambda: ops.conv_dgrad(packs, dy, w, 1, out, stat=("red", 8, x, stx)), fl)
     ops.USE_K3S1 = False
     timeit("conv_generic fwd 32->32", lambda: ops.conv_forward(packs, x, w, 1, out), fl)
     ops.USE_K3S1 = True
