@@ -120,6 +120,11 @@ typedef struct {
   int32_t stat_mode;
   rtp_p8 stat_aux;
   float* stat_ws;
+  /* structurally sparse weights (space-to-depth stride-2 convs): K is split into tap_mask_groups equal channel groups and
+   * bit t9 = kx*3+ky of tap_mask[g] says whether in-plane tap t9 of group g has any non-zero weight; all-zero taps are
+   * skipped by the MMA issuer.  use_tap_mask = 0: dense. */
+  int32_t use_tap_mask, tap_mask_groups;
+  uint16_t tap_mask[8];
   void* debug; /* tools only (tools/dbg_k3s1.py): [grid][8] int64 cycle counters of the MMA warp; NULL otherwise */
 } rtp_conv_k3s1_desc;
 int rtp_conv_k3s1(const rtp_conv_k3s1_desc* d, void* stream);
@@ -155,6 +160,8 @@ typedef struct {
   int8_t tz[RTP_MAX_TAPS], tx[RTP_MAX_TAPS], ty[RTP_MAX_TAPS];
   int32_t RZ, RX, RY, IS;
   int32_t nsplit;
+  int16_t tc[RTP_MAX_TAPS]; /* first 8-channel chunk of x the tap reads (0 = plain tensor; parity group * Cin/8 when x is
+                               a space-to-depth view and the taps are its 27 (parity, offset) pairs) */
   float* workspace;
 } rtp_wgrad_desc;
 int64_t rtp_wgrad_workspace_bytes(int32_t Cin, int32_t NP, int32_t ntaps, int32_t nsplit);
@@ -199,6 +206,23 @@ int rtp_gn_bwd_reduce(rtp_p8 x, rtp_p8 dy, int32_t C, int32_t G, const float* st
 int rtp_gn_bwd_apply(rtp_p8 x, rtp_p8 dy, int32_t C, int32_t G, const float* stats, const float* red,
                      const float* gamma, float* dgamma, float* dbeta, int32_t accumulate_params, rtp_p8 dx,
                      int32_t accumulate_dx, int32_t relu_mask, void* stream);
+/* Space-to-depth ("s2d") variants for the stride-2 exchange convs (fuse_layers / transition, hr_util/hr3d.py:159-203,
+ * :262-292).  The s2d view of a tensor with grid (Z, X, Y) (all even) and C8 chunks is a P8 tensor with grid
+ * (Z/2, X/2, Y/2) and 8*C8 chunks: voxel (z, x, y), chunk c lives at voxel (z/2, x/2, y/2), chunk
+ * ((z&1)*4 + (x&1)*2 + (y&1))*C8 + c.  A stride-2 3x3x3 pad-1 conv over the tensor equals a stride-1 one over the view
+ * with the weights of rtp_weight_s2d_expand, so it runs on rtp_conv_k3s1 / rtp_wgrad_k3s1 instead of the gather kernels.
+ * rtp_gn_apply_s2d writes the normalised tensor directly as that view; the *_bwd_*_s2d calls read dL/d(view). */
+int rtp_gn_apply_s2d(rtp_p8 x, int32_t C, int32_t G, const float* stats, const float* gamma, const float* beta,
+                     rtp_p8 y_s2d, void* stream);
+int rtp_gn_bwd_reduce_s2d(rtp_p8 x, rtp_p8 dy_s2d, int32_t C, int32_t G, const float* stats, float* red, float* workspace,
+                          void* stream);
+int rtp_gn_bwd_apply_s2d(rtp_p8 x, rtp_p8 dy_s2d, int32_t C, int32_t G, const float* stats, const float* red,
+                         const float* gamma, float* dgamma, float* dbeta, int32_t accumulate_params, rtp_p8 dx,
+                         int32_t accumulate_dx, int32_t relu_mask, void* stream);
+/* w [Cout][Cin][3][3][3] fp32 -> w_s2d [Cout][8*Cin][3][3][3] fp32 (zero except the 27 matching (parity, offset) pairs),
+ * and the transpose for the weight gradient: dw (=|+=) fold(dw_s2d). */
+int rtp_weight_s2d_expand(const float* w, float* w_s2d, int32_t Cout, int32_t Cin, void* stream);
+int rtp_weight_s2d_fold(const float* dw_s2d, float* dw, int32_t Cout, int32_t Cin, int32_t accumulate, void* stream);
 
 /* ---- branch exchange ---------------------------------------------------------------------------------------
  * replaces: the fuse sum of HighResolutionModule.forward (hr_util/hr3d.py:213-227) and the upsample+cat of

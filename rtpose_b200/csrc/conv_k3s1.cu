@@ -47,6 +47,7 @@ struct K3 {
   //   2: sum v, sum v*aux      (GroupNorm backward: v = dL/d(normalised x), aux = x)
   P8 stat_aux;
   float* stat_ws;  // [grid*8 warp slabs][N][64] then [grid CTA slabs][N][64]
+  uint16_t tapmask[32];  // per K pass: bit t9 set = in-plane tap t9 has non-zero weights (structurally sparse weights)
 };
 
 template <int KS, int STAT>  // KS = KG / 16: k16 steps per tap (1 or 2); STAT: fused statistics mode (0 = off)
@@ -85,7 +86,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_k3s1_kernel(const __grid_con
 
   if (warp == 0) {
     // ============================================================ producer
-    if (lane == 0) {
+    // lane 0 runs the barrier protocol; the copies of a step are issued by several lanes at once (one thread issuing
+    // bulk copies back to back is limited to ~8 GB/s per SM, profiles/r01_bulk_probe.txt)
+    {
       uint32_t it = 0, wit = 0;
       bool w_loaded = false;
       for (int u = blockIdx.x; u < p.nunits; u += gridDim.x) {
@@ -98,23 +101,29 @@ __global__ void __launch_bounds__(kThreads, 1) conv_k3s1_kernel(const __grid_con
         for (int g = 0; g < p.npass; ++g) {
           if (p.npass > 1 || !w_loaded) {
             const int wb = wit & 1;
-            mbar_wait(&bar_wempty[wb], ((wit >> 1) & 1) ^ 1);
-            mbar_arrive_expect_tx(&bar_wfull[wb], p.wbuf_bytes);
-            for (int t9 = 0; t9 < 9; ++t9)
-              bulk_g2s(wbuf + (size_t)wb * p.wbuf_bytes + (size_t)t9 * p.wtap_bytes,
-                       reinterpret_cast<const uint8_t*>(p.w) + (size_t)t9 * p.wtap_stride + (size_t)g * p.wtap_bytes,
+            if (lane == 0) {
+              mbar_wait(&bar_wempty[wb], ((wit >> 1) & 1) ^ 1);
+              mbar_arrive_expect_tx(&bar_wfull[wb], p.wbuf_bytes);
+            }
+            __syncwarp();
+            if (lane < 9)
+              bulk_g2s(wbuf + (size_t)wb * p.wbuf_bytes + (size_t)lane * p.wtap_bytes,
+                       reinterpret_cast<const uint8_t*>(p.w) + (size_t)lane * p.wtap_stride + (size_t)g * p.wtap_bytes,
                        p.wtap_bytes, &bar_wfull[wb]);
             ++wit;
             w_loaded = true;
           }
           for (int iz = iz0; iz < iz1; ++iz) {
             const int s = it % S;
-            mbar_wait(&bar_empty[s], ((it / S) & 1) ^ 1);
-            mbar_arrive_expect_tx(&bar_full[s], p.stage_bytes);
+            if (lane == 0) {
+              mbar_wait(&bar_empty[s], ((it / S) & 1) ^ 1);
+              mbar_arrive_expect_tx(&bar_full[s], p.stage_bytes);
+            }
+            __syncwarp();
             uint8_t* dst = stages + (size_t)s * p.stage_bytes;
-            for (int c = 0; c < kch; ++c)
-              bulk_g2s(dst + (size_t)c * p.PW * 16,
-                       in_n + (int64_t)(g * kch + c) * p.in.c_stride + (int64_t)iz * p.in.plane_elems(), p.PW * 16,
+            if (lane < kch)
+              bulk_g2s(dst + (size_t)lane * p.PW * 16,
+                       in_n + (int64_t)(g * kch + lane) * p.in.c_stride + (int64_t)iz * p.in.plane_elems(), p.PW * 16,
                        &bar_full[s]);
             ++it;
           }
@@ -192,9 +201,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_k3s1_kernel(const __grid_con
               }
             }
             first_done = (g == 0);
+            const uint32_t tm = p.tapmask[g];
             if (elect_one()) {  // elect.sync: the compiler knows exactly one lane runs this block (no per-MMA waterfall)
 #pragma unroll
               for (int t9 = 0; t9 < 9; ++t9) {
+                if (!((tm >> t9) & 1u)) continue;  // all-zero tap of this pass (space-to-depth weights)
                 const uint32_t at = a_lo + (uint32_t)((t9 / 3) * Yp + (t9 % 3));
                 const uint32_t bt = b_lo + boff16 + t9 * b_tap16;
 #pragma unroll
@@ -510,6 +521,11 @@ extern "C" int rtp_conv_k3s1(const rtp_conv_k3s1_desc* d, void* stream) {
                     "rtp_conv_k3s1: stat_aux must have the output's geometry");
   }
   k.stat_aux = P8(d->stat_aux); k.stat_ws = d->stat_ws;
+  RTP_CHECK_ARG(pl.npass <= 32, "rtp_conv_k3s1: too many K passes");
+  for (int g = 0; g < 32; ++g) k.tapmask[g] = d->use_tap_mask ? (uint16_t)(d->tap_mask[g < pl.npass ? g * pl.KG / (d->Cin / d->tap_mask_groups) : 0] & 0x1FF) : 0x1FF;
+  if (d->use_tap_mask) RTP_CHECK_ARG(d->tap_mask_groups >= 1 && d->tap_mask_groups <= 8 && d->Cin % d->tap_mask_groups == 0 &&
+                                         (d->Cin / d->tap_mask_groups) % pl.KG == 0,
+                                     "rtp_conv_k3s1: tap_mask_groups must split K into whole passes");
   const int ki = (pl.KG == 32 ? 1 : 0) + 2 * d->stat_mode;
   void (*kerns[6])(const K3) = {conv_k3s1_kernel<1, 0>, conv_k3s1_kernel<2, 0>, conv_k3s1_kernel<1, 1>,
                                 conv_k3s1_kernel<2, 1>, conv_k3s1_kernel<1, 2>, conv_k3s1_kernel<2, 2>};

@@ -230,6 +230,54 @@ extern "C" int rtp_weight_pack_k3s1(const float* w, void* dst_bf16, int32_t Cout
   RTP_LAUNCH_CHECK();
 }
 
+// ---------------------------------------------------------------------------------------------- space-to-depth weights
+// A stride-2 3x3x3 conv (pad 1) over x equals a stride-1 3x3x3 conv over the space-to-depth view of x (8 parity groups
+// of Cin channels at half resolution, see norm.cu s2d_offset): input index 2o + k - 1 has parity 1 / offset -1 for
+// k = 0, parity 0 / offset 0 for k = 1, parity 1 / offset 0 for k = 2.  W'[co][par*Cin + ci][t] with taps t in the
+// reference order (kz*3 + ky)*3 + kx holds W[co][ci][k] at the 27 matching (parity, offset) pairs and zero elsewhere.
+__device__ __forceinline__ int s2d_src_tap(int par, int t) { return par == 0 ? (t == 1 ? 1 : -1) : (t == 0 ? 0 : (t == 1 ? 2 : -1)); }
+
+__global__ void weight_s2d_expand_kernel(const float* __restrict__ w, float* __restrict__ we, int Cout, int Cin) {
+  const int64_t total = (int64_t)Cout * 8 * Cin * 27;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int t = (int)(i % 27);
+    const int64_t r = i / 27;
+    const int kk = (int)(r % (8 * Cin)), co = (int)(r / (8 * Cin));
+    const int par = kk / Cin, ci = kk % Cin;
+    const int sz = s2d_src_tap((par >> 2) & 1, t / 9), sy = s2d_src_tap(par & 1, (t / 3) % 3), sx = s2d_src_tap((par >> 1) & 1, t % 3);
+    we[i] = (sz >= 0 && sy >= 0 && sx >= 0) ? w[((int64_t)co * Cin + ci) * 27 + (sz * 3 + sy) * 3 + sx] : 0.f;
+  }
+}
+// the transpose: dW[co][ci][k] (=|+=) dW'[co][par(k)*Cin + ci][t(k)]
+__global__ void weight_s2d_fold_kernel(const float* __restrict__ dwe, float* __restrict__ dw, int Cout, int Cin, int accumulate) {
+  const int64_t total = (int64_t)Cout * Cin * 27;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(i % 27);
+    const int64_t r = i / 27;
+    const int ci = (int)(r % Cin), co = (int)(r / Cin);
+    const int kz = k / 9, ky = (k / 3) % 3, kx = k % 3;
+    // k = 0 -> (parity 1, tap 0); 1 -> (0, 1); 2 -> (1, 1)
+    const int pz = kz != 1, py = ky != 1, px = kx != 1;
+    const int tz = kz == 0 ? 0 : 1, ty = ky == 0 ? 0 : 1, tx = kx == 0 ? 0 : 1;
+    const int par = (pz << 2) | (px << 1) | py;
+    const float v = dwe[((int64_t)co * 8 * Cin + par * Cin + ci) * 27 + (tz * 3 + ty) * 3 + tx];
+    dw[i] = accumulate ? dw[i] + v : v;
+  }
+}
+extern "C" int rtp_weight_s2d_expand(const float* w, float* w_s2d, int32_t Cout, int32_t Cin, void* stream) {
+  RTP_CHECK_ARG(w && w_s2d && Cout > 0 && Cin > 0, "rtp_weight_s2d_expand: bad arguments");
+  const int64_t total = (int64_t)Cout * 8 * Cin * 27;
+  weight_s2d_expand_kernel<<<ceil_div(total, 256) > 1024 ? 1024 : ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(w, w_s2d, Cout, Cin);
+  RTP_LAUNCH_CHECK();
+}
+extern "C" int rtp_weight_s2d_fold(const float* dw_s2d, float* dw, int32_t Cout, int32_t Cin, int32_t accumulate, void* stream) {
+  RTP_CHECK_ARG(dw_s2d && dw && Cout > 0 && Cin > 0, "rtp_weight_s2d_fold: bad arguments");
+  const int64_t total = (int64_t)Cout * Cin * 27;
+  weight_s2d_fold_kernel<<<ceil_div(total, 256) > 1024 ? 1024 : ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(dw_s2d, dw, Cout, Cin,
+                                                                                                                     accumulate);
+  RTP_LAUNCH_CHECK();
+}
+
 // ---------------------------------------------------------------------------------------------- misc
 __global__ void scale_kernel(float* __restrict__ b, int64_t n, float s) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) b[i] *= s;

@@ -39,6 +39,31 @@ __device__ __forceinline__ void rows_foreach(const P8& t, int row_begin, int row
     }
   }
 }
+// same walk, also handing out the voxel coordinates: f(element_offset, z, x, y)
+template <typename F>
+__device__ __forceinline__ void rows_foreach_zxy(const P8& t, int row_begin, int row_end, int log2ty, F&& f) {
+  const int TY = 1 << log2ty;
+  const int ty = threadIdx.x & (TY - 1), tr = threadIdx.x >> log2ty;
+  const int rstep = (int)blockDim.x >> log2ty;
+  int row = row_begin + tr;
+  if (row < row_end) {
+    int z = row / t.X, x = row - z * t.X;
+    for (; row < row_end; row += rstep) {
+      const int64_t base = t.voxel(z, x, 0);
+      for (int y = ty; y < t.Y; y += TY) f(base + (int64_t)y * 8, z, x, y);
+      x += rstep;
+      while (x >= t.X) { x -= t.X; ++z; }
+    }
+  }
+}
+// Space-to-depth view of a tensor with C8 chunks: voxel (z, x, y), chunk c8 lives in the half-resolution tensor `s` at
+// voxel (z/2, x/2, y/2), chunk ((z&1)*4 + (x&1)*2 + (y&1)) * C8 + c8.  A stride-2 3x3x3 conv over the original is a
+// stride-1 conv over this view (tap k = 0 / 1 / 2 of a dimension reads parity 1 at offset -1 / parity 0 at 0 / parity 1
+// at 0), which is what lets the stride-2 exchange convs run on the plane-streaming kernels.
+__device__ __forceinline__ int64_t s2d_offset(const P8& s, int C8, int c8, int z, int x, int y) {
+  const int par = ((z & 1) << 2) | ((x & 1) << 1) | (y & 1);
+  return (int64_t)(par * C8 + c8) * s.c_stride + s.voxel(z >> 1, x >> 1, y >> 1);
+}
 __host__ __device__ inline int log2_ty(int Y) {
   int l = 3;
   while ((1 << l) < Y && l < 6) ++l;
@@ -122,6 +147,7 @@ __global__ void gn_finalize_kernel(const float* __restrict__ sums, int N, int C,
 }
 
 // y = (x - mean) * rstd * gamma + beta  on real voxels (pads are never written)
+template <bool S2D>  // S2D: y is the space-to-depth view (half resolution, 8x the chunks)
 __global__ void __launch_bounds__(256) gn_apply_kernel(P8 x, int C, int G, const float* __restrict__ stats,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        P8 y) {
@@ -147,17 +173,30 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(P8 x, int C, int G, const
   const int R = x.Z * x.X;
   const int r0 = (int)((int64_t)R * blockIdx.x / gridDim.x), r1 = (int)((int64_t)R * (blockIdx.x + 1) / gridDim.x);
   const bf16* xb = x.ptr + n * x.n_stride + c8 * x.c_stride;
-  bf16* yb = y.ptr + n * y.n_stride + c8 * y.c_stride;
-  rows_foreach(x, r0, r1, log2_ty(x.Y), [&](int64_t off) {
-    float f[8];
-    unpack8(ldg16(xb + off), f);
+  if constexpr (S2D) {
+    bf16* yb = y.ptr + n * y.n_stride;
+    const int C8 = (int)gridDim.y;
+    rows_foreach_zxy(x, r0, r1, log2_ty(x.Y), [&](int64_t off, int z, int xx, int yy) {
+      float f[8];
+      unpack8(ldg16(xb + off), f);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) f[i] = fmaf(f[i], a[i], b[i]);
-    stg16(yb + off, pack8(f));
-  });
+      for (int i = 0; i < 8; ++i) f[i] = fmaf(f[i], a[i], b[i]);
+      stg16(yb + s2d_offset(y, C8, c8, z, xx, yy), pack8(f));
+    });
+  } else {
+    bf16* yb = y.ptr + n * y.n_stride + c8 * y.c_stride;
+    rows_foreach(x, r0, r1, log2_ty(x.Y), [&](int64_t off) {
+      float f[8];
+      unpack8(ldg16(xb + off), f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] = fmaf(f[i], a[i], b[i]);
+      stg16(yb + off, pack8(f));
+    });
+  }
 }
 
 // partial[n][c8][slab][16] = (sum dy[0..7], sum dy*xhat[0..7])
+template <bool S2D>  // S2D: dy is laid out as the space-to-depth view of x's grid
 __global__ void __launch_bounds__(256) gn_bwd_partial_kernel(P8 x, P8 dy, int C, int G, const float* __restrict__ stats,
                                                              float* __restrict__ partial) {
   __shared__ float sh[8 * 16];
@@ -174,14 +213,15 @@ __global__ void __launch_bounds__(256) gn_bwd_partial_kernel(P8 x, P8 dy, int C,
   const int R = x.Z * x.X;
   const int r0 = (int)((int64_t)R * slab / kSlabs), r1 = (int)((int64_t)R * (slab + 1) / kSlabs);
   const bf16* xb = x.ptr + n * x.n_stride + c8 * x.c_stride;
-  const bf16* db = dy.ptr + n * dy.n_stride + c8 * dy.c_stride;
+  const bf16* db = dy.ptr + n * dy.n_stride + (S2D ? 0 : c8 * dy.c_stride);
+  const int C8 = (int)gridDim.y;
   float acc[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) acc[i] = 0.f;
-  rows_foreach(x, r0, r1, log2_ty(x.Y), [&](int64_t off) {
+  rows_foreach_zxy(x, r0, r1, log2_ty(x.Y), [&](int64_t off, int z, int xx, int yy) {
     float f[8], d[8];
     unpack8(ldg16(xb + off), f);
-    unpack8(ldg16(db + off), d);
+    unpack8(ldg16(db + (S2D ? s2d_offset(dy, C8, c8, z, xx, yy) : off)), d);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       acc[i] += d[i];
@@ -206,6 +246,7 @@ __global__ void gn_param_grad_kernel(const float* __restrict__ red, int N, int C
 }
 
 // dx (=|+=) [x>0] * rstd * (gamma*dy - (s1 + xhat*s2)/m)
+template <bool S2D>
 __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(P8 x, P8 dy, int C, int G, const float* __restrict__ stats,
                                                            const float* __restrict__ red, const float* __restrict__ gamma,
                                                            P8 dx, int accumulate, int relu_mask) {
@@ -237,12 +278,13 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(P8 x, P8 dy, int C, i
   const int R = x.Z * x.X;
   const int r0 = (int)((int64_t)R * blockIdx.x / gridDim.x), r1 = (int)((int64_t)R * (blockIdx.x + 1) / gridDim.x);
   const bf16* xb = x.ptr + n * x.n_stride + c8 * x.c_stride;
-  const bf16* db = dy.ptr + n * dy.n_stride + c8 * dy.c_stride;
+  const bf16* db = dy.ptr + n * dy.n_stride + (S2D ? 0 : c8 * dy.c_stride);
   bf16* ob = dx.ptr + n * dx.n_stride + c8 * dx.c_stride;
-  rows_foreach(x, r0, r1, log2_ty(x.Y), [&](int64_t off) {
+  const int C8 = (int)gridDim.y;
+  rows_foreach_zxy(x, r0, r1, log2_ty(x.Y), [&](int64_t off, int z, int xx, int yy) {
     float f[8], d[8], o[8];
     unpack8(ldg16(xb + off), f);
-    unpack8(ldg16(db + off), d);
+    unpack8(ldg16(db + (S2D ? s2d_offset(dy, C8, c8, z, xx, yy) : off)), d);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const float xh = (f[i] - mean[i]) * rstd[i];
@@ -284,44 +326,102 @@ extern "C" int rtp_gn_finalize(const float* sums, int32_t N, int32_t C, int32_t 
   RTP_LAUNCH_CHECK();
 }
 
-extern "C" int rtp_gn_apply(rtp_p8 x, int32_t C, int32_t G, const float* stats, const float* gamma, const float* beta,
-                            rtp_p8 y, void* stream) {
+namespace {
+// `v` must be the space-to-depth view of a tensor with x's grid and ceil(C/8) chunks
+bool s2d_view_of(const rtp_p8& v, const rtp_p8& x, int C) {
+  return x.Z % 2 == 0 && x.X % 2 == 0 && x.Y % 2 == 0 && v.N == x.N && v.Z == x.Z / 2 && v.X == x.X / 2 && v.Y == x.Y / 2 &&
+         v.C8 >= 8 * ceil_div(C, 8);
+}
+
+int gn_apply_impl(rtp_p8 x, int32_t C, int32_t G, const float* stats, const float* gamma, const float* beta, rtp_p8 y, bool s2d,
+                  void* stream) {
   RTP_CHECK_ARG(x.ptr && y.ptr && stats && gamma && beta, "rtp_gn_apply: null argument");
-  RTP_CHECK_ARG(C > 0 && C % G == 0 && C <= x.C8 * 8 && C <= y.C8 * 8, "rtp_gn_apply: bad C/G");
-  RTP_CHECK_ARG(x.N == y.N && x.Z == y.Z && x.X == y.X && x.Y == y.Y, "rtp_gn_apply: geometry mismatch");
+  RTP_CHECK_ARG(C > 0 && C % G == 0 && C <= x.C8 * 8, "rtp_gn_apply: bad C/G");
+  if (s2d)
+    RTP_CHECK_ARG(s2d_view_of(y, x, C), "rtp_gn_apply_s2d: y must be the half-resolution view with 8x the chunks (even extents)");
+  else
+    RTP_CHECK_ARG(C <= y.C8 * 8 && x.N == y.N && x.Z == y.Z && x.X == y.X && x.Y == y.Y, "rtp_gn_apply: geometry mismatch");
   P8 tx(x), ty(y);
   const int64_t V = (int64_t)x.Z * x.X * x.Y;
-  gn_apply_kernel<<<dim3(ew_blocks(V), ceil_div(C, 8), x.N), 256, 0, (cudaStream_t)stream>>>(tx, C, G, stats, gamma, beta, ty);
+  const dim3 grid(ew_blocks(V), ceil_div(C, 8), x.N);
+  if (s2d)
+    gn_apply_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(tx, C, G, stats, gamma, beta, ty);
+  else
+    gn_apply_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(tx, C, G, stats, gamma, beta, ty);
   RTP_LAUNCH_CHECK();
 }
 
-extern "C" int rtp_gn_bwd_reduce(rtp_p8 x, rtp_p8 dy, int32_t C, int32_t G, const float* stats, float* red,
-                                 float* workspace, void* stream) {
+int gn_bwd_reduce_impl(rtp_p8 x, rtp_p8 dy, int32_t C, int32_t G, const float* stats, float* red, float* workspace, bool s2d,
+                       void* stream) {
   RTP_CHECK_ARG(x.ptr && dy.ptr && stats && red && workspace, "rtp_gn_bwd_reduce: null argument");
-  RTP_CHECK_ARG(C > 0 && C % G == 0 && C <= x.C8 * 8 && C <= dy.C8 * 8, "rtp_gn_bwd_reduce: bad C/G");
-  RTP_CHECK_ARG(x.N == dy.N && x.Z == dy.Z && x.X == dy.X && x.Y == dy.Y, "rtp_gn_bwd_reduce: geometry mismatch");
+  RTP_CHECK_ARG(C > 0 && C % G == 0 && C <= x.C8 * 8, "rtp_gn_bwd_reduce: bad C/G");
+  if (s2d)
+    RTP_CHECK_ARG(s2d_view_of(dy, x, C), "rtp_gn_bwd_reduce_s2d: dy must be the space-to-depth view of x's grid");
+  else
+    RTP_CHECK_ARG(C <= dy.C8 * 8 && x.N == dy.N && x.Z == dy.Z && x.X == dy.X && x.Y == dy.Y, "rtp_gn_bwd_reduce: geometry mismatch");
   P8 tx(x), td(dy);
   tx.C8 = ceil_div(C, 8);
-  gn_bwd_partial_kernel<<<dim3(kSlabs, tx.C8, tx.N), 256, 0, (cudaStream_t)stream>>>(tx, td, C, G, stats, workspace);
+  const dim3 grid(kSlabs, tx.C8, tx.N);
+  if (s2d)
+    gn_bwd_partial_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(tx, td, C, G, stats, workspace);
+  else
+    gn_bwd_partial_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(tx, td, C, G, stats, workspace);
   gn_sums_final_kernel<<<ceil_div(tx.N * tx.C8 * 8, 128), 128, 0, (cudaStream_t)stream>>>(workspace, tx.N, tx.C8, C, red);
   RTP_LAUNCH_CHECK();
 }
 
-extern "C" int rtp_gn_bwd_apply(rtp_p8 x, rtp_p8 dy, int32_t C, int32_t G, const float* stats, const float* red,
-                                const float* gamma, float* dgamma, float* dbeta, int32_t accumulate_params, rtp_p8 dx,
-                                int32_t accumulate_dx, int32_t relu_mask, void* stream) {
+int gn_bwd_apply_impl(rtp_p8 x, rtp_p8 dy, int32_t C, int32_t G, const float* stats, const float* red, const float* gamma,
+                      float* dgamma, float* dbeta, int32_t accumulate_params, rtp_p8 dx, int32_t accumulate_dx, int32_t relu_mask,
+                      bool s2d, void* stream) {
   RTP_CHECK_ARG(x.ptr && dy.ptr && stats && red && gamma, "rtp_gn_bwd_apply: null argument");
-  RTP_CHECK_ARG(C > 0 && C % G == 0 && C <= x.C8 * 8 && C <= dy.C8 * 8, "rtp_gn_bwd_apply: bad C/G");
+  RTP_CHECK_ARG(C > 0 && C % G == 0 && C <= x.C8 * 8, "rtp_gn_bwd_apply: bad C/G");
+  if (s2d)
+    RTP_CHECK_ARG(s2d_view_of(dy, x, C), "rtp_gn_bwd_apply_s2d: dy must be the space-to-depth view of x's grid");
+  else
+    RTP_CHECK_ARG(C <= dy.C8 * 8, "rtp_gn_bwd_apply: bad C/G");
   if (dgamma && dbeta)
     gn_param_grad_kernel<<<ceil_div(C, 64), 64, 0, (cudaStream_t)stream>>>(red, x.N, C, dgamma, dbeta, accumulate_params);
   if (dx.ptr) {
     RTP_CHECK_ARG(x.N == dx.N && x.Z == dx.Z && x.X == dx.X && x.Y == dx.Y && C <= dx.C8 * 8, "rtp_gn_bwd_apply: dx geometry mismatch");
     P8 tx(x), td(dy), to(dx);
     const int64_t V = (int64_t)x.Z * x.X * x.Y;
-    gn_bwd_apply_kernel<<<dim3(ew_blocks(V), ceil_div(C, 8), x.N), 256, 0, (cudaStream_t)stream>>>(
-        tx, td, C, G, stats, red, gamma, to, accumulate_dx, relu_mask);
+    const dim3 grid(ew_blocks(V), ceil_div(C, 8), x.N);
+    if (s2d)
+      gn_bwd_apply_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(tx, td, C, G, stats, red, gamma, to, accumulate_dx, relu_mask);
+    else
+      gn_bwd_apply_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(tx, td, C, G, stats, red, gamma, to, accumulate_dx, relu_mask);
   }
   RTP_LAUNCH_CHECK();
+}
+}  // namespace
+
+extern "C" int rtp_gn_apply(rtp_p8 x, int32_t C, int32_t G, const float* stats, const float* gamma, const float* beta,
+                            rtp_p8 y, void* stream) {
+  return gn_apply_impl(x, C, G, stats, gamma, beta, y, false, stream);
+}
+extern "C" int rtp_gn_apply_s2d(rtp_p8 x, int32_t C, int32_t G, const float* stats, const float* gamma, const float* beta,
+                                rtp_p8 y_s2d, void* stream) {
+  return gn_apply_impl(x, C, G, stats, gamma, beta, y_s2d, true, stream);
+}
+extern "C" int rtp_gn_bwd_reduce(rtp_p8 x, rtp_p8 dy, int32_t C, int32_t G, const float* stats, float* red,
+                                 float* workspace, void* stream) {
+  return gn_bwd_reduce_impl(x, dy, C, G, stats, red, workspace, false, stream);
+}
+extern "C" int rtp_gn_bwd_reduce_s2d(rtp_p8 x, rtp_p8 dy_s2d, int32_t C, int32_t G, const float* stats, float* red,
+                                     float* workspace, void* stream) {
+  return gn_bwd_reduce_impl(x, dy_s2d, C, G, stats, red, workspace, true, stream);
+}
+extern "C" int rtp_gn_bwd_apply(rtp_p8 x, rtp_p8 dy, int32_t C, int32_t G, const float* stats, const float* red,
+                                const float* gamma, float* dgamma, float* dbeta, int32_t accumulate_params, rtp_p8 dx,
+                                int32_t accumulate_dx, int32_t relu_mask, void* stream) {
+  return gn_bwd_apply_impl(x, dy, C, G, stats, red, gamma, dgamma, dbeta, accumulate_params, dx, accumulate_dx, relu_mask, false,
+                           stream);
+}
+extern "C" int rtp_gn_bwd_apply_s2d(rtp_p8 x, rtp_p8 dy_s2d, int32_t C, int32_t G, const float* stats, const float* red,
+                                    const float* gamma, float* dgamma, float* dbeta, int32_t accumulate_params, rtp_p8 dx,
+                                    int32_t accumulate_dx, int32_t relu_mask, void* stream) {
+  return gn_bwd_apply_impl(x, dy_s2d, C, G, stats, red, gamma, dgamma, dbeta, accumulate_params, dx, accumulate_dx, relu_mask, true,
+                           stream);
 }
 
 // ================================================================================================ stem / bias grads

@@ -23,6 +23,7 @@ struct WgradK {
   P8 x, dy;
   int Cin, NP, ntaps;
   int8_t tz[RTP_MAX_TAPS], tx[RTP_MAX_TAPS], ty[RTP_MAX_TAPS];
+  int16_t tc[RTP_MAX_TAPS];  // first 8-channel chunk of X read by the tap (space-to-depth views: parity group * Cin/8)
   int RZ, RX, RY, IS;
   int64_t total_rows;
   int ntiles, tiles_per_split;
@@ -111,8 +112,9 @@ __global__ void __launch_bounds__(kThreads) wgrad_generic_kernel(const __grid_co
           const int tap = pair / kch, c = pair - tap * kch;
           const int tz = p.tz[tap];
           const int iz = rz * p.IS + tz;
-          ok = iz >= 0 && iz < p.x.Z && c < p.x.C8;
-          src = x_row + (((int64_t)tz * p.x.Xp + p.tx[tap]) * p.x.Yp + p.ty[tap]) * 8 + (int64_t)c * p.x.c_stride;
+          const int cc = p.tc[tap] + c;
+          ok = iz >= 0 && iz < p.x.Z && cc < p.x.C8;
+          src = x_row + (((int64_t)tz * p.x.Xp + p.tx[tap]) * p.x.Yp + p.ty[tap]) * 8 + (int64_t)cc * p.x.c_stride;
         }
         cp_async16(sA + ((size_t)mc * kTileK + pos) * 16, ok ? (const void*)src : (const void*)p.x.ptr, ok);
       }
@@ -256,7 +258,7 @@ extern "C" int rtp_wgrad(const rtp_wgrad_desc* d, void* stream) {
   WgradK k;
   k.x = P8(d->x); k.dy = P8(d->dy);
   k.Cin = d->Cin; k.NP = d->NP; k.ntaps = d->ntaps;
-  for (int t = 0; t < RTP_MAX_TAPS; ++t) { k.tz[t] = d->tz[t]; k.tx[t] = d->tx[t]; k.ty[t] = d->ty[t]; }
+  for (int t = 0; t < RTP_MAX_TAPS; ++t) { k.tz[t] = d->tz[t]; k.tx[t] = d->tx[t]; k.ty[t] = d->ty[t]; k.tc[t] = d->tc[t]; }
   k.RZ = d->RZ; k.RX = d->RX; k.RY = d->RY; k.IS = d->IS;
   k.total_rows = (int64_t)d->x.N * d->RZ * d->RX * d->RY;
   k.ntiles = (int)((k.total_rows + kTileK - 1) / kTileK);

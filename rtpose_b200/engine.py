@@ -76,9 +76,11 @@ class Engine:
         if stats is None:
             stats = ops.gn_stats(x, G)
             self.stats_cache[id(x)] = stats
-        xn = ops.gn_apply(x, G, stats, gamma, beta, self.new(x))
         Zo, Yo, Xo = ops.out_grid(x, stride)
         y = self.new(x, C=w.shape[0], grid=(Zo, Yo, Xo))
+        if stride == 2 and k == 3 and ops.s2d_eligible(x, w):
+            return self._gn_conv_s2d(x, y, G, stats, gamma, beta, w, gn, conv, relu, res, train, x_needs_grad, res_needs_grad)
+        xn = ops.gn_apply(x, G, stats, gamma, beta, self.new(x))
         if y_stats and stride == 1 and y.C % 8 == 0 and ops.stat_fusable(xn, w, False):
             _, st = ops.conv_forward(self.packs, xn, w, stride, y, relu=relu, res=res, stat=("stats", 8, 1e-5))
             self.stats_cache[id(y)] = st
@@ -107,6 +109,40 @@ class Engine:
                 else:
                     gx, accx = None, False
                 ops.gn_backward(x, dxn, G, stats, gamma, gg, gb, accg, gx, accx, red=red)
+            self.tape.append(bwd)
+        return y
+
+    def _gn_conv_s2d(self, x, y, G, stats, gamma, beta, w, gn, conv, relu, res, train, x_needs_grad, res_needs_grad):
+        """Stride-2 3x3x3 gn_conv through the space-to-depth view (include/rtpose_b200.h, rtp_gn_apply_s2d): GroupNorm
+        writes the view, the conv / dgrad / wgrad are stride-1 plane-streaming launches with the expanded weights, and
+        GroupNorm backward reads the gradient of the view."""
+        dev = x.buf.device
+        xs = self.pool.get(x.N, 8 * x.C, x.Z // 2, x.Y // 2, x.X // 2, dev)
+        ops.gn_apply_s2d(x, G, stats, gamma, beta, xs)
+        we = ops.s2d_expand(w)
+        wkey, wver = ("s2d", w.data_ptr()), w._version
+        ops.conv_forward(self.packs, xs, we, 1, y, relu=relu, res=res, key=wkey, version=wver,
+                         tap_mask=[ops.s2d_tap_mask(par, False) for par in range(8)])
+        y.relu_out = bool(relu)
+        if train:
+            def bwd():
+                dy = y.grad
+                if dy is None:
+                    return
+                if res is not None and res_needs_grad:
+                    g, acc = self._grad_of(res)
+                    ops.grad_add(dy, g, mask=res if res.relu_out else None, accumulate=acc)
+                gw, accw = self._pgrad(conv + ".weight")
+                ops.on_wgrad_stream(xs, lambda: ops.conv_wgrad_s2d(xs, dy, x.C, gw, accumulate=accw))
+                dxs = ops.conv_dgrad(self.packs, dy, we, 1, self.pool.get(x.N, 8 * x.C, x.Z // 2, x.Y // 2, x.X // 2, dev),
+                                     key=wkey, version=wver, s2d_cin=x.C)
+                gg, accg = self._pgrad(gn + ".weight")
+                gb, _ = self._pgrad(gn + ".bias")
+                if x_needs_grad:
+                    gx, accx = self._grad_of(x)
+                else:
+                    gx, accx = None, False
+                ops.gn_backward(x, dxs, G, stats, gamma, gg, gb, accg, gx, accx, s2d=True)
             self.tape.append(bwd)
         return y
 

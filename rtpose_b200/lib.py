@@ -33,14 +33,15 @@ class ConvK3S1Desc(C.Structure):
     _fields_ = [("inp", P8Struct), ("out", P8Struct), ("res", P8Struct), ("mask", P8Struct), ("w", C.c_void_p),
                 ("bias", C.c_void_p), ("Cin", C.c_int32), ("NPo", C.c_int32), ("out_c8", C.c_int32),
                 ("relu", C.c_int32), ("accumulate", C.c_int32), ("stat_mode", C.c_int32), ("stat_aux", P8Struct),
-                ("stat_ws", C.c_void_p), ("debug", C.c_void_p)]
+                ("stat_ws", C.c_void_p), ("use_tap_mask", C.c_int32), ("tap_mask_groups", C.c_int32), ("tap_mask", C.c_uint16 * 8),
+                ("debug", C.c_void_p)]
 
 
 class WgradDesc(C.Structure):
     _fields_ = [("x", P8Struct), ("dy", P8Struct), ("Cin", C.c_int32), ("NP", C.c_int32), ("ntaps", C.c_int32),
                 ("tz", C.c_int8 * MAX_TAPS), ("tx", C.c_int8 * MAX_TAPS), ("ty", C.c_int8 * MAX_TAPS),
                 ("RZ", C.c_int32), ("RX", C.c_int32), ("RY", C.c_int32), ("IS", C.c_int32), ("nsplit", C.c_int32),
-                ("workspace", C.c_void_p)]
+                ("tc", C.c_int16 * MAX_TAPS), ("workspace", C.c_void_p)]
 
 
 class FuseDesc(C.Structure):
@@ -84,6 +85,12 @@ PROTOTYPES = {
     "rtp_gn_bwd_reduce": (C.c_int, [P8Struct, P8Struct, _i32, _i32, _vp, _vp, _vp, _vp]),
     "rtp_gn_bwd_apply": (C.c_int, [P8Struct, P8Struct, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _i32, P8Struct, _i32,
                                    _i32, _vp]),
+    "rtp_gn_apply_s2d": (C.c_int, [P8Struct, _i32, _i32, _vp, _vp, _vp, P8Struct, _vp]),
+    "rtp_gn_bwd_reduce_s2d": (C.c_int, [P8Struct, P8Struct, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "rtp_gn_bwd_apply_s2d": (C.c_int, [P8Struct, P8Struct, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _i32, P8Struct, _i32,
+                                       _i32, _vp]),
+    "rtp_weight_s2d_expand": (C.c_int, [_vp, _vp, _i32, _i32, _vp]),
+    "rtp_weight_s2d_fold": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp]),
     "rtp_fuse_sum": (C.c_int, [C.POINTER(FuseDesc), _vp]),
     "rtp_upsample_bwd_workspace_bytes": (C.c_int64, [P8Struct, P8Struct, _i32]),
     "rtp_upsample_bwd": (C.c_int, [P8Struct, P8Struct, _i32, _i32, _vp, _vp]),
@@ -152,7 +159,8 @@ LAUNCHES = {"rtp_pack_ncdhw": 1, "rtp_unpack_ncdhw": 1, "rtp_ingest_pack": 1, "r
             "rtp_fuse_sum": 1, "rtp_upsample_bwd": 3, "rtp_grad_add": 1, "rtp_channel_sum": 2, "rtp_stem_fwd": 1,
             "rtp_stem_bwd": 2, "rtp_head_loss": 2, "rtp_decode": 1, "rtp_scale_f32": 1, "rtp_dcn_fwd": 1,
             "rtp_dcn_bwd_input": 1, "rtp_dcn_bwd_weight": 1, "rtp_adam_step": 2, "rtp_adam_step_dev": 2,
-            "rtp_assign_targets": 2, "rtp_wgrad_k3s1": 1, "rtp_wgrad_k3s1_reduce": 1, "rtp_conv_pw": 1}
+            "rtp_assign_targets": 2, "rtp_wgrad_k3s1": 1, "rtp_wgrad_k3s1_reduce": 1, "rtp_conv_pw": 1, "rtp_gn_apply_s2d": 1, "rtp_gn_bwd_reduce_s2d": 2,
+            "rtp_gn_bwd_apply_s2d": 2, "rtp_conv_k3s1_stat_finalize": 1}
 launch_count = 0
 
 

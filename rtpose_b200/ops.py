@@ -291,8 +291,20 @@ def k3s1_eligible(x, K, NPo):
 FUSE_GN_STATS = True  # GroupNorm statistics / backward reductions come out of the producing conv's epilogue
 
 
+def s2d_tap_mask(par, flipped):
+    """In-plane taps (bit kx*3+ky, offsets -1/0/+1 along P8 x / y) that carry weights for parity group `par` of the
+    space-to-depth view: parity 0 -> offset 0 only; parity 1 -> offsets -1, 0 (forward) or 0, +1 (dgrad, mirrored)."""
+    def valid(bit):
+        return (1,) if not bit else ((1, 2) if flipped else (0, 1))
+    m = 0
+    for tx in valid((par >> 1) & 1):
+        for ty in valid(par & 1):
+            m |= 1 << (tx * 3 + ty)
+    return m
+
+
 def conv_k3s1(packs, x, w, out, transpose_flip, bias=None, relu=False, res=None, mask=None, accumulate=False, key=None,
-              version=None, stat=None):
+              version=None, stat=None, tap_mask=None):
     """Plane-streaming 3x3x3 s1 conv (forward: transpose_flip=False; dgrad: True).
     stat: None | ("stats", G, eps) -> returns (out, stats[N][G][2]) of the stored result (GroupNorm forward)
                | ("red", G, x_gn, stats) -> returns (out, red[N][C][2]) (GroupNorm backward reductions, out = dL/dxn)."""
@@ -310,6 +322,11 @@ def conv_k3s1(packs, x, w, out, transpose_flip, bias=None, relu=False, res=None,
     d.relu, d.accumulate = int(relu), int(accumulate)
     d.debug = None
     d.stat_mode, d.stat_ws = 0, None
+    d.use_tap_mask = 0
+    if tap_mask is not None:  # list of per-K-group in-plane tap masks (structurally sparse weights)
+        d.use_tap_mask, d.tap_mask_groups = 1, len(tap_mask)
+        for i, m in enumerate(tap_mask):
+            d.tap_mask[i] = m
     if stat is not None:
         L = lib.load()
         sws = workspace(L.rtp_conv_k3s1_stat_ws_bytes(x.N), x.buf.device, "k3stat")
@@ -347,12 +364,13 @@ def stat_fusable(x, w, transpose_flip):
 
 
 def conv_forward(packs, x, w, stride, out, bias=None, relu=False, res=None, ci0=0, ci_n=None, key=None, version=None,
-                 stat=None):
+                 stat=None, tap_mask=None):
     """y = conv3d(x[:, ci0:ci0+ci_n], w[:, ci0:ci0+ci_n], stride, padding=k//2) (+bias)(+res)(relu).
     stat (only when stat_fusable(x, w, False) and stride 1): see conv_k3s1; the return value becomes (y, stats)."""
     k = w.shape[2]
     if k == 3 and stride == 1 and ci0 == 0 and ci_n is None and k3s1_eligible(x, ceil_to(w.shape[1], 16), ceil_to(w.shape[0], 16)):
-        return conv_k3s1(packs, x, w, out, False, bias=bias, relu=relu, res=res, key=key, version=version, stat=stat)
+        return conv_k3s1(packs, x, w, out, False, bias=bias, relu=relu, res=res, key=key, version=version, stat=stat,
+                         tap_mask=tap_mask)
     assert stat is None, "fused statistics need the plane-streaming kernel (check stat_fusable first)"
     if k == 1 and stride == 1 and res is None and USE_PW:
         wp, KP, NP = packs.get(w, 0, ci0, ci_n, key, version)
@@ -364,7 +382,8 @@ def conv_forward(packs, x, w, stride, out, bias=None, relu=False, res=None, ci0=
                 relu=relu, real=(ci_n if ci_n is not None else w.shape[1], w.shape[0]))
 
 
-def conv_dgrad(packs, dy, w, stride, dx, mask=None, accumulate=False, ci0=0, ci_n=None, key=None, version=None, stat=None):
+def conv_dgrad(packs, dy, w, stride, dx, mask=None, accumulate=False, ci0=0, ci_n=None, key=None, version=None, stat=None,
+               s2d_cin=None):
     """dx (=|+=) conv_transpose(dy, w) [* (mask > 0)]; dx has the forward input's geometry.
     stat (only when stat_fusable(dy, w, True) and stride 1): see conv_k3s1; the return value becomes (dx, red)."""
     k = w.shape[2]
@@ -378,7 +397,8 @@ def conv_dgrad(packs, dy, w, stride, dx, mask=None, accumulate=False, ci0=0, ci_
             conv_k3s1(packs, dy, w[:, g * 32:(g + 1) * 32], dx.channels(g * 32, 32), True,
                       mask=mask.channels(g * 32, 32) if mask is not None else None, accumulate=accumulate,
                       key=(key if key is not None else w.data_ptr(), "dgrad_group", g),
-                      version=version if version is not None else w._version)
+                      version=version if version is not None else w._version,
+                      tap_mask=[s2d_tap_mask((g * 32) // s2d_cin, True)] if s2d_cin else None)
         return dx
     wp, KP, NP = packs.get(w, 1, ci0, ci_n, key, version)
     real = (w.shape[0], ci_n if ci_n is not None else w.shape[1])
@@ -445,6 +465,8 @@ def _wgrad_k3s1(x, dy, outs):
                 h += hn
 
 
+import os as _os
+_SKIP_WGRAD = bool(_os.environ.get("RTP_SKIP_WGRAD"))
 ASYNC_WGRAD = True  # weight gradients run on a side stream (nothing in backward depends on them); see join_wgrad()
 _side = {}
 
@@ -466,18 +488,27 @@ def join_wgrad(device=None):
             st["busy"] = False
 
 
-def conv_wgrad_async(x, dy, k, stride, dW, accumulate=False, ci0=0, n0=0, more=()):
+def conv_wgrad_async(x, dy, k, stride, dW, accumulate=False, ci0=0, n0=0, more=(), then=None):
     """conv_wgrad queued on a side stream, ordered after everything issued so far on the current stream.  The caller
     keeps x, dy and dW alive and untouched until join_wgrad() (the engine's buffers live until the end of the step).
-    Falls back to the in-stream call when ASYNC_WGRAD is off."""
+    `then()` is called right after, on the same stream (post-processing of dW).  Falls back to the in-stream call when
+    ASYNC_WGRAD is off."""
     dev = x.buf.device
+    if _SKIP_WGRAD:  # timing experiments only (RTP_SKIP_WGRAD=1): how much of the step the weight gradients cost net
+        return None
     if not ASYNC_WGRAD:
-        return conv_wgrad(x, dy, k, stride, dW, accumulate, ci0, n0, more)
+        conv_wgrad(x, dy, k, stride, dW, accumulate, ci0, n0, more)
+        if then is not None:
+            then()
+        return None
     st = _side_stream(dev)
     st["stream"].wait_stream(torch.cuda.current_stream(dev))
     st["busy"] = True
     with torch.cuda.stream(st["stream"]):
-        return conv_wgrad(x, dy, k, stride, dW, accumulate, ci0, n0, more)
+        conv_wgrad(x, dy, k, stride, dW, accumulate, ci0, n0, more)
+        if then is not None:
+            then()
+    return None
 
 
 def conv_wgrad(x, dy, k, stride, dW, accumulate=False, ci0=0, n0=0, more=()):
@@ -537,13 +568,110 @@ def gn_apply(x, G, stats, gamma, beta, out):
     return out
 
 
-def gn_backward(x, dxn, G, stats, gamma, dgamma, dbeta, acc_params, dx, acc_dx, red=None):
-    """red: the [N][C][2] reductions when the conv that produced dxn already computed them (conv_dgrad(stat=...))."""
+S2D_MIN_VOXELS = 1 << 20
+USE_S2D = not bool(_os.environ.get("RTP_NO_S2D"))  # stride-2 3x3x3 convs as stride-1 convs over the space-to-depth view (plane-streaming kernels)
+
+
+def s2d_eligible(x, w):
+    """True when conv3d(GN(x), w, stride 2, pad 1) can run through the space-to-depth view: even grid, Cin a multiple of
+    8, and the stride-1 problems (forward K = 8*Cin, dgrad in 32-channel groups, wgrad) fit the plane-streaming kernels."""
+    Cout, Cin = w.shape[0], w.shape[1]
+    if not (USE_S2D and USE_K3S1 and USE_WGRAD_K3S1 and w.shape[2] == 3 and x.C == Cin and Cin % 8 == 0):
+        return False
+    if x.Z % 2 or x.Y % 2 or x.X % 2 or x.c_stride != x.Z * (x.X + 2) * (x.Y + 2) * 8:
+        return False
+    if x.N * x.voxels < S2D_MIN_VOXELS:  # small problems are launch-bound: 1 + 8 + 8 stride-1 launches do not pay
+        return False
+    L = lib.load()
+    Z, X, Y = x.Z // 2, x.X // 2, x.Y // 2
+    NPo = ceil_to(Cout, 16)
+    return (L.rtp_conv_k3s1_smem_bytes(8 * Cin, NPo, Z, X, Y) > 0 and (8 * Cin) % 32 == 0
+            and L.rtp_conv_k3s1_smem_bytes(NPo, 32, Z, X, Y) > 0 and L.rtp_wgrad_k3s1_supported(32, 32, Z, X, Y) > 0)
+
+
+def conv_wgrad_s2d(xs, dy, Cin, dW, accumulate=False):
+    """Weight gradient of a stride-2 3x3x3 conv whose (normalised) input is held as the space-to-depth view xs: the 27
+    taps of the reference weight are 27 (parity group, offset -1/0) pairs of the view, gathered with unit stride by the
+    generic wgrad kernel (per-tap chunk base rtp_wgrad_desc.tc) and written straight into dW[Cout][Cin][3][3][3]."""
+    def dim(k):  # tap k of one dimension -> (parity, offset)
+        return (1, -1) if k == 0 else ((0, 0) if k == 1 else (1, 0))
+    Cin8 = ceil_to(Cin, 8)
+    NP = ceil_to(dy.C, 16)
+    d = lib.WgradDesc()
+    d.x, d.dy = xs.struct(), dy.struct()
+    d.Cin, d.NP = Cin8, NP
+    i = 0
+    for kz in range(3):
+        for ky in range(3):
+            for kx in range(3):
+                (pz, oz), (py, oy), (px, ox) = dim(kz), dim(ky), dim(kx)
+                d.tz[i], d.tx[i], d.ty[i] = oz, ox, oy
+                d.tc[i] = ((pz << 2) | (px << 1) | py) * (Cin8 // 8)
+                i += 1
+    d.ntaps = 27
+    d.RZ, d.RX, d.RY = dy.Z, dy.X, dy.Y
+    d.IS = 1
+    rows = dy.N * dy.voxels
+    ntiles = (rows + 63) // 64
+    nblocks = (27 * (Cin8 // 8) + 15) // 16
+    per_cta = max(1, 512 // NP)
+    groups = (nblocks + per_cta - 1) // per_cta
+    nsplit = max(1, min(ntiles, (2 * num_sms()) // groups))
+    d.nsplit = nsplit
+    ws = workspace(lib.load().rtp_wgrad_workspace_bytes(Cin8, NP, 27, nsplit), xs.buf.device, "wgrad")
+    d.workspace = ws.data_ptr()
+    key = ("wgrad_generic", Cin, dy.C, 27, 2, 1, (dy.Z, dy.X, dy.Y))
+    ev = _prof_begin(key)
+    lib.call("rtp_wgrad", C.byref(d), _stream())
+    _prof_end(key, ev, 2.0 * rows * Cin * dy.C * 27)
+    assert dW.is_contiguous()
+    lib.call("rtp_wgrad_reduce", ws.data_ptr(), nsplit, Cin8, NP, 27, dW.data_ptr(), dW.shape[1], dW.shape[0], 0, 0, Cin,
+             int(accumulate), _stream())
+
+
+def on_wgrad_stream(x, fn):
+    """Runs fn() on the weight-gradient side stream (ordered after the current stream), or in place when ASYNC_WGRAD is off."""
+    dev = x.buf.device
+    if _SKIP_WGRAD:
+        return
+    if not ASYNC_WGRAD:
+        return fn()
+    st = _side_stream(dev)
+    st["stream"].wait_stream(torch.cuda.current_stream(dev))
+    st["busy"] = True
+    with torch.cuda.stream(st["stream"]):
+        fn()
+
+
+def gn_apply_s2d(x, G, stats, gamma, beta, out):
+    """GroupNorm apply that writes the result as the space-to-depth view `out` (grid halved, 8x the channels)."""
+    lib.call("rtp_gn_apply_s2d", x.struct(), x.C, G, stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), out.struct(),
+             _stream())
+    return out
+
+
+def s2d_expand(w, out=None):
+    """[Cout][Cin][3][3][3] -> the weights [Cout][8*Cin][3][3][3] of the equivalent stride-1 conv over the s2d view."""
+    Cout, Cin = w.shape[0], w.shape[1]
+    if out is None:
+        out = torch.empty((Cout, 8 * Cin, 3, 3, 3), dtype=torch.float32, device=w.device)
+    lib.call("rtp_weight_s2d_expand", w.detach().contiguous().data_ptr(), out.data_ptr(), Cout, Cin, _stream())
+    return out
+
+
+def s2d_fold(dw_s2d, dw, accumulate):
+    lib.call("rtp_weight_s2d_fold", dw_s2d.data_ptr(), dw.data_ptr(), dw.shape[0], dw.shape[1], int(accumulate), _stream())
+
+
+def gn_backward(x, dxn, G, stats, gamma, dgamma, dbeta, acc_params, dx, acc_dx, red=None, s2d=False):
+    """red: the [N][C][2] reductions when the conv that produced dxn already computed them (conv_dgrad(stat=...)).
+    s2d: dxn is the gradient of the space-to-depth view of GN(x)."""
+    sfx = "_s2d" if s2d else ""
     if red is None:
         red = torch.empty((x.N, x.C, 2), dtype=torch.float32, device=x.buf.device)
-        lib.call("rtp_gn_bwd_reduce", x.struct(), dxn.struct(), x.C, G, stats.data_ptr(), red.data_ptr(),
+        lib.call("rtp_gn_bwd_reduce" + sfx, x.struct(), dxn.struct(), x.C, G, stats.data_ptr(), red.data_ptr(),
                  gn_ws(x).data_ptr(), _stream())
-    lib.call("rtp_gn_bwd_apply", x.struct(), dxn.struct(), x.C, G, stats.data_ptr(), red.data_ptr(), gamma.data_ptr(),
+    lib.call("rtp_gn_bwd_apply" + sfx, x.struct(), dxn.struct(), x.C, G, stats.data_ptr(), red.data_ptr(), gamma.data_ptr(),
              dgamma.data_ptr(), dbeta.data_ptr(), int(acc_params), dx.struct() if dx is not None else lib.NULL_P8,
              int(acc_dx), int(x.relu_out), _stream())
 

@@ -501,3 +501,66 @@ def test_conv_k3s1_fused_groupnorm_statistics(ctx, case):
         assert torch.equal(d0.to_ncdhw(), d1.to_ncdhw())
         scale = red_ref.abs().max().item()
         assert (red - red_ref).abs().max().item() <= 2e-5 * scale + 1e-4
+
+
+S2D_CASES = [
+    # N, Cin, Cout, grid(Z,Y,X) (even)
+    (2, 32, 32, (8, 20, 24)),
+    (1, 32, 64, (4, 12, 16)),
+    (2, 32, 32, (2, 64, 10)),
+]
+
+
+@pytest.mark.parametrize("case", S2D_CASES, ids=[str(c) for c in S2D_CASES])
+def test_stride2_conv_through_space_to_depth_view(ctx, case):
+    """GroupNorm -> stride-2 3x3x3 conv, forward / dgrad / wgrad / GroupNorm backward, computed through the s2d view with
+    the stride-1 plane-streaming kernels, against torch (F.group_norm + F.conv3d stride 2) on the same bf16 inputs."""
+    from rtpose_b200 import ops
+    from rtpose_b200.p8 import P8
+    N, Cin, Cout, grid = case
+    x = rnd(N, Cin, *grid, seed=80).requires_grad_(True)
+    w = rnd(Cout, Cin, 3, 3, 3, seed=81, scale=0.1).requires_grad_(True)
+    gamma = (1.0 + 0.1 * rnd(Cin, seed=82)).requires_grad_(True)
+    beta = (0.1 * rnd(Cin, seed=83)).requires_grad_(True)
+    xn_ref = F.group_norm(x, 8, gamma, beta, eps=1e-5)
+    xn_ref.retain_grad()
+    y_ref = F.conv3d(bf(xn_ref.detach()).requires_grad_(False) + (xn_ref - xn_ref.detach()), w, stride=2, padding=1)
+    og = tuple((g - 1) // 2 + 1 for g in grid)
+    dy = rnd(N, Cout, *og, seed=84)
+    y_ref.backward(dy)
+
+    xp = to_p8(x.detach())
+    wc, gc, bc = w.detach().cuda(), gamma.detach().cuda(), beta.detach().cuda()
+    stats = ops.gn_stats(xp, 8)
+    xs = ops.gn_apply_s2d(xp, 8, stats, gc, bc, P8(N, 8 * Cin, grid[0] // 2, grid[1] // 2, grid[2] // 2))
+    we = ops.s2d_expand(wc)
+    ops.S2D_MIN_VOXELS = 0
+    assert ops.s2d_eligible(xp, wc)
+    y = ops.conv_forward(ctx, xs, we, 1, P8(N, Cout, *og), key=("t", case), version=0)
+    ym = ops.conv_forward(ctx, xs, we, 1, P8(N, Cout, *og), key=("t", case), version=0,
+                          tap_mask=[ops.s2d_tap_mask(par, False) for par in range(8)])
+    torch.cuda.synchronize()
+    close(y.to_ncdhw(), y_ref, what="s2d forward")
+    close(ym.to_ncdhw(), y_ref, what="s2d forward, all-zero taps skipped")
+    # backward
+    dyp = to_p8(dy)
+    gwe = torch.zeros_like(we)
+    ops.conv_wgrad(xs, dyp, 3, 1, gwe)
+    gw = torch.full(wc.shape, 7.0, device="cuda")
+    ops.s2d_fold(gwe, gw, False)
+    torch.cuda.synchronize()
+    close(gw, w.grad, tol=3e-3, what="s2d wgrad")
+    gw2 = torch.full(wc.shape, 7.0, device="cuda")
+    ops.conv_wgrad_s2d(xs, dyp, Cin, gw2)            # generic kernel over the view, 27 (parity, offset) taps
+    ops.conv_wgrad_s2d(xs, dyp, Cin, gw2, accumulate=True)
+    torch.cuda.synchronize()
+    close(gw2, 2 * w.grad, tol=3e-3, what="s2d wgrad (gather kernel over the view)")
+    dxs = ops.conv_dgrad(ctx, dyp, we, 1, P8(N, 8 * Cin, grid[0] // 2, grid[1] // 2, grid[2] // 2), key=("t", case), version=0,
+                         s2d_cin=Cin)
+    dg, db = torch.zeros(Cin, device="cuda"), torch.zeros(Cin, device="cuda")
+    dx = P8(N, Cin, *grid)
+    ops.gn_backward(xp, dxs, 8, stats, gc, dg, db, False, dx, False, s2d=True)
+    torch.cuda.synchronize()
+    close(dx.to_ncdhw(), x.grad, tol=2e-2, what="s2d dx")
+    close(dg, gamma.grad, tol=2e-2, what="s2d dgamma")
+    close(db, beta.grad, tol=2e-2, what="s2d dbeta")
