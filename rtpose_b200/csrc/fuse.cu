@@ -50,13 +50,6 @@ __global__ void __launch_bounds__(256) fuse_sum_rows_kernel(const __grid_constan
     sx[j] = ac_scale(p.low[j].X, o.X);
     sy[j] = ac_scale(p.low[j].Y, o.Y);
   }
-  // the y interpolation of a lane's (up to two) outputs is the same for every row: hoisted when the row fits 64 lanes
-  const bool hoist = o.Y <= 64;
-  Axis ayh[3][2];
-#pragma unroll
-  for (int j = 0; j < 3; ++j)
-#pragma unroll
-    for (int k = 0; k < 2; ++k) ayh[j][k] = ac_axis(min(lane + 32 * k, o.Y - 1), j < p.n_low ? p.low[j].Y : 1, j < p.n_low ? sy[j] : 0.f);
   for (int row = r0 + warp; row < r1; row += 8) {
     const int z = row / o.X, x = row - z * o.X;
     for (int j = 0; j < p.n_low; ++j) {
@@ -86,17 +79,10 @@ __global__ void __launch_bounds__(256) fuse_sum_rows_kernel(const __grid_constan
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[i] += f[i];
       }
+      for (int j = 0; j < p.n_low; ++j) {
+        const Axis ay = ac_axis(y, p.low[j].Y, sy[j]);
 #pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        if (j >= p.n_low) break;
-        const Axis ay = hoist ? (y < 32 ? ayh[j][0] : ayh[j][1]) : ac_axis(y, p.low[j].Y, sy[j]);
-        const float4* s0 = reinterpret_cast<const float4*>(srow[warp][j][ay.i0]);
-        const float4* s1 = reinterpret_cast<const float4*>(srow[warp][j][ay.i1]);
-        const float4 a0 = s0[0], a1 = s0[1], b0 = s1[0], b1 = s1[1];
-        acc[0] += ay.w0 * a0.x + ay.w1 * b0.x; acc[1] += ay.w0 * a0.y + ay.w1 * b0.y;
-        acc[2] += ay.w0 * a0.z + ay.w1 * b0.z; acc[3] += ay.w0 * a0.w + ay.w1 * b0.w;
-        acc[4] += ay.w0 * a1.x + ay.w1 * b1.x; acc[5] += ay.w0 * a1.y + ay.w1 * b1.y;
-        acc[6] += ay.w0 * a1.z + ay.w1 * b1.z; acc[7] += ay.w0 * a1.w + ay.w1 * b1.w;
+        for (int i = 0; i < 8; ++i) acc[i] += ay.w0 * srow[warp][j][ay.i0][i] + ay.w1 * srow[warp][j][ay.i1][i];
       }
 #pragma unroll
       for (int i = 0; i < 8; ++i) {

@@ -392,13 +392,24 @@ def conv_dgrad(packs, dy, w, stride, dx, mask=None, accumulate=False, ci0=0, ci_
     assert stat is None, "fused statistics need the plane-streaming kernel (check stat_fusable first)"
     if (k == 3 and stride == 1 and ci0 == 0 and ci_n is None and w.shape[1] > 80 and w.shape[1] % 32 == 0
             and k3s1_eligible(dy, ceil_to(w.shape[0], 16), 32)):
-        # wide dX (e.g. the 128-channel head input): one plane-streaming launch per 32-channel group of dX
-        for g in range(w.shape[1] // 32):
-            conv_k3s1(packs, dy, w[:, g * 32:(g + 1) * 32], dx.channels(g * 32, 32), True,
-                      mask=mask.channels(g * 32, 32) if mask is not None else None, accumulate=accumulate,
-                      key=(key if key is not None else w.data_ptr(), "dgrad_group", g),
-                      version=version if version is not None else w._version,
-                      tap_mask=[s2d_tap_mask((g * 32) // s2d_cin, True)] if s2d_cin else None)
+        # wide dX (e.g. the 128-channel head input, or a space-to-depth view): one plane-streaming launch per group of dX
+        # channels.  View groups are paired (64 channels = two parity groups that differ in y: the odd one's taps cover
+        # the even one's) when the shape allows, to halve the number of launches.
+        gs = 32
+        if s2d_cin and w.shape[1] % 64 == 0 and (64 % s2d_cin == 0 or s2d_cin % 64 == 0) and S2D_DGRAD_PAIR \
+                and k3s1_eligible(dy, ceil_to(w.shape[0], 16), 64):
+            gs = 64
+        for g in range(w.shape[1] // gs):
+            tm = None
+            if s2d_cin:
+                tm = 0
+                for par in set((c // s2d_cin) for c in range(g * gs, (g + 1) * gs, 8)):
+                    tm |= s2d_tap_mask(par, True)
+                tm = [tm]
+            conv_k3s1(packs, dy, w[:, g * gs:(g + 1) * gs], dx.channels(g * gs, gs), True,
+                      mask=mask.channels(g * gs, gs) if mask is not None else None, accumulate=accumulate,
+                      key=(key if key is not None else w.data_ptr(), "dgrad_group", gs, g),
+                      version=version if version is not None else w._version, tap_mask=tm)
         return dx
     wp, KP, NP = packs.get(w, 1, ci0, ci_n, key, version)
     real = (w.shape[0], ci_n if ci_n is not None else w.shape[1])
@@ -569,6 +580,7 @@ def gn_apply(x, G, stats, gamma, beta, out):
 
 
 S2D_MIN_VOXELS = 1 << 20
+S2D_DGRAD_PAIR = not bool(_os.environ.get("RTP_NO_PAIR"))
 USE_S2D = not bool(_os.environ.get("RTP_NO_S2D"))  # stride-2 3x3x3 convs as stride-1 convs over the space-to-depth view (plane-streaming kernels)
 
 
