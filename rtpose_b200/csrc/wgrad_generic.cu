@@ -8,6 +8,7 @@
 // accumulators [128 x NP] all stay resident in TMEM for the whole range; the partial result goes to a
 // workspace and rtp_wgrad_reduce sums the splits in a fixed order (deterministic) into the reference's
 // [Cout][Cin][taps] fp32 layout.
+#include <climits>
 #include "common.cuh"
 #include "tc05.cuh"
 
@@ -38,6 +39,11 @@ __global__ void __launch_bounds__(kThreads) wgrad_generic_kernel(const __grid_co
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t bar_full[kStages], bar_empty[kStages], bar_acc;
   __shared__ uint32_t tmem_base_s;
+  // per (tap, chunk) pair: element offset from the row's voxel (or INT_MIN when the chunk does not exist) and the z tap.
+  // Computed once: the gather loop below then costs one shared load + one add per 16-byte cp.async instead of ~30
+  // integer instructions (the kernel runs at 2 CTAs / SM, so it was bound by exactly that dependent ALU chain).
+  __shared__ int s_off[RTP_MAX_TAPS * 32];
+  __shared__ int8_t s_tz[RTP_MAX_TAPS * 32];
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const uint32_t a_bytes = 16 * kTileK * 16;            // [16 pairs][64 rows][16 B]
@@ -51,6 +57,13 @@ __global__ void __launch_bounds__(kThreads) wgrad_generic_kernel(const __grid_co
   const int nitems = max(0, tile1 - tile0) * nblk;
   const int kch = p.Cin >> 3;
 
+  for (int pair = tid; pair < p.npairs && pair < RTP_MAX_TAPS * 32; pair += kThreads) {
+    const int tap = pair / kch, c = pair - tap * kch;
+    const int cc = p.tc[tap] + c;
+    const int64_t off = (((int64_t)p.tz[tap] * p.x.Xp + p.tx[tap]) * p.x.Yp + p.ty[tap]) * 8 + (int64_t)cc * p.x.c_stride;
+    s_off[pair] = cc < p.x.C8 ? (int)off : INT_MIN;
+    s_tz[pair] = p.tz[tap];
+  }
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&bar_full[s], 128);
@@ -109,12 +122,9 @@ __global__ void __launch_bounds__(kThreads) wgrad_generic_kernel(const __grid_co
         bool ok = row_ok && pair < p.npairs;
         const bf16* src = p.x.ptr;
         if (ok) {
-          const int tap = pair / kch, c = pair - tap * kch;
-          const int tz = p.tz[tap];
-          const int iz = rz * p.IS + tz;
-          const int cc = p.tc[tap] + c;
-          ok = iz >= 0 && iz < p.x.Z && cc < p.x.C8;
-          src = x_row + (((int64_t)tz * p.x.Xp + p.tx[tap]) * p.x.Yp + p.ty[tap]) * 8 + (int64_t)cc * p.x.c_stride;
+          const int off = s_off[pair];
+          ok = off != INT_MIN && (unsigned)(rz * p.IS + s_tz[pair]) < (unsigned)p.x.Z;
+          src = x_row + off;
         }
         cp_async16(sA + ((size_t)mc * kTileK + pos) * 16, ok ? (const void*)src : (const void*)p.x.ptr, ok);
       }
@@ -245,7 +255,7 @@ extern "C" int64_t rtp_wgrad_workspace_bytes(int32_t Cin, int32_t NP, int32_t nt
 
 extern "C" int rtp_wgrad(const rtp_wgrad_desc* d, void* stream) {
   RTP_CHECK_ARG(d != nullptr && d->x.ptr && d->dy.ptr && d->workspace, "rtp_wgrad: null argument");
-  RTP_CHECK_ARG(d->Cin >= 8 && d->Cin % 8 == 0, "rtp_wgrad: Cin=%d must be a multiple of 8", d->Cin);
+  RTP_CHECK_ARG(d->Cin >= 8 && d->Cin % 8 == 0 && d->Cin <= 256, "rtp_wgrad: Cin=%d must be a multiple of 8, <= 256", d->Cin);
   RTP_CHECK_ARG(d->NP >= 16 && d->NP % 16 == 0 && d->NP <= 256, "rtp_wgrad: NP=%d must be a multiple of 16 <= 256", d->NP);
   RTP_CHECK_ARG(d->ntaps >= 1 && d->ntaps <= RTP_MAX_TAPS && d->nsplit >= 1, "rtp_wgrad: bad ntaps/nsplit");
   RTP_CHECK_ARG(d->IS == 1 || d->IS == 2, "rtp_wgrad: IS must be 1 or 2");

@@ -579,7 +579,7 @@ def gn_apply(x, G, stats, gamma, beta, out):
     return out
 
 
-S2D_MIN_VOXELS = 1 << 20
+S2D_MIN_VOXELS = int(_os.environ.get("RTP_S2D_MIN_VOXELS", 1 << 20))
 S2D_DGRAD_PAIR = not bool(_os.environ.get("RTP_NO_PAIR"))
 USE_S2D = not bool(_os.environ.get("RTP_NO_S2D"))  # stride-2 3x3x3 convs as stride-1 convs over the space-to-depth view (plane-streaming kernels)
 
