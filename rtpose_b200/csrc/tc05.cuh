@@ -147,6 +147,10 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, boo
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(n)
                : "memory");
 }
+__device__ __forceinline__ void cp_async16_s32(uint32_t smem_dst, const void* gsrc, bool valid) {  // dst as a shared-window address
+  const uint32_t n = valid ? 16u : 0u;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gsrc), "r"(n) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {

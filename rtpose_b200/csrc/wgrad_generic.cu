@@ -17,7 +17,8 @@ using namespace tc05;
 namespace {
 
 constexpr int kStages = 4;
-constexpr int kThreads = 160;
+constexpr int kProducers = 256;           // 8 gather warps: thread = (row of the tile, quarter of the pair slots)
+constexpr int kThreads = kProducers + 32;  // + the MMA warp
 constexpr int kTileK = 64;  // rows per pipeline item
 
 struct WgradK {
@@ -42,8 +43,7 @@ __global__ void __launch_bounds__(kThreads) wgrad_generic_kernel(const __grid_co
   // per (tap, chunk) pair: element offset from the row's voxel (or INT_MIN when the chunk does not exist) and the z tap.
   // Computed once: the gather loop below then costs one shared load + one add per 16-byte cp.async instead of ~30
   // integer instructions (the kernel runs at 2 CTAs / SM, so it was bound by exactly that dependent ALU chain).
-  __shared__ int s_off[RTP_MAX_TAPS * 32];
-  __shared__ int8_t s_tz[RTP_MAX_TAPS * 32];
+  __shared__ int2 s_tab[RTP_MAX_TAPS * 32 + 16];  // {offset, z tap}; padded with INT_MIN up to a whole m-block
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const uint32_t a_bytes = 16 * kTileK * 16;            // [16 pairs][64 rows][16 B]
@@ -57,22 +57,25 @@ __global__ void __launch_bounds__(kThreads) wgrad_generic_kernel(const __grid_co
   const int nitems = max(0, tile1 - tile0) * nblk;
   const int kch = p.Cin >> 3;
 
-  for (int pair = tid; pair < p.npairs && pair < RTP_MAX_TAPS * 32; pair += kThreads) {
-    const int tap = pair / kch, c = pair - tap * kch;
-    const int cc = p.tc[tap] + c;
-    const int64_t off = (((int64_t)p.tz[tap] * p.x.Xp + p.tx[tap]) * p.x.Yp + p.ty[tap]) * 8 + (int64_t)cc * p.x.c_stride;
-    s_off[pair] = cc < p.x.C8 ? (int)off : INT_MIN;
-    s_tz[pair] = p.tz[tap];
+  for (int pair = tid; pair < p.nblocks * 16 && pair < RTP_MAX_TAPS * 32 + 16; pair += kThreads) {
+    int2 e = make_int2(INT_MIN, 0);
+    if (pair < p.npairs) {
+      const int tap = pair / kch, c = pair - tap * kch;
+      const int cc = p.tc[tap] + c;
+      const int64_t off = (((int64_t)p.tz[tap] * p.x.Xp + p.tx[tap]) * p.x.Yp + p.ty[tap]) * 8 + (int64_t)cc * p.x.c_stride;
+      e = make_int2(cc < p.x.C8 ? (int)off : INT_MIN, p.tz[tap]);
+    }
+    s_tab[pair] = e;
   }
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(&bar_full[s], 128);
+      mbar_init(&bar_full[s], kProducers);
       mbar_init(&bar_empty[s], 1);
     }
     mbar_init(&bar_acc, 1);
     mbar_fence_init();
   }
-  if (warp == 4) {
+  if (warp == kProducers / 32) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
                  "r"(p.tmem_cols)
                  : "memory");
@@ -83,74 +86,66 @@ __global__ void __launch_bounds__(kThreads) wgrad_generic_kernel(const __grid_co
   fence_after_sync();
   const uint32_t tmem = tmem_base_s;
 
-  if (warp < 4) {
+  if (warp < kProducers / 32) {
     const int r = tid;
     const int pos = r & (kTileK - 1);  // this thread always serves the same row of the tile
-    const int half = r >> 6;           // and the pair slots half, half+2, ...
+    const int half = r >> 6;           // and the pair slots half, half+4, half+8, half+12 ("half" = quarter 0..3)
 
-    int cur_tile = -1;
-    bool row_ok = false;
-    int rz = 0;
-    const bf16 *x_row = p.x.ptr, *dy_row = p.dy.ptr;
-
-    auto issue = [&](int item) {
-      const int st = item % kStages;
-      uint8_t* sA = smem + (size_t)st * stage_bytes;
-      uint8_t* sB = sA + a_bytes;
-      const int tile = tile0 + item / nblk;
-      const int blk = blk0 + item % nblk;
-      if (tile != cur_tile) {
-        cur_tile = tile;
-        const int64_t L = (int64_t)tile * kTileK + pos;
-        row_ok = L < p.total_rows;
-        int n = 0, rx = 0, ry = 0;
-        rz = 0;
-        if (row_ok) {
-          int64_t q = L;
-          ry = (int)(q % p.RY); q /= p.RY;
-          rx = (int)(q % p.RX); q /= p.RX;
-          rz = (int)(q % p.RZ);
-          n = (int)(q / p.RZ);
-        }
-        x_row = p.x.ptr + (int64_t)n * p.x.n_stride + p.x.voxel(rz * p.IS, rx * p.IS, ry * p.IS);
-        dy_row = p.dy.ptr + (int64_t)n * p.dy.n_stride + p.dy.voxel(rz, rx, ry);
-      }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int mc = i * 2 + half;
-        const int pair = blk * 16 + mc;
-        bool ok = row_ok && pair < p.npairs;
-        const bf16* src = p.x.ptr;
-        if (ok) {
-          const int off = s_off[pair];
-          ok = off != INT_MIN && (unsigned)(rz * p.IS + s_tz[pair]) < (unsigned)p.x.Z;
-          src = x_row + off;
-        }
-        cp_async16(sA + ((size_t)mc * kTileK + pos) * 16, ok ? (const void*)src : (const void*)p.x.ptr, ok);
-      }
-      for (int c = half; c < p.NP / 8; c += 2) {
-        const bool ok = row_ok && c < p.dy.C8;
-        cp_async16(sB + ((size_t)c * kTileK + pos) * 16, ok ? (const void*)(dy_row + (int64_t)c * p.dy.c_stride) : (const void*)p.dy.ptr, ok);
-      }
-      cp_async_commit();
-    };
+    const uint32_t smem32 = smem_u32(smem) + (uint32_t)((half * kTileK + pos) * 16);  // this thread's slot in pair `half`
+    const int lane = tid & 31;
     auto publish = [&](int item) {
       fence_proxy_async();
-      mbar_arrive(&bar_full[item % kStages]);
+      mbar_arrive(&bar_full[item & (kStages - 1)]);
     };
-
-    for (int item = 0; item < nitems; ++item) {
-      if (item >= kStages) mbar_wait(&bar_empty[item % kStages], ((item / kStages) - 1) & 1);
-      issue(item);
-      if (item >= kStages - 1) {
-        cp_async_wait<kStages - 1>();
-        publish(item - (kStages - 1));
+    static_assert((kStages & (kStages - 1)) == 0, "kStages must be a power of two");
+    // Nested (tile, m-block) loops: the row decode (32-bit, once per tile) and the item -> (tile, block) mapping cost no
+    // divisions per item — with 2 CTAs x 4 producer warps per SM this loop's dependent integer chain IS the kernel's
+    // critical path (ncu: 55 % of the stall samples inside it, MMA warp idle).
+    int item = 0;
+    for (int tile = tile0; tile < tile1; ++tile) {
+      const int64_t L = (int64_t)tile * kTileK + pos;
+      const bool row_ok = L < p.total_rows;
+      int n = 0, rx = 0, ry = 0, rz = 0;
+      if (row_ok) {
+        uint32_t q = (uint32_t)L;  // total_rows < 2^31 (checked on the host)
+        ry = (int)(q % (uint32_t)p.RY); q /= (uint32_t)p.RY;
+        rx = (int)(q % (uint32_t)p.RX); q /= (uint32_t)p.RX;
+        rz = (int)(q % (uint32_t)p.RZ);
+        n = (int)(q / (uint32_t)p.RZ);
+      }
+      const bf16* x_row = p.x.ptr + (int64_t)n * p.x.n_stride + p.x.voxel(rz * p.IS, rx * p.IS, ry * p.IS);
+      const bf16* dy_row = p.dy.ptr + (int64_t)n * p.dy.n_stride + p.dy.voxel(rz, rx, ry);
+      const int izb = rz * p.IS;
+      for (int b = 0; b < nblk; ++b, ++item) {
+        const int st = item & (kStages - 1);
+        if (item >= kStages) {  // one lane per warp polls; the others park on the warp barrier
+          if (lane == 0) mbar_wait(&bar_empty[st], ((item / kStages) - 1) & 1);
+          __syncwarp();
+        }
+        const uint32_t sA = smem32 + (uint32_t)st * stage_bytes, sB = sA + a_bytes;
+        const int2* tab = s_tab + (blk0 + b) * 16 + half;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {  // pair slots half, half+4, ...: 4 KB apart in the stage
+          const int2 e = tab[4 * i];
+          const bool ok = row_ok && e.x != INT_MIN && (unsigned)(izb + e.y) < (unsigned)p.x.Z;
+          cp_async16_s32(sA + i * (4 * kTileK * 16), ok ? (const void*)(x_row + e.x) : (const void*)p.x.ptr, ok);
+        }
+        for (int c = half; c < p.NP / 8; c += 4) {
+          const bool ok = row_ok && c < p.dy.C8;
+          cp_async16_s32(sB + (c - half) * (kTileK * 16), ok ? (const void*)(dy_row + (int64_t)c * p.dy.c_stride) : (const void*)p.dy.ptr, ok);
+        }
+        cp_async_commit();
+        if (item >= kStages - 1) {
+          cp_async_wait<kStages - 1>();
+          publish(item - (kStages - 1));
+        }
       }
     }
     cp_async_wait<0>();
-    for (int item = (nitems >= kStages - 1 ? nitems - (kStages - 1) : 0); item < nitems; ++item) publish(item);
+    for (int it2 = (nitems >= kStages - 1 ? nitems - (kStages - 1) : 0); it2 < nitems; ++it2) publish(it2);
 
-    // ------------------------------------------------------------------ epilogue: TMEM -> fp32 partials
+    // ------------------------------------------------------------------ epilogue: TMEM -> fp32 partials (warps 0-3)
+    if (warp < 4) {
     if (nitems > 0) {
       mbar_wait(&bar_acc, 0);
       fence_after_sync();
@@ -173,7 +168,8 @@ __global__ void __launch_bounds__(kThreads) wgrad_generic_kernel(const __grid_co
               make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
       }
     }
-  } else if (tid == 128) {
+    }
+  } else if (tid == kProducers) {
     const uint32_t idesc = idesc_bf16(128, p.NP, 1, 1);
     for (int item = 0; item < nitems; ++item) {
       const int st = item % kStages;
@@ -196,7 +192,7 @@ __global__ void __launch_bounds__(kThreads) wgrad_generic_kernel(const __grid_co
   }
   fence_before_sync();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == kProducers / 32) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(p.tmem_cols) : "memory");
   }
 }
@@ -271,6 +267,7 @@ extern "C" int rtp_wgrad(const rtp_wgrad_desc* d, void* stream) {
   for (int t = 0; t < RTP_MAX_TAPS; ++t) { k.tz[t] = d->tz[t]; k.tx[t] = d->tx[t]; k.ty[t] = d->ty[t]; k.tc[t] = d->tc[t]; }
   k.RZ = d->RZ; k.RX = d->RX; k.RY = d->RY; k.IS = d->IS;
   k.total_rows = (int64_t)d->x.N * d->RZ * d->RX * d->RY;
+  RTP_CHECK_ARG(k.total_rows < (1ll << 31), "rtp_wgrad: too many rows");
   k.ntiles = (int)((k.total_rows + kTileK - 1) / kTileK);
   k.tiles_per_split = (k.ntiles + d->nsplit - 1) / d->nsplit;
   k.npairs = d->ntaps * (d->Cin / 8);
