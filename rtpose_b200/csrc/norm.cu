@@ -64,6 +64,43 @@ __device__ __forceinline__ int64_t s2d_offset(const P8& s, int C8, int c8, int z
   const int par = ((z & 1) << 2) | ((x & 1) << 1) | (y & 1);
   return (int64_t)(par * C8 + c8) * s.c_stride + s.voxel(z >> 1, x >> 1, y >> 1);
 }
+// Same walk with the loads of U rows issued before any of them is consumed: `ld(offset, z, x, y)` returns the loaded vectors,
+// `use(offset, data)` computes / stores.  Without this the compiler cannot hoist the next row's loads above the current
+// row's store (possible aliasing), and each thread has a single 16-byte load pair in flight.
+template <int U, typename L, typename F>
+__device__ __forceinline__ void rows_foreach_u(const P8& t, int row_begin, int row_end, int log2ty, L&& ld, F&& use) {
+  const int TY = 1 << log2ty;
+  const int ty = threadIdx.x & (TY - 1), tr = threadIdx.x >> log2ty;
+  const int rstep = (int)blockDim.x >> log2ty;
+  using D = decltype(ld((int64_t)0, 0, 0, 0));
+  for (int y = ty; y < t.Y; y += TY) {
+    int row = row_begin + tr;
+    for (; row + (U - 1) * rstep < row_end; row += U * rstep) {
+      int64_t off[U];
+      D d[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int r = row + u * rstep;
+        const int z = r / t.X, x = r - z * t.X;
+        off[u] = t.voxel(z, x, y);
+        d[u] = ld(off[u], z, x, y);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) use(off[u], d[u]);
+    }
+    for (; row < row_end; row += rstep) {
+      const int z = row / t.X, x = row - z * t.X;
+      const int64_t off = t.voxel(z, x, y);
+      use(off, ld(off, z, x, y));
+    }
+  }
+}
+struct Vec2 {
+  uint4 a, b;
+};
+struct Vec3 {
+  uint4 a, b, c;
+};
 __host__ __device__ inline int log2_ty(int Y) {
   int l = 3;
   while ((1 << l) < Y && l < 6) ++l;
@@ -98,15 +135,17 @@ __global__ void __launch_bounds__(256) gn_sums_partial_kernel(P8 x, float* __res
   float acc[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) acc[i] = 0.f;
-  rows_foreach(x, r0, r1, log2_ty(x.Y), [&](int64_t off) {
-    float f[8];
-    unpack8(ldg16(base + off), f);
+  rows_foreach_u<4>(
+      x, r0, r1, log2_ty(x.Y), [&](int64_t off, int, int, int) { return ldg16(base + off); },
+      [&](int64_t, const uint4& v) {
+        float f[8];
+        unpack8(v, f);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      acc[i] += f[i];
-      acc[8 + i] += f[i] * f[i];
-    }
-  });
+        for (int i = 0; i < 8; ++i) {
+          acc[i] += f[i];
+          acc[8 + i] += f[i] * f[i];
+        }
+      });
   block_reduce<16>(acc, sh, partial + (((size_t)n * x.C8 + c8) * kSlabs + slab) * 16);
 }
 
@@ -176,22 +215,33 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(P8 x, int C, int G, const
   if constexpr (S2D) {
     bf16* yb = y.ptr + n * y.n_stride;
     const int C8 = (int)gridDim.y;
-    rows_foreach_zxy(x, r0, r1, log2_ty(x.Y), [&](int64_t off, int z, int xx, int yy) {
-      float f[8];
-      unpack8(ldg16(xb + off), f);
+    rows_foreach_u<4>(
+        x, r0, r1, log2_ty(x.Y),
+        [&](int64_t off, int z, int xx, int yy) {
+          Vec2 v;  // .b carries the destination offset inside the view
+          v.a = ldg16(xb + off);
+          const int64_t so = s2d_offset(y, C8, c8, z, xx, yy);
+          v.b = make_uint4((uint32_t)so, (uint32_t)(so >> 32), 0u, 0u);
+          return v;
+        },
+        [&](int64_t, const Vec2& v) {
+          float f[8];
+          unpack8(v.a, f);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) f[i] = fmaf(f[i], a[i], b[i]);
-      stg16(yb + s2d_offset(y, C8, c8, z, xx, yy), pack8(f));
-    });
+          for (int i = 0; i < 8; ++i) f[i] = fmaf(f[i], a[i], b[i]);
+          stg16(yb + (int64_t)(((uint64_t)v.b.y << 32) | v.b.x), pack8(f));
+        });
   } else {
     bf16* yb = y.ptr + n * y.n_stride + c8 * y.c_stride;
-    rows_foreach(x, r0, r1, log2_ty(x.Y), [&](int64_t off) {
-      float f[8];
-      unpack8(ldg16(xb + off), f);
+    rows_foreach_u<4>(
+        x, r0, r1, log2_ty(x.Y), [&](int64_t off, int, int, int) { return ldg16(xb + off); },
+        [&](int64_t off, const uint4& v) {
+          float f[8];
+          unpack8(v, f);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) f[i] = fmaf(f[i], a[i], b[i]);
-      stg16(yb + off, pack8(f));
-    });
+          for (int i = 0; i < 8; ++i) f[i] = fmaf(f[i], a[i], b[i]);
+          stg16(yb + off, pack8(f));
+        });
   }
 }
 
@@ -218,16 +268,24 @@ __global__ void __launch_bounds__(256) gn_bwd_partial_kernel(P8 x, P8 dy, int C,
   float acc[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) acc[i] = 0.f;
-  rows_foreach_zxy(x, r0, r1, log2_ty(x.Y), [&](int64_t off, int z, int xx, int yy) {
-    float f[8], d[8];
-    unpack8(ldg16(xb + off), f);
-    unpack8(ldg16(db + (S2D ? s2d_offset(dy, C8, c8, z, xx, yy) : off)), d);
+  rows_foreach_u<4>(
+      x, r0, r1, log2_ty(x.Y),
+      [&](int64_t off, int z, int xx, int yy) {
+        Vec2 v;
+        v.a = ldg16(xb + off);
+        v.b = ldg16(db + (S2D ? s2d_offset(dy, C8, c8, z, xx, yy) : off));
+        return v;
+      },
+      [&](int64_t, const Vec2& v) {
+        float f[8], d[8];
+        unpack8(v.a, f);
+        unpack8(v.b, d);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      acc[i] += d[i];
-      acc[8 + i] += d[i] * ((f[i] - mean[i]) * rstd[i]);
-    }
-  });
+        for (int i = 0; i < 8; ++i) {
+          acc[i] += d[i];
+          acc[8 + i] += d[i] * ((f[i] - mean[i]) * rstd[i]);
+        }
+      });
   block_reduce<16>(acc, sh, partial + (((size_t)n * x.C8 + c8) * kSlabs + slab) * 16);
 }
 
@@ -281,24 +339,33 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(P8 x, P8 dy, int C, i
   const bf16* db = dy.ptr + n * dy.n_stride + (S2D ? 0 : c8 * dy.c_stride);
   bf16* ob = dx.ptr + n * dx.n_stride + c8 * dx.c_stride;
   const int C8 = (int)gridDim.y;
-  rows_foreach_zxy(x, r0, r1, log2_ty(x.Y), [&](int64_t off, int z, int xx, int yy) {
-    float f[8], d[8], o[8];
-    unpack8(ldg16(xb + off), f);
-    unpack8(ldg16(db + (S2D ? s2d_offset(dy, C8, c8, z, xx, yy) : off)), d);
+  rows_foreach_u<4>(
+      x, r0, r1, log2_ty(x.Y),
+      [&](int64_t off, int z, int xx, int yy) {
+        Vec3 v;
+        v.a = ldg16(xb + off);
+        v.b = ldg16(db + (S2D ? s2d_offset(dy, C8, c8, z, xx, yy) : off));
+        v.c = accumulate ? *reinterpret_cast<const uint4*>(ob + off) : make_uint4(0u, 0u, 0u, 0u);
+        return v;
+      },
+      [&](int64_t off, const Vec3& v) {
+        float f[8], d[8], o[8];
+        unpack8(v.a, f);
+        unpack8(v.b, d);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float xh = (f[i] - mean[i]) * rstd[i];
-      o[i] = rstd[i] * (ga[i] * d[i] - k1[i] - xh * k2[i]);
-      if (relu_mask && !(f[i] > 0.f)) o[i] = 0.f;
-    }
-    if (accumulate) {
-      float p[8];
-      unpack8(*reinterpret_cast<const uint4*>(ob + off), p);
+        for (int i = 0; i < 8; ++i) {
+          const float xh = (f[i] - mean[i]) * rstd[i];
+          o[i] = rstd[i] * (ga[i] * d[i] - k1[i] - xh * k2[i]);
+          if (relu_mask && !(f[i] > 0.f)) o[i] = 0.f;
+        }
+        if (accumulate) {
+          float p[8];
+          unpack8(v.c, p);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] += p[i];
-    }
-    stg16(ob + off, pack8(o));
-  });
+          for (int i = 0; i < 8; ++i) o[i] += p[i];
+        }
+        stg16(ob + off, pack8(o));
+      });
 }
 
 // blocks along the row dimension for the elementwise kernels: every thread gets >= ~8 vectors
