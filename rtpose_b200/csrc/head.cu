@@ -139,50 +139,78 @@ __global__ void __launch_bounds__(256) head_loss_final_kernel(const __grid_const
     if (tid < s) sred[tid] += sred[tid + s];
     __syncthreads();
   }
-  if (tid < 64) s_reg[tid] = 0.f;
-  __syncthreads();
+  // The per-target work is spread over the block (thread = target for the heat-map terms, thread = regression channel
+  // for the L1 terms) but every sum keeps the serial order of the reference loop, so the result does not depend on
+  // the thread count.  (One thread walking all N*M*R dependent global loads took 0.22 ms.)
+  __shared__ float s_pos[256];
+  __shared__ float s_np;
+  const int NM = hm.N * p.M;
+  const int YX = hm.Y * hm.X;
   if (tid == 0) {
-    const float neg = (float)sred[0];
-    const int NM = hm.N * p.M;
-    float num_pos = 0.f;
-    for (int i = 0; i < NM; ++i) num_pos += p.mask[i] ? 1.f : 0.f;
-    const float inv_np = num_pos > 0.f ? 1.f / num_pos : 1.f;
-    const float reg_den = num_pos + 1e-4f;
-    float pos = 0.f;
-    const int YX = hm.Y * hm.X;
-    for (int i = 0; i < NM; ++i) {
+    float np = 0.f;
+    for (int i = 0; i < NM; ++i) np += p.mask[i] ? 1.f : 0.f;
+    s_np = np;
+  }
+  __syncthreads();
+  const float num_pos = s_np;
+  const float inv_np = num_pos > 0.f ? 1.f / num_pos : 1.f;
+  const float reg_den = num_pos + 1e-4f;
+  // heat-map positive terms: target i -> s_pos (chunks of 256 targets, summed in order by thread 0)
+  float pos = 0.f;
+  for (int base = 0; base < NM; base += 256) {
+    const int i = base + tid;
+    float term = 0.f;
+    if (i < NM) {
       const int n = i / p.M;
       const float m = p.mask[i] ? 1.f : 0.f;
       const int64_t id = p.ind[i];
       const int z = (int)(id / YX), y = (int)((id % YX) / hm.X), x = (int)(id % hm.X);
       const int c = (int)p.cat[i];
-      // heatmap positive term
       const bf16* hp = hm.ptr + n * hm.n_stride + (c >> 3) * hm.c_stride + hm.voxel(z, x, y) + (c & 7);
-      const float s = sigmoidf_(__bfloat162float(*hp));
-      const float pr = fminf(fmaxf(s, kPMin), kPMax);
+      const float sg = sigmoidf_(__bfloat162float(*hp));
+      const float pr = fminf(fmaxf(sg, kPMin), kPMax);
       const float lp = logf(pr);
-      pos += lp * (1.f - pr) * (1.f - pr) * m;
-      if (p.has_grad && m > 0.f && num_pos > 0.f && s >= kPMin && s <= kPMax) {
+      term = lp * (1.f - pr) * (1.f - pr) * m;
+      if (p.has_grad && m > 0.f && num_pos > 0.f && sg >= kPMin && sg <= kPMax) {
+        // two targets of one sample may share a voxel only with different classes (cat), i.e. different elements
         const float dpos_dp = (1.f - pr) * (1.f - pr) / pr - 2.f * (1.f - pr) * lp;
         bf16* gp = p.d_hm.ptr + n * p.d_hm.n_stride + (c >> 3) * p.d_hm.c_stride + p.d_hm.voxel(z, x, y) + (c & 7);
         const float g = __bfloat162float(*gp) - inv_np * dpos_dp * pr * (1.f - pr) * p.grad_scale;
         *gp = __float2bfloat16(g);
       }
-      // regression
-      for (int r = 0; r < p.R; ++r) {
-        const bf16* rp = p.reg.ptr + n * p.reg.n_stride + (r >> 3) * p.reg.c_stride + p.reg.voxel(z, x, y) + (r & 7);
-        const float pred = __bfloat162float(*rp) * m;
-        const float tg = p.anno[(int64_t)i * p.R + r] * m;
-        const float diff = pred - tg;
-        s_reg[r] += fabsf(diff) / reg_den;
-        if (p.has_grad && m > 0.f) {
-          const float sg = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);
-          bf16* gp = p.d_reg.ptr + n * p.d_reg.n_stride + (r >> 3) * p.d_reg.c_stride + p.d_reg.voxel(z, x, y) + (r & 7);
-          const float g = __bfloat162float(*gp) + p.weight * p.code_w[r] * sg / reg_den * p.grad_scale;
-          *gp = __float2bfloat16(g);
-        }
+    }
+    s_pos[tid] = term;
+    __syncthreads();
+    if (tid == 0)
+      for (int j = 0; j < 256 && base + j < NM; ++j) pos += s_pos[j];
+    __syncthreads();
+  }
+  // regression: thread r walks the targets in order
+  if (tid < p.R) {
+    const int r = tid;
+    float sr = 0.f;
+    for (int i = 0; i < NM; ++i) {
+      const int n = i / p.M;
+      const float m = p.mask[i] ? 1.f : 0.f;
+      const int64_t id = p.ind[i];
+      const int z = (int)(id / YX), y = (int)((id % YX) / hm.X), x = (int)(id % hm.X);
+      const bf16* rp = p.reg.ptr + n * p.reg.n_stride + (r >> 3) * p.reg.c_stride + p.reg.voxel(z, x, y) + (r & 7);
+      const float pred = __bfloat162float(*rp) * m;
+      const float tg = p.anno[(int64_t)i * p.R + r] * m;
+      const float diff = pred - tg;
+      sr += fabsf(diff) / reg_den;
+      if (p.has_grad && m > 0.f) {
+        const float sgn = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);
+        bf16* gp = p.d_reg.ptr + n * p.d_reg.n_stride + (r >> 3) * p.d_reg.c_stride + p.d_reg.voxel(z, x, y) + (r & 7);
+        const float g = __bfloat162float(*gp) + p.weight * p.code_w[r] * sgn / reg_den * p.grad_scale;
+        *gp = __float2bfloat16(g);
       }
     }
+    s_reg[r] = sr;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const float neg = (float)sred[0];
     const float hm_loss = num_pos > 0.f ? -(pos + neg) / num_pos : -neg;
     float loc = 0.f;
     for (int r = 0; r < p.R; ++r) {
