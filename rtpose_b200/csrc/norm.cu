@@ -543,22 +543,33 @@ __global__ void __launch_bounds__(256) stem_bwd_partial_kernel(P8 x, P8 dy, floa
   block_reduce<16>(acc, sh, partial + (((size_t)n * gridDim.y + c8) * kSlabs + slab) * 16);
 }
 
-// out0[c] (+)= sum_{n,slab} partial[..][j], out1[c] (+)= sum partial[..][8+j]  (fixed order)
-__global__ void slab_final_kernel(const float* __restrict__ partial, int N, int C8, int C, float* __restrict__ out0,
-                                  float* __restrict__ out1, int accumulate) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  const int c8 = c >> 3, j = c & 7;
-  double a = 0, b = 0;
-  for (int n = 0; n < N; ++n) {
-    const float* p = partial + ((size_t)n * C8 + c8) * kSlabs * 16;
-    for (int k = 0; k < kSlabs; ++k) {
-      a += p[k * 16 + j];
-      b += p[k * 16 + 8 + j];
+// out0[c] (+)= sum_{n,slab} partial[..][j], out1[c] (+)= sum partial[..][8+j]: one block per 8-channel chunk, the N*kSlabs
+// partial rows spread over the threads, fixed-shape tree reduction (deterministic).  (One thread per channel walking
+// 2*N*kSlabs dependent loads took 47 us.)
+__global__ void __launch_bounds__(256) slab_final_kernel(const float* __restrict__ partial, int N, int C8, int C,
+                                                         float* __restrict__ out0, float* __restrict__ out1, int accumulate) {
+  __shared__ float sh[8 * 16];
+  __shared__ float res[16];
+  const int c8 = blockIdx.x;
+  float acc[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+  for (int i = threadIdx.x; i < N * kSlabs; i += 256) {
+    const int n = i / kSlabs, k = i - n * kSlabs;
+    const float4* p = reinterpret_cast<const float4*>(partial + (((size_t)n * C8 + c8) * kSlabs + k) * 16);
+    const float4 a = p[0], b = p[1], c = p[2], d = p[3];
+    acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w; acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+    acc[8] += c.x; acc[9] += c.y; acc[10] += c.z; acc[11] += c.w; acc[12] += d.x; acc[13] += d.y; acc[14] += d.z; acc[15] += d.w;
+  }
+  block_reduce<16>(acc, sh, res);
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    const int c = c8 * 8 + threadIdx.x;
+    if (c < C) {
+      if (out0) out0[c] = accumulate ? out0[c] + res[threadIdx.x] : res[threadIdx.x];
+      if (out1) out1[c] = accumulate ? out1[c] + res[8 + threadIdx.x] : res[8 + threadIdx.x];
     }
   }
-  if (out0) out0[c] = accumulate ? out0[c] + (float)a : (float)a;
-  if (out1) out1[c] = accumulate ? out1[c] + (float)b : (float)b;
 }
 
 }  // namespace
@@ -576,7 +587,7 @@ extern "C" int rtp_stem_bwd(rtp_p8 x, rtp_p8 dy, int32_t C, float* dw, float* db
   RTP_CHECK_ARG(x.ptr && dy.ptr && dw && db && workspace && C > 0 && C <= dy.C8 * 8, "rtp_stem_bwd: bad args");
   const int C8 = ceil_div(C, 8);
   stem_bwd_partial_kernel<<<dim3(kSlabs, C8, x.N), 256, 0, (cudaStream_t)stream>>>(P8(x), P8(dy), workspace);
-  slab_final_kernel<<<ceil_div(C, 64), 64, 0, (cudaStream_t)stream>>>(workspace, x.N, C8, C, db, dw, accumulate);
+  slab_final_kernel<<<C8, 256, 0, (cudaStream_t)stream>>>(workspace, x.N, C8, C, db, dw, accumulate);
   RTP_LAUNCH_CHECK();
 }
 
@@ -585,6 +596,6 @@ extern "C" int rtp_channel_sum(rtp_p8 x, int32_t C, float* out, int32_t accumula
   P8 t(x);
   t.C8 = ceil_div(C, 8);
   gn_sums_partial_kernel<<<dim3(kSlabs, t.C8, t.N), 256, 0, (cudaStream_t)stream>>>(t, workspace);
-  slab_final_kernel<<<ceil_div(C, 64), 64, 0, (cudaStream_t)stream>>>(workspace, t.N, t.C8, C, out, nullptr, accumulate);
+  slab_final_kernel<<<t.C8, 256, 0, (cudaStream_t)stream>>>(workspace, t.N, t.C8, C, out, nullptr, accumulate);
   RTP_LAUNCH_CHECK();
 }
