@@ -181,28 +181,34 @@ __device__ __forceinline__ float hat_weight(int d, int l, float scale) {
 // axis: 0 = z, 1 = x, 2 = y.  `in` and `out` differ only in the extent of `axis`.  The destinations touching l are
 // the d with |scale*d - l| < 1; they are visited four at a time with clamped indices (weight 0 outside the range) so
 // the loads of a group are independent and issue back to back.
-__global__ void __launch_bounds__(256) upsample_bwd_axis_kernel(P8 in, P8 out, int C8, int axis, int accumulate) {
+// Launch geometry: grid (x tiles, z, n*C8 + c8), block = (2^log2ty lanes along y) x (256 >> log2ty rows along x) — no
+// per-element index divisions.  The candidate range is exact: the conservative bounds from the reciprocal are tightened
+// with the same `scale * d` expression the weights use, so a 2x pass reads one group of <= 4 vectors per output.
+__global__ void __launch_bounds__(256) upsample_bwd_axis_kernel(P8 in, P8 out, int C8, int axis, int accumulate, int log2ty) {
   const int in_n = axis == 0 ? in.Z : (axis == 1 ? in.X : in.Y);
   const int out_n = axis == 0 ? out.Z : (axis == 1 ? out.X : out.Y);
   const float scale = ac_scale(out_n, in_n);  // low-res (out) is the interpolation source, high-res (in) the dest
   const float inv = scale > 0.f ? 1.f / scale : 0.f;
   const int64_t astride = axis == 0 ? in.plane_elems() : (axis == 1 ? (int64_t)in.Yp * 8 : 8);
-  const uint32_t total = (uint32_t)((int64_t)out.Z * out.X * out.Y * C8 * out.N);  // < 2^31 vectors
-  for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < total; i += gridDim.x * 256u) {
-    uint32_t q = i;
-    const int y = (int)(q % (uint32_t)out.Y); q /= (uint32_t)out.Y;
-    const int x = (int)(q % (uint32_t)out.X); q /= (uint32_t)out.X;
-    const int z = (int)(q % (uint32_t)out.Z); q /= (uint32_t)out.Z;
-    const int c8 = (int)(q % (uint32_t)C8);
-    const int n = (int)(q / (uint32_t)C8);
+  const int TY = 1 << log2ty, TX = 256 >> log2ty;
+  const int ty = threadIdx.x & (TY - 1), tx = threadIdx.x >> log2ty;
+  const int z = blockIdx.y;
+  const int c8 = blockIdx.z % C8, n = blockIdx.z / C8;
+  const int x = blockIdx.x * TX + tx;
+  if (x >= out.X) return;
+  const bf16* in_nc = in.ptr + n * in.n_stride + c8 * in.c_stride;
+  bf16* out_nc = out.ptr + n * out.n_stride + c8 * out.c_stride;
+  for (int y = ty; y < out.Y; y += TY) {
     const int l = axis == 0 ? z : (axis == 1 ? x : y);
     int lo = 0, hi = in_n - 1;
-    if (scale > 0.f) {  // one extra candidate on each side absorbs the rounding of the reciprocal
+    if (scale > 0.f) {
       lo = max(0, (int)floorf((float)(l - 1) * inv));
       hi = min(in_n - 1, (int)ceilf((float)(l + 1) * inv));
+      if (scale * (float)lo <= (float)(l - 1)) ++lo;  // weight exactly 0 there
+      if (scale * (float)hi >= (float)(l + 1)) --hi;
     }
     // voxel of this output with the reduced axis at 0
-    const bf16* ib = in.ptr + n * in.n_stride + c8 * in.c_stride + in.voxel(axis == 0 ? 0 : z, axis == 1 ? 0 : x, axis == 2 ? 0 : y);
+    const bf16* ib = in_nc + in.voxel(axis == 0 ? 0 : z, axis == 1 ? 0 : x, axis == 2 ? 0 : y);
     float acc[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) acc[k] = 0.f;
@@ -223,7 +229,7 @@ __global__ void __launch_bounds__(256) upsample_bwd_axis_kernel(P8 in, P8 out, i
         for (int k = 0; k < 8; ++k) acc[k] = fmaf(w[u], f[k], acc[k]);
       }
     }
-    bf16* dst = out.ptr + n * out.n_stride + c8 * out.c_stride + out.voxel(z, x, y);
+    bf16* dst = out_nc + out.voxel(z, x, y);
     if (accumulate) {
       float g[8];
       unpack8(*reinterpret_cast<const uint4*>(dst), g);
@@ -317,10 +323,11 @@ extern "C" int rtp_upsample_bwd(rtp_p8 dout, rtp_p8 dlow, int32_t C, int32_t acc
   t2.ptr = (char*)workspace + (size_t)t1.N * t1.n_stride * 2; t2.C8 = C8; t2.Y = dlow.Y; t2.X = dlow.X;
   t2.c_stride = (int64_t)t2.Z * (t2.X + 2) * (t2.Y + 2) * 8; t2.n_stride = t2.c_stride * C8;
   auto launch = [&](const rtp_p8& a, const rtp_p8& b, int axis, int acc) {
-    const int64_t total = (int64_t)b.Z * b.X * b.Y * C8 * b.N;
-    int64_t blocks = (total + 255) / 256;
-    if (blocks > 148 * 16) blocks = 148 * 16;
-    upsample_bwd_axis_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(P8(a), P8(b), C8, axis, acc);
+    int log2ty = 2;
+    while ((1 << log2ty) < b.Y && log2ty < 6) ++log2ty;
+    const int TX = 256 >> log2ty;
+    upsample_bwd_axis_kernel<<<dim3((unsigned)ceil_div(b.X, TX), (unsigned)b.Z, (unsigned)(b.N * C8)), 256, 0, (cudaStream_t)stream>>>(
+        P8(a), P8(b), C8, axis, acc, log2ty);
   };
   launch(dout, t1, 2, 0);
   launch(t1, t2, 1, 0);
