@@ -28,6 +28,11 @@ namespace {
 constexpr int kThreads = 320;  // warp 0 producer, warp 1 MMA, warps 2-5 / 6-9 epilogue groups 0 / 1
 constexpr int kMaxBlocks = 32;
 constexpr int kMaxStages = 8;
+#ifdef RTP_K3S1_DEBUG
+constexpr bool kDbg = true;   // cycle counters of the MMA warp (tools/dbg_k3s1.py builds with -DRTP_K3S1_DEBUG)
+#else
+constexpr bool kDbg = false;  // the counters cost a CS2R per step boundary: compiled out of the production kernel
+#endif
 
 struct K3 {
   P8 in, out, res, mask;
@@ -137,7 +142,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_k3s1_kernel(const __grid_con
     {
       const bool leader = lane == 0;
       uint32_t it = 0, wit = 0, fresh_mask = 0;  // bit b: parity of the number of first-writes to block b so far
-      long long t_empty = 0, t_full = 0, t_issue = 0, t0 = clock64(), tk = 0;
+      long long t_empty = 0, t_full = 0, t_issue = 0, t_first = 0, t_commit = 0, t0 = kDbg ? clock64() : 0, tk = 0;
       bool w_ready = false;
       uint32_t wcur = 0;
       const uint32_t idesc1 = idesc_bf16(128, p.NPo, 0, 0), idesc2 = idesc_bf16(128, 2 * p.NPo, 0, 0),
@@ -162,22 +167,22 @@ __global__ void __launch_bounds__(kThreads, 1) conv_k3s1_kernel(const __grid_con
           for (int iz = iz0; iz < iz1; ++iz) {
             const int s = it % S;
             const int lo = max(iz - 1, zo0), hi = min(iz + 1, zo1 - 1);
-            tk = clock64();
+            if constexpr (kDbg) tk = clock64();
             if (g == 0) {  // blocks written for the first time in this unit must have been drained by the epilogue
               if (iz + 1 <= hi) {
                 const int b = iz + 1 - zo0;
-                mbar_wait(&bar_acc_empty[b], ((fresh_mask >> b) & 1) ^ 1);
+                mbar_wait(&bar_acc_empty[b], (fresh_mask >> b) & 1);
                 fresh_mask ^= 1u << b;
               }
               if (iz == 0) {
-                mbar_wait(&bar_acc_empty[0], (fresh_mask & 1) ^ 1);
+                mbar_wait(&bar_acc_empty[0], fresh_mask & 1);
                 fresh_mask ^= 1u;
               }
             }
-            { const long long t1 = clock64(); t_empty += t1 - tk; tk = t1; }
+            if constexpr (kDbg) { const long long t1 = clock64(); t_empty += t1 - tk; tk = t1; }
             mbar_wait(&bar_full[s], (it / S) & 1);
             fence_after_sync();
-            { const long long t1 = clock64(); t_full += t1 - tk; tk = t1; }
+            if constexpr (kDbg) { const long long t1 = clock64(); t_full += t1 - tk; tk = t1; }
             // Descriptors are built from precomputed halves: only the 14-bit start-address field (16-byte units) of the
             // low word changes between MMAs, so one elected thread sustains the issue rate (~10 instructions / MMA).
             const uint32_t dcol = tmem + (uint32_t)(lo - zo0) * p.NPo;
@@ -186,21 +191,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_k3s1_kernel(const __grid_con
             const uint32_t idesc = nblk == 3 ? idesc3 : (nblk == 2 ? idesc2 : idesc1);
             const uint32_t a_lo = a_lo_c + ((stage0 + (uint32_t)s * p.stage_bytes) >> 4);
             const uint32_t b_lo = b_lo_c + ((wbase0 + wcur * p.wbuf_bytes) >> 4);
-            bool first_done = false;
-            if (g == 0 && elect_one()) {
-              // first touch of this input plane: the block of output plane iz+1 (and plane 0 when iz == 0) is fresh
-              // and must be overwritten, the others accumulate
-              const uint64_t ad = mk_desc(a_lo, a_hi);
-              if (iz == 0 || lo == iz + 1) {
-                mma_ss(dcol, ad, mk_desc(b_lo + boff16, b_hi), idesc, 0u);
-              } else {
-                const int nacc = min(iz, hi) - lo + 1;  // iz > hi on the halo plane behind a z-chunk
-                mma_ss(dcol, ad, mk_desc(b_lo + boff16, b_hi), nacc == 2 ? idesc2 : idesc1, 1u);
-                if (iz + 1 <= hi)
-                  mma_ss(tmem + (uint32_t)(iz + 1 - zo0) * p.NPo, ad, mk_desc(b_lo + 2 * p.NPo, b_hi), idesc1, 0u);
-              }
-            }
-            first_done = (g == 0);
+            // every accumulator block is handed over zeroed by the epilogue (tcgen05.st after the drain, and once at
+            // kernel start), so all MMAs accumulate: no overwrite / split first tap, one uniform N = 96 stream
+            if constexpr (kDbg) { const long long t1 = clock64(); t_first += t1 - tk; tk = t1; }
             const uint32_t tm = p.tapmask[g];
             if (elect_one()) {  // elect.sync: the compiler knows exactly one lane runs this block (no per-MMA waterfall)
 #pragma unroll
@@ -210,10 +203,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_k3s1_kernel(const __grid_con
                 const uint32_t bt = b_lo + boff16 + t9 * b_tap16;
 #pragma unroll
                 for (int k16 = 0; k16 < KS; ++k16) {
-                  if (t9 == 0 && k16 == 0 && first_done) continue;
                   mma_ss(dcol, mk_desc(at + k16 * a_k16, a_hi), mk_desc(bt + k16 * b_k16, b_hi), idesc, 1u);
                 }
               }
+              if constexpr (kDbg) { const long long t1 = clock64(); t_issue += t1 - tk; tk = t1; }
               mma_commit(&bar_empty[s]);
               if (g == p.npass - 1) {
                 if (iz - 1 >= zo0) mma_commit(&bar_acc_full[iz - 1 - zo0]);
@@ -221,7 +214,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_k3s1_kernel(const __grid_con
               }
             }
             __syncwarp();
-            t_issue += clock64() - tk;
+            if constexpr (kDbg) t_commit += clock64() - tk;
             ++it;
           }
           if (p.npass > 1) {
@@ -230,9 +223,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_k3s1_kernel(const __grid_con
           }
         }
       }
-      if (p.dbg && leader) {
+      if (kDbg && p.dbg && leader) {
         long long* d = p.dbg + (size_t)blockIdx.x * 8;
-        d[0] = clock64() - t0; d[1] = t_empty; d[2] = t_full; d[3] = t_issue; d[4] = it;
+        d[0] = clock64() - t0; d[1] = t_empty; d[2] = t_full; d[3] = t_issue; d[4] = it; d[5] = t_first; d[6] = t_commit;
       }
     }
   } else {
@@ -242,6 +235,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_k3s1_kernel(const __grid_con
     const int r = lane_q * 32 + lane;               // GEMM row
     const uint32_t trow = tmem + ((uint32_t)(lane_q * 32) << 16);
     uint32_t full_mask = 0;  // bit b: parity of the number of times block b has been drained so far
+    // hand every accumulator block of this group to the MMA warp zeroed (the MMAs only ever accumulate)
+    for (int b = eg; b < p.ZC; b += 2) {
+      for (int c = 0; c < p.NPo; c += 16) tmem_st16_zero(trow + b * p.NPo + c);
+      tmem_st_wait();
+      fence_before_sync();
+      mbar_arrive(&bar_acc_empty[b]);
+    }
     // STAT: per-thread partial sums over the rows this thread stores; folded over the warp at the end of every unit
     // (fixed butterfly => deterministic) and added to this warp's private [N][64] slab in global memory
     float st0[STAT ? 32 : 1], st1[STAT ? 32 : 1];
@@ -301,7 +301,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_k3s1_kernel(const __grid_con
           uint32_t v[16];
           tmem_ld16(trow + b * p.NPo + c16 * 16, v);
           tmem_ld_wait();
-          if (c16 * 16 + 16 >= p.NPo) {  // last read of this block: hand it back to the MMA warp
+          if (c16 * 16 + 16 >= p.NPo) {  // last read of this block: zero it and hand it back to the MMA warp
+            for (int c = 0; c < p.NPo; c += 16) tmem_st16_zero(trow + b * p.NPo + c);
+            tmem_st_wait();
             fence_before_sync();
             mbar_arrive(&bar_acc_empty[b]);
           }

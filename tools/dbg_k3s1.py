@@ -20,4 +20,5 @@ torch.cuda.synchronize()
 t = dbg.view(148, 8).float()
 m = t.mean(0)
 print("per CTA: total %.0f cyc, wait acc_empty %.0f, wait full %.0f, issue %.0f, plane-steps %.0f" % tuple(m[:5].tolist()))
-print("per plane-step: total %.0f, empty %.0f, full %.0f, issue %.0f" % tuple((m[:4] / m[4]).tolist()))
+print("per plane-step: total %.0f, empty %.0f, full %.0f, tap-loop issue %.0f, first-touch %.0f, commits+syncwarp %.0f" % tuple((m[[0, 1, 2, 3, 5, 6]] / m[4]).tolist()))
+print("(needs a build with RTP_NVCC_EXTRA=-DRTP_K3S1_DEBUG python -m rtpose_b200.build --force)")

@@ -123,22 +123,28 @@ __global__ void probe_mnmajor(const bf16* __restrict__ X, const bf16* __restrict
 // ---------------------------------------------------------------------------------------------------
 // T4: throughput.  mode 0: K-major A/B, A start cycles through 9 tap shifts; mode 1: MN-major A/B.
 // mode 2: K-major, fixed aligned A.  Each CTA issues `iters` MMAs of shape 128 x N x 16 and reports cycles.
-__global__ void probe_rate(long long* __restrict__ cycles, int N, int iters, int mode) {
+// Interference modes (what a real conv kernel adds around the same MMA stream as mode 0):
+//   3: B also cycles through 9 tap slices        4: 3 + a second warp streams bulk copies into shared memory
+//   5: 3 + four warps drain TMEM with tcgen05.ld 6: 3 + 4 + 5 together           7: 3 with the D column block rotating
+__global__ void probe_rate(long long* __restrict__ cycles, int N, int iters, int mode, const uint8_t* __restrict__ gsrc) {
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ uint64_t bar_mma;
+  __shared__ uint64_t bar_mma, bar_cp[2];
   __shared__ uint32_t tmem_base;
+  __shared__ volatile int stop_flag;
   const int tid = threadIdx.x, warp = tid >> 5;
   const int P = 600;  // positions per channel chunk
   bf16* sX = reinterpret_cast<bf16*>(smem);                 // [16 chunks][P][8] = 153.6 KB
-  bf16* sW = sX + 16 * P * 8;                               // [2][256][8] = 8 KB
-  for (int i = tid; i < 16 * P * 8 + 2 * 256 * 8; i += blockDim.x) sX[i] = __float2bfloat16(0.001f * (i % 7));
-  if (tid == 0) { mbar_init(&bar_mma, 1); mbar_fence_init(); }
+  bf16* sW = sX + 16 * P * 8;                               // 9 tap slices x [2][N<=96.. 256][8] (mode >= 3: N <= 96)
+  uint8_t* sCopy = reinterpret_cast<uint8_t*>(sW) + 9 * 2 * 96 * 16 + 2 * 256 * 16;  // 2 x 16.8 KB landing zone
+  for (int i = tid; i < 16 * P * 8 + 9 * 2 * 96 * 8 + 2 * 256 * 8; i += blockDim.x) sX[i] = __float2bfloat16(0.001f * (i % 7));
+  if (tid == 0) { mbar_init(&bar_mma, 1); mbar_init(&bar_cp[0], 1); mbar_init(&bar_cp[1], 1); mbar_fence_init(); stop_flag = 0; }
   if (warp == 0) tmem_alloc<512>(&tmem_base);
   fence_proxy_async();
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
   const uint32_t tm = tmem_base;
+  const bool vary_b = mode >= 3, copies = mode == 4 || mode == 6, drain = mode == 5 || mode == 6;
   if (tid == 0) {
     const int Yp = 66;
     const uint32_t idesc = (mode == 1) ? idesc_bf16(128, N, 1, 1) : idesc_bf16(128, N, 0, 0);
@@ -156,9 +162,10 @@ __global__ void probe_rate(long long* __restrict__ cycles, int N, int iters, int
             bd = smem_desc(xb + (k16 * 16 + 200) * 16, 128, P * 16);
           } else {
             ad = smem_desc(xb + sh * 16 + k16 * 2 * P * 16, P * 16, 128);
-            bd = smem_desc(wb, 256 * 16, 128);
+            bd = vary_b ? smem_desc(wb + (j * 2 * N + k16 * 2 * N) * 16 * 0 + j * 2 * N * 16 + k16 * 0, N * 16, 128) : smem_desc(wb, 256 * 16, 128);
           }
-          mma_ss(tm, ad, bd, idesc, (it | j | k16) ? 1u : 0u);
+          const uint32_t dcol = (mode == 7) ? tm + ((it / 18) % 4) * 128 : tm;
+          mma_ss(dcol, ad, bd, idesc, (it | j | k16) ? 1u : 0u);
         }
       }
     }
@@ -166,6 +173,32 @@ __global__ void probe_rate(long long* __restrict__ cycles, int N, int iters, int
     mbar_wait(&bar_mma, 0);
     long long t1 = clock64();
     cycles[blockIdx.x] = t1 - t0;
+    stop_flag = 1;
+  } else if (tid == 32 && copies) {
+    // 16.8 KB (4 x 4192 B) per 18 MMAs in the real kernel; here: as fast as the two-slot ring allows
+    uint32_t it = 0;
+    while (!stop_flag) {
+      const int s = it & 1;
+      if (it >= 2) mbar_wait(&bar_cp[s], ((it >> 1) - 1) & 1);
+      mbar_arrive_expect_tx(&bar_cp[s], 4 * 4192);
+      for (int c = 0; c < 4; ++c) bulk_g2s(sCopy + s * 16768 + c * 4192, gsrc + ((size_t)(blockIdx.x * 64 + (it & 63)) * 4 + c) * 4192, 4192, &bar_cp[s]);
+      ++it;
+    }
+    if (it >= 1) mbar_wait(&bar_cp[(it - 1) & 1], ((it - 1) >> 1) & 1);
+    if (it >= 2) mbar_wait(&bar_cp[it & 1], ((it - 2) >> 1) & 1);
+  } else if (warp >= 2 && drain) {
+    // epilogue-like TMEM reads: 96 columns per "plane", back to back
+    const uint32_t trow = tm + ((uint32_t)((warp & 3) * 32) << 16);
+    uint32_t sink = 0;
+    while (!stop_flag) {
+      for (int c = 0; c < 96; c += 16) {
+        uint32_t v[16];
+        tmem_ld16(trow + 256 + c, v);
+        tmem_ld_wait();
+        sink += v[0];
+      }
+    }
+    if (sink == 0x12345678u) cycles[0] = 0;
   }
   fence_before_sync();
   __syncthreads();
@@ -248,12 +281,15 @@ int main() {
   {
     const int nsm = prop.multiProcessorCount;
     long long* dC; CK(cudaMalloc(&dC, nsm * 8));
-    size_t smem = (16 * 600 * 8 + 2 * 256 * 8) * 2;
+    size_t smem = (16 * 600 * 8 + 9 * 2 * 96 * 8 + 2 * 256 * 8) * 2 + 2 * 16768;
     CK(cudaFuncSetAttribute(probe_rate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    uint8_t* gsrc; CK(cudaMalloc(&gsrc, (size_t)nsm * 64 * 4 * 4192 + 4192)); CK(cudaMemset(gsrc, 1, (size_t)nsm * 64 * 4 * 4192));
     const int iters = 18 * 512;
-    for (int mode = 0; mode < 3; ++mode) for (int N : {32, 64, 96, 128, 192, 256}) {
+    for (int mode = 0; mode < 8; ++mode) for (int N : {32, 64, 96, 128, 192, 256}) {
       if (mode == 1 && N > 128) continue;
-      for (int rep = 0; rep < 2; ++rep) { probe_rate<<<nsm, 128, smem>>>(dC, N, iters, mode); CK(cudaDeviceSynchronize()); }
+      if (mode >= 3 && N != 96 && N != 32) continue;  // the interference modes model conv_k3s1 (N = 96) and wgrad (N = 32)
+      const int threads = mode >= 4 && mode <= 6 ? 192 : 128;
+      for (int rep = 0; rep < 2; ++rep) { probe_rate<<<nsm, threads, smem>>>(dC, N, iters, mode, gsrc); CK(cudaDeviceSynchronize()); }
       std::vector<long long> hC(nsm);
       CK(cudaMemcpy(hC.data(), dC, nsm * 8, cudaMemcpyDeviceToHost));
       std::sort(hC.begin(), hC.end());
@@ -262,6 +298,7 @@ int main() {
       printf("T4 mode=%d N=%3d: %.1f cyc/MMA median (max %.1f), math floor %.0f -> %.0f%% of tensor peak\n", mode, N, med, mx, ideal, 100.0 * ideal / med);
       if (jf) fprintf(jf, ", \"t4_m%d_n%d_cyc\": %.2f", mode, N, med);
     }
+    cudaFree(gsrc);
     cudaFree(dC);
   }
   if (jf) { fprintf(jf, "}\n"); fclose(jf); }
