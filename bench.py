@@ -44,33 +44,58 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """Samples nvidia-smi SM clocks / throttle reasons while the timed region runs."""
+    """Samples the SM clock and the throttle reasons while the timed region runs: NVML every 10 ms (a step is ~25 ms,
+    the timed region a few hundred ms), falling back to polling nvidia-smi when pynvml is unavailable."""
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.index, self.rows, self.stop_flag, self.max_mhz, self.source = index, [], False, None, None
 
-    def run(self):
+    def _run_nvml(self):
+        import pynvml as N
+        N.nvmlInit()
+        h = N.nvmlDeviceGetHandleByIndex(self.index)
+        self.max_mhz = int(N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM))
+        bits = [N.nvmlClocksThrottleReasonHwSlowdown, N.nvmlClocksThrottleReasonHwThermalSlowdown,
+                N.nvmlClocksThrottleReasonSwThermalSlowdown, N.nvmlClocksThrottleReasonSwPowerCap]
+        self.source = "nvml"
+        while not self.stop_flag:
+            mhz = int(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM))
+            mask = int(N.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+            self.rows.append((mhz, [bool(mask & b) for b in bits]))
+            time.sleep(0.01)
+
+    def _run_smi(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        self.source = "nvidia-smi"
         while not self.stop_flag:
             try:
                 r = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
                                    capture_output=True, text=True, timeout=5)
-                if r.returncode == 0 and r.stdout.strip():
-                    self.rows.append([c.strip() for c in r.stdout.strip().split(",")])
+                c = [v.strip() for v in r.stdout.strip().split(",")] if r.returncode == 0 else []
+                if len(c) >= 6 and c[0].isdigit():
+                    self.max_mhz = int(c[1]) if c[1].isdigit() else self.max_mhz
+                    self.rows.append((int(c[0]), [v.lower().startswith("active") for v in c[2:6]]))
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.05)
+
+    def run(self):
+        try:
+            self._run_nvml()
+        except Exception:
+            if not self.stop_flag:
+                self._run_smi()
 
     def summary(self):
         if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.rows[0][1]) if self.rows[0][1].isdigit() else None,
-                "reasons": reasons, "samples": len(self.rows)}
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0, "source": self.source}
+        sm = sorted(r[0] for r in self.rows)
+        reasons = [n for i, n in enumerate(self.NAMES) if any(r[1][i] for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(self.rows),
+                "source": self.source}
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
