@@ -232,7 +232,7 @@ def run_ours(args, rank, world, local_rank):
         from rtpose_b200.graph import StepGraph
         try:
             lib.launch_count = 0
-            graph = StepGraph(step_body, warmup=0).capture()
+            graph = StepGraph(step_body, warmup=0, high_priority=not os.environ.get("RTP_NO_PRIO")).capture()
             launches_per_step = lib.launch_count
             use_graph = True
             for _ in range(2):  # replays are steps too: keep the schedule moving

@@ -14,8 +14,9 @@ class StepGraph:
     """g = StepGraph(fn, warmup=3); g() replays.  `fn` must read its inputs from fixed device buffers and must not
     synchronise or touch host memory.  Its return value (device tensors) is kept and returned by every replay."""
 
-    def __init__(self, fn, warmup=3):
+    def __init__(self, fn, warmup=3, high_priority=True):
         self.fn = fn
+        self.high_priority = high_priority
         self.graph = None
         self.result = None
         self.warmup = warmup
@@ -29,7 +30,10 @@ class StepGraph:
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
+        # capture on a high-priority stream: kernel nodes inherit it, so when a main-chain kernel and a weight gradient
+        # of the (default-priority) side stream are both ready, the main chain's blocks are dispatched first
+        cs = torch.cuda.Stream(priority=-1) if self.high_priority else None
+        with torch.cuda.graph(g, stream=cs):
             self.result = self.fn()
         self.graph = g
         return self
