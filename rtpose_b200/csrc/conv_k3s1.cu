@@ -458,6 +458,9 @@ Plan make_plan(int K, int NPo, int Z, int X, int Y) {
   if (K % 16 != 0 || NPo % 16 != 0 || NPo < 16 || 3 * NPo > 256) return pl;
   const int N3 = 3 * NPo;
   int KG = (9 * 32 * N3 * 2 <= 56 * 1024) ? 32 : 16;
+  // K = 32 with a wide N (e.g. the paired space-to-depth dgrad, N3 = 192): a single pass needs only ONE weight buffer,
+  // which then stays resident for the whole kernel instead of being re-fetched per (unit, pass)
+  if (KG == 16 && K == 32 && (size_t)9 * 32 * N3 * 2 + 4 * (size_t)4 * (128 + 2 * (Y + 2) + 2) * 16 <= 220 * 1024) KG = 32;
   if (K < KG) KG = K;
   if (K % KG != 0) KG = 16;  // e.g. K = 48 (dgrad of the 45-channel regression conv): three passes of 16
   if (K % KG != 0) return pl;
