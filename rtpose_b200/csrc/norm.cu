@@ -67,13 +67,15 @@ __device__ __forceinline__ int64_t s2d_offset(const P8& s, int C8, int c8, int z
 // Same walk with the loads of U rows issued before any of them is consumed: `ld(offset, z, x, y)` returns the loaded vectors,
 // `use(offset, data)` computes / stores.  Without this the compiler cannot hoist the next row's loads above the current
 // row's store (possible aliasing), and each thread has a single 16-byte load pair in flight.
-template <int U, typename L, typename F>
+// PAIR: a lane handles the two voxels (y, y+1), y even (t.Y even): used by the space-to-depth variants, where the two
+// voxels live in different parity groups of the view and each group is then accessed with unit stride by the warp.
+template <int U, bool PAIR = false, typename L, typename F>
 __device__ __forceinline__ void rows_foreach_u(const P8& t, int row_begin, int row_end, int log2ty, L&& ld, F&& use) {
   const int TY = 1 << log2ty;
   const int ty = threadIdx.x & (TY - 1), tr = threadIdx.x >> log2ty;
   const int rstep = (int)blockDim.x >> log2ty;
   using D = decltype(ld((int64_t)0, 0, 0, 0));
-  for (int y = ty; y < t.Y; y += TY) {
+  for (int y = PAIR ? 2 * ty : ty; y < t.Y; y += PAIR ? 2 * TY : TY) {
     int row = row_begin + tr;
     for (; row + (U - 1) * rstep < row_end; row += U * rstep) {
       int64_t off[U];
@@ -100,6 +102,12 @@ struct Vec2 {
 };
 struct Vec3 {
   uint4 a, b, c;
+};
+struct Vec4 {
+  uint4 a, b, c, d;
+};
+struct Vec6 {
+  uint4 a, b, c, d, e, f;
 };
 __host__ __device__ inline int log2_ty(int Y) {
   int l = 3;
@@ -215,21 +223,29 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(P8 x, int C, int G, const
   if constexpr (S2D) {
     bf16* yb = y.ptr + n * y.n_stride;
     const int C8 = (int)gridDim.y;
-    rows_foreach_u<4>(
-        x, r0, r1, log2_ty(x.Y),
+    const int64_t pstride = (int64_t)C8 * y.c_stride;  // y -> y+1 (y even): next parity group of the view
+    rows_foreach_u<2, true>(
+        x, r0, r1, log2_ty(x.Y / 2),
         [&](int64_t off, int z, int xx, int yy) {
-          Vec2 v;  // .b carries the destination offset inside the view
+          Vec3 v;  // .c carries the destination offset inside the view
           v.a = ldg16(xb + off);
+          v.b = ldg16(xb + off + 8);
           const int64_t so = s2d_offset(y, C8, c8, z, xx, yy);
-          v.b = make_uint4((uint32_t)so, (uint32_t)(so >> 32), 0u, 0u);
+          v.c = make_uint4((uint32_t)so, (uint32_t)(so >> 32), 0u, 0u);
           return v;
         },
-        [&](int64_t, const Vec2& v) {
-          float f[8];
+        [&](int64_t, const Vec3& v) {
+          float f[8], g[8];
           unpack8(v.a, f);
+          unpack8(v.b, g);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) f[i] = fmaf(f[i], a[i], b[i]);
-          stg16(yb + (int64_t)(((uint64_t)v.b.y << 32) | v.b.x), pack8(f));
+          for (int i = 0; i < 8; ++i) {
+            f[i] = fmaf(f[i], a[i], b[i]);
+            g[i] = fmaf(g[i], a[i], b[i]);
+          }
+          const int64_t so = (int64_t)(((uint64_t)v.c.y << 32) | v.c.x);
+          stg16(yb + so, pack8(f));
+          stg16(yb + so + pstride, pack8(g));
         });
   } else {
     bf16* yb = y.ptr + n * y.n_stride + c8 * y.c_stride;
@@ -268,24 +284,44 @@ __global__ void __launch_bounds__(256) gn_bwd_partial_kernel(P8 x, P8 dy, int C,
   float acc[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) acc[i] = 0.f;
-  rows_foreach_u<4>(
-      x, r0, r1, log2_ty(x.Y),
-      [&](int64_t off, int z, int xx, int yy) {
-        Vec2 v;
-        v.a = ldg16(xb + off);
-        v.b = ldg16(db + (S2D ? s2d_offset(dy, C8, c8, z, xx, yy) : off));
-        return v;
-      },
-      [&](int64_t, const Vec2& v) {
-        float f[8], d[8];
-        unpack8(v.a, f);
-        unpack8(v.b, d);
+  auto accum = [&](const uint4& xv, const uint4& dv) {
+    float f[8], d[8];
+    unpack8(xv, f);
+    unpack8(dv, d);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          acc[i] += d[i];
-          acc[8 + i] += d[i] * ((f[i] - mean[i]) * rstd[i]);
-        }
-      });
+    for (int i = 0; i < 8; ++i) {
+      acc[i] += d[i];
+      acc[8 + i] += d[i] * ((f[i] - mean[i]) * rstd[i]);
+    }
+  };
+  if constexpr (S2D) {
+    const int64_t pstride = (int64_t)C8 * dy.c_stride;
+    rows_foreach_u<2, true>(
+        x, r0, r1, log2_ty(x.Y / 2),
+        [&](int64_t off, int z, int xx, int yy) {
+          Vec4 v;
+          v.a = ldg16(xb + off);
+          v.b = ldg16(xb + off + 8);
+          const int64_t so = s2d_offset(dy, C8, c8, z, xx, yy);
+          v.c = ldg16(db + so);
+          v.d = ldg16(db + so + pstride);
+          return v;
+        },
+        [&](int64_t, const Vec4& v) {
+          accum(v.a, v.c);
+          accum(v.b, v.d);
+        });
+  } else {
+    rows_foreach_u<4>(
+        x, r0, r1, log2_ty(x.Y),
+        [&](int64_t off, int, int, int) {
+          Vec2 v;
+          v.a = ldg16(xb + off);
+          v.b = ldg16(db + off);
+          return v;
+        },
+        [&](int64_t, const Vec2& v) { accum(v.a, v.b); });
+  }
   block_reduce<16>(acc, sh, partial + (((size_t)n * x.C8 + c8) * kSlabs + slab) * 16);
 }
 
@@ -339,33 +375,56 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(P8 x, P8 dy, int C, i
   const bf16* db = dy.ptr + n * dy.n_stride + (S2D ? 0 : c8 * dy.c_stride);
   bf16* ob = dx.ptr + n * dx.n_stride + c8 * dx.c_stride;
   const int C8 = (int)gridDim.y;
-  rows_foreach_u<4>(
-      x, r0, r1, log2_ty(x.Y),
-      [&](int64_t off, int z, int xx, int yy) {
-        Vec3 v;
-        v.a = ldg16(xb + off);
-        v.b = ldg16(db + (S2D ? s2d_offset(dy, C8, c8, z, xx, yy) : off));
-        v.c = accumulate ? *reinterpret_cast<const uint4*>(ob + off) : make_uint4(0u, 0u, 0u, 0u);
-        return v;
-      },
-      [&](int64_t off, const Vec3& v) {
-        float f[8], d[8], o[8];
-        unpack8(v.a, f);
-        unpack8(v.b, d);
+  auto emit = [&](int64_t off, const uint4& xv, const uint4& dv, const uint4& old) {
+    float f[8], d[8], o[8];
+    unpack8(xv, f);
+    unpack8(dv, d);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float xh = (f[i] - mean[i]) * rstd[i];
-          o[i] = rstd[i] * (ga[i] * d[i] - k1[i] - xh * k2[i]);
-          if (relu_mask && !(f[i] > 0.f)) o[i] = 0.f;
-        }
-        if (accumulate) {
-          float p[8];
-          unpack8(v.c, p);
+    for (int i = 0; i < 8; ++i) {
+      const float xh = (f[i] - mean[i]) * rstd[i];
+      o[i] = rstd[i] * (ga[i] * d[i] - k1[i] - xh * k2[i]);
+      if (relu_mask && !(f[i] > 0.f)) o[i] = 0.f;
+    }
+    if (accumulate) {
+      float p[8];
+      unpack8(old, p);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) o[i] += p[i];
-        }
-        stg16(ob + off, pack8(o));
-      });
+      for (int i = 0; i < 8; ++i) o[i] += p[i];
+    }
+    stg16(ob + off, pack8(o));
+  };
+  const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+  if constexpr (S2D) {
+    const int64_t pstride = (int64_t)C8 * dy.c_stride;
+    rows_foreach_u<2, true>(
+        x, r0, r1, log2_ty(x.Y / 2),
+        [&](int64_t off, int z, int xx, int yy) {
+          Vec6 v;
+          v.a = ldg16(xb + off);
+          v.b = ldg16(xb + off + 8);
+          const int64_t so = s2d_offset(dy, C8, c8, z, xx, yy);
+          v.c = ldg16(db + so);
+          v.d = ldg16(db + so + pstride);
+          v.e = accumulate ? *reinterpret_cast<const uint4*>(ob + off) : zero4;
+          v.f = accumulate ? *reinterpret_cast<const uint4*>(ob + off + 8) : zero4;
+          return v;
+        },
+        [&](int64_t off, const Vec6& v) {
+          emit(off, v.a, v.c, v.e);
+          emit(off + 8, v.b, v.d, v.f);
+        });
+  } else {
+    rows_foreach_u<4>(
+        x, r0, r1, log2_ty(x.Y),
+        [&](int64_t off, int, int, int) {
+          Vec3 v;
+          v.a = ldg16(xb + off);
+          v.b = ldg16(db + off);
+          v.c = accumulate ? *reinterpret_cast<const uint4*>(ob + off) : zero4;
+          return v;
+        },
+        [&](int64_t off, const Vec3& v) { emit(off, v.a, v.b, v.c); });
+  }
 }
 
 // blocks along the row dimension for the elementwise kernels: every thread gets >= ~8 vectors
