@@ -50,9 +50,33 @@ __global__ void __launch_bounds__(256) fuse_sum_rows_kernel(const __grid_constan
     sx[j] = ac_scale(p.low[j].X, o.X);
     sy[j] = ac_scale(p.low[j].Y, o.Y);
   }
+  // With three low-resolution terms the rows of the two coarsest ones (Y1 + Y2 <= 32 vectors) are blended in ONE pass:
+  // lanes [0, Y1) work on term 1, lanes [Y1, Y1+Y2) on term 2 (the blend costs ~225 instructions per pass whatever the
+  // number of active lanes, and was 52 % of this kernel's instructions).
+  const bool merge12 = p.n_low == 3 && p.low[1].Y + p.low[2].Y <= 32;
+  const int Y1 = p.low[1].Y;
+  const bool second = merge12 && lane >= Y1;
+  const P8& lm = second ? p.low[2] : p.low[1];
+  const int mj = second ? 2 : 1, myl = second ? lane - Y1 : lane;
+  const float msz = second ? sz[2] : sz[1], msx = second ? sx[2] : sx[1];
+  const bf16* mlb = lm.ptr + n * lm.n_stride + c8 * lm.c_stride;
+  const int mZ = lm.Z, mX = lm.X, mXp = lm.Xp, mYp = lm.Yp;
+  const bool mactive = merge12 && myl < lm.Y;
   for (int row = r0 + warp; row < r1; row += 8) {
     const int z = row / o.X, x = row - z * o.X;
-    for (int j = 0; j < p.n_low; ++j) {
+    if (mactive) {
+      const Axis az = ac_axis(z, mZ, msz), ax = ac_axis(x, mX, msx);
+      auto vox = [&](int zz, int xx) { return (((int64_t)zz * mXp + (xx + 1)) * mYp + (myl + 1)) * 8; };
+      float f00[8], f01[8], f10[8], f11[8];
+      unpack8(ldg16(mlb + vox(az.i0, ax.i0)), f00);
+      unpack8(ldg16(mlb + vox(az.i0, ax.i1)), f01);
+      unpack8(ldg16(mlb + vox(az.i1, ax.i0)), f10);
+      unpack8(ldg16(mlb + vox(az.i1, ax.i1)), f11);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        srow[warp][mj][myl][i] = az.w0 * (ax.w0 * f00[i] + ax.w1 * f01[i]) + az.w1 * (ax.w0 * f10[i] + ax.w1 * f11[i]);
+    }
+    for (int j = 0; j < (merge12 ? 1 : p.n_low); ++j) {
       const P8& l = p.low[j];
       const Axis az = ac_axis(z, l.Z, sz[j]), ax = ac_axis(x, l.X, sx[j]);
       const bf16* lb = l.ptr + n * l.n_stride + c8 * l.c_stride;
