@@ -97,6 +97,10 @@ typedef struct {
   int32_t accumulate; /* out += result (read-modify-write) */
 } rtp_conv_desc;
 int rtp_conv(const rtp_conv_desc* d, void* stream);
+/* Several descriptors in ONE launch: descs[0..n) (n <= 8) must agree in everything but the tap list and the row grid /
+ * offsets.  Used for the 8 output-parity classes of a stride-2 dgrad, which at low resolution are each a handful of
+ * latency-bound CTAs. */
+int rtp_conv_multi(const rtp_conv_desc* descs, int32_t n, void* stream);
 
 /* Plane-streaming 3x3x3 stride-1 conv (the dominant shape): the z-taps are stacked into GEMM N
  * (N = 3*NPo), accumulators for all output planes stay resident in TMEM, input planes are streamed once

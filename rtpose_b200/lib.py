@@ -62,6 +62,7 @@ PROTOTYPES = {
                                   _vp, _vp]),
     "rtp_weight_pack": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "rtp_conv": (C.c_int, [C.POINTER(ConvDesc), _vp]),
+    "rtp_conv_multi": (C.c_int, [C.POINTER(ConvDesc), _i32, _vp]),
     "rtp_weight_pack_k3s1": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "rtp_conv_k3s1": (C.c_int, [C.POINTER(ConvK3S1Desc), _vp]),
     "rtp_conv_k3s1_smem_bytes": (C.c_int64, [_i32, _i32, _i32, _i32, _i32]),
@@ -160,7 +161,7 @@ LAUNCHES = {"rtp_pack_ncdhw": 1, "rtp_unpack_ncdhw": 1, "rtp_ingest_pack": 1, "r
             "rtp_stem_bwd": 2, "rtp_head_loss": 2, "rtp_decode": 1, "rtp_scale_f32": 1, "rtp_dcn_fwd": 1,
             "rtp_dcn_bwd_input": 1, "rtp_dcn_bwd_weight": 1, "rtp_adam_step": 2, "rtp_adam_step_dev": 2,
             "rtp_assign_targets": 2, "rtp_wgrad_k3s1": 1, "rtp_wgrad_k3s1_reduce": 1, "rtp_conv_pw": 1, "rtp_gn_apply_s2d": 1, "rtp_gn_bwd_reduce_s2d": 2,
-            "rtp_gn_bwd_apply_s2d": 2, "rtp_conv_k3s1_stat_finalize": 1}
+            "rtp_gn_bwd_apply_s2d": 2, "rtp_conv_k3s1_stat_finalize": 1, "rtp_conv_multi": 1}
 launch_count = 0
 
 

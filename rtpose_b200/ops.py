@@ -242,6 +242,33 @@ def conv(x, wpack, KP, NP, out, taps, rows, IS=1, OS=1, off=(0, 0, 0), bias=None
     return out
 
 
+def conv_multi(x, wpack, KP, NP, out, classes, IS=1, OS=1, mask=None, accumulate=False, real=None):
+    """Several (taps, rows, offset) classes of one generic conv in ONE launch (rtp_conv_multi): the output-parity classes
+    of a stride-2 dgrad."""
+    n = len(classes)
+    arr = (lib.ConvDesc * n)()
+    flops = 0.0
+    rc = real or (KP, NP)
+    for d, (taps, rows, off) in zip(arr, classes):
+        d.inp, d.out = x.struct(), out.struct()
+        d.res = lib.NULL_P8
+        d.mask = mask.struct() if mask is not None else lib.NULL_P8
+        d.w = wpack.data_ptr()
+        d.bias = None
+        d.Cin, d.NP, d.out_c8 = KP, NP, out.C8
+        _fill_taps(d, taps)
+        d.RZ, d.RX, d.RY = rows
+        d.IS, d.OS = IS, OS
+        d.oz0, d.ox0, d.oy0 = off
+        d.relu, d.accumulate = 0, int(accumulate)
+        flops += 2.0 * x.N * rows[0] * rows[1] * rows[2] * rc[0] * rc[1] * len(taps)
+    key = ("conv_generic", rc[0], rc[1], sum(len(c[0]) for c in classes), IS, OS, classes[-1][1])
+    ev = _prof_begin(key)
+    lib.call("rtp_conv_multi", arr, n, _stream())
+    _prof_end(key, ev, flops)
+    return out
+
+
 def pad_bias(b, NP):
     if b is None:
         return None
@@ -418,15 +445,14 @@ def conv_dgrad(packs, dy, w, stride, dx, mask=None, accumulate=False, ci0=0, ci_
     if stride == 1:
         return conv(dy, wp, KP, NP, dx, taps_dgrad_s1(k), (dx.Z, dx.X, dx.Y), mask=mask, accumulate=accumulate, real=real)
     assert stride == 2 and k == 3
+    classes = []
     for pz in range(2):
         for px in range(2):
             for py in range(2):
                 rows = ((dx.Z - pz + 1) // 2, (dx.X - px + 1) // 2, (dx.Y - py + 1) // 2)
-                if min(rows) <= 0:
-                    continue
-                conv(dy, wp, KP, NP, dx, taps_dgrad_s2(pz, px, py), rows, IS=1, OS=2, off=(pz, px, py), mask=mask,
-                     accumulate=accumulate, real=real)
-    return dx
+                if min(rows) > 0:
+                    classes.append((taps_dgrad_s2(pz, px, py), rows, (pz, px, py)))
+    return conv_multi(dy, wp, KP, NP, dx, classes, IS=1, OS=2, mask=mask, accumulate=accumulate, real=real)
 
 
 _NSM = None
