@@ -199,6 +199,8 @@ int64_t rtp_gn_workspace_bytes(int32_t N, int32_t C8);
 int rtp_gn_sums(rtp_p8 x, int32_t C, float* sums, float* workspace, void* stream);
 int rtp_gn_finalize(const float* sums, int32_t N, int32_t C, int32_t G, int64_t voxels, float eps, float* stats,
                     void* stream);
+/* rtp_gn_sums + rtp_gn_finalize in two launches instead of three (same arithmetic, C <= 256). */
+int rtp_gn_stats(rtp_p8 x, int32_t C, int32_t G, float eps, float* stats, float* workspace, void* stream);
 /* y = bf16((x - mean) * rstd * gamma + beta), pads stay zero */
 int rtp_gn_apply(rtp_p8 x, int32_t C, int32_t G, const float* stats, const float* gamma, const float* beta, rtp_p8 y,
                  void* stream);

@@ -343,10 +343,25 @@ __global__ void gn_param_grad_kernel(const float* __restrict__ red, int N, int C
 template <bool S2D>
 __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(P8 x, P8 dy, int C, int G, const float* __restrict__ stats,
                                                            const float* __restrict__ red, const float* __restrict__ gamma,
-                                                           P8 dx, int accumulate, int relu_mask) {
+                                                           P8 dx, int accumulate, int relu_mask, float* __restrict__ dgamma,
+                                                           float* __restrict__ dbeta, int accumulate_params) {
   __shared__ float s_k[5 * 8];
   const int c8 = blockIdx.y, n = blockIdx.z;
   const int cpg = C / G;
+  // the parameter gradients of this chunk (sum over samples of `red`, same order as gn_param_grad_kernel) ride along in
+  // one block instead of costing a launch of their own
+  if (dgamma && blockIdx.x == 0 && n == 0 && threadIdx.x >= 32 && threadIdx.x < 40) {
+    const int c = c8 * 8 + (int)threadIdx.x - 32;
+    if (c < C) {
+      double a = 0, b = 0;
+      for (int nn = 0; nn < x.N; ++nn) {
+        a += red[((size_t)nn * C + c) * 2];
+        b += red[((size_t)nn * C + c) * 2 + 1];
+      }
+      dbeta[c] = accumulate_params ? dbeta[c] + (float)a : (float)a;
+      dgamma[c] = accumulate_params ? dgamma[c] + (float)b : (float)b;
+    }
+  }
   if (threadIdx.x < 8) {  // per-(sample, chunk) constants, computed once per block
     const int64_t V = (int64_t)x.Z * x.X * x.Y;
     const float inv_m = 1.0f / ((float)V * (float)cpg);
@@ -445,6 +460,50 @@ extern "C" int rtp_gn_sums(rtp_p8 x, int32_t C, float* sums, float* workspace, v
   RTP_LAUNCH_CHECK();
 }
 
+namespace {
+// slab partials -> (mean, rstd) per (sample, group) in one step: thread c sums its channel's slabs (fp64, fixed order),
+// then thread g combines the channels of its group — gn_sums_final + gn_finalize without the second launch
+__global__ void __launch_bounds__(256) gn_stats_final_kernel(const float* __restrict__ partial, int C8, int C, int G, double count,
+                                                             float eps, float* __restrict__ stats) {
+  __shared__ double ss[256], sq[256];
+  const int n = blockIdx.x, c = threadIdx.x;
+  if (c < C) {
+    const float* p = partial + ((size_t)n * C8 + (c >> 3)) * kSlabs * 16;
+    const int j = c & 7;
+    double s = 0, q = 0;
+    for (int k = 0; k < kSlabs; ++k) {
+      s += p[k * 16 + j];
+      q += p[k * 16 + 8 + j];
+    }
+    ss[c] = (double)(float)s;  // rounded like the fp32 `sums` the two-kernel path hands over
+    sq[c] = (double)(float)q;
+  }
+  __syncthreads();
+  if (c < G) {
+    const int cpg = C / G;
+    double s = 0, q = 0;
+    for (int cc = c * cpg; cc < (c + 1) * cpg; ++cc) {
+      s += ss[cc];
+      q += sq[cc];
+    }
+    const double m = count * cpg, mean = s / m;
+    double var = q / m - mean * mean;
+    if (var < 0) var = 0;
+    stats[((size_t)n * G + c) * 2] = (float)mean;
+    stats[((size_t)n * G + c) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+}
+}  // namespace
+
+extern "C" int rtp_gn_stats(rtp_p8 x, int32_t C, int32_t G, float eps, float* stats, float* workspace, void* stream) {
+  RTP_CHECK_ARG(x.ptr && stats && workspace && C > 0 && C <= x.C8 * 8 && C <= 256 && G > 0 && C % G == 0, "rtp_gn_stats: bad args");
+  P8 t(x);
+  t.C8 = ceil_div(C, 8);
+  gn_sums_partial_kernel<<<dim3(kSlabs, t.C8, t.N), 256, 0, (cudaStream_t)stream>>>(t, workspace);
+  gn_stats_final_kernel<<<t.N, 256, 0, (cudaStream_t)stream>>>(workspace, t.C8, C, G, (double)((int64_t)x.Z * x.X * x.Y), eps, stats);
+  RTP_LAUNCH_CHECK();
+}
+
 extern "C" int rtp_gn_finalize(const float* sums, int32_t N, int32_t C, int32_t G, int64_t voxels, float eps, float* stats,
                                void* stream) {
   RTP_CHECK_ARG(sums && stats && N > 0 && C > 0 && G > 0 && C % G == 0 && voxels > 0, "rtp_gn_finalize: bad args");
@@ -505,17 +564,20 @@ int gn_bwd_apply_impl(rtp_p8 x, rtp_p8 dy, int32_t C, int32_t G, const float* st
     RTP_CHECK_ARG(s2d_view_of(dy, x, C), "rtp_gn_bwd_apply_s2d: dy must be the space-to-depth view of x's grid");
   else
     RTP_CHECK_ARG(C <= dy.C8 * 8, "rtp_gn_bwd_apply: bad C/G");
-  if (dgamma && dbeta)
+  if (dgamma && dbeta && !dx.ptr)
     gn_param_grad_kernel<<<ceil_div(C, 64), 64, 0, (cudaStream_t)stream>>>(red, x.N, C, dgamma, dbeta, accumulate_params);
   if (dx.ptr) {
+    float* dg = (dgamma && dbeta) ? dgamma : nullptr;
     RTP_CHECK_ARG(x.N == dx.N && x.Z == dx.Z && x.X == dx.X && x.Y == dx.Y && C <= dx.C8 * 8, "rtp_gn_bwd_apply: dx geometry mismatch");
     P8 tx(x), td(dy), to(dx);
     const int64_t V = (int64_t)x.Z * x.X * x.Y;
     const dim3 grid(ew_blocks(V), ceil_div(C, 8), x.N);
     if (s2d)
-      gn_bwd_apply_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(tx, td, C, G, stats, red, gamma, to, accumulate_dx, relu_mask);
+      gn_bwd_apply_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(tx, td, C, G, stats, red, gamma, to, accumulate_dx, relu_mask, dg, dbeta,
+                                                                         accumulate_params);
     else
-      gn_bwd_apply_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(tx, td, C, G, stats, red, gamma, to, accumulate_dx, relu_mask);
+      gn_bwd_apply_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(tx, td, C, G, stats, red, gamma, to, accumulate_dx, relu_mask, dg, dbeta,
+                                                                          accumulate_params);
   }
   RTP_LAUNCH_CHECK();
 }

@@ -592,8 +592,11 @@ def gn_ws(x):
 
 
 def gn_stats(x, G, eps=1e-5):
-    sums = torch.empty((x.N, x.C, 2), dtype=torch.float32, device=x.buf.device)
     stats = torch.empty((x.N, G, 2), dtype=torch.float32, device=x.buf.device)
+    if x.C <= 256:
+        lib.call("rtp_gn_stats", x.struct(), x.C, G, eps, stats.data_ptr(), gn_ws(x).data_ptr(), _stream())
+        return stats
+    sums = torch.empty((x.N, x.C, 2), dtype=torch.float32, device=x.buf.device)
     lib.call("rtp_gn_sums", x.struct(), x.C, sums.data_ptr(), gn_ws(x).data_ptr(), _stream())
     lib.call("rtp_gn_finalize", sums.data_ptr(), x.N, x.C, G, x.voxels, eps, stats.data_ptr(), _stream())
     return stats
