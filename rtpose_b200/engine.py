@@ -8,6 +8,8 @@ static, so no autograd engine is needed; `autograd_bridge.py` exposes it to torc
 Gradient convention: for a tensor that is the output of a ReLU, `.grad` holds the gradient w.r.t. the *pre-ReLU*
 value; every kernel that writes into such a gradient applies the (t > 0) mask itself.
 """
+import contextlib
+
 import torch
 
 from . import lib, ops
@@ -42,6 +44,7 @@ class Engine:
         # the branches of an HR module are independent between two fuse layers: run branch b >= 1 on its own stream
         # so the small low-resolution kernels fill the gaps of the full-resolution branch (forward and backward)
         self.parallel_branches = True
+        self.parallel_fuse = True
         self._bstreams = {}
 
     # ------------------------------------------------------------------ helpers
@@ -178,7 +181,33 @@ class Engine:
         """HighResolutionModule.forward (hr_util/hr3d.py:205-229)."""
         xs = self._branches(xs, prefix, nb, train)
         outs = []
-        for i in (range(nb) if outputs is None else outputs):
+        idx = list(range(nb) if outputs is None else outputs)
+        # The fuse computations of the output branches read the same inputs and are independent of each other: in the
+        # FORWARD pass output i >= 1 runs on branch stream i (forked here, joined below), so e.g. the element-wise
+        # fuse_sum of output 0 overlaps the stride-2 convs of the others.  (Their backward closures stay on the main
+        # stream: they accumulate into the shared input gradients in program order.)
+        par = self.parallel_fuse and self.parallel_branches and len(idx) > 1
+        if par:
+            dev = xs[0].buf.device
+            main = torch.cuda.current_stream(dev)
+            for x in xs:  # statistics every fuse conv may ask for, computed once, before the fork
+                if id(x) not in self.stats_cache:
+                    self.stats_cache[id(x)] = ops.gn_stats(x, 8 if x.C >= 8 else 1)
+            used = {i: self._branch_stream(i, dev) for i in idx if i > 0}
+            for st in used.values():  # fork everything first: a later wait_stream(main) would also wait for output 0
+                st.wait_stream(main)
+        for i in idx:
+            st = used.get(i) if par else None
+            with (torch.cuda.stream(st) if st is not None else contextlib.nullcontext()):
+                y = self._fuse_output(xs, prefix, nb, i, train)
+            outs.append(y)
+        if par:
+            for st in used.values():
+                main.wait_stream(st)
+        return outs
+
+    def _fuse_output(self, xs, prefix, nb, i, train):
+        if True:
             same, low = [], []
             for j in range(nb):
                 if j == i:
@@ -196,8 +225,7 @@ class Engine:
             y.relu_out = True
             if train:
                 self.tape.append(self._fuse_bwd(y, same, low))
-            outs.append(y)
-        return outs
+            return y
 
     def _branch_stream(self, b, device):
         st = self._bstreams.get((b, str(device)))
@@ -222,12 +250,13 @@ class Engine:
                     cur.wait_stream(st)
             self.tape.append(join_bwd)
         outs = [None] * nb
+        for st in side:  # fork BEFORE branch 0 is issued: a later wait_stream(main) would also wait for branch 0
+            st.wait_stream(main)
         for b in range(nb):
             if b == 0:
                 outs[0] = self.res_block(xs[0], "%s.branches.0.0" % prefix, train)
                 continue
             st = side[b - 1]
-            st.wait_stream(main)
             t0 = len(self.tape)
             with torch.cuda.stream(st):
                 outs[b] = self.res_block(xs[b], "%s.branches.%d.0" % (prefix, b), train)
