@@ -45,6 +45,8 @@ class Engine:
         # so the small low-resolution kernels fill the gaps of the full-resolution branch (forward and backward)
         self.parallel_branches = True
         self.parallel_fuse = True
+        self.parallel_fuse_bwd = False  # measured: no gain (the ordered accumulation into shared gradients serialises it)
+        self._ordered_grads = False  # set while backward closures may run on several streams
         self._bstreams = {}
 
     # ------------------------------------------------------------------ helpers
@@ -53,11 +55,20 @@ class Engine:
         return self.pool.get(like.N, like.C if C is None else C, Z, Y, X, like.buf.device)
 
     def _grad_of(self, t):
-        """Returns (grad tensor, accumulate flag) for a writer into t.grad."""
+        """Returns (grad tensor, accumulate flag) for a writer into t.grad.  Writers on different streams are chained in
+        program order: the current stream first waits for the previous writer's event; call _wrote(t) after the write."""
+        if t.grad_ev is not None:
+            torch.cuda.current_stream(t.buf.device).wait_event(t.grad_ev)
         if t.grad is None:
             t.grad = self.new(t)
             return t.grad, False
         return t.grad, True
+
+    def _wrote(self, t):
+        if self._ordered_grads:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(t.buf.device))
+            t.grad_ev = ev
 
     def _pgrad(self, name):
         """fp32 gradient tensor of parameter `name` and whether to accumulate into it."""
@@ -98,6 +109,7 @@ class Engine:
                 if res is not None and res_needs_grad:
                     g, acc = self._grad_of(res)
                     ops.grad_add(dy, g, mask=res if res.relu_out else None, accumulate=acc)
+                    self._wrote(res)
                 gw, accw = self._pgrad(conv + ".weight")
                 ops.conv_wgrad_async(xn, dy, k, stride, gw, accumulate=accw)
                 red = None
@@ -112,6 +124,8 @@ class Engine:
                 else:
                     gx, accx = None, False
                 ops.gn_backward(x, dxn, G, stats, gamma, gg, gb, accg, gx, accx, red=red)
+                if gx is not None:
+                    self._wrote(x)
             self.tape.append(bwd)
         return y
 
@@ -135,6 +149,7 @@ class Engine:
                 if res is not None and res_needs_grad:
                     g, acc = self._grad_of(res)
                     ops.grad_add(dy, g, mask=res if res.relu_out else None, accumulate=acc)
+                    self._wrote(res)
                 gw, accw = self._pgrad(conv + ".weight")
                 ops.on_wgrad_stream(xs, lambda: ops.conv_wgrad_s2d(xs, dy, x.C, gw, accumulate=accw))
                 dxs = ops.conv_dgrad(self.packs, dy, we, 1, self.pool.get(x.N, 8 * x.C, x.Z // 2, x.Y // 2, x.X // 2, dev),
@@ -146,6 +161,8 @@ class Engine:
                 else:
                     gx, accx = None, False
                 ops.gn_backward(x, dxs, G, stats, gamma, gg, gb, accg, gx, accx, s2d=True)
+                if gx is not None:
+                    self._wrote(x)
             self.tape.append(bwd)
         return y
 
@@ -196,14 +213,32 @@ class Engine:
             used = {i: self._branch_stream(i, dev) for i in idx if i > 0}
             for st in used.values():  # fork everything first: a later wait_stream(main) would also wait for output 0
                 st.wait_stream(main)
+            if train and self.parallel_fuse_bwd:  # runs LAST among the fuse closures in backward
+                def join_bwd():
+                    cur = torch.cuda.current_stream(dev)
+                    for st in used.values():
+                        cur.wait_stream(st)
+                self.tape.append(join_bwd)
         for i in idx:
             st = used.get(i) if par else None
+            t0 = len(self.tape)
             with (torch.cuda.stream(st) if st is not None else contextlib.nullcontext()):
                 y = self._fuse_output(xs, prefix, nb, i, train)
+            if st is not None and train and self.parallel_fuse_bwd:
+                # backward of output i's fuse layers on the same stream; accumulation into the shared input gradients
+                # is chained in program order by _grad_of / _wrote
+                for k in range(t0, len(self.tape)):
+                    self.tape[k] = self._on_stream(self.tape[k], st)
             outs.append(y)
         if par:
             for st in used.values():
                 main.wait_stream(st)
+            if train and self.parallel_fuse_bwd:  # runs FIRST: the side streams wait for the gradients of the outputs
+                def fork_bwd():
+                    cur = torch.cuda.current_stream(dev)
+                    for st in used.values():
+                        st.wait_stream(cur)
+                self.tape.append(fork_bwd)
         return outs
 
     def _fuse_output(self, xs, prefix, nb, i, train):
@@ -290,9 +325,11 @@ class Engine:
                 else:
                     gt, acc = self._grad_of(t)
                     ops.grad_add(g, gt, mask=t if t.relu_out else None, accumulate=acc)
+                    self._wrote(t)
             for t in low:
                 gt, acc = self._grad_of(t)
                 ops.upsample_bwd(g, gt, accumulate=acc)
+                self._wrote(t)
         return bwd
 
     # ------------------------------------------------------------------ network
@@ -340,6 +377,7 @@ class Engine:
                     gy, acc = self._grad_of(y)
                     ops.conv_dgrad(self.packs, gt, w, 1, gy, mask=y if y.relu_out else None, accumulate=acc, ci0=ci0,
                                    ci_n=y.C)
+                    self._wrote(y)
             self.tape.append(bwd)
         return f
 
@@ -392,6 +430,7 @@ class Engine:
                 gf, accf = self._grad_of(f)
                 ops.conv_dgrad(self.packs, tg, w0, 1, gf, mask=f if f.relu_out else None, accumulate=accf, key=wkey,
                                version=wver)
+                self._wrote(f)
             self.tape.append(bwd)
         return hm, reg
 
@@ -439,6 +478,7 @@ class Engine:
         """Runs the tape in reverse; `grads`: dict name -> fp32 tensor receiving d loss / d param."""
         self.grads = grads
         self._touched = set()
+        self._ordered_grads = bool(self.parallel_fuse_bwd and self.parallel_fuse and self.parallel_branches)
         for fn in reversed(self.tape):
             fn()
         self.tape = []

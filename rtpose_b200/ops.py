@@ -30,6 +30,7 @@ class BufferPool:
             t.C = Cc
             t.relu_out = False
             t.grad = None
+            t.grad_ev = None
         else:
             t = P8(N, Cc, Z, Y, X, device=device)
         t._keep = key
@@ -39,6 +40,7 @@ class BufferPool:
     def release_all(self):
         for t in self.live:
             t.grad = None
+            t.grad_ev = None
             self.free.setdefault(t._keep, []).append(t)
         self.live = []
 
