@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "librtpose_b200.so")
+LIB_PATH = os.environ.get("RTPOSE_B200_LIB") or os.path.join(HERE, "librtpose_b200.so")  # override: A/B runs of two builds
 MAX_TAPS = 27
 GUARD_BYTES = 8192
 
