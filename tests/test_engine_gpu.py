@@ -164,3 +164,31 @@ def test_inference_matches_training_forward():
     a, _, _ = run_engine(eng, params, x, None, train=False)
     b, _, _ = run_engine(eng, params, x, tgt, train=True)
     assert torch.equal(a["hm"], b["hm"]) and torch.equal(a["reg"], b["reg"])
+
+
+def test_stream_schedules_are_bitwise_equivalent():
+    """Every execution schedule of the engine — one stream, branch / fuse / weight-gradient side streams, and the optional
+    stream-parallel fuse backward with event-ordered gradient accumulation — produces bit-identical outputs, loss and
+    gradients (all reductions have a fixed order; accumulation into shared gradients follows program order)."""
+    from rtpose_b200 import ops
+    cfg, grid, batch = "hr3d_one_hm_doppler", (8, 16, 24), 2
+    x, poses, tgt = G.make_example(cfg, batch, grid, seed=33)
+    results = []
+    for branches, fuse, fuse_bwd, async_wgrad in ((False, False, False, False), (True, True, False, True),
+                                                  (True, True, True, True)):
+        eng, params = build_engine(cfg)
+        eng.parallel_branches, eng.parallel_fuse, eng.parallel_fuse_bwd = branches, fuse, fuse_bwd
+        old = ops.ASYNC_WGRAD
+        ops.ASYNC_WGRAD = async_wgrad
+        try:
+            out, _, _ = run_engine(eng, params, x, tgt, True)
+        finally:
+            ops.ASYNC_WGRAD = old
+        results.append(out)
+    ref = results[0]
+    for out in results[1:]:
+        assert torch.equal(out["hm"], ref["hm"]) and torch.equal(out["reg"], ref["reg"])
+        assert torch.equal(out["loss"], ref["loss"])
+        assert set(out["grads"]) == set(ref["grads"])
+        for k in ref["grads"]:
+            assert torch.equal(out["grads"][k], ref["grads"][k]), k
