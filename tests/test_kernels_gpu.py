@@ -564,3 +564,35 @@ def test_stride2_conv_through_space_to_depth_view(ctx, case):
     close(dx.to_ncdhw(), x.grad, tol=2e-2, what="s2d dx")
     close(dg, gamma.grad, tol=2e-2, what="s2d dgamma")
     close(db, beta.grad, tol=2e-2, what="s2d dbeta")
+
+
+def test_fused_launch_variants_match_their_multi_launch_forms(ctx):
+    """rtp_gn_stats == rtp_gn_sums + rtp_gn_finalize and rtp_conv_multi == one rtp_conv per parity class, bit for bit."""
+    from rtpose_b200 import lib, ops
+    from rtpose_b200.p8 import P8, _stream
+    x = to_p8(rnd(3, 64, 4, 10, 12, seed=90))
+    a = ops.gn_stats(x, 8)
+    sums = torch.empty((x.N, x.C, 2), dtype=torch.float32, device="cuda")
+    b = torch.empty((x.N, 8, 2), dtype=torch.float32, device="cuda")
+    lib.call("rtp_gn_sums", x.struct(), x.C, sums.data_ptr(), ops.gn_ws(x).data_ptr(), _stream())
+    lib.call("rtp_gn_finalize", sums.data_ptr(), x.N, x.C, 8, x.voxels, 1e-5, b.data_ptr(), _stream())
+    torch.cuda.synchronize()
+    assert torch.equal(a, b)
+    # stride-2 dgrad through the gather kernel: 8 parity classes in one launch vs one launch each
+    dy = to_p8(rnd(2, 32, 2, 5, 6, seed=91))
+    w = rnd(32, 32, 3, 3, 3, seed=92, scale=0.1).cuda()
+    old = ops.USE_S2D
+    ops.USE_S2D = False
+    try:
+        d_multi = ops.conv_dgrad(ctx, dy, w, 2, P8(2, 32, 4, 10, 12))
+    finally:
+        ops.USE_S2D = old
+    wp, KP, NP = ctx.get(w, 1)
+    d_single = P8(2, 32, 4, 10, 12)
+    for pz in range(2):
+        for px in range(2):
+            for py in range(2):
+                rows = ((4 - pz + 1) // 2, (12 - px + 1) // 2, (10 - py + 1) // 2)
+                ops.conv(dy, wp, KP, NP, d_single, ops.taps_dgrad_s2(pz, px, py), rows, IS=1, OS=2, off=(pz, px, py))
+    torch.cuda.synchronize()
+    assert torch.equal(d_multi.to_ncdhw(), d_single.to_ncdhw())
