@@ -267,7 +267,8 @@ def run_ours(args, rank, world, local_rank):
     graph, async_was, par_was = None, ops.ASYNC_WGRAD, eng.parallel_branches
     ops.ASYNC_WGRAD, eng.parallel_branches = False, False
     step()
-    ops.PROFILE = {"_only": {"conv_generic", "conv_k3s1", "conv_pw", "wgrad_generic", "wgrad_k3s1"}}
+    EW = {"gn_apply", "gn_backward", "fuse_sum", "upsample_bwd", "grad_add"}  # these record algorithmic bytes
+    ops.PROFILE = {"_only": {"conv_generic", "conv_k3s1", "conv_pw", "wgrad_generic", "wgrad_k3s1"} | EW}
     p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     nprof = min(args.steps, 5)
     p0.record()
@@ -286,13 +287,19 @@ def run_ours(args, rank, world, local_rank):
     value = world * B / (ms * 1e-3)
 
     # ---- roofline of the dominant kernel family (most total time among the profiled conv kernels)
-    pk_burst, pk_sust, hbm, src = peaks()
-    fam = {}
+    pk_burst, pk_sust, hbm_peak, src = peaks()
+    fam, ew = {}, {}
     for key, evs in prof.items():
         if key == "_only":
             continue
         tms = [s.elapsed_time(e) for s, e, _ in evs]
+        if key[0] in EW:  # HBM-bound kernels: per function, algorithmic bytes / time vs the measured copy bandwidth
+            a = ew.setdefault(key[0], [0.0, 0, 0.0])
+            a[0] += sum(tms); a[1] += len(tms); a[2] += sum(f for _, _, f in evs)
+            continue
         fam[key] = (sum(tms), len(tms), sum(f for _, _, f in evs))
+    hbm_kernels = {k: {"GBps": round(v[2] / (v[0] * 1e-3) / 1e9, 1), "frac_of_hbm_peak": round(v[2] / (v[0] * 1e-3) / 1e9 / hbm_peak, 3),
+                       "launches_per_step": v[1] // nprof, "share_of_step": round(v[0] / (ms_serial * nprof), 3)} for k, v in ew.items()}
     roof, top = None, []
     if fam:
         for key, (tt, n, fl) in sorted(fam.items(), key=lambda kv: -kv[1][0])[:16]:
@@ -319,6 +326,7 @@ def run_ours(args, rank, world, local_rank):
                           "timed region (%.2f ms/step; the timed region itself replays a CUDA graph with weight gradients on a "
                           "side stream, %.2f ms/step)" % (nprof, ms_serial, ms),
                 "traffic_source": "profiles/r01_ncu_traffic.json (ncu --set full, bytes per launch)" if traffic else None,
+                "hbm_bound_kernels": hbm_kernels, "hbm_peak_GBps": hbm_peak,
                 "other_tensor_kernels": {k: {"tflops": round(v[2] / (v[0] * 1e-3) / 1e12, 1), "frac": round(v[2] / (v[0] * 1e-3) / 1e12 / pk_sust, 3),
                                              "share_of_step": round(v[0] / (ms_serial * nprof), 3)} for k, v in by_kernel.items() if k != kname}}
 

@@ -220,6 +220,12 @@ def _prof_end(key, ev, flops):
     PROFILE.setdefault(key, []).append((ev, end, flops))
 
 
+def _tbytes(t, C=None):
+    """Algorithmic bytes of the real voxels of a P8 tensor (bf16, whole 8-channel chunks are moved)."""
+    c8 = ((t.C if C is None else C) + 7) // 8
+    return 16.0 * t.N * c8 * t.voxels
+
+
 # ------------------------------------------------------------------------------------------------ conv
 def conv(x, wpack, KP, NP, out, taps, rows, IS=1, OS=1, off=(0, 0, 0), bias=None, res=None, mask=None, relu=False,
          accumulate=False, real=None):
@@ -605,8 +611,11 @@ def gn_stats(x, G, eps=1e-5):
 
 
 def gn_apply(x, G, stats, gamma, beta, out):
+    key = ("gn_apply", x.C, x.C, 0, 1, 1, (x.Z, x.X, x.Y))
+    ev = _prof_begin(key)
     lib.call("rtp_gn_apply", x.struct(), x.C, G, stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), out.struct(),
              _stream())
+    _prof_end(key, ev, 2 * _tbytes(x))  # element-wise kernels record algorithmic BYTES in the flops slot
     return out
 
 
@@ -710,6 +719,8 @@ def gn_backward(x, dxn, G, stats, gamma, dgamma, dbeta, acc_params, dx, acc_dx, 
     """red: the [N][C][2] reductions when the conv that produced dxn already computed them (conv_dgrad(stat=...)).
     s2d: dxn is the gradient of the space-to-depth view of GN(x)."""
     sfx = "_s2d" if s2d else ""
+    key = ("gn_backward", x.C, x.C, 0 if red is None else 1, 1, 1, (x.Z, x.X, x.Y))
+    ev = _prof_begin(key)
     if red is None:
         red = torch.empty((x.N, x.C, 2), dtype=torch.float32, device=x.buf.device)
         lib.call("rtp_gn_bwd_reduce" + sfx, x.struct(), dxn.struct(), x.C, G, stats.data_ptr(), red.data_ptr(),
@@ -717,6 +728,9 @@ def gn_backward(x, dxn, G, stats, gamma, dgamma, dbeta, acc_params, dx, acc_dx, 
     lib.call("rtp_gn_bwd_apply" + sfx, x.struct(), dxn.struct(), x.C, G, stats.data_ptr(), red.data_ptr(), gamma.data_ptr(),
              dgamma.data_ptr(), dbeta.data_ptr(), int(acc_params), dx.struct() if dx is not None else lib.NULL_P8,
              int(acc_dx), int(x.relu_out), _stream())
+    # bytes: (reduction pass: x + dxn) + (apply pass: x + dxn read, dx written [+ read when accumulating])
+    nb = (0 if key[3] else 2) + (0 if dx is None else 3 + (1 if acc_dx else 0))
+    _prof_end(key, ev, nb * _tbytes(x))
 
 
 # ------------------------------------------------------------------------------------------------ fuse / misc
@@ -730,18 +744,27 @@ def fuse_sum(out, same, low, bias=None, relu=False):
         d.low[i] = t.struct()
     d.bias = bias.data_ptr() if bias is not None else None
     d.relu = int(relu)
+    key = ("fuse_sum", out.C, out.C, len(same) + len(low), 1, 1, (out.Z, out.X, out.Y))
+    ev = _prof_begin(key)
     lib.call("rtp_fuse_sum", C.byref(d), _stream())
+    _prof_end(key, ev, _tbytes(out) * (1 + len(same)) + sum(_tbytes(t, out.C) for t in low))
     return out
 
 
 def upsample_bwd(dout, dlow, accumulate=False):
     ws = workspace(lib.load().rtp_upsample_bwd_workspace_bytes(dout.struct(), dlow.struct(), dlow.C), dout.buf.device, "upbwd")
+    key = ("upsample_bwd", dlow.C, dlow.C, 0, 1, 1, (dout.Z, dout.X, dout.Y))
+    ev = _prof_begin(key)
     lib.call("rtp_upsample_bwd", dout.struct(), dlow.struct(), dlow.C, int(accumulate), ws.data_ptr(), _stream())
+    _prof_end(key, ev, _tbytes(dout, dlow.C) + _tbytes(dlow) * (2 if accumulate else 1))
 
 
 def grad_add(src, dst, mask=None, accumulate=False):
+    key = ("grad_add", dst.C, dst.C, 0, 1, 1, (dst.Z, dst.X, dst.Y))
+    ev = _prof_begin(key)
     lib.call("rtp_grad_add", src.struct(), mask.struct() if mask is not None else lib.NULL_P8, dst.struct(), dst.C,
              int(accumulate), _stream())
+    _prof_end(key, ev, _tbytes(dst) * (2 + (1 if mask is not None else 0) + (1 if accumulate else 0)))
 
 
 def channel_sum(x, out, accumulate=False):
