@@ -125,7 +125,11 @@ def test_against_reference_golden(path):
 
 
 @pytest.mark.parametrize("cfg,grid,batch", [("hr3d_one_hm_doppler", (8, 16, 24), 2), ("hr3d", (8, 16, 16), 1),
-                                            ("hr3d_one_hm_doppler_phase", (8, 16, 16), 1)])
+                                            ("hr3d_one_hm_doppler_phase", (8, 16, 16), 1),
+                                            # ragged grid: every resolution level has an odd extent somewhere (6,10,14 ->
+                                            # 3,5,7 -> 2,3,4 -> 1,2,2), so no stride-2 conv can use the s2d view and the
+                                            # upsample factors are not powers of two
+                                            ("hr3d_one_hm_doppler", (6, 10, 14), 3)])
 def test_against_oracle_full_gradient(cfg, grid, batch):
     x, poses, tgt = G.make_example(cfg, batch, grid, seed=101)
     sd = O.synth_state_dict(cfg, seed=3)
