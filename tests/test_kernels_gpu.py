@@ -596,3 +596,31 @@ def test_fused_launch_variants_match_their_multi_launch_forms(ctx):
                 ops.conv(dy, wp, KP, NP, d_single, ops.taps_dgrad_s2(pz, px, py), rows, IS=1, OS=2, off=(pz, px, py))
     torch.cuda.synchronize()
     assert torch.equal(d_multi.to_ncdhw(), d_single.to_ncdhw())
+
+
+def test_head_loss_without_positives():
+    """Frames whose skeleton falls outside the ROI: mask all zero, empty target heat-map (center_head.py:244-270 with
+    num_pos = 0: hm_loss = -neg, regression loss 0 and no regression gradient)."""
+    from oracle import hrpose_oracle as O
+    from rtpose_b200.engine import Engine
+    grid, N, ncls, R = (4, 8, 12), 2, 1, 45
+    rs = np.random.RandomState(9)
+    tgt = O.batch_targets([O.synth_pose(rs, grid) for _ in range(N)], grid, True)
+    tgt = {k: v.clone() for k, v in tgt.items()}
+    tgt["mask"].zero_()
+    tgt["hm"].zero_()
+    hm = bf(rnd(N, ncls, *grid, seed=40) * 0.5 - 2.0).requires_grad_(True)
+    reg = rnd(N, R, *grid, seed=41).requires_grad_(True)
+    L = O.head_loss({"hm": hm, "reg": reg}, tgt, 0.5, [1.0] * 45)
+    L["loss"].backward()
+    eng = Engine("hr_tiny_feat32_zyx_l4_in32", "top", {}, R, ncls, 0.5, [1.0] * 45)
+    eng.begin()
+    hp, rp = to_p8(hm.detach()), to_p8(reg.detach())
+    out = eng.loss(hp, rp, tgt["hm"].cuda(), tgt["ind"].cuda(), tgt["mask"].cuda(), tgt["cat"].cuda(), tgt["anno_pose"].cuda())
+    torch.cuda.synchronize()
+    o = out.cpu()
+    assert o[3].item() == 0.0 and L["num_positive"].item() == 0
+    assert abs(o[0].item() - L["loss"].item()) <= 1e-4 * abs(L["loss"].item())
+    assert o[2].item() == 0.0
+    close(hp.grad.to_ncdhw(), hm.grad, tol=2 * BF16_ULP, what="d loss / d hm (no positives)")
+    assert float(rp.grad.to_ncdhw().abs().max()) == 0.0
