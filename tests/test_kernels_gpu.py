@@ -624,3 +624,36 @@ def test_head_loss_without_positives():
     assert o[2].item() == 0.0
     close(hp.grad.to_ncdhw(), hm.grad, tol=2 * BF16_ULP, what="d loss / d hm (no positives)")
     assert float(rp.grad.to_ncdhw().abs().max()) == 0.0
+
+
+def test_full_size_linearity_properties(ctx):
+    """Size-independent properties at the BASELINE shape (batch 16, 32 ch, 16x64x160), where the oracle is too slow to
+    run: scaling an operand by 2 is exact in bf16 / fp32, so conv, dgrad and wgrad must scale bit-exactly; and the
+    forward conv of a one-hot input reproduces the packed weights (checks tap / channel ordering at full resolution)."""
+    from rtpose_b200 import ops
+    from rtpose_b200.p8 import P8
+    N, Cc, grid = 16, 32, (16, 64, 160)
+    g = torch.Generator(device="cuda").manual_seed(7)
+    x = torch.randn(N, Cc, *grid, device="cuda", generator=g)
+    w = (torch.randn(Cc, Cc, 3, 3, 3, device="cuda", generator=g) * 0.05)
+    xp, x2p = P8.from_ncdhw(x), P8.from_ncdhw(2 * x)
+    y1 = ops.conv_forward(ctx, xp, w, 1, P8(N, Cc, *grid)).to_ncdhw()
+    y2 = ops.conv_forward(ctx, x2p, w, 1, P8(N, Cc, *grid)).to_ncdhw()
+    assert torch.equal(y2, 2 * y1)
+    d1 = ops.conv_dgrad(ctx, xp, w, 1, P8(N, Cc, *grid)).to_ncdhw()
+    d2 = ops.conv_dgrad(ctx, x2p, w, 1, P8(N, Cc, *grid)).to_ncdhw()
+    assert torch.equal(d2, 2 * d1)
+    g1, g2 = torch.zeros_like(w), torch.zeros_like(w)
+    ops.conv_wgrad(xp, xp, 3, 1, g1)
+    ops.conv_wgrad(xp, x2p, 3, 1, g2)
+    torch.cuda.synchronize()
+    assert torch.equal(g2, 2 * g1)
+    del y2, d1, d2, x2p
+    # one-hot probe: x = delta at an interior voxel of sample 3, channel 5  ->  y[3, :, v - (k - 1)] = bf16(w[:, 5, k])
+    z0, y0, x0 = 7, 31, 80
+    xh = torch.zeros(N, Cc, *grid, device="cuda")
+    xh[3, 5, z0, y0, x0] = 1.0
+    yh = ops.conv_forward(ctx, P8.from_ncdhw(xh), w, 1, P8(N, Cc, *grid)).to_ncdhw()
+    patch = yh[3, :, z0 - 1:z0 + 2, y0 - 1:y0 + 2, x0 - 1:x0 + 2]
+    assert torch.equal(patch, bf(w[:, 5].flip(1, 2, 3).cpu()).cuda())
+    assert float(yh.abs().sum()) == float(patch.abs().sum())
