@@ -657,3 +657,47 @@ def test_full_size_linearity_properties(ctx):
     patch = yh[3, :, z0 - 1:z0 + 2, y0 - 1:y0 + 2, x0 - 1:x0 + 2]
     assert torch.equal(patch, bf(w[:, 5].flip(1, 2, 3).cpu()).cuda())
     assert float(yh.abs().sum()) == float(patch.abs().sum())
+
+
+def test_full_size_stride2_s2d_agrees_with_gather_kernels(ctx):
+    """At the BASELINE shape the stride-2 exchange conv is computed twice with independent kernels — through the
+    space-to-depth view (plane-streaming conv, masked taps, paired dgrad launches, view wgrad) and with the gather
+    kernels on the plain tensor — and the results must agree to bf16 / fp32-accumulation round-off."""
+    from rtpose_b200 import ops
+    from rtpose_b200.p8 import P8
+    N, Cc, grid, og = 16, 32, (16, 64, 160), (8, 32, 80)
+    g = torch.Generator(device="cuda").manual_seed(11)
+    x = P8.from_ncdhw(torch.randn(N, Cc, *grid, device="cuda", generator=g))
+    dy = P8.from_ncdhw(torch.randn(N, Cc, *og, device="cuda", generator=g))
+    w = torch.randn(Cc, Cc, 3, 3, 3, device="cuda", generator=g) * 0.05
+    gamma, beta = torch.ones(Cc, device="cuda"), torch.zeros(Cc, device="cuda")
+    st = ops.gn_stats(x, 8)
+    assert ops.s2d_eligible(x, w)
+    xn = ops.gn_apply(x, 8, st, gamma, beta, P8(N, Cc, *grid))
+    xs = ops.gn_apply_s2d(x, 8, st, gamma, beta, P8(N, 8 * Cc, *og))
+    we = ops.s2d_expand(w)
+    y_s = ops.conv_forward(ctx, xs, we, 1, P8(N, Cc, *og), key="fs2", version=0,
+                           tap_mask=[ops.s2d_tap_mask(p, False) for p in range(8)]).to_ncdhw()
+    y_g = ops.conv_forward(ctx, xn, w, 2, P8(N, Cc, *og)).to_ncdhw()
+    close(y_s, y_g, what="s2 forward: s2d vs gather")
+    gw_s, gw_g = torch.zeros_like(w), torch.zeros_like(w)
+    ops.conv_wgrad_s2d(xs, dy, Cc, gw_s)
+    ops.conv_wgrad(xn, dy, 3, 2, gw_g)
+    torch.cuda.synchronize()
+    close(gw_s, gw_g, tol=1e-3, what="s2 wgrad: view vs plain tensor")
+    dxs = ops.conv_dgrad(ctx, dy, we, 1, P8(N, 8 * Cc, *og), key="fs2", version=0, s2d_cin=Cc)
+    old = ops.USE_S2D
+    ops.USE_S2D = False
+    try:
+        dxn = ops.conv_dgrad(ctx, dy, w, 2, P8(N, Cc, *grid))
+    finally:
+        ops.USE_S2D = old
+    # compare through GroupNorm backward (reads the view / the plain gradient)
+    dg1, db1, dg2, db2 = (torch.zeros(Cc, device="cuda") for _ in range(4))
+    dx1, dx2 = P8(N, Cc, *grid), P8(N, Cc, *grid)
+    ops.gn_backward(x, dxs, 8, st, gamma, dg1, db1, False, dx1, False, s2d=True)
+    ops.gn_backward(x, dxn, 8, st, gamma, dg2, db2, False, dx2, False)
+    torch.cuda.synchronize()
+    close(dx1.to_ncdhw(), dx2.to_ncdhw(), tol=2 * BF16_ULP, what="s2 dgrad + GN backward: s2d vs gather")
+    close(dg1, dg2, tol=1e-3, what="dgamma")
+    close(db1, db2, tol=1e-3, what="dbeta")
