@@ -460,6 +460,7 @@ STAT_CASES = [
     (16, 32, 32, (4, 20, 24)),     # more samples than the common case: slab rows for every n
     (2, 64, 32, (6, 12, 10)),      # two K passes
     (2, 32, 16, (4, 10, 12)),      # 16 result channels
+    (16, 32, 32, (16, 64, 160)),   # the BASELINE shape: 9 units per CTA, every sample touched by several CTAs
 ]
 
 
