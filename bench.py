@@ -344,25 +344,26 @@ def run_ours(args, rank, world, local_rank):
             "model_tflops": 3 * gf_fwd * 1e9 * value / 1e12, "model_flops_frac_of_peak": 3 * gf_fwd * 1e9 * value / 1e12 / world / pk_sust,
             "loss": float(out[0]), "gpu_launches": launches, "host_issue_ms_per_step": round(host_issue_ms, 2), "clocks": sampler.summary(), "roofline": roof, "top_kernels": top}
 
+    if not args.no_extras:
+        line["e2e"] = e2e_public_api(args, dev, rank, world)  # every rank takes part (gradient all-reduce inside)
     if rank == 0 and world == 1 and not args.no_extras:
-        line["e2e"] = e2e_public_api(args, dev)
         line["cpu_baseline"] = cpu_baseline(args)
         try:
             line["inference"] = inference_bench(args, eng, dev)
         except Exception as ex:  # extras must never take the headline down
             line["inference"] = {"error": repr(ex)}
-    elif rank == 0:
-        line["e2e"] = {"value": None, "unit": "frames/s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": None,
-                       "note": "measured at N=1 only"}
     if rank == 0:
         print(json.dumps(line))
 
 
-def e2e_public_api(args, dev):
+def e2e_public_api(args, dev, rank=0, world=1):
     """Same metric through the reference-facing API (build_detector -> model(example) -> loss.backward()) with HOST
-    buffers: per step the fp32 rdr_tensor + targets go pinned-host -> device and the loss comes back."""
+    buffers: per step the fp32 rdr_tensor + targets go pinned-host -> device and the loss comes back.  At N > 1 every
+    rank steps its own shard and the gradients are averaged after backward() the way the reference's trainer does
+    (rtpose_b200.dist.allreduce_grads <-> det3d/core/utils/dist_utils.py:40-57); time = max over ranks."""
     from rtpose_b200 import det3d_compat as D
     from rtpose_b200 import targets
+    from rtpose_b200 import dist as rdist
     cfg = args.cfg
     arch, fin, fout, fuse, reg, ncls, weight, in_ch, norm, _ = CFGS[cfg]
     B = args.batch
@@ -379,7 +380,9 @@ def e2e_public_api(args, dev):
     model = D.build_detector(model_cfg, train_cfg=None, test_cfg=None).to(dev)
     model.pose_head.sync_free_losses = True
     model.cuda_graph = not args.no_graph  # one replayed graph per training step (det3d_compat._StepJob)
-    rs = np.random.RandomState(7)
+    if world > 1:
+        rdist.broadcast_params(list(model.parameters()))
+    rs = np.random.RandomState(7 + rank)
     x_host = torch.from_numpy(np.maximum(rs.uniform(-0.2, 1.0, (B, in_ch) + GRID), 0).astype(np.float32)).pin_memory()
     tg = targets.assign(targets.random_poses(rs, B, GRID), GRID, one_hm=(ncls == 1), min_radius=2 if ncls == 1 else 1)
     t_host = {k: torch.from_numpy(v).pin_memory() for k, v in tg.items()}
@@ -408,23 +411,35 @@ def e2e_public_api(args, dev):
             p.grad = None
         losses = model(ex, return_loss=True)
         losses["loss"][0].backward()
+        if world > 1:
+            rdist.allreduce_grads(params, world)
         nxt = fetch()                                        # overlaps with the GPU work just enqueued
         return float(losses["loss"][0].detach().cpu()), nxt  # D2H read of the step's result
 
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    params = list(model.parameters())
     nxt = fetch()
     for _ in range(max(3, min(args.warmup, 3))):
         _, nxt = step(*nxt)
-    torch.cuda.synchronize()
+    barrier()
     steps = max(3, min(args.steps, 10))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
         _, nxt = step(*nxt)
     e1.record()
-    torch.cuda.synchronize()
+    barrier()
     ms = e0.elapsed_time(e1) / steps
-    return {"value": B / (ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
-            "ms_per_step": ms, "cuda_graph": bool(model.cuda_graph),
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms = float(t[0])
+    return {"value": world * B / (ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
+            "bytes_are": "per rank", "ms_per_step": ms, "cuda_graph": bool(model.cuda_graph),
             "api": "det3d_compat.build_detector(...)(example, return_loss=True); loss.backward()"}
 
 

@@ -30,6 +30,26 @@ def allreduce_flat(flat, world=None, async_op=False):
     return None
 
 
+def allreduce_grads(params, world=None):
+    """Average `.grad` of every parameter over the ranks through one coalesced buffer — the call a trainer makes after
+    loss.backward() (det3d/core/utils/dist_utils.py:40-57 `allreduce_grads(..., coalesce=True)`).  No-op when
+    torch.distributed is not initialised or the world is one rank."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return
+    world = world or dist.get_world_size()
+    if world == 1:
+        return
+    grads = [p.grad for p in params if p.requires_grad and p.grad is not None]
+    if not grads:
+        return
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    allreduce_flat(flat, world)
+    o = 0
+    for g in grads:
+        g.copy_(flat[o:o + g.numel()].view_as(g))
+        o += g.numel()
+
+
 def scale_flat(flat, s):
     if flat.is_cuda:
         from . import lib

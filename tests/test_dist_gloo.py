@@ -29,6 +29,10 @@ def _worker(rank, world, port, out):
         rdist.broadcast_params([params])
         h = rdist.allreduce_flat(torch.ones(3) * rank, world, async_op=True)
         h.wait()
+        ps = [torch.nn.Parameter(torch.zeros(2, 3)), torch.nn.Parameter(torch.zeros(4)), torch.nn.Parameter(torch.zeros(1))]
+        ps[0].grad, ps[1].grad = torch.full((2, 3), float(rank)), torch.full((4,), 10.0 * (rank + 1))  # ps[2] has no grad
+        rdist.allreduce_grads(ps, world)
+        assert ps[0].grad.tolist() == [[0.5] * 3] * 2 and ps[1].grad.tolist() == [15.0] * 4 and ps[2].grad is None
         out.put((rank, lo, hi, flat.tolist(), params.tolist()))
     finally:
         dist.destroy_process_group()
