@@ -352,6 +352,10 @@ def run_ours(args, rank, world, local_rank):
             line["inference"] = inference_bench(args, eng, dev)
         except Exception as ex:  # extras must never take the headline down
             line["inference"] = {"error": repr(ex)}
+        try:
+            line["loader"] = loader_bench(args, dev)
+        except Exception as ex:
+            line["loader"] = {"error": repr(ex)}
     if rank == 0:
         print(json.dumps(line))
 
@@ -462,6 +466,57 @@ def cpu_baseline(args):
     dt = float(np.median(times[1:]))
     return {"value": 1.0 / dt, "unit": "frames/s", "cores": cores, "kind": "port",
             "sample": "batch 1 fwd+bwd at 16x64x160, fp32, 1 warm-up + median of 3 (torch CPU ops, %d threads)" % cores}
+
+
+def loader_bench(args, dev):
+    """on-disk fp16 cubes -> P8 model input through rtpose_b200.loader.CubeLoader (ROI-row preads ->
+    pinned slab -> H2D -> rtp_ingest_pack), beside the reference's way of producing the same tensor in one process
+    (np.load + astype(float32) + crop + normalise + clamp, cruw_pose.py:170-185; torch.tensor + blocking H2D,
+    cruw_pose.py:264-266, train.py(apis):27-62).  Files are synthetic, written to a temp dir and read from the page cache."""
+    import shutil
+    import tempfile
+    from rtpose_b200 import loader
+    arch, fin, fout, fuse, reg, ncls, weight, in_ch, norm, _ = CFGS[args.cfg]
+    B, nfiles = args.batch, 2 * args.batch
+    shape = ((in_ch,) if in_ch > 1 else ()) + RAW_SHAPE
+    a, b = norm if norm is not None else (0.0, 1.0)
+    need = 2 * nfiles * int(np.prod(shape)) * 2
+    shm_ok = os.path.isdir("/dev/shm") and shutil.disk_usage("/dev/shm").free > need
+    tmp = tempfile.mkdtemp(prefix="rtp_cubes_", dir="/dev/shm" if shm_ok else None)
+    try:
+        rs = np.random.RandomState(11)
+        base = (a + (b - a) * (rs.rand(*shape).astype(np.float32) * 1.2 - 0.2)).astype(np.float16)
+        paths = []
+        for i in range(nfiles):
+            paths.append(os.path.join(tmp, "%06d.npy" % i))
+            np.save(paths[-1], np.roll(base, i, axis=-1))
+        ld = loader.CubeLoader(paths, batch=B, norm=norm, depth=3, frame_workers=8, io_threads=4)
+        for _ in ld:  # warm-up epoch (page cache, pinned allocations)
+            pass
+        torch.cuda.synchronize()
+        epochs, t0 = 3, time.perf_counter()
+        for _ in range(epochs):
+            for x, _p in ld:
+                pass
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        ours = epochs * len(ld) * B / dt
+        # the reference's way, same files, one process (it uses 2 DataLoader workers: build_loader.py:46-57)
+        z0, y0, x0 = ROI0
+        t0 = time.perf_counter()
+        for p in paths[:B]:
+            arr = np.load(p).astype(np.float32)
+            arr = arr[..., z0:z0 + GRID[0], y0:y0 + GRID[1], x0:x0 + GRID[2]]
+            arr = (arr - a) / (b - a)
+            arr[arr < 0.] = 0.
+            t = torch.tensor(arr[None]).to(dev)
+        torch.cuda.synchronize()
+        ref = B / (time.perf_counter() - t0)
+        return {"value": ours, "unit": "frames/s", "reference_style_1proc": ref, "file_MB": round(base.nbytes / 1e6, 1),
+                "read_MB_per_frame": round(ld.bytes_per_frame / 1e6, 1), "files": nfiles, "batch": B,
+                "source": "page cache (%s)" % os.path.dirname(paths[0]), "includes": "pread ROI rows + H2D + ingest kernel"}
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
 
 
 def inference_bench(args, eng, dev):

@@ -62,6 +62,32 @@ int rtp_ingest_pack(const void* raw_f16, int32_t N, int32_t D, int32_t RZ, int32
                     int32_t y0, int32_t x0, float norm_start, float norm_scale, int32_t normalize, rtp_p8 dst,
                     float* dst_f32, void* stream);
 
+/* ---- on-disk cubes: ROI-only reads (host code, no device work) ---------------------------------------------
+ * replaces: `np.load(<seq>/DZYX_npy_f16/<frame>.npy).astype(np.float32)` followed by the z/y crop in
+ * CRUW_POSE_Dataset.get_cube (det3d/datasets/cruw_pose/cruw_pose.py:170, :176-181) and get_cube_phase (:189-192);
+ * the DataLoader workers / pickle / blocking H2D around them (det3d/datasets/loader/build_loader.py:46-57).
+ * A cube file is a numpy .npy (v1-v3) holding little-endian float16 in C order with shape [..., RZ, RY, RX]; all
+ * leading dimensions (Doppler bins, re/im planes) are flattened to `lead` planes.  rtp_npy_read_roi_slab copies rows
+ * z[z0,z0+Z) y[y0,y0+Y) with their FULL x extent into dst as fp16 [lead][Z][Y][RX] using `threads` reader threads
+ * (pread; dst is typically pinned memory that is then copied to the device and handed to rtp_ingest_pack with
+ * RZ=Z, RY=Y, z0=y0=0, which crops x, normalises, clamps and packs).  Errors (return < 0, message in
+ * rtp_last_error): missing/short file, bad magic or version, dtype other than float16, Fortran order, fewer than 3
+ * dimensions, ROI outside the cube, dst too small. */
+typedef struct {
+  int32_t ndim;
+  int32_t elem_bytes;
+  int32_t fortran_order;
+  int32_t reserved_;
+  int64_t shape[8];
+  int64_t data_offset; /* byte offset of element 0 in the file */
+  int64_t file_bytes;
+  char descr[16];      /* numpy dtype string, e.g. "<f2" */
+} rtp_npy_info;
+int rtp_npy_probe(const char* path, rtp_npy_info* info);
+int64_t rtp_npy_roi_slab_bytes(const rtp_npy_info* info, int32_t Z, int32_t Y); /* < 0 on bad arguments */
+int rtp_npy_read_roi_slab(const char* path, int32_t z0, int32_t Z, int32_t y0, int32_t Y, void* dst, int64_t dst_bytes,
+                          int32_t threads);
+
 /* ---- weights ---------------------------------------------------------------------------------------------
  * replaces: nothing in the reference (cuDNN consumes [Cout,Cin,kz,ky,kx] fp32 directly); repacks an fp32
  * nn.Conv3d weight into the bf16 UMMA B-operand tiles.

@@ -49,6 +49,11 @@ class FuseDesc(C.Structure):
                 ("same", P8Struct * 4), ("low", P8Struct * 3), ("bias", C.c_void_p), ("relu", C.c_int32)]
 
 
+class NpyInfo(C.Structure):
+    _fields_ = [("ndim", C.c_int32), ("elem_bytes", C.c_int32), ("fortran_order", C.c_int32), ("reserved_", C.c_int32),
+                ("shape", C.c_int64 * 8), ("data_offset", C.c_int64), ("file_bytes", C.c_int64), ("descr", C.c_char * 16)]
+
+
 _i32, _i64, _f32, _vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
 
 # name -> (restype, argtypes); every symbol include/rtpose_b200.h declares
@@ -56,6 +61,9 @@ PROTOTYPES = {
     "rtp_last_error": (C.c_char_p, []),
     "rtp_version": (C.c_int, []),
     "rtp_device_ok": (C.c_int, []),
+    "rtp_npy_probe": (C.c_int, [C.c_char_p, C.POINTER(NpyInfo)]),
+    "rtp_npy_roi_slab_bytes": (C.c_int64, [C.POINTER(NpyInfo), _i32, _i32]),
+    "rtp_npy_read_roi_slab": (C.c_int, [C.c_char_p, _i32, _i32, _i32, _i32, _vp, _i64, _i32]),
     "rtp_pack_ncdhw": (C.c_int, [_vp, P8Struct, _i32, _vp]),
     "rtp_unpack_ncdhw": (C.c_int, [P8Struct, _vp, _i32, _i32, _vp]),
     "rtp_ingest_pack": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _f32, _i32, P8Struct,
@@ -162,7 +170,8 @@ LAUNCHES = {"rtp_pack_ncdhw": 1, "rtp_unpack_ncdhw": 1, "rtp_ingest_pack": 1, "r
             "rtp_stem_bwd": 2, "rtp_head_loss": 2, "rtp_decode": 1, "rtp_scale_f32": 1, "rtp_dcn_fwd": 1,
             "rtp_dcn_bwd_input": 1, "rtp_dcn_bwd_weight": 1, "rtp_adam_step": 2, "rtp_adam_step_dev": 2,
             "rtp_assign_targets": 2, "rtp_wgrad_k3s1": 1, "rtp_wgrad_k3s1_reduce": 1, "rtp_conv_pw": 1, "rtp_gn_apply_s2d": 1, "rtp_gn_bwd_reduce_s2d": 2,
-            "rtp_gn_bwd_apply_s2d": 1, "rtp_conv_k3s1_stat_finalize": 1, "rtp_conv_multi": 1, "rtp_gn_stats": 2}
+            "rtp_gn_bwd_apply_s2d": 1, "rtp_conv_k3s1_stat_finalize": 1, "rtp_conv_multi": 1, "rtp_gn_stats": 2,
+            "rtp_npy_probe": 0, "rtp_npy_read_roi_slab": 0}  # host-only file readers
 launch_count = 0
 
 
