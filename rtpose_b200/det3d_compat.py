@@ -128,6 +128,35 @@ def _get(cfg, key):
     return cfg[key] if isinstance(cfg, dict) else getattr(cfg, key)
 
 
+def _model_input(x, what):
+    """The cube a detector is fed: the reference's fp32 [B,C,Z,Y,X] CUDA tensor, or an already packed P8 (what
+    rtpose_b200.loader.CubeLoader yields), which is used as is."""
+    if isinstance(x, P8):
+        return x
+    return _cuda_input(x, what).float().contiguous()
+
+
+def _as_p8(x):
+    return x if isinstance(x, P8) else P8.from_ncdhw(x)
+
+
+def _x_key(x):
+    return ("p8", x.N, x.C, x.Z, x.Y, x.X, x.n_stride, x.c_stride) if isinstance(x, P8) else tuple(x.shape)
+
+
+def _x_static(x):
+    return x.like() if isinstance(x, P8) else torch.empty_like(x)
+
+
+def _x_copy(dst, src):
+    if isinstance(src, P8):
+        if (src.n_stride, src.c_stride, src.buf.numel(), src.offset) != (dst.n_stride, dst.c_stride, dst.buf.numel(), dst.offset):
+            raise lib.RtpError("graphed step: a packed input must own its buffer (not a channel view)")
+        dst.buf.copy_(src.buf)
+    else:
+        dst.copy_(src)
+
+
 def _cuda_input(x, what):
     if not torch.is_tensor(x) or not x.is_cuda:
         raise lib.RtpError("%s must be a CUDA tensor: the rtpose_b200 path has no CPU fallback" % what)
@@ -196,31 +225,30 @@ class _StepJob(_ParamJob):
         if self.graph_state is not None:
             return self._run_graphed()
         e = self.engine
-        xp = P8.from_ncdhw(self.x)
-        hm, reg = e.forward(xp, self.train)
+        hm, reg = e.forward(_as_p8(self.x), self.train)
         return e.loss(hm, reg, *self._targets(), with_grad=self.train)
 
     def _run_graphed(self):
         from .graph import StepGraph
         st, e, tgt = self.graph_state, self.engine, self._targets()
-        key = (tuple(p.data_ptr() for p in self.params.values()), tuple(self.x.shape), tuple(tuple(t.shape) for t in tgt))
+        key = (tuple(p.data_ptr() for p in self.params.values()), _x_key(self.x), tuple(tuple(t.shape) for t in tgt))
         if st.get("key") != key:
             st.clear()
-            st["x"], st["tgt"] = torch.empty_like(self.x), tuple(torch.empty_like(t) for t in tgt)
+            st["x"], st["tgt"] = _x_static(self.x), tuple(torch.empty_like(t) for t in tgt)
             st["flat"], st["views"] = self.grads_buffer()
 
             def body():
                 e.packs.refresh_async()  # the optimizer rewrites the weights between replays: repack inside the graph
-                hm, reg = e.forward(P8.from_ncdhw(st["x"]), True)
+                hm, reg = e.forward(_as_p8(st["x"]), True)
                 out = e.loss(hm, reg, *st["tgt"], with_grad=True)
                 st["touched"] = e.backward(st["views"])
                 return out
-            st["x"].copy_(self.x)
+            _x_copy(st["x"], self.x)
             for d, t in zip(st["tgt"], tgt):
                 d.copy_(t)
             st["graph"] = StepGraph(body, warmup=1).capture()
             st["key"] = key
-        st["x"].copy_(self.x)
+        _x_copy(st["x"], self.x)
         for d, t in zip(st["tgt"], tgt):
             d.copy_(t)
         return st["graph"]().clone()
@@ -501,7 +529,7 @@ class RadarPoseNet(nn.Module):
         ex = {}
         ex.update(example[self.sensor_type])
         ex.update({"meta": example["meta"]})
-        x = _cuda_input(self.reader(ex["rdr_tensor"]), "example['rdr']['rdr_tensor']").float().contiguous()
+        x = _model_input(self.reader(ex["rdr_tensor"]), "example['rdr']['rdr_tensor']")
         params = _named(self)
         e = self._eng(params)
         if return_loss:
@@ -509,7 +537,7 @@ class RadarPoseNet(nn.Module):
             (out,) = _Bridge.apply(_StepJob(e, params, x, ex, torch.is_grad_enabled(), graph_state=gs), *params.values())
             return self.pose_head._format_losses(out)
         with torch.no_grad():
-            hm, reg = e.forward(P8.from_ncdhw(x), False)
+            hm, reg = e.forward(_as_p8(x), False)
             return self.pose_head._predict_p8(hm, reg, self.test_cfg, ex["meta"], engine=e)
 
 

@@ -83,7 +83,7 @@ class CubeLoader:
     ingest kernel of that batch has been enqueued.
     """
 
-    def __init__(self, paths, batch, device="cuda", roi0=ROI0, grid=GRID, norm=None, depth=3, frame_workers=4, io_threads=4,
+    def __init__(self, paths, batch, device="cuda", roi0=ROI0, grid=GRID, norm=None, depth=3, frame_workers=2, io_threads=8,
                  drop_last=True, want_f32=False):
         lib.require_device()
         self.paths = [os.fspath(p) for p in paths]
@@ -102,29 +102,46 @@ class CubeLoader:
         self.file_shape = shape
         self.slab = slab_shape(shape, self.grid[0], self.grid[1])
         self.bytes_per_frame = 2 * self.slab[0] * self.slab[1] * self.slab[2] * self.slab[3]
+        self._stage, self._live = None, None
 
     def __len__(self):
         return len(self.batches)
 
+    def _staging(self):
+        """Pinned + device slabs and their events: allocated once (cudaHostAlloc of ~1 GB is far slower than an epoch of
+        reads) and shared by successive epochs, of which only one is live at a time."""
+        if self._stage is None:
+            full = (self.batch,) + self.slab
+            self._stage = {"pinned": [torch.empty(full, dtype=torch.float16).pin_memory() for _ in range(self.depth)],
+                           "dev": [torch.empty(full, dtype=torch.float16, device=self.device) for _ in range(self.depth)],
+                           "copied": [torch.cuda.Event() for _ in range(self.depth)],   # H2D out of the pinned slot finished
+                           "consumed": [None] * self.depth,                             # ingest that read the device slot
+                           "copy_stream": torch.cuda.Stream(device=self.device),
+                           "pool": ThreadPoolExecutor(max_workers=max(1, self.frame_workers))}
+        return self._stage
+
+    def close(self):
+        """Stops a live epoch's producer thread (safe to call at any time; the loader can be iterated again)."""
+        if self._live is not None:
+            self._live.close()
+
     def __iter__(self):
-        return _Epoch(self)
+        if self._live is not None:
+            self._live.close()  # an abandoned epoch must stop writing into the staging slots first
+        self._live = _Epoch(self)
+        return self._live
 
 
 class _Epoch:
     def __init__(self, ld):
         self.ld = ld
-        dev = ld.device
-        full = (ld.batch,) + ld.slab
-        self.pinned = [torch.empty(full, dtype=torch.float16).pin_memory() for _ in range(ld.depth)]
-        self.dev = [torch.empty(full, dtype=torch.float16, device=dev) for _ in range(ld.depth)]
-        self.copied = [torch.cuda.Event() for _ in range(ld.depth)]   # H2D of the slot finished
-        self.consumed = [None] * ld.depth                             # ingest of the slot's previous batch enqueued
-        self.copy_stream = torch.cuda.Stream(device=dev)
+        st = ld._staging()
+        self.pinned, self.dev, self.copied, self.consumed = st["pinned"], st["dev"], st["copied"], st["consumed"]
+        self.copy_stream, self.pool = st["copy_stream"], st["pool"]
         self.free, self.ready = queue.Queue(), queue.Queue()
         for s in range(ld.depth):
             self.free.put(s)
         self.stop = False
-        self.pool = ThreadPoolExecutor(max_workers=max(1, ld.frame_workers))
         self.thread = threading.Thread(target=self._produce, name="rtp-cube-loader", daemon=True)
         self.thread.start()
 
@@ -143,6 +160,8 @@ class _Epoch:
                         for i, p in enumerate(paths)]
                 for f in futs:
                     f.result()
+                if self.stop:
+                    return
                 n = len(paths)
                 with torch.cuda.stream(self.copy_stream):
                     if self.consumed[s] is not None:
@@ -158,6 +177,8 @@ class _Epoch:
         return self
 
     def __next__(self):
+        if self.stop:
+            raise StopIteration
         s, n, paths, err = self.ready.get()
         if err is not None:
             self.close()
@@ -176,13 +197,11 @@ class _Epoch:
         return out, paths
 
     def close(self):
+        """Stops the producer and waits for it (it may be in the middle of filling a staging slot)."""
         if not self.stop:
             self.stop = True
             self.free.put(None)
-            self.pool.shutdown(wait=False)
-
-    def __del__(self):
-        try:
-            self.close()
-        except Exception:
-            pass
+        if self.thread is not threading.current_thread():
+            self.thread.join()
+        if self.ld._live is self:
+            self.ld._live = None

@@ -46,6 +46,10 @@ class P8:
         v.relu_out = self.relu_out
         return v
 
+    @property
+    def device(self):
+        return self.buf.device
+
     def like(self, C=None):
         return P8(self.N, self.C if C is None else C, self.Z, self.Y, self.X, device=self.buf.device)
 
