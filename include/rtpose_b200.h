@@ -322,6 +322,23 @@ int rtp_dcn_bwd_weight(const float* x, const float* offset, const float* dy, flo
                        int32_t H, int32_t W, int32_t Cout, int32_t kh, int32_t kw, int32_t stride, int32_t pad,
                        int32_t dil, int32_t dg, float scale, void* stream);
 
+/* ---- deformable convolution v2 ("modulated", 2-D) ---------------------------------------------------------------
+ * replaces: modulated_deform_conv_cuda_forward / modulated_deform_conv_cuda_backward
+ * (det3d/ops/dcn/src/deform_conv_cuda.cpp:490-684; kernels deform_conv_cuda_kernel.cu:467-867; bound at
+ * deform_conv_cuda.cpp:687-701 and called from det3d/ops/dcn/deform_conv.py:141,161).
+ * As v1 plus mask fp32 [N][dg*kh*kw][Ho][Wo] multiplying every sample and an optional bias[Cout] (NULL = none).
+ * bwd_input overwrites dx / doffset / dmask; bwd_weight ACCUMULATES scale * gradient into dw and (if not NULL) dbias,
+ * like the reference, whose autograd function passes zero-filled tensors (deform_conv.py:156-160). */
+int rtp_mdcn_fwd(const float* x, const float* offset, const float* mask, const float* w, const float* bias, float* y,
+                 int32_t N, int32_t C, int32_t H, int32_t W, int32_t Cout, int32_t kh, int32_t kw, int32_t stride,
+                 int32_t pad, int32_t dil, int32_t dg, void* stream);
+int rtp_mdcn_bwd_input(const float* x, const float* offset, const float* mask, const float* w, const float* dy, float* dx,
+                       float* doffset, float* dmask, int32_t N, int32_t C, int32_t H, int32_t W, int32_t Cout, int32_t kh,
+                       int32_t kw, int32_t stride, int32_t pad, int32_t dil, int32_t dg, void* stream);
+int rtp_mdcn_bwd_weight(const float* x, const float* offset, const float* mask, const float* dy, float* dw, float* dbias,
+                        int32_t N, int32_t C, int32_t H, int32_t W, int32_t Cout, int32_t kh, int32_t kw, int32_t stride,
+                        int32_t pad, int32_t dil, int32_t dg, float scale, void* stream);
+
 /* ---- "next" rows around the path --------------------------------------------------------------
  * N2 fused optimizer step on flat fp32 buffers.  replaces: OptimizerHook.clip_grads (clip_grad_norm_, max_norm 35;
  * det3d/torchie/trainer/hooks/optimizer.py:9-24) + OptimWrapper.step (decoupled weight decay p *= 1 - wd*lr on every

@@ -1,5 +1,7 @@
-// dcn.cu — deformable convolution v1 (2-D, groups = 1) forward / backward without the reference's `columns`
-// round trip through HBM (det3d/ops/dcn/src/deform_conv_cuda.cpp:196-247 materialises C*kh*kw x N*Ho*Wo fp32).
+// dcn.cu — deformable convolution v1 and v2 ("modulated": a per-tap mask multiplies every sample, optional bias)
+// (2-D, groups = 1) forward / backward without the reference's `columns` round trip through HBM
+// (det3d/ops/dcn/src/deform_conv_cuda.cpp:196-247 materialises C*kh*kw x N*Ho*Wo fp32; the modulated path :490-684).
+// Every kernel takes an optional `mask` [N][dg*kh*kw][Ho][Wo]; nullptr = v1.
 //
 // Each CTA owns a tile of 32 output pixels of one sample.  A channel tile of the deformed im2col matrix is sampled
 // straight into shared memory with warp-level bilinear gathers (lanes = consecutive output pixels, so the offset
@@ -36,11 +38,12 @@ __device__ __forceinline__ Sample make_sample(const Dcn& p, float h, float w) {
   s.lh = h - (float)h_low;
   s.lw = w - (float)w_low;
   const float hh = 1.f - s.lh, hw = 1.f - s.lw;
-  const bool t = h_low >= 0, b = h_high <= p.H - 1, l = w_low >= 0, r = w_high <= p.W - 1;
-  s.w1 = (s.valid && t && l) ? hh * hw : 0.f;
-  s.w2 = (s.valid && t && r) ? hh * s.lw : 0.f;
-  s.w3 = (s.valid && b && l) ? s.lh * hw : 0.f;
-  s.w4 = (s.valid && b && r) ? s.lh * s.lw : 0.f;
+  // corner flags include `valid`: an invalid position (also NaN / far outside) must never turn into a load address
+  const bool t = s.valid && h_low >= 0, b = s.valid && h_high <= p.H - 1, l = s.valid && w_low >= 0, r = s.valid && w_high <= p.W - 1;
+  s.w1 = (t && l) ? hh * hw : 0.f;
+  s.w2 = (t && r) ? hh * s.lw : 0.f;
+  s.w3 = (b && l) ? s.lh * hw : 0.f;
+  s.w4 = (b && r) ? s.lh * s.lw : 0.f;
   s.o1 = (t && l) ? h_low * p.W + w_low : 0;
   s.o2 = (t && r) ? h_low * p.W + w_high : 0;
   s.o3 = (b && l) ? h_high * p.W + w_low : 0;
@@ -60,8 +63,8 @@ __device__ __forceinline__ void tap_pos(const Dcn& p, const float* __restrict__ 
 }
 
 // col[ck][px] for channels [c0, c0+kCT): one warp-level gather per (channel, tap) row
-__device__ __forceinline__ void sample_tile(const Dcn& p, const float* __restrict__ x_n, const float* __restrict__ off_n, int c0,
-                                            int pix0, float* col) {
+__device__ __forceinline__ void sample_tile(const Dcn& p, const float* __restrict__ x_n, const float* __restrict__ off_n,
+                                            const float* __restrict__ mask_n, int c0, int pix0, float* col) {
   const int K = p.kh * p.kw, npix = p.Ho * p.Wo, cpg = p.C / p.dg;
   for (int i = threadIdx.x; i < kCT * K * kPix; i += blockDim.x) {
     const int px = i % kPix, ck = i / kPix;
@@ -75,6 +78,7 @@ __device__ __forceinline__ void sample_tile(const Dcn& p, const float* __restric
       const Sample s = make_sample(p, h, w);
       const float* xc = x_n + (int64_t)c * p.H * p.W;
       v = s.w1 * __ldg(xc + s.o1) + s.w2 * __ldg(xc + s.o2) + s.w3 * __ldg(xc + s.o3) + s.w4 * __ldg(xc + s.o4);
+      if (mask_n) v *= __ldg(mask_n + (int64_t)((c / cpg) * K + t) * npix + pix);  // modulated_deformable_im2col (kernel.cu:571-634)
     }
     col[ck * kPix + px] = v;
   }
@@ -82,19 +86,24 @@ __device__ __forceinline__ void sample_tile(const Dcn& p, const float* __restric
 
 // y[n, co, pix] = sum_{c,t} w[co, c, t] * col[(c,t), pix]
 __global__ void __launch_bounds__(256) dcn_fwd_kernel(Dcn p, const float* __restrict__ x, const float* __restrict__ off,
-                                                      const float* __restrict__ w, float* __restrict__ y) {
+                                                      const float* __restrict__ mask, const float* __restrict__ w,
+                                                      const float* __restrict__ bias, float* __restrict__ y) {
   extern __shared__ float col[];  // [kCT*K][kPix]
   const int K = p.kh * p.kw, npix = p.Ho * p.Wo;
   const int n = blockIdx.y, pix0 = blockIdx.x * kPix, co0 = blockIdx.z * 128;
   const int px = threadIdx.x & 31, cg = threadIdx.x >> 5;  // 8 warps: warp cg owns output channels co0 + cg + 8*j
   const float* x_n = x + (int64_t)n * p.C * p.H * p.W;
   const float* off_n = off + (int64_t)n * p.dg * K * 2 * npix;
+  const float* mask_n = mask ? mask + (int64_t)n * p.dg * K * npix : nullptr;
   float acc[16];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+  for (int j = 0; j < 16; ++j) {
+    const int co = co0 + cg + 8 * j;
+    acc[j] = (bias && co < p.Cout) ? __ldg(bias + co) : 0.f;
+  }
   for (int c0 = 0; c0 < p.C; c0 += kCT) {
     __syncthreads();
-    sample_tile(p, x_n, off_n, c0, pix0, col);
+    sample_tile(p, x_n, off_n, mask_n, c0, pix0, col);
     __syncthreads();
     const int nck = min(kCT, p.C - c0) * K;
     for (int ck = 0; ck < nck; ++ck) {
@@ -117,8 +126,9 @@ __global__ void __launch_bounds__(256) dcn_fwd_kernel(Dcn p, const float* __rest
 
 // dx (atomic scatter) and doffset for one pixel tile
 __global__ void __launch_bounds__(256) dcn_bwd_input_kernel(Dcn p, const float* __restrict__ x, const float* __restrict__ off,
-                                                            const float* __restrict__ w, const float* __restrict__ dy,
-                                                            float* __restrict__ dx, float* __restrict__ doff) {
+                                                            const float* __restrict__ mask, const float* __restrict__ w,
+                                                            const float* __restrict__ dy, float* __restrict__ dx,
+                                                            float* __restrict__ doff, float* __restrict__ dmask) {
   extern __shared__ float sm[];
   const int K = p.kh * p.kw, npix = p.Ho * p.Wo, cpg = p.C / p.dg;
   float* dcol = sm;                      // [kCT*K][kPix]
@@ -128,6 +138,8 @@ __global__ void __launch_bounds__(256) dcn_bwd_input_kernel(Dcn p, const float* 
   const float* off_n = off + (int64_t)n * p.dg * K * 2 * npix;
   float* dx_n = dx + (int64_t)n * p.C * p.H * p.W;
   float* doff_n = doff + (int64_t)n * p.dg * K * 2 * npix;
+  const float* mask_n = mask ? mask + (int64_t)n * p.dg * K * npix : nullptr;
+  float* dmask_n = mask ? dmask + (int64_t)n * p.dg * K * npix : nullptr;
   for (int i = threadIdx.x; i < p.Cout * kPix; i += blockDim.x) {
     const int px = i % kPix, co = i / kPix;
     dys[i] = (pix0 + px < npix) ? dy[((int64_t)n * p.Cout + co) * npix + pix0 + px] : 0.f;
@@ -156,7 +168,9 @@ __global__ void __launch_bounds__(256) dcn_bwd_input_kernel(Dcn p, const float* 
         float h, wv;
         tap_pos(p, off_n, g, t, ho, wo, h, wv);
         const Sample s = make_sample(p, h, wv);
-        const float d = dcol[(cc * K + t) * kPix + px];
+        const float draw = dcol[(cc * K + t) * kPix + px];  // gradient w.r.t. the masked sample
+        const float mk = mask_n ? __ldg(mask_n + (int64_t)(g * K + t) * npix + pix) : 1.f;
+        const float d = draw * mk;                          // gradient w.r.t. the bilinear sample
         const float* xc = x_n + (int64_t)c * p.H * p.W;
         float* dxc = dx_n + (int64_t)c * p.H * p.W;
         if (s.w1 != 0.f) atomicAdd(dxc + s.o1, d * s.w1);
@@ -176,6 +190,8 @@ __global__ void __launch_bounds__(256) dcn_bwd_input_kernel(Dcn p, const float* 
           float* o = doff_n + ((int64_t)(g * K + t) * 2) * plane + pix;
           o[0] += d * gh;      // this thread is the only writer of (n, g, t, pix) — channels are visited sequentially
           o[plane] += d * gw;
+          // d / d mask = the unmodulated sample (modulated_deformable_col2im_coord, kernel.cu:696-767)
+          if (dmask_n) dmask_n[(int64_t)(g * K + t) * plane + pix] += draw * (s.w1 * x1 + s.w2 * x2 + s.w3 * x3 + s.w4 * x4);
         }
       }
     }
@@ -184,8 +200,8 @@ __global__ void __launch_bounds__(256) dcn_bwd_input_kernel(Dcn p, const float* 
 
 // dw[co, c, t] += scale * sum_{pixels of this chunk} dy[co, pix] * col[(c,t), pix]
 __global__ void __launch_bounds__(256) dcn_bwd_weight_kernel(Dcn p, const float* __restrict__ x, const float* __restrict__ off,
-                                                             const float* __restrict__ dy, float* __restrict__ dw, float scale,
-                                                             int tiles_per_block) {
+                                                             const float* __restrict__ mask, const float* __restrict__ dy,
+                                                             float* __restrict__ dw, float scale, int tiles_per_block) {
   extern __shared__ float sm[];
   const int K = p.kh * p.kw, npix = p.Ho * p.Wo;
   float* col = sm;                   // [kCT*K][kPix]
@@ -195,6 +211,7 @@ __global__ void __launch_bounds__(256) dcn_bwd_weight_kernel(Dcn p, const float*
   const int nck = kCT * K, per = (nck + 3) / 4;
   const float* x_n = x + (int64_t)n * p.C * p.H * p.W;
   const float* off_n = off + (int64_t)n * p.dg * K * 2 * npix;
+  const float* mask_n = mask ? mask + (int64_t)n * p.dg * K * npix : nullptr;
   for (int cob = 0; cob < p.Cout; cob += 64) {
     float acc[18];
 #pragma unroll
@@ -203,7 +220,7 @@ __global__ void __launch_bounds__(256) dcn_bwd_weight_kernel(Dcn p, const float*
       const int pix0 = (blockIdx.x * tiles_per_block + tl) * kPix;
       if (pix0 >= npix) break;
       __syncthreads();
-      sample_tile(p, x_n, off_n, c0, pix0, col);
+      sample_tile(p, x_n, off_n, mask_n, c0, pix0, col);
       for (int i = threadIdx.x; i < 64 * kPix; i += blockDim.x) {
         const int px = i % kPix, co = i / kPix;
         dys[px * 64 + co] = (cob + co < p.Cout && pix0 + px < npix) ? dy[((int64_t)n * p.Cout + cob + co) * npix + pix0 + px] : 0.f;
@@ -239,6 +256,61 @@ int make(Dcn& d, int N, int C, int H, int W, int Cout, int kh, int kw, int strid
   return 0;
 }
 
+// dbias[co] += scale * sum_{n, pix} dy[n, co, pix]   (one CTA per output channel)
+__global__ void __launch_bounds__(256) dcn_bias_grad_kernel(const float* __restrict__ dy, float* __restrict__ dbias, int N, int Cout,
+                                                            int npix, float scale) {
+  __shared__ float red[8];
+  const int co = blockIdx.x;
+  float a = 0.f;
+  for (int n = 0; n < N; ++n) {
+    const float* r = dy + ((int64_t)n * Cout + co) * npix;
+    for (int i = threadIdx.x; i < npix; i += blockDim.x) a += __ldg(r + i);
+  }
+  a = warp_sum(a);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = a;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += red[i];
+    dbias[co] += scale * t;
+  }
+}
+
+int launch_fwd(const Dcn& d, const float* x, const float* offset, const float* mask, const float* w, const float* bias, float* y,
+               cudaStream_t st) {
+  dim3 grid(ceil_div((int64_t)d.Ho * d.Wo, kPix), d.N, ceil_div(d.Cout, 128));
+  dcn_fwd_kernel<<<grid, 256, kCT * d.kh * d.kw * kPix * sizeof(float), st>>>(d, x, offset, mask, w, bias, y);
+  RTP_LAUNCH_CHECK();
+}
+
+int launch_bwd_input(const Dcn& d, const float* x, const float* offset, const float* mask, const float* w, const float* dy, float* dx,
+                     float* doffset, float* dmask, cudaStream_t st, const char* who) {
+  const size_t smem = ((size_t)kCT * d.kh * d.kw * kPix + (size_t)d.Cout * kPix) * sizeof(float);
+  RTP_CHECK_ARG(smem <= 200 * 1024, "%s: Cout=%d too large", who, d.Cout);
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaFuncSetAttribute(dcn_bwd_input_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = smem;
+  }
+  const size_t taps = (size_t)d.N * d.dg * d.kh * d.kw * d.Ho * d.Wo;
+  cudaMemsetAsync(dx, 0, (size_t)d.N * d.C * d.H * d.W * sizeof(float), st);
+  cudaMemsetAsync(doffset, 0, taps * 2 * sizeof(float), st);
+  if (mask) cudaMemsetAsync(dmask, 0, taps * sizeof(float), st);
+  dim3 grid(ceil_div((int64_t)d.Ho * d.Wo, kPix), d.N);
+  dcn_bwd_input_kernel<<<grid, 256, smem, st>>>(d, x, offset, mask, w, dy, dx, doffset, dmask);
+  RTP_LAUNCH_CHECK();
+}
+
+int launch_bwd_weight(const Dcn& d, const float* x, const float* offset, const float* mask, const float* dy, float* dw, float scale,
+                      cudaStream_t st) {
+  const int tiles = ceil_div((int64_t)d.Ho * d.Wo, kPix);
+  const int tiles_per_block = tiles > 64 ? 16 : 1;
+  const size_t smem = ((size_t)kCT * d.kh * d.kw * kPix + 64 * kPix) * sizeof(float);
+  dim3 grid(ceil_div(tiles, tiles_per_block), d.N, ceil_div(d.C, kCT));
+  dcn_bwd_weight_kernel<<<grid, 256, smem, st>>>(d, x, offset, mask, dy, dw, scale, tiles_per_block);
+  RTP_LAUNCH_CHECK();
+}
+
 }  // namespace
 
 extern "C" int rtp_dcn_fwd(const float* x, const float* offset, const float* w, float* y, int32_t N, int32_t C, int32_t H,
@@ -247,9 +319,7 @@ extern "C" int rtp_dcn_fwd(const float* x, const float* offset, const float* w, 
   RTP_CHECK_ARG(x && offset && w && y, "rtp_dcn_fwd: null pointer");
   Dcn d;
   if (make(d, N, C, H, W, Cout, kh, kw, stride, pad, dil, dg, "rtp_dcn_fwd")) return -1;
-  dim3 grid(ceil_div((int64_t)d.Ho * d.Wo, kPix), N, ceil_div(Cout, 128));
-  dcn_fwd_kernel<<<grid, 256, kCT * kh * kw * kPix * sizeof(float), (cudaStream_t)stream>>>(d, x, offset, w, y);
-  RTP_LAUNCH_CHECK();
+  return launch_fwd(d, x, offset, nullptr, w, nullptr, y, (cudaStream_t)stream);
 }
 
 extern "C" int rtp_dcn_bwd_input(const float* x, const float* offset, const float* w, const float* dy, float* dx, float* doffset,
@@ -258,18 +328,7 @@ extern "C" int rtp_dcn_bwd_input(const float* x, const float* offset, const floa
   RTP_CHECK_ARG(x && offset && w && dy && dx && doffset, "rtp_dcn_bwd_input: null pointer");
   Dcn d;
   if (make(d, N, C, H, W, Cout, kh, kw, stride, pad, dil, dg, "rtp_dcn_bwd_input")) return -1;
-  const size_t smem = ((size_t)kCT * kh * kw * kPix + (size_t)Cout * kPix) * sizeof(float);
-  RTP_CHECK_ARG(smem <= 200 * 1024, "rtp_dcn_bwd_input: Cout=%d too large", Cout);
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaFuncSetAttribute(dcn_bwd_input_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = smem;
-  }
-  cudaMemsetAsync(dx, 0, (size_t)N * C * H * W * sizeof(float), (cudaStream_t)stream);
-  cudaMemsetAsync(doffset, 0, (size_t)N * dg * kh * kw * 2 * d.Ho * d.Wo * sizeof(float), (cudaStream_t)stream);
-  dim3 grid(ceil_div((int64_t)d.Ho * d.Wo, kPix), N);
-  dcn_bwd_input_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(d, x, offset, w, dy, dx, doffset);
-  RTP_LAUNCH_CHECK();
+  return launch_bwd_input(d, x, offset, nullptr, w, dy, dx, doffset, nullptr, (cudaStream_t)stream, "rtp_dcn_bwd_input");
 }
 
 extern "C" int rtp_dcn_bwd_weight(const float* x, const float* offset, const float* dy, float* dw, int32_t N, int32_t C, int32_t H,
@@ -278,10 +337,34 @@ extern "C" int rtp_dcn_bwd_weight(const float* x, const float* offset, const flo
   RTP_CHECK_ARG(x && offset && dy && dw, "rtp_dcn_bwd_weight: null pointer");
   Dcn d;
   if (make(d, N, C, H, W, Cout, kh, kw, stride, pad, dil, dg, "rtp_dcn_bwd_weight")) return -1;
-  const int tiles = ceil_div((int64_t)d.Ho * d.Wo, kPix);
-  const int tiles_per_block = tiles > 64 ? 16 : 1;
-  const size_t smem = ((size_t)kCT * kh * kw * kPix + 64 * kPix) * sizeof(float);
-  dim3 grid(ceil_div(tiles, tiles_per_block), N, ceil_div(C, kCT));
-  dcn_bwd_weight_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(d, x, offset, dy, dw, scale, tiles_per_block);
-  RTP_LAUNCH_CHECK();
+  return launch_bwd_weight(d, x, offset, nullptr, dy, dw, scale, (cudaStream_t)stream);
+}
+
+// ---- v2 (modulated) ---------------------------------------------------------------------------------------------
+extern "C" int rtp_mdcn_fwd(const float* x, const float* offset, const float* mask, const float* w, const float* bias, float* y,
+                            int32_t N, int32_t C, int32_t H, int32_t W, int32_t Cout, int32_t kh, int32_t kw, int32_t stride,
+                            int32_t pad, int32_t dil, int32_t dg, void* stream) {
+  RTP_CHECK_ARG(x && offset && mask && w && y, "rtp_mdcn_fwd: null pointer");
+  Dcn d;
+  if (make(d, N, C, H, W, Cout, kh, kw, stride, pad, dil, dg, "rtp_mdcn_fwd")) return -1;
+  return launch_fwd(d, x, offset, mask, w, bias, y, (cudaStream_t)stream);
+}
+
+extern "C" int rtp_mdcn_bwd_input(const float* x, const float* offset, const float* mask, const float* w, const float* dy, float* dx,
+                                  float* doffset, float* dmask, int32_t N, int32_t C, int32_t H, int32_t W, int32_t Cout,
+                                  int32_t kh, int32_t kw, int32_t stride, int32_t pad, int32_t dil, int32_t dg, void* stream) {
+  RTP_CHECK_ARG(x && offset && mask && w && dy && dx && doffset && dmask, "rtp_mdcn_bwd_input: null pointer");
+  Dcn d;
+  if (make(d, N, C, H, W, Cout, kh, kw, stride, pad, dil, dg, "rtp_mdcn_bwd_input")) return -1;
+  return launch_bwd_input(d, x, offset, mask, w, dy, dx, doffset, dmask, (cudaStream_t)stream, "rtp_mdcn_bwd_input");
+}
+
+extern "C" int rtp_mdcn_bwd_weight(const float* x, const float* offset, const float* mask, const float* dy, float* dw, float* dbias,
+                                   int32_t N, int32_t C, int32_t H, int32_t W, int32_t Cout, int32_t kh, int32_t kw,
+                                   int32_t stride, int32_t pad, int32_t dil, int32_t dg, float scale, void* stream) {
+  RTP_CHECK_ARG(x && offset && mask && dy && dw, "rtp_mdcn_bwd_weight: null pointer");
+  Dcn d;
+  if (make(d, N, C, H, W, Cout, kh, kw, stride, pad, dil, dg, "rtp_mdcn_bwd_weight")) return -1;
+  if (dbias) dcn_bias_grad_kernel<<<Cout, 256, 0, (cudaStream_t)stream>>>(dy, dbias, N, Cout, d.Ho * d.Wo, scale);
+  return launch_bwd_weight(d, x, offset, mask, dy, dw, scale, (cudaStream_t)stream);
 }

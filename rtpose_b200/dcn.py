@@ -1,10 +1,14 @@
-"""Deformable convolution v1 (2-D) with the reference's Python API.
+"""Deformable convolution v1 and v2 (2-D) with the reference's Python API (det3d/ops/dcn/__init__.py: DeformConv,
+DeformConvPack, ModulatedDeformConv, ModulatedDeformConvPack, deform_conv, modulated_deform_conv).
 
 Mirrors det3d/ops/dcn/deform_conv.py:14-112 (`DeformConvFunction`: forward / backward, 8-argument signature,
 `_output_size`) and :192-255 (`DeformConv` module: no bias, uniform(-1/sqrt(fan_in)) init, small-input padding
 work-around).  The kernels are librtpose_b200.so's rtp_dcn_* (no `columns` buffer, no im2col_step batching — the
 argument is accepted and ignored).  groups must be 1, as in every use the reference makes of the op
 (center_head.py:45-51: DeformConv(C, C, 3, padding=1, deformable_groups=4)).
+
+v2: `ModulatedDeformConvFunction` (deform_conv.py:115-186), `ModulatedDeformConv` (:326-379) and the two `*Pack` modules
+(:258-323, :382-446), whose offset/mask predictor is an ordinary nn.Conv2d exactly as in the reference; kernels rtp_mdcn_*.
 """
 import math
 
@@ -115,3 +119,153 @@ class DeformConv(nn.Module):
         if input_pad:
             out = out[:, :, :out.size(2) - pad_h, :out.size(3) - pad_w].contiguous()
         return out
+
+
+class DeformConvPack(DeformConv):
+    """det3d/ops/dcn/deform_conv.py:258-323: DeformConv that predicts its own offsets with a zero-initialised conv."""
+
+    _version = 2
+
+    def __init__(self, *args, **kwargs):
+        super(DeformConvPack, self).__init__(*args, **kwargs)
+        self.conv_offset = nn.Conv2d(self.in_channels, self.deformable_groups * 2 * self.kernel_size[0] * self.kernel_size[1],
+                                     kernel_size=self.kernel_size, stride=_pair(self.stride), padding=_pair(self.padding), bias=True)
+        self.init_offset()
+
+    def init_offset(self):
+        self.conv_offset.weight.data.zero_()
+        self.conv_offset.bias.data.zero_()
+
+    def forward(self, x):
+        return deform_conv(x, self.conv_offset(x), self.weight, self.stride, self.padding, self.dilation, self.groups,
+                           self.deformable_groups)
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
+        _rename_v1_offset_keys(state_dict, prefix, local_metadata)
+        super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs)
+
+
+def _rename_v1_offset_keys(state_dict, prefix, local_metadata):
+    """Checkpoints written before module version 2 call the predictor `<name>_offset` instead of `<name>.conv_offset`."""
+    version = local_metadata.get("version", None)
+    if version is None or version < 2:
+        for leaf in ("weight", "bias"):
+            new, old = prefix + "conv_offset." + leaf, prefix[:-1] + "_offset." + leaf
+            if new not in state_dict and old in state_dict:
+                state_dict[new] = state_dict.pop(old)
+
+
+class ModulatedDeformConvFunction(Function):
+    @staticmethod
+    def forward(ctx, input, offset, mask, weight, bias=None, stride=1, padding=0, dilation=1, groups=1, deformable_groups=1):
+        if not input.is_cuda:
+            raise NotImplementedError  # deform_conv.py:137-138
+        if input.dim() != 4:
+            raise ValueError("Expected 4D tensor as input, got {}D tensor instead.".format(input.dim()))
+        if groups != 1:
+            raise NotImplementedError("rtpose_b200 ModulatedDeformConv supports groups=1 only")
+        if any(isinstance(v, (tuple, list)) and v[0] != v[1] for v in (stride, padding, dilation)):
+            raise NotImplementedError("anisotropic stride/padding/dilation")
+        ctx.stride, ctx.padding, ctx.dilation = _pair(stride)[0], _pair(padding)[0], _pair(dilation)[0]
+        ctx.groups, ctx.deformable_groups, ctx.with_bias = groups, deformable_groups, bias is not None
+        input, offset, mask, weight = (t.contiguous().float() for t in (input, offset, mask, weight))
+        bias = bias.contiguous().float() if ctx.with_bias else None
+        N, Cc, H, W = input.shape
+        out_size = ModulatedDeformConvFunction._infer_shape(ctx, input, weight)
+        K = weight.shape[2] * weight.shape[3]
+        if offset.shape != (N, deformable_groups * 2 * K, out_size[2], out_size[3]):
+            raise ValueError("invalid offset shape {} for output {}".format(tuple(offset.shape), out_size))
+        if mask.shape != (N, deformable_groups * K, out_size[2], out_size[3]):
+            raise ValueError("invalid mask shape {} for output {}".format(tuple(mask.shape), out_size))
+        ctx.save_for_backward(input, offset, mask, weight)
+        output = input.new_empty(out_size)
+        lib.call("rtp_mdcn_fwd", input.data_ptr(), offset.data_ptr(), mask.data_ptr(), weight.data_ptr(),
+                 bias.data_ptr() if ctx.with_bias else None, output.data_ptr(), N, Cc, H, W, weight.shape[0], weight.shape[2],
+                 weight.shape[3], ctx.stride, ctx.padding, ctx.dilation, deformable_groups, _stream())
+        return output
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        if not grad_output.is_cuda:
+            raise NotImplementedError
+        input, offset, mask, weight = ctx.saved_tensors
+        grad_output = grad_output.contiguous().float()
+        N, Cc, H, W = input.shape
+        args = (N, Cc, H, W, weight.shape[0], weight.shape[2], weight.shape[3], ctx.stride, ctx.padding, ctx.dilation,
+                ctx.deformable_groups)
+        grad_input, grad_offset, grad_mask = torch.empty_like(input), torch.empty_like(offset), torch.empty_like(mask)
+        lib.call("rtp_mdcn_bwd_input", input.data_ptr(), offset.data_ptr(), mask.data_ptr(), weight.data_ptr(),
+                 grad_output.data_ptr(), grad_input.data_ptr(), grad_offset.data_ptr(), grad_mask.data_ptr(), *args, _stream())
+        grad_weight = torch.zeros_like(weight)
+        grad_bias = torch.zeros(weight.shape[0], dtype=torch.float32, device=weight.device) if ctx.with_bias else None
+        lib.call("rtp_mdcn_bwd_weight", input.data_ptr(), offset.data_ptr(), mask.data_ptr(), grad_output.data_ptr(),
+                 grad_weight.data_ptr(), grad_bias.data_ptr() if ctx.with_bias else None, *args, 1.0, _stream())
+        return (grad_input, grad_offset, grad_mask, grad_weight, grad_bias, None, None, None, None, None)
+
+    @staticmethod
+    def _infer_shape(ctx, input, weight):
+        n, channels_out = input.size(0), weight.size(0)
+        height, width = input.shape[2:4]
+        kernel_h, kernel_w = weight.shape[2:4]
+        height_out = (height + 2 * ctx.padding - (ctx.dilation * (kernel_h - 1) + 1)) // ctx.stride + 1
+        width_out = (width + 2 * ctx.padding - (ctx.dilation * (kernel_w - 1) + 1)) // ctx.stride + 1
+        return n, channels_out, height_out, width_out
+
+
+modulated_deform_conv = ModulatedDeformConvFunction.apply
+
+
+class ModulatedDeformConv(nn.Module):
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1, deformable_groups=1,
+                 bias=True):
+        super(ModulatedDeformConv, self).__init__()
+        self.in_channels, self.out_channels, self.kernel_size = in_channels, out_channels, _pair(kernel_size)
+        self.stride, self.padding, self.dilation = stride, padding, dilation
+        self.groups, self.deformable_groups, self.with_bias = groups, deformable_groups, bias
+        self.transposed, self.output_padding = False, _single(0)
+        self.weight = nn.Parameter(torch.Tensor(out_channels, in_channels // groups, *self.kernel_size))
+        if bias:
+            self.bias = nn.Parameter(torch.Tensor(out_channels))
+        else:
+            self.register_parameter("bias", None)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        n = self.in_channels
+        for k in self.kernel_size:
+            n *= k
+        stdv = 1.0 / math.sqrt(n)
+        self.weight.data.uniform_(-stdv, stdv)
+        if self.bias is not None:
+            self.bias.data.zero_()
+
+    def forward(self, x, offset, mask):
+        return modulated_deform_conv(x, offset, mask, self.weight, self.bias, self.stride, self.padding, self.dilation,
+                                     self.groups, self.deformable_groups)
+
+
+class ModulatedDeformConvPack(ModulatedDeformConv):
+    """det3d/ops/dcn/deform_conv.py:382-446: predicts 2K offset + K mask channels per deformable group with one
+    zero-initialised conv; mask = sigmoid of the last third, offset = the first two thirds concatenated."""
+
+    _version = 2
+
+    def __init__(self, *args, **kwargs):
+        super(ModulatedDeformConvPack, self).__init__(*args, **kwargs)
+        self.conv_offset = nn.Conv2d(self.in_channels, self.deformable_groups * 3 * self.kernel_size[0] * self.kernel_size[1],
+                                     kernel_size=self.kernel_size, stride=_pair(self.stride), padding=_pair(self.padding), bias=True)
+        self.init_offset()
+
+    def init_offset(self):
+        self.conv_offset.weight.data.zero_()
+        self.conv_offset.bias.data.zero_()
+
+    def forward(self, x):
+        o1, o2, mask = torch.chunk(self.conv_offset(x), 3, dim=1)
+        return modulated_deform_conv(x, torch.cat((o1, o2), dim=1), torch.sigmoid(mask), self.weight, self.bias, self.stride,
+                                     self.padding, self.dilation, self.groups, self.deformable_groups)
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
+        _rename_v1_offset_keys(state_dict, prefix, local_metadata)
+        super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs)

@@ -115,6 +115,9 @@ PROTOTYPES = {
     "rtp_dcn_fwd": (C.c_int, [_vp, _vp, _vp, _vp] + [_i32] * 11 + [_vp]),
     "rtp_dcn_bwd_input": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp] + [_i32] * 11 + [_vp]),
     "rtp_dcn_bwd_weight": (C.c_int, [_vp, _vp, _vp, _vp] + [_i32] * 11 + [_f32, _vp]),
+    "rtp_mdcn_fwd": (C.c_int, [_vp] * 6 + [_i32] * 11 + [_vp]),
+    "rtp_mdcn_bwd_input": (C.c_int, [_vp] * 8 + [_i32] * 11 + [_vp]),
+    "rtp_mdcn_bwd_weight": (C.c_int, [_vp] * 6 + [_i32] * 11 + [_f32, _vp]),
     "rtp_scale_f32": (C.c_int, [_vp, _i64, _f32, _vp]),
     "rtp_adam_workspace_bytes": (C.c_int64, []),
     "rtp_adam_step": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _i32, _f32, _vp, _vp, _vp]),
@@ -168,7 +171,7 @@ LAUNCHES = {"rtp_pack_ncdhw": 1, "rtp_unpack_ncdhw": 1, "rtp_ingest_pack": 1, "r
             "rtp_gn_sums": 2, "rtp_gn_finalize": 1, "rtp_gn_apply": 1, "rtp_gn_bwd_reduce": 2, "rtp_gn_bwd_apply": 1,
             "rtp_fuse_sum": 1, "rtp_upsample_bwd": 3, "rtp_grad_add": 1, "rtp_channel_sum": 2, "rtp_stem_fwd": 1,
             "rtp_stem_bwd": 2, "rtp_head_loss": 2, "rtp_decode": 1, "rtp_scale_f32": 1, "rtp_dcn_fwd": 1,
-            "rtp_dcn_bwd_input": 1, "rtp_dcn_bwd_weight": 1, "rtp_adam_step": 2, "rtp_adam_step_dev": 2,
+            "rtp_dcn_bwd_input": 1, "rtp_dcn_bwd_weight": 1, "rtp_mdcn_fwd": 1, "rtp_mdcn_bwd_input": 1, "rtp_mdcn_bwd_weight": 2, "rtp_adam_step": 2, "rtp_adam_step_dev": 2,
             "rtp_assign_targets": 2, "rtp_wgrad_k3s1": 1, "rtp_wgrad_k3s1_reduce": 1, "rtp_conv_pw": 1, "rtp_gn_apply_s2d": 1, "rtp_gn_bwd_reduce_s2d": 2,
             "rtp_gn_bwd_apply_s2d": 1, "rtp_conv_k3s1_stat_finalize": 1, "rtp_conv_multi": 1, "rtp_gn_stats": 2,
             "rtp_npy_probe": 0, "rtp_npy_read_roi_slab": 0}  # host-only file readers

@@ -169,3 +169,24 @@ def test_shard_frames_partitions_exactly():
             assert spans[0][0] == 0 and spans[-1][1] == total
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             assert max(b - a for a, b in spans) - min(b - a for a, b in spans) <= 1
+
+
+def test_dcn_pack_modules_rename_pre_v2_checkpoint_keys():
+    """deform_conv.py:294-323 / :418-446: checkpoints older than module version 2 name the predictor `<name>_offset`;
+    the module's _load_from_state_dict hook moves those entries to `<name>.conv_offset` (hook called the way
+    nn.Module.load_state_dict calls it, with the whole checkpoint dict and the module's prefix)."""
+    import torch
+    from rtpose_b200.dcn import DeformConvPack, ModulatedDeformConvPack
+    for cls, ch in ((DeformConvPack, 18), (ModulatedDeformConvPack, 27)):
+        m = cls(4, 4, 3, padding=1, deformable_groups=1)
+        sd = {"conv2." + k: v.clone() for k, v in m.state_dict().items() if not k.startswith("conv_offset")}
+        sd["conv2_offset.weight"] = torch.full((ch, 4, 3, 3), 0.25)
+        sd["conv2_offset.bias"] = torch.full((ch,), -1.0)
+        missing, unexpected, errors = [], [], []
+        m._load_from_state_dict(sd, "conv2.", {}, True, missing, unexpected, errors)  # {} = no version metadata -> < 2
+        assert "conv2.conv_offset.weight" in sd and "conv2_offset.weight" not in sd and not errors and not missing
+        m.conv_offset._load_from_state_dict(sd, "conv2.conv_offset.", {}, True, missing, unexpected, errors)
+        assert float(m.conv_offset.weight.mean()) == 0.25 and float(m.conv_offset.bias.mean()) == -1.0 and not errors
+        keep = dict(sd)
+        m._load_from_state_dict(sd, "conv2.", {"version": 2}, True, missing, unexpected, errors)  # current version: untouched
+        assert sd.keys() == keep.keys()

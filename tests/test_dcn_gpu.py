@@ -42,3 +42,109 @@ def test_deform_conv_rejects_cpu_and_bad_rank():
         deform_conv(torch.zeros(1, 4, 5, 5), torch.zeros(1, 18, 5, 5), torch.zeros(4, 4, 3, 3), 1, 1, 1, 1, 1)
     with pytest.raises(ValueError):
         deform_conv(torch.zeros(1, 4, 2, 5, 5).cuda(), torch.zeros(1, 18, 5, 5).cuda(), torch.zeros(4, 4, 3, 3).cuda(), 1, 1, 1, 1, 1)
+
+
+MCASES = [(2, 8, 7, 9, 8, 3, 1, 1, 1, 4, True), (1, 16, 12, 10, 24, 3, 1, 1, 1, 4, False), (2, 8, 9, 11, 16, 3, 2, 1, 1, 2, True),
+          (1, 8, 8, 8, 8, 1, 1, 0, 1, 1, True), (1, 8, 10, 9, 8, 3, 1, 2, 2, 1, False), (1, 32, 16, 40, 32, 3, 1, 1, 1, 4, True)]
+
+
+@pytest.mark.parametrize("case", MCASES, ids=[str(c) for c in MCASES])
+def test_modulated_deform_conv_matches_torchvision(case):
+    """DCN v2 (det3d/ops/dcn/deform_conv.py:115-186, kernels deform_conv_cuda_kernel.cu:571-767): rtp_mdcn_* against
+    torchvision.ops.deform_conv2d with a mask (same arithmetic, mask channel order [dg][kh*kw])."""
+    from rtpose_b200.dcn import ModulatedDeformConv
+    N, Cc, H, W, Cout, k, stride, pad, dil, dg, with_bias = case
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(N, Cc, H, W, generator=g, requires_grad=True)
+    Ho = (H + 2 * pad - (dil * (k - 1) + 1)) // stride + 1
+    Wo = (W + 2 * pad - (dil * (k - 1) + 1)) // stride + 1
+    off = (torch.randn(N, dg * 2 * k * k, Ho, Wo, generator=g) * 1.5).requires_grad_(True)
+    mask = torch.sigmoid(torch.randn(N, dg * k * k, Ho, Wo, generator=g)).requires_grad_(True)
+    m = ModulatedDeformConv(Cc, Cout, k, stride=stride, padding=pad, dilation=dil, deformable_groups=dg, bias=with_bias)
+    if with_bias:
+        m.bias.data.copy_(torch.randn(Cout, generator=g))
+    w = m.weight.detach().clone().requires_grad_(True)
+    b = m.bias.detach().clone().requires_grad_(True) if with_bias else None
+    ref = tv.deform_conv2d(x, off, w, b, stride=stride, padding=pad, dilation=dil, mask=mask)
+    gy = torch.randn(ref.shape, generator=g)
+    ref.backward(gy)
+    m = m.cuda()
+    xc, oc, mc = (t.detach().cuda().requires_grad_(True) for t in (x, off, mask))
+    out = m(xc, oc, mc)
+    out.backward(gy.cuda())
+    torch.cuda.synchronize()
+    torch.testing.assert_close(out.detach().cpu(), ref.detach(), rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(xc.grad.cpu(), x.grad, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(oc.grad.cpu(), off.grad, rtol=1e-3, atol=1e-3)
+    torch.testing.assert_close(mc.grad.cpu(), mask.grad, rtol=1e-3, atol=1e-3)
+    torch.testing.assert_close(m.weight.grad.cpu(), w.grad, rtol=1e-4, atol=1e-3)
+    if with_bias:
+        torch.testing.assert_close(m.bias.grad.cpu(), b.grad, rtol=1e-4, atol=1e-3)
+
+
+def test_far_outside_and_nan_offsets_never_become_addresses():
+    """Sampling positions far outside the image (or NaN) are 'invalid' (deform_conv_cuda_kernel.cu:229): they contribute
+    0 and must not be dereferenced.  x sits at the very end of its allocation so a stray read would fault or pick up the
+    NaN guard that follows it."""
+    from rtpose_b200.dcn import deform_conv
+    g = torch.Generator().manual_seed(2)
+    buf = torch.full((2 * 8 * 6 * 7 + 4096,), float("nan")).cuda()
+    x = buf[:2 * 8 * 6 * 7].view(2, 8, 6, 7)
+    x.copy_(torch.randn(2, 8, 6, 7, generator=g))
+    w = torch.randn(4, 8, 3, 3, generator=g).cuda()
+    off = torch.zeros(2, 18, 6, 7)
+    off[:, 0::2] = torch.tensor([1e4, -1e4, 6.0, 40.0, -7.5, 5.5, 1e9, float("nan"), 0.25])[None, :, None, None]
+    off[:, 1::2] = torch.tensor([0.0, 3.0, 1e4, 0.5, -1e9, 6.5, 7.0, 0.0, float("nan")])[None, :, None, None]
+    out = deform_conv(x, off.cuda(), w, 1, 1, 1, 1, 1)
+    ref = tv.deform_conv2d(x.cpu(), torch.nan_to_num(off, nan=1e9), w.cpu(), None, padding=1)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out).all()
+    torch.testing.assert_close(out.cpu(), ref, rtol=1e-4, atol=1e-4)
+
+
+def test_mask_of_ones_is_v1_bitwise():
+    from rtpose_b200.dcn import deform_conv, modulated_deform_conv
+    g = torch.Generator().manual_seed(9)
+    x, w = torch.randn(2, 16, 10, 12, generator=g).cuda(), torch.randn(8, 16, 3, 3, generator=g).cuda()
+    off = (torch.randn(2, 4 * 18, 10, 12, generator=g) * 2).cuda()
+    a = deform_conv(x, off, w, 1, 1, 1, 1, 4)
+    b = modulated_deform_conv(x, off, torch.ones(2, 4 * 9, 10, 12).cuda(), w, None, 1, 1, 1, 1, 4)
+    assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("modulated", [False, True])
+def test_pack_modules(modulated):
+    """*Pack modules (deform_conv.py:258-323, :382-446): with the zero-initialised predictor the op is a plain conv
+    (x 0.5 for v2: sigmoid(0)); with a trained predictor it equals predictor -> torchvision deform_conv2d."""
+    import torch.nn.functional as F
+    from rtpose_b200.dcn import DeformConvPack, ModulatedDeformConvPack
+    torch.manual_seed(1)
+    m = (ModulatedDeformConvPack(8, 16, 3, padding=1, deformable_groups=2, bias=True) if modulated
+         else DeformConvPack(8, 16, 3, padding=1, deformable_groups=2)).cuda()
+    x = torch.randn(2, 8, 9, 11).cuda()
+    plain = F.conv2d(x.cpu(), m.weight.detach().cpu(), None, padding=1)
+    torch.testing.assert_close(m(x).detach().cpu(), plain * (0.5 if modulated else 1.0), rtol=1e-4, atol=1e-4)
+    m.conv_offset.weight.data.normal_(0, 0.1)
+    m.conv_offset.bias.data.normal_(0, 0.5)
+    pred = F.conv2d(x.cpu(), m.conv_offset.weight.detach().cpu(), m.conv_offset.bias.detach().cpu(), padding=1)
+    if modulated:
+        o1, o2, mk = torch.chunk(pred, 3, dim=1)
+        ref = tv.deform_conv2d(x.cpu(), torch.cat((o1, o2), 1), m.weight.detach().cpu(), m.bias.detach().cpu(), padding=1,
+                               mask=torch.sigmoid(mk))
+    else:
+        ref = tv.deform_conv2d(x.cpu(), pred, m.weight.detach().cpu(), None, padding=1)
+    out = m(x)
+    out.sum().backward()
+    assert m.conv_offset.weight.grad is not None and m.weight.grad is not None
+    torch.testing.assert_close(out.detach().cpu(), ref, rtol=2e-3, atol=2e-3)  # the predictor conv runs in TF32/fp32 on the GPU
+
+
+def test_modulated_rejects_cpu_and_bad_shapes():
+    from rtpose_b200.dcn import modulated_deform_conv
+    with pytest.raises(NotImplementedError):
+        modulated_deform_conv(torch.zeros(1, 4, 5, 5), torch.zeros(1, 18, 5, 5), torch.zeros(1, 9, 5, 5), torch.zeros(4, 4, 3, 3), None, 1, 1)
+    z = lambda *s: torch.zeros(*s).cuda()
+    with pytest.raises(ValueError, match="mask shape"):
+        modulated_deform_conv(z(1, 4, 5, 5), z(1, 18, 5, 5), z(1, 8, 5, 5), z(4, 4, 3, 3), None, 1, 1)
+    with pytest.raises(ValueError, match="offset shape"):
+        modulated_deform_conv(z(1, 4, 5, 5), z(1, 18, 4, 5), z(1, 9, 5, 5), z(4, 4, 3, 3), None, 1, 1)
