@@ -362,6 +362,17 @@ int rtp_assign_targets(const double* poses, int32_t B, int32_t Z, int32_t Y, int
                        const double* voxel_xyz, const float* range_xyz, float* hm, int64_t* ind, uint8_t* mask,
                        int64_t* cat, float* anno, void* stream);
 
+/* N4 pose-error metrics on the device.  replaces: PJPE / ABS_PJPE (eval_util.py:5-11) and the per-sequence, per-joint
+ * means of CRUW_POSE_Dataset.evaluation (det3d/datasets/cruw_pose/cruw_pose.py:277-295).
+ * pred_xyz: device fp32 [N][J][3] (rtp_decode's out_xyz: J = 15 rows of 3 for `hr3d`, one row of 45 for `one_hm`);
+ * gt_xyz: device fp64 [N][J][3] (the label file's floats).  out_rel = root-relative error (joint 0 subtracted on both
+ * sides), out_abs = absolute error, both fp64 [N][J] in metres, computed in the reference's fp64 operation order.
+ * rtp_pjpe_seq_mean: seq_index int32 [N] in [0,S) -> means over each sequence's frames x 1000 (millimetres),
+ * fp64 [S][J] each, and the frame count per sequence (0 frames -> 0). */
+int rtp_pjpe(const float* pred_xyz, const double* gt_xyz, int32_t N, int32_t J, double* out_rel, double* out_abs, void* stream);
+int rtp_pjpe_seq_mean(const double* rel, const double* abs_, const int32_t* seq_index, int32_t N, int32_t J, int32_t S,
+                      double* out_rel_mm, double* out_abs_mm, int32_t* out_count, void* stream);
+
 /* ---- flat-buffer helpers for the data-parallel step ----------------------------------------------------------
  * replaces: _allreduce_coalesced's flatten / div_ / copy-back (det3d/core/utils/dist_utils.py:8-28); the
  * collective itself is ncclAllReduce issued by torch.distributed on the same flat buffer. */

@@ -407,3 +407,39 @@ def batch_targets(poses, grid_zyx, one_hm):
     # min_radius: 2 for the one_hm configs (hr3d_one_hm.py:107), 1 for hr3d (hr3d.py:108)
     ts = [assign_targets(p, grid_zyx, one_hm, radius=2 if one_hm else 1) for p in poses]
     return {k: torch.from_numpy(np.stack([t[k] for t in ts])) for k in ts[0]}
+
+
+# ------------------------------------------------------------------------------------------------ evaluation
+def abs_pjpe(pred, gt):
+    """eval_util.py:10-11 — per-joint Euclidean error, float64 [J]."""
+    d = np.asarray(pred, dtype=np.float64) - np.asarray(gt, dtype=np.float64)
+    return np.sqrt((d * d).sum(axis=-1))
+
+
+def pjpe(pred, gt):
+    """eval_util.py:5-8 — the same after subtracting joint 0 (the root) on both sides."""
+    pred, gt = np.array(pred, dtype=np.float64), np.array(gt, dtype=np.float64)
+    return abs_pjpe(pred - pred[:1], gt - gt[:1])
+
+
+def evaluation(detections, gt, seq_id_to_name):
+    """det3d/datasets/cruw_pose/cruw_pose.py:277-310: per-sequence, per-joint mean errors in millimetres, their means,
+    and the mean over sequences.  detections: {'seq/frame/rdr_frame': {'keypoints': [(label, x, y, z, score)] * 15}};
+    gt: {seq: {frame: [{'pose': [[x, y, z]] * 15}]}}."""
+    rel, ab = {}, {}
+    for key, val in detections.items():
+        seq, frame, _ = key.split("/")
+        kp = [p[1:4] for p in val["keypoints"]]
+        rel.setdefault(seq, []).append(pjpe(kp, gt[seq][frame][0]["pose"]))
+        ab.setdefault(seq, []).append(abs_pjpe(kp, gt[seq][frame][0]["pose"]))
+    seq_res = {}
+    for seq in rel:
+        r, a = np.mean(np.array(rel[seq]), axis=0) * 1000, np.mean(np.array(ab[seq]), axis=0) * 1000
+        out = {"MPJPE": np.mean(r), "ABS_MPJPE": np.mean(a)}
+        for j in range(r.shape[0]):
+            out["PJPE_%d" % j], out["ABS_PJPE_%d" % j] = r[j], a[j]
+        seq_res[seq_id_to_name[seq]] = out
+    total = {k: np.mean([v[k] for v in seq_res.values()]) for k in ["MPJPE", "ABS_MPJPE"] +
+             [p % j for j in range(15) for p in ("PJPE_%d", "ABS_PJPE_%d")]}
+    seq_res["ALL"] = total
+    return {"results": total, "seq_results": seq_res}
