@@ -322,6 +322,14 @@ int rtp_dcn_bwd_weight(const float* x, const float* offset, const float* dy, flo
                        int32_t H, int32_t W, int32_t Cout, int32_t kh, int32_t kw, int32_t stride, int32_t pad,
                        int32_t dil, int32_t dg, float scale, void* stream);
 
+/* Tensor-core forward, step 1 of 2: deformed im2col as a bf16 P8 volume whose z axis is the tap index,
+ * dst[n][c/8][t = i*kw+j][wo][ho][c%8] (dst: N, C8*8 >= C, Z = kh*kw, Y = Ho, X = Wo; halo left untouched, i.e. zero).
+ * mask = NULL for v1.  Step 2 is rtp_conv with taps {(tz = t, tx = 0, ty = 0, wt = t)}, row grid (1, Wo, Ho) and the weight
+ * packed by rtp_weight_pack(ntaps = kh*kw): the contraction over C*kh*kw runs on tcgen05 with fp32 accumulation instead of
+ * the reference's fp32 `columns` x cuBLAS GEMM (deform_conv_cuda.cpp:196-247).  (C / dg) % 8 == 0, N*dg*kh*kw <= 65535. */
+int rtp_dcn_sample_p8(const float* x, const float* offset, const float* mask, rtp_p8 dst, int32_t N, int32_t C, int32_t H,
+                      int32_t W, int32_t kh, int32_t kw, int32_t stride, int32_t pad, int32_t dil, int32_t dg, void* stream);
+
 /* ---- deformable convolution v2 ("modulated", 2-D) ---------------------------------------------------------------
  * replaces: modulated_deform_conv_cuda_forward / modulated_deform_conv_cuda_backward
  * (det3d/ops/dcn/src/deform_conv_cuda.cpp:490-684; kernels deform_conv_cuda_kernel.cu:467-867; bound at

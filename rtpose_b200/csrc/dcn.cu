@@ -246,6 +246,58 @@ __global__ void __launch_bounds__(256) dcn_bwd_weight_kernel(Dcn p, const float*
   }
 }
 
+// Tensor-core path, step 1: the deformed im2col tensor as a bf16 P8 volume whose z axis is the tap index,
+// S[n][c/8][t][wo][ho][c%8] = mask * bilinear(x[n, c], p(ho, wo) + tap t + offset); step 2 is rtp_conv on it with the tap
+// list {(tz = t, 0, 0)} — a 1x1 conv over K = C*kh*kw accumulated in TMEM (fp32).
+// One thread per (n, deformable group, tap, ho, wo) computes the sampling geometry once and reuses it for all channels
+// of the group.  A CTA covers 32 wo x 8 ho: while sampling, lanes run along wo (the fastest axis of x and of the offsets,
+// so the corner reads of neighbouring lanes share cache lines); each 8-channel result goes through a shared-memory
+// transpose so that the stores run along ho, the fastest P8 axis (8 x 16 B = 128 contiguous bytes per wo).
+__global__ void __launch_bounds__(256) dcn_sample_p8_kernel(Dcn p, const float* __restrict__ x, const float* __restrict__ off,
+                                                            const float* __restrict__ mask, P8 dst) {
+  __shared__ uint4 stage[8][33];
+  const int K = p.kh * p.kw, npix = p.Ho * p.Wo, cpg = p.C / p.dg;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wo = blockIdx.x * 32 + lane, ho = blockIdx.y * 8 + warp;
+  int b = blockIdx.z;
+  const int t = b % K;
+  b /= K;
+  const int g = b % p.dg, n = b / p.dg;
+  const bool live = ho < p.Ho && wo < p.Wo;
+  Sample s;
+  s.w1 = s.w2 = s.w3 = s.w4 = 0.f;
+  s.o1 = s.o2 = s.o3 = s.o4 = 0;
+  if (live) {
+    const float* off_n = off + (int64_t)n * p.dg * K * 2 * npix;
+    float h, w;
+    tap_pos(p, off_n, g, t, ho, wo, h, w);
+    s = make_sample(p, h, w);
+    if (mask) {
+      const float m = __ldg(mask + ((int64_t)n * p.dg * K + g * K + t) * npix + (int64_t)ho * p.Wo + wo);
+      s.w1 *= m, s.w2 *= m, s.w3 *= m, s.w4 *= m;
+    }
+  }
+  const int64_t plane = (int64_t)p.H * p.W;
+  const float* xg = x + ((int64_t)n * p.C + (int64_t)g * cpg) * plane;
+  // store role: 8 consecutive threads cover the 8 ho of one wo
+  const int s_ho = threadIdx.x & 7, s_wo = threadIdx.x >> 3;
+  const int st_ho = blockIdx.y * 8 + s_ho, st_wo = blockIdx.x * 32 + s_wo;
+  const bool st_live = st_ho < p.Ho && st_wo < p.Wo;
+  bf16* d = dst.ptr + (int64_t)n * dst.n_stride + dst.voxel(t, st_wo, st_ho);
+  for (int c0 = 0; c0 < cpg; c0 += 8) {  // cpg % 8 == 0 (checked by the host): a chunk never straddles two groups
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float* xc = xg + (int64_t)(c0 + k) * plane;
+      v[k] = s.w1 * __ldg(xc + s.o1) + s.w2 * __ldg(xc + s.o2) + s.w3 * __ldg(xc + s.o3) + s.w4 * __ldg(xc + s.o4);
+    }
+    stage[warp][lane] = pack8(v);
+    __syncthreads();
+    if (st_live) stg16(d + (int64_t)((g * cpg + c0) >> 3) * dst.c_stride, stage[s_ho][s_wo]);
+    __syncthreads();
+  }
+}
+
 int make(Dcn& d, int N, int C, int H, int W, int Cout, int kh, int kw, int stride, int pad, int dil, int dg, const char* who) {
   RTP_CHECK_ARG(N > 0 && C > 0 && H > 0 && W > 0 && Cout > 0 && kh > 0 && kw > 0 && stride > 0 && dil > 0 && dg > 0, "%s: bad sizes", who);
   RTP_CHECK_ARG(C % dg == 0, "%s: input channels %d not divisible by deformable groups %d", who, C, dg);
@@ -338,6 +390,22 @@ extern "C" int rtp_dcn_bwd_weight(const float* x, const float* offset, const flo
   Dcn d;
   if (make(d, N, C, H, W, Cout, kh, kw, stride, pad, dil, dg, "rtp_dcn_bwd_weight")) return -1;
   return launch_bwd_weight(d, x, offset, nullptr, dy, dw, scale, (cudaStream_t)stream);
+}
+
+extern "C" int rtp_dcn_sample_p8(const float* x, const float* offset, const float* mask, rtp_p8 dst, int32_t N, int32_t C, int32_t H,
+                                 int32_t W, int32_t kh, int32_t kw, int32_t stride, int32_t pad, int32_t dil, int32_t dg,
+                                 void* stream) {
+  RTP_CHECK_ARG(x && offset && dst.ptr, "rtp_dcn_sample_p8: null pointer");
+  Dcn d;
+  if (make(d, N, C, H, W, 1, kh, kw, stride, pad, dil, dg, "rtp_dcn_sample_p8")) return -1;
+  RTP_CHECK_ARG((C / dg) % 8 == 0, "rtp_dcn_sample_p8: channels per deformable group (%d) must be a multiple of 8", C / dg);
+  RTP_CHECK_ARG(dst.N == N && dst.C8 * 8 >= C && dst.Z == kh * kw && dst.Y == d.Ho && dst.X == d.Wo,
+                "rtp_dcn_sample_p8: dst must be P8 [N=%d][C>=%d][Z=%d taps][Y=%d][X=%d]", N, C, kh * kw, d.Ho, d.Wo);
+  RTP_CHECK_ARG((int64_t)N * dg * kh * kw <= 65535, "rtp_dcn_sample_p8: N*dg*taps = %lld exceeds the grid limit; split the batch",
+                (long long)N * dg * kh * kw);
+  dim3 grid(ceil_div(d.Wo, 32), ceil_div(d.Ho, 8), N * dg * kh * kw);
+  dcn_sample_p8_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d, x, offset, mask, P8(dst));
+  RTP_LAUNCH_CHECK();
 }
 
 // ---- v2 (modulated) ---------------------------------------------------------------------------------------------

@@ -11,6 +11,7 @@ v2: `ModulatedDeformConvFunction` (deform_conv.py:115-186), `ModulatedDeformConv
 (:258-323, :382-446), whose offset/mask predictor is an ordinary nn.Conv2d exactly as in the reference; kernels rtp_mdcn_*.
 """
 import math
+import os
 
 import torch
 import torch.nn.functional as F
@@ -24,6 +25,57 @@ from . import lib
 
 def _stream():
     return torch.cuda.current_stream().cuda_stream
+
+
+# Forward contraction on the tcgen05 tensor cores (bf16 operands, fp32 accumulation) instead of the fp32 CUDA-core kernel:
+# the deformed samples are written once as a bf16 P8 volume with the taps on the z axis (rtp_dcn_sample_p8) and contracted
+# by rtp_conv.  Off by default because it changes the op's precision from fp32 to bf16-in / fp32-accumulate (what the rest
+# of the path computes in); enable with RTP_DCN_TC=1 or `rtpose_b200.dcn.TENSOR_CORE = True`.  The backward pass always uses
+# the fp32 kernels (gradients of the fp32 op evaluated at the same inputs).
+TENSOR_CORE = os.environ.get("RTP_DCN_TC", "0") not in ("", "0")
+TC_SAMPLE_BYTES = 512 << 20   # the sampled volume is produced and consumed in batch chunks of at most this size
+_tc_state = {}
+
+
+def tc_supported(C, Cout, kh, kw, dg):
+    return (C % dg == 0 and (C // dg) % 8 == 0 and -(-C // 16) * 16 <= 512 and -(-Cout // 16) * 16 <= 256 and kh * kw <= lib.MAX_TAPS)
+
+
+def _tc_forward(input, offset, mask, weight, bias, stride, pad, dil, dg, out_size):
+    """input fp32 [N,C,H,W] -> output fp32 [N,Cout,Ho,Wo] through rtp_dcn_sample_p8 + rtp_conv (+ rtp_unpack_ncdhw)."""
+    from . import ops
+    from .p8 import P8
+    N, Cc, H, W = input.shape
+    Cout, _, kh, kw = weight.shape
+    K, Ho, Wo = kh * kw, out_size[2], out_size[3]
+    if not tc_supported(Cc, Cout, kh, kw, dg):
+        raise lib.RtpError("tensor-core DCN needs (C/dg) %% 8 == 0, C <= 512, Cout <= 256 (got C=%d Cout=%d dg=%d)" % (Cc, Cout, dg))
+    KP, NP = -(-Cc // 16) * 16, -(-Cout // 16) * 16
+    per = (-(-Cc // 8)) * K * (Wo + 2) * (Ho + 2) * 16
+    nb = max(1, min(N, TC_SAMPLE_BYTES // per, 65535 // (dg * K)))
+    dev = input.device
+    key = (dev, nb, Cc, K, Ho, Wo, Cout)
+    st = _tc_state.get(key)
+    if st is None:  # zero-filled once: the kernels only ever write the interior, the halo stays zero
+        st = _tc_state[key] = {"S": P8(nb, Cc, K, Ho, Wo, device=dev), "Y": P8(nb, Cout, 1, Ho, Wo, device=dev), "w": None}
+    wkey = (weight.data_ptr(), weight._version, None if bias is None else (bias.data_ptr(), bias._version))
+    if st["w"] is None or st["w"][0] != wkey:
+        pack = torch.empty(K * KP * NP, dtype=torch.bfloat16, device=dev)
+        lib.call("rtp_weight_pack", weight.data_ptr(), pack.data_ptr(), Cout, Cc, K, 0, Cc, KP, NP, 0, _stream())
+        st["w"] = (wkey, pack, ops.pad_bias(bias, NP) if bias is not None else None)
+    _, pack, bias_p = st["w"]
+    taps = [(t, 0, 0, t) for t in range(K)]
+    out = input.new_empty(out_size)
+    for n0 in range(0, N, nb):
+        n = min(nb, N - n0)
+        S, Y = st["S"], st["Y"]
+        if n != nb:
+            S, Y = P8(n, Cc, K, Ho, Wo, buf=S.buf, offset=S.offset), P8(n, Cout, 1, Ho, Wo, buf=Y.buf, offset=Y.offset)
+        lib.call("rtp_dcn_sample_p8", input[n0:].data_ptr(), offset[n0:].data_ptr(), mask[n0:].data_ptr() if mask is not None else None,
+                 S.struct(), n, Cc, H, W, kh, kw, stride, pad, dil, dg, _stream())
+        ops.conv(S, pack, KP, NP, Y, taps, (1, Wo, Ho), bias=bias_p, real=(Cc, Cout))
+        lib.call("rtp_unpack_ncdhw", Y.struct(), out[n0:].data_ptr(), Cout, 0, _stream())
+    return out
 
 
 class DeformConvFunction(Function):
@@ -45,6 +97,9 @@ class DeformConvFunction(Function):
         N, Cc, H, W = input.shape
         if offset.shape != (N, deformable_groups * 2 * weight.shape[2] * weight.shape[3], out_size[2], out_size[3]):
             raise ValueError("invalid offset shape {} for output {}".format(tuple(offset.shape), out_size))
+        if TENSOR_CORE and tc_supported(Cc, weight.shape[0], weight.shape[2], weight.shape[3], deformable_groups):
+            return _tc_forward(input, offset, None, weight, None, ctx.stride[0], ctx.padding[0], ctx.dilation[0], deformable_groups,
+                               out_size)
         output = input.new_empty(out_size)
         lib.call("rtp_dcn_fwd", input.data_ptr(), offset.data_ptr(), weight.data_ptr(), output.data_ptr(), N, Cc, H, W,
                  weight.shape[0], weight.shape[2], weight.shape[3], ctx.stride[0], ctx.padding[0], ctx.dilation[0],
@@ -178,6 +233,8 @@ class ModulatedDeformConvFunction(Function):
         if mask.shape != (N, deformable_groups * K, out_size[2], out_size[3]):
             raise ValueError("invalid mask shape {} for output {}".format(tuple(mask.shape), out_size))
         ctx.save_for_backward(input, offset, mask, weight)
+        if TENSOR_CORE and tc_supported(Cc, weight.shape[0], weight.shape[2], weight.shape[3], deformable_groups):
+            return _tc_forward(input, offset, mask, weight, bias, ctx.stride, ctx.padding, ctx.dilation, deformable_groups, out_size)
         output = input.new_empty(out_size)
         lib.call("rtp_mdcn_fwd", input.data_ptr(), offset.data_ptr(), mask.data_ptr(), weight.data_ptr(),
                  bias.data_ptr() if ctx.with_bias else None, output.data_ptr(), N, Cc, H, W, weight.shape[0], weight.shape[2],

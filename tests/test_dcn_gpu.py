@@ -148,3 +148,45 @@ def test_modulated_rejects_cpu_and_bad_shapes():
         modulated_deform_conv(z(1, 4, 5, 5), z(1, 18, 5, 5), z(1, 8, 5, 5), z(4, 4, 3, 3), None, 1, 1)
     with pytest.raises(ValueError, match="offset shape"):
         modulated_deform_conv(z(1, 4, 5, 5), z(1, 18, 4, 5), z(1, 9, 5, 5), z(4, 4, 3, 3), None, 1, 1)
+
+
+TC_CASES = [(2, 32, 12, 20, 32, 3, 1, 1, 1, 4, False), (3, 64, 16, 40, 48, 3, 1, 1, 1, 4, True), (1, 128, 64, 160, 128, 3, 1, 1, 1, 4, False),
+            (2, 16, 9, 11, 24, 3, 2, 1, 1, 2, True), (1, 32, 10, 9, 16, 1, 1, 0, 1, 1, True)]
+
+
+@pytest.mark.parametrize("case", TC_CASES, ids=[str(c) for c in TC_CASES])
+def test_tensor_core_forward(case, monkeypatch):
+    """RTP_DCN_TC path (rtp_dcn_sample_p8 + rtp_conv on tcgen05): bf16 operands, fp32 accumulation -> the conv tolerance of
+    SURVEY.md §8c (1), |d| <= 2^-7 * max|ref|, against torchvision's fp32 op; v1 and v2 (mask, bias); the batch is also
+    pushed through in chunks (TC_SAMPLE_BYTES) and must give the same bits."""
+    from rtpose_b200 import dcn
+    N, Cc, H, W, Cout, k, stride, pad, dil, dg, modulated = case
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(N, Cc, H, W, generator=g)
+    Ho = (H + 2 * pad - (dil * (k - 1) + 1)) // stride + 1
+    Wo = (W + 2 * pad - (dil * (k - 1) + 1)) // stride + 1
+    off = torch.randn(N, dg * 2 * k * k, Ho, Wo, generator=g) * 1.5
+    w = torch.randn(Cout, Cc, k, k, generator=g) / (Cc * k * k) ** 0.5
+    mask = torch.sigmoid(torch.randn(N, dg * k * k, Ho, Wo, generator=g)) if modulated else None
+    bias = torch.randn(Cout, generator=g) if modulated else None
+    ref = tv.deform_conv2d(x, off, w, bias, stride=stride, padding=pad, dilation=dil, mask=mask)
+    monkeypatch.setattr(dcn, "TENSOR_CORE", True)
+
+    def run():
+        if modulated:
+            return dcn.modulated_deform_conv(x.cuda(), off.cuda(), mask.cuda(), w.cuda(), bias.cuda(), stride, pad, dil, 1, dg)
+        return dcn.deform_conv(x.cuda(), off.cuda(), w.cuda(), stride, pad, dil, 1, dg)
+    out = run()
+    torch.cuda.synchronize()
+    err, lim = (out.cpu() - ref).abs().max().item(), 2.0 ** -7 * ref.abs().max().item()
+    assert err <= lim, "max abs err %.4g > %.4g" % (err, lim)
+    if N > 1:
+        per = -(-Cc // 8) * k * k * (Wo + 2) * (Ho + 2) * 16
+        monkeypatch.setattr(dcn, "TC_SAMPLE_BYTES", per)  # one sample per chunk
+        assert torch.equal(run(), out)
+    # gradients still flow (fp32 kernels) when the forward ran on the tensor cores
+    xg = x.cuda().requires_grad_(True)
+    y = dcn.modulated_deform_conv(xg, off.cuda(), mask.cuda(), w.cuda(), bias.cuda(), stride, pad, dil, 1, dg) if modulated else \
+        dcn.deform_conv(xg, off.cuda(), w.cuda(), stride, pad, dil, 1, dg)
+    y.sum().backward()
+    assert xg.grad is not None and torch.isfinite(xg.grad).all()
