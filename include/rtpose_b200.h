@@ -330,6 +330,15 @@ int rtp_dcn_bwd_weight(const float* x, const float* offset, const float* dy, flo
 int rtp_dcn_sample_p8(const float* x, const float* offset, const float* mask, rtp_p8 dst, int32_t N, int32_t C, int32_t H,
                       int32_t W, int32_t kh, int32_t kw, int32_t stride, int32_t pad, int32_t dil, int32_t dg, void* stream);
 
+/* Tensor-core backward, last step.  ds: bf16 P8 gradient of the sample volume (layout of rtp_dcn_sample_p8; produced by
+ * kh*kw single-tap rtp_conv launches from dy with the dgrad-packed weight, output plane oz0 = t).  Overwrites dx
+ * (zero + atomic scatter), doffset and, when mask != NULL, dmask.  The weight gradient of this path is rtp_wgrad over
+ * (sample volume, dy) with the tap list {(t, 0, 0)}; rtp_dcn_bias_grad ACCUMULATES scale * sum_{n,pix} dy into dbias. */
+int rtp_dcn_col2im_p8(const float* x, const float* offset, const float* mask, rtp_p8 ds, float* dx, float* doffset, float* dmask,
+                      int32_t N, int32_t C, int32_t H, int32_t W, int32_t kh, int32_t kw, int32_t stride, int32_t pad,
+                      int32_t dil, int32_t dg, void* stream);
+int rtp_dcn_bias_grad(const float* dy, float* dbias, int32_t N, int32_t Cout, int32_t npix, float scale, void* stream);
+
 /* ---- deformable convolution v2 ("modulated", 2-D) ---------------------------------------------------------------
  * replaces: modulated_deform_conv_cuda_forward / modulated_deform_conv_cuda_backward
  * (det3d/ops/dcn/src/deform_conv_cuda.cpp:490-684; kernels deform_conv_cuda_kernel.cu:467-867; bound at

@@ -298,6 +298,60 @@ __global__ void __launch_bounds__(256) dcn_sample_p8_kernel(Dcn p, const float* 
   }
 }
 
+// Tensor-core backward, last step: dS (bf16 P8, taps on z; produced by rtp_conv from dy) -> dx (atomic scatter through
+// the bilinear weights), doffset and dmask.  One thread per (n, deformable group, tap, ho, wo) walks the channels of its
+// group, so doffset / dmask are plain stores of register sums; lanes run along ho, the contiguous axis of dS.
+__global__ void __launch_bounds__(256) dcn_col2im_p8_kernel(Dcn p, const float* __restrict__ x, const float* __restrict__ off,
+                                                            const float* __restrict__ mask, P8 ds, float* __restrict__ dx,
+                                                            float* __restrict__ doff, float* __restrict__ dmask) {
+  const int K = p.kh * p.kw, npix = p.Ho * p.Wo, cpg = p.C / p.dg;
+  const int ho = blockIdx.x * 32 + (threadIdx.x & 31), wo = blockIdx.y * 8 + (threadIdx.x >> 5);
+  int b = blockIdx.z;
+  const int t = b % K;
+  b /= K;
+  const int g = b % p.dg, n = b / p.dg;
+  if (ho >= p.Ho || wo >= p.Wo) return;
+  const int pix = ho * p.Wo + wo;
+  const float* off_n = off + (int64_t)n * p.dg * K * 2 * npix;
+  float h, w;
+  tap_pos(p, off_n, g, t, ho, wo, h, w);
+  const Sample s = make_sample(p, h, w);
+  const float mk = mask ? __ldg(mask + ((int64_t)n * p.dg * K + g * K + t) * npix + pix) : 1.f;
+  const int64_t plane = (int64_t)p.H * p.W;
+  const float* xg = x + ((int64_t)n * p.C + (int64_t)g * cpg) * plane;
+  float* dxg = dx + ((int64_t)n * p.C + (int64_t)g * cpg) * plane;
+  const bf16* d = ds.ptr + (int64_t)n * ds.n_stride + ds.voxel(t, wo, ho);
+  const float hw = 1.f - s.lw, hh = 1.f - s.lh;
+  const int h_low = (int)floorf(h), w_low = (int)floorf(w);
+  const bool tt = s.valid && h_low >= 0, bb = s.valid && h_low + 1 <= p.H - 1, ll = s.valid && w_low >= 0, rr = s.valid && w_low + 1 <= p.W - 1;
+  float goh = 0.f, gow = 0.f, gm = 0.f;
+  for (int c0 = 0; c0 < cpg; c0 += 8) {
+    float dv[8];
+    unpack8(ldg16(d + (int64_t)((g * cpg + c0) >> 3) * ds.c_stride), dv);
+    if (!s.valid) continue;  // an invalid position contributes nothing to any gradient
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float* xc = xg + (int64_t)(c0 + k) * plane;
+      float* dxc = dxg + (int64_t)(c0 + k) * plane;
+      const float draw = dv[k], dd = draw * mk;
+      // a corner outside the image reads as 0 in the slopes even where its bilinear weight happens to be 0
+      const float x1 = (tt && ll) ? __ldg(xc + s.o1) : 0.f, x2 = (tt && rr) ? __ldg(xc + s.o2) : 0.f;
+      const float x3 = (bb && ll) ? __ldg(xc + s.o3) : 0.f, x4 = (bb && rr) ? __ldg(xc + s.o4) : 0.f;
+      if (s.w1 != 0.f) atomicAdd(dxc + s.o1, dd * s.w1);
+      if (s.w2 != 0.f) atomicAdd(dxc + s.o2, dd * s.w2);
+      if (s.w3 != 0.f) atomicAdd(dxc + s.o3, dd * s.w3);
+      if (s.w4 != 0.f) atomicAdd(dxc + s.o4, dd * s.w4);
+      goh += dd * (-hw * x1 - s.lw * x2 + hw * x3 + s.lw * x4);
+      gow += dd * (-hh * x1 + hh * x2 - s.lh * x3 + s.lh * x4);
+      gm += draw * (s.w1 * x1 + s.w2 * x2 + s.w3 * x3 + s.w4 * x4);
+    }
+  }
+  float* o = doff + ((int64_t)n * p.dg * K + g * K + t) * 2 * npix + pix;
+  o[0] = goh;
+  o[npix] = gow;
+  if (dmask) dmask[((int64_t)n * p.dg * K + g * K + t) * npix + pix] = gm;
+}
+
 int make(Dcn& d, int N, int C, int H, int W, int Cout, int kh, int kw, int stride, int pad, int dil, int dg, const char* who) {
   RTP_CHECK_ARG(N > 0 && C > 0 && H > 0 && W > 0 && Cout > 0 && kh > 0 && kw > 0 && stride > 0 && dil > 0 && dg > 0, "%s: bad sizes", who);
   RTP_CHECK_ARG(C % dg == 0, "%s: input channels %d not divisible by deformable groups %d", who, C, dg);
@@ -405,6 +459,28 @@ extern "C" int rtp_dcn_sample_p8(const float* x, const float* offset, const floa
                 (long long)N * dg * kh * kw);
   dim3 grid(ceil_div(d.Wo, 32), ceil_div(d.Ho, 8), N * dg * kh * kw);
   dcn_sample_p8_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d, x, offset, mask, P8(dst));
+  RTP_LAUNCH_CHECK();
+}
+
+extern "C" int rtp_dcn_col2im_p8(const float* x, const float* offset, const float* mask, rtp_p8 ds, float* dx, float* doffset,
+                                 float* dmask, int32_t N, int32_t C, int32_t H, int32_t W, int32_t kh, int32_t kw, int32_t stride,
+                                 int32_t pad, int32_t dil, int32_t dg, void* stream) {
+  RTP_CHECK_ARG(x && offset && ds.ptr && dx && doffset && (!mask || dmask), "rtp_dcn_col2im_p8: null pointer");
+  Dcn d;
+  if (make(d, N, C, H, W, 1, kh, kw, stride, pad, dil, dg, "rtp_dcn_col2im_p8")) return -1;
+  RTP_CHECK_ARG((C / dg) % 8 == 0, "rtp_dcn_col2im_p8: channels per deformable group (%d) must be a multiple of 8", C / dg);
+  RTP_CHECK_ARG(ds.N == N && ds.C8 * 8 >= C && ds.Z == kh * kw && ds.Y == d.Ho && ds.X == d.Wo,
+                "rtp_dcn_col2im_p8: ds must be P8 [N=%d][C>=%d][Z=%d taps][Y=%d][X=%d]", N, C, kh * kw, d.Ho, d.Wo);
+  RTP_CHECK_ARG((int64_t)N * dg * kh * kw <= 65535, "rtp_dcn_col2im_p8: N*dg*taps exceeds the grid limit; split the batch");
+  cudaMemsetAsync(dx, 0, (size_t)N * C * H * W * sizeof(float), (cudaStream_t)stream);
+  dim3 grid(ceil_div(d.Ho, 32), ceil_div(d.Wo, 8), N * dg * kh * kw);
+  dcn_col2im_p8_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d, x, offset, mask, P8(ds), dx, doffset, mask ? dmask : nullptr);
+  RTP_LAUNCH_CHECK();
+}
+
+extern "C" int rtp_dcn_bias_grad(const float* dy, float* dbias, int32_t N, int32_t Cout, int32_t npix, float scale, void* stream) {
+  RTP_CHECK_ARG(dy && dbias && N > 0 && Cout > 0 && npix > 0, "rtp_dcn_bias_grad: bad arguments");
+  dcn_bias_grad_kernel<<<Cout, 256, 0, (cudaStream_t)stream>>>(dy, dbias, N, Cout, npix, scale);
   RTP_LAUNCH_CHECK();
 }
 

@@ -33,12 +33,65 @@ def _stream():
 # of the path computes in); enable with RTP_DCN_TC=1 or `rtpose_b200.dcn.TENSOR_CORE = True`.  The backward pass always uses
 # the fp32 kernels (gradients of the fp32 op evaluated at the same inputs).
 TENSOR_CORE = os.environ.get("RTP_DCN_TC", "0") not in ("", "0")
+# The same for the backward pass (RTP_DCN_TC_BWD=1 / TENSOR_CORE_BACKWARD): weight gradient = rtp_wgrad over (sample
+# volume, dy), sample gradient = kh*kw single-tap rtp_conv launches with the dgrad-packed weight, then rtp_dcn_col2im_p8
+# scatters it into dx / doffset / dmask.  Gradients then carry bf16 operand rounding like every other conv of the path.
+TENSOR_CORE_BACKWARD = os.environ.get("RTP_DCN_TC_BWD", "0") not in ("", "0")
 TC_SAMPLE_BYTES = 512 << 20   # the sampled volume is produced and consumed in batch chunks of at most this size
 _tc_state = {}
 
 
 def tc_supported(C, Cout, kh, kw, dg):
     return (C % dg == 0 and (C // dg) % 8 == 0 and -(-C // 16) * 16 <= 512 and -(-Cout // 16) * 16 <= 256 and kh * kw <= lib.MAX_TAPS)
+
+
+def _tc_chunk(N, Cc, K, Ho, Wo, dg):
+    per = (-(-Cc // 8)) * K * (Wo + 2) * (Ho + 2) * 16
+    return max(1, min(N, TC_SAMPLE_BYTES // per, 65535 // (dg * K)))
+
+
+def _tc_backward(input, offset, mask, weight, grad_output, with_bias, stride, pad, dil, dg):
+    """(grad_input, grad_offset, grad_mask | None, grad_weight, grad_bias | None) on the tensor-core path."""
+    from . import ops
+    from .p8 import P8
+    N, Cc, H, W = input.shape
+    Cout, _, kh, kw = weight.shape
+    K, Ho, Wo = kh * kw, grad_output.shape[2], grad_output.shape[3]
+    KPd, NPd = -(-Cout // 16) * 16, -(-Cc // 16) * 16  # dgrad GEMM: K = Cout, N = C
+    dev = input.device
+    nb = _tc_chunk(N, Cc, K, Ho, Wo, dg)
+    key = (dev, nb, Cc, K, Ho, Wo, Cout, "bwd")
+    st = _tc_state.get(key)
+    if st is None:
+        st = _tc_state[key] = {"S": P8(nb, Cc, K, Ho, Wo, device=dev), "w": None}
+    wkey = (weight.data_ptr(), weight._version)
+    if st["w"] is None or st["w"][0] != wkey:
+        pack = torch.empty(K * KPd * NPd, dtype=torch.bfloat16, device=dev)
+        lib.call("rtp_weight_pack", weight.data_ptr(), pack.data_ptr(), Cout, Cc, K, 0, Cc, KPd, NPd, 1, _stream())
+        st["w"] = (wkey, pack)
+    pack = st["w"][1]
+    grad_input, grad_offset = torch.empty_like(input), torch.empty_like(offset)
+    grad_mask = torch.empty_like(mask) if mask is not None else None
+    grad_weight = torch.empty_like(weight)
+    taps = [(t, 0, 0) for t in range(K)]
+    for n0 in range(0, N, nb):
+        n = min(nb, N - n0)
+        S = st["S"] if n == nb else P8(n, Cc, K, Ho, Wo, buf=st["S"].buf, offset=st["S"].offset)
+        mptr = mask[n0:].data_ptr() if mask is not None else None
+        lib.call("rtp_dcn_sample_p8", input[n0:].data_ptr(), offset[n0:].data_ptr(), mptr, S.struct(), n, Cc, H, W, kh, kw, stride, pad,
+                 dil, dg, _stream())
+        dY = P8.from_ncdhw(grad_output[n0:n0 + n].reshape(n, Cout, 1, Ho, Wo))
+        ops.conv_wgrad(S, dY, 1, 1, grad_weight, accumulate=n0 > 0, taps=taps)
+        for t in range(K):  # the sample volume is dead now: its buffer receives the sample gradient, one tap plane per launch
+            ops.conv(dY, pack, KPd, NPd, S, [(0, 0, 0, t)], (1, Wo, Ho), off=(t, 0, 0), real=(Cout, Cc))
+        lib.call("rtp_dcn_col2im_p8", input[n0:].data_ptr(), offset[n0:].data_ptr(), mptr, S.struct(), grad_input[n0:].data_ptr(),
+                 grad_offset[n0:].data_ptr(), grad_mask[n0:].data_ptr() if mask is not None else None, n, Cc, H, W, kh, kw, stride, pad,
+                 dil, dg, _stream())
+    grad_bias = None
+    if with_bias:
+        grad_bias = torch.zeros(Cout, dtype=torch.float32, device=dev)
+        lib.call("rtp_dcn_bias_grad", grad_output.data_ptr(), grad_bias.data_ptr(), N, Cout, Ho * Wo, 1.0, _stream())
+    return grad_input, grad_offset, grad_mask, grad_weight, grad_bias
 
 
 def _tc_forward(input, offset, mask, weight, bias, stride, pad, dil, dg, out_size):
@@ -51,8 +104,7 @@ def _tc_forward(input, offset, mask, weight, bias, stride, pad, dil, dg, out_siz
     if not tc_supported(Cc, Cout, kh, kw, dg):
         raise lib.RtpError("tensor-core DCN needs (C/dg) %% 8 == 0, C <= 512, Cout <= 256 (got C=%d Cout=%d dg=%d)" % (Cc, Cout, dg))
     KP, NP = -(-Cc // 16) * 16, -(-Cout // 16) * 16
-    per = (-(-Cc // 8)) * K * (Wo + 2) * (Ho + 2) * 16
-    nb = max(1, min(N, TC_SAMPLE_BYTES // per, 65535 // (dg * K)))
+    nb = _tc_chunk(N, Cc, K, Ho, Wo, dg)
     dev = input.device
     key = (dev, nb, Cc, K, Ho, Wo, Cout)
     st = _tc_state.get(key)
@@ -115,6 +167,10 @@ class DeformConvFunction(Function):
         args = (N, Cc, H, W, weight.shape[0], weight.shape[2], weight.shape[3], ctx.stride[0], ctx.padding[0],
                 ctx.dilation[0], ctx.deformable_groups)
         grad_input = grad_offset = grad_weight = None
+        if TENSOR_CORE_BACKWARD and tc_supported(Cc, weight.shape[0], weight.shape[2], weight.shape[3], ctx.deformable_groups):
+            grad_input, grad_offset, _, grad_weight, _ = _tc_backward(input, offset, None, weight, grad_output, False, ctx.stride[0],
+                                                                      ctx.padding[0], ctx.dilation[0], ctx.deformable_groups)
+            return (grad_input, grad_offset, grad_weight, None, None, None, None, None, None)
         if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
             grad_input, grad_offset = torch.empty_like(input), torch.empty_like(offset)
             lib.call("rtp_dcn_bwd_input", input.data_ptr(), offset.data_ptr(), weight.data_ptr(), grad_output.data_ptr(),
@@ -251,6 +307,9 @@ class ModulatedDeformConvFunction(Function):
         N, Cc, H, W = input.shape
         args = (N, Cc, H, W, weight.shape[0], weight.shape[2], weight.shape[3], ctx.stride, ctx.padding, ctx.dilation,
                 ctx.deformable_groups)
+        if TENSOR_CORE_BACKWARD and tc_supported(Cc, weight.shape[0], weight.shape[2], weight.shape[3], ctx.deformable_groups):
+            return _tc_backward(input, offset, mask, weight, grad_output, ctx.with_bias, ctx.stride, ctx.padding, ctx.dilation,
+                                ctx.deformable_groups) + (None, None, None, None, None)
         grad_input, grad_offset, grad_mask = torch.empty_like(input), torch.empty_like(offset), torch.empty_like(mask)
         lib.call("rtp_mdcn_bwd_input", input.data_ptr(), offset.data_ptr(), mask.data_ptr(), weight.data_ptr(),
                  grad_output.data_ptr(), grad_input.data_ptr(), grad_offset.data_ptr(), grad_mask.data_ptr(), *args, _stream())

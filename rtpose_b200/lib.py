@@ -118,6 +118,8 @@ PROTOTYPES = {
     "rtp_pjpe": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp, _vp]),
     "rtp_pjpe_seq_mean": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
     "rtp_dcn_sample_p8": (C.c_int, [_vp, _vp, _vp, P8Struct] + [_i32] * 10 + [_vp]),
+    "rtp_dcn_col2im_p8": (C.c_int, [_vp, _vp, _vp, P8Struct, _vp, _vp, _vp] + [_i32] * 10 + [_vp]),
+    "rtp_dcn_bias_grad": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _f32, _vp]),
     "rtp_mdcn_fwd": (C.c_int, [_vp] * 6 + [_i32] * 11 + [_vp]),
     "rtp_mdcn_bwd_input": (C.c_int, [_vp] * 8 + [_i32] * 11 + [_vp]),
     "rtp_mdcn_bwd_weight": (C.c_int, [_vp] * 6 + [_i32] * 11 + [_f32, _vp]),

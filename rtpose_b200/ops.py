@@ -556,18 +556,19 @@ def conv_wgrad_async(x, dy, k, stride, dW, accumulate=False, ci0=0, n0=0, more=(
     return None
 
 
-def conv_wgrad(x, dy, k, stride, dW, accumulate=False, ci0=0, n0=0, more=()):
+def conv_wgrad(x, dy, k, stride, dW, accumulate=False, ci0=0, n0=0, more=(), taps=None):
     """dW[:, ci0:ci0+x.C] (=|+=) wgrad(x, dy[:, n0:n0+dW.shape[0]]).  x: forward input (P8), dy: P8 gradient.
-    `more`: further (dW, accumulate, ci0, n0) outputs reduced from the same split-K workspace."""
+    `more`: further (dW, accumulate, ci0, n0) outputs reduced from the same split-K workspace.
+    `taps`: explicit (tz, tx, ty) list instead of the k^3 stencil (the DCN sample volume keeps its taps on the z axis)."""
     outs = ((dW, accumulate, ci0, n0),) + tuple(more)
-    if (USE_WGRAD_K3S1 and k == 3 and stride == 1 and x.C % 32 == 0 and x.c_stride == x.Z * (x.X + 2) * (x.Y + 2) * 8
+    if (taps is None and USE_WGRAD_K3S1 and k == 3 and stride == 1 and x.C % 32 == 0 and x.c_stride == x.Z * (x.X + 2) * (x.Y + 2) * 8
             and dy.c_stride == x.c_stride and all(o[3] % 8 == 0 for o in outs)
             and lib.load().rtp_wgrad_k3s1_supported(32, 32, x.Z, x.X, x.Y)):
         return _wgrad_k3s1(x, dy, outs)
     ci_n = x.C
     Cin8 = ceil_to(ci_n, 8)
     NP = ceil_to(dy.C, 16)
-    taps = taps_fwd(k)
+    taps = taps_fwd(k) if taps is None else taps
     d = lib.WgradDesc()
     d.x, d.dy = x.struct(), dy.struct()
     d.Cin, d.NP = Cin8, NP

@@ -190,3 +190,47 @@ def test_tensor_core_forward(case, monkeypatch):
         dcn.deform_conv(xg, off.cuda(), w.cuda(), stride, pad, dil, 1, dg)
     y.sum().backward()
     assert xg.grad is not None and torch.isfinite(xg.grad).all()
+
+
+@pytest.mark.parametrize("case", TC_CASES[:4], ids=[str(c) for c in TC_CASES[:4]])
+def test_tensor_core_backward(case, monkeypatch):
+    """RTP_DCN_TC_BWD path: weight gradient by rtp_wgrad over the sample volume, sample gradient by single-tap rtp_conv
+    launches, scatter by rtp_dcn_col2im_p8 — against torchvision's fp32 autograd with the conv tolerance (bf16 operands,
+    fp32 accumulation): |d| <= 2^-7 * max|ref| per gradient tensor (2^-6 for the offset gradient, a product of two
+    rounded factors).  Chunked execution must give the same input-side gradients bit for bit."""
+    from rtpose_b200 import dcn
+    N, Cc, H, W, Cout, k, stride, pad, dil, dg, modulated = case
+    g = torch.Generator().manual_seed(13)
+    x = torch.randn(N, Cc, H, W, generator=g, requires_grad=True)
+    Ho = (H + 2 * pad - (dil * (k - 1) + 1)) // stride + 1
+    Wo = (W + 2 * pad - (dil * (k - 1) + 1)) // stride + 1
+    off = (torch.randn(N, dg * 2 * k * k, Ho, Wo, generator=g) * 1.5).requires_grad_(True)
+    w = (torch.randn(Cout, Cc, k, k, generator=g) / (Cc * k * k) ** 0.5).requires_grad_(True)
+    mask = torch.sigmoid(torch.randn(N, dg * k * k, Ho, Wo, generator=g)).requires_grad_(True) if modulated else None
+    bias = torch.randn(Cout, generator=g).requires_grad_(True) if modulated else None
+    gy = torch.randn(N, Cout, Ho, Wo, generator=g)
+    tv.deform_conv2d(x, off, w, bias, stride=stride, padding=pad, dilation=dil, mask=mask).backward(gy)
+    monkeypatch.setattr(dcn, "TENSOR_CORE", True)
+    monkeypatch.setattr(dcn, "TENSOR_CORE_BACKWARD", True)
+
+    def run():
+        leaves = [t.detach().cuda().requires_grad_(True) if t is not None else None for t in (x, off, mask, w, bias)]
+        xc, oc, mc, wc, bc = leaves
+        y = dcn.modulated_deform_conv(xc, oc, mc, wc, bc, stride, pad, dil, 1, dg) if modulated else \
+            dcn.deform_conv(xc, oc, wc, stride, pad, dil, 1, dg)
+        y.backward(gy.cuda())
+        torch.cuda.synchronize()
+        return [t.grad.cpu() if t is not None else None for t in leaves]
+    got = run()
+    for name, a, r, tol in zip(("dx", "doffset", "dmask", "dw", "dbias"), got, (x, off, mask, w, bias),
+                               (2.0 ** -7, 2.0 ** -6, 2.0 ** -7, 2.0 ** -7, 1e-5)):
+        if r is None:
+            continue
+        err, lim = (a - r.grad).abs().max().item(), tol * r.grad.abs().max().item()
+        assert err <= lim, "%s: max abs err %.4g > %.4g" % (name, err, lim)
+    if N > 1:
+        per = -(-Cc // 8) * k * k * (Wo + 2) * (Ho + 2) * 16
+        monkeypatch.setattr(dcn, "TC_SAMPLE_BYTES", per)
+        again = run()
+        assert torch.equal(again[1], got[1]) and (mask is None or torch.equal(again[2], got[2]))  # per-sample quantities
+        torch.testing.assert_close(again[3], got[3], rtol=1e-4, atol=1e-5)  # dw: split-K order differs across chunkings

@@ -32,7 +32,10 @@ for (N, C) in ((16, 128), (32, 128), (16, 256)):
     def fb(fn):
         for t_ in (xr, orr, wr): t_.grad = None
         fn().sum().backward()
-    t = bench(lambda: fb(lambda: deform_conv(xr, orr, wr, 1, 1, 1, 1, dg)), 3)
-    print("N=%d C=%d ours fwd+bwd %.3f ms" % (N, C, t))
+    for name, tc in (("fp32 CUDA cores", False), ("tcgen05 bf16", True)):
+        D.TENSOR_CORE = D.TENSOR_CORE_BACKWARD = tc
+        t = bench(lambda: fb(lambda: deform_conv(xr, orr, wr, 1, 1, 1, 1, dg)), 3)
+        print("N=%d C=%d ours[%s] fwd+bwd %.3f ms" % (N, C, name, t))
+    D.TENSOR_CORE = D.TENSOR_CORE_BACKWARD = False
     t = bench(lambda: fb(lambda: tv.deform_conv2d(xr, orr, wr, None, padding=1)), 3)
     print("N=%d C=%d torchvision fwd+bwd %.3f ms" % (N, C, t))
