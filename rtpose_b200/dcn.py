@@ -385,3 +385,25 @@ class ModulatedDeformConvPack(ModulatedDeformConv):
     def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
         _rename_v1_offset_keys(state_dict, prefix, local_metadata)
         super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs)
+
+
+class FeatureAdaption(nn.Module):
+    """det3d/models/pose_heads/center_head.py:24-62: offsets from a zero-weight 1x1 conv (its bias keeps the default
+    init, as in the reference), DCN v1 with `deformable_groups` groups, ReLU.  state_dict keys: conv_offset.{weight,bias},
+    conv_adaption.weight."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=3, deformable_groups=4):
+        super(FeatureAdaption, self).__init__()
+        offset_channels = kernel_size * kernel_size * 2
+        self.conv_offset = nn.Conv2d(in_channels, deformable_groups * offset_channels, 1, bias=True)
+        self.conv_adaption = DeformConv(in_channels, out_channels, kernel_size=kernel_size, padding=(kernel_size - 1) // 2,
+                                        deformable_groups=deformable_groups)
+        self.relu = nn.ReLU(inplace=True)
+        self.init_offset()
+
+    def init_offset(self):
+        self.conv_offset.weight.data.zero_()
+
+    def forward(self, x):
+        offset = self.conv_offset(x)
+        return self.relu(self.conv_adaption(x, offset))

@@ -234,3 +234,29 @@ def test_tensor_core_backward(case, monkeypatch):
         again = run()
         assert torch.equal(again[1], got[1]) and (mask is None or torch.equal(again[2], got[2]))  # per-sample quantities
         torch.testing.assert_close(again[3], got[3], rtol=1e-4, atol=1e-5)  # dw: split-K order differs across chunkings
+
+
+@pytest.mark.parametrize("tc", [False, True])
+def test_feature_adaption(tc, monkeypatch):
+    """FeatureAdaption (center_head.py:24-62) = 1x1 offset predictor -> DCN v1 (dg 4) -> ReLU, against the same pipeline
+    built from torch / torchvision ops with the module's own parameters; fp32 kernels and the tensor-core path."""
+    import torch.nn.functional as F
+    from rtpose_b200 import dcn
+    monkeypatch.setattr(dcn, "TENSOR_CORE", tc)
+    monkeypatch.setattr(dcn, "TENSOR_CORE_BACKWARD", tc)
+    torch.manual_seed(3)
+    m = dcn.FeatureAdaption(32, 32, kernel_size=3, deformable_groups=4)
+    assert sorted(m.state_dict()) == ["conv_adaption.weight", "conv_offset.bias", "conv_offset.weight"]
+    assert float(m.conv_offset.weight.abs().sum()) == 0.0 and m.conv_offset.weight.shape == (72, 32, 1, 1)
+    m.conv_offset.weight.data.normal_(0, 0.2)  # a trained predictor
+    x = torch.randn(2, 32, 12, 20)
+    off = F.conv2d(x, m.conv_offset.weight, m.conv_offset.bias)
+    ref = F.relu(tv.deform_conv2d(x, off, m.conv_adaption.weight, None, padding=1))
+    m = m.cuda()
+    xc = x.cuda().requires_grad_(True)
+    out = m(xc)
+    out.sum().backward()
+    torch.cuda.synchronize()
+    tol = 2.0 ** -7 * ref.abs().max().item() if tc else 2e-3
+    assert (out.detach().cpu() - ref).abs().max().item() <= tol
+    assert xc.grad is not None and m.conv_offset.weight.grad is not None and m.conv_adaption.weight.grad is not None
