@@ -1,7 +1,9 @@
 """Prints the path-level parity numbers: our CUDA path vs the fp32 CPU oracle, next to the oracle's own
 bf16-autocast spread on the same inputs/weights (SURVEY.md §8c contract (3)).  Run on the GPU box:
 
-    python tools/parity_report.py [cfg ...]  > gpurun_out/parity.txt
+    python tests/parity_report.py [cfg ...]  > gpurun_out/parity.txt
+
+Lives under tests/ because it drives the oracle (test infrastructure); it is a report, not a collected test.
 """
 import json
 import os
@@ -12,7 +14,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))  # this directory
 
 from oracle import hrpose_oracle as O  # noqa: E402
 from oracle import make_golden as G  # noqa: E402
