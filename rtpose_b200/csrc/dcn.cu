@@ -3,20 +3,20 @@
 // (det3d/ops/dcn/src/deform_conv_cuda.cpp:196-247 materialises C*kh*kw x N*Ho*Wo fp32; the modulated path :490-684).
 // Every kernel takes an optional `mask` [N][dg*kh*kw][Ho][Wo]; nullptr = v1.
 //
-// Each CTA owns a tile of 32 output pixels of one sample.  A channel tile of the deformed im2col matrix is sampled
-// straight into shared memory with warp-level bilinear gathers (lanes = consecutive output pixels, so the offset
-// reads and most of the 4-corner reads coalesce) and is consumed in place by the contraction with the weights.
-// fp32 NCHW in and out, exactly the reference op's dtype/layout.  Sampling semantics follow
-// deform_conv_cuda_kernel.cu:84-115 (bilinear, zero outside) and :229 (validity h>-1 && w>-1 && h<H && w<W);
-// offset channel order [dg][kh*kw][dy,dx].
+// fp32 kernels (the default; the reference op's dtype and NCHW layout in and out): each CTA owns a tile of output pixels
+// of one sample (64 in the forward, 32 in the two backward kernels).  A channel tile of the deformed im2col matrix is
+// sampled straight into shared memory with warp-level bilinear gathers (lanes = consecutive output pixels, so the offset
+// reads and most of the 4-corner reads coalesce) and is consumed in place by the contraction with the weights on the fp32
+// CUDA cores.  Sampling semantics follow deform_conv_cuda_kernel.cu:84-115 (bilinear, zero outside) and :229 (validity
+// h>-1 && w>-1 && h<H && w<W); offset channel order [dg][kh*kw][dy,dx].
 //
-// Roofline: the gather is L2/HBM-bound, the contraction runs on the fp32 CUDA cores in this version (moving it to
-// tcgen05 is the round-2 item listed in DESIGN.md).
+// Tensor-core path (opt-in from rtpose_b200/dcn.py): rtp_dcn_sample_p8 writes the sample volume in bf16 P8 with the taps
+// on the z axis, rtp_conv / rtp_wgrad contract it on tcgen05, rtp_dcn_col2im_p8 scatters the sample gradient.
 #include "common.cuh"
 
 namespace {
 
-constexpr int kPix = 32;   // output pixels per CTA
+constexpr int kPix = 32;   // output pixels per CTA (backward kernels)
 constexpr int kCT = 8;     // input channels per smem tile
 
 struct Dcn {
@@ -63,11 +63,12 @@ __device__ __forceinline__ void tap_pos(const Dcn& p, const float* __restrict__ 
 }
 
 // col[ck][px] for channels [c0, c0+kCT): one warp-level gather per (channel, tap) row
+template <int PIX = kPix>
 __device__ __forceinline__ void sample_tile(const Dcn& p, const float* __restrict__ x_n, const float* __restrict__ off_n,
                                             const float* __restrict__ mask_n, int c0, int pix0, float* col) {
   const int K = p.kh * p.kw, npix = p.Ho * p.Wo, cpg = p.C / p.dg;
-  for (int i = threadIdx.x; i < kCT * K * kPix; i += blockDim.x) {
-    const int px = i % kPix, ck = i / kPix;
+  for (int i = threadIdx.x; i < kCT * K * PIX; i += blockDim.x) {
+    const int px = i % PIX, ck = i / PIX;
     const int c = c0 + ck / K, t = ck % K;
     float v = 0.f;
     const int pix = pix0 + px;
@@ -80,46 +81,129 @@ __device__ __forceinline__ void sample_tile(const Dcn& p, const float* __restric
       v = s.w1 * __ldg(xc + s.o1) + s.w2 * __ldg(xc + s.o2) + s.w3 * __ldg(xc + s.o3) + s.w4 * __ldg(xc + s.o4);
       if (mask_n) v *= __ldg(mask_n + (int64_t)((c / cpg) * K + t) * npix + pix);  // modulated_deformable_im2col (kernel.cu:571-634)
     }
-    col[ck * kPix + px] = v;
+    col[ck * PIX + px] = v;
   }
 }
 
-// y[n, co, pix] = sum_{c,t} w[co, c, t] * col[(c,t), pix]
+// y[n, co, pix] = bias[co] + sum_{c,t} w[co, c, t] * col[(c,t), pix]
+// CTA tile: 64 pixels x 128 output channels, 256 threads, 4 pixels x 8 channels of accumulators per thread.  Per channel
+// tile (8 channels x K taps) the deformed samples AND the matching weight slice are staged in shared memory, so the inner
+// loop is 3 LDS.128 (4 pixels, 8 weights broadcast within a half-warp) per 32 FMAs.  The weight slice is read from the
+// reference's [Cout][C][kh][kw] layout in 32-byte runs along (c, tap) — a warp covers 4 output channels x 8 consecutive
+// (c, tap) — and stored transposed with a row pitch of 132 floats: bank = (4*ck + co) mod 32 is distinct for those 32 lanes.
+constexpr int kFPix = 64, kFCo = 128, kWPitch = kFCo + 4;
 __global__ void __launch_bounds__(256) dcn_fwd_kernel(Dcn p, const float* __restrict__ x, const float* __restrict__ off,
                                                       const float* __restrict__ mask, const float* __restrict__ w,
                                                       const float* __restrict__ bias, float* __restrict__ y) {
-  extern __shared__ float col[];  // [kCT*K][kPix]
-  const int K = p.kh * p.kw, npix = p.Ho * p.Wo;
-  const int n = blockIdx.y, pix0 = blockIdx.x * kPix, co0 = blockIdx.z * 128;
-  const int px = threadIdx.x & 31, cg = threadIdx.x >> 5;  // 8 warps: warp cg owns output channels co0 + cg + 8*j
+  extern __shared__ float4 dcn_smem4[];
+  const int K = p.kh * p.kw, npix = p.Ho * p.Wo, nckmax = kCT * K;
+  float* col = reinterpret_cast<float*>(dcn_smem4);  // [kCT*K][kFPix]
+  float* wsm = col + nckmax * kFPix;                 // [kCT*K][kWPitch]
+  const int n = blockIdx.y, pix0 = blockIdx.x * kFPix, co0 = blockIdx.z * kFCo;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // pixels pix0 + 4*tx + {0..3}, channels co0 + 8*ty + {0..7}
   const float* x_n = x + (int64_t)n * p.C * p.H * p.W;
   const float* off_n = off + (int64_t)n * p.dg * K * 2 * npix;
   const float* mask_n = mask ? mask + (int64_t)n * p.dg * K * npix : nullptr;
-  float acc[16];
+  float acc[4][8];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    const int co = co0 + cg + 8 * j;
-    acc[j] = (bias && co < p.Cout) ? __ldg(bias + co) : 0.f;
+  for (int j = 0; j < 8; ++j) {
+    const int co = co0 + ty * 8 + j;
+    const float b = (bias && co < p.Cout) ? __ldg(bias + co) : 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc[q][j] = b;
   }
+  // The sampling geometry (4 corner weights incl. the mask, 4 corner offsets) depends on (deformable group, tap, pixel)
+  // only: when channel tiles do not straddle groups it is computed once per group into shared memory and every channel
+  // of the group then costs 2 LDS.128 + 4 independent gathers, with no offset-load -> address -> gather chain.
+  float4* geo = reinterpret_cast<float4*>(col + ((nckmax * (kFPix + kWPitch) + 3) & ~3));  // [K*kFPix][2]
+  const int cpg = p.C / p.dg;
+  const bool cached = (cpg % kCT) == 0;
+  int cur_g = -1;
   for (int c0 = 0; c0 < p.C; c0 += kCT) {
     __syncthreads();
-    sample_tile(p, x_n, off_n, mask_n, c0, pix0, col);
-    __syncthreads();
+    // weight slice of this channel tile: asynchronous 4-byte copies (zero-filled beyond Cout), issued first so that their
+    // L2 latency overlaps the gathers below
     const int nck = min(kCT, p.C - c0) * K;
+    {
+      const int nckb = (nck + 7) >> 3;
+      const uint32_t wsm_s = (uint32_t)__cvta_generic_to_shared(wsm);
+      for (int i = threadIdx.x; i < (kFCo / 4) * nckb * 32; i += blockDim.x) {
+        const int q = i >> 5, cob = q / nckb, ckb = q - cob * nckb;
+        const int ck = ckb * 8 + (i & 7), co = cob * 4 + ((i >> 3) & 3);
+        if (ck < nck) {
+          const int cg = min(co0 + co, p.Cout - 1);
+          const float* src = w + ((int64_t)cg * p.C + c0) * K + ck;
+          const int nbytes = (co0 + co < p.Cout) ? 4 : 0;
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(wsm_s + (uint32_t)(ck * kWPitch + co) * 4u), "l"(src), "r"(nbytes)
+                       : "memory");
+        }
+      }
+    }
+    if (cached) {
+      const int g = c0 / cpg;
+      if (g != cur_g) {  // uniform over the CTA
+        for (int i = threadIdx.x; i < K * kFPix; i += blockDim.x) {
+          const int t = i / kFPix, pix = pix0 + (i - t * kFPix);
+          float4 wq = make_float4(0.f, 0.f, 0.f, 0.f);
+          int4 oq = make_int4(0, 0, 0, 0);
+          if (pix < npix) {
+            const int ho = pix / p.Wo, wo = pix - ho * p.Wo;
+            float h, wv;
+            tap_pos(p, off_n, g, t, ho, wo, h, wv);
+            const Sample sm = make_sample(p, h, wv);
+            const float mk = mask_n ? __ldg(mask_n + (int64_t)(g * K + t) * npix + pix) : 1.f;
+            wq = make_float4(sm.w1 * mk, sm.w2 * mk, sm.w3 * mk, sm.w4 * mk);
+            oq = make_int4(sm.o1, sm.o2, sm.o3, sm.o4);
+          }
+          geo[2 * i] = wq;
+          geo[2 * i + 1] = *reinterpret_cast<float4*>(&oq);
+        }
+        cur_g = g;
+        __syncthreads();
+      }
+      const int64_t plane = (int64_t)p.H * p.W;
+#pragma unroll 6
+      for (int i = threadIdx.x; i < kCT * K * kFPix; i += blockDim.x) {
+        const int px = i % kFPix, ck = i / kFPix;
+        const int cc = ck / K, t = ck - cc * K;
+        const float4 wq = geo[2 * (t * kFPix + px)];
+        const float4 of = geo[2 * (t * kFPix + px) + 1];
+        const int4 oq = *reinterpret_cast<const int4*>(&of);
+        const float* xc = x_n + (int64_t)min(c0 + cc, p.C - 1) * plane;
+        col[ck * kFPix + px] = wq.x * __ldg(xc + oq.x) + wq.y * __ldg(xc + oq.y) + wq.z * __ldg(xc + oq.z) + wq.w * __ldg(xc + oq.w);
+      }
+    } else {
+      sample_tile<kFPix>(p, x_n, off_n, mask_n, c0, pix0, col);
+    }
+    asm volatile("cp.async.wait_all;\n" ::: "memory");
+    __syncthreads();
     for (int ck = 0; ck < nck; ++ck) {
-      const float v = col[ck * kPix + px];
+      const float4 v = *reinterpret_cast<const float4*>(col + ck * kFPix + tx * 4);
+      const float4 wa = *reinterpret_cast<const float4*>(wsm + ck * kWPitch + ty * 8);
+      const float4 wb = *reinterpret_cast<const float4*>(wsm + ck * kWPitch + ty * 8 + 4);
+      const float wr[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int co = co0 + cg + 8 * j;
-        if (co < p.Cout) acc[j] = fmaf(__ldg(w + ((int64_t)co * p.C + c0) * K + ck), v, acc[j]);
+      for (int j = 0; j < 8; ++j) {
+        const float wv = wr[j];
+        acc[0][j] = fmaf(wv, v.x, acc[0][j]);
+        acc[1][j] = fmaf(wv, v.y, acc[1][j]);
+        acc[2][j] = fmaf(wv, v.z, acc[2][j]);
+        acc[3][j] = fmaf(wv, v.w, acc[3][j]);
       }
     }
   }
-  if (pix0 + px < npix) {
+  const int pix = pix0 + tx * 4;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const int co = co0 + cg + 8 * j;
-      if (co < p.Cout) y[((int64_t)n * p.Cout + co) * npix + pix0 + px] = acc[j];
+  for (int j = 0; j < 8; ++j) {
+    const int co = co0 + ty * 8 + j;
+    if (co >= p.Cout) continue;
+    float* yr = y + ((int64_t)n * p.Cout + co) * npix + pix;
+    if ((npix & 3) == 0 && pix + 3 < npix) {
+      *reinterpret_cast<float4*>(yr) = make_float4(acc[0][j], acc[1][j], acc[2][j], acc[3][j]);
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (pix + q < npix) yr[q] = acc[q][j];
     }
   }
 }
@@ -301,7 +385,7 @@ __global__ void __launch_bounds__(256) dcn_sample_p8_kernel(Dcn p, const float* 
 // Tensor-core backward, last step: dS (bf16 P8, taps on z; produced by rtp_conv from dy) -> dx (atomic scatter through
 // the bilinear weights), doffset and dmask.  One thread per (n, deformable group, tap, ho, wo) walks the channels of its
 // group, so doffset / dmask are plain stores of register sums; lanes run along ho, the contiguous axis of dS.
-__global__ void __launch_bounds__(256) dcn_col2im_p8_kernel(Dcn p, const float* __restrict__ x, const float* __restrict__ off,
+__global__ void __launch_bounds__(256, 2) dcn_col2im_p8_kernel(Dcn p, const float* __restrict__ x, const float* __restrict__ off,
                                                             const float* __restrict__ mask, P8 ds, float* __restrict__ dx,
                                                             float* __restrict__ doff, float* __restrict__ dmask) {
   const int K = p.kh * p.kw, npix = p.Ho * p.Wo, cpg = p.C / p.dg;
@@ -384,8 +468,15 @@ __global__ void __launch_bounds__(256) dcn_bias_grad_kernel(const float* __restr
 
 int launch_fwd(const Dcn& d, const float* x, const float* offset, const float* mask, const float* w, const float* bias, float* y,
                cudaStream_t st) {
-  dim3 grid(ceil_div((int64_t)d.Ho * d.Wo, kPix), d.N, ceil_div(d.Cout, 128));
-  dcn_fwd_kernel<<<grid, 256, kCT * d.kh * d.kw * kPix * sizeof(float), st>>>(d, x, offset, mask, w, bias, y);
+  const size_t smem = (((size_t)kCT * d.kh * d.kw * (kFPix + kWPitch) + 3) & ~(size_t)3) * sizeof(float) +
+                      (size_t)d.kh * d.kw * kFPix * 2 * sizeof(float4);
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaFuncSetAttribute(dcn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = smem;
+  }
+  dim3 grid(ceil_div((int64_t)d.Ho * d.Wo, kFPix), d.N, ceil_div(d.Cout, kFCo));
+  dcn_fwd_kernel<<<grid, 256, smem, st>>>(d, x, offset, mask, w, bias, y);
   RTP_LAUNCH_CHECK();
 }
 
