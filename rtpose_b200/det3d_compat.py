@@ -555,4 +555,11 @@ def install_as_det3d():
                   "HRNet3D", "CenterHead", "RadarFeatureNet"):
             setattr(m, k, getattr(me, k))
         sys.modules[n] = m
+    # `from det3d.ops.dcn import DeformConv` (pose_heads/center_head.py:18) and det3d/ops/dcn/__init__.py's other names
+    from . import dcn
+    ops_mod = sys.modules.get("det3d.ops") or types.ModuleType("det3d.ops")
+    ops_mod.__path__ = getattr(ops_mod, "__path__", [])
+    ops_mod.dcn = dcn
+    sys.modules["det3d.ops"], sys.modules["det3d.ops.dcn"], sys.modules["det3d.ops.dcn.deform_conv"] = ops_mod, dcn, dcn
+    sys.modules["det3d"].ops = ops_mod
     return sys.modules["det3d"]

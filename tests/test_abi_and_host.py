@@ -145,6 +145,10 @@ def test_registry_and_builder_errors():
         D.DETECTORS.register_module(D.RadarPoseNet)  # already registered
     assert set(["RadarPoseNet"]) <= set(D.DETECTORS.module_dict)
     assert D.install_as_det3d().build_detector is D.build_detector
+    from det3d.ops.dcn import DeformConv, ModulatedDeformConvPack  # center_head.py:18; det3d/ops/dcn/__init__.py
+    from det3d.ops.dcn.deform_conv import deform_conv
+    from rtpose_b200 import dcn
+    assert DeformConv is dcn.DeformConv and ModulatedDeformConvPack is dcn.ModulatedDeformConvPack and deform_conv is dcn.deform_conv
 
 
 @pytest.mark.skipif(not os.path.isdir(REF_CFG), reason="reference configs not present (GPU box)")
