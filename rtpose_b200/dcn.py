@@ -41,6 +41,21 @@ TC_SAMPLE_BYTES = 512 << 20   # the sampled volume is produced and consumed in b
 _tc_state = {}
 
 
+def _same_tensors(entry, tensors):
+    """A cached pack is valid only for the SAME tensor objects at the same version counters: a new tensor that happens to
+    reuse a freed tensor's address (and starts at version 0 as well) must not hit."""
+    if entry is None:
+        return False
+    refs, vers = entry
+    return all((r is None and t is None) or (r is not None and t is not None and r() is t and v == t._version)
+               for r, v, t in zip(refs, vers, tensors))
+
+
+def _tensor_key(tensors):
+    import weakref
+    return ([weakref.ref(t) if t is not None else None for t in tensors], [t._version if t is not None else None for t in tensors])
+
+
 def tc_supported(C, Cout, kh, kw, dg):
     return (C % dg == 0 and (C // dg) % 8 == 0 and -(-C // 16) * 16 <= 512 and -(-Cout // 16) * 16 <= 256 and kh * kw <= lib.MAX_TAPS)
 
@@ -64,11 +79,10 @@ def _tc_backward(input, offset, mask, weight, grad_output, with_bias, stride, pa
     st = _tc_state.get(key)
     if st is None:
         st = _tc_state[key] = {"S": P8(nb, Cc, K, Ho, Wo, device=dev), "w": None}
-    wkey = (weight.data_ptr(), weight._version)
-    if st["w"] is None or st["w"][0] != wkey:
+    if st["w"] is None or not _same_tensors(st["w"][0], (weight,)):
         pack = torch.empty(K * KPd * NPd, dtype=torch.bfloat16, device=dev)
         lib.call("rtp_weight_pack", weight.data_ptr(), pack.data_ptr(), Cout, Cc, K, 0, Cc, KPd, NPd, 1, _stream())
-        st["w"] = (wkey, pack)
+        st["w"] = (_tensor_key((weight,)), pack)
     pack = st["w"][1]
     grad_input, grad_offset = torch.empty_like(input), torch.empty_like(offset)
     grad_mask = torch.empty_like(mask) if mask is not None else None
@@ -110,11 +124,10 @@ def _tc_forward(input, offset, mask, weight, bias, stride, pad, dil, dg, out_siz
     st = _tc_state.get(key)
     if st is None:  # zero-filled once: the kernels only ever write the interior, the halo stays zero
         st = _tc_state[key] = {"S": P8(nb, Cc, K, Ho, Wo, device=dev), "Y": P8(nb, Cout, 1, Ho, Wo, device=dev), "w": None}
-    wkey = (weight.data_ptr(), weight._version, None if bias is None else (bias.data_ptr(), bias._version))
-    if st["w"] is None or st["w"][0] != wkey:
+    if st["w"] is None or not _same_tensors(st["w"][0], (weight, bias)):
         pack = torch.empty(K * KP * NP, dtype=torch.bfloat16, device=dev)
         lib.call("rtp_weight_pack", weight.data_ptr(), pack.data_ptr(), Cout, Cc, K, 0, Cc, KP, NP, 0, _stream())
-        st["w"] = (wkey, pack, ops.pad_bias(bias, NP) if bias is not None else None)
+        st["w"] = (_tensor_key((weight, bias)), pack, ops.pad_bias(bias, NP) if bias is not None else None)
     _, pack, bias_p = st["w"]
     taps = [(t, 0, 0, t) for t in range(K)]
     out = input.new_empty(out_size)

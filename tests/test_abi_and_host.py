@@ -194,3 +194,17 @@ def test_dcn_pack_modules_rename_pre_v2_checkpoint_keys():
         keep = dict(sd)
         m._load_from_state_dict(sd, "conv2.", {"version": 2}, True, missing, unexpected, errors)  # current version: untouched
         assert sd.keys() == keep.keys()
+
+
+def test_dcn_pack_cache_is_keyed_on_tensor_identity_and_version():
+    """The tensor-core DCN path caches bf16 weight packs; a hit needs the same tensor OBJECTS at the same version."""
+    import torch
+    from rtpose_b200 import dcn
+    a, c = torch.zeros(3), torch.zeros(3)
+    k = dcn._tensor_key((a, None))
+    assert dcn._same_tensors(k, (a, None))
+    assert not dcn._same_tensors(k, (c, None)) and not dcn._same_tensors(k, (a, c)) and not dcn._same_tensors(None, (a, None))
+    a.add_(1)  # in-place update (an optimizer step) bumps the version counter
+    assert not dcn._same_tensors(k, (a, None))
+    assert dcn.tc_supported(128, 128, 3, 3, 4) and not dcn.tc_supported(8, 8, 3, 3, 4) and not dcn.tc_supported(128, 512, 3, 3, 4)
+    assert dcn._tc_chunk(256, 128, 9, 64, 160, 4) == (512 << 20) // (16 * 9 * 162 * 66 * 16)
