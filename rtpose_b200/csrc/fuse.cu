@@ -4,6 +4,8 @@
 //
 // Interpolation follows ATen's upsample_trilinear3d (align_corners=True): scale = float(in-1)/float(out-1)
 // (0 when out == 1), src = scale * dst, i0 = int(src), i1 = i0 + (i0 < in-1), w1 = src - i0, w0 = 1 - w1.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace {
@@ -264,6 +266,80 @@ __global__ void __launch_bounds__(256) upsample_bwd_axis_kernel(P8 in, P8 out, i
   }
 }
 
+// Exact candidate range of destinations d with non-zero weight for source index l (see upsample_bwd_axis_kernel).
+__device__ __forceinline__ void hat_range(int l, int in_n, float scale, float inv, int& lo, int& hi) {
+  lo = max(0, (int)floorf((float)(l - 1) * inv));
+  hi = min(in_n - 1, (int)ceilf((float)(l + 1) * inv));
+  if (scale * (float)lo <= (float)(l - 1)) ++lo;
+  if (scale * (float)hi >= (float)(l + 1)) --hi;
+}
+
+// The y and x reductions of U^T in ONE launch: a CTA owns kTXL low-resolution x positions of one (n, chunk, z) plane.
+// Phase 1 reduces every full-resolution row it needs along y into shared memory (fp32), phase 2 reduces those rows along
+// x.  The [Z][X][Yl] intermediate of the separable scheme never goes to HBM (a third of its traffic at ratio 2) and is not
+// rounded to bf16 in between.  Requires both scales > 0 (low extents > 1); the host falls back to two axis launches otherwise.
+constexpr int kTXL = 8;
+__global__ void __launch_bounds__(256) upsample_bwd_yx_kernel(P8 in, P8 out, int C8, int nrows_max) {
+  extern __shared__ float4 up_smem[];  // [nrows_max][Yl][2] float4
+  const float sy = ac_scale(out.Y, in.Y), sx = ac_scale(out.X, in.X);
+  const float iy = 1.f / sy, ix = 1.f / sx;
+  const int z = blockIdx.y, c8 = blockIdx.z % C8, n = blockIdx.z / C8;
+  const int xl0 = blockIdx.x * kTXL, xl1 = min(out.X, xl0 + kTXL) - 1;
+  int r0, r1, tmp;
+  hat_range(xl0, in.X, sx, ix, r0, tmp);
+  hat_range(xl1, in.X, sx, ix, tmp, r1);
+  const int nrows = min(r1 - r0 + 1, nrows_max);
+  const int Yl = out.Y;
+  const bf16* in_nc = in.ptr + n * in.n_stride + c8 * in.c_stride;
+  for (int i = threadIdx.x; i < nrows * Yl; i += blockDim.x) {
+    const int r = i / Yl, yl = i - r * Yl;
+    int lo, hi;
+    hat_range(yl, in.Y, sy, iy, lo, hi);
+    const bf16* ib = in_nc + in.voxel(z, r0 + r, 0);
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    for (int d0 = lo; d0 <= hi; d0 += 4) {
+      uint4 v[4];
+      float w[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int d = min(d0 + u, hi);
+        v[u] = ldg16(ib + d * 8);
+        w[u] = d0 + u <= hi ? hat_weight(d, yl, sy) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float f[8];
+        unpack8(v[u], f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = fmaf(w[u], f[k], acc[k]);
+      }
+    }
+    up_smem[2 * i] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    up_smem[2 * i + 1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+  }
+  __syncthreads();
+  bf16* out_nc = out.ptr + n * out.n_stride + c8 * out.c_stride;
+  const int nxl = xl1 - xl0 + 1;
+  for (int i = threadIdx.x; i < nxl * Yl; i += blockDim.x) {
+    const int xi = i / Yl, yl = i - xi * Yl, xl = xl0 + xi;
+    int lo, hi;
+    hat_range(xl, in.X, sx, ix, lo, hi);
+    hi = min(hi, r0 + nrows - 1);
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    for (int d = lo; d <= hi; ++d) {
+      const float w = hat_weight(d, xl, sx);
+      const float4 a = up_smem[2 * ((d - r0) * Yl + yl)], b = up_smem[2 * ((d - r0) * Yl + yl) + 1];
+      acc[0] = fmaf(w, a.x, acc[0]); acc[1] = fmaf(w, a.y, acc[1]); acc[2] = fmaf(w, a.z, acc[2]); acc[3] = fmaf(w, a.w, acc[3]);
+      acc[4] = fmaf(w, b.x, acc[4]); acc[5] = fmaf(w, b.y, acc[5]); acc[6] = fmaf(w, b.z, acc[6]); acc[7] = fmaf(w, b.w, acc[7]);
+    }
+    stg16(out_nc + out.voxel(z, xl, yl), pack8(acc));
+  }
+}
+
 // dst (=|+=) src [* (mask > 0)]
 __global__ void __launch_bounds__(256) grad_add_kernel(P8 src, P8 mask, int has_mask, P8 dst, int accumulate) {
   const int c8 = blockIdx.y, n = blockIdx.z;
@@ -353,8 +429,22 @@ extern "C" int rtp_upsample_bwd(rtp_p8 dout, rtp_p8 dlow, int32_t C, int32_t acc
     upsample_bwd_axis_kernel<<<dim3((unsigned)ceil_div(b.X, TX), (unsigned)b.Z, (unsigned)(b.N * C8)), 256, 0, (cudaStream_t)stream>>>(
         P8(a), P8(b), C8, axis, acc, log2ty);
   };
-  launch(dout, t1, 2, 0);
-  launch(t1, t2, 1, 0);
+  static const bool no_fused = getenv("RTP_NO_FUSED_UPBWD") != nullptr;  // A/B switch
+  const float sxh = dlow.X > 1 && dout.X > 1 ? (float)(dlow.X - 1) / (float)(dout.X - 1) : 0.f;
+  const int nrows_max = sxh > 0.f ? (int)ceilf((float)(kTXL + 1) / sxh) + 3 : 0;
+  const size_t smem = (size_t)nrows_max * dlow.Y * 32;
+  if (!no_fused && sxh > 0.f && dlow.Y > 1 && dout.Y > 1 && smem <= 96 * 1024) {
+    static size_t configured = 0;
+    if (smem > configured) {
+      cudaFuncSetAttribute(upsample_bwd_yx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      configured = smem;
+    }
+    upsample_bwd_yx_kernel<<<dim3((unsigned)ceil_div(t2.X, kTXL), (unsigned)t2.Z, (unsigned)(t2.N * C8)), 256, smem, (cudaStream_t)stream>>>(
+        P8(dout), P8(t2), C8, nrows_max);
+  } else {
+    launch(dout, t1, 2, 0);
+    launch(t1, t2, 1, 0);
+  }
   launch(t2, dlow, 0, accumulate);
   RTP_LAUNCH_CHECK();
 }

@@ -174,7 +174,7 @@ def require_device():
 LAUNCHES = {"rtp_pack_ncdhw": 1, "rtp_unpack_ncdhw": 1, "rtp_ingest_pack": 1, "rtp_weight_pack": 1,
             "rtp_weight_pack_k3s1": 1, "rtp_conv": 1, "rtp_conv_k3s1": 1, "rtp_wgrad": 1, "rtp_wgrad_reduce": 1,
             "rtp_gn_sums": 2, "rtp_gn_finalize": 1, "rtp_gn_apply": 1, "rtp_gn_bwd_reduce": 2, "rtp_gn_bwd_apply": 1,
-            "rtp_fuse_sum": 1, "rtp_upsample_bwd": 3, "rtp_grad_add": 1, "rtp_channel_sum": 2, "rtp_stem_fwd": 1,
+            "rtp_fuse_sum": 1, "rtp_upsample_bwd": 2, "rtp_grad_add": 1, "rtp_channel_sum": 2, "rtp_stem_fwd": 1,
             "rtp_stem_bwd": 2, "rtp_head_loss": 2, "rtp_decode": 1, "rtp_scale_f32": 1, "rtp_dcn_fwd": 1,
             "rtp_dcn_bwd_input": 1, "rtp_dcn_bwd_weight": 1, "rtp_mdcn_fwd": 1, "rtp_mdcn_bwd_input": 1, "rtp_mdcn_bwd_weight": 2, "rtp_adam_step": 2, "rtp_adam_step_dev": 2,
             "rtp_assign_targets": 2, "rtp_wgrad_k3s1": 1, "rtp_wgrad_k3s1_reduce": 1, "rtp_conv_pw": 1, "rtp_gn_apply_s2d": 1, "rtp_gn_bwd_reduce_s2d": 2,
