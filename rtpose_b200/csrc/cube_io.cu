@@ -211,7 +211,11 @@ extern "C" int rtp_npy_read_roi_slab(const char* path, int32_t z0, int32_t Z, in
   } else {
     std::vector<std::thread> pool;
     pool.reserve(nt - 1);
-    for (int i = 1; i < nt; ++i) pool.emplace_back(work);
+    try {
+      for (int i = 1; i < nt; ++i) pool.emplace_back(work);
+    } catch (...) {
+      // the process is out of threads: whatever helpers exist plus this thread drain the queue (no exception may cross the C ABI)
+    }
     work();
     for (auto& t : pool) t.join();
   }
