@@ -208,3 +208,19 @@ def test_dcn_pack_cache_is_keyed_on_tensor_identity_and_version():
     assert not dcn._same_tensors(k, (a, None))
     assert dcn.tc_supported(128, 128, 3, 3, 4) and not dcn.tc_supported(8, 8, 3, 3, 4) and not dcn.tc_supported(128, 512, 3, 3, 4)
     assert dcn._tc_chunk(256, 128, 9, 64, 160, 4) == (512 << 20) // (16 * 9 * 162 * 66 * 16)
+
+
+def test_one_cycle_schedule_equals_reference_golden():
+    """rtpose_b200.optim.one_cycle against the values the reference's own OneCycle class produced
+    (det3d/solver/learning_schedules_fastai.py:53-95; oracle/make_sched_golden.py -> tests/golden/one_cycle_golden.json),
+    every step of three schedules, relative 1e-12 (math.cos vs numpy.cos)."""
+    import json
+    import os
+    from rtpose_b200.optim import one_cycle
+    cases = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "one_cycle_golden.json")))
+    assert [c["total_step"] for c in cases] == [1000, 37, 10]
+    for c in cases:
+        for step, (lr, mom) in enumerate(c["lr_mom"]):
+            got = one_cycle(step, c["total_step"], lr_max=c["lr_max"], div_factor=c["div_factor"], pct_start=c["pct_start"],
+                            moms=tuple(c["moms"]))
+            assert abs(got[0] - lr) <= 1e-12 * abs(lr) and abs(got[1] - mom) <= 1e-12 * abs(mom), (c["total_step"], step, got, lr, mom)
