@@ -21,7 +21,7 @@ from oracle import make_golden as G
 
 pytestmark = pytest.mark.gpu
 
-GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*_g*x*x*.npz")))  # model goldens (make_golden.py)
 
 
 def build_engine(cfg, sd=None):

@@ -10,7 +10,7 @@ import torch
 from oracle import hrpose_oracle as O
 from oracle import make_golden as G
 
-GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*_g*x*x*.npz")))  # model goldens (make_golden.py)
 
 
 def _load(path):
@@ -77,3 +77,23 @@ def test_ingest_matches_numpy_semantics():
     np.testing.assert_array_equal(out, ref)
     one = O.ingest_cube(raw[0], (150000.0, 200000.0))
     assert one.shape == (1, 16, 64, 160)
+
+
+def test_target_assignment_equals_reference_golden():
+    """oracle.assign_targets against the reference's own AssignLabelPose / AssignLabelPose2 (pose.py:153-255, :345-452) run
+    from source by oracle/make_target_golden.py (NumPy-1 promotion, see that file): heat-map, ind, mask, cat and anno_pose
+    bit-exact for 7 random skeletons and one outside the ROI, both label layouts."""
+    from oracle import hrpose_oracle as O
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "targets_golden.npz"))
+    grid = tuple(int(v) for v in g["grid"])
+    assert grid == (16, 64, 160) and g["poses"].shape == (8, 15, 3)
+    for tag, one_hm in (("one_hm", True), ("hr3d", False)):
+        for i, pose in enumerate(g["poses"]):
+            mine = O.assign_targets(pose, grid, one_hm, radius=2 if one_hm else 1)
+            hm = np.zeros(tuple(g["%s_%d_hm_shape" % (tag, i)]), np.float32)
+            hm.reshape(-1)[g["%s_%d_hm_idx" % (tag, i)]] = g["%s_%d_hm_val" % (tag, i)]
+            assert hm.shape == mine["hm"].shape and np.array_equal(hm, mine["hm"]), (tag, i, "hm")
+            for k in ("ind", "mask", "cat", "anno_pose"):
+                ref = g["%s_%d_%s" % (tag, i, k)]
+                assert ref.dtype == np.asarray(mine[k]).dtype and np.array_equal(ref, mine[k]), (tag, i, k)
+    assert int(g["one_hm_7_mask"].sum()) == 0 and int(g["hr3d_7_mask"].sum()) < 15  # the skeleton pushed out of the ROI
