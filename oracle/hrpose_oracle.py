@@ -443,3 +443,23 @@ def evaluation(detections, gt, seq_id_to_name):
              [p % j for j in range(15) for p in ("PJPE_%d", "ABS_PJPE_%d")]}
     seq_res["ALL"] = total
     return {"results": total, "seq_results": seq_res}
+
+
+# ------------------------------------------------------------------------------------------------ optimizer step
+def adam_step_flat(p, g, m, v, step, lr, mom, beta2=0.99, eps=1e-8, wd=0.01, max_norm=35.0):
+    """One training-step update on flat float32 numpy buffers (in place on p, m, v; returns the pre-clip gradient norm):
+    OptimizerHook.clip_grads (hooks/optimizer.py:9-12: clip_grad_norm_, coefficient max_norm / (norm + 1e-6) capped at 1),
+    OptimWrapper.step's decoupled decay p *= 1 - wd*lr (fastai_optim.py:158-174, true_wd, bn_wd) and
+    torch.optim.Adam(betas=(mom, beta2), eps).step() with bias correction at time step `step` >= 1.
+    This is the arithmetic rtp_adam_step fuses into one pass (csrc/train_aux.cu)."""
+    f = np.float32
+    norm = f(np.sqrt(np.sum(g.astype(np.float64) ** 2)))
+    coef = f(min(1.0, float(f(max_norm) / (norm + f(1e-6))))) if max_norm > 0 else f(1.0)
+    gi = g * coef
+    p *= f(1.0) - f(wd) * f(lr)
+    m[:] = f(mom) * m + (f(1.0) - f(mom)) * gi
+    v[:] = f(beta2) * v + (f(1.0) - f(beta2)) * gi * gi
+    bias1 = f(1.0 - mom ** step)
+    bias2_sqrt = f(np.sqrt(1.0 - beta2 ** step))
+    p -= (f(lr) / bias1) * m / (np.sqrt(v) / bias2_sqrt + f(eps))
+    return float(norm)

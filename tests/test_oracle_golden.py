@@ -97,3 +97,22 @@ def test_target_assignment_equals_reference_golden():
                 ref = g["%s_%d_%s" % (tag, i, k)]
                 assert ref.dtype == np.asarray(mine[k]).dtype and np.array_equal(ref, mine[k]), (tag, i, k)
     assert int(g["one_hm_7_mask"].sum()) == 0 and int(g["hr3d_7_mask"].sum()) < 15  # the skeleton pushed out of the ROI
+
+
+def test_fused_optimizer_step_equals_reference_trajectory():
+    """oracle.adam_step_flat (the arithmetic of rtp_adam_step) driven by rtpose_b200.optim.one_cycle against the parameter
+    trajectory the reference's own OptimWrapper + OneCycle + clip_grad_norm_ produced (oracle/make_optim_golden.py ->
+    tests/golden/optim_golden.npz): 6 steps, the second one clipped (norm 1789 > 35).  float32 both sides; the operation
+    order differs slightly (torch divides by bias corrections separately), hence rel 2e-6 on the parameters."""
+    from rtpose_b200.optim import one_cycle
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "optim_golden.npz"))
+    p = g["p0"].astype(np.float32).copy()
+    m, v = np.zeros_like(p), np.zeros_like(p)
+    for step in range(6):
+        lr, mom = one_cycle(step, 10, lr_max=0.002)
+        assert abs(lr - g["lr_mom_%d" % step][0]) <= 1e-12 and abs(mom - g["lr_mom_%d" % step][1]) <= 1e-12
+        norm = O.adam_step_flat(p, g["grad_%d" % step].astype(np.float32), m, v, step + 1, lr, mom)
+        assert abs(norm - float(g["norm_%d" % step])) <= 1e-5 * float(g["norm_%d" % step])
+        ref = g["p_%d" % step]
+        assert np.abs(p - ref).max() <= 2e-6 * np.abs(ref).max() + 1e-8, (step, np.abs(p - ref).max())
+    assert float(g["norm_1"]) > 35.0 > float(g["norm_0"])

@@ -67,6 +67,25 @@ def test_fused_adam_matches_reference_optimizer_semantics():
         torch.testing.assert_close(p.cpu(), ref_flat, rtol=2e-5, atol=2e-7)
 
 
+def test_fused_adam_follows_reference_trajectory():
+    """rtp_adam_step on the device against the parameter trajectory produced by the reference's own OptimWrapper + OneCycle
+    + clip_grad_norm_ (oracle/make_optim_golden.py -> tests/golden/optim_golden.npz; 6 steps, step 1 clipped)."""
+    import os
+    from rtpose_b200.optim import FlatAdam, one_cycle
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "optim_golden.npz"))
+    p = torch.from_numpy(g["p0"].astype(np.float32)).cuda()
+    gr = torch.zeros_like(p)
+    fa = FlatAdam(p, gr, wd=0.01, max_norm=35.0)
+    for step in range(6):
+        lr, mom = one_cycle(step, 10, lr_max=0.002)
+        gr.copy_(torch.from_numpy(g["grad_%d" % step].astype(np.float32)).cuda())
+        fa.step(lr, mom)
+        torch.cuda.synchronize()
+        ref = torch.from_numpy(g["p_%d" % step])
+        assert abs(float(fa.grad_norm) - float(g["norm_%d" % step])) <= 1e-4 * float(g["norm_%d" % step])
+        torch.testing.assert_close(p.cpu(), ref, rtol=2e-5, atol=2e-7)
+
+
 def test_adam_by_value_and_device_hyper_agree():
     from rtpose_b200.optim import FlatAdam
     g = torch.Generator().manual_seed(3)
