@@ -116,3 +116,22 @@ def test_fused_optimizer_step_equals_reference_trajectory():
         ref = g["p_%d" % step]
         assert np.abs(p - ref).max() <= 2e-6 * np.abs(ref).max() + 1e-8, (step, np.abs(p - ref).max())
     assert float(g["norm_1"]) > 35.0 > float(g["norm_0"])
+
+
+def test_ingest_equals_reference_dataset_golden():
+    """oracle.ROI_IDX / ingest_cube / ingest_cube_phase against the reference dataset's own consider_roi_cube + get_cube +
+    get_cube_phase run from source (oracle/make_ingest_golden.py -> tests/golden/ingest_golden.npz), bit-exact on a strided
+    sub-sample plus sum / abs-sum / zero-count of the whole result."""
+    from oracle import make_ingest_golden as M
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ingest_golden.npz"))
+    assert tuple(int(v) for v in g["roi_idx"]) == tuple(O.ROI_IDX) == (13, 28, 32, 95, 17, 176)
+    for kind, norm in (("dzyx", (0.0, 10.0)), ("zyx", (30000.0, 50000.0)), ("phase", None)):
+        raw = M.synth_cube(kind, int(g[kind + "_seed"]))
+        mine = O.ingest_cube_phase(raw) if kind == "phase" else O.ingest_cube(raw, norm)
+        assert str(g[kind + "_dtype"]) == "float32" and mine.dtype == np.float32
+        assert int(np.prod(g[kind + "_shape"])) == mine.size and tuple(g[kind + "_shape"][-3:]) == mine.shape[-3:] == (16, 64, 160)
+        flat = mine.reshape((-1,) + mine.shape[-3:])
+        assert np.array_equal(flat[(slice(None),) + M.SUB], g[kind + "_sub"]), kind
+        stats = [flat.astype(np.float64).sum(), np.abs(flat.astype(np.float64)).sum(), float((flat == 0).sum())]
+        assert stats == g[kind + "_stats"].tolist(), (kind, stats, g[kind + "_stats"].tolist())
+    assert g["dzyx_stats"][2] > 0  # the clamp was exercised
