@@ -7,7 +7,14 @@ under `rtpose_b200/` does.
 
 Parity pin: the reference ships no tests or golden vectors, so this restatement is pinned
 against outputs of the reference's own unmodified modules executed in the build container
-(`oracle/make_golden.py` -> `tests/golden/*.npz`, checked by `tests/test_oracle_golden.py`).  The arithmetic
+(checked by `tests/test_oracle_golden.py`, `tests/test_evaluation.py`, `tests/test_abi_and_host.py`):
+  model forward / loss / gradients / decode   oracle/make_golden.py        -> tests/golden/*_g*x*x*.npz
+  ingest (ROI indices, crop, normalise, clamp)  oracle/make_ingest_golden.py -> tests/golden/ingest_golden.npz
+  target assignment (both label layouts)        oracle/make_target_golden.py -> tests/golden/targets_golden.npz
+  optimizer step (clip + decay + Adam)          oracle/make_optim_golden.py  -> tests/golden/optim_golden.npz
+  one-cycle schedule                            oracle/make_sched_golden.py  -> tests/golden/one_cycle_golden.json
+  evaluation (PJPE / MPJPE)                     oracle/make_eval_golden.py   -> tests/golden/eval_golden.json
+The arithmetic
 itself (conv3d / group_norm / trilinear interpolate) lives in PyTorch, the reference's pinned third-party
 dependency (requirements-torch.txt:1, torch==2.0.1; here torch 2.11) — both sides call the same ATen ops.
 
