@@ -431,7 +431,8 @@ extern "C" int rtp_upsample_bwd(rtp_p8 dout, rtp_p8 dlow, int32_t C, int32_t acc
   };
   static const bool no_fused = getenv("RTP_NO_FUSED_UPBWD") != nullptr;  // A/B switch
   const float sxh = dlow.X > 1 && dout.X > 1 ? (float)(dlow.X - 1) / (float)(dout.X - 1) : 0.f;
-  const int nrows_max = sxh > 0.f ? (int)ceilf((float)(kTXL + 1) / sxh) + 3 : 0;
+  // rows a tile can need: hi(l1) - lo(l0) + 1 <= (kTXL + 1) / scale + 3 in exact arithmetic; one more for fp32 rounding
+  const int nrows_max = sxh > 0.f ? (int)ceilf((float)(kTXL + 1) / sxh) + 4 : 0;
   const size_t smem = (size_t)nrows_max * dlow.Y * 32;
   if (!no_fused && sxh > 0.f && dlow.Y > 1 && dout.Y > 1 && smem <= 96 * 1024) {
     static size_t configured = 0;
