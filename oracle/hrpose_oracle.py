@@ -470,3 +470,28 @@ def adam_step_flat(p, g, m, v, step, lr, mom, beta2=0.99, eps=1e-8, wd=0.01, max
     bias2_sqrt = f(np.sqrt(1.0 - beta2 ** step))
     p -= (f(lr) / bias1) * m / (np.sqrt(v) / bias2_sqrt + f(eps))
     return float(norm)
+
+
+# ------------------------------------------------------------------------------------------------ space-to-depth identity
+def s2d_view(x):
+    """[N,C,Z,Y,X] (even extents) -> [N,8C,Z/2,Y/2,X/2], channel (pz*4 + px*2 + py)*C + c = x[n, c, 2z+pz, 2y+py, 2x+px]
+    (px is the parity of the LAST tensor axis, py of the one before: the P8 x / y axes)."""
+    parts = [x[:, :, pz::2, py::2, px::2] for pz in (0, 1) for px in (0, 1) for py in (0, 1)]
+    return torch.cat(parts, dim=1)
+
+
+def s2d_expand_weight(w):
+    """[Cout,Cin,3,3,3] of a stride-2 pad-1 conv -> [Cout,8Cin,3,3,3] of the equivalent stride-1 pad-1 conv over s2d_view:
+    input index i = 2o + k - 1, so per axis tap k=0 reads parity 1 at offset -1 (view tap 0), k=1 parity 0 at offset 0
+    (view tap 1), k=2 parity 1 at offset 0 (view tap 1); every other (parity, view tap) pair is zero.  Restates
+    weight_s2d_expand_kernel (csrc/layout.cu)."""
+    Cout, Cin = w.shape[:2]
+    we = torch.zeros((Cout, 8 * Cin, 3, 3, 3), dtype=w.dtype)
+    pt = {0: (1, 0), 1: (0, 1), 2: (1, 1)}  # k -> (parity, view tap)
+    for kz in range(3):
+        for ky in range(3):
+            for kx in range(3):
+                (pz, tz), (py, ty), (px, tx) = pt[kz], pt[ky], pt[kx]
+                par = pz * 4 + px * 2 + py
+                we[:, par * Cin:(par + 1) * Cin, tz, ty, tx] = w[:, :, kz, ky, kx]
+    return we

@@ -135,3 +135,30 @@ def test_ingest_equals_reference_dataset_golden():
         stats = [flat.astype(np.float64).sum(), np.abs(flat.astype(np.float64)).sum(), float((flat == 0).sum())]
         assert stats == g[kind + "_stats"].tolist(), (kind, stats, g[kind + "_stats"].tolist())
     assert g["dzyx_stats"][2] > 0  # the clamp was exercised
+
+
+def test_space_to_depth_identity_of_stride2_convs():
+    """DESIGN.md §3.5 on the CPU in float64: conv3d(x, W, stride 2, pad 1) == conv3d(s2d_view(x), s2d_expand_weight(W),
+    stride 1, pad 1), and 19 of the 27 x 8 (tap, parity) blocks of the expanded weight are structurally zero."""
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 5, 8, 6, 10, generator=g, dtype=torch.float64)
+    w = torch.randn(7, 5, 3, 3, 3, generator=g, dtype=torch.float64)
+    ref = torch.nn.functional.conv3d(x, w, stride=2, padding=1)
+    we = O.s2d_expand_weight(w)
+    got = torch.nn.functional.conv3d(O.s2d_view(x), we, stride=1, padding=1)
+    assert got.shape == ref.shape == (2, 7, 4, 3, 5)
+    torch.testing.assert_close(got, ref, rtol=1e-12, atol=1e-12)
+    blocks = we.reshape(7, 8, 5, 27).abs().sum(dim=(0, 2)) > 0   # [parity, view tap]
+    assert int(blocks.sum()) == 27 and blocks.shape == (8, 27)
+    # the gradient of the expanded weight folds back onto the 27 original taps (weight_s2d_fold_kernel)
+    we_g = we.clone().requires_grad_(True)
+    torch.nn.functional.conv3d(O.s2d_view(x), we_g, stride=1, padding=1).square().sum().backward()
+    w_g = w.clone().requires_grad_(True)
+    torch.nn.functional.conv3d(x, w_g, stride=2, padding=1).square().sum().backward()
+    pt = {0: (1, 0), 1: (0, 1), 2: (1, 1)}
+    for kz in range(3):
+        for ky in range(3):
+            for kx in range(3):
+                (pz, tz), (py, ty), (px, tx) = pt[kz], pt[ky], pt[kx]
+                par = pz * 4 + px * 2 + py
+                torch.testing.assert_close(we_g.grad[:, par * 5:(par + 1) * 5, tz, ty, tx], w_g.grad[:, :, kz, ky, kx], rtol=1e-10, atol=1e-10)
