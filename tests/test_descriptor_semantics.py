@@ -86,3 +86,34 @@ def test_pointwise_and_dcn_tap_lists():
     got = emulate(S, fwd9, (1, 3, 4), [(t, 0, 0, t) for t in range(9)], (1, 4, 3))
     ref = np.einsum("nctyx,oct->noyx", S, wd.reshape(6, 5, 9))
     np.testing.assert_allclose(got[:, :, 0], ref, atol=1e-12)
+
+
+def emulate_wgrad(x, dy, taps, rows, IS=1):
+    """rtp_wgrad: dW[tap][ci][co] = sum_rows X[row*IS + tap][ci] * dY[row][co] (zero outside X); rows index dY directly."""
+    N, Ci, Z, Y, X = x.shape
+    Co = dy.shape[1]
+    dW = np.zeros((len(taps), Ci, Co))
+    RZ, RX, RY = rows
+    for i, (tz, tx, ty) in enumerate(t[:3] for t in taps):
+        for rz in range(RZ):
+            for rx in range(RX):
+                for ry in range(RY):
+                    z, xx, y = rz * IS + tz, rx * IS + tx, ry * IS + ty
+                    if 0 <= z < Z and 0 <= xx < X and 0 <= y < Y:
+                        dW[i] += x[:, :, z, y, xx].T @ dy[:, :, rz, ry, rx]
+    return dW
+
+
+@pytest.mark.parametrize("stride,grid", [(1, (4, 5, 6)), (2, (4, 6, 8)), (2, (5, 7, 9))])
+def test_weight_gradient_descriptors(stride, grid):
+    """ops.conv_wgrad: taps_fwd(3), rows = dY grid, IS = stride; the reduction kernel writes dW[co][ci][tap]."""
+    rs = np.random.RandomState(stride + sum(grid))
+    Z, Y, X = grid
+    x = torch.from_numpy(rs.randn(2, 3, Z, Y, X))
+    w = torch.from_numpy(rs.randn(4, 3, 3, 3, 3)).requires_grad_(True)
+    out = F.conv3d(x, w, stride=stride, padding=1)
+    dy = torch.from_numpy(rs.randn(*out.shape))
+    out.backward(dy)
+    oz, oy, ox = out.shape[2:]
+    dW = emulate_wgrad(x.numpy(), dy.numpy(), ops.taps_fwd(3), (oz, ox, oy), IS=stride)
+    np.testing.assert_allclose(dW.transpose(2, 1, 0).reshape(4, 3, 3, 3, 3), w.grad.numpy(), atol=1e-11)
