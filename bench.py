@@ -98,6 +98,13 @@ class ClockSampler(threading.Thread):
                 "source": self.source}
 
 
+def workload_config(cfg, B, world, D):
+    """The `config` keys that name the workload; shared by both arms so the driver compares like with like."""
+    return {"workload": "%s training fwd+bwd, batch %d per GPU, raw fp16 cube [%d,32,128,256] -> ingest -> "
+                        "HRNet3D -> CenterHead -> loss -> backward" % (cfg, B, D),
+            "per_gpu_batch": B, "global_batch": B * world, "grid": list(GRID), "parallelism": "dp%d" % world}
+
+
 # ------------------------------------------------------------------------------------------------ reference arm
 def run_reference(args, rank, world):
     """The reference's own CPU implementation of the path (oracle port: same ATen ops, fp32, all host threads) on a
@@ -120,19 +127,20 @@ def run_reference(args, rank, world):
         L["loss"].backward()
         return float(L["loss"])
 
-    for _ in range(max(1, min(args.warmup, 1))):
+    warm = max(1, args.warmup)
+    for _ in range(warm):
         step()
-    steps = max(1, min(args.steps, 5))
+    steps = max(1, args.steps)  # exactly the K requested: a step is ~0.6 s on 16 cores, K = 10 ends in seconds
     t0 = time.perf_counter()
     for _ in range(steps):
         step()
     dt = (time.perf_counter() - t0) / steps
     val = 1.0 / dt
     line = {"impl": "reference", "metric": "radar frames/sec HRRadarPose fwd+bwd", "value": val, "unit": "frames/s",
-            "n_gpus": args.gpus, "steps": steps, "warmup": 1, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "%s fwd+bwd, batch 1 per step on host cores (bounded sample of the batch-16 workload)" % cfg,
-                       "grid": list(GRID)},
+            "config": dict(workload_config(cfg, args.batch, max(1, args.gpus), CFGS[cfg][7]),
+                           reference_sample="each step = batch 1 forward+backward of that workload on the host cores"),
             "cpu_baseline": {"value": val, "unit": "frames/s", "cores": cores, "kind": "port",
                              "sample": "%d steps x batch 1, fp32, torch CPU ops (same ATen kernels the reference calls)" % steps},
             "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -333,14 +341,12 @@ def run_ours(args, rank, world, local_rank):
     line = {"metric": "radar frames/sec HRRadarPose fwd+bwd", "value": value, "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "%s training fwd+bwd, batch %d per GPU, raw fp16 cube [%d,32,128,256] -> ingest -> "
-                                   "HRNet3D -> CenterHead -> loss -> backward" % (cfg, B, D),
-                       "per_gpu_batch": B, "global_batch": B * world, "grid": list(GRID), "parallelism": "dp%d" % world,
+            "config": dict(workload_config(cfg, B, world, D), **{
                        "l2": "inputs+activations per step >> 126 MB L2 (no explicit flush needed)",
                        "cuda_graph": use_graph, "wgrad_side_stream": bool(ops.ASYNC_WGRAD), "branch_streams": bool(eng.parallel_branches),
                        "targets": "assigned on the device from resident fp64 skeletons every step (rtp_assign_targets)",
                        "optimizer": ("fused clip(35) + decoupled wd + Adam, one-cycle lr (rtp_adam_step) inside the timed region"
-                                     if opt is not None else "none (--no-optimizer)")},
+                                     if opt is not None else "none (--no-optimizer)")}),
             "model_tflops": 3 * gf_fwd * 1e9 * value / 1e12, "model_flops_frac_of_peak": 3 * gf_fwd * 1e9 * value / 1e12 / world / pk_sust,
             "loss": float(out[0]), "gpu_launches": launches, "host_issue_ms_per_step": round(host_issue_ms, 2), "clocks": sampler.summary(), "roofline": roof, "top_kernels": top}
 
