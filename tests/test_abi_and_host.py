@@ -224,3 +224,52 @@ def test_one_cycle_schedule_equals_reference_golden():
             got = one_cycle(step, c["total_step"], lr_max=c["lr_max"], div_factor=c["div_factor"], pct_start=c["pct_start"],
                             moms=tuple(c["moms"]))
             assert abs(got[0] - lr) <= 1e-12 * abs(lr) and abs(got[1] - mom) <= 1e-12 * abs(mom), (c["total_step"], step, got, lr, mom)
+
+
+def test_header_is_plain_c_and_a_c_program_can_bind_the_library(tmp_path):
+    """include/rtpose_b200.h must be consumable by a C compiler (the FFI boundary, no C++ or torch types) and a C program
+    linked against librtpose_b200.so must be able to call it: version, error string, and the host-only .npy probe."""
+    import shutil
+    import subprocess
+    import numpy as np
+    from rtpose_b200 import lib
+    gcc = shutil.which("gcc")
+    if gcc is None or not os.path.exists(lib.LIB_PATH):
+        pytest.skip("needs gcc and the built library")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "bind.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "rtpose_b200.h"
+int main(int argc, char** argv) {
+  rtp_npy_info info;
+  rtp_conv_desc d;
+  memset(&d, 0, sizeof d);
+  if (argc < 2) return 9;
+  if (rtp_version() <= 0) return 10;
+  if (rtp_npy_probe("/nonexistent/cube.npy", &info) >= 0) return 11;
+  if (strstr(rtp_last_error(), "cannot open") == NULL) return 12;
+  if (rtp_npy_probe(argv[1], &info) != 0) return 13;
+  printf("%d %lld %lld %lld %s %d %d %d %d %d %d\n", info.ndim, (long long)info.shape[0], (long long)info.shape[1],
+         (long long)info.shape[2], info.descr, (int)sizeof(rtp_p8), (int)sizeof(rtp_conv_desc), (int)sizeof(rtp_npy_info),
+         (int)sizeof(rtp_conv_k3s1_desc), (int)sizeof(rtp_wgrad_desc), (int)sizeof(rtp_fuse_desc));
+  return 0;
+}
+''')
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", os.path.join(root, "include"),
+                    str(src)], check=True)
+    exe = tmp_path / "bind"
+    libdir = os.path.dirname(lib.LIB_PATH)
+    subprocess.run([gcc, "-std=c99", "-I", os.path.join(root, "include"), str(src), "-o", str(exe), "-L", libdir, "-lrtpose_b200",
+                    "-Wl,-rpath," + libdir], check=True)
+    cube = tmp_path / "c.npy"
+    np.save(cube, np.zeros((4, 6, 8), dtype=np.float16))
+    r = subprocess.run([str(exe), str(cube)], capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stderr)
+    out = r.stdout.split()
+    assert out[:5] == ["3", "4", "6", "8", "<f2"]
+    # the ctypes mirrors in rtpose_b200/lib.py have the C compiler's struct sizes (field order, padding)
+    import ctypes as C
+    assert [int(v) for v in out[5:]] == [C.sizeof(lib.P8Struct), C.sizeof(lib.ConvDesc), C.sizeof(lib.NpyInfo),
+                                         C.sizeof(lib.ConvK3S1Desc), C.sizeof(lib.WgradDesc), C.sizeof(lib.FuseDesc)]
