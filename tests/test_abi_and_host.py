@@ -239,6 +239,7 @@ def test_header_is_plain_c_and_a_c_program_can_bind_the_library(tmp_path):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     src = tmp_path / "bind.c"
     src.write_text(r'''
+#include <stddef.h>
 #include <stdio.h>
 #include <string.h>
 #include "rtpose_b200.h"
@@ -254,6 +255,12 @@ int main(int argc, char** argv) {
   printf("%d %lld %lld %lld %s %d %d %d %d %d %d\n", info.ndim, (long long)info.shape[0], (long long)info.shape[1],
          (long long)info.shape[2], info.descr, (int)sizeof(rtp_p8), (int)sizeof(rtp_conv_desc), (int)sizeof(rtp_npy_info),
          (int)sizeof(rtp_conv_k3s1_desc), (int)sizeof(rtp_wgrad_desc), (int)sizeof(rtp_fuse_desc));
+  printf("%d %d %d %d %d %d %d %d %d %d %d %d %d %d %d %d\n", (int)offsetof(rtp_conv_desc, w), (int)offsetof(rtp_conv_desc, Cin),
+         (int)offsetof(rtp_conv_desc, ntaps), (int)offsetof(rtp_conv_desc, tz), (int)offsetof(rtp_conv_desc, wt),
+         (int)offsetof(rtp_conv_desc, RZ), (int)offsetof(rtp_conv_desc, accumulate), (int)offsetof(rtp_conv_k3s1_desc, stat_mode),
+         (int)offsetof(rtp_conv_k3s1_desc, stat_ws), (int)offsetof(rtp_conv_k3s1_desc, tap_mask), (int)offsetof(rtp_conv_k3s1_desc, debug),
+         (int)offsetof(rtp_wgrad_desc, tc), (int)offsetof(rtp_wgrad_desc, workspace), (int)offsetof(rtp_fuse_desc, low),
+         (int)offsetof(rtp_fuse_desc, bias), (int)offsetof(rtp_npy_info, data_offset));
   return 0;
 }
 ''')
@@ -267,8 +274,15 @@ int main(int argc, char** argv) {
     np.save(cube, np.zeros((4, 6, 8), dtype=np.float16))
     r = subprocess.run([str(exe), str(cube)], capture_output=True, text=True)
     assert r.returncode == 0, (r.returncode, r.stderr)
-    out = r.stdout.split()
+    lines = r.stdout.strip().splitlines()
+    out = lines[0].split()
     assert out[:5] == ["3", "4", "6", "8", "<f2"]
+    offs = [int(v) for v in lines[1].split()]
+    L = lib
+    assert offs == [L.ConvDesc.w.offset, L.ConvDesc.Cin.offset, L.ConvDesc.ntaps.offset, L.ConvDesc.tz.offset, L.ConvDesc.wt.offset,
+                    L.ConvDesc.RZ.offset, L.ConvDesc.accumulate.offset, L.ConvK3S1Desc.stat_mode.offset, L.ConvK3S1Desc.stat_ws.offset,
+                    L.ConvK3S1Desc.tap_mask.offset, L.ConvK3S1Desc.debug.offset, L.WgradDesc.tc.offset, L.WgradDesc.workspace.offset,
+                    L.FuseDesc.low.offset, L.FuseDesc.bias.offset, L.NpyInfo.data_offset.offset]
     # the ctypes mirrors in rtpose_b200/lib.py have the C compiler's struct sizes (field order, padding)
     import ctypes as C
     assert [int(v) for v in out[5:]] == [C.sizeof(lib.P8Struct), C.sizeof(lib.ConvDesc), C.sizeof(lib.NpyInfo),
