@@ -56,6 +56,17 @@ def read_roi_slab(path, z0=ROI0[0], Z=GRID[0], y0=ROI0[1], Y=GRID[1], out=None, 
     return out
 
 
+def shard_paths(paths, rank, world, batch=1):
+    """The contiguous share of `paths` for data-parallel rank `rank` of `world` (rtpose_b200.dist.shard_frames), trimmed to whole
+    batches so that every rank iterates the same number of batches (the gradient all-reduce needs them in lock step):
+    `CubeLoader(shard_paths(paths, rank, world, batch), batch)`."""
+    from .dist import shard_frames
+    paths = list(paths)
+    per_rank = (len(paths) // world // batch) * batch if batch > 0 else len(paths) // world
+    lo, _ = shard_frames(len(paths), rank, world)
+    return paths[lo:lo + per_rank]
+
+
 def ingest_slab(slab, x0=ROI0[2], X=GRID[2], norm=None, out=None, want_f32=False):
     """Device slab fp16 [B, lead, Z, Y, RX] -> P8 bf16 [B, lead, Z, Y, X] (and optionally the reference's fp32 tensor)."""
     from .p8 import P8, _stream

@@ -116,3 +116,17 @@ def test_loader_refuses_to_run_without_a_device(tmp_path):
     p = _save(tmp_path / "g.npy", np.zeros((2, 32, 128, 256), dtype=np.float16))
     with pytest.raises(lib.RtpError, match="no CPU fallback"):
         loader.CubeLoader([p], 1)
+
+
+def test_shard_paths_gives_every_rank_the_same_number_of_whole_batches():
+    paths = ["f%03d.npy" % i for i in range(103)]
+    for world, batch in ((1, 16), (2, 16), (4, 8), (8, 3), (3, 1)):
+        shards = [loader.shard_paths(paths, r, world, batch) for r in range(world)]
+        n = (103 // world // batch) * batch
+        assert all(len(s) == n for s in shards), (world, batch, [len(s) for s in shards])
+        flat = [p for s in shards for p in s]
+        assert len(set(flat)) == len(flat) and all(s == sorted(s) for s in shards)   # disjoint, order kept
+        for r, s in enumerate(shards):
+            if s:
+                from rtpose_b200.dist import shard_frames
+                assert paths.index(s[0]) == shard_frames(103, r, world)[0]
