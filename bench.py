@@ -106,27 +106,64 @@ def workload_config(cfg, B, world, D):
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
-def run_reference(args, rank, world):
-    """The reference's own CPU implementation of the path (oracle port: same ATen ops, fp32, all host threads) on a
-    bounded sample: batch 1 forward+backward per step at the full 16x64x160 grid."""
-    if rank != 0:
-        return
+def reference_runner(cfg, batch, device="cpu", seed=1234):
+    """(train_step() -> loss, infer_step() -> detections, kind).  kind "reference": the reference's own, unmodified
+    RadarPoseNet (det3d registry -> build_detector) loaded from the staged copy baseline/_ref (or /root/reference in the
+    build container) through oracle/ref_loader.py, its stock code path (model(example, return_loss=True) -> loss dict ->
+    backward; model(example, return_loss=False) -> predict), random-init weights under manual_seed(0).
+    kind "port": the oracle restatement (same ATen ops), used only when no reference tree is reachable."""
     from oracle import hrpose_oracle as O
     from oracle import make_golden as G
-    cfg = args.cfg
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    x, poses, tgt = G.make_example(cfg, 1, GRID, seed=1234)
-    sd = {k: v.requires_grad_(True) for k, v in O.synth_state_dict(cfg).items()}
-    xt = torch.from_numpy(x)
+    from oracle import ref_loader
+    x, poses, tgt = G.make_example(cfg, batch, GRID, seed=seed)
+    xt = torch.from_numpy(x).to(device)
+    if ref_loader.available():
+        import contextlib
+        with contextlib.redirect_stdout(sys.stderr):  # the reference prints while importing / building; stdout carries the JSON line
+            mods = ref_loader.load()
+            torch.manual_seed(0)
+            model = mods["build_detector"](G.ref_model_cfg(cfg), train_cfg=None, test_cfg=G.ref_test_cfg()).to(device)
+        example = {"rdr": {"rdr_tensor": xt, "hm": [tgt["hm"].to(device)], "anno_pose": [tgt["anno_pose"].to(device)],
+                           "ind": [tgt["ind"].to(device)], "mask": [tgt["mask"].to(device)], "cat": [tgt["cat"].to(device)]},
+                   "meta": [{"i": i} for i in range(batch)]}
 
-    def step():
+        def train_step():
+            model.train()
+            model.zero_grad(set_to_none=True)
+            losses = model(example, return_loss=True)
+            losses["loss"][0].backward()
+            return losses["loss"][0]
+
+        def infer_step():
+            model.eval()
+            with torch.no_grad():
+                return model(example, return_loss=False)
+        return train_step, infer_step, "reference"
+    sd = {k: v.to(device).requires_grad_(True) for k, v in O.synth_state_dict(cfg).items()}
+
+    def train_step():
         for v in sd.values():
             v.grad = None
         L = O.forward_loss(xt, sd, cfg, tgt)
         L["loss"].backward()
-        return float(L["loss"])
+        return L["loss"]
 
+    def infer_step():
+        with torch.no_grad():
+            hm, reg = O.forward(xt, sd, cfg)
+            return O.decode(hm, reg)
+    return train_step, infer_step, "port"
+
+
+def run_reference(args, rank, world):
+    """The reference's own CPU implementation of the path (its unmodified modules, fp32, all host threads) on a bounded
+    sample: batch 1 forward+backward per step at the full 16x64x160 grid."""
+    if rank != 0:
+        return
+    cfg = args.cfg
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    step, _, kind = reference_runner(cfg, 1)
     warm = max(1, args.warmup)
     for _ in range(warm):
         step()
@@ -141,11 +178,56 @@ def run_reference(args, rank, world):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": dict(workload_config(cfg, args.batch, max(1, args.gpus), CFGS[cfg][7]),
                            reference_sample="each step = batch 1 forward+backward of that workload on the host cores"),
-            "cpu_baseline": {"value": val, "unit": "frames/s", "cores": cores, "kind": "port",
-                             "sample": "%d steps x batch 1, fp32, torch CPU ops (same ATen kernels the reference calls)" % steps},
+            "cpu_baseline": {"value": val, "unit": "frames/s", "cores": cores, "kind": kind,
+                             "sample": "%d steps x batch 1, fp32, %s" % (steps, "the reference's RadarPoseNet from baseline/_ref (stock code path)"
+                                                                        if kind == "reference" else "oracle port (same ATen kernels the reference calls)")},
             "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
+
+
+def ref_gpu_probe(args):
+    """Informative baseline: the UNMODIFIED reference modules on the same B200 through stock
+    PyTorch (cuDNN / ATen), fp32 and bf16 autocast — training fwd+bwd at the bench batch and inference + decode at batch
+    32.  Prints one JSON line; not the target, not part of the bench contract."""
+    dev = torch.device("cuda", 0)
+    out = {"probe": "reference modules on stock PyTorch %s, cuDNN %s, %s" % (torch.__version__, torch.backends.cudnn.version(),
+                                                                              torch.cuda.get_device_name(0)), "cfg": args.cfg}
+    torch.backends.cudnn.benchmark = True
+
+    def timed(fn, n):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+    for name, B, train in (("train_b%d" % args.batch, args.batch, True), ("infer_b32_incl_decode", 32, False)):
+        try:
+            tstep, istep, kind = reference_runner(args.cfg, B, device=dev)
+            out["kind"] = kind
+            fn = tstep if train else istep
+            for mode in ("fp32", "tf32", "bf16_autocast"):
+                torch.backends.cudnn.allow_tf32 = mode != "fp32"
+                torch.backends.cuda.matmul.allow_tf32 = mode != "fp32"
+                if mode == "bf16_autocast":
+                    def run(fn=fn):
+                        with torch.autocast("cuda", dtype=torch.bfloat16):
+                            return fn()
+                else:
+                    run = fn
+                ms = timed(run, 5)
+                out["%s_%s" % (name, mode)] = {"ms_per_step": round(ms, 2), "frames_per_s": round(B / ms * 1e3, 1)}
+            out["%s_peak_mem_GB" % name] = round(torch.cuda.max_memory_allocated() / 1e9, 1)
+            del tstep, istep, fn
+            torch.cuda.empty_cache()
+        except Exception as ex:
+            out[name] = {"error": repr(ex)[:300]}
+    print(json.dumps(out))
 
 
 # ------------------------------------------------------------------------------------------------ our arm
@@ -182,7 +264,7 @@ def run_ours(args, rank, world, local_rank):
     B = args.batch
     params, grads, flat, gflat = build_params(cfg, dev)
     if world > 1:
-        rdist.broadcast_params([flat])
+        rdist.broadcast_params([flat])  # in place, under no_grad: the views' shared version counter moves with it
     code_w = [1.0] * 45 if reg == 45 else [1.0, 1.5, 2.0]
     eng = Engine(arch, fuse, params, reg, ncls, weight, code_w)
 
@@ -454,24 +536,27 @@ def e2e_public_api(args, dev, rank=0, world=1):
 
 
 def cpu_baseline(args):
-    """Oracle port on the box's host cores: bounded sample (batch 1 fwd+bwd, full grid)."""
-    from oracle import hrpose_oracle as O
-    from oracle import make_golden as G
+    """The reference's modules (baseline/_ref; the oracle port when absent) on the box's host cores: bounded samples at
+    batch 1, full grid — training fwd+bwd (the headline metric) and forward + decode (BASELINE.json configs[0])."""
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    x, poses, tgt = G.make_example(args.cfg, 1, GRID, seed=1234)
-    sd = {k: v.requires_grad_(True) for k, v in O.synth_state_dict(args.cfg).items()}
-    xt = torch.from_numpy(x)
+    tstep, istep, kind = reference_runner(args.cfg, 1)
     times = []
     for i in range(4):
-        for v in sd.values():
-            v.grad = None
         t0 = time.perf_counter()
-        O.forward_loss(xt, sd, args.cfg, tgt)["loss"].backward()
+        tstep()
         times.append(time.perf_counter() - t0)
     dt = float(np.median(times[1:]))
-    return {"value": 1.0 / dt, "unit": "frames/s", "cores": cores, "kind": "port",
-            "sample": "batch 1 fwd+bwd at 16x64x160, fp32, 1 warm-up + median of 3 (torch CPU ops, %d threads)" % cores}
+    itimes = []
+    for i in range(4):
+        t0 = time.perf_counter()
+        istep()
+        itimes.append(time.perf_counter() - t0)
+    di = float(np.median(itimes[1:]))
+    return {"value": 1.0 / dt, "unit": "frames/s", "cores": cores, "kind": kind,
+            "sample": "batch 1 fwd+bwd at 16x64x160, fp32, 1 warm-up + median of 3 (%d threads)" % cores,
+            "fwd_decode_b1": {"value": 1.0 / di, "unit": "frames/s", "ms": di * 1e3,
+                              "sample": "configs[0]: batch 1 forward + predict/decode on the host cores, median of 3"}}
 
 
 def loader_bench(args, dev):
@@ -580,11 +665,16 @@ def main():
     ap.add_argument("--sync-wgrad", action="store_true", help="run weight gradients in-stream (no side stream)")
     ap.add_argument("--no-extras", action="store_true", help="skip e2e / cpu_baseline / inference legs")
     ap.add_argument("--no-optimizer", action="store_true", help="time forward+backward only (no fused clip+Adam step)")
+    ap.add_argument("--ref-gpu-probe", action="store_true", help="time the unmodified reference on this GPU through stock PyTorch (informative)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.ref_gpu_probe:
+        if rank == 0:
+            ref_gpu_probe(args)
+        return
     if args.impl == "reference":
         run_reference(args, rank, world)
         return

@@ -396,6 +396,42 @@ def synth_state_dict(cfg, seed=0):
     return sd
 
 
+def reference_init_state_dict(cfg, seed=0):
+    """Random-init weights with the distributions the reference's constructors draw from:
+    Conv3d default = kaiming_uniform_(a=sqrt(5)) -> U(+-1/sqrt(fan_in)), conv bias U(+-1/sqrt(fan_in)) (torch
+    nn.Conv3d.reset_parameters, called at common.py:40,114; hr3d.py:84-185; hrnet3d.py:20; center_head.py:86-91);
+    GroupNorm gamma 1 / beta 0; every conv of a non-'hm' head kaiming_init (normal, fan_out, relu, bias 0:
+    center_head.py:96-99, torchie/cnn/weight_init.py:32-45); 'hm' last-conv bias = -2.19 (center_head.py:94-95).
+    Same distributions as the reference model under a seed, not the same bits (the draw order of its constructors is
+    not reproduced); tests/test_oracle_golden.py pins the per-tensor statistics against the reference's own model."""
+    g = torch.Generator().manual_seed(1000 + seed)
+    sd = {}
+    for key, shape in state_dict_spec(cfg):
+        if len(shape) == 5:
+            fan_in = shape[1] * shape[2] * shape[3] * shape[4]
+            if ".reg." in key:
+                fan_out = shape[0] * shape[2] * shape[3] * shape[4]
+                w = torch.randn(shape, generator=g) * math.sqrt(2.0 / fan_out)
+            else:
+                b = 1.0 / math.sqrt(fan_in)
+                w = (torch.rand(shape, generator=g) * 2 - 1) * b
+        elif key.endswith("hm.2.bias"):
+            w = torch.full(shape, -2.19)
+        elif ".reg." in key and key.endswith(".bias"):
+            w = torch.zeros(shape)
+        elif key.endswith(".bias") and ("groupnorm" in key or key.split(".")[-2] in ("0",) and "tasks" not in key and "conv1" not in key):
+            w = torch.zeros(shape)  # GroupNorm beta
+        elif key.endswith(".bias"):
+            fan_in = dict(state_dict_spec(cfg))[key[:-4] + "weight"]
+            fan_in = fan_in[1] * fan_in[2] * fan_in[3] * fan_in[4]
+            b = 1.0 / math.sqrt(fan_in)
+            w = (torch.rand(shape, generator=g) * 2 - 1) * b
+        else:
+            w = torch.ones(shape)  # GroupNorm gamma
+        sd[key] = w.float()
+    return sd
+
+
 def synth_pose(rs, grid_zyx, voxel=VOXEL_SIZE, pc_range=PC_RANGE):
     """Random 15-joint skeleton: pelvis uniform in the ROI shrunk by 0.5 m (or 25 % of a small
     test grid), joints = pelvis + N(0, 0.3 m) clipped to the ROI."""

@@ -1,16 +1,17 @@
 """TEST INFRASTRUCTURE — not part of the product path.
 
-Loads the *unmodified* reference hot-path modules from /root/reference behind namespace shells so that
-golden vectors can be generated in the build container (the reference cannot travel to the GPU box).
-Recipe follows SURVEY.md Appendix B.  Only `oracle/make_golden.py` and `tests/` (not-gpu, skipped when
-/root/reference is absent) may import this file.
+Loads the *unmodified* reference hot-path modules behind namespace shells: from /root/reference in the build
+container (golden vectors), or from the staged copy baseline/_ref (oracle/install_ref.py; git-ignored, it travels to
+the GPU box) for `bench.py --impl reference`, `cpu_baseline` and the stock-PyTorch GPU probe.
+Recipe follows SURVEY.md Appendix B.  Only `oracle/make_*.py`, `tests/` and `bench.py`'s reference legs import this.
 """
 import importlib
 import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("RTPOSE_REFERENCE", "/root/reference")
+_STAGED = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
+REF_ROOT = os.environ.get("RTPOSE_REFERENCE") or ("/root/reference" if os.path.isdir("/root/reference/det3d") else _STAGED)
 
 
 def available():

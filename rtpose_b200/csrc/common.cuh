@@ -17,6 +17,15 @@ void rtp_set_error(const char* fmt, ...);
       return -1;                      \
     }                                 \
   } while (0)
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) applies per device: launchers cache "already opted in up to N bytes"
+// per device ordinal so a process that drives several GPUs configures each of them.
+#define RTP_MAX_DEVICES 64
+static inline int rtp_current_device() {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= RTP_MAX_DEVICES) d = 0;
+  return d;
+}
+
 #define RTP_LAUNCH_CHECK()                                                        \
   do {                                                                            \
     cudaError_t e__ = cudaGetLastError();                                         \

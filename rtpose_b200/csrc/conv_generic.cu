@@ -275,7 +275,8 @@ int conv_launch(const rtp_conv_desc* descs, int n, void* stream) {
   const size_t smem = stages * stage;
   RTP_CHECK_ARG(smem <= 200 * 1024, "rtp_conv: Cin=%d NP=%d needs %zu B of shared memory", d->Cin, d->NP, smem);
   auto kern = stages == 4 ? conv_generic_kernel<4> : (stages == 3 ? conv_generic_kernel<3> : conv_generic_kernel<2>);
-  static size_t configured[5] = {0, 0, 0, 0, 0};
+  static size_t configured_dev[RTP_MAX_DEVICES][5];  /* the opt-in is per device */
+  size_t* configured = configured_dev[rtp_current_device()];
   if (smem > configured[stages]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { rtp_set_error("rtp_conv: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }

@@ -535,7 +535,8 @@ extern "C" int rtp_conv_k3s1(const rtp_conv_k3s1_desc* d, void* stream) {
   void (*kerns[6])(const K3) = {conv_k3s1_kernel<1, 0>, conv_k3s1_kernel<2, 0>, conv_k3s1_kernel<1, 1>,
                                 conv_k3s1_kernel<2, 1>, conv_k3s1_kernel<1, 2>, conv_k3s1_kernel<2, 2>};
   auto kern = kerns[ki];
-  static size_t configured[6] = {0, 0, 0, 0, 0, 0};
+  static size_t configured_dev[RTP_MAX_DEVICES][6];  /* the opt-in is per device */
+  size_t* configured = configured_dev[rtp_current_device()];
   if (pl.smem > configured[ki]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
     if (e != cudaSuccess) { rtp_set_error("rtp_conv_k3s1: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }

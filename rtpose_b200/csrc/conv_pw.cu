@@ -204,7 +204,8 @@ extern "C" int rtp_conv_pw(rtp_p8 in, rtp_p8 out, rtp_p8 mask, const void* w, co
   k.ntile = (k.npos + 127) / 128;
   k.nunits = in.N * k.ntile;
   k.stage_bytes = (uint32_t)K * 256; k.w_bytes = (uint32_t)K * NP * 2;
-  static size_t configured = 0;
+  static size_t configured_dev[RTP_MAX_DEVICES];  /* the opt-in is per device */
+  size_t& configured = configured_dev[rtp_current_device()];
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(conv_pw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { rtp_set_error("rtp_conv_pw: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }

@@ -470,7 +470,8 @@ int launch_fwd(const Dcn& d, const float* x, const float* offset, const float* m
                cudaStream_t st) {
   const size_t smem = (((size_t)kCT * d.kh * d.kw * (kFPix + kWPitch) + 3) & ~(size_t)3) * sizeof(float) +
                       (size_t)d.kh * d.kw * kFPix * 2 * sizeof(float4);
-  static size_t configured = 0;
+  static size_t configured_dev[RTP_MAX_DEVICES];  /* the opt-in is per device */
+  size_t& configured = configured_dev[rtp_current_device()];
   if (smem > configured) {
     cudaFuncSetAttribute(dcn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     configured = smem;
@@ -484,7 +485,8 @@ int launch_bwd_input(const Dcn& d, const float* x, const float* offset, const fl
                      float* doffset, float* dmask, cudaStream_t st, const char* who) {
   const size_t smem = ((size_t)kCT * d.kh * d.kw * kPix + (size_t)d.Cout * kPix) * sizeof(float);
   RTP_CHECK_ARG(smem <= 200 * 1024, "%s: Cout=%d too large", who, d.Cout);
-  static size_t configured = 0;
+  static size_t configured_dev[RTP_MAX_DEVICES];  /* the opt-in is per device */
+  size_t& configured = configured_dev[rtp_current_device()];
   if (smem > configured) {
     cudaFuncSetAttribute(dcn_bwd_input_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     configured = smem;

@@ -435,7 +435,8 @@ extern "C" int rtp_upsample_bwd(rtp_p8 dout, rtp_p8 dlow, int32_t C, int32_t acc
   const int nrows_max = sxh > 0.f ? (int)ceilf((float)(kTXL + 1) / sxh) + 4 : 0;
   const size_t smem = (size_t)nrows_max * dlow.Y * 32;
   if (!no_fused && sxh > 0.f && dlow.Y > 1 && dout.Y > 1 && smem <= 96 * 1024) {
-    static size_t configured = 0;
+    static size_t configured_dev[RTP_MAX_DEVICES];  /* the opt-in is per device */
+  size_t& configured = configured_dev[rtp_current_device()];
     if (smem > configured) {
       cudaFuncSetAttribute(upsample_bwd_yx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       configured = smem;

@@ -278,7 +278,8 @@ extern "C" int rtp_wgrad(const rtp_wgrad_desc* d, void* stream) {
   k.tmem_cols = cols_pow2(k.blocks_per_cta * d->NP);
   k.partial = d->workspace;
   const size_t smem = (size_t)kStages * (16 * kTileK * 16 + (d->NP / 8) * kTileK * 16);
-  static size_t configured = 0;
+  static size_t configured_dev[RTP_MAX_DEVICES];  /* the opt-in is per device */
+  size_t& configured = configured_dev[rtp_current_device()];
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(wgrad_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { rtp_set_error("rtp_wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }

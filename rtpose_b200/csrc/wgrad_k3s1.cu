@@ -292,7 +292,8 @@ extern "C" int rtp_wgrad_k3s1(rtp_p8 x, rtp_p8 dy, int32_t NP, const void* zero_
   }
   const int grid = k.nunits < nsm ? k.nunits : nsm;
   *nsplit_out = grid;
-  static size_t configured = 0;
+  static size_t configured_dev[RTP_MAX_DEVICES];  /* the opt-in is per device */
+  size_t& configured = configured_dev[rtp_current_device()];
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(wgrad_k3s1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { rtp_set_error("rtp_wgrad_k3s1: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }

@@ -202,6 +202,15 @@ class _ParamJob:
         return [views[k] if (k in touched and self.params[k].requires_grad) else None for k in self.names]
 
 
+def _check_live(now, stamp):
+    """An engine keeps ONE tape and one set of activation buffers: a second training forward (micro-batch accumulation,
+    (loss_a + loss_b).backward()) recycles what the first one recorded.  Fail loudly instead of returning gradients of
+    the wrong forward."""
+    if now != stamp:
+        raise lib.RtpError("backward() of a forward pass whose tape was overwritten by a later forward of the same module "
+                           "(run forward -> backward pairs one at a time; accumulate gradients across them instead)")
+
+
 class _StepJob(_ParamJob):
     """RadarPoseNet training step: input cube -> backbone -> head -> loss (+ gradient seeds) in one go.
 
@@ -226,6 +235,7 @@ class _StepJob(_ParamJob):
             return self._run_graphed()
         e = self.engine
         hm, reg = e.forward(_as_p8(self.x), self.train)
+        self.gen = e.generation
         return e.loss(hm, reg, *self._targets(), with_grad=self.train)
 
     def _run_graphed(self):
@@ -251,17 +261,21 @@ class _StepJob(_ParamJob):
         _x_copy(st["x"], self.x)
         for d, t in zip(st["tgt"], tgt):
             d.copy_(t)
+        st["replays"] = st.get("replays", 0) + 1
+        self.gen = st["replays"]
         return st["graph"]().clone()
 
     def run_backward(self, gouts):
         if self.graph_state is not None:
             st = self.graph_state
+            _check_live(st.get("replays"), self.gen)
             flat = st["flat"].clone()  # the static buffer is overwritten by the next replay
             views, o = {}, 0
             for k, p in self.params.items():
                 views[k] = flat[o:o + p.numel()].view(p.shape)
                 o += p.numel()
             return self.finish(flat, views, gouts[0][0], st["touched"])
+        _check_live(self.engine.generation, self.gen)
         flat, views = self.grads_buffer()
         touched = self.engine.backward(views)
         # d(out[0]) is the only differentiable element; its incoming gradient rescales everything linearly
@@ -276,11 +290,13 @@ class _BackboneJob(_ParamJob):
     def run_forward(self):
         e = self.engine
         e.begin()
+        self.gen = e.generation
         self.f = e.backbone(P8.from_ncdhw(self.x), self.train)
         return self.f.to_ncdhw()
 
     def run_backward(self, gouts):
         e, f = self.engine, self.f
+        _check_live(e.generation, self.gen)
         g = P8.from_ncdhw(gouts[0].contiguous())
         if f.relu_out:
             f.grad = e.new(f)
@@ -302,12 +318,14 @@ class _HeadJob(_ParamJob):
     def run_forward(self):
         e = self.engine
         e.begin()
+        self.gen = e.generation
         self.fp = P8.from_ncdhw(self.x)
         self.hm, self.reg = e.head(self.fp, self.train)
         return self.hm.to_ncdhw(), self.reg.to_ncdhw()
 
     def run_backward(self, gouts):
         e = self.engine
+        _check_live(e.generation, self.gen)
         self.hm.grad = P8.from_ncdhw(gouts[0].contiguous())
         self.reg.grad = P8.from_ncdhw(gouts[1].contiguous())
         flat, views = self.grads_buffer()
@@ -542,24 +560,63 @@ class RadarPoseNet(nn.Module):
 
 
 # ------------------------------------------------------------------------------------------------ det3d aliasing
+def _real_or_shell(name, attach_to=None):
+    """The real det3d module `name` when the reference is on sys.path and it imports; otherwise a shell module whose
+    __path__ points at the real package directory when that exists (so its untouched sub-modules stay importable) or is
+    empty (no reference on sys.path at all).  Never replaces a module that is already in sys.modules."""
+    import importlib
+    import importlib.util
+    m = sys.modules.get(name)
+    if m is not None:
+        return m
+    spec = None
+    try:
+        spec = importlib.util.find_spec(name)
+    except Exception:
+        spec = None
+    if spec is not None:
+        try:
+            return importlib.import_module(name)
+        except Exception:
+            sys.modules.pop(name, None)  # e.g. det3d.models needs spconv / pycocotools: fall through to a shell
+    m = types.ModuleType(name)
+    m.__path__ = list(spec.submodule_search_locations or []) if spec is not None and spec.submodule_search_locations else []
+    m.__package__ = name
+    if spec is not None:
+        m.__spec__ = spec
+    sys.modules[name] = m
+    if "." in name:
+        parent = sys.modules.get(name.rsplit(".", 1)[0])
+        if parent is not None:
+            setattr(parent, name.rsplit(".", 1)[1], m)
+    return m
+
+
 def install_as_det3d():
-    """Registers `det3d`, `det3d.models`, `det3d.models.builder`, ... aliases so that `from det3d.models import
-    build_detector` (tools/train.py:21, tools/test.py:17) resolves to this implementation."""
+    """Makes `from det3d.models import build_detector` (tools/train.py:22, tools/test.py:20) and the builder / registry
+    names resolve to this implementation WITHOUT hiding the rest of the reference: when the real `det3d` package is
+    importable (the maintainer's case) it is imported first and only the model-builder attributes are patched onto
+    `det3d.models`, `det3d.models.builder`, `det3d.models.registry` and `det3d.builder`; `det3d.utils`, `det3d.torchie`,
+    `det3d.datasets`, ... stay the reference's own modules.  Shell modules are created only for names that cannot be
+    imported (no reference on sys.path, or `det3d.models` failing on its optional dependencies)."""
     me = sys.modules[__name__]
-    names = ["det3d", "det3d.models", "det3d.models.builder", "det3d.models.registry", "det3d.utils", "det3d.builder"]
-    for n in names:
-        m = sys.modules.get(n) or types.ModuleType(n)
-        m.__path__ = getattr(m, "__path__", [])
-        for k in ("build_detector", "build_backbone", "build_head", "build_reader", "build_neck", "build", "Registry",
-                  "build_from_cfg", "READERS", "BACKBONES", "NECKS", "HEADS", "LOSSES", "DETECTORS", "RadarPoseNet",
-                  "HRNet3D", "CenterHead", "RadarFeatureNet"):
+    _real_or_shell("det3d")
+    exported = ("build_detector", "build_backbone", "build_head", "build_reader", "build_neck", "build", "Registry",
+                "build_from_cfg", "READERS", "BACKBONES", "NECKS", "HEADS", "LOSSES", "DETECTORS", "RadarPoseNet",
+                "HRNet3D", "CenterHead", "RadarFeatureNet")
+    for n in ("det3d", "det3d.models", "det3d.models.builder", "det3d.models.registry", "det3d.builder"):
+        m = _real_or_shell(n)
+        for k in exported:
             setattr(m, k, getattr(me, k))
-        sys.modules[n] = m
-    # `from det3d.ops.dcn import DeformConv` (pose_heads/center_head.py:18) and det3d/ops/dcn/__init__.py's other names
+    u = _real_or_shell("det3d.utils")  # the reference's own module when present: only fill in what it lacks
+    for k in ("Registry", "build_from_cfg"):
+        if not hasattr(u, k):
+            setattr(u, k, getattr(me, k))
+    # `from det3d.ops.dcn import DeformConv` (pose_heads/center_head.py:18) and det3d/ops/dcn/__init__.py's other names:
+    # the reference's extension is not built on sm_100, so these always resolve to the B200 kernels
     from . import dcn
-    ops_mod = sys.modules.get("det3d.ops") or types.ModuleType("det3d.ops")
-    ops_mod.__path__ = getattr(ops_mod, "__path__", [])
+    ops_mod = _real_or_shell("det3d.ops")
     ops_mod.dcn = dcn
-    sys.modules["det3d.ops"], sys.modules["det3d.ops.dcn"], sys.modules["det3d.ops.dcn.deform_conv"] = ops_mod, dcn, dcn
+    sys.modules["det3d.ops.dcn"], sys.modules["det3d.ops.dcn.deform_conv"] = dcn, dcn
     sys.modules["det3d"].ops = ops_mod
     return sys.modules["det3d"]

@@ -16,17 +16,35 @@ def shard_frames(total_frames, rank, world):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def allreduce_flat(flat, world=None, async_op=False):
-    """In-place mean of a flat gradient buffer over all ranks.  Returns the work handle when async_op."""
+class _MeanWork:
+    """Handle of an asynchronous mean all-reduce: wait() also applies the 1/world scale (once)."""
+
+    def __init__(self, work, flat, world):
+        self.work, self.flat, self.world = work, flat, world
+
+    def wait(self):
+        if self.work is not None:
+            self.work.wait()
+            scale_flat(self.flat, 1.0 / self.world)
+            self.work = None
+        return True
+
+
+def allreduce_flat(flat, world=None, async_op=False, prescaled=False):
+    """In-place mean of a flat gradient buffer over all ranks.  async_op: returns a handle whose wait() completes the
+    mean (sum, then 1/world).  prescaled: the caller already folded 1/world in (e.g. into the loss gradient seed), so
+    only the sum is taken."""
     if not (dist.is_available() and dist.is_initialized()):
         return None
     world = world or dist.get_world_size()
     if world == 1:
         return None
     if async_op:
-        return dist.all_reduce(flat, op=dist.ReduceOp.SUM, async_op=True)
+        work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, async_op=True)
+        return work if prescaled else _MeanWork(work, flat, world)
     dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-    scale_flat(flat, 1.0 / world)
+    if not prescaled:
+        scale_flat(flat, 1.0 / world)
     return None
 
 
@@ -39,8 +57,17 @@ def allreduce_grads(params, world=None):
     world = world or dist.get_world_size()
     if world == 1:
         return
-    grads = [p.grad for p in params if p.requires_grad and p.grad is not None]
-    if not grads:
+    params = [p for p in params if p.requires_grad]
+    if not params:
+        return
+    # every rank must reduce the same layout: a parameter without a gradient on this rank contributes zeros
+    for p in params:
+        if p.grad is None:
+            p.grad = torch.zeros_like(p)
+    grads = [p.grad for p in params]
+    base = _common_flat(grads)
+    if base is not None:  # the gradients are already views of one flat buffer (det3d_compat hands them out that way)
+        allreduce_flat(base, world)
         return
     flat = torch.cat([g.reshape(-1) for g in grads])
     allreduce_flat(flat, world)
@@ -48,6 +75,19 @@ def allreduce_grads(params, world=None):
     for g in grads:
         g.copy_(flat[o:o + g.numel()].view_as(g))
         o += g.numel()
+
+
+def _common_flat(grads):
+    """The flat tensor the gradients are consecutive, gap-free views of, or None."""
+    b = grads[0]._base if grads[0]._base is not None else None
+    if b is None or b.dim() != 1 or not b.is_contiguous():
+        return None
+    o = 0
+    for g in grads:
+        if g._base is not b or not g.is_contiguous() or g.storage_offset() != b.storage_offset() + o:
+            return None
+        o += g.numel()
+    return b if o == b.numel() else None
 
 
 def scale_flat(flat, s):
@@ -61,5 +101,6 @@ def scale_flat(flat, s):
 def broadcast_params(params, src=0):
     """One-time parameter broadcast (DDP does this at wrap time)."""
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-        for p in params:
-            dist.broadcast(p.data if hasattr(p, "data") else p, src)
+        with torch.no_grad():  # broadcast INTO the tensor (not .data) so its version counter moves and weight packs rebuild
+            for p in params:
+                dist.broadcast(p, src)

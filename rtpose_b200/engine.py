@@ -48,6 +48,7 @@ class Engine:
         self.parallel_fuse_bwd = False  # measured: no gain (the ordered accumulation into shared gradients serialises it)
         self._ordered_grads = False  # set while backward closures may run on several streams
         self._bstreams = {}
+        self.generation = 0  # bumped by begin(): a backward job checks that the tape it recorded is still the live one
 
     # ------------------------------------------------------------------ helpers
     def new(self, like, C=None, grid=None):
@@ -436,6 +437,7 @@ class Engine:
 
     # ------------------------------------------------------------------ entry points
     def begin(self):
+        self.generation += 1
         self.pool.release_all()
         self.tape = []
         self.stats_cache = {}

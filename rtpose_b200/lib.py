@@ -181,9 +181,11 @@ LAUNCHES = {"rtp_pack_ncdhw": 1, "rtp_unpack_ncdhw": 1, "rtp_ingest_pack": 1, "r
             "rtp_gn_bwd_apply_s2d": 1, "rtp_conv_k3s1_stat_finalize": 1, "rtp_conv_multi": 1, "rtp_gn_stats": 2,
             "rtp_npy_probe": 0, "rtp_npy_read_roi_slab": 0}  # host-only file readers
 launch_count = 0
+call_counts = {}  # C-ABI entry point -> number of calls (tests assert which kernel path a shape really took)
 
 
 def call(name, *args):
     global launch_count
     launch_count += LAUNCHES.get(name, 1)
+    call_counts[name] = call_counts.get(name, 0) + 1
     check(getattr(load(), name)(*args), name)

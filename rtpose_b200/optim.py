@@ -23,13 +23,16 @@ class FlatAdam:
     from a pinned ring — runs before each replay."""
     RING = 1024  # pinned schedule slots: the host may run this many steps ahead of the device
 
-    def __init__(self, flat_params, flat_grads, wd=0.01, eps=1e-8, beta2=0.99, max_norm=35.0):
+    def __init__(self, flat_params, flat_grads, wd=0.01, eps=1e-8, beta2=0.99, max_norm=35.0, params=()):
+        """params: tensors that alias the flat buffer WITHOUT sharing its version counter (nn.Parameters whose .data was
+        pointed into it); views taken with flat[a:b].view(...) share the counter and need not be listed."""
         assert flat_params.is_cuda and flat_params.dtype == torch.float32 and flat_params.is_contiguous()
         assert flat_grads.shape == flat_params.shape and flat_grads.dtype == torch.float32
         self.p, self.g = flat_params, flat_grads
         self.m, self.v = torch.zeros_like(flat_params), torch.zeros_like(flat_params)
         self.wd, self.eps, self.beta2, self.max_norm = float(wd), float(eps), float(beta2), float(max_norm)
         self.t = 0
+        self._aliases = list(params)
         dev = flat_params.device
         self.ws = torch.empty(lib.load().rtp_adam_workspace_bytes(), dtype=torch.uint8, device=dev)
         self.grad_norm = torch.zeros(1, dtype=torch.float32, device=dev)
@@ -48,9 +51,19 @@ class FlatAdam:
         slot[7] = self.max_norm
         self.hyper.copy_(slot, non_blocking=True)
 
+    def _mark_written(self):
+        """The kernel rewrote the parameters through raw pointers: tell torch, so that everything keyed on a parameter's
+        `_version` — the engine's bf16 weight packs (ops.PackedWeights), its space-to-depth and merged-head keys — sees
+        the change and repacks.  (Inside a replayed CUDA graph no Python runs: a captured step must contain
+        `packs.refresh_async()` itself, as bench.py and det3d_compat do.)"""
+        torch.autograd.graph.increment_version(self.p)
+        for t in self._aliases:
+            torch.autograd.graph.increment_version(t)
+
     def step_dev(self):
         lib.call("rtp_adam_step_dev", self.p.data_ptr(), self.g.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), self.p.numel(),
                  self.hyper.data_ptr(), self.ws.data_ptr(), self.grad_norm.data_ptr(), _stream())
+        self._mark_written()
 
     def step(self, lr, mom=0.9):
         self.set_hyper(lr, mom)
@@ -62,6 +75,7 @@ class FlatAdam:
         lib.call("rtp_adam_step", self.p.data_ptr(), self.g.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), self.p.numel(),
                  float(lr), float(mom), self.beta2, self.eps, self.wd, self.t, self.max_norm, self.ws.data_ptr(),
                  self.grad_norm.data_ptr(), _stream())
+        self._mark_written()
 
 
 def one_cycle(step, total_steps, lr_max=2e-3, div_factor=10.0, pct_start=0.4, moms=(0.95, 0.85)):

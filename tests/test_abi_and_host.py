@@ -3,6 +3,7 @@ host logic (tap lists, target assignment, config loading, registry/builder, stat
 no-CPU-fallback contract."""
 import os
 import re
+import sys
 
 import numpy as np
 import pytest
@@ -287,3 +288,34 @@ int main(int argc, char** argv) {
     import ctypes as C
     assert [int(v) for v in out[5:]] == [C.sizeof(lib.P8Struct), C.sizeof(lib.ConvDesc), C.sizeof(lib.NpyInfo),
                                          C.sizeof(lib.ConvK3S1Desc), C.sizeof(lib.WgradDesc), C.sizeof(lib.FuseDesc)]
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/det3d"), reason="reference tree not present (GPU box)")
+def test_install_as_det3d_does_not_shadow_the_reference_package():
+    """INTEGRATION.md §1 calls install_as_det3d() at the top of tools/train.py, BEFORE det3d is imported: the reference's
+    own packages (det3d.utils, det3d.torchie, det3d.datasets, ...) must stay reachable afterwards.  This container lacks
+    some of the reference's third-party dependencies (terminaltables, spconv), so `import det3d.torchie` may still fail —
+    but only on a third-party name, never because a det3d.* module was replaced by an empty shell."""
+    import subprocess
+    code = r'''
+import sys
+sys.path.insert(0, "/root/reference"); sys.path.insert(0, %r)
+import rtpose_b200.det3d_compat as b
+d = b.install_as_det3d()
+assert d.__file__.startswith("/root/reference/det3d"), d
+from det3d.models import build_detector
+assert build_detector is b.build_detector
+import det3d.utils
+assert any(p.startswith("/root/reference/det3d/utils") for p in det3d.utils.__path__), det3d.utils.__path__
+assert hasattr(det3d.utils, "Registry") and hasattr(det3d.utils, "build_from_cfg")
+import det3d.utils.dist                      # a sub-package of the reference that needs no third-party module
+for name in ("det3d.torchie", "det3d.datasets", "det3d.torchie.utils"):
+    try:
+        __import__(name)
+    except ModuleNotFoundError as ex:
+        assert not (ex.name or "").startswith("det3d"), (name, ex.name)   # only a missing third-party dependency
+from det3d.ops.dcn import DeformConv
+print("ok")
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd="/tmp", timeout=300)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stderr[-2000:]

@@ -140,3 +140,70 @@ def test_graphed_train_step_equals_eager_and_follows_weight_updates():
         for k in ge:
             assert torch.equal(ge[k], gg[k]), (it, k)
     assert graphed._graph_state.get("graph") is not None
+
+
+def test_second_forward_before_backward_raises_instead_of_wrong_gradients():
+    """One engine = one tape: backward of a forward whose tape a later forward recycled must fail loudly (eager and
+    graphed), not return the other forward's gradients."""
+    from rtpose_b200.lib import RtpError
+    cfg, grid, batch = "hr3d_one_hm_doppler", (8, 16, 16), 1
+    for graphed in (False, True):
+        model, _ = build(cfg)
+        model.cuda_graph = graphed
+        model.pose_head.sync_free_losses = True
+        model.train()
+        xa, _, ta = G.make_example(cfg, batch, grid, seed=61)
+        xb, _, tb = G.make_example(cfg, batch, grid, seed=62)
+        la = model(example_of(xa, ta, batch), return_loss=True)["loss"][0]
+        lb = model(example_of(xb, tb, batch), return_loss=True)["loss"][0]
+        with pytest.raises(RtpError):
+            la.backward()
+        model.zero_grad(set_to_none=True)
+        lb2 = model(example_of(xb, tb, batch), return_loss=True)["loss"][0]
+        lb2.backward()  # the latest forward is still fine
+        assert model.backbone.backbone.layer1.conv2.conv.weight.grad is not None
+
+
+def test_flat_adam_step_invalidates_the_weight_packs_of_an_eager_engine():
+    """FlatAdam rewrites the parameters through raw pointers; the engine's bf16 weight packs are keyed on the parameters'
+    version counters, so the optimizer must bump them — otherwise an eager engine keeps convolving with step-0 weights."""
+    from rtpose_b200.engine import Engine
+    from rtpose_b200.optim import FlatAdam
+    from rtpose_b200.p8 import P8
+    cfg, grid, batch = "hr3d_one_hm_doppler", (8, 16, 16), 1
+    c = O.CONFIGS[cfg]
+    sd = O.synth_state_dict(cfg)
+    total = sum(v.numel() for v in sd.values())
+    flat = torch.empty(total, dtype=torch.float32, device="cuda")
+    gflat = torch.zeros_like(flat)
+    params, grads, o = {}, {}, 0
+    for k, v in sd.items():
+        params[k] = flat[o:o + v.numel()].view(v.shape)
+        params[k].copy_(v)
+        grads[k] = gflat[o:o + v.numel()].view(v.shape)
+        o += v.numel()
+    eng = Engine(c["arch"], c["fuse"], params, c["reg"], c["ncls"], c["weight"], c["code_weights"])
+    opt = FlatAdam(flat, gflat, wd=0.01, max_norm=35.0)
+    x, _, tgt = G.make_example(cfg, batch, grid, seed=63)
+    xp = P8.from_ncdhw(torch.from_numpy(x).cuda())
+    tg = [tgt[k].cuda() for k in ("hm", "ind", "mask", "cat", "anno_pose")]
+    losses = []
+    for it in range(3):
+        hm, reg = eng.forward(xp, True)
+        losses.append(float(eng.loss(hm, reg, *tg)[0]))
+        eng.backward(grads)
+        opt.step(5e-3, 0.9)
+    assert losses[1] != losses[0] and losses[2] != losses[1], losses
+    # the same three steps with explicitly invalidated packs give the same losses: the version bump alone is enough
+    for k, v in sd.items():
+        params[k].copy_(v)
+    torch.autograd.graph.increment_version(flat)
+    opt2 = FlatAdam(flat, gflat, wd=0.01, max_norm=35.0)
+    ref = []
+    for it in range(3):
+        eng.packs.invalidate()
+        hm, reg = eng.forward(xp, True)
+        ref.append(float(eng.loss(hm, reg, *tg)[0]))
+        eng.backward(grads)
+        opt2.step(5e-3, 0.9)
+    assert ref == losses, (ref, losses)

@@ -27,12 +27,25 @@ def _worker(rank, world, port, out):
         rdist.allreduce_flat(flat, world)
         params = torch.full((5,), float(rank + 7))
         rdist.broadcast_params([params])
-        h = rdist.allreduce_flat(torch.ones(3) * rank, world, async_op=True)
+        t3 = torch.ones(3) * rank
+        h = rdist.allreduce_flat(t3, world, async_op=True)
         h.wait()
+        assert t3.tolist() == [0.5] * 3, t3     # wait() completes the MEAN, not just the sum
+        h.wait()
+        assert t3.tolist() == [0.5] * 3         # ... exactly once
         ps = [torch.nn.Parameter(torch.zeros(2, 3)), torch.nn.Parameter(torch.zeros(4)), torch.nn.Parameter(torch.zeros(1))]
-        ps[0].grad, ps[1].grad = torch.full((2, 3), float(rank)), torch.full((4,), 10.0 * (rank + 1))  # ps[2] has no grad
+        ps[0].grad, ps[1].grad = torch.full((2, 3), float(rank)), torch.full((4,), 10.0 * (rank + 1))
+        if rank == 1:
+            ps[2].grad = torch.ones(1)  # only one rank touched this parameter: the other contributes zeros, same layout
         rdist.allreduce_grads(ps, world)
-        assert ps[0].grad.tolist() == [[0.5] * 3] * 2 and ps[1].grad.tolist() == [15.0] * 4 and ps[2].grad is None
+        assert ps[0].grad.tolist() == [[0.5] * 3] * 2 and ps[1].grad.tolist() == [15.0] * 4 and ps[2].grad.tolist() == [0.5]
+        # gradients that are consecutive views of one flat buffer are reduced in place, without flatten / copy-back
+        flatg = torch.arange(11, dtype=torch.float32) * (rank + 1)
+        qs = [torch.nn.Parameter(torch.zeros(2, 3)), torch.nn.Parameter(torch.zeros(5))]
+        qs[0].grad, qs[1].grad = flatg[0:6].view(2, 3), flatg[6:11].view(5)
+        assert rdist._common_flat([q.grad for q in qs]) is flatg
+        rdist.allreduce_grads(qs, world)
+        assert flatg.tolist() == [i * 1.5 for i in range(11)] and qs[1].grad.data_ptr() == flatg[6:].data_ptr()
         out.put((rank, lo, hi, flat.tolist(), params.tolist()))
     finally:
         dist.destroy_process_group()

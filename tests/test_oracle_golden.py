@@ -162,3 +162,28 @@ def test_space_to_depth_identity_of_stride2_convs():
                 (pz, tz), (py, ty), (px, tx) = pt[kz], pt[ky], pt[kx]
                 par = pz * 4 + px * 2 + py
                 torch.testing.assert_close(we_g.grad[:, par * 5:(par + 1) * 5, tz, ty, tx], w_g.grad[:, :, kz, ky, kx], rtol=1e-10, atol=1e-10)
+
+
+@pytest.mark.parametrize("cfg", ["hr3d_one_hm_doppler", "hr3d", "hr3d_one_hm_doppler_phase"])
+def test_reference_init_distribution_matches_reference_model(cfg):
+    """oracle.reference_init_state_dict draws from the distributions the reference's constructors use: compared, tensor by
+    tensor, with the state_dict of the reference's own model built under manual_seed(0) (names, order, shapes; constants
+    exactly; random tensors by standard deviation and range)."""
+    from oracle import make_golden as G
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("reference tree not available")
+    mods = ref_loader.load()
+    torch.manual_seed(0)
+    model = mods["build_detector"](G.ref_model_cfg(cfg), train_cfg=None, test_cfg=G.ref_test_cfg())
+    ref, mine = model.state_dict(), O.reference_init_state_dict(cfg)
+    assert list(ref) == list(mine)
+    for k in ref:
+        a, b = ref[k].float(), mine[k]
+        assert a.shape == b.shape, k
+        if a.numel() == 1 or float(a.std()) == 0.0:
+            assert torch.equal(a, b), k
+            continue
+        tol = 0.05 if a.numel() >= 8192 else (0.12 if a.numel() >= 512 else 0.6)
+        assert abs(float(a.std()) - float(b.std())) <= tol * float(a.std()), (k, float(a.std()), float(b.std()))
+        assert abs(float(a.abs().max()) - float(b.abs().max())) <= max(tol, 0.25) * float(a.abs().max()), k
