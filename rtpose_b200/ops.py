@@ -514,10 +514,11 @@ import os as _os
 _SKIP_WGRAD = bool(_os.environ.get("RTP_SKIP_WGRAD"))
 ASYNC_WGRAD = True  # weight gradients run on a side stream (nothing in backward depends on them); see join_wgrad()
 _side = {}
+LANE = 0  # engines that run concurrently on different streams (half-batch lanes) each get their own weight-gradient stream
 
 
 def _side_stream(device):
-    key = str(device)
+    key = "%s/%d" % (device, LANE)
     st = _side.get(key)
     if st is None:
         st = {"stream": torch.cuda.Stream(device=device), "busy": False, "events": []}
@@ -528,7 +529,7 @@ def _side_stream(device):
 def join_wgrad(device=None):
     """Makes the current stream wait for every weight gradient queued on the side stream(s)."""
     for key, st in _side.items():
-        if st["busy"] and (device is None or key == str(device)):
+        if st["busy"] and key.endswith("/%d" % LANE) and (device is None or key.split("/")[0] == str(device)):
             torch.cuda.current_stream(st["stream"].device).wait_stream(st["stream"])
             st["busy"] = False
 

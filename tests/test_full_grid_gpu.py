@@ -84,7 +84,8 @@ def test_engine_full_grid(cfg, batch, wkind):
     print("C-ABI calls:", {k: v for k, v in sorted(cc.items()) if v})
     # the plane-streaming kernels and their fused-statistics / span-mode variants are the ones that ran
     assert cc.get("rtp_conv_k3s1", 0) > 0 and cc.get("rtp_wgrad_k3s1", 0) > 0
-    assert cc.get("rtp_conv_k3s1_stat_finalize", 0) > 0, "GroupNorm reductions were not fused into the conv epilogues"
+    if not cfg.endswith("phase"):  # the feat64 backbone has 64 result channels per conv: its statistics use the reduction kernels
+        assert cc.get("rtp_conv_k3s1_stat_finalize", 0) > 0, "GroupNorm reductions were not fused into the conv epilogues"
     kps, ref_idx = O.decode(out["hm"], out["reg"])
     assert out["decode"][0].tolist() == ref_idx  # bit-exact at the decode boundary
     check_outputs(out["hm"], out["reg"], out["loss"][0].item(), out["grads"], out["decode"][0], ref, auto)
