@@ -252,6 +252,71 @@ def build_params(cfg, device):
     return params, grads, flat, gflat
 
 
+EW = {"gn_apply", "gn_backward", "fuse_sum", "upsample_bwd", "grad_add"}  # element-wise families: they record algorithmic BYTES
+TENSOR = {"conv_generic", "conv_k3s1", "conv_pw", "wgrad_generic", "wgrad_k3s1", "wgrad_s2d"}
+
+
+def ncu_traffic(kname, key, batch):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture) for this
+    kernel at this shape, from the newest profiles/r*_ncu_traffic.json that has it; None when never captured."""
+    import glob
+    want = "%s|%d|%d|%s|b%d" % (kname, key[1], key[2], "x".join(str(v) for v in key[6]), batch)
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_traffic.json")), reverse=True):
+        try:
+            d = json.load(open(path))
+        except Exception:
+            continue
+        e = d.get("by_shape", {}).get(want)
+        if e and e.get("traffic_MB"):
+            return e["traffic_MB"] * 1e6, os.path.relpath(path, ROOT) + " [" + want + "]"
+        if kname in d and key[1] == 32 and key[2] == 32 and tuple(key[6]) == (16, 160, 64) and batch == 16 and d[kname].get("traffic_MB"):
+            return d[kname]["traffic_MB"] * 1e6, os.path.relpath(path, ROOT)
+    return None, None
+
+
+def summarize_profile(prof, total_ms, nprof, batch, timing_note):
+    """roofline object + top-kernel list from the per-launch CUDA-event pairs ops.PROFILE collected.  The dominant kernel
+    is the tensor-kernel FUNCTION with the largest summed time; the figures quoted are those of its most time-consuming
+    shape.  `peak` is the measured BURST bf16 peak (the denominator BASELINE.md's >= 60 % target is stated against); the
+    fraction of the sustained peak is given beside it."""
+    pk_burst, pk_sust, hbm_peak, src = peaks()
+    fam, ew = {}, {}
+    for key, evs in prof.items():
+        if key == "_only":
+            continue
+        tms = [s.elapsed_time(e) for s, e, _ in evs]
+        if key[0] in EW:  # HBM-bound kernels: per function, algorithmic bytes / time vs the measured copy bandwidth
+            a = ew.setdefault(key[0], [0.0, 0, 0.0])
+            a[0] += sum(tms); a[1] += len(tms); a[2] += sum(f for _, _, f in evs)
+            continue
+        fam[key] = (sum(tms), len(tms), sum(f for _, _, f in evs))
+    hbm_kernels = {k: {"GBps": round(v[2] / (v[0] * 1e-3) / 1e9, 1), "frac_of_hbm_peak": round(v[2] / (v[0] * 1e-3) / 1e9 / hbm_peak, 3),
+                       "launches_per_step": v[1] // nprof, "ms_per_step": round(v[0] / nprof, 3), "share_of_step": round(v[0] / total_ms, 3)}
+                   for k, v in ew.items()}
+    roof, top = None, []
+    if fam:
+        for key, (tt, n, fl) in sorted(fam.items(), key=lambda kv: -kv[1][0])[:16]:
+            top.append({"kernel": key[0], "cin": key[1], "cout": key[2], "taps": key[3], "is_os": [key[4], key[5]], "rows": list(key[6]),
+                        "launches": n, "ms_total": round(tt, 3), "tflops": round(fl / (tt * 1e-3) / 1e12, 1)})
+        by_kernel = {}
+        for key, (tt, n, fl) in fam.items():
+            a = by_kernel.setdefault(key[0], [0.0, 0, 0.0])
+            a[0] += tt; a[1] += n; a[2] += fl
+        kname = max(by_kernel, key=lambda k: by_kernel[k][0])
+        key, (tt, n, fl) = max(((k, v) for k, v in fam.items() if k[0] == kname), key=lambda kv: kv[1][0])
+        ach = fl / (tt * 1e-3) / 1e12
+        traffic, tsrc = ncu_traffic(kname, key, batch)
+        roof = {"bound": "tensor", "kernel": "%s Cin=%d Cout=%d taps=%d" % key[:4], "achieved": ach, "peak": pk_burst,
+                "unit": "TFLOP/s", "frac": ach / pk_burst, "frac_of_sustained_peak": ach / pk_sust, "peak_sustained": pk_sust,
+                "peak_source": src + " (MEASURED_PEAKS.json bf16_tflops = burst; bf16_tflops_sustained beside it)",
+                "algorithmic_flops_per_launch": fl / n, "avg_launch_ms": tt / n, "share_of_step": by_kernel[kname][0] / total_ms,
+                "traffic": traffic, "traffic_source": tsrc, "timing": timing_note,
+                "hbm_bound_kernels": hbm_kernels, "hbm_peak_GBps": hbm_peak,
+                "all_tensor_kernels": {k: {"tflops": round(v[2] / (v[0] * 1e-3) / 1e12, 1), "frac_of_burst": round(v[2] / (v[0] * 1e-3) / 1e12 / pk_burst, 3),
+                                           "ms_per_step": round(v[0] / nprof, 3), "share_of_step": round(v[0] / total_ms, 3)} for k, v in by_kernel.items()}}
+    return roof, top
+
+
 def run_ours(args, rank, world, local_rank):
     from rtpose_b200 import lib, ops, targets
     from rtpose_b200 import dist as rdist
@@ -357,8 +422,7 @@ def run_ours(args, rank, world, local_rank):
     graph, async_was, par_was = None, ops.ASYNC_WGRAD, eng.parallel_branches
     ops.ASYNC_WGRAD, eng.parallel_branches = False, False
     step()
-    EW = {"gn_apply", "gn_backward", "fuse_sum", "upsample_bwd", "grad_add"}  # these record algorithmic bytes
-    ops.PROFILE = {"_only": {"conv_generic", "conv_k3s1", "conv_pw", "wgrad_generic", "wgrad_k3s1"} | EW}
+    ops.PROFILE = {"_only": TENSOR | EW}
     p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     nprof = min(args.steps, 5)
     p0.record()
@@ -376,49 +440,11 @@ def run_ours(args, rank, world, local_rank):
         ms = float(t[0])
     value = world * B / (ms * 1e-3)
 
-    # ---- roofline of the dominant kernel family (most total time among the profiled conv kernels)
+    roof, top = summarize_profile(prof, ms_serial * nprof, nprof, B,
+                                  "CUDA events around each launch in %d eager, single-stream steps of the same workload run right "
+                                  "after the timed region (%.2f ms/step; the timed region itself replays a CUDA graph with weight "
+                                  "gradients on a side stream, %.2f ms/step)" % (nprof, ms_serial, ms))
     pk_burst, pk_sust, hbm_peak, src = peaks()
-    fam, ew = {}, {}
-    for key, evs in prof.items():
-        if key == "_only":
-            continue
-        tms = [s.elapsed_time(e) for s, e, _ in evs]
-        if key[0] in EW:  # HBM-bound kernels: per function, algorithmic bytes / time vs the measured copy bandwidth
-            a = ew.setdefault(key[0], [0.0, 0, 0.0])
-            a[0] += sum(tms); a[1] += len(tms); a[2] += sum(f for _, _, f in evs)
-            continue
-        fam[key] = (sum(tms), len(tms), sum(f for _, _, f in evs))
-    hbm_kernels = {k: {"GBps": round(v[2] / (v[0] * 1e-3) / 1e9, 1), "frac_of_hbm_peak": round(v[2] / (v[0] * 1e-3) / 1e9 / hbm_peak, 3),
-                       "launches_per_step": v[1] // nprof, "share_of_step": round(v[0] / (ms_serial * nprof), 3)} for k, v in ew.items()}
-    roof, top = None, []
-    if fam:
-        for key, (tt, n, fl) in sorted(fam.items(), key=lambda kv: -kv[1][0])[:16]:
-            top.append({"kernel": key[0], "cin": key[1], "cout": key[2], "taps": key[3], "is_os": [key[4], key[5]], "rows": list(key[6]), "launches": n,
-                        "ms_total": round(tt, 3), "tflops": round(fl / (tt * 1e-3) / 1e12, 1)})
-        # dominant kernel = the kernel FUNCTION with the largest summed time (all its shapes); the per-launch figures
-        # quoted are those of its most time-consuming shape
-        by_kernel = {}
-        for key, (tt, n, fl) in fam.items():
-            a = by_kernel.setdefault(key[0], [0.0, 0, 0.0])
-            a[0] += tt; a[1] += n; a[2] += fl
-        kname = max(by_kernel, key=lambda k: by_kernel[k][0])
-        key, (tt, n, fl) = max(((k, v) for k, v in fam.items() if k[0] == kname), key=lambda kv: kv[1][0])
-        ach = fl / (tt * 1e-3) / 1e12
-        traffic = None
-        tj = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
-        if os.path.exists(tj) and key[1] == 32 and key[2] == 32 and tuple(key[6]) == (16, 160, 64) and B == 16:
-            traffic = json.load(open(tj)).get(kname, {}).get("traffic_MB")
-            traffic = traffic * 1e6 if traffic else None
-        roof = {"bound": "tensor", "kernel": "%s Cin=%d Cout=%d taps=%d" % key[:4], "achieved": ach, "peak": pk_sust,
-                "unit": "TFLOP/s", "frac": ach / pk_sust, "frac_of_burst_peak": ach / pk_burst, "peak_source": src + " (sustained)",
-                "avg_launch_ms": tt / n, "share_of_step": by_kernel[kname][0] / (ms_serial * nprof), "traffic": traffic,
-                "timing": "CUDA events around each launch in %d eager, single-stream steps of the same workload run right after the "
-                          "timed region (%.2f ms/step; the timed region itself replays a CUDA graph with weight gradients on a "
-                          "side stream, %.2f ms/step)" % (nprof, ms_serial, ms),
-                "traffic_source": "profiles/r01_ncu_traffic.json (ncu --set full, bytes per launch)" if traffic else None,
-                "hbm_bound_kernels": hbm_kernels, "hbm_peak_GBps": hbm_peak,
-                "other_tensor_kernels": {k: {"tflops": round(v[2] / (v[0] * 1e-3) / 1e12, 1), "frac": round(v[2] / (v[0] * 1e-3) / 1e12 / pk_sust, 3),
-                                             "share_of_step": round(v[0] / (ms_serial * nprof), 3)} for k, v in by_kernel.items() if k != kname}}
 
     line = {"metric": "radar frames/sec HRRadarPose fwd+bwd", "value": value, "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
@@ -429,7 +455,8 @@ def run_ours(args, rank, world, local_rank):
                        "targets": "assigned on the device from resident fp64 skeletons every step (rtp_assign_targets)",
                        "optimizer": ("fused clip(35) + decoupled wd + Adam, one-cycle lr (rtp_adam_step) inside the timed region"
                                      if opt is not None else "none (--no-optimizer)")}),
-            "model_tflops": 3 * gf_fwd * 1e9 * value / 1e12, "model_flops_frac_of_peak": 3 * gf_fwd * 1e9 * value / 1e12 / world / pk_sust,
+            "model_tflops": 3 * gf_fwd * 1e9 * value / 1e12, "model_flops_frac_of_peak": 3 * gf_fwd * 1e9 * value / 1e12 / world / pk_burst,
+            "model_flops_frac_of_sustained_peak": 3 * gf_fwd * 1e9 * value / 1e12 / world / pk_sust,
             "loss": float(out[0]), "gpu_launches": launches, "host_issue_ms_per_step": round(host_issue_ms, 2), "clocks": sampler.summary(), "roofline": roof, "top_kernels": top}
 
     if not args.no_extras:
@@ -611,10 +638,11 @@ def loader_bench(args, dev):
 
 
 def inference_bench(args, eng, dev):
-    """BASELINE.json configs[1]: inference batch 32 incl. keypoint decode (reported beside the headline)."""
-    from rtpose_b200 import lib
+    """BASELINE.json configs[1]: inference, batch 32, bf16, incl. heat-map arg-max keypoint decode — a second leg of the
+    same line with its own roofline (per-launch CUDA events of an eager single-stream pass, like the training leg)."""
+    from rtpose_b200 import lib, ops
     from rtpose_b200.p8 import P8, _stream
-    arch, fin, fout, fuse, reg, ncls, weight, in_ch, norm, _ = CFGS[args.cfg]
+    arch, fin, fout, fuse, reg, ncls, weight, in_ch, norm, gf_fwd = CFGS[args.cfg]
     B = 32
     g = torch.Generator(device=dev).manual_seed(5)
     a, b = norm if norm is not None else (0.0, 1.0)
@@ -631,6 +659,9 @@ def inference_bench(args, eng, dev):
         step()
     torch.cuda.synchronize()
     run, graphed = step, False
+    lib.launch_count = 0
+    step()
+    launches = lib.launch_count
     if not args.no_graph:  # the inference step is static too: replay it as one graph (weights packed once, outside)
         from rtpose_b200.graph import StepGraph
         try:
@@ -641,15 +672,38 @@ def inference_bench(args, eng, dev):
             run = step
             print("bench: inference graph capture failed (%r); running eagerly" % (ex,), file=sys.stderr)
     torch.cuda.synchronize()
+    n = 10
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(10):
+    for _ in range(n):
         idx, score, xyz = run()
     e1.record()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / 10
-    return {"value": B / (ms * 1e-3), "unit": "frames/s", "batch": B, "ms_per_step": ms, "cuda_graph": graphed,
-            "includes": "ingest + forward + arg-max decode"}
+    ms = e0.elapsed_time(e1) / n
+    # per-kernel pass: eager, one stream
+    par_was = eng.parallel_branches
+    eng.parallel_branches = False
+    step()
+    ops.PROFILE = {"_only": TENSOR | EW}
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    for _ in range(3):
+        step()
+    p1.record()
+    torch.cuda.synchronize()
+    prof, ops.PROFILE = ops.PROFILE, None
+    eng.parallel_branches = par_was
+    ms_serial = p0.elapsed_time(p1) / 3
+    roof, top = summarize_profile(prof, ms_serial * 3, 3, B, "CUDA events around each launch in 3 eager single-stream inference steps "
+                                  "(%.2f ms/step; the timed region replays a CUDA graph, %.2f ms/step)" % (ms_serial, ms))
+    pk_burst, pk_sust, _, _ = peaks()
+    val = B / (ms * 1e-3)
+    return {"metric": "radar frames/sec HRRadarPose inference incl. decode", "value": val, "unit": "frames/s", "batch": B,
+            "ms_per_step": ms, "steps": n, "cuda_graph": graphed, "dtype": "bf16",
+            "config": {"workload": "%s inference, batch %d, raw fp16 cube -> ingest -> HRNet3D -> CenterHead -> arg-max keypoint decode "
+                                   "(BASELINE.json configs[1])" % (args.cfg, B)},
+            "model_tflops": gf_fwd * 1e9 * val / 1e12, "model_flops_frac_of_peak": gf_fwd * 1e9 * val / 1e12 / pk_burst,
+            "gpu_launches_per_step": launches, "roofline": roof, "top_kernels": top[:8]}
 
 
 def main():

@@ -233,11 +233,13 @@ int rtp_gn_apply(rtp_p8 x, int32_t C, int32_t G, const float* stats, const float
 /* backward, two steps.  red[N][C][2] = per-channel (sum dy, sum dy*xhat) */
 int rtp_gn_bwd_reduce(rtp_p8 x, rtp_p8 dy, int32_t C, int32_t G, const float* stats, float* red, float* workspace,
                       void* stream);
-/* dgamma/dbeta (+)= sum_n red; dx (=|+=) rstd*(gamma*dy - (s1 + xhat*s2)/m), optionally times (x > 0) when x is
- * itself a ReLU output (the gradient of every tensor is kept w.r.t. its pre-ReLU value). */
+/* dgamma/dbeta (+)= sum_n red; dx (=|+=) [x > 0]? (rstd*(gamma*dy - (s1 + xhat*s2)/m) + add): the (x > 0) factor when x
+ * is itself a ReLU output (the gradient of every tensor is kept w.r.t. its pre-ReLU value); `add` (ptr NULL = none, x's
+ * geometry) is a second gradient into the same tensor — the residual / fuse-sum pass-through of autograd's
+ * AddBackward (hr_util/common.py:146, hr3d.py:213-227) — folded into this pass. */
 int rtp_gn_bwd_apply(rtp_p8 x, rtp_p8 dy, int32_t C, int32_t G, const float* stats, const float* red,
                      const float* gamma, float* dgamma, float* dbeta, int32_t accumulate_params, rtp_p8 dx,
-                     int32_t accumulate_dx, int32_t relu_mask, void* stream);
+                     int32_t accumulate_dx, int32_t relu_mask, rtp_p8 add, void* stream);
 /* Space-to-depth ("s2d") variants for the stride-2 exchange convs (fuse_layers / transition, hr_util/hr3d.py:159-203,
  * :262-292).  The s2d view of a tensor with grid (Z, X, Y) (all even) and C8 chunks is a P8 tensor with grid
  * (Z/2, X/2, Y/2) and 8*C8 chunks: voxel (z, x, y), chunk c lives at voxel (z/2, x/2, y/2), chunk
@@ -250,7 +252,7 @@ int rtp_gn_bwd_reduce_s2d(rtp_p8 x, rtp_p8 dy_s2d, int32_t C, int32_t G, const f
                           void* stream);
 int rtp_gn_bwd_apply_s2d(rtp_p8 x, rtp_p8 dy_s2d, int32_t C, int32_t G, const float* stats, const float* red,
                          const float* gamma, float* dgamma, float* dbeta, int32_t accumulate_params, rtp_p8 dx,
-                         int32_t accumulate_dx, int32_t relu_mask, void* stream);
+                         int32_t accumulate_dx, int32_t relu_mask, rtp_p8 add, void* stream);
 /* w [Cout][Cin][3][3][3] fp32 -> w_s2d [Cout][8*Cin][3][3][3] fp32 (zero except the 27 matching (parity, offset) pairs),
  * and the transpose for the weight gradient: dw (=|+=) fold(dw_s2d). */
 int rtp_weight_s2d_expand(const float* w, float* w_s2d, int32_t Cout, int32_t Cin, void* stream);

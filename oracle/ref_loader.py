@@ -36,6 +36,8 @@ def load():
     if not available():
         raise RuntimeError("reference tree not found at %s" % REF_ROOT)
     R = REF_ROOT
+    for name in [n for n in sys.modules if n == "det3d" or n.startswith("det3d.")]:
+        del sys.modules[name]  # e.g. aliases left by rtpose_b200.det3d_compat.install_as_det3d() earlier in this process
 
     def ns(name, path=None):
         m = types.ModuleType(name)

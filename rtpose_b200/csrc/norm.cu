@@ -109,6 +109,9 @@ struct Vec4 {
 struct Vec6 {
   uint4 a, b, c, d, e, f;
 };
+struct Vec8 {
+  uint4 a, b, c, d, e, f, g, h;
+};
 __host__ __device__ inline int log2_ty(int Y) {
   int l = 3;
   while ((1 << l) < Y && l < 6) ++l;
@@ -339,12 +342,14 @@ __global__ void gn_param_grad_kernel(const float* __restrict__ red, int N, int C
   dgamma[c] = accumulate ? dgamma[c] + (float)b : (float)b;
 }
 
-// dx (=|+=) [x>0] * rstd * (gamma*dy - (s1 + xhat*s2)/m)
-template <bool S2D>
+// dx (=|+=) [x>0] * (rstd * (gamma*dy - (s1 + xhat*s2)/m) + add)
+// `add` (optional, x's geometry): a second gradient flowing into the same tensor — the residual / fuse-sum pass-through —
+// folded into this pass instead of costing a grad_add pass (3 tensor passes) of its own.
+template <bool S2D, bool ADD>
 __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(P8 x, P8 dy, int C, int G, const float* __restrict__ stats,
                                                            const float* __restrict__ red, const float* __restrict__ gamma,
                                                            P8 dx, int accumulate, int relu_mask, float* __restrict__ dgamma,
-                                                           float* __restrict__ dbeta, int accumulate_params) {
+                                                           float* __restrict__ dbeta, int accumulate_params, P8 add) {
   __shared__ float s_k[5 * 8];
   const int c8 = blockIdx.y, n = blockIdx.z;
   const int cpg = C / G;
@@ -389,15 +394,18 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(P8 x, P8 dy, int C, i
   const bf16* xb = x.ptr + n * x.n_stride + c8 * x.c_stride;
   const bf16* db = dy.ptr + n * dy.n_stride + (S2D ? 0 : c8 * dy.c_stride);
   bf16* ob = dx.ptr + n * dx.n_stride + c8 * dx.c_stride;
+  const bf16* ab = ADD ? add.ptr + n * add.n_stride + c8 * add.c_stride : nullptr;
   const int C8 = (int)gridDim.y;
-  auto emit = [&](int64_t off, const uint4& xv, const uint4& dv, const uint4& old) {
-    float f[8], d[8], o[8];
+  auto emit = [&](int64_t off, const uint4& xv, const uint4& dv, const uint4& old, const uint4& av) {
+    float f[8], d[8], o[8], a[8];
     unpack8(xv, f);
     unpack8(dv, d);
+    if constexpr (ADD) unpack8(av, a);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const float xh = (f[i] - mean[i]) * rstd[i];
       o[i] = rstd[i] * (ga[i] * d[i] - k1[i] - xh * k2[i]);
+      if constexpr (ADD) o[i] += a[i];
       if (relu_mask && !(f[i] > 0.f)) o[i] = 0.f;
     }
     if (accumulate) {
@@ -414,7 +422,7 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(P8 x, P8 dy, int C, i
     rows_foreach_u<2, true>(
         x, r0, r1, log2_ty(x.Y / 2),
         [&](int64_t off, int z, int xx, int yy) {
-          Vec6 v;
+          Vec8 v;
           v.a = ldg16(xb + off);
           v.b = ldg16(xb + off + 8);
           const int64_t so = s2d_offset(dy, C8, c8, z, xx, yy);
@@ -422,23 +430,28 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(P8 x, P8 dy, int C, i
           v.d = ldg16(db + so + pstride);
           v.e = accumulate ? *reinterpret_cast<const uint4*>(ob + off) : zero4;
           v.f = accumulate ? *reinterpret_cast<const uint4*>(ob + off + 8) : zero4;
+          if constexpr (ADD) {
+            v.g = ldg16(ab + off);
+            v.h = ldg16(ab + off + 8);
+          }
           return v;
         },
-        [&](int64_t off, const Vec6& v) {
-          emit(off, v.a, v.c, v.e);
-          emit(off + 8, v.b, v.d, v.f);
+        [&](int64_t off, const Vec8& v) {
+          emit(off, v.a, v.c, v.e, v.g);
+          emit(off + 8, v.b, v.d, v.f, v.h);
         });
   } else {
     rows_foreach_u<4>(
         x, r0, r1, log2_ty(x.Y),
         [&](int64_t off, int, int, int) {
-          Vec3 v;
+          Vec4 v;
           v.a = ldg16(xb + off);
           v.b = ldg16(db + off);
           v.c = accumulate ? *reinterpret_cast<const uint4*>(ob + off) : zero4;
+          if constexpr (ADD) v.d = ldg16(ab + off);
           return v;
         },
-        [&](int64_t off, const Vec3& v) { emit(off, v.a, v.b, v.c); });
+        [&](int64_t off, const Vec4& v) { emit(off, v.a, v.b, v.c, v.d); });
   }
 }
 
@@ -557,7 +570,7 @@ int gn_bwd_reduce_impl(rtp_p8 x, rtp_p8 dy, int32_t C, int32_t G, const float* s
 
 int gn_bwd_apply_impl(rtp_p8 x, rtp_p8 dy, int32_t C, int32_t G, const float* stats, const float* red, const float* gamma,
                       float* dgamma, float* dbeta, int32_t accumulate_params, rtp_p8 dx, int32_t accumulate_dx, int32_t relu_mask,
-                      bool s2d, void* stream) {
+                      rtp_p8 add, bool s2d, void* stream) {
   RTP_CHECK_ARG(x.ptr && dy.ptr && stats && red && gamma, "rtp_gn_bwd_apply: null argument");
   RTP_CHECK_ARG(C > 0 && C % G == 0 && C <= x.C8 * 8, "rtp_gn_bwd_apply: bad C/G");
   if (s2d)
@@ -569,15 +582,17 @@ int gn_bwd_apply_impl(rtp_p8 x, rtp_p8 dy, int32_t C, int32_t G, const float* st
   if (dx.ptr) {
     float* dg = (dgamma && dbeta) ? dgamma : nullptr;
     RTP_CHECK_ARG(x.N == dx.N && x.Z == dx.Z && x.X == dx.X && x.Y == dx.Y && C <= dx.C8 * 8, "rtp_gn_bwd_apply: dx geometry mismatch");
-    P8 tx(x), td(dy), to(dx);
+    if (add.ptr)
+      RTP_CHECK_ARG(x.N == add.N && x.Z == add.Z && x.X == add.X && x.Y == add.Y && C <= add.C8 * 8, "rtp_gn_bwd_apply: add geometry mismatch");
+    P8 tx(x), td(dy), to(dx), ta(add);
     const int64_t V = (int64_t)x.Z * x.X * x.Y;
     const dim3 grid(ew_blocks(V), ceil_div(C, 8), x.N);
-    if (s2d)
-      gn_bwd_apply_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(tx, td, C, G, stats, red, gamma, to, accumulate_dx, relu_mask, dg, dbeta,
-                                                                         accumulate_params);
-    else
-      gn_bwd_apply_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(tx, td, C, G, stats, red, gamma, to, accumulate_dx, relu_mask, dg, dbeta,
-                                                                          accumulate_params);
+    auto kern = s2d ? (add.ptr ? gn_bwd_apply_kernel<true, true> : gn_bwd_apply_kernel<true, false>)
+                    : (add.ptr ? gn_bwd_apply_kernel<false, true> : gn_bwd_apply_kernel<false, false>);
+    kern<<<grid, 256, 0, (cudaStream_t)stream>>>(tx, td, C, G, stats, red, gamma, to, accumulate_dx, relu_mask, dg, dbeta,
+                                                 accumulate_params, ta);
+  } else {
+    RTP_CHECK_ARG(!add.ptr, "rtp_gn_bwd_apply: add given without dx");
   }
   RTP_LAUNCH_CHECK();
 }
@@ -601,15 +616,15 @@ extern "C" int rtp_gn_bwd_reduce_s2d(rtp_p8 x, rtp_p8 dy_s2d, int32_t C, int32_t
 }
 extern "C" int rtp_gn_bwd_apply(rtp_p8 x, rtp_p8 dy, int32_t C, int32_t G, const float* stats, const float* red,
                                 const float* gamma, float* dgamma, float* dbeta, int32_t accumulate_params, rtp_p8 dx,
-                                int32_t accumulate_dx, int32_t relu_mask, void* stream) {
-  return gn_bwd_apply_impl(x, dy, C, G, stats, red, gamma, dgamma, dbeta, accumulate_params, dx, accumulate_dx, relu_mask, false,
-                           stream);
+                                int32_t accumulate_dx, int32_t relu_mask, rtp_p8 add, void* stream) {
+  return gn_bwd_apply_impl(x, dy, C, G, stats, red, gamma, dgamma, dbeta, accumulate_params, dx, accumulate_dx, relu_mask, add,
+                           false, stream);
 }
 extern "C" int rtp_gn_bwd_apply_s2d(rtp_p8 x, rtp_p8 dy_s2d, int32_t C, int32_t G, const float* stats, const float* red,
                                     const float* gamma, float* dgamma, float* dbeta, int32_t accumulate_params, rtp_p8 dx,
-                                    int32_t accumulate_dx, int32_t relu_mask, void* stream) {
-  return gn_bwd_apply_impl(x, dy_s2d, C, G, stats, red, gamma, dgamma, dbeta, accumulate_params, dx, accumulate_dx, relu_mask, true,
-                           stream);
+                                    int32_t accumulate_dx, int32_t relu_mask, rtp_p8 add, void* stream) {
+  return gn_bwd_apply_impl(x, dy_s2d, C, G, stats, red, gamma, dgamma, dbeta, accumulate_params, dx, accumulate_dx, relu_mask, add,
+                           true, stream);
 }
 
 // ================================================================================================ stem / bias grads

@@ -9,6 +9,7 @@ Gradient convention: for a tensor that is the output of a ReLU, `.grad` holds th
 value; every kernel that writes into such a gradient applies the (t > 0) mask itself.
 """
 import contextlib
+import os
 
 import torch
 
@@ -48,6 +49,7 @@ class Engine:
         self.parallel_fuse_bwd = False  # measured: no gain (the ordered accumulation into shared gradients serialises it)
         self._ordered_grads = False  # set while backward closures may run on several streams
         self._bstreams = {}
+        self.fold_grad_adds = not os.environ.get("RTP_NO_FOLD_ADDS")  # residual / fuse-sum gradient pass-throughs ride in the next GroupNorm backward (_defer_add)
         self.generation = 0  # bumped by begin(): a backward job checks that the tape it recorded is still the live one
 
     # ------------------------------------------------------------------ helpers
@@ -70,6 +72,36 @@ class Engine:
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream(t.buf.device))
             t.grad_ev = ev
+
+    def _defer_add(self, t, src):
+        """t.grad += src (times (t > 0) when t is a ReLU output) — the pass-through of a residual / fuse sum — WITHOUT a pass
+        of its own: the next GroupNorm backward that writes t.grad takes `src` as its `add` input (rtp_gn_bwd_apply).  If
+        t.grad is read before such a writer comes, _g() performs the add with rtp_grad_add."""
+        if not self.fold_grad_adds:
+            gt, acc = self._grad_of(t)
+            ops.grad_add(src, gt, mask=t if t.relu_out else None, accumulate=acc)
+            self._wrote(t)
+            return
+        self._flush_pending(t)
+        t.pending = src
+
+    def _flush_pending(self, t):
+        if t.pending is not None:
+            src, t.pending = t.pending, None
+            gt, acc = self._grad_of(t)
+            ops.grad_add(src, gt, mask=t if t.relu_out else None, accumulate=acc)
+            self._wrote(t)
+
+    def _g(self, t):
+        """t.grad for a READER (every deferred add applied first)."""
+        self._flush_pending(t)
+        if t.grad_ev is not None:  # written on another stream (stream-parallel fuse backward)
+            torch.cuda.current_stream(t.buf.device).wait_event(t.grad_ev)
+        return t.grad
+
+    def _take_pending(self, t):
+        src, t.pending = t.pending, None
+        return src
 
     def _pgrad(self, name):
         """fp32 gradient tensor of parameter `name` and whether to accumulate into it."""
@@ -104,13 +136,11 @@ class Engine:
         y.relu_out = bool(relu)
         if train:
             def bwd():
-                dy = y.grad
+                dy = self._g(y)
                 if dy is None:
                     return
                 if res is not None and res_needs_grad:
-                    g, acc = self._grad_of(res)
-                    ops.grad_add(dy, g, mask=res if res.relu_out else None, accumulate=acc)
-                    self._wrote(res)
+                    self._defer_add(res, dy)
                 gw, accw = self._pgrad(conv + ".weight")
                 ops.conv_wgrad_async(xn, dy, k, stride, gw, accumulate=accw)
                 red = None
@@ -124,7 +154,8 @@ class Engine:
                     gx, accx = self._grad_of(x)
                 else:
                     gx, accx = None, False
-                ops.gn_backward(x, dxn, G, stats, gamma, gg, gb, accg, gx, accx, red=red)
+                ops.gn_backward(x, dxn, G, stats, gamma, gg, gb, accg, gx, accx, red=red,
+                                add=self._take_pending(x) if gx is not None else None)
                 if gx is not None:
                     self._wrote(x)
             self.tape.append(bwd)
@@ -144,13 +175,11 @@ class Engine:
         y.relu_out = bool(relu)
         if train:
             def bwd():
-                dy = y.grad
+                dy = self._g(y)
                 if dy is None:
                     return
                 if res is not None and res_needs_grad:
-                    g, acc = self._grad_of(res)
-                    ops.grad_add(dy, g, mask=res if res.relu_out else None, accumulate=acc)
-                    self._wrote(res)
+                    self._defer_add(res, dy)
                 gw, accw = self._pgrad(conv + ".weight")
                 ops.on_wgrad_stream(xs, lambda: ops.conv_wgrad_s2d(xs, dy, x.C, gw, accumulate=accw))
                 dxs = ops.conv_dgrad(self.packs, dy, we, 1, self.pool.get(x.N, 8 * x.C, x.Z // 2, x.Y // 2, x.X // 2, dev),
@@ -161,7 +190,8 @@ class Engine:
                     gx, accx = self._grad_of(x)
                 else:
                     gx, accx = None, False
-                ops.gn_backward(x, dxs, G, stats, gamma, gg, gb, accg, gx, accx, s2d=True)
+                ops.gn_backward(x, dxs, G, stats, gamma, gg, gb, accg, gx, accx, s2d=True,
+                                add=self._take_pending(x) if gx is not None else None)
                 if gx is not None:
                     self._wrote(x)
             self.tape.append(bwd)
@@ -179,7 +209,7 @@ class Engine:
             lib.call("rtp_stem_fwd", x.struct(), wv.data_ptr(), b1.data_ptr(), w1.shape[0], r.struct(), _stream())
             if train:
                 def bwd():
-                    if r.grad is None:
+                    if self._g(r) is None:
                         return
                     gw, acc = self._pgrad(prefix + ".conv1.weight")
                     gb, _ = self._pgrad(prefix + ".conv1.bias")
@@ -220,6 +250,7 @@ class Engine:
                     for st in used.values():
                         cur.wait_stream(st)
                 self.tape.append(join_bwd)
+        self._fuse_closures = []
         for i in idx:
             st = used.get(i) if par else None
             t0 = len(self.tape)
@@ -231,6 +262,8 @@ class Engine:
                 for k in range(t0, len(self.tape)):
                     self.tape[k] = self._on_stream(self.tape[k], st)
             outs.append(y)
+        self.tape.extend(self._fuse_closures)
+        self._fuse_closures = []
         if par:
             for st in used.values():
                 main.wait_stream(st)
@@ -260,7 +293,10 @@ class Engine:
             y = ops.fuse_sum(self.new(xs[i]), same, low, relu=True)
             y.relu_out = True
             if train:
-                self.tape.append(self._fuse_bwd(y, same, low))
+                # the sum's own backward closures are appended by hr_module AFTER every output's conv closures, so in the
+                # backward pass they all run first: each pass-through gradient (y_i -> xs[i]) is then still pending when the
+                # first GroupNorm backward into xs[i] comes, and rides in it (_defer_add)
+                self._fuse_closures.append(self._fuse_bwd(y, same, low))
             return y
 
     def _branch_stream(self, b, device):
@@ -317,16 +353,14 @@ class Engine:
 
     def _fuse_bwd(self, y, same, low):
         def bwd():
-            g = y.grad
+            g = self._g(y)
             if g is None:
                 return
             for t in same:
-                if t.grad is None and not t.relu_out:
+                if t.grad is None and t.pending is None and not t.relu_out:
                     t.grad = g  # single consumer, no mask: alias instead of copying
                 else:
-                    gt, acc = self._grad_of(t)
-                    ops.grad_add(g, gt, mask=t if t.relu_out else None, accumulate=acc)
-                    self._wrote(t)
+                    self._defer_add(t, g)
             for t in low:
                 gt, acc = self._grad_of(t)
                 ops.upsample_bwd(g, gt, accumulate=acc)
@@ -360,7 +394,7 @@ class Engine:
         f = ops.fuse_sum(self.new(ys[0], C=w.shape[0]), [terms[0][1]], [t for _, t, _ in terms[1:]], bias=b)
         if train:
             def bwd():
-                g = f.grad
+                g = self._g(f)
                 if g is None:
                     return
                 gb, accb = self._pgrad(self.pb + "final_conv.bias")

@@ -94,11 +94,11 @@ PROTOTYPES = {
     "rtp_gn_apply": (C.c_int, [P8Struct, _i32, _i32, _vp, _vp, _vp, P8Struct, _vp]),
     "rtp_gn_bwd_reduce": (C.c_int, [P8Struct, P8Struct, _i32, _i32, _vp, _vp, _vp, _vp]),
     "rtp_gn_bwd_apply": (C.c_int, [P8Struct, P8Struct, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _i32, P8Struct, _i32,
-                                   _i32, _vp]),
+                                   _i32, P8Struct, _vp]),
     "rtp_gn_apply_s2d": (C.c_int, [P8Struct, _i32, _i32, _vp, _vp, _vp, P8Struct, _vp]),
     "rtp_gn_bwd_reduce_s2d": (C.c_int, [P8Struct, P8Struct, _i32, _i32, _vp, _vp, _vp, _vp]),
     "rtp_gn_bwd_apply_s2d": (C.c_int, [P8Struct, P8Struct, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _i32, P8Struct, _i32,
-                                       _i32, _vp]),
+                                       _i32, P8Struct, _vp]),
     "rtp_weight_s2d_expand": (C.c_int, [_vp, _vp, _i32, _i32, _vp]),
     "rtp_weight_s2d_fold": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp]),
     "rtp_fuse_sum": (C.c_int, [C.POINTER(FuseDesc), _vp]),

@@ -31,6 +31,7 @@ class BufferPool:
             t.relu_out = False
             t.grad = None
             t.grad_ev = None
+            t.pending = None
         else:
             t = P8(N, Cc, Z, Y, X, device=device)
         t._keep = key
@@ -41,6 +42,7 @@ class BufferPool:
         for t in self.live:
             t.grad = None
             t.grad_ev = None
+            t.pending = None
             self.free.setdefault(t._keep, []).append(t)
         self.live = []
 
@@ -717,9 +719,10 @@ def s2d_fold(dw_s2d, dw, accumulate):
     lib.call("rtp_weight_s2d_fold", dw_s2d.data_ptr(), dw.data_ptr(), dw.shape[0], dw.shape[1], int(accumulate), _stream())
 
 
-def gn_backward(x, dxn, G, stats, gamma, dgamma, dbeta, acc_params, dx, acc_dx, red=None, s2d=False):
+def gn_backward(x, dxn, G, stats, gamma, dgamma, dbeta, acc_params, dx, acc_dx, red=None, s2d=False, add=None):
     """red: the [N][C][2] reductions when the conv that produced dxn already computed them (conv_dgrad(stat=...)).
-    s2d: dxn is the gradient of the space-to-depth view of GN(x)."""
+    s2d: dxn is the gradient of the space-to-depth view of GN(x).
+    add: a second gradient into x (same geometry; masked with (x > 0) like the GroupNorm term when x is a ReLU output)."""
     sfx = "_s2d" if s2d else ""
     key = ("gn_backward", x.C, x.C, 0 if red is None else 1, 1, 1, (x.Z, x.X, x.Y))
     ev = _prof_begin(key)
@@ -729,9 +732,9 @@ def gn_backward(x, dxn, G, stats, gamma, dgamma, dbeta, acc_params, dx, acc_dx, 
                  gn_ws(x).data_ptr(), _stream())
     lib.call("rtp_gn_bwd_apply" + sfx, x.struct(), dxn.struct(), x.C, G, stats.data_ptr(), red.data_ptr(), gamma.data_ptr(),
              dgamma.data_ptr(), dbeta.data_ptr(), int(acc_params), dx.struct() if dx is not None else lib.NULL_P8,
-             int(acc_dx), int(x.relu_out), _stream())
-    # bytes: (reduction pass: x + dxn) + (apply pass: x + dxn read, dx written [+ read when accumulating])
-    nb = (0 if key[3] else 2) + (0 if dx is None else 3 + (1 if acc_dx else 0))
+             int(acc_dx), int(x.relu_out), add.struct() if add is not None else lib.NULL_P8, _stream())
+    # bytes: (reduction pass: x + dxn) + (apply pass: x + dxn read, dx written [+ read when accumulating] [+ add read])
+    nb = (0 if key[3] else 2) + (0 if dx is None else 3 + (1 if acc_dx else 0) + (1 if add is not None else 0))
     _prof_end(key, ev, nb * _tbytes(x))
 
 

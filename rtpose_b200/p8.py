@@ -11,7 +11,7 @@ GUARD_ELEMS = lib.GUARD_BYTES // 2
 
 
 class P8:
-    __slots__ = ("buf", "offset", "N", "C", "C8", "Z", "Y", "X", "n_stride", "c_stride", "relu_out", "grad", "grad_ev", "_keep")
+    __slots__ = ("buf", "offset", "N", "C", "C8", "Z", "Y", "X", "n_stride", "c_stride", "relu_out", "grad", "grad_ev", "pending", "_keep")
 
     def __init__(self, N, C, Z, Y, X, device="cuda", buf=None, offset=None, n_stride=None, c_stride=None):
         self.N, self.C, self.Z, self.Y, self.X = int(N), int(C), int(Z), int(Y), int(X)
@@ -28,6 +28,7 @@ class P8:
         self.relu_out = False  # True when the tensor is the output of a ReLU (gradients are kept pre-ReLU)
         self.grad = None
         self.grad_ev = None  # event of the last kernel that wrote .grad (ordered accumulation across streams)
+        self.pending = None  # a gradient still to be added into .grad (engine._defer_add): folded into the next GroupNorm backward
         self._keep = None
 
     # ------------------------------------------------------------------ views

@@ -185,6 +185,15 @@ def test_groupnorm_fwd_bwd(C, grid):
     torch.cuda.synchronize()
     close(dx2.to_ncdhw(), base + x.grad * (x.detach() > 0), tol=2 * BF16_ULP, what="gn dx mask+acc")
     close(dg, 2 * gamma.grad, tol=1e-3, what="gn dgamma acc")
+    # a second gradient into x folded into the same pass (`add`): dx = [x > 0] * (gn term + add) (+ old)
+    extra = rnd(N, C, *grid, seed=16)
+    dx3, dx4 = P8(N, C, *grid), to_p8(base)
+    ops.gn_backward(xp, to_p8(dy), G, stats, gamma.detach().cuda(), dg, db, False, dx3, False, add=to_p8(extra))
+    ops.gn_backward(xp, to_p8(dy), G, stats, gamma.detach().cuda(), dg, db, False, dx4, True, add=to_p8(extra))
+    torch.cuda.synchronize()
+    want = (x.grad + bf(extra)) * (x.detach() > 0)
+    close(dx3.to_ncdhw(), want, tol=2 * BF16_ULP, what="gn dx + add, masked")
+    close(dx4.to_ncdhw(), base + want, tol=3 * BF16_ULP, what="gn dx + add, masked, accumulated")
 
 
 def test_fuse_sum_and_upsample_bwd():
@@ -565,6 +574,11 @@ def test_stride2_conv_through_space_to_depth_view(ctx, case):
     close(dx.to_ncdhw(), x.grad, tol=2e-2, what="s2d dx")
     close(dg, gamma.grad, tol=2e-2, what="s2d dgamma")
     close(db, beta.grad, tol=2e-2, what="s2d dbeta")
+    extra = rnd(N, Cin, *grid, seed=77)
+    dx5 = P8(N, Cin, *grid)
+    ops.gn_backward(xp, dxs, 8, stats, gc, dg, db, False, dx5, False, s2d=True, add=to_p8(extra))
+    torch.cuda.synchronize()
+    close(dx5.to_ncdhw(), dx.to_ncdhw() + bf(extra), tol=2 * BF16_ULP, what="s2d dx + add")
 
 
 def test_fused_launch_variants_match_their_multi_launch_forms(ctx):
