@@ -18,6 +18,8 @@
 //    accumulators stay in TMEM across passes.
 //
 // Roofline: tensor pipe.  Algorithmic FLOPs per launch = 2 * N*Z*Y*X * Cout * Cin * 27.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "tc05.cuh"
 
@@ -25,7 +27,8 @@ using namespace tc05;
 
 namespace {
 
-constexpr int kThreads = 320;  // warp 0 producer, warp 1 MMA, warps 2-5 / 6-9 epilogue groups 0 / 1
+constexpr int kThreads = 320;   // LANES = 1: warp 0 producer, warp 1 MMA, warps 2-5 / 6-9 epilogue groups 0 / 1
+constexpr int kThreads2 = 384;  // LANES = 2: warps 0-1 producers, 2-3 MMA issuers, 4-7 / 8-11 the epilogue group of lane 0 / 1
 constexpr int kMaxBlocks = 32;
 constexpr int kMaxStages = 8;
 #ifdef RTP_K3S1_DEBUG
@@ -55,41 +58,60 @@ struct K3 {
   uint16_t tapmask[32];  // per K pass: bit t9 set = in-plane tap t9 has non-zero weights (structurally sparse weights)
 };
 
-template <int KS, int STAT>  // KS = KG / 16: k16 steps per tap (1 or 2); STAT: fused statistics mode (0 = off)
-__global__ void __launch_bounds__(kThreads, 1) conv_k3s1_kernel(const __grid_constant__ K3 p) {
+// LANES = 2 ("dual issue"): the issuing thread, not the tensor pipe, bounds the single-lane kernel — per plane-step it
+// spends ~875 cycles issuing 18 MMAs and ~560 in barrier waits / commits (tools/dbg_k3s1.py) while the pipe needs 1008 and
+// idles whenever its short queue drains.  With two lanes the CTA runs TWO independent producer / issuer / epilogue chains
+// that share the weights and the tensor pipe: lane L owns z-chunk L of the unit (output planes [L*ZC, (L+1)*ZC), its own
+// half of TMEM, its own half of the stage ring), so while one issuer waits or commits the other keeps the pipe fed.  Every
+// output is still accumulated by ONE issuer in a fixed order (results stay run-to-run identical); the price is the halo
+// plane at the chunk boundary (18 instead of 16 plane loads, +8 % MMA cycles at Z = 16).  Single K pass only.
+template <int KS, int STAT, int LANES>  // KS = KG / 16: k16 steps per tap (1 or 2); STAT: fused statistics mode (0 = off)
+__global__ void __launch_bounds__(LANES == 2 ? kThreads2 : kThreads, 1) conv_k3s1_kernel(const __grid_constant__ K3 p) {
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ uint64_t bar_full[kMaxStages], bar_empty[kMaxStages], bar_wfull[2], bar_wempty[2];
-  __shared__ uint64_t bar_acc_full[kMaxBlocks], bar_acc_empty[kMaxBlocks];
+  __shared__ uint64_t bar_full_s[kMaxStages], bar_empty_s[kMaxStages], bar_wfull[2], bar_wempty[2];
+  __shared__ uint64_t bar_acc_full_s[kMaxBlocks], bar_acc_empty_s[kMaxBlocks];
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int S = p.nstages;
+  // role of this warp and the lane (z-chunk chain) it serves
+  const int role = LANES == 2 ? (warp < 2 ? 0 : (warp < 4 ? 1 : 2)) : (warp == 0 ? 0 : (warp == 1 ? 1 : 2));
+  const int L = LANES == 2 ? (role == 2 ? (warp - 4) >> 2 : (warp & 1)) : 0;
+  const int S = p.nstages / LANES;  // stages per lane
   const int nwbuf = p.npass > 1 ? 2 : 1;
   uint8_t* wbuf = smem;
-  uint8_t* stages = smem + (size_t)nwbuf * p.wbuf_bytes;
+  uint8_t* stages = smem + (size_t)nwbuf * p.wbuf_bytes + (size_t)L * S * p.stage_bytes;
+  uint64_t* bar_full = bar_full_s + L * S;
+  uint64_t* bar_empty = bar_empty_s + L * S;
+  uint64_t* bar_acc_full = bar_acc_full_s + L * (kMaxBlocks / 2);
+  uint64_t* bar_acc_empty = bar_acc_empty_s + L * (kMaxBlocks / 2);
   const int Yp = p.in.Yp, Z = p.in.Z;
   const int kch = p.KG >> 3;
 
   if (tid == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
+    for (int s = 0; s < kMaxStages; ++s) { mbar_init(&bar_full_s[s], 1); mbar_init(&bar_empty_s[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&bar_wfull[s], 1); mbar_init(&bar_wempty[s], 1); }
-    for (int b = 0; b < kMaxBlocks; ++b) { mbar_init(&bar_acc_full[b], 1); mbar_init(&bar_acc_empty[b], 128); }
+    for (int b = 0; b < kMaxBlocks; ++b) { mbar_init(&bar_acc_full_s[b], 1); mbar_init(&bar_acc_empty_s[b], 128); }
     mbar_fence_init();
   }
-  if (warp == 1) tmem_alloc<512>(&tmem_base_s);
+  if (warp == (LANES == 2 ? 2 : 1)) tmem_alloc<512>(&tmem_base_s);
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
-  const uint32_t tmem = tmem_base_s;
+  const uint32_t tmem = tmem_base_s + (uint32_t)L * 256u;  // lane L accumulates in its own 256 columns
 
   auto decode = [&](int u, int& n, int& zc, int& tile) {
     tile = u % p.ntile;
     const int r = u / p.ntile;
-    zc = r % p.nzc;
-    n = r / p.nzc;
+    if constexpr (LANES == 2) {  // a unit is (sample, tile); the z-chunk is the lane
+      zc = L;
+      n = r;
+    } else {
+      zc = r % p.nzc;
+      n = r / p.nzc;
+    }
   };
 
-  if (warp == 0) {
+  if (role == 0) {
     // ============================================================ producer
     // lane 0 runs the barrier protocol; the copies of a step are issued by several lanes at once (one thread issuing
     // bulk copies back to back is limited to ~8 GB/s per SM, profiles/r01_bulk_probe.txt)
@@ -104,7 +126,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_k3s1_kernel(const __grid_con
         const int64_t qoff = ((int64_t)tile * 128 - 1) * 8;  // first staged position = q0 - Yp - 1, q0 = Yp + tile*128
         const bf16* in_n = p.in.ptr + (int64_t)n * p.in.n_stride + qoff;
         for (int g = 0; g < p.npass; ++g) {
-          if (p.npass > 1 || !w_loaded) {
+          if ((p.npass > 1 || !w_loaded) && L == 0) {
             const int wb = wit & 1;
             if (lane == 0) {
               mbar_wait(&bar_wempty[wb], ((wit >> 1) & 1) ^ 1);
@@ -135,7 +157,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_k3s1_kernel(const __grid_con
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (role == 1) {
     // ============================================================ MMA issuer
     // Loop control, barrier waits and descriptor arithmetic run warp-uniformly (uniform datapath, no per-MMA
     // reconvergence); only the tcgen05.mma / commit instructions are predicated on the leader lane.
@@ -223,20 +245,23 @@ __global__ void __launch_bounds__(kThreads, 1) conv_k3s1_kernel(const __grid_con
           }
         }
       }
-      if (kDbg && p.dbg && leader) {
+      if (kDbg && p.dbg && leader && L == 0) {
         long long* d = p.dbg + (size_t)blockIdx.x * 8;
         d[0] = clock64() - t0; d[1] = t_empty; d[2] = t_full; d[3] = t_issue; d[4] = it; d[5] = t_first; d[6] = t_commit;
       }
     }
   } else {
     // ============================================================ epilogue groups
-    const int eg = (warp - 2) >> 2;                 // 0 / 1: even / odd accumulator blocks
+    // LANES = 1: two groups take the even / odd accumulator blocks; LANES = 2: the group drains every block of its lane
+    const int eg = LANES == 2 ? 0 : (warp - 2) >> 2;
+    constexpr int kEgStep = LANES == 2 ? 1 : 2;
+    const int ewarp = LANES == 2 ? warp - 4 : warp - 2;  // 0..7: index of this epilogue warp in the CTA
     const int lane_q = warp & 3;                    // TMEM lane quarter this warp may access
     const int r = lane_q * 32 + lane;               // GEMM row
     const uint32_t trow = tmem + ((uint32_t)(lane_q * 32) << 16);
     uint32_t full_mask = 0;  // bit b: parity of the number of times block b has been drained so far
     // hand every accumulator block of this group to the MMA warp zeroed (the MMAs only ever accumulate)
-    for (int b = eg; b < p.ZC; b += 2) {
+    for (int b = eg; b < p.ZC; b += kEgStep) {
       for (int c = 0; c < p.NPo; c += 16) tmem_st16_zero(trow + b * p.NPo + c);
       tmem_st_wait();
       fence_before_sync();
@@ -249,7 +274,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_k3s1_kernel(const __grid_con
     if constexpr (STAT != 0) {
 #pragma unroll
       for (int i = 0; i < 32; ++i) st0[i] = st1[i] = 0.f;
-      wslab = p.stat_ws + ((size_t)blockIdx.x * 8 + (warp - 2)) * p.out.N * 64;
+      wslab = p.stat_ws + ((size_t)blockIdx.x * 8 + ewarp) * p.out.N * 64;
       for (int n = 0; n < p.out.N; ++n) reinterpret_cast<float2*>(wslab + n * 64)[lane] = make_float2(0.f, 0.f);
     }
     for (int u = blockIdx.x; u < p.nunits; u += gridDim.x) {
@@ -260,7 +285,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_k3s1_kernel(const __grid_con
       const int xp = q / Yp, yp = q - xp * Yp;
       const bool ok = xp >= 1 && xp <= p.out.X && yp >= 1 && yp <= p.out.Y;
       const int64_t pos = (int64_t)q * 8;
-      for (int oz = zo0 + eg; oz < zo1; oz += 2) {
+      for (int oz = zo0 + eg; oz < zo1; oz += kEgStep) {
         const int b = oz - zo0;
         const int64_t plane = (int64_t)oz * p.out.plane_elems() + pos;
         bf16* out_row = p.out.ptr + (int64_t)n * p.out.n_stride + plane;
@@ -389,12 +414,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_k3s1_kernel(const __grid_con
   }
   fence_before_sync();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<512>(tmem);
+  if (warp == (LANES == 2 ? 2 : 1)) tmem_dealloc<512>(tmem_base_s);
   if constexpr (STAT != 0) {  // the 8 warp slabs of this CTA -> its CTA slab (fixed order)
     const int per = p.out.N * 64;
     const float* ws = p.stat_ws + (size_t)blockIdx.x * 8 * per;
     float* cs = p.stat_ws + (size_t)gridDim.x * 8 * per + (size_t)blockIdx.x * per;
-    for (int i = tid; i < per; i += kThreads) {
+    for (int i = tid; i < per; i += (int)blockDim.x) {
       float t = 0.f;
 #pragma unroll
       for (int w = 0; w < 8; ++w) t += ws[(size_t)w * per + i];
@@ -446,7 +471,7 @@ __global__ void __launch_bounds__(256) stat_finalize_kernel(const float* __restr
 }
 
 struct Plan {
-  int KG, npass, PW, ntile, ZC, nzc, nstages;
+  int KG, npass, PW, ntile, ZC, nzc, nstages, lanes;
   uint32_t stage_bytes, wbuf_bytes;
   size_t smem;
   bool ok;
@@ -483,9 +508,22 @@ Plan make_plan(int K, int NPo, int Z, int X, int Y) {
   if (S > kMaxStages) S = kMaxStages;
   pl.nstages = S;
   pl.smem = wtotal + (size_t)S * pl.stage_bytes;
+  pl.lanes = 1;
+  // dual issue (two z-chunk lanes per CTA, see the kernel): single K pass, <= 32 result channels, both chunks' accumulators
+  // in TMEM (2 * ceil(Z/2) * NPo <= 512 columns), at least two stages per lane
+  static const bool no_dual = getenv("RTP_NO_DUAL") != nullptr;  // A/B switch
+  const int zc2 = (Z + 1) / 2;
+  if (!no_dual && pl.npass == 1 && NPo <= 32 && Z >= 2 && zc2 * NPo <= 256 && zc2 <= kMaxBlocks / 2 && S >= 4) {
+    pl.lanes = 2;
+    pl.ZC = zc2;
+    pl.nzc = 2;
+    pl.nstages = S & ~1;
+  }
   pl.ok = true;
   return pl;
 }
+
+int plan_units(const Plan& pl, int N) { return pl.lanes == 2 ? N * pl.ntile : N * pl.ntile * pl.nzc; }
 
 }  // namespace
 
@@ -510,7 +548,7 @@ extern "C" int rtp_conv_k3s1(const rtp_conv_k3s1_desc* d, void* stream) {
   k.NPo = d->NPo; k.N3 = 3 * d->NPo; k.out_c8 = d->out_c8; k.relu = d->relu; k.accumulate = d->accumulate;
   k.has_res = d->res.ptr != nullptr; k.has_mask = d->mask.ptr != nullptr;
   k.KG = pl.KG; k.npass = pl.npass; k.PW = pl.PW; k.ntile = pl.ntile; k.ZC = pl.ZC; k.nzc = pl.nzc;
-  k.nunits = d->in.N * pl.ntile * pl.nzc;
+  k.nunits = plan_units(pl, d->in.N);
   k.nstages = pl.nstages; k.stage_bytes = pl.stage_bytes; k.wbuf_bytes = pl.wbuf_bytes;
   k.wtap_bytes = (uint32_t)(pl.KG / 8) * k.N3 * 16;          // one tap's [KG/8][N3][8] slice
   k.wtap_stride = (uint32_t)(d->Cin / 8) * k.N3 * 16;        // distance between taps in the packed weights
@@ -531,11 +569,13 @@ extern "C" int rtp_conv_k3s1(const rtp_conv_k3s1_desc* d, void* stream) {
   if (d->use_tap_mask) RTP_CHECK_ARG(d->tap_mask_groups >= 1 && d->tap_mask_groups <= 8 && d->Cin % d->tap_mask_groups == 0 &&
                                          (d->Cin / d->tap_mask_groups) % pl.KG == 0,
                                      "rtp_conv_k3s1: tap_mask_groups must split K into whole passes");
-  const int ki = (pl.KG == 32 ? 1 : 0) + 2 * d->stat_mode;
-  void (*kerns[6])(const K3) = {conv_k3s1_kernel<1, 0>, conv_k3s1_kernel<2, 0>, conv_k3s1_kernel<1, 1>,
-                                conv_k3s1_kernel<2, 1>, conv_k3s1_kernel<1, 2>, conv_k3s1_kernel<2, 2>};
+  const int ki = (pl.KG == 32 ? 1 : 0) + 2 * d->stat_mode + (pl.lanes == 2 ? 6 : 0);
+  void (*kerns[12])(const K3) = {conv_k3s1_kernel<1, 0, 1>, conv_k3s1_kernel<2, 0, 1>, conv_k3s1_kernel<1, 1, 1>,
+                                 conv_k3s1_kernel<2, 1, 1>, conv_k3s1_kernel<1, 2, 1>, conv_k3s1_kernel<2, 2, 1>,
+                                 conv_k3s1_kernel<1, 0, 2>, conv_k3s1_kernel<2, 0, 2>, conv_k3s1_kernel<1, 1, 2>,
+                                 conv_k3s1_kernel<2, 1, 2>, conv_k3s1_kernel<1, 2, 2>, conv_k3s1_kernel<2, 2, 2>};
   auto kern = kerns[ki];
-  static size_t configured_dev[RTP_MAX_DEVICES][6];  /* the opt-in is per device */
+  static size_t configured_dev[RTP_MAX_DEVICES][12];  /* the opt-in is per device */
   size_t* configured = configured_dev[rtp_current_device()];
   if (pl.smem > configured[ki]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
@@ -549,7 +589,7 @@ extern "C" int rtp_conv_k3s1(const rtp_conv_k3s1_desc* d, void* stream) {
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
   }
   const int grid = k.nunits < nsm ? k.nunits : nsm;
-  kern<<<grid, kThreads, pl.smem, (cudaStream_t)stream>>>(k);
+  kern<<<grid, pl.lanes == 2 ? kThreads2 : kThreads, pl.smem, (cudaStream_t)stream>>>(k);
   RTP_LAUNCH_CHECK();
 }
 
@@ -566,7 +606,7 @@ extern "C" int32_t rtp_conv_k3s1_num_ctas(int32_t Cin, int32_t NPo, int32_t N, i
   int dev = 0, nsm = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-  const int nunits = N * pl.ntile * pl.nzc;
+  const int nunits = plan_units(pl, N);
   return nunits < nsm ? nunits : nsm;
 }
 

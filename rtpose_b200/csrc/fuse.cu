@@ -121,6 +121,123 @@ __global__ void __launch_bounds__(256) fuse_sum_rows_kernel(const __grid_constan
   }
 }
 
+// Tile variant (output rows of <= 64 vectors, low-resolution rows of <= 32): a CTA owns XT consecutive x rows of one
+// (n, chunk, z) plane.  Phase 1 blends, for every low-resolution term, the four (z, x) corner rows of each of the XT output
+// rows into shared memory (fp32) — the z axis and the per-term pointers are CTA constants, so a blended vector costs 4 loads,
+// 4 unpacks and 8 x 4 FMAs and nothing else.  Phase 2: thread = (row, y) with y fixed for the whole kernel, so the y-axis
+// interpolation of every term (indices, weights) lives in registers; per output vector: the same-resolution loads, two
+// shared-memory rows per term, bias / ReLU, one 16-byte store.  Same fp32 expressions as fuse_sum_rows_kernel (which spent
+// ~3x the instructions on per-row address arithmetic, int<->float conversions and local-memory copies of the term table).
+template <int NLOW>
+__global__ void __launch_bounds__(256, 3) fuse_sum_tile_kernel(const __grid_constant__ FuseK p, int XT, int log2ty) {
+  extern __shared__ float4 fs_smem[];  // per term j: [XT][Yl_j][2]
+  const P8& o = p.out;
+  const int z = blockIdx.y;
+  const int c8 = blockIdx.z % ((p.C + 7) / 8), n = blockIdx.z / ((p.C + 7) / 8);
+  const int x0 = blockIdx.x * XT, nx = min(XT, o.X - x0);
+  const int tid = threadIdx.x;
+  const bf16* lb[NLOW];
+  int Yl[NLOW], Ypl[NLOW], Xl[NLOW], sbase[NLOW];
+  int64_t zo0[NLOW], zo1[NLOW];
+  float wz0[NLOW], wz1[NLOW], sx[NLOW];
+  int sm = 0;
+#pragma unroll
+  for (int j = 0; j < NLOW; ++j) {
+    const P8& l = p.low[j];
+    lb[j] = l.ptr + n * l.n_stride + c8 * l.c_stride;
+    Yl[j] = l.Y; Ypl[j] = l.Yp; Xl[j] = l.X;
+    const Axis az = ac_axis(z, l.Z, ac_scale(l.Z, o.Z));
+    zo0[j] = (int64_t)az.i0 * l.Xp * l.Yp * 8;
+    zo1[j] = (int64_t)az.i1 * l.Xp * l.Yp * 8;
+    wz0[j] = az.w0; wz1[j] = az.w1;
+    sx[j] = ac_scale(l.X, o.X);
+    sbase[j] = sm;
+    sm += XT * l.Y * 2;
+  }
+  // the first same-resolution term of this thread's rows is requested BEFORE the blend phase, so its HBM latency is hidden
+  // behind phase 1 and the barrier (a thread has at most kRows rows: XT <= 16, >= 4 rows of threads)
+  constexpr int kRows = 4;
+  const int y = tid & ((1 << log2ty) - 1), rstep = 256 >> log2ty, xr0 = tid >> log2ty;
+  const bool yok = y < o.Y;
+  const int64_t xstride = (int64_t)o.Yp * 8;
+  const int64_t obase = n * o.n_stride + c8 * o.c_stride + o.voxel(z, x0, y);
+  uint4 pre[kRows];
+  {
+    const bf16* sb = p.same[0].ptr + n * p.same[0].n_stride + c8 * p.same[0].c_stride + o.voxel(z, x0, y);
+#pragma unroll
+    for (int k = 0; k < kRows; ++k) {
+      const int xr = xr0 + k * rstep;
+      pre[k] = (p.n_same > 0 && yok && xr < nx) ? ldg16(sb + (int64_t)xr * xstride) : make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+  // ---- phase 1: corner blend of the low-resolution rows
+#pragma unroll
+  for (int j = 0; j < NLOW; ++j) {
+    int l2 = 0;
+    while ((1 << l2) < Yl[j]) ++l2;
+    const int yl = tid & ((1 << l2) - 1), rs1 = 256 >> l2;
+    if (yl < Yl[j]) {
+      for (int xr = tid >> l2; xr < nx; xr += rs1) {
+        const Axis ax = ac_axis(x0 + xr, Xl[j], sx[j]);
+        const int64_t o0 = ((int64_t)(ax.i0 + 1) * Ypl[j] + (yl + 1)) * 8, o1 = ((int64_t)(ax.i1 + 1) * Ypl[j] + (yl + 1)) * 8;
+        float f00[8], f01[8], f10[8], f11[8], r[8];
+        unpack8(ldg16(lb[j] + zo0[j] + o0), f00);
+        unpack8(ldg16(lb[j] + zo0[j] + o1), f01);
+        unpack8(ldg16(lb[j] + zo1[j] + o0), f10);
+        unpack8(ldg16(lb[j] + zo1[j] + o1), f11);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          r[i] = wz0[j] * (ax.w0 * f00[i] + ax.w1 * f01[i]) + wz1[j] * (ax.w0 * f10[i] + ax.w1 * f11[i]);
+        float4* d = fs_smem + sbase[j] + (xr * Yl[j] + yl) * 2;
+        d[0] = make_float4(r[0], r[1], r[2], r[3]);
+        d[1] = make_float4(r[4], r[5], r[6], r[7]);
+      }
+    }
+  }
+  __syncthreads();
+  // ---- phase 2
+  if (!yok) return;
+  int yi0[NLOW], yi1[NLOW];
+  float wy0[NLOW], wy1[NLOW];
+#pragma unroll
+  for (int j = 0; j < NLOW; ++j) {
+    const Axis ay = ac_axis(y, Yl[j], ac_scale(Yl[j], o.Y));
+    yi0[j] = ay.i0 * 2; yi1[j] = ay.i1 * 2; wy0[j] = ay.w0; wy1[j] = ay.w1;
+  }
+  float bias[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) bias[i] = (p.bias && c8 * 8 + i < p.C) ? p.bias[c8 * 8 + i] : 0.f;
+#pragma unroll
+  for (int k = 0; k < kRows; ++k) {
+    const int xr = xr0 + k * rstep;
+    if (xr >= nx) break;
+    const int64_t off = o.voxel(z, x0 + xr, y);
+    float acc[8];
+    unpack8(pre[k], acc);  // zeros when there is no same-resolution term
+    for (int s = 1; s < p.n_same; ++s) {
+      float f[8];
+      unpack8(ldg16(p.same[s].ptr + n * p.same[s].n_stride + c8 * p.same[s].c_stride + off), f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += f[i];
+    }
+#pragma unroll
+    for (int j = 0; j < NLOW; ++j) {
+      const float4* r = fs_smem + sbase[j] + xr * Yl[j] * 2;
+      const float4 a0 = r[yi0[j]], a1 = r[yi0[j] + 1], b0 = r[yi1[j]], b1 = r[yi1[j] + 1];
+      acc[0] += wy0[j] * a0.x + wy1[j] * b0.x; acc[1] += wy0[j] * a0.y + wy1[j] * b0.y;
+      acc[2] += wy0[j] * a0.z + wy1[j] * b0.z; acc[3] += wy0[j] * a0.w + wy1[j] * b0.w;
+      acc[4] += wy0[j] * a1.x + wy1[j] * b1.x; acc[5] += wy0[j] * a1.y + wy1[j] * b1.y;
+      acc[6] += wy0[j] * a1.z + wy1[j] * b1.z; acc[7] += wy0[j] * a1.w + wy1[j] * b1.w;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      acc[i] += bias[i];
+      if (p.relu) acc[i] = fmaxf(acc[i], 0.f);
+    }
+    stg16(o.ptr + obase + (int64_t)xr * xstride, pack8(acc));
+  }
+}
+
 __global__ void __launch_bounds__(256) fuse_sum_kernel(const __grid_constant__ FuseK p) {
   // rows (fixed z, x) x lanes along y: the z/x interpolation indices and weights are computed once per row
   const int c8 = blockIdx.y, n = blockIdx.z;
@@ -396,7 +513,19 @@ extern "C" int rtp_fuse_sum(const rtp_fuse_desc* d, void* stream) {
   const int64_t V = (int64_t)d->out.Z * d->out.X * d->out.Y;
   bool rows_ok = d->n_low > 0;
   for (int i = 0; i < d->n_low; ++i) rows_ok = rows_ok && d->low[i].Y <= 32;
-  if (rows_ok)
+  static const bool no_tile = getenv("RTP_NO_FUSE_TILE") != nullptr;  // A/B switch
+  if (rows_ok && d->out.Y <= 64 && !no_tile) {
+    int sumY = 0;
+    for (int i = 0; i < d->n_low; ++i) sumY += d->low[i].Y;
+    const int XT = 16 * sumY * 32 <= 32 * 1024 ? 16 : 8;
+    const size_t smem = (size_t)XT * sumY * 32;
+    int log2ty = 0;
+    while ((1 << log2ty) < d->out.Y) ++log2ty;  // <= 6: at least 4 rows of threads, so a thread has <= XT / 4 <= 4 rows
+    const dim3 grid((unsigned)ceil_div(d->out.X, XT), (unsigned)d->out.Z, (unsigned)(d->out.N * C8));
+    if (d->n_low == 1) fuse_sum_tile_kernel<1><<<grid, 256, smem, (cudaStream_t)stream>>>(k, XT, log2ty);
+    else if (d->n_low == 2) fuse_sum_tile_kernel<2><<<grid, 256, smem, (cudaStream_t)stream>>>(k, XT, log2ty);
+    else fuse_sum_tile_kernel<3><<<grid, 256, smem, (cudaStream_t)stream>>>(k, XT, log2ty);
+  } else if (rows_ok)
     fuse_sum_rows_kernel<<<dim3(ew_blocks(V), C8, d->out.N), 256, 0, (cudaStream_t)stream>>>(k);
   else
     fuse_sum_kernel<<<dim3(ew_blocks(V), C8, d->out.N), 256, 0, (cudaStream_t)stream>>>(k);

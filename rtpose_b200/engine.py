@@ -57,6 +57,18 @@ class Engine:
         Z, Y, X = grid if grid is not None else like.grid
         return self.pool.get(like.N, like.C if C is None else C, Z, Y, X, like.buf.device)
 
+    # GroupNorm statistics are computed once per tensor and shared by every GN that reads it.  The cache is keyed by the
+    # tensor OBJECT and keeps it alive: keyed by id() alone, a temporary P8 that died (a channel view, a converted input)
+    # could hand its statistics to a new tensor allocated at the same address.
+    def _stats_get(self, t):
+        hit = self.stats_cache.get(id(t))
+        if hit is not None and hit[0] is t and hit[2] == (t.buf.data_ptr(), t.offset):
+            return hit[1]
+        return None
+
+    def _stats_put(self, t, stats):
+        self.stats_cache[id(t)] = (t, stats, (t.buf.data_ptr(), t.offset))
+
     def _grad_of(self, t):
         """Returns (grad tensor, accumulate flag) for a writer into t.grad.  Writers on different streams are chained in
         program order: the current stream first waits for the previous writer's event; call _wrote(t) after the write."""
@@ -119,10 +131,10 @@ class Engine:
         p = self.p
         gamma, beta, w = p[gn + ".weight"], p[gn + ".bias"], p[conv + ".weight"]
         G = 8 if x.C >= 8 else 1
-        stats = self.stats_cache.get(id(x))
+        stats = self._stats_get(x)
         if stats is None:
             stats = ops.gn_stats(x, G)
-            self.stats_cache[id(x)] = stats
+            self._stats_put(x, stats)
         Zo, Yo, Xo = ops.out_grid(x, stride)
         y = self.new(x, C=w.shape[0], grid=(Zo, Yo, Xo))
         if stride == 2 and k == 3 and ops.s2d_eligible(x, w):
@@ -130,7 +142,7 @@ class Engine:
         xn = ops.gn_apply(x, G, stats, gamma, beta, self.new(x))
         if y_stats and stride == 1 and y.C % 8 == 0 and ops.stat_fusable(xn, w, False):
             _, st = ops.conv_forward(self.packs, xn, w, stride, y, relu=relu, res=res, stat=("stats", 8, 1e-5))
-            self.stats_cache[id(y)] = st
+            self._stats_put(y, st)
         else:
             ops.conv_forward(self.packs, xn, w, stride, y, relu=relu, res=res)
         y.relu_out = bool(relu)
@@ -239,8 +251,8 @@ class Engine:
             dev = xs[0].buf.device
             main = torch.cuda.current_stream(dev)
             for x in xs:  # statistics every fuse conv may ask for, computed once, before the fork
-                if id(x) not in self.stats_cache:
-                    self.stats_cache[id(x)] = ops.gn_stats(x, 8 if x.C >= 8 else 1)
+                if self._stats_get(x) is None:
+                    self._stats_put(x, ops.gn_stats(x, 8 if x.C >= 8 else 1))
             used = {i: self._branch_stream(i, dev) for i in idx if i > 0}
             for st in used.values():  # fork everything first: a later wait_stream(main) would also wait for output 0
                 st.wait_stream(main)

@@ -129,7 +129,10 @@ def test_engine_full_grid_takes_the_space_to_depth_path():
     rel, cos = grad_report(out["grads"], out2["grads"])
     print("s2d vs gather path: gradient cosine %.6f, rel-L2 max %.3g; hm max diff %.3g" %
           (cos, rel.max(), (out["hm"] - out2["hm"]).abs().max().item()))
-    assert cos > 0.999 and (out["hm"] - out2["hm"]).abs().max().item() <= 0.02 * max(r_hm.std().item(), 1e-3) + 1e-3
+    # the two kernel paths sum in different orders: the bf16 logits may differ by a rounding step (the logits sit at the
+    # hm bias, -2.19, where bf16 is spaced 2^-6 apart) — bound: two bf16 steps at the largest magnitude
+    step = 2.0 ** (np.floor(np.log2(out["hm"].abs().max().item())) - 7)
+    assert cos > 0.999 and (out["hm"] - out2["hm"]).abs().max().item() <= 2 * step
 
 
 def test_detector_full_grid_graphed():

@@ -578,7 +578,7 @@ def test_stride2_conv_through_space_to_depth_view(ctx, case):
     dx5 = P8(N, Cin, *grid)
     ops.gn_backward(xp, dxs, 8, stats, gc, dg, db, False, dx5, False, s2d=True, add=to_p8(extra))
     torch.cuda.synchronize()
-    close(dx5.to_ncdhw(), dx.to_ncdhw() + bf(extra), tol=2 * BF16_ULP, what="s2d dx + add")
+    close(dx5.to_ncdhw(), dx.to_ncdhw().cpu() + bf(extra), tol=2 * BF16_ULP, what="s2d dx + add")
 
 
 def test_fused_launch_variants_match_their_multi_launch_forms(ctx):
