@@ -350,15 +350,25 @@ def run_ours(args, rank, world, local_rank):
     if args.serial_branches:
         eng.parallel_branches = False
 
+    # N > 1: the flat gradient buffer is all-reduced in 3 slices on a communication stream, each launched as soon as
+    # backward has issued the slice's last gradient; the mean comes from seeding backward with 1/world
+    sar = None
+    if world > 1 and not args.late_allreduce:
+        from rtpose_b200 import spec as _spec  # noqa: F401
+        sar = rdist.SlicedAllReduce(gflat, [(k, v.numel()) for k, v in params.items()], 3, world).attach(eng)
+
     def step_body():
         lib.call("rtp_ingest_pack", raw.data_ptr(), B, D, RAW_SHAPE[0], RAW_SHAPE[1], RAW_SHAPE[2], ROI0[0], ROI0[1], ROI0[2],
                  float(a), float(b - a), 1 if norm is not None else 0, xin.struct(), None, _stream())
         tgt = targets.assign_device(poses, GRID, one_hm=(ncls == 1), min_radius=2 if ncls == 1 else 1)
         eng.packs.refresh_async()  # the optimizer rewrote the weights: every pack is rebuilt inside the timed region
         hm, rg = eng.forward(xin, True)
-        out = eng.loss(hm, rg, tgt["hm"], tgt["ind"], tgt["mask"], tgt["cat"], tgt["anno_pose"])
+        out = eng.loss(hm, rg, tgt["hm"], tgt["ind"], tgt["mask"], tgt["cat"], tgt["anno_pose"],
+                       grad_scale=(1.0 / world) if sar is not None else 1.0)
         eng.backward(grads)
-        if world > 1:
+        if sar is not None:
+            sar.join()
+        elif world > 1:
             rdist.allreduce_flat(gflat, world)
         if opt is not None:
             opt.step_dev()
@@ -451,6 +461,8 @@ def run_ours(args, rank, world, local_rank):
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": dict(workload_config(cfg, B, world, D), **{
                        "l2": "inputs+activations per step >> 126 MB L2 (no explicit flush needed)",
+                       "allreduce": (None if world == 1 else ("3 slices overlapped with backward on a communication stream" if sar is not None
+                                                              else "one flat all-reduce after backward")),
                        "cuda_graph": use_graph, "wgrad_side_stream": bool(ops.ASYNC_WGRAD), "branch_streams": bool(eng.parallel_branches),
                        "targets": "assigned on the device from resident fp64 skeletons every step (rtp_assign_targets)",
                        "optimizer": ("fused clip(35) + decoupled wd + Adam, one-cycle lr (rtp_adam_step) inside the timed region"
@@ -719,6 +731,7 @@ def main():
     ap.add_argument("--sync-wgrad", action="store_true", help="run weight gradients in-stream (no side stream)")
     ap.add_argument("--no-extras", action="store_true", help="skip e2e / cpu_baseline / inference legs")
     ap.add_argument("--no-optimizer", action="store_true", help="time forward+backward only (no fused clip+Adam step)")
+    ap.add_argument("--late-allreduce", action="store_true", help="N > 1: one all-reduce after backward instead of overlapped slices (A/B)")
     ap.add_argument("--ref-gpu-probe", action="store_true", help="time the unmodified reference on this GPU through stock PyTorch (informative)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -77,6 +77,78 @@ def allreduce_grads(params, world=None):
         o += g.numel()
 
 
+class SlicedAllReduce:
+    """All-reduce of a flat gradient buffer in a few contiguous slices, each launched on a communication stream as soon
+    as the backward pass has issued the last gradient of the slice (engine.Engine.set_grad_groups), so the collective
+    runs under the rest of backward instead of after it.  SURVEY.md §8e; replaces DDP's bucketed overlap
+    (det3d/torchie/apis/train.py:285-291) for the flat-buffer trainer.
+
+    `names_in_flat_order`: [(name, numel)] in the order the parameters sit in `flat` — state_dict order, i.e. roughly
+    forward order, so backward completes the TAIL of the buffer first and the slices are cut from the back.
+    The mean is obtained by seeding the backward pass with 1/world (Engine.loss(grad_scale=1/world)): the collective is a
+    plain sum and no scale pass follows.  Everything here is stream-ordered and capturable in a CUDA graph."""
+
+    def __init__(self, flat, names_in_flat_order, nslices=3, world=None, extra_streams=()):
+        self.flat = flat
+        self.world = world or (dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1)
+        total = sum(n for _, n in names_in_flat_order)
+        assert total == flat.numel()
+        # cut points: equal element counts, snapped to parameter boundaries, slice 0 = tail of the buffer
+        bounds, acc, target = [0], 0, total / float(nslices)
+        for name, n in names_in_flat_order:
+            acc += n
+            if len(bounds) < nslices and acc >= target * len(bounds):
+                bounds.append(acc)
+        if bounds[-1] != total:
+            bounds.append(total)
+        spans = [(bounds[i], bounds[i + 1]) for i in range(len(bounds) - 1)][::-1]
+        self.spans = spans
+        self.groups = []
+        for lo, hi in spans:
+            o, g = 0, []
+            for name, n in names_in_flat_order:
+                if lo <= o < hi:
+                    g.append(name)
+                o += n
+            self.groups.append(g)
+        self.stream = torch.cuda.Stream(device=flat.device) if flat.is_cuda else None
+        self.extra_streams = list(extra_streams)
+        self.launched = []
+
+    def attach(self, engine):
+        self.engine = engine
+        engine.set_grad_groups(self.groups, self.on_ready)
+        return self
+
+    def on_ready(self, k):
+        """Called by Engine.backward when every gradient of slice k has been issued."""
+        lo, hi = self.spans[k]
+        self.launched.append(k)
+        if self.world == 1 or not (dist.is_available() and dist.is_initialized()):
+            return
+        piece = self.flat[lo:hi]
+        if self.stream is None:
+            dist.all_reduce(piece, op=dist.ReduceOp.SUM)
+            return
+        from . import ops
+        cur = torch.cuda.current_stream(self.flat.device)
+        self.stream.wait_stream(cur)
+        for key, st in ops._side.items():           # weight gradients queued so far
+            if key.split("/")[0] == str(self.flat.device):
+                self.stream.wait_stream(st["stream"])
+        eng = getattr(self, "engine", None)
+        for st in list(self.extra_streams) + (list(eng._bstreams.values()) if eng is not None else []):
+            self.stream.wait_stream(st)             # branch streams (GroupNorm parameter gradients of side branches)
+        with torch.cuda.stream(self.stream):
+            dist.all_reduce(piece, op=dist.ReduceOp.SUM)
+
+    def join(self):
+        """The current stream waits for every slice's collective (call before the optimizer step)."""
+        self.launched = []
+        if self.stream is not None:
+            torch.cuda.current_stream(self.flat.device).wait_stream(self.stream)
+
+
 def _common_flat(grads):
     """The flat tensor the gradients are consecutive, gap-free views of, or None."""
     b = grads[0]._base if grads[0]._base is not None else None

@@ -50,6 +50,8 @@ class Engine:
         self._ordered_grads = False  # set while backward closures may run on several streams
         self._bstreams = {}
         self.fold_grad_adds = not os.environ.get("RTP_NO_FOLD_ADDS")  # residual / fuse-sum gradient pass-throughs ride in the next GroupNorm backward (_defer_add)
+        self._last_touch, self._closure_idx = {}, -1
+        self._grad_groups, self._on_ready, self._milestones = None, None, None
         self.generation = 0  # bumped by begin(): a backward job checks that the tape it recorded is still the live one
 
     # ------------------------------------------------------------------ helpers
@@ -120,7 +122,19 @@ class Engine:
         g = self.grads[name]
         acc = name in self._touched
         self._touched.add(name)
+        self._last_touch[name] = self._closure_idx
         return g, acc
+
+    def set_grad_groups(self, groups, on_ready):
+        """Gradient-ready notifications for overlapping the data-parallel all-reduce with the backward pass
+        (what DDP's buckets do for the reference, det3d/torchie/apis/train.py:285-291).  `groups`: lists of parameter
+        names; `on_ready(k)` is called inside backward() right after the LAST tape closure that writes a gradient of group
+        k has been issued (its kernels are queued on the current / weight-gradient / branch streams — the callback
+        makes its communication stream wait for them, see dist.SlicedAllReduce).  The closure -> group map is learnt from
+        the previous backward pass (the tape is static); until then every group is reported at the end of backward()."""
+        self._grad_groups = [list(g) for g in groups]
+        self._on_ready = on_ready
+        self._milestones = None
 
     # ------------------------------------------------------------------ ops with backward closures
     def gn_conv(self, x, gn, conv, k, stride, relu, res=None, train=True, x_needs_grad=True, res_needs_grad=True,
@@ -526,11 +540,29 @@ class Engine:
         """Runs the tape in reverse; `grads`: dict name -> fp32 tensor receiving d loss / d param."""
         self.grads = grads
         self._touched = set()
+        self._last_touch = {}
         self._ordered_grads = bool(self.parallel_fuse_bwd and self.parallel_fuse and self.parallel_branches)
-        for fn in reversed(self.tape):
+        ms, fired = self._milestones, set()
+        for i, fn in enumerate(reversed(self.tape)):
+            self._closure_idx = i
             fn()
+            if ms is not None:
+                for k in ms.get(i, ()):
+                    fired.add(k)
+                    self._on_ready(k)
+        ntape = len(self.tape)
         self.tape = []
         ops.join_wgrad()
+        if self._grad_groups is not None:
+            for k in range(len(self._grad_groups)):  # groups not reported on the way (first pass, or nothing touched)
+                if k not in fired:
+                    self._on_ready(k)
+            learnt = {}
+            for k, names in enumerate(self._grad_groups):
+                idx = [self._last_touch[n] for n in names if n in self._last_touch]
+                if idx:
+                    learnt.setdefault(max(idx), []).append(k)
+            self._milestones = learnt if ntape else None
         return self._touched
 
     def decode(self, hm, reg, voxel_xyz, range_xyz):

@@ -46,6 +46,16 @@ def _worker(rank, world, port, out):
         assert rdist._common_flat([q.grad for q in qs]) is flatg
         rdist.allreduce_grads(qs, world)
         assert flatg.tolist() == [i * 1.5 for i in range(11)] and qs[1].grad.data_ptr() == flatg[6:].data_ptr()
+        # sliced all-reduce (the collective side of the backward overlap): slices are cut from the tail of the buffer at
+        # parameter boundaries and reduced as they are reported ready; pre-scaled gradients -> plain sum
+        names = [("a", 10), ("b", 30), ("c", 5), ("d", 55), ("e", 20), ("f", 40)]
+        fl = torch.arange(160, dtype=torch.float32) * (rank + 1) / world
+        sar = rdist.SlicedAllReduce(fl, names, 3, world)
+        assert sar.spans == [(120, 160), (100, 120), (0, 100)] and sar.groups == [["f"], ["e"], ["a", "b", "c", "d"]]
+        for k in range(len(sar.spans)):
+            sar.on_ready(k)
+        sar.join()
+        assert fl.tolist() == [i * 1.5 for i in range(160)]
         out.put((rank, lo, hi, flat.tolist(), params.tolist()))
     finally:
         dist.destroy_process_group()

@@ -196,3 +196,34 @@ def test_stream_schedules_are_bitwise_equivalent():
         assert set(out["grads"]) == set(ref["grads"])
         for k in ref["grads"]:
             assert torch.equal(out["grads"][k], ref["grads"][k]), k
+
+
+def test_gradient_ready_notifications_follow_the_tape():
+    """Engine.set_grad_groups: after the first (learning) backward pass every group is reported exactly once per pass, in
+    backward order (tail of the flat buffer first), and only after its last gradient has been issued — the hook the
+    sliced all-reduce hangs on (dist.SlicedAllReduce)."""
+    from rtpose_b200 import dist as rdist
+    cfg, grid, batch = "hr3d_one_hm_doppler", (8, 16, 24), 2
+    x, poses, tgt = G.make_example(cfg, batch, grid, seed=5)
+    eng, params = build_engine(cfg)
+    total = sum(v.numel() for v in params.values())
+    flat = torch.zeros(total, device="cuda")
+    sar = rdist.SlicedAllReduce(flat, [(k, v.numel()) for k, v in params.items()], 3, world=1).attach(eng)
+    assert [hi for _, hi in sar.spans][0] == total and sar.spans[-1][0] == 0
+    assert sum(len(g) for g in sar.groups) == len(params)
+    seen = []
+    orig = sar.on_ready
+    def spy(k):
+        seen.append((k, set(eng._touched)))
+        orig(k)
+    eng._on_ready = spy
+    for it in range(3):
+        seen.clear()
+        out, _, _ = run_engine(eng, params, x, tgt)
+        assert sorted(k for k, _ in seen) == [0, 1, 2], seen
+        if it > 0:  # learnt: reported in backward order, each after all of its gradients were issued
+            assert [k for k, _ in seen] == [0, 1, 2]
+            for k, touched in seen:
+                assert set(sar.groups[k]) & set(out["grads"]) <= touched, k
+            # the first slice is reported before the backward pass has reached the stem
+            assert "backbone.backbone.layer1.conv2.conv.weight" not in seen[0][1]
