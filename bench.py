@@ -355,7 +355,8 @@ def run_ours(args, rank, world, local_rank):
     sar = None
     if world > 1 and not args.late_allreduce:
         from rtpose_b200 import spec as _spec  # noqa: F401
-        sar = rdist.SlicedAllReduce(gflat, [(k, v.numel()) for k, v in params.items()], 3, world).attach(eng)
+        sar = rdist.SlicedAllReduce(gflat, [(k, v.numel()) for k, v in params.items()], world=world,
+                                    fractions=(0.5, 0.35, 0.15)).attach(eng)
 
     def step_body():
         lib.call("rtp_ingest_pack", raw.data_ptr(), B, D, RAW_SHAPE[0], RAW_SHAPE[1], RAW_SHAPE[2], ROI0[0], ROI0[1], ROI0[2],
@@ -483,6 +484,115 @@ def run_ours(args, rank, world, local_rank):
             line["loader"] = loader_bench(args, dev)
         except Exception as ex:
             line["loader"] = {"error": repr(ex)}
+    if rank == 0:
+        print(json.dumps(line))
+
+
+def run_dcn_head(args, rank, world, local_rank):
+    """BASELINE.json configs[4]: the wide-channel (phase) HRRadarPose variant with the deformable head, data-parallel
+    training.  The head is the 3-D-compatible DCNSepHead (det3d_compat, dcn_head='fold_z': 2-D ops on the z-folded batch),
+    a module-level composition, so this leg drives the det3d-style model — model(example) -> loss -> backward -> flat
+    gradient all-reduce -> fused clip + Adam — eagerly (no CUDA graph), inputs resident in HBM."""
+    from rtpose_b200 import det3d_compat as D
+    from rtpose_b200 import dist as rdist
+    from rtpose_b200 import lib, ops, targets
+    from rtpose_b200.optim import FlatAdam, one_cycle
+    lib.require_device()
+    cfg = args.cfg
+    arch, fin, fout, fuse, reg, ncls, weight, in_ch, norm, gf_fwd = CFGS[cfg]
+    dev = torch.device("cuda", local_rank)
+    B = args.batch
+    names = ["Pelvis"]
+    head_in = fout if fuse != "top" else 32
+    model_cfg = dict(type="RadarPoseNet", pretrained=None, reader=dict(type="RadarFeatureNet"),
+                     backbone=dict(type="HRNet3D", backbone_cfg=arch, final_conv_in=fin, final_conv_out=fout, final_fuse=fuse, ds_factor=1),
+                     pose_head=dict(type="CenterHead", tasks=[dict(num_class=ncls, class_names=names[:ncls])], in_channels=head_in,
+                                    share_conv_channel=head_in, dataset="cruw_pose", weight=weight,
+                                    code_weights=[1.0] * 45, common_heads={"reg": (reg, 2)}, dcn_head="fold_z"),
+                     neck=None)
+    torch.manual_seed(0)
+    model = D.build_detector(model_cfg, train_cfg=None, test_cfg=None).to(dev)
+    model.pose_head.sync_free_losses = True
+    params = [p for p in model.parameters()]
+    total = sum(p.numel() for p in params)
+    flat = torch.empty(total, dtype=torch.float32, device=dev)
+    gflat = torch.zeros(total, dtype=torch.float32, device=dev)
+    o = 0
+    for p in params:  # parameters become views of one flat buffer (fused optimizer, one all-reduce)
+        flat[o:o + p.numel()].copy_(p.data.reshape(-1))
+        p.data = flat[o:o + p.numel()].view(p.shape)
+        o += p.numel()
+    if world > 1:
+        rdist.broadcast_params([flat])
+    opt = FlatAdam(flat, gflat, wd=0.01, max_norm=35.0, params=params)
+    rs = np.random.RandomState(7 + rank)
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    x = torch.clamp(torch.rand((B, in_ch) + GRID, device=dev, generator=g) * 1.2 - 0.2, min=0)
+    tg = targets.assign(targets.random_poses(rs, B, GRID), GRID, one_hm=True, min_radius=2)
+    ex = {"rdr": {"rdr_tensor": x}, "meta": [{}] * B}
+    for k, v in tg.items():
+        ex["rdr"][k] = [torch.from_numpy(v).to(dev)]
+    it = [0]
+
+    def step():
+        lr, mom = one_cycle(it[0], 1000, lr_max=2e-3)
+        it[0] += 1
+        for p in params:
+            p.grad = None
+        losses = model(ex, return_loss=True)
+        losses["loss"][0].backward()
+        torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in params], out=gflat)
+        if world > 1:
+            rdist.allreduce_flat(gflat, world)
+        opt.step(lr, mom)
+        return losses["loss"][0]
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        loss = step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    lib.launch_count = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = step()
+    e1.record()
+    barrier()
+    launches = lib.launch_count
+    ms = e0.elapsed_time(e1) / args.steps
+    ops.PROFILE = {"_only": TENSOR | EW}
+    ops.ASYNC_WGRAD = False
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    step()
+    p1.record()
+    barrier()
+    prof, ops.PROFILE = ops.PROFILE, None
+    sampler.stop_flag = True
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms = float(t[0])
+    roof, top = summarize_profile(prof, p0.elapsed_time(p1), 1, B, "CUDA events around each conv / element-wise launch of one eager step "
+                                  "run after the timed region (DCN sampling / scatter kernels are not itemised)")
+    value = world * B / (ms * 1e-3)
+    line = {"metric": "radar frames/sec HRRadarPose fwd+bwd", "value": value, "unit": "frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "%s + deformable head (CenterHead dcn_head='fold_z': FeatureAdaption x2 at C=%d, DCN v1 dg=4 on the "
+                                   "z-folded batch [B*16, %d, 64, 160]) training fwd+bwd, batch %d per GPU, model input resident in HBM "
+                                   "(BASELINE.json configs[4])" % (cfg, head_in, head_in, B),
+                       "per_gpu_batch": B, "global_batch": B * world, "grid": list(GRID), "parallelism": "dp%d" % world,
+                       "cuda_graph": False, "optimizer": "fused clip(35) + decoupled wd + Adam (rtp_adam_step) inside the timed region",
+                       "l2": "activations per step >> 126 MB L2"},
+            "loss": float(loss), "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roof, "top_kernels": top,
+            "params": total}
     if rank == 0:
         print(json.dumps(line))
 
@@ -731,6 +841,7 @@ def main():
     ap.add_argument("--sync-wgrad", action="store_true", help="run weight gradients in-stream (no side stream)")
     ap.add_argument("--no-extras", action="store_true", help="skip e2e / cpu_baseline / inference legs")
     ap.add_argument("--no-optimizer", action="store_true", help="time forward+backward only (no fused clip+Adam step)")
+    ap.add_argument("--dcn-head", action="store_true", help="configs[4]: the deformable head (dcn_head='fold_z') on the det3d-style model")
     ap.add_argument("--late-allreduce", action="store_true", help="N > 1: one all-reduce after backward instead of overlapped slices (A/B)")
     ap.add_argument("--ref-gpu-probe", action="store_true", help="time the unmodified reference on this GPU through stock PyTorch (informative)")
     args = ap.parse_args()
@@ -750,7 +861,10 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:
-        run_ours(args, rank, world, local_rank)
+        if args.dcn_head:
+            run_dcn_head(args, rank, world, local_rank)
+        else:
+            run_ours(args, rank, world, local_rank)
     finally:
         if world > 1:
             torch.distributed.destroy_process_group()

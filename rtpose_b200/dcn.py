@@ -29,14 +29,14 @@ def _stream():
 
 # Forward contraction on the tcgen05 tensor cores (bf16 operands, fp32 accumulation) instead of the fp32 CUDA-core kernel:
 # the deformed samples are written once as a bf16 P8 volume with the taps on the z axis (rtp_dcn_sample_p8) and contracted
-# by rtp_conv.  Off by default because it changes the op's precision from fp32 to bf16-in / fp32-accumulate (what the rest
-# of the path computes in); enable with RTP_DCN_TC=1 or `rtpose_b200.dcn.TENSOR_CORE = True`.  The backward pass always uses
-# the fp32 kernels (gradients of the fp32 op evaluated at the same inputs).
-TENSOR_CORE = os.environ.get("RTP_DCN_TC", "0") not in ("", "0")
+# by rtp_conv.  This is the DEFAULT for every shape it supports (tc_supported): the op then computes in bf16-in / fp32-
+# accumulate like the rest of the path, 2-4x faster than the fp32 kernels (profiles/r01_dcn_timings.txt).  RTP_DCN_TC=0 or
+# `rtpose_b200.dcn.TENSOR_CORE = False` selects the fp32 CUDA-core kernels (bit-for-bit the reference op's precision).
+TENSOR_CORE = os.environ.get("RTP_DCN_TC", "1") not in ("", "0")
 # The same for the backward pass (RTP_DCN_TC_BWD=1 / TENSOR_CORE_BACKWARD): weight gradient = rtp_wgrad over (sample
 # volume, dy), sample gradient = kh*kw single-tap rtp_conv launches with the dgrad-packed weight, then rtp_dcn_col2im_p8
 # scatters it into dx / doffset / dmask.  Gradients then carry bf16 operand rounding like every other conv of the path.
-TENSOR_CORE_BACKWARD = os.environ.get("RTP_DCN_TC_BWD", "0") not in ("", "0")
+TENSOR_CORE_BACKWARD = os.environ.get("RTP_DCN_TC_BWD", "1") not in ("", "0")
 TC_SAMPLE_BYTES = 512 << 20   # the sampled volume is produced and consumed in batch chunks of at most this size
 _tc_state = {}
 

@@ -397,6 +397,73 @@ class HRNet3D(nn.Module):
         return _Bridge.apply(job, *params.values())[0]
 
 
+class DCNSepHead(nn.Module):
+    """A 3-D-compatible definition of the reference's deformable head (center_head.py:111-163, `DCNSepHead`).
+
+    The reference's class cannot be constructed (it passes bn= on to nn.Module.__init__, a TypeError: SURVEY F4) and, built
+    from Conv2d / BatchNorm2d / a 2-D DeformConv, could not consume the 5-D feature map of the radar-pose backbone anyway.
+    This module keeps its structure and parameter names and gives it a meaning on [B, C, Z, Y, X]:
+
+      * every 2-D operator acts on the z-folded batch [B*Z, C, Y, X] — the (y, x) plane is the range-azimuth plane the
+        deformable sampling is meant for; z slices are independent samples for the 2-D ops;
+      * feature_adapt_cls / feature_adapt_reg: FeatureAdaption (1x1 offset predictor with zero-initialised weight, DCN v1
+        3x3 with 4 deformable groups, ReLU), center_head.py:24-62;
+      * cls_head: Conv2d 3x3 (C -> head_conv) + norm + ReLU + Conv2d 3x3 (head_conv -> num_cls, bias = init_bias).  The norm
+        is GroupNorm(8) instead of BatchNorm2d: per-sample statistics, like every other norm of the path ('GCR'), so the
+        result does not depend on how frames are sharded over ranks;
+      * task_head: the ordinary SepHead on the un-folded reg feature (Conv3d 3x3x3, head_conv = 64), center_head.py:66-109.
+
+    Enabled with CenterHead(dcn_head="fold_z"); dcn_head=True keeps raising TypeError like the reference.  Contractions run on
+    the tcgen05 kernels (rtpose_b200.convfn, rtpose_b200.dcn with TENSOR_CORE)."""
+
+    def __init__(self, in_channels, num_cls, heads, head_conv=64, final_kernel=3, init_bias=-2.19):
+        super(DCNSepHead, self).__init__()
+        from . import dcn
+        if final_kernel != 3:
+            raise NotImplementedError("DCNSepHead: final_kernel=%d" % final_kernel)
+        self.feature_adapt_cls = dcn.FeatureAdaption(in_channels, in_channels, kernel_size=3, deformable_groups=4)
+        self.feature_adapt_reg = dcn.FeatureAdaption(in_channels, in_channels, kernel_size=3, deformable_groups=4)
+        self.heads, self.head_conv, self.num_cls = dict(heads), head_conv, num_cls
+        # cls_head.{0: conv, 1: norm, 3: conv}: the reference's Sequential indices
+        entries = [("cls_head.0.weight", (head_conv, in_channels, 3, 3), "conv"),
+                   ("cls_head.0.bias", (head_conv,), "conv_bias:%d" % (in_channels * 9)),
+                   ("cls_head.1.weight", (head_conv,), "ones"), ("cls_head.1.bias", (head_conv,), "zeros"),
+                   ("cls_head.3.weight", (num_cls, head_conv, 3, 3), "conv"),
+                   ("cls_head.3.bias", (num_cls,), "const:%r" % init_bias)]
+        for name, (classes, num_conv) in self.heads.items():
+            if num_conv != 2:
+                raise NotImplementedError("SepHead with num_conv=%d" % num_conv)
+            q = "task_head.%s" % name  # SepHead: every conv kaiming_init (normal, fan_out), bias 0 (center_head.py:96-99)
+            entries += [(q + ".0.weight", (head_conv, in_channels, 3, 3, 3), "kaiming_fan_out"), (q + ".0.bias", (head_conv,), "zeros"),
+                        (q + ".2.weight", (classes, head_conv, 3, 3, 3), "kaiming_fan_out"), (q + ".2.bias", (classes,), "zeros")]
+        _install(self, entries)
+
+    def _adapt(self, fa, x5):
+        """FeatureAdaption on the z-folded batch; offsets from our 1x1 conv kernel, DCN from rtpose_b200.dcn."""
+        from . import convfn
+        B, Cc, Z, Y, X = x5.shape
+        off5 = convfn.conv2d_as_3d(x5, fa.conv_offset.weight, fa.conv_offset.bias)              # [B, 72, Z, Y, X]
+        x2 = x5.permute(0, 2, 1, 3, 4).reshape(B * Z, Cc, Y, X)
+        off2 = off5.permute(0, 2, 1, 3, 4).reshape(B * Z, off5.shape[1], Y, X)
+        y2 = fa.relu(fa.conv_adaption(x2, off2))
+        return y2.reshape(B, Z, -1, Y, X).permute(0, 2, 1, 3, 4).contiguous()
+
+    def forward(self, x):
+        from . import convfn
+        x = _cuda_input(x, "DCNSepHead input").float()
+        p = dict(self.named_parameters())
+        center = self._adapt(self.feature_adapt_cls, x)
+        regf = self._adapt(self.feature_adapt_reg, x)
+        h = convfn.conv2d_as_3d(center, p["cls_head.0.weight"], p["cls_head.0.bias"])
+        h = torch.relu(convfn.group_norm(h, 8, p["cls_head.1.weight"], p["cls_head.1.bias"]))
+        ret = {}
+        for name in self.heads:
+            t = convfn.conv3d(regf, p["task_head.%s.0.weight" % name], p["task_head.%s.0.bias" % name], relu=True)
+            ret[name] = convfn.conv3d(t, p["task_head.%s.2.weight" % name], p["task_head.%s.2.bias" % name])
+        ret["hm"] = convfn.conv2d_as_3d(h, p["cls_head.3.weight"], p["cls_head.3.bias"])
+        return ret
+
+
 @HEADS.register_module
 class CenterHead(nn.Module):
     """det3d/models/pose_heads/center_head.py:166-360."""
@@ -404,10 +471,12 @@ class CenterHead(nn.Module):
     def __init__(self, in_channels=128, tasks=[], dataset="cruw_pose", common_heads=dict(), logger=None, init_bias=-2.19,
                  share_conv_channel=64, num_hm_conv=2, weight=0.1, code_weights=[], dcn_head=False):
         super(CenterHead, self).__init__()
-        if dcn_head:
+        if dcn_head and dcn_head != "fold_z":
             # the reference's DCNSepHead cannot be constructed either (TypeError at center_head.py:152)
             raise TypeError("dcn_head=True is not constructible in the reference (DCNSepHead passes bn= to "
-                            "nn.Module.__init__); use rtpose_b200.dcn.DeformConv at operator level")
+                            "nn.Module.__init__); dcn_head='fold_z' selects the 3-D-compatible definition "
+                            "(rtpose_b200.det3d_compat.DCNSepHead)")
+        self.dcn_head = dcn_head or False
         num_classes = [len(_get(t, "class_names")) for t in tasks]
         if len(num_classes) != 1:
             raise NotImplementedError("the cruw_pose configs define exactly one task")
@@ -420,9 +489,16 @@ class CenterHead(nn.Module):
         if list(heads) != ["reg", "hm"]:
             raise NotImplementedError("heads %s (the radar-pose path has common_heads={'reg': ...})" % list(heads))
         self.reg_channels = heads["reg"][0]
-        _install(self, spec.head_spec(in_channels, share_conv_channel, heads, init_bias=init_bias))
-        if in_channels == share_conv_channel:
+        if self.dcn_head:
+            if in_channels != share_conv_channel:
+                raise NotImplementedError("dcn_head with a shared_conv (in_channels != share_conv_channel)")
             self.shared_conv = nn.Identity()
+            self.tasks = nn.ModuleList([DCNSepHead(share_conv_channel, num_classes[0], dict(common_heads), head_conv=64,
+                                                   final_kernel=3, init_bias=init_bias)])
+        else:
+            _install(self, spec.head_spec(in_channels, share_conv_channel, heads, init_bias=init_bias))
+            if in_channels == share_conv_channel:
+                self.shared_conv = nn.Identity()
         self.sync_free_losses = False  # True: keep every returned loss term on the device (no .cpu() syncs)
         self._engine = None
 
@@ -435,6 +511,8 @@ class CenterHead(nn.Module):
 
     def forward(self, x, *kwargs):
         x = _cuda_input(x, "CenterHead input").float()
+        if self.dcn_head:
+            return [self.tasks[0](x)], x
         params = _named(self)
         e = self._eng(params)
         e.p = params
@@ -548,6 +626,16 @@ class RadarPoseNet(nn.Module):
         ex.update(example[self.sensor_type])
         ex.update({"meta": example["meta"]})
         x = _model_input(self.reader(ex["rdr_tensor"]), "example['rdr']['rdr_tensor']")
+        if getattr(self.pose_head, "dcn_head", False):
+            # the deformable head is a module-level composition (DCNSepHead): backbone job -> head -> loss / predict,
+            # as the reference's RadarPoseNet.forward does (radar_pose_net.py:36-46)
+            if isinstance(x, P8):
+                x = x.to_ncdhw()
+            preds, _ = self.pose_head(self.backbone(x))
+            if return_loss:
+                return self.pose_head.loss(ex, preds, self.test_cfg)
+            with torch.no_grad():
+                return self.pose_head.predict(ex, preds, self.test_cfg)
         params = _named(self)
         e = self._eng(params)
         if return_loss:

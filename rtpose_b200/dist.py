@@ -88,16 +88,23 @@ class SlicedAllReduce:
     The mean is obtained by seeding the backward pass with 1/world (Engine.loss(grad_scale=1/world)): the collective is a
     plain sum and no scale pass follows.  Everything here is stream-ordered and capturable in a CUDA graph."""
 
-    def __init__(self, flat, names_in_flat_order, nslices=3, world=None, extra_streams=()):
+    def __init__(self, flat, names_in_flat_order, nslices=3, world=None, extra_streams=(), fractions=None):
         self.flat = flat
         self.world = world or (dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1)
         total = sum(n for _, n in names_in_flat_order)
         assert total == flat.numel()
-        # cut points: equal element counts, snapped to parameter boundaries, slice 0 = tail of the buffer
-        bounds, acc, target = [0], 0, total / float(nslices)
+        # cut points snapped to parameter boundaries; slice 0 = tail of the buffer.  `fractions` (of the element count, in
+        # launch order) default to equal parts; a small LAST slice keeps the collective that cannot overlap short.
+        fr = list(fractions) if fractions is not None else [1.0 / nslices] * nslices
+        nslices = len(fr)
+        marks, c = [], 0.0
+        for f in fr[::-1][:-1]:
+            c += f
+            marks.append(c * total)
+        bounds, acc = [0], 0
         for name, n in names_in_flat_order:
             acc += n
-            if len(bounds) < nslices and acc >= target * len(bounds):
+            if len(bounds) <= len(marks) and acc >= marks[len(bounds) - 1]:
                 bounds.append(acc)
         if bounds[-1] != total:
             bounds.append(total)

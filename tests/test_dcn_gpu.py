@@ -7,6 +7,15 @@ import torch
 pytestmark = pytest.mark.gpu
 tv = pytest.importorskip("torchvision.ops")
 
+
+@pytest.fixture(autouse=True)
+def _fp32_kernels_by_default(monkeypatch):
+    """The operator-parity tests below pin the fp32 CUDA-core kernels (rtol 1e-4 against torchvision); the tensor-core path —
+    the library default — is selected explicitly by the tests that check it (bf16 tolerances)."""
+    from rtpose_b200 import dcn
+    monkeypatch.setattr(dcn, "TENSOR_CORE", False)
+    monkeypatch.setattr(dcn, "TENSOR_CORE_BACKWARD", False)
+
 CASES = [(2, 8, 7, 9, 8, 3, 1, 1, 1, 4), (1, 16, 12, 10, 24, 3, 1, 1, 1, 4), (2, 8, 9, 11, 16, 3, 2, 1, 1, 2),
          (1, 32, 16, 20, 32, 3, 1, 1, 1, 4), (1, 8, 8, 8, 8, 1, 1, 0, 1, 1), (1, 8, 10, 9, 8, 3, 1, 2, 2, 1)]
 
@@ -260,3 +269,87 @@ def test_feature_adaption(tc, monkeypatch):
     tol = 2.0 ** -7 * ref.abs().max().item() if tc else 2e-3
     assert (out.detach().cpu() - ref).abs().max().item() <= tol
     assert xc.grad is not None and m.conv_offset.weight.grad is not None and m.conv_adaption.weight.grad is not None
+
+
+def test_tensor_core_path_is_the_default():
+    import importlib
+    import os
+    from rtpose_b200 import dcn
+    if os.environ.get("RTP_DCN_TC") or os.environ.get("RTP_DCN_TC_BWD"):
+        pytest.skip("explicitly configured")
+    fresh = importlib.reload(dcn)
+    assert fresh.TENSOR_CORE and fresh.TENSOR_CORE_BACKWARD
+
+
+def test_dcn_head_fold_z_matches_torch_composition(monkeypatch):
+    """CenterHead(dcn_head='fold_z') — the 3-D-compatible definition of the reference's DCNSepHead (2-D ops on the z-folded
+    batch, center_head.py:24-62,111-163) — against the same composition written with torch / torchvision ops in fp32:
+    FeatureAdaption x2 (1x1 offsets, deform_conv2d dg=4, ReLU), cls head (conv2d 3x3, GroupNorm(8), ReLU, conv2d 3x3),
+    SepHead (conv3d 3x3x3, ReLU, conv3d).  Tensor-core path (bf16 operands): conv tolerances."""
+    import torch.nn.functional as F
+    from rtpose_b200 import dcn
+    from rtpose_b200 import det3d_compat as D
+    monkeypatch.setattr(dcn, "TENSOR_CORE", True)
+    monkeypatch.setattr(dcn, "TENSOR_CORE_BACKWARD", True)
+    B, Cc, Z, Y, X = 2, 32, 3, 12, 20
+    names = ["Pelvis"]
+    torch.manual_seed(0)
+    head = D.CenterHead(in_channels=Cc, tasks=[dict(num_class=1, class_names=names)], dataset="cruw_pose", weight=0.5,
+                        code_weights=[1.0] * 45, common_heads={"reg": (45, 2)}, share_conv_channel=Cc, dcn_head="fold_z").cuda()
+    with pytest.raises(TypeError):
+        D.CenterHead(in_channels=Cc, tasks=[dict(num_class=1, class_names=names)], common_heads={"reg": (45, 2)},
+                     share_conv_channel=Cc, dcn_head=True)
+    t = head.tasks[0]
+    with torch.no_grad():  # non-trivial offsets (the reference initialises the offset weights to zero)
+        for fa in (t.feature_adapt_cls, t.feature_adapt_reg):
+            fa.conv_offset.weight.normal_(0, 0.05)
+            fa.conv_offset.bias.uniform_(-1.0, 1.0)
+    g = torch.Generator().manual_seed(5)
+    bf = lambda v: v.to(torch.bfloat16).float()
+    x = bf(torch.randn(B, Cc, Z, Y, X, generator=g)).cuda().requires_grad_(True)
+    preds, same = head(x)
+    hm, reg = preds[0]["hm"], preds[0]["reg"]
+    assert hm.shape == (B, 1, Z, Y, X) and reg.shape == (B, 45, Z, Y, X) and same is x
+    gh, gr = torch.randn(hm.shape, generator=g).cuda(), torch.randn(reg.shape, generator=g).cuda()
+    (hm * gh).sum().add((reg * gr).sum()).backward()
+    got = {k: p.grad.clone() for k, p in head.named_parameters()}
+    gx = x.grad.clone()
+    # ---- torch / torchvision composition, fp32
+    p = {k: v.detach().clone().requires_grad_(True) for k, v in head.named_parameters()}
+    xr = x.detach().clone().requires_grad_(True)
+
+    def adapt(prefix, x5):
+        x2 = x5.permute(0, 2, 1, 3, 4).reshape(B * Z, Cc, Y, X)
+        off = F.conv2d(x2, p[prefix + ".conv_offset.weight"], p[prefix + ".conv_offset.bias"])
+        y2 = F.relu(tv.deform_conv2d(x2, off, p[prefix + ".conv_adaption.weight"], None, padding=1))
+        return y2, y2.reshape(B, Z, Cc, Y, X).permute(0, 2, 1, 3, 4)
+    c2, _ = adapt("tasks.0.feature_adapt_cls", xr)
+    _, r5 = adapt("tasks.0.feature_adapt_reg", xr)
+    h = F.conv2d(c2, p["tasks.0.cls_head.0.weight"], p["tasks.0.cls_head.0.bias"], padding=1)
+    # GroupNorm over the whole (z, y, x) volume of a sample, like every norm of the path: un-fold, normalise, fold back
+    h5 = h.reshape(B, Z, -1, Y, X).permute(0, 2, 1, 3, 4)
+    h5 = F.relu(F.group_norm(h5, 8, p["tasks.0.cls_head.1.weight"], p["tasks.0.cls_head.1.bias"], 1e-5))
+    h = h5.permute(0, 2, 1, 3, 4).reshape(B * Z, -1, Y, X)
+    hm_r = F.conv2d(h, p["tasks.0.cls_head.3.weight"], p["tasks.0.cls_head.3.bias"], padding=1)
+    hm_r = hm_r.reshape(B, Z, 1, Y, X).permute(0, 2, 1, 3, 4)
+    tr = F.relu(F.conv3d(r5, p["tasks.0.task_head.reg.0.weight"], p["tasks.0.task_head.reg.0.bias"], padding=1))
+    reg_r = F.conv3d(tr, p["tasks.0.task_head.reg.2.weight"], p["tasks.0.task_head.reg.2.bias"], padding=1)
+    (hm_r * gh).sum().add((reg_r * gr).sum()).backward()
+
+    def rel(a, b):
+        return float((a - b).abs().max() / b.abs().max().clamp_min(1e-6))
+    print("hm rel err %.4g, reg rel err %.4g, dx rel err %.4g" % (rel(hm, hm_r), rel(reg, reg_r), rel(gx, xr.grad)))
+    assert rel(hm, hm_r) <= 2 ** -5 and rel(reg, reg_r) <= 2 ** -5
+    assert rel(gx, xr.grad) <= 2 ** -4
+    for k in p:
+        assert got[k] is not None, k
+        a, b = got[k].double().flatten(), p[k].grad.double().flatten()
+        cos = float(a @ b / (a.norm() * b.norm() + 1e-30))
+        assert cos >= 0.995, (k, cos)
+    assert sorted(k for k in dict(head.named_parameters())) == sorted(
+        ["tasks.0.feature_adapt_cls.conv_offset.weight", "tasks.0.feature_adapt_cls.conv_offset.bias",
+         "tasks.0.feature_adapt_cls.conv_adaption.weight", "tasks.0.feature_adapt_reg.conv_offset.weight",
+         "tasks.0.feature_adapt_reg.conv_offset.bias", "tasks.0.feature_adapt_reg.conv_adaption.weight",
+         "tasks.0.cls_head.0.weight", "tasks.0.cls_head.0.bias", "tasks.0.cls_head.1.weight", "tasks.0.cls_head.1.bias",
+         "tasks.0.cls_head.3.weight", "tasks.0.cls_head.3.bias", "tasks.0.task_head.reg.0.weight", "tasks.0.task_head.reg.0.bias",
+         "tasks.0.task_head.reg.2.weight", "tasks.0.task_head.reg.2.bias"])
