@@ -145,6 +145,58 @@ __global__ void __launch_bounds__(256) ingest_kernel(const __half* __restrict__ 
   }
 }
 
+// Vectorised variant (no fp32 side output, 16-byte aligned raw rows): one block per (n, 8-Doppler chunk, z, 8 y rows) and the
+// WHOLE x range of the ROI.  Reads are 16-byte vectors of 8 halves from the aligned superset [x0 & ~7, ...) of each raw row
+// (one coalesced run of ~340 B per (plane, row) instead of 2-byte scalar loads of 64-byte pieces: the scalar kernel ran at
+// 0.21 of the HBM rate, instruction-bound), normalised / clamped / rounded to bf16 into shared memory, then written as
+// 16-byte channel vectors, 8 consecutive y (one full 128-byte line) per x.  Same arithmetic, same rounding.
+constexpr int kIngY = 8, kIngXMax = 176;  // rows per block; widest ROI handled (vectors cover <= kIngXMax + 8 halves)
+__global__ void __launch_bounds__(256) ingest_vec_kernel(const __half* __restrict__ raw, int D, int RZ, int RY, int RX,
+                                                         int z0, int y0, int x0, float a, float scale, int normalize, P8 t) {
+  __shared__ __align__(16) bf16 tile[8][kIngY][kIngXMax + 16];
+  const int yt = blockIdx.x * kIngY;
+  int b = blockIdx.y;
+  const int z = b % t.Z;
+  b /= t.Z;
+  const int ch = b % t.C8, n = b / t.C8;
+  const int xa = x0 & ~7;                          // aligned start of the superset
+  const int nvec = (x0 + t.X - xa + 7) >> 3;       // 16-byte vectors per row
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 8 * kIngY * nvec; i += 256) {
+    const int v = i % nvec, r = i / nvec, yy = r % kIngY, c = r / kIngY;
+    const int y = yt + yy, d = ch * 8 + c;
+    uint4 q = make_uint4(0u, 0u, 0u, 0u);
+    const bool ok = y < t.Y && d < D;
+    if (ok) q = __ldg(reinterpret_cast<const uint4*>(raw + ((((int64_t)n * D + d) * RZ + (z0 + z)) * RY + (y0 + y)) * RX + xa) + v);
+    const __half2* h2 = reinterpret_cast<const __half2*>(&q);
+    __nv_bfloat162 o2[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float2 f = __half22float2(h2[k]);
+      if (normalize) {
+        f.x = (f.x - a) / scale; f.x = f.x < 0.f ? 0.f : f.x;
+        f.y = (f.y - a) / scale; f.y = f.y < 0.f ? 0.f : f.y;
+      }
+      if (!ok) f.x = f.y = 0.f;
+      o2[k] = __floats2bfloat162_rn(f.x, f.y);
+    }
+    *reinterpret_cast<uint4*>(&tile[c][yy][v * 8]) = *reinterpret_cast<const uint4*>(o2);
+  }
+  __syncthreads();
+  bf16* pbase = t.ptr + n * t.n_stride + ch * t.c_stride;
+  const int xs = x0 - xa;  // first ROI element inside the superset
+  for (int i = tid; i < t.X * kIngY; i += 256) {
+    const int yy = i % kIngY, x = i / kIngY, y = yt + yy;
+    if (y < t.Y) {
+      bf16x8 o;
+      bf16* ob = reinterpret_cast<bf16*>(&o);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) ob[c] = tile[c][yy][xs + x];
+      stg16(pbase + t.voxel(z, x, y), *reinterpret_cast<const uint4*>(&o));
+    }
+  }
+}
+
 extern "C" int rtp_ingest_pack(const void* raw_f16, int32_t N, int32_t D, int32_t RZ, int32_t RY, int32_t RX,
                                int32_t z0, int32_t y0, int32_t x0, float norm_start, float norm_scale,
                                int32_t normalize, rtp_p8 dst, float* dst_f32, void* stream) {
@@ -153,6 +205,13 @@ extern "C" int rtp_ingest_pack(const void* raw_f16, int32_t N, int32_t D, int32_
   RTP_CHECK_ARG(z0 >= 0 && y0 >= 0 && x0 >= 0 && z0 + dst.Z <= RZ && y0 + dst.Y <= RY && x0 + dst.X <= RX,
                 "rtp_ingest_pack: ROI outside the raw cube");
   RTP_CHECK_ARG(!normalize || norm_scale != 0.f, "rtp_ingest_pack: zero normalisation scale");
+  const int64_t blocks_y = (int64_t)dst.N * dst.C8 * dst.Z;
+  if (!dst_f32 && RX % 8 == 0 && ((uintptr_t)raw_f16 & 15) == 0 && (x0 & 7) + dst.X <= kIngXMax + 8 &&
+      (x0 & ~7) + (((x0 & 7) + dst.X + 7) & ~7) <= RX && blocks_y <= 65535) {
+    ingest_vec_kernel<<<dim3(ceil_div(dst.Y, kIngY), (unsigned)blocks_y), 256, 0, (cudaStream_t)stream>>>(
+        (const __half*)raw_f16, D, RZ, RY, RX, z0, y0, x0, norm_start, normalize ? norm_scale : 1.f, normalize, P8(dst));
+    RTP_LAUNCH_CHECK();
+  }
   dim3 grid(ceil_div(dst.X, 32), ceil_div(dst.Y, 32), dst.N * dst.C8 * dst.Z);
   ingest_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)raw_f16, D, RZ, RY, RX, z0, y0, x0, norm_start,
                                                         normalize ? norm_scale : 1.f, normalize, P8(dst),

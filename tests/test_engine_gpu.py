@@ -53,7 +53,7 @@ def run_engine(eng, params, x, tgt, train=True):
 def oracle_run(x, sd, cfg, tgt, autocast):
     """fp32 (or bf16-autocast) CPU oracle: returns hm, reg, loss, grads."""
     sdr = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
-    c = O.CONFIGS[cfg]
+    c = O.CONFIGS[cfg] if isinstance(cfg, str) else cfg
     torch.set_num_threads(8)
     with torch.autocast("cpu", dtype=torch.bfloat16, enabled=autocast):
         preds = O.forward(torch.from_numpy(x), sdr, cfg)
@@ -227,3 +227,28 @@ def test_gradient_ready_notifications_follow_the_tape():
                 assert set(sar.groups[k]) & set(out["grads"]) <= touched, k
             # the first slice is reported before the backward pass has reached the stem
             assert "backbone.backbone.layer1.conv2.conv.weight" not in seen[0][1]
+
+
+def test_shared_conv_branch_of_the_head():
+    """CenterHead with in_channels != share_conv_channel: the GN -> Conv3d(3x3x3, no bias) -> ReLU `shared_conv`
+    (center_head.py:203-211) in front of the task heads — not used by the shipped configs, but part of the head's API."""
+    cfg = dict(O.CONFIGS["hr3d"], share=64)  # hr3d backbone ('top', 32 channels out) feeding a 64-channel shared conv
+    grid, batch = (8, 16, 16), 2
+    x, poses, tgt = G.make_example("hr3d", batch, grid, seed=77)
+    sd = O.synth_state_dict(cfg, seed=5)
+    assert "pose_head.shared_conv.1.weight" in sd and sd["pose_head.tasks.0.reg.0.weight"].shape[1] == 64
+    from rtpose_b200.engine import Engine
+    params = {k: v.cuda() for k, v in sd.items()}
+    eng = Engine(cfg["arch"], cfg["fuse"], params, cfg["reg"], cfg["ncls"], cfg["weight"], cfg["code_weights"])
+    out, hm, reg = run_engine(eng, params, x, tgt)
+    r_hm, r_reg, r_loss, r_grads = oracle_run(x, sd, cfg, tgt, False)
+    b_hm, b_reg, b_loss, b_grads = oracle_run(x, sd, cfg, tgt, True)
+    for ours, a, r, name in ((out["hm"], b_hm, r_hm, "hm"), (out["reg"], b_reg, r_reg, "reg")):
+        spread = max((a - r).abs().max().item(), 0.02 * r.std().item())
+        assert (ours - r).abs().max().item() <= 2.0 * spread, name
+    assert abs(out["loss"][0].item() - r_loss) <= 1.5e-2 * abs(r_loss)
+    rel, cos = grad_report(out["grads"], r_grads)
+    brel, bcos = grad_report(b_grads, r_grads)
+    assert cos >= min(0.97, bcos - 0.01), (cos, bcos)
+    for k in ("pose_head.shared_conv.0.weight", "pose_head.shared_conv.0.bias", "pose_head.shared_conv.1.weight"):
+        assert k in out["grads"] and float(out["grads"][k].abs().sum()) > 0, k

@@ -273,6 +273,11 @@ def test_ingest_matches_oracle():
     torch.cuda.synchronize()
     assert np.array_equal(f32.cpu().numpy(), ref), "fp32 side output must be bit-identical to numpy"
     assert torch.equal(dst.to_ncdhw().cpu(), bf(torch.from_numpy(ref)))
+    # without the fp32 side output the vectorised kernel runs (16-byte loads of the aligned superset of each row): same bits
+    dstv = P8(2, 16, 16, 64, 160)
+    lib.call("rtp_ingest_pack", rawd.data_ptr(), 2, 16, 32, 128, 256, z0, y0, x0, 0.0, 10.0, 1, dstv.struct(), None, _stream())
+    torch.cuda.synchronize()
+    assert torch.equal(dstv.buf, dst.buf), "vectorised ingest differs from the scalar kernel (pads included)"
     # single-channel 'zyx_real' cube and the crop-only phase variant
     one = rs.uniform(25000, 60000, size=(1, 1, 32, 128, 256)).astype(np.float16)  # finite in fp16 (150000 is not)
     d1 = P8(1, 1, 16, 64, 160)
