@@ -39,3 +39,43 @@ for (N, C) in ((16, 128), (32, 128), (16, 256)):
     D.TENSOR_CORE = D.TENSOR_CORE_BACKWARD = False
     t = bench(lambda: fb(lambda: tv.deform_conv2d(xr, orr, wr, None, padding=1)), 3)
     print("N=%d C=%d torchvision fwd+bwd %.3f ms" % (N, C, t))
+
+# ---- the reference's own extension (det3d/ops/dcn/src), built UNMODIFIED from the staged copy baseline/_ref with
+#      -DAT_CHECK=TORCH_CHECK (the macro was renamed in torch >= 1.5); outputs only under baseline/_ref/_build.  "The kernel to
+#      beat" of SURVEY §2.2.  Skipped (with the reason) when the staged sources are absent or do not compile on this torch.
+if "--ref-ext" in sys.argv:
+    src = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref", "det3d", "ops", "dcn", "src")
+    try:
+        from torch.utils.cpp_extension import load
+        bdir = os.path.join(os.path.dirname(src), "_build")
+        os.makedirs(bdir, exist_ok=True)
+        os.environ.setdefault("TORCH_CUDA_ARCH_LIST", "10.0a")
+        ext = load(name="deform_conv_cuda_ref", sources=[os.path.join(src, "deform_conv_cuda.cpp"), os.path.join(src, "deform_conv_cuda_kernel.cu")],
+                   extra_cflags=["-DAT_CHECK=TORCH_CHECK", "-w"], extra_cuda_cflags=["-DAT_CHECK=TORCH_CHECK", "-w"], build_directory=bdir, verbose=False)
+    except Exception as ex:  # noqa: BLE001
+        print("reference DCN extension: not built (%s)" % (repr(ex)[:400],))
+        ext = None
+    if ext is not None:
+        for (N, C) in ((16, 128), (16, 256)):
+            H, W, dg, step = 64, 160, 4, 16
+            g = torch.Generator(device="cuda").manual_seed(0)
+            x = torch.randn(N, C, H, W, device="cuda", generator=g)
+            off = torch.randn(N, dg * 18, H, W, device="cuda", generator=g)
+            w = torch.randn(C, C, 3, 3, device="cuda", generator=g) * 0.05
+            gy = torch.randn(N, C, H, W, device="cuda", generator=g)
+            out = x.new_empty(N, C, H, W)
+            bufs = [x.new_empty(0), x.new_empty(0)]
+
+            def fwd():  # deform_conv.py:48-67
+                ext.deform_conv_forward_cuda(x, w, off, out, bufs[0], bufs[1], 3, 3, 1, 1, 1, 1, 1, 1, 1, dg, step)
+
+            def bwd():  # deform_conv.py:84-110
+                gi, go, gw = torch.zeros_like(x), torch.zeros_like(off), torch.zeros_like(w)
+                ext.deform_conv_backward_input_cuda(x, off, gy, gi, go, w, bufs[0], 3, 3, 1, 1, 1, 1, 1, 1, 1, dg, step)
+                ext.deform_conv_backward_parameters_cuda(x, off, gy, gw, bufs[0], bufs[1], 3, 3, 1, 1, 1, 1, 1, 1, 1, dg, 1, step)
+            t_f = bench(fwd)
+            t_fb = bench(lambda: (fwd(), bwd()), 3)
+            ref = tv.deform_conv2d(x, off, w, None, padding=1)
+            err = float((out - ref).abs().max() / ref.abs().max())
+            print("N=%d C=%d reference extension (im2col_step %d) fwd %.3f ms, fwd+bwd %.3f ms  (max rel diff to torchvision %.2e)" %
+                  (N, C, step, t_f, t_fb, err))
