@@ -384,12 +384,15 @@ __global__ void __launch_bounds__(256) dcn_sample_p8_kernel(Dcn p, const float* 
 
 // Tensor-core backward, last step: dS (bf16 P8, taps on z; produced by rtp_conv from dy) -> dx (atomic scatter through
 // the bilinear weights), doffset and dmask.  One thread per (n, deformable group, tap, ho, wo) walks the channels of its
-// group, so doffset / dmask are plain stores of register sums; lanes run along ho, the contiguous axis of dS.
+// group, so doffset / dmask are plain stores of register sums.  Lanes run along wo — the contiguous axis of x, dx, offset
+// and doffset (NCHW) — so a warp's four corner gathers and four atomic adds per channel fall into one or two 128-byte lines
+// instead of 32 (with lanes along ho, dS's contiguous axis, this kernel was 66 % of the deformable head's step: 7 ms per
+// launch at C = 256); the price is a 16-byte-per-lane strided read of dS, 1/64 of the traffic.
 __global__ void __launch_bounds__(256, 2) dcn_col2im_p8_kernel(Dcn p, const float* __restrict__ x, const float* __restrict__ off,
                                                             const float* __restrict__ mask, P8 ds, float* __restrict__ dx,
                                                             float* __restrict__ doff, float* __restrict__ dmask) {
   const int K = p.kh * p.kw, npix = p.Ho * p.Wo, cpg = p.C / p.dg;
-  const int ho = blockIdx.x * 32 + (threadIdx.x & 31), wo = blockIdx.y * 8 + (threadIdx.x >> 5);
+  const int wo = blockIdx.x * 32 + (threadIdx.x & 31), ho = blockIdx.y * 8 + (threadIdx.x >> 5);
   int b = blockIdx.z;
   const int t = b % K;
   b /= K;
@@ -566,7 +569,7 @@ extern "C" int rtp_dcn_col2im_p8(const float* x, const float* offset, const floa
                 "rtp_dcn_col2im_p8: ds must be P8 [N=%d][C>=%d][Z=%d taps][Y=%d][X=%d]", N, C, kh * kw, d.Ho, d.Wo);
   RTP_CHECK_ARG((int64_t)N * dg * kh * kw <= 65535, "rtp_dcn_col2im_p8: N*dg*taps exceeds the grid limit; split the batch");
   cudaMemsetAsync(dx, 0, (size_t)N * C * H * W * sizeof(float), (cudaStream_t)stream);
-  dim3 grid(ceil_div(d.Ho, 32), ceil_div(d.Wo, 8), N * dg * kh * kw);
+  dim3 grid(ceil_div(d.Wo, 32), ceil_div(d.Ho, 8), N * dg * kh * kw);
   dcn_col2im_p8_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d, x, offset, mask, P8(ds), dx, doffset, mask ? dmask : nullptr);
   RTP_LAUNCH_CHECK();
 }

@@ -505,6 +505,10 @@ class Engine:
 
     def forward(self, x, train):
         """x: P8 input cube [N, in_ch, Z, Y, X].  Returns (hm, reg) raw head outputs as P8 tensors."""
+        if x.buf.device.index != torch.cuda.current_device():
+            # every launch goes to the CURRENT device's current stream (p8._stream): one process per GPU, or select the
+            # device with torch.cuda.device(...) around the call
+            raise lib.RtpError("input lives on %s but the current CUDA device is %d" % (x.buf.device, torch.cuda.current_device()))
         self.begin()
         f = self.backbone(x, train)
         return self.head(f, train)
