@@ -37,7 +37,7 @@ TENSOR_CORE = os.environ.get("RTP_DCN_TC", "1") not in ("", "0")
 # volume, dy), sample gradient = kh*kw single-tap rtp_conv launches with the dgrad-packed weight, then rtp_dcn_col2im_p8
 # scatters it into dx / doffset / dmask.  Gradients then carry bf16 operand rounding like every other conv of the path.
 TENSOR_CORE_BACKWARD = os.environ.get("RTP_DCN_TC_BWD", "1") not in ("", "0")
-TC_SAMPLE_BYTES = 512 << 20   # the sampled volume is produced and consumed in batch chunks of at most this size
+TC_SAMPLE_BYTES = 2 << 30     # the sampled volume is produced and consumed in batch chunks of at most this size
 _tc_state = {}
 
 

@@ -438,22 +438,30 @@ class DCNSepHead(nn.Module):
                         (q + ".2.weight", (classes, head_conv, 3, 3, 3), "kaiming_fan_out"), (q + ".2.bias", (classes,), "zeros")]
         _install(self, entries)
 
-    def _adapt(self, fa, x5):
-        """FeatureAdaption on the z-folded batch; offsets from our 1x1 conv kernel, DCN from rtpose_b200.dcn."""
+    def _adapt_both(self, x5):
+        """Both FeatureAdaption modules on the z-folded batch.  They read the same feature map, so the two 1x1 offset
+        predictors run as ONE conv with 2 x 72 output channels (our kernel) and the z-fold of the input is done once; the
+        DCN itself is rtpose_b200.dcn (tensor-core path)."""
         from . import convfn
         B, Cc, Z, Y, X = x5.shape
-        off5 = convfn.conv2d_as_3d(x5, fa.conv_offset.weight, fa.conv_offset.bias)              # [B, 72, Z, Y, X]
+        fc, fr = self.feature_adapt_cls, self.feature_adapt_reg
+        w = torch.cat([fc.conv_offset.weight, fr.conv_offset.weight], 0)
+        b = torch.cat([fc.conv_offset.bias, fr.conv_offset.bias], 0)
+        off5 = convfn.conv2d_as_3d(x5, w, b)                                                     # [B, 144, Z, Y, X]
         x2 = x5.permute(0, 2, 1, 3, 4).reshape(B * Z, Cc, Y, X)
         off2 = off5.permute(0, 2, 1, 3, 4).reshape(B * Z, off5.shape[1], Y, X)
-        y2 = fa.relu(fa.conv_adaption(x2, off2))
-        return y2.reshape(B, Z, -1, Y, X).permute(0, 2, 1, 3, 4).contiguous()
+        no = fc.conv_offset.weight.shape[0]
+        outs = []
+        for fa, o2 in ((fc, off2[:, :no]), (fr, off2[:, no:])):
+            y2 = fa.relu(fa.conv_adaption(x2, o2))
+            outs.append(y2.reshape(B, Z, -1, Y, X).permute(0, 2, 1, 3, 4))
+        return outs
 
     def forward(self, x):
         from . import convfn
         x = _cuda_input(x, "DCNSepHead input").float()
         p = dict(self.named_parameters())
-        center = self._adapt(self.feature_adapt_cls, x)
-        regf = self._adapt(self.feature_adapt_reg, x)
+        center, regf = self._adapt_both(x)
         h = convfn.conv2d_as_3d(center, p["cls_head.0.weight"], p["cls_head.0.bias"])
         h = torch.relu(convfn.group_norm(h, 8, p["cls_head.1.weight"], p["cls_head.1.bias"]))
         ret = {}
