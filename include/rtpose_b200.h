@@ -255,6 +255,17 @@ int rtp_gn_bwd_apply_s2d(rtp_p8 x, rtp_p8 dy_s2d, int32_t C, int32_t G, const fl
                          int32_t accumulate_dx, int32_t relu_mask, rtp_p8 add, void* stream);
 /* w [Cout][Cin][3][3][3] fp32 -> w_s2d [Cout][8*Cin][3][3][3] fp32 (zero except the 27 matching (parity, offset) pairs),
  * and the transpose for the weight gradient: dw (=|+=) fold(dw_s2d). */
+/* Weight gradient of the stride-2 conv straight from the view, plane-streaming (csrc/wgrad_s2d.cu): xs = s2d view of the
+ * normalised input (8*Cin/8 chunks), dy = gradient of the conv output (same grid as the view), Cin = 32.  One persistent
+ * CTA per SM writes an fp32 partial [nsplit][6][128][2*NP]; rtp_wgrad_s2d_reduce sums them in a fixed order into
+ * dW[co][ci][kz][ky][kx] (= or +=).  zero_page: >= 2048 bytes of device zeros; workspace: >= rtp_wgrad_s2d_workspace_bytes.
+ * replaces: autograd's conv3d weight gradient for the fuse / transition convs (hr_util/hr3d.py:162-197, :286-331). */
+int rtp_wgrad_s2d_supported(int32_t Cin, int32_t NP, int32_t Z, int32_t X, int32_t Y);
+int64_t rtp_wgrad_s2d_workspace_bytes(int32_t NP, int32_t nsm);
+int rtp_wgrad_s2d(rtp_p8 xs, rtp_p8 dy, int32_t Cin, int32_t NP, const void* zero_page, float* workspace,
+                  int32_t* nsplit_out, void* stream);
+int rtp_wgrad_s2d_reduce(const float* workspace, int32_t nsplit, int32_t Cin, int32_t NP, float* dW, int32_t co_n,
+                         int32_t accumulate, void* stream);
 int rtp_weight_s2d_expand(const float* w, float* w_s2d, int32_t Cout, int32_t Cin, void* stream);
 int rtp_weight_s2d_fold(const float* dw_s2d, float* dw, int32_t Cout, int32_t Cin, int32_t accumulate, void* stream);
 

@@ -118,7 +118,11 @@ class SlicedAllReduce:
                     g.append(name)
                 o += n
             self.groups.append(g)
-        self.stream = torch.cuda.Stream(device=flat.device) if flat.is_cuda else None
+        if flat.is_cuda:
+            from . import ops
+            self.stream = ops.named_stream(flat.device, "comm")
+        else:
+            self.stream = None
         self.extra_streams = list(extra_streams)
         self.launched = []
 

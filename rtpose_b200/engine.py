@@ -328,7 +328,7 @@ class Engine:
     def _branch_stream(self, b, device):
         st = self._bstreams.get((b, str(device)))
         if st is None:
-            st = torch.cuda.Stream(device=device)
+            st = ops.named_stream(device, "branch%d/%d" % (ops.LANE, b))  # shared by all engines of the process (see ops.named_stream)
             self._bstreams[(b, str(device))] = st
         return st
 

@@ -22,7 +22,9 @@ class StepGraph:
         self.warmup = warmup
 
     def capture(self):
-        s = torch.cuda.Stream()
+        from . import ops
+        dev = torch.cuda.current_device()
+        s = ops.named_stream(dev, "graph_warmup")
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):  # warm-up off the default stream: allocations and lazy initialisation happen here
             for _ in range(self.warmup):
@@ -32,7 +34,7 @@ class StepGraph:
         g = torch.cuda.CUDAGraph()
         # capture on a high-priority stream: kernel nodes inherit it, so when a main-chain kernel and a weight gradient
         # of the (default-priority) side stream are both ready, the main chain's blocks are dispatched first
-        cs = torch.cuda.Stream(priority=-1) if self.high_priority else None
+        cs = ops.named_stream(dev, "graph_capture", priority=-1) if self.high_priority else ops.named_stream(dev, "graph_capture_lo")
         with torch.cuda.graph(g, stream=cs):
             self.result = self.fn()
         self.graph = g

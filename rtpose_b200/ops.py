@@ -48,6 +48,24 @@ class BufferPool:
 
 
 _workspaces = {}
+_streams = {}
+
+
+def named_stream(device, name, priority=0):
+    """One CUDA stream per (device, role) for the whole process.  torch hands out streams from a pool of 32 per priority and
+    device, round-robin: code that creates fresh streams per engine / per graph capture starts to ALIAS them once the pool
+    wraps (two roles on one cudaStream_t), which showed up as an order-dependent capture invalidation in the test-suite.
+    Engines, the weight-gradient / pack / communication streams and StepGraph therefore share these few named streams."""
+    dev = torch.device(device)
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    key = (str(dev), name)
+    st = _streams.get(key)
+    if st is None:
+        st = torch.cuda.Stream(device=dev, priority=priority)
+        _streams[key] = st
+    return st
+
 
 
 def workspace(nbytes, device, tag="ws"):
@@ -185,7 +203,7 @@ class PackedWeights:
                 dev = w.device
                 global _pack_stream
                 if _pack_stream is None or _pack_stream.device != dev:
-                    _pack_stream = torch.cuda.Stream(device=dev)
+                    _pack_stream = named_stream(dev, "pack")
                 _pack_stream.wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.stream(_pack_stream):
                 repack(w)
@@ -523,7 +541,7 @@ def _side_stream(device):
     key = "%s/%d" % (device, LANE)
     st = _side.get(key)
     if st is None:
-        st = {"stream": torch.cuda.Stream(device=device), "busy": False, "events": []}
+        st = {"stream": named_stream(device, "wgrad%d" % LANE), "busy": False, "events": []}
         _side[key] = st
     return st
 
@@ -625,6 +643,7 @@ def gn_apply(x, G, stats, gamma, beta, out):
 
 S2D_MIN_VOXELS = int(_os.environ.get("RTP_S2D_MIN_VOXELS", 1 << 20))
 S2D_DGRAD_PAIR = not bool(_os.environ.get("RTP_NO_PAIR"))
+USE_WGRAD_S2D = not bool(_os.environ.get("RTP_NO_WGRAD_S2D"))  # plane-streaming weight gradient over the s2d view (csrc/wgrad_s2d.cu)
 USE_S2D = not bool(_os.environ.get("RTP_NO_S2D"))  # stride-2 3x3x3 convs as stride-1 convs over the space-to-depth view (plane-streaming kernels)
 
 
@@ -653,6 +672,22 @@ def conv_wgrad_s2d(xs, dy, Cin, dW, accumulate=False):
         return (1, -1) if k == 0 else ((0, 0) if k == 1 else (1, 0))
     Cin8 = ceil_to(Cin, 8)
     NP = ceil_to(dy.C, 16)
+    L = lib.load()
+    if (USE_WGRAD_S2D and Cin == 32 and xs.C8 == 32 and dy.c_stride == xs.c_stride and dy.C8 * 8 >= NP
+            and xs.c_stride == xs.Z * (xs.X + 2) * (xs.Y + 2) * 8 and dW.shape[0] <= NP
+            and L.rtp_wgrad_s2d_supported(Cin, NP, xs.Z, xs.X, xs.Y)):
+        # plane-streaming kernel: X staged once per plane, the 27 (parity, offset) pairs are descriptor shifts / N halves
+        dev = xs.buf.device
+        ws = workspace(L.rtp_wgrad_s2d_workspace_bytes(NP, num_sms()), dev, "wgrads2d")
+        zero = _zero_page(4096, dev)
+        nsplit = C.c_int32(0)
+        key = ("wgrad_s2d", Cin, dy.C, 27, 2, 1, (dy.Z, dy.X, dy.Y))
+        ev = _prof_begin(key)
+        lib.call("rtp_wgrad_s2d", xs.struct(), dy.struct(), Cin, NP, zero.data_ptr(), ws.data_ptr(), C.byref(nsplit), _stream())
+        _prof_end(key, ev, 2.0 * dy.N * dy.voxels * Cin * dy.C * 27)
+        assert dW.is_contiguous()
+        lib.call("rtp_wgrad_s2d_reduce", ws.data_ptr(), nsplit.value, Cin, NP, dW.data_ptr(), dW.shape[0], int(accumulate), _stream())
+        return
     d = lib.WgradDesc()
     d.x, d.dy = xs.struct(), dy.struct()
     d.Cin, d.NP = Cin8, NP

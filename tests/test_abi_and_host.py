@@ -208,7 +208,7 @@ def test_dcn_pack_cache_is_keyed_on_tensor_identity_and_version():
     a.add_(1)  # in-place update (an optimizer step) bumps the version counter
     assert not dcn._same_tensors(k, (a, None))
     assert dcn.tc_supported(128, 128, 3, 3, 4) and not dcn.tc_supported(8, 8, 3, 3, 4) and not dcn.tc_supported(128, 512, 3, 3, 4)
-    assert dcn._tc_chunk(256, 128, 9, 64, 160, 4) == (512 << 20) // (16 * 9 * 162 * 66 * 16)
+    assert dcn._tc_chunk(256, 128, 9, 64, 160, 4) == dcn.TC_SAMPLE_BYTES // (16 * 9 * 162 * 66 * 16)
 
 
 def test_one_cycle_schedule_equals_reference_golden():

@@ -569,7 +569,20 @@ def test_stride2_conv_through_space_to_depth_view(ctx, case):
     ops.conv_wgrad_s2d(xs, dyp, Cin, gw2)            # generic kernel over the view, 27 (parity, offset) taps
     ops.conv_wgrad_s2d(xs, dyp, Cin, gw2, accumulate=True)
     torch.cuda.synchronize()
-    close(gw2, 2 * w.grad, tol=3e-3, what="s2d wgrad (gather kernel over the view)")
+    close(gw2, 2 * w.grad, tol=3e-3, what="s2d wgrad (plane-streaming kernel over the view when Cin = 32, else gather kernel)")
+    old = ops.USE_WGRAD_S2D
+    ops.USE_WGRAD_S2D = False
+    try:
+        gw3 = torch.full(wc.shape, 7.0, device="cuda")
+        ops.conv_wgrad_s2d(xs, dyp, Cin, gw3)        # generic kernel over the view, 27 (parity, offset) taps
+    finally:
+        ops.USE_WGRAD_S2D = old
+    torch.cuda.synchronize()
+    close(gw3, w.grad, tol=3e-3, what="s2d wgrad (gather kernel over the view)")
+    gw4 = torch.full(wc.shape, 7.0, device="cuda")
+    ops.conv_wgrad_s2d(xs, dyp, Cin, gw4)
+    torch.cuda.synchronize()
+    close(gw4, gw3, tol=2e-5, what="s2d wgrad: plane-streaming vs gather kernel (same bf16 operands, fp32 accumulation)")
     dxs = ops.conv_dgrad(ctx, dyp, we, 1, P8(N, 8 * Cin, grid[0] // 2, grid[1] // 2, grid[2] // 2), key=("t", case), version=0,
                          s2d_cin=Cin)
     dg, db = torch.zeros(Cin, device="cuda"), torch.zeros(Cin, device="cuda")
