@@ -457,6 +457,95 @@ __global__ void __launch_bounds__(256) upsample_bwd_yx_kernel(P8 in, P8 out, int
   }
 }
 
+// Warp-cooperative variant of upsample_bwd_yx_kernel for Y == B * Yl (B = 2, 4, 8; Yl a power of two <= 32).
+// ncu of the gather version (profiles/r02_ncu_elementwise.txt): 80 % L1/TEX throughput, 31 % DRAM — consecutive lanes
+// (consecutive yl) gathered full-resolution vectors B apart, and every vector was requested by two or three hats: ~4 L1
+// wavefronts per input vector.  Here lane l of a row group loads the B consecutive vectors [l*B, (l+1)*B) of the row — a
+// fully coalesced read, each vector requested ONCE — and the hat of yl, whose support lies inside the blocks of lanes
+// l-1, l, l+1 (tests/test_upsample_math.py), is evaluated from its own registers and warp shuffles.  The hat weights depend
+// only on (l, offset), so they are computed once per thread.  Candidates are visited in ascending d with the same fma chain as
+// the gather kernel (zero-weight candidates leave the sum unchanged), so the result is bit-identical.
+template <int B>
+__global__ void __launch_bounds__(256) upsample_bwd_yx_shfl_kernel(P8 in, P8 out, int C8, int nrows_max) {
+  extern __shared__ float4 up_smem[];  // [nrows_max][Yl][2] float4
+  const float sy = ac_scale(out.Y, in.Y), sx = ac_scale(out.X, in.X);
+  const float ix = 1.f / sx;
+  const int z = blockIdx.y, c8 = blockIdx.z % C8, n = blockIdx.z / C8;
+  const int xl0 = blockIdx.x * kTXL, xl1 = min(out.X, xl0 + kTXL) - 1;
+  int r0, r1, tmp;
+  hat_range(xl0, in.X, sx, ix, r0, tmp);
+  hat_range(xl1, in.X, sx, ix, tmp, r1);
+  const int nrows = min(r1 - r0 + 1, nrows_max);
+  const int Yl = out.Y, Y = in.Y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int rpw = 32 / Yl, g = lane / Yl, l = lane - g * Yl;  // rows per warp, row group and yl of this lane
+  float wgt[3][B];
+  int srcl[3];
+#pragma unroll
+  for (int o = 0; o < 3; ++o) {
+    const int ln = l + o - 1;
+    srcl[o] = g * Yl + min(max(ln, 0), Yl - 1);
+#pragma unroll
+    for (int k = 0; k < B; ++k) {
+      const int d = ln * B + k;
+      wgt[o][k] = (ln >= 0 && ln < Yl && d < Y) ? hat_weight(d, l, sy) : 0.f;
+    }
+  }
+  const bf16* in_nc = in.ptr + n * in.n_stride + c8 * in.c_stride + in.voxel(z, r0, 0);
+  const int64_t rstride = (int64_t)in.Yp * 8;
+  for (int rb = warp * rpw; rb < nrows; rb += 8 * rpw) {
+    const int r = rb + g;
+    const bool valid = r < nrows;
+    uint4 raw[B];
+#pragma unroll
+    for (int k = 0; k < B; ++k) raw[k] = valid ? ldg16(in_nc + r * rstride + (l * B + k) * 8) : make_uint4(0u, 0u, 0u, 0u);
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+#pragma unroll
+    for (int o = 0; o < 3; ++o) {
+#pragma unroll
+      for (int k = 0; k < B; ++k) {
+        uint4 v = raw[k];
+        if (o != 1) {
+          v.x = __shfl_sync(0xffffffffu, raw[k].x, srcl[o]);
+          v.y = __shfl_sync(0xffffffffu, raw[k].y, srcl[o]);
+          v.z = __shfl_sync(0xffffffffu, raw[k].z, srcl[o]);
+          v.w = __shfl_sync(0xffffffffu, raw[k].w, srcl[o]);
+        }
+        float f[8];
+        unpack8(v, f);
+        const float w = wgt[o][k];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[q] = fmaf(w, f[q], acc[q]);
+      }
+    }
+    if (valid) {
+      up_smem[2 * (r * Yl + l)] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      up_smem[2 * (r * Yl + l) + 1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    }
+  }
+  __syncthreads();
+  bf16* out_nc = out.ptr + n * out.n_stride + c8 * out.c_stride;
+  const int nxl = xl1 - xl0 + 1;
+  for (int i = threadIdx.x; i < nxl * Yl; i += blockDim.x) {
+    const int xi = i / Yl, yl = i - xi * Yl, xl = xl0 + xi;
+    int lo, hi;
+    hat_range(xl, in.X, sx, ix, lo, hi);
+    hi = min(hi, r0 + nrows - 1);
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    for (int d = lo; d <= hi; ++d) {
+      const float w = hat_weight(d, xl, sx);
+      const float4 a = up_smem[2 * ((d - r0) * Yl + yl)], b = up_smem[2 * ((d - r0) * Yl + yl) + 1];
+      acc[0] = fmaf(w, a.x, acc[0]); acc[1] = fmaf(w, a.y, acc[1]); acc[2] = fmaf(w, a.z, acc[2]); acc[3] = fmaf(w, a.w, acc[3]);
+      acc[4] = fmaf(w, b.x, acc[4]); acc[5] = fmaf(w, b.y, acc[5]); acc[6] = fmaf(w, b.z, acc[6]); acc[7] = fmaf(w, b.w, acc[7]);
+    }
+    stg16(out_nc + out.voxel(z, xl, yl), pack8(acc));
+  }
+}
+
 // dst (=|+=) src [* (mask > 0)]
 __global__ void __launch_bounds__(256) grad_add_kernel(P8 src, P8 mask, int has_mask, P8 dst, int accumulate) {
   const int c8 = blockIdx.y, n = blockIdx.z;
@@ -570,8 +659,17 @@ extern "C" int rtp_upsample_bwd(rtp_p8 dout, rtp_p8 dlow, int32_t C, int32_t acc
       cudaFuncSetAttribute(upsample_bwd_yx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       configured = smem;
     }
-    upsample_bwd_yx_kernel<<<dim3((unsigned)ceil_div(t2.X, kTXL), (unsigned)t2.Z, (unsigned)(t2.N * C8)), 256, smem, (cudaStream_t)stream>>>(
-        P8(dout), P8(t2), C8, nrows_max);
+    static const bool no_shfl = getenv("RTP_NO_UPBWD_SHFL") != nullptr;  // A/B switch
+    const int Bq = dlow.Y > 0 ? dout.Y / dlow.Y : 0;
+    const bool pow2 = (dlow.Y & (dlow.Y - 1)) == 0;
+    const dim3 grid((unsigned)ceil_div(t2.X, kTXL), (unsigned)t2.Z, (unsigned)(t2.N * C8));
+    if (!no_shfl && smem <= 48 * 1024 && pow2 && dlow.Y <= 32 && dlow.Y >= 4 && Bq * dlow.Y == dout.Y && (Bq == 2 || Bq == 4)) {
+      // (B = 8 — 24 candidate vectors per output, 103 registers — measured slower than the gather kernel: 0.103 vs 0.083 ms)
+      if (Bq == 2) upsample_bwd_yx_shfl_kernel<2><<<grid, 256, smem, (cudaStream_t)stream>>>(P8(dout), P8(t2), C8, nrows_max);
+      else upsample_bwd_yx_shfl_kernel<4><<<grid, 256, smem, (cudaStream_t)stream>>>(P8(dout), P8(t2), C8, nrows_max);
+    } else {
+      upsample_bwd_yx_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(P8(dout), P8(t2), C8, nrows_max);
+    }
   } else {
     launch(dout, t1, 2, 0);
     launch(t1, t2, 1, 0);

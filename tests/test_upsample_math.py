@@ -67,3 +67,20 @@ def test_candidate_range_is_complete_and_tile_bound_holds(n_lo, n_hi):
     for l0 in range(0, n_lo, kTXL):
         l1 = min(n_lo, l0 + kTXL) - 1
         assert ranges[l1][1] - ranges[l0][0] + 1 <= nrows_max - 1, (l0, l1, ranges[l0], ranges[l1], nrows_max)
+
+
+@pytest.mark.parametrize("n_lo,B", [(32, 2), (16, 4), (8, 8), (16, 2), (8, 4), (8, 2), (4, 4), (4, 2), (4, 8), (32, 4), (32, 8)])
+def test_hat_support_lies_in_the_blocks_of_the_neighbouring_lanes(n_lo, B):
+    """upsample_bwd_yx_shfl_kernel (Y == B * Yl): lane l holds the B high-resolution vectors [l*B, (l+1)*B) of a row and
+    evaluates the hat of source index l from its own block and the blocks of lanes l-1 and l+1 — every destination with a
+    non-zero weight must lie in [(l-1)*B, (l+2)*B), and visiting those candidates in ascending order with the hat weight
+    itself (zero outside the hat) reproduces the exact candidate range of the gather kernel."""
+    n_hi = n_lo * B
+    scale = ac_scale(n_lo, n_hi)
+    for l in range(n_lo):
+        nz = [d for d in range(n_hi) if hat_weight(d, l, scale) > 0]
+        assert nz[0] >= (l - 1) * B and nz[-1] < (l + 2) * B, (n_lo, B, l, nz)
+        lo, hi = hat_range(l, n_hi, scale)
+        cand = [d for d in range(max(0, (l - 1) * B), min(n_hi, (l + 2) * B))]
+        assert [d for d in cand if hat_weight(d, l, scale) > 0] == nz
+        assert all(hat_weight(d, l, scale) == 0 for d in cand if d < lo or d > hi)
