@@ -39,6 +39,12 @@ for L in lanes_list:
         lib.call("rtp_ingest_pack", rw.data_ptr(), nb, in_ch, *bench.RAW_SHAPE, *bench.ROI0, float(a), float(b - a),
                  1 if norm is not None else 0, xin.struct(), None, _stream())
         tgt = targets.assign_device(ps, bench.GRID, one_hm=(ncls == 1), min_radius=2 if ncls == 1 else 1)
+        if os.environ.get("FWD_ONLY"):  # forward (with tape) + loss only: how much of the FORWARD pass hides under the other lane
+            hm, rg = eng.forward(xin, True)
+            out = eng.loss(hm, rg, tgt["hm"], tgt["ind"], tgt["mask"], tgt["cat"], tgt["anno_pose"])
+            eng.tape = []
+            ops.LANE = 0
+            return out
         hm, rg = eng.forward(xin, True)
         out = eng.loss(hm, rg, tgt["hm"], tgt["ind"], tgt["mask"], tgt["cat"], tgt["anno_pose"])
         eng.backward(grads)
