@@ -238,6 +238,12 @@ def build_params(cfg, device):
     entries = [("backbone." + n, s, i) for n, s, i in spec.backbone_spec(arch, fin, fout)]
     heads = {"reg": (reg, 2), "hm": (ncls, 2)}
     entries += [("pose_head." + n, s, i) for n, s, i in spec.head_spec(fout if fuse != "top" else 32, fout if fuse != "top" else 32, heads)]
+    # reg.0 and hm.0 are evaluated as one merged conv: place their weights (and biases) next to each other in the flat buffer,
+    # so the merged operand is a view of it (engine._adjacent_cat) instead of a per-step torch.cat
+    order = {"pose_head.tasks.0.reg.0.weight": 0, "pose_head.tasks.0.hm.0.weight": 1, "pose_head.tasks.0.reg.0.bias": 2,
+             "pose_head.tasks.0.hm.0.bias": 3}
+    tail = sorted((e for e in entries if e[0] in order), key=lambda e: order[e[0]])
+    entries = [e for e in entries if e[0] not in order] + tail
     total = sum(int(np.prod(s)) for _, s, _ in entries)
     flat = torch.empty(total, dtype=torch.float32, device=device)
     gflat = torch.zeros(total, dtype=torch.float32, device=device)

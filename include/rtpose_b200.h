@@ -135,6 +135,10 @@ int rtp_conv_multi(const rtp_conv_desc* descs, int32_t n, void* stream);
  * processed in z-chunks of 512/NPo planes.  gn_sums is reserved (must be NULL in this version). */
 int rtp_weight_pack_k3s1(const float* w, void* dst_bf16, int32_t Cout, int32_t Cin, int32_t KP, int32_t NPo,
                          int32_t transpose_flip, void* stream);
+/* The same pack for the window [ci0, ci0 + ci_n) of the weight's input channels (w is [Cout][Cin_total][3][3][3]): the
+ * per-group packs of the space-to-depth dgrad, without materialising the slice. */
+int rtp_weight_pack_k3s1_window(const float* w, void* dst_bf16, int32_t Cout, int32_t Cin_total, int32_t ci0, int32_t ci_n,
+                                int32_t KP, int32_t NPo, int32_t transpose_flip, void* stream);
 typedef struct {
   rtp_p8 in, out, res, mask;
   const void* w;

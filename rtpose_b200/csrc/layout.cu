@@ -153,7 +153,9 @@ __global__ void __launch_bounds__(256) ingest_kernel(const __half* __restrict__ 
 constexpr int kIngY = 8, kIngXMax = 176;  // rows per block; widest ROI handled (vectors cover <= kIngXMax + 8 halves)
 __global__ void __launch_bounds__(256) ingest_vec_kernel(const __half* __restrict__ raw, int D, int RZ, int RY, int RX,
                                                          int z0, int y0, int x0, float a, float scale, int normalize, P8 t) {
-  __shared__ __align__(16) bf16 tile[8][kIngY][kIngXMax + 16];
+  // row pitch 200 halves = 400 B: 16-byte aligned for the vector stores, and 100 words % 32 = 4, so the 8 lanes that read the
+  // same x of 8 consecutive rows in the write phase hit 8 different banks (a 192-half pitch put them all in one)
+  __shared__ __align__(16) bf16 tile[8][kIngY][kIngXMax + 24];
   const int yt = blockIdx.x * kIngY;
   int b = blockIdx.y;
   const int z = b % t.Z;
@@ -256,8 +258,10 @@ extern "C" int rtp_weight_pack(const float* w, void* dst_bf16, int32_t Cout, int
 // (block order [kz=2 | kz=1 | kz=0] so the three TMEM accumulator blocks of output planes z-1, z, z+1 are
 // contiguous).  In-plane tap index t9 = kx*3 + ky (x is the slow in-plane axis of the P8 layout).
 // transpose_flip = 1 builds the dgrad operand: K = Cout, N = Cin, taps mirrored.
+// (Cin_total, ci0): the pack may cover a window [ci0, ci0 + Cin) of the weight's input channels (a group of the
+// space-to-depth dgrad) without the caller materialising the slice.
 __global__ void weight_pack_k3s1_kernel(const float* __restrict__ w, bf16* __restrict__ dst, int Cout, int Cin, int KP,
-                                        int NPo, int tf) {
+                                        int NPo, int tf, int Cin_total, int ci0) {
   const int N3 = 3 * NPo;
   const int64_t total = (int64_t)9 * KP * N3;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -273,20 +277,29 @@ __global__ void weight_pack_k3s1_kernel(const float* __restrict__ w, bf16* __res
     int co, ci;
     if (!tf) { ci = k; co = nn; } else { co = k; ci = nn; kz = 2 - kz; ky = 2 - ky; kx = 2 - kx; }
     float v = 0.f;
-    if (co < Cout && ci < Cin) v = w[((int64_t)co * Cin + ci) * 27 + (kz * 3 + ky) * 3 + kx];
+    if (co < Cout && ci < Cin) v = w[((int64_t)co * Cin_total + ci0 + ci) * 27 + (kz * 3 + ky) * 3 + kx];
     dst[i] = __float2bfloat16(v);
   }
 }
-extern "C" int rtp_weight_pack_k3s1(const float* w, void* dst_bf16, int32_t Cout, int32_t Cin, int32_t KP, int32_t NPo,
-                                    int32_t transpose_flip, void* stream) {
+static int weight_pack_k3s1_launch(const float* w, void* dst_bf16, int Cout, int Cin, int KP, int NPo, int transpose_flip,
+                                   int Cin_total, int ci0, void* stream) {
   RTP_CHECK_ARG(w && dst_bf16, "rtp_weight_pack_k3s1: null pointer");
   RTP_CHECK_ARG(KP % 16 == 0 && NPo % 16 == 0 && 3 * NPo <= 256, "rtp_weight_pack_k3s1: bad KP/NPo");
   RTP_CHECK_ARG(transpose_flip ? (Cout <= KP && Cin <= NPo) : (Cin <= KP && Cout <= NPo),
                 "rtp_weight_pack_k3s1: padding too small");
+  RTP_CHECK_ARG(ci0 >= 0 && Cin >= 1 && ci0 + Cin <= Cin_total, "rtp_weight_pack_k3s1: bad input-channel window");
   const int64_t total = (int64_t)9 * KP * 3 * NPo;
   weight_pack_k3s1_kernel<<<ceil_div(total, 256) > 1024 ? 1024 : ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      w, (bf16*)dst_bf16, Cout, Cin, KP, NPo, transpose_flip);
+      w, (bf16*)dst_bf16, Cout, Cin, KP, NPo, transpose_flip, Cin_total, ci0);
   RTP_LAUNCH_CHECK();
+}
+extern "C" int rtp_weight_pack_k3s1(const float* w, void* dst_bf16, int32_t Cout, int32_t Cin, int32_t KP, int32_t NPo,
+                                    int32_t transpose_flip, void* stream) {
+  return weight_pack_k3s1_launch(w, dst_bf16, Cout, Cin, KP, NPo, transpose_flip, Cin, 0, stream);
+}
+extern "C" int rtp_weight_pack_k3s1_window(const float* w, void* dst_bf16, int32_t Cout, int32_t Cin_total, int32_t ci0,
+                                           int32_t ci_n, int32_t KP, int32_t NPo, int32_t transpose_flip, void* stream) {
+  return weight_pack_k3s1_launch(w, dst_bf16, Cout, ci_n, KP, NPo, transpose_flip, Cin_total, ci0, stream);
 }
 
 // ---------------------------------------------------------------------------------------------- space-to-depth weights

@@ -23,6 +23,16 @@ ARCH = {  # det3d/models/backbones/hrnet3D_config.py:85-177 — (input planes, p
 }
 
 
+def _adjacent_cat(a, b):
+    """cat([a, b], 0) of two parameters — as a VIEW when b starts where a ends in the same storage (flat-buffer trainers,
+    bench.build_params places the two merged head convs next to each other), else a copy (torch.cat)."""
+    a, b = a.detach(), b.detach()
+    if (a.is_contiguous() and b.is_contiguous() and a.untyped_storage().data_ptr() == b.untyped_storage().data_ptr()
+            and a.storage_offset() + a.numel() == b.storage_offset() and a.shape[1:] == b.shape[1:]):
+        return torch.as_strided(a, (a.shape[0] + b.shape[0],) + tuple(a.shape[1:]), a.stride())
+    return torch.cat([a, b], 0).contiguous()
+
+
 class Engine:
     def __init__(self, arch, final_fuse, params, reg_channels, num_classes, loss_weight, code_weights,
                  prefix_backbone="backbone.", prefix_head="pose_head."):
@@ -449,8 +459,8 @@ class Engine:
         if ph + "shared_conv.1.weight" in p:
             f = self.gn_conv(f, ph + "shared_conv.0", ph + "shared_conv.1", 3, 1, True, train=train)
         q = ph + "tasks.0."
-        w0 = torch.cat([p[q + "reg.0.weight"].detach(), p[q + "hm.0.weight"].detach()], 0).contiguous()
-        b0 = torch.cat([p[q + "reg.0.bias"].detach(), p[q + "hm.0.bias"].detach()], 0).contiguous()
+        w0 = _adjacent_cat(p[q + "reg.0.weight"], p[q + "hm.0.weight"])
+        b0 = _adjacent_cat(p[q + "reg.0.bias"], p[q + "hm.0.bias"])
         hc = p[q + "reg.0.weight"].shape[0]
         wkey = ("merged_head", p[q + "reg.0.weight"].data_ptr(), p[q + "hm.0.weight"].data_ptr())
         wver = (p[q + "reg.0.weight"]._version, p[q + "hm.0.weight"]._version)
@@ -480,14 +490,9 @@ class Engine:
                 gw_r, acc_r = self._pgrad(q + "reg.0.weight")
                 gw_h, acc_h = self._pgrad(q + "hm.0.weight")
                 ops.conv_wgrad_async(f, tg, 3, 1, gw_r, accumulate=acc_r, n0=0, more=((gw_h, acc_h, 0, hc),))
-                gball = torch.empty(2 * hc, dtype=torch.float32, device=f.buf.device)
-                ops.channel_sum(tg, gball)
                 for name, c0 in (("reg", 0), ("hm", hc)):
                     gb, accb = self._pgrad(q + name + ".0.bias")
-                    if accb:
-                        gb.add_(gball[c0:c0 + hc])
-                    else:
-                        gb.copy_(gball[c0:c0 + hc])
+                    ops.channel_sum(tg.channels(c0, hc), gb, accumulate=accb)
                 gf, accf = self._grad_of(f)
                 ops.conv_dgrad(self.packs, tg, w0, 1, gf, mask=f if f.relu_out else None, accumulate=accf, key=wkey,
                                version=wver)

@@ -72,6 +72,7 @@ PROTOTYPES = {
     "rtp_conv": (C.c_int, [C.POINTER(ConvDesc), _vp]),
     "rtp_conv_multi": (C.c_int, [C.POINTER(ConvDesc), _i32, _vp]),
     "rtp_weight_pack_k3s1": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "rtp_weight_pack_k3s1_window": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "rtp_conv_k3s1": (C.c_int, [C.POINTER(ConvK3S1Desc), _vp]),
     "rtp_conv_k3s1_smem_bytes": (C.c_int64, [_i32, _i32, _i32, _i32, _i32]),
     "rtp_conv_k3s1_stat_ws_bytes": (C.c_int64, [_i32]),
@@ -176,7 +177,7 @@ def require_device():
 
 # kernels launched per C-ABI call (for the bench's `gpu_launches` claim)
 LAUNCHES = {"rtp_pack_ncdhw": 1, "rtp_unpack_ncdhw": 1, "rtp_ingest_pack": 1, "rtp_weight_pack": 1,
-            "rtp_weight_pack_k3s1": 1, "rtp_conv": 1, "rtp_conv_k3s1": 1, "rtp_wgrad": 1, "rtp_wgrad_reduce": 1,
+            "rtp_weight_pack_k3s1": 1, "rtp_weight_pack_k3s1_window": 1, "rtp_conv": 1, "rtp_conv_k3s1": 1, "rtp_wgrad": 1, "rtp_wgrad_reduce": 1,
             "rtp_gn_sums": 2, "rtp_gn_finalize": 1, "rtp_gn_apply": 1, "rtp_gn_bwd_reduce": 2, "rtp_gn_bwd_apply": 1,
             "rtp_fuse_sum": 1, "rtp_upsample_bwd": 2, "rtp_grad_add": 1, "rtp_channel_sum": 2, "rtp_stem_fwd": 1,
             "rtp_stem_bwd": 2, "rtp_head_loss": 2, "rtp_decode": 1, "rtp_scale_f32": 1, "rtp_dcn_fwd": 1,

@@ -165,10 +165,11 @@ class PackedWeights:
         self._store(key, w, ver, val, explicit, repack)
         return val
 
-    def get_k3s1(self, w, K, NPo, transpose_flip, key=None, version=None):
-        """kz-stacked pack for the plane-streaming kernel: [9][K/8][3*NPo][8]."""
+    def get_k3s1(self, w, K, NPo, transpose_flip, key=None, version=None, ci_window=None):
+        """kz-stacked pack for the plane-streaming kernel: [9][K/8][3*NPo][8].  ci_window = (ci0, ci_n): pack only that
+        window of w's input channels (w stays the full, contiguous weight: no slice is materialised)."""
         explicit = key is not None
-        key = (key if explicit else w.data_ptr(), "k3s1", bool(transpose_flip), K, NPo, tuple(w.shape))
+        key = (key if explicit else w.data_ptr(), "k3s1", bool(transpose_flip), K, NPo, tuple(w.shape), ci_window)
         ver = version if version is not None else w._version
         val, old = self._lookup(key, w, ver, explicit)
         if val is not None:
@@ -178,6 +179,10 @@ class PackedWeights:
 
         def repack(src):
             wc = src.detach().contiguous()
+            if ci_window is not None:
+                lib.call("rtp_weight_pack_k3s1_window", wc.data_ptr(), dst.data_ptr(), shape[0], shape[1], ci_window[0], ci_window[1],
+                         K, NPo, int(bool(transpose_flip)), _stream())
+                return
             lib.call("rtp_weight_pack_k3s1", wc.data_ptr(), dst.data_ptr(), shape[0], shape[1], K, NPo,
                      int(bool(transpose_flip)), _stream())
         repack(w)
@@ -359,13 +364,15 @@ def s2d_tap_mask(par, flipped):
 
 
 def conv_k3s1(packs, x, w, out, transpose_flip, bias=None, relu=False, res=None, mask=None, accumulate=False, key=None,
-              version=None, stat=None, tap_mask=None):
+              version=None, stat=None, tap_mask=None, ci_window=None):
     """Plane-streaming 3x3x3 s1 conv (forward: transpose_flip=False; dgrad: True).
     stat: None | ("stats", G, eps) -> returns (out, stats[N][G][2]) of the stored result (GroupNorm forward)
                | ("red", G, x_gn, stats) -> returns (out, red[N][C][2]) (GroupNorm backward reductions, out = dL/dxn)."""
     Cout, Cin = w.shape[0], w.shape[1]
+    if ci_window is not None:  # dgrad of a group of input channels: the GEMM N is the window
+        Cin = ci_window[1]
     K, NPo = (ceil_to(Cin, 16), ceil_to(Cout, 16)) if not transpose_flip else (ceil_to(Cout, 16), ceil_to(Cin, 16))
-    wp = packs.get_k3s1(w, K, NPo, transpose_flip, key, version)
+    wp = packs.get_k3s1(w, K, NPo, transpose_flip, key, version, ci_window)
     d = lib.ConvK3S1Desc()
     d.inp, d.out = x.struct(), out.struct()
     d.res = res.struct() if res is not None else lib.NULL_P8
@@ -461,10 +468,10 @@ def conv_dgrad(packs, dy, w, stride, dx, mask=None, accumulate=False, ci0=0, ci_
                 for par in set((c // s2d_cin) for c in range(g * gs, (g + 1) * gs, 8)):
                     tm |= s2d_tap_mask(par, True)
                 tm = [tm]
-            conv_k3s1(packs, dy, w[:, g * gs:(g + 1) * gs], dx.channels(g * gs, gs), True,
+            conv_k3s1(packs, dy, w, dx.channels(g * gs, gs), True,
                       mask=mask.channels(g * gs, gs) if mask is not None else None, accumulate=accumulate,
                       key=(key if key is not None else w.data_ptr(), "dgrad_group", gs, g),
-                      version=version if version is not None else w._version, tap_mask=tm)
+                      version=version if version is not None else w._version, tap_mask=tm, ci_window=(g * gs, gs))
         return dx
     wp, KP, NP = packs.get(w, 1, ci0, ci_n, key, version)
     real = (w.shape[0], ci_n if ci_n is not None else w.shape[1])
