@@ -55,6 +55,7 @@ struct K3 {
   //   2: sum v, sum v*aux      (GroupNorm backward: v = dL/d(normalised x), aux = x)
   P8 stat_aux;
   float* stat_ws;  // [grid*8 warp slabs][N][64] then [grid CTA slabs][N][64]
+  uint32_t pre_off;      // LANES = 2: byte offset (dynamic smem) of the per-thread residual / aux prefetch ring, 0 = off
   uint16_t tapmask[32];  // per K pass: bit t9 set = in-plane tap t9 has non-zero weights (structurally sparse weights)
 };
 
@@ -277,6 +278,17 @@ __global__ void __launch_bounds__(LANES == 2 ? kThreads2 : kThreads, 1) conv_k3s
       wslab = p.stat_ws + ((size_t)blockIdx.x * 8 + ewarp) * p.out.N * 64;
       for (int n = 0; n < p.out.N; ++n) reinterpret_cast<float2*>(wslab + n * 64)[lane] = make_float2(0.f, 0.f);
     }
+    // LANES = 2, opt-in (RTP_PRE_RING=1, see rtp_conv_k3s1): the residual (forward) / GroupNorm-input (dgrad statistics)
+    // vectors of the NEXT block are fetched with cp.async into a two-deep per-thread ring in shared memory while the current
+    // block is drained — an experiment against the exposed HBM latency of the register prefetch (ncu: 170 us with a residual,
+    // 139 us without).  A thread only reads back what it copied itself, so cp.async.wait_group is the only synchronisation.
+    constexpr bool kRing = LANES == 2 && STAT != 0;
+    uint4* pre_ring = nullptr;
+    bool use_ring = false;
+    if constexpr (kRing) {
+      use_ring = p.pre_off != 0 && (STAT == 2 || p.has_res);
+      pre_ring = reinterpret_cast<uint4*>(smem + p.pre_off) + (size_t)(L * 128 + r) * 8;  // [2 buffers][4 chunks]
+    }
     for (int u = blockIdx.x; u < p.nunits; u += gridDim.x) {
       int n, zc, tile;
       decode(u, n, zc, tile);
@@ -285,6 +297,21 @@ __global__ void __launch_bounds__(LANES == 2 ? kThreads2 : kThreads, 1) conv_k3s
       const int xp = q / Yp, yp = q - xp * Yp;
       const bool ok = xp >= 1 && xp <= p.out.X && yp >= 1 && yp <= p.out.Y;
       const int64_t pos = (int64_t)q * 8;
+      uint32_t rb = 0;  // ring buffer holding the CURRENT block's vectors
+      auto ring_issue = [&](int oz2, uint32_t buf) {
+        if constexpr (kRing) {
+          if (ok) {
+            const bf16* src = STAT == 2 ? p.stat_aux.ptr + (int64_t)n * p.stat_aux.n_stride + (int64_t)oz2 * p.stat_aux.plane_elems() + pos
+                                        : p.res.ptr + (int64_t)n * p.res.n_stride + (int64_t)oz2 * p.res.plane_elems() + pos;
+            const int64_t cs = STAT == 2 ? p.stat_aux.c_stride : p.res.c_stride;
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              if (c < p.out_c8) cp_async16(pre_ring + buf * 4 + c, src + c * cs, true);
+          }
+          cp_async_commit();
+        }
+      };
+      if (use_ring && zo0 + eg < zo1) ring_issue(zo0 + eg, 0);
       for (int oz = zo0 + eg; oz < zo1; oz += kEgStep) {
         const int b = oz - zo0;
         const int64_t plane = (int64_t)oz * p.out.plane_elems() + pos;
@@ -303,18 +330,38 @@ __global__ void __launch_bounds__(LANES == 2 ? kThreads2 : kThreads, 1) conv_k3s
           if constexpr (kMaskAcc) pre_mask[c] = pre_acc[c] = make_uint4(0, 0, 0, 0);
           if constexpr (STAT == 2) {
             pre_aux[c] = make_uint4(0, 0, 0, 0);
-            if (ok && c < p.out_c8)
+            if (ok && c < p.out_c8 && !use_ring)
               pre_aux[c] = ldg16(p.stat_aux.ptr + (int64_t)n * p.stat_aux.n_stride + (int64_t)oz * p.stat_aux.plane_elems() + pos +
                                  c * p.stat_aux.c_stride);
           }
           if (ok && c < p.out_c8) {
             if constexpr (kRes) {
-              if (res_row) pre_res[c] = ldg16(res_row + c * p.res.c_stride);
+              if (res_row && !use_ring) pre_res[c] = ldg16(res_row + c * p.res.c_stride);
             }
             if constexpr (kMaskAcc) {
               if (mask_row) pre_mask[c] = ldg16(mask_row + c * p.mask.c_stride);
               if (p.accumulate) pre_acc[c] = *reinterpret_cast<const uint4*>(out_row + c * p.out.c_stride);
             }
+          }
+        }
+        if constexpr (kRing) {
+          if (use_ring) {  // request the next block's vectors, then pick up this block's (requested one block ago)
+            if (oz + kEgStep < zo1) {
+              ring_issue(oz + kEgStep, rb ^ 1u);
+              cp_async_wait<1>();
+            } else {
+              cp_async_wait<0>();
+            }
+            if (ok) {
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                if (c < p.out_c8) {
+                  if constexpr (STAT == 2) pre_aux[c] = pre_ring[rb * 4 + c];
+                  else pre_res[c] = pre_ring[rb * 4 + c];
+                }
+              }
+            }
+            rb ^= 1u;
           }
         }
         mbar_wait(&bar_acc_full[b], (full_mask >> b) & 1);
@@ -471,13 +518,16 @@ __global__ void __launch_bounds__(256) stat_finalize_kernel(const float* __restr
 }
 
 struct Plan {
+  uint32_t pre_off = 0;
   int KG, npass, PW, ntile, ZC, nzc, nstages, lanes;
   uint32_t stage_bytes, wbuf_bytes;
   size_t smem;
   bool ok;
 };
 
-Plan make_plan(int K, int NPo, int Z, int X, int Y) {
+constexpr size_t kPreRingBytes = 2 * 128 * 2 * 4 * 16;  // 2 lanes x 128 epilogue rows x 2 buffers x 4 chunks x 16 B
+
+Plan make_plan(int K, int NPo, int Z, int X, int Y, bool pre_ring = false) {
   Plan pl{};
   pl.ok = false;
   if (K % 16 != 0 || NPo % 16 != 0 || NPo < 16 || 3 * NPo > 256) return pl;
@@ -502,7 +552,10 @@ Plan make_plan(int K, int NPo, int Z, int X, int Y) {
   pl.stage_bytes = (uint32_t)(KG / 8) * pl.PW * 16;
   pl.wbuf_bytes = (uint32_t)9 * KG * N3 * 2;
   const size_t wtotal = (size_t)(pl.npass > 1 ? 2 : 1) * pl.wbuf_bytes;
-  const size_t budget = 220 * 1024;
+  size_t budget = 220 * 1024;
+  // the residual / aux prefetch ring of the dual-lane kernel comes out of the stage budget (only where lanes == 2 is possible)
+  const bool ring_ok = pre_ring && pl.npass == 1 && NPo <= 32 && Z >= 2 && ((Z + 1) / 2) * NPo <= 256;
+  if (ring_ok) budget -= kPreRingBytes;
   if (wtotal + 2 * (size_t)pl.stage_bytes > budget) return pl;
   int S = (int)((budget - wtotal) / pl.stage_bytes);
   if (S > kMaxStages) S = kMaxStages;
@@ -518,6 +571,11 @@ Plan make_plan(int K, int NPo, int Z, int X, int Y) {
     pl.ZC = zc2;
     pl.nzc = 2;
     pl.nstages = S & ~1;
+    pl.smem = wtotal + (size_t)pl.nstages * pl.stage_bytes;
+    if (ring_ok) {
+      pl.pre_off = (uint32_t)pl.smem;
+      pl.smem += kPreRingBytes;
+    }
   }
   pl.ok = true;
   return pl;
@@ -540,7 +598,13 @@ extern "C" int rtp_conv_k3s1(const rtp_conv_k3s1_desc* d, void* stream) {
   RTP_CHECK_ARG(d->out_c8 >= 1 && d->out_c8 * 8 <= d->NPo + 7 && d->out_c8 <= d->out.C8, "rtp_conv_k3s1: bad out_c8");
   RTP_CHECK_ARG(d->in.c_stride == (int64_t)d->in.Z * (d->in.X + 2) * (d->in.Y + 2) * 8,
                 "rtp_conv_k3s1: input planes must be contiguous per channel chunk");
-  Plan pl = make_plan(d->Cin, d->NPo, d->in.Z, d->in.X, d->in.Y);
+  // The cp.async prefetch ring is OFF by default: measured in the step it is slower than the register prefetch (32->32:
+  // 929 vs 1016 TFLOP/s, 21.25 vs 20.99 ms per step).  RTP_PRE_RING=1 enables it (A/B).  Restructuring the epilogue for it
+  // did lower the register count of the statistics variants (157 -> 145 / 149), which is where the default path's gain over
+  // the previous build (932-984 TFLOP/s) comes from.
+  static const bool ring_on = getenv("RTP_PRE_RING") != nullptr;
+  const bool want_ring = ring_on && ((d->stat_mode == 1 && d->res.ptr != nullptr) || d->stat_mode == 2);
+  Plan pl = make_plan(d->Cin, d->NPo, d->in.Z, d->in.X, d->in.Y, want_ring);
   RTP_CHECK_ARG(pl.ok, "rtp_conv_k3s1: unsupported shape K=%d NPo=%d Z=%d X=%d Y=%d", d->Cin, d->NPo, d->in.Z, d->in.X, d->in.Y);
   K3 k;
   k.in = P8(d->in); k.out = P8(d->out); k.res = P8(d->res); k.mask = P8(d->mask);
@@ -550,6 +614,7 @@ extern "C" int rtp_conv_k3s1(const rtp_conv_k3s1_desc* d, void* stream) {
   k.KG = pl.KG; k.npass = pl.npass; k.PW = pl.PW; k.ntile = pl.ntile; k.ZC = pl.ZC; k.nzc = pl.nzc;
   k.nunits = plan_units(pl, d->in.N);
   k.nstages = pl.nstages; k.stage_bytes = pl.stage_bytes; k.wbuf_bytes = pl.wbuf_bytes;
+  k.pre_off = pl.lanes == 2 ? pl.pre_off : 0;
   k.wtap_bytes = (uint32_t)(pl.KG / 8) * k.N3 * 16;          // one tap's [KG/8][N3][8] slice
   k.wtap_stride = (uint32_t)(d->Cin / 8) * k.N3 * 16;        // distance between taps in the packed weights
   k.dbg = (long long*)d->debug;
