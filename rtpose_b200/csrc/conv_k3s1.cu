@@ -29,6 +29,13 @@ namespace {
 
 constexpr int kThreads = 320;   // LANES = 1: warp 0 producer, warp 1 MMA, warps 2-5 / 6-9 epilogue groups 0 / 1
 constexpr int kThreads2 = 384;  // LANES = 2: warps 0-1 producers, 2-3 MMA issuers, 4-7 / 8-11 the epilogue group of lane 0 / 1
+// Register cap of the dual-lane instantiations, expressed as a launch bound.  -DRTP_K3S1_DUAL_BOUND=512 compiles them to
+// <= 128 registers (no spills: 48 k of the SM's 64 k registers, room for an element-wise CTA of another stream next to the
+// persistent conv CTA); measured, it changes nothing in the step (20.99 vs 21.03 ms) and costs the kernel 1 %, so the
+// default stays at the launch size (145-149 registers).
+#ifndef RTP_K3S1_DUAL_BOUND
+#define RTP_K3S1_DUAL_BOUND 384
+#endif
 constexpr int kMaxBlocks = 32;
 constexpr int kMaxStages = 8;
 #ifdef RTP_K3S1_DEBUG
@@ -67,7 +74,7 @@ struct K3 {
 // output is still accumulated by ONE issuer in a fixed order (results stay run-to-run identical); the price is the halo
 // plane at the chunk boundary (18 instead of 16 plane loads, +8 % MMA cycles at Z = 16).  Single K pass only.
 template <int KS, int STAT, int LANES>  // KS = KG / 16: k16 steps per tap (1 or 2); STAT: fused statistics mode (0 = off)
-__global__ void __launch_bounds__(LANES == 2 ? kThreads2 : kThreads, 1) conv_k3s1_kernel(const __grid_constant__ K3 p) {
+__global__ void __launch_bounds__(LANES == 2 ? RTP_K3S1_DUAL_BOUND : kThreads, 1) conv_k3s1_kernel(const __grid_constant__ K3 p) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t bar_full_s[kMaxStages], bar_empty_s[kMaxStages], bar_wfull[2], bar_wempty[2];
   __shared__ uint64_t bar_acc_full_s[kMaxBlocks], bar_acc_empty_s[kMaxBlocks];
