@@ -259,7 +259,7 @@ def build_params(cfg, device):
 
 
 EW = {"gn_apply", "gn_backward", "fuse_sum", "upsample_bwd", "grad_add"}  # element-wise families: they record algorithmic BYTES
-TENSOR = {"conv_generic", "conv_k3s1", "conv_pw", "wgrad_generic", "wgrad_k3s1", "wgrad_s2d"}
+TENSOR = {"conv_generic", "conv_k3s1", "conv_pw", "wgrad_generic", "wgrad_k3s1", "wgrad_s2d", "wgrad_pw"}
 
 
 def ncu_traffic(kname, key, batch):

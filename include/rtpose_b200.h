@@ -259,6 +259,14 @@ int rtp_gn_bwd_apply_s2d(rtp_p8 x, rtp_p8 dy_s2d, int32_t C, int32_t G, const fl
                          int32_t accumulate_dx, int32_t relu_mask, rtp_p8 add, void* stream);
 /* w [Cout][Cin][3][3][3] fp32 -> w_s2d [Cout][8*Cin][3][3][3] fp32 (zero except the 27 matching (parity, offset) pairs),
  * and the transpose for the weight gradient: dw (=|+=) fold(dw_s2d). */
+/* Weight gradient of a 1x1x1 conv as a streaming GEMM over P8 positions (csrc/wgrad_pw.cu): dW[co][ci0+ci] (= or +=)
+ * sum dY[co] * X[ci], dW fp32 [co_n][Cin_total], x: >= Cin channels, dy: <= 128 channels, same grid, dense planes.
+ * replaces: autograd's weight gradient of the 1x1 fuse convs and of final_conv (hr_util/hr3d.py:144-158, hrnet3d.py:20). */
+int rtp_wgrad_pw_supported(int32_t Cin, int32_t Cout, int32_t Z, int32_t X, int32_t Y);
+int64_t rtp_wgrad_pw_workspace_bytes(int32_t Cin, int32_t nsm);
+int rtp_wgrad_pw(rtp_p8 x, rtp_p8 dy, int32_t Cin, const void* zero_page, float* workspace, int32_t* nsplit_out, void* stream);
+int rtp_wgrad_pw_reduce(const float* workspace, int32_t nsplit, int32_t Cin, float* dW, int32_t Cin_total, int32_t co_n,
+                        int32_t ci0, int32_t accumulate, void* stream);
 /* Weight gradient of the stride-2 conv straight from the view, plane-streaming (csrc/wgrad_s2d.cu): xs = s2d view of the
  * normalised input (8*Cin/8 chunks), dy = gradient of the conv output (same grid as the view), Cin = 32.  One persistent
  * CTA per SM writes an fp32 partial [nsplit][6][128][2*NP]; rtp_wgrad_s2d_reduce sums them in a fixed order into

@@ -594,6 +594,23 @@ def conv_wgrad(x, dy, k, stride, dW, accumulate=False, ci0=0, n0=0, more=(), tap
             and lib.load().rtp_wgrad_k3s1_supported(32, 32, x.Z, x.X, x.Y)):
         return _wgrad_k3s1(x, dy, outs)
     ci_n = x.C
+    if (taps is None and USE_WGRAD_PW and k == 1 and stride == 1 and not more and n0 == 0 and dy.C <= 128 and dy.C8 <= 16
+            and x.grid == dy.grid and _dense_planes(x) and _dense_planes(dy) and dW.shape[0] <= dy.C8 * 8
+            and lib.load().rtp_wgrad_pw_supported(ci_n, dy.C, x.Z, x.X, x.Y)):
+        # streaming GEMM over the padded positions (csrc/wgrad_pw.cu): M = dY channels, N = X channels
+        L = lib.load()
+        dev = x.buf.device
+        ws = workspace(L.rtp_wgrad_pw_workspace_bytes(ci_n, num_sms()), dev, "wgradpw")
+        zero = _zero_page(4096, dev)
+        nsplit = C.c_int32(0)
+        key = ("wgrad_pw", ci_n, dy.C, 1, 1, 1, (dy.Z, dy.X, dy.Y))
+        ev = _prof_begin(key)
+        lib.call("rtp_wgrad_pw", x.struct(), dy.struct(), ci_n, zero.data_ptr(), ws.data_ptr(), C.byref(nsplit), _stream())
+        _prof_end(key, ev, 2.0 * dy.N * dy.voxels * ci_n * dy.C)
+        assert dW.is_contiguous()
+        lib.call("rtp_wgrad_pw_reduce", ws.data_ptr(), nsplit.value, ci_n, dW.data_ptr(), dW.shape[1], dW.shape[0], ci0, int(accumulate),
+                 _stream())
+        return
     Cin8 = ceil_to(ci_n, 8)
     NP = ceil_to(dy.C, 16)
     taps = taps_fwd(k) if taps is None else taps
@@ -650,6 +667,7 @@ def gn_apply(x, G, stats, gamma, beta, out):
 
 S2D_MIN_VOXELS = int(_os.environ.get("RTP_S2D_MIN_VOXELS", 1 << 20))
 S2D_DGRAD_PAIR = not bool(_os.environ.get("RTP_NO_PAIR"))
+USE_WGRAD_PW = not bool(_os.environ.get("RTP_NO_WGRAD_PW"))    # streaming 1x1 weight gradient (csrc/wgrad_pw.cu)
 USE_WGRAD_S2D = not bool(_os.environ.get("RTP_NO_WGRAD_S2D"))  # plane-streaming weight gradient over the s2d view (csrc/wgrad_s2d.cu)
 USE_S2D = not bool(_os.environ.get("RTP_NO_S2D"))  # stride-2 3x3x3 convs as stride-1 convs over the space-to-depth view (plane-streaming kernels)
 

@@ -734,3 +734,37 @@ def test_full_size_stride2_s2d_agrees_with_gather_kernels(ctx):
     close(dx1.to_ncdhw(), dx2.to_ncdhw(), tol=2 * BF16_ULP, what="s2 dgrad + GN backward: s2d vs gather")
     close(dg1, dg2, tol=1e-3, what="dgamma")
     close(db1, db2, tol=1e-3, what="dbeta")
+
+
+@pytest.mark.parametrize("case", [(2, 32, 128, (3, 20, 18)), (1, 64, 128, (2, 14, 30)), (2, 32, 32, (4, 16, 14)), (1, 40, 24, (2, 14, 16))],
+                         ids=str)
+def test_pointwise_wgrad_streaming_kernel(case):
+    """rtp_wgrad_pw (1x1x1 weight gradient as a streaming GEMM over the padded positions) against torch and against the
+    gather kernel, with the final-conv style input-channel offset (ci0) and accumulation."""
+    from rtpose_b200 import lib, ops
+    N, Cin, Cout, grid = case
+    x = rnd(N, Cin, *grid, seed=21)
+    dy = rnd(N, Cout, *grid, seed=22)
+    w = torch.zeros(Cout, Cin, 1, 1, 1, requires_grad=True)
+    F.conv3d(x, w).backward(dy)
+    xp, dyp = to_p8(x), to_p8(dy)
+    assert lib.load().rtp_wgrad_pw_supported(Cin, Cout, *[grid[0], grid[2], grid[1]]) == 1
+    lib.call_counts.clear()
+    big = torch.full((Cout, Cin + 24, 1, 1, 1), 3.0, device="cuda")
+    ops.conv_wgrad(xp, dyp, 1, 1, big, ci0=16)
+    ops.conv_wgrad(xp, dyp, 1, 1, big, ci0=16, accumulate=True)
+    torch.cuda.synchronize()
+    assert lib.call_counts.get("rtp_wgrad_pw", 0) == 2
+    close(big[:, 16:16 + Cin], 2 * w.grad, tol=2e-3, what="streaming 1x1 wgrad (ci0, accumulate)")
+    assert float((big[:, :16] - 3.0).abs().max()) == 0 and float((big[:, 16 + Cin:] - 3.0).abs().max()) == 0
+    old = ops.USE_WGRAD_PW
+    ops.USE_WGRAD_PW = False
+    try:
+        ref = torch.zeros((Cout, Cin, 1, 1, 1), device="cuda")
+        ops.conv_wgrad(xp, dyp, 1, 1, ref)
+    finally:
+        ops.USE_WGRAD_PW = old
+    got = torch.zeros((Cout, Cin, 1, 1, 1), device="cuda")
+    ops.conv_wgrad(xp, dyp, 1, 1, got)
+    torch.cuda.synchronize()
+    close(got, ref, tol=2e-5, what="streaming vs gather 1x1 wgrad (same bf16 operands)")
