@@ -280,6 +280,26 @@ int rtp_wgrad_s2d_reduce(const float* workspace, int32_t nsplit, int32_t Cin, in
                          int32_t accumulate, void* stream);
 int rtp_weight_s2d_expand(const float* w, float* w_s2d, int32_t Cout, int32_t Cin, void* stream);
 int rtp_weight_s2d_fold(const float* dw_s2d, float* dw, int32_t Cout, int32_t Cin, int32_t accumulate, void* stream);
+/* Sibling stride-2 fuse convs that read the same tensor (fuse_layers[i][0][0], i = 1..3, of one HighResolutionModule,
+ * hr_util/hr3d.py:159-203: each is GroupNorm -> Conv3d(stride 2) on the full-resolution branch) share ONE space-to-depth
+ * view of xhat = (x - mean) * rstd (rtp_gn_apply_s2d with gamma = 1, beta = 0); the GroupNorm affine of each sibling is folded
+ * into its conv (csrc/s2d_shared.cu):
+ *   rtp_s2d_fold_weights: w_s2d = expand(W * diag(gamma)) [Cout][8*Cin][27]; bias_cls[8][Cout] = the beta term per border
+ *     class (bit 2: zo == 0, bit 1: xo == 0, bit 0: yo == 0 — the output positions whose k = 0 taps leave the volume);
+ *   rtp_s2d_border_bias: r (P8, N = 1, broadcast over samples through n_stride = 0 as the conv's `res`) =
+ *     bias_cls[class(pos)][c] - bias_cls[0][c]; bias_cls[0] goes in as the conv's per-channel bias;
+ *   rtp_s2d_fold_wgrad: from dw_xhat = wgrad(xhat view, dy) and the box sums of dy (workspace >=
+ *     rtp_s2d_box_sums_workspace_bytes(N, ceil(Cout/8))): dW (=|+=) gamma*dw_xhat + beta*T, dgamma (=|+=) sum W*dw_xhat,
+ *     dbeta (=|+=) sum W*T, with T[co][tap] = sum of dy[co] over the positions whose tap is inside the volume.
+ * The siblings' dgrads (gamma-folded weights) accumulate into one dL/dxhat view and ONE rtp_gn_bwd_*_s2d call with
+ * gamma = 1 (dgamma = dbeta = NULL) produces dL/dx.  replaces: autograd through those GroupNorm + Conv3d pairs. */
+int rtp_s2d_fold_weights(const float* w, const float* gamma, const float* beta, float* w_s2d, float* bias_cls, int32_t Cout,
+                         int32_t Cin, void* stream);
+int rtp_s2d_border_bias(const float* bias_cls, rtp_p8 r, int32_t C, void* stream);
+int64_t rtp_s2d_box_sums_workspace_bytes(int32_t N, int32_t C8);
+int rtp_s2d_fold_wgrad(rtp_p8 dy, const float* dw_xhat, const float* w, const float* gamma, const float* beta, float* workspace,
+                       float* dW, float* dgamma, float* dbeta, int32_t Cout, int32_t Cin, int32_t accumulate_w,
+                       int32_t accumulate_gb, void* stream);
 
 /* ---- branch exchange ---------------------------------------------------------------------------------------
  * replaces: the fuse sum of HighResolutionModule.forward (hr_util/hr3d.py:213-227) and the upsample+cat of

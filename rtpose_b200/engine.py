@@ -62,6 +62,7 @@ class Engine:
         self.fold_grad_adds = not os.environ.get("RTP_NO_FOLD_ADDS")  # residual / fuse-sum gradient pass-throughs ride in the next GroupNorm backward (_defer_add)
         self._last_touch, self._closure_idx = {}, -1
         self._grad_groups, self._on_ready, self._milestones = None, None, None
+        self._s2d_share, self._s2d_scratch, self._unit_affine = {}, {}, {}
         self.generation = 0  # bumped by begin(): a backward job checks that the tape it recorded is still the live one
 
     # ------------------------------------------------------------------ helpers
@@ -233,6 +234,75 @@ class Engine:
             self.tape.append(bwd)
         return y
 
+    def _s2d_share_prepare(self, x, n_sib):
+        """One space-to-depth view of xhat = (x - mean) * rstd for the `n_sib` stride-2 fuse convs that read x (their
+        GroupNorms share x's statistics; the affine of each is folded into its conv, csrc/s2d_shared.cu)."""
+        dev = x.buf.device
+        G = 8 if x.C >= 8 else 1
+        stats = self._stats_get(x)
+        if stats is None:
+            stats = ops.gn_stats(x, G)
+            self._stats_put(x, stats)
+        key = (x.C, str(dev))
+        if key not in self._unit_affine:
+            self._unit_affine[key] = (torch.ones(x.C, dtype=torch.float32, device=dev),
+                                      torch.zeros(x.C, dtype=torch.float32, device=dev))
+        ones, zeros = self._unit_affine[key]
+        V = self.pool.get(x.N, 8 * x.C, x.Z // 2, x.Y // 2, x.X // 2, dev)
+        ops.gn_apply_s2d(x, G, stats, ones, zeros, V)
+        return {"x": x, "V": V, "G": G, "stats": stats, "ones": ones, "dV": None, "left": n_sib}
+
+    def _gn_conv_s2d_shared(self, grp, gn, conv, relu, train):
+        """ReLU?( conv3x3x3_stride2( GroupNorm(x) ) ) for one of the sibling fuse convs of grp["x"], reading the shared view:
+        y = conv_{W diag(gamma)}(xhat view) + border-class bias (the beta term).  Backward: the weight gradient over xhat gives
+        dW / dgamma / dbeta (rtp_s2d_fold_wgrad), the dgrads of the siblings accumulate into one dL/dxhat view, and the last
+        sibling to run its closure issues the single GroupNorm backward into x."""
+        p = self.p
+        x, V = grp["x"], grp["V"]
+        dev = x.buf.device
+        gamma, beta, w = p[gn + ".weight"], p[gn + ".bias"], p[conv + ".weight"]
+        Cout, Cin = w.shape[0], w.shape[1]
+        sc = self._s2d_scratch.get((conv, str(dev)))
+        if sc is None:
+            sc = (torch.empty((Cout, 8 * Cin, 3, 3, 3), dtype=torch.float32, device=dev),
+                  torch.empty((8, Cout), dtype=torch.float32, device=dev),
+                  torch.empty((Cout, Cin, 3, 3, 3), dtype=torch.float32, device=dev))
+            self._s2d_scratch[(conv, str(dev))] = sc
+        we, bias_cls, dwp = sc
+        ops.s2d_fold_weights(w, gamma, beta, we, bias_cls)
+        y = self.pool.get(x.N, Cout, V.Z, V.Y, V.X, dev)
+        r1 = self.pool.get(1, Cout, V.Z, V.Y, V.X, dev)
+        ops.s2d_border_bias(bias_cls, r1, Cout)
+        rb = P8(x.N, Cout, V.Z, V.Y, V.X, buf=r1.buf, offset=r1.offset, n_stride=0, c_stride=r1.c_stride)
+        wkey, wver = ("s2dgn", w.data_ptr()), (w._version, gamma._version, beta._version)
+        ops.conv_forward(self.packs, V, we, 1, y, bias=bias_cls[0], relu=relu, res=rb, key=wkey, version=wver,
+                         tap_mask=[ops.s2d_tap_mask(par, False) for par in range(8)])
+        y.relu_out = bool(relu)
+        if train:
+            def bwd():
+                grp["left"] -= 1
+                dy = self._g(y)
+                if dy is not None:
+                    gw, accw = self._pgrad(conv + ".weight")
+                    gg, accg = self._pgrad(gn + ".weight")
+                    gb, _ = self._pgrad(gn + ".bias")
+
+                    def wg():
+                        ops.conv_wgrad_s2d(V, dy, Cin, dwp, accumulate=False)
+                        ops.s2d_fold_wgrad(dy, dwp, w, gamma, beta, gw, gg, gb, accw, accg)
+                    ops.on_wgrad_stream(V, wg)
+                    first = grp["dV"] is None
+                    if first:
+                        grp["dV"] = self.pool.get(x.N, 8 * Cin, V.Z, V.Y, V.X, dev)
+                    ops.conv_dgrad(self.packs, dy, we, 1, grp["dV"], accumulate=not first, key=wkey, version=wver, s2d_cin=Cin)
+                if grp["left"] == 0 and grp["dV"] is not None:
+                    gx, accx = self._grad_of(x)
+                    ops.gn_backward(x, grp["dV"], grp["G"], grp["stats"], grp["ones"], None, None, False, gx, accx, s2d=True,
+                                    add=self._take_pending(x))
+                    self._wrote(x)
+            self.tape.append(bwd)
+        return y
+
     def res_block(self, x, prefix, train, x_needs_grad=True):
         """ResNetBlock.forward (hr_util/common.py:138-148)."""
         p = self.p
@@ -271,6 +341,11 @@ class Engine:
         # fuse_sum of output 0 overlaps the stride-2 convs of the others.  (Their backward closures stay on the main
         # stream: they accumulate into the shared input gradients in program order.)
         par = self.parallel_fuse and self.parallel_branches and len(idx) > 1
+        self._s2d_share = {}
+        sib = ["%s.fuse_layers.%d.0.0" % (prefix, i) for i in idx if i > 0]
+        if ops.USE_S2D_SHARE and len(sib) >= 2 and all(ops.s2d_eligible(xs[0], self.p[q + ".1.weight"]) for q in sib):
+            # the stride-2 fuse convs out of branch 0 share one view of xhat (issued here, before the streams fork)
+            self._s2d_share[id(xs[0])] = self._s2d_share_prepare(xs[0], len(sib))
         if par:
             dev = xs[0].buf.device
             main = torch.cuda.current_stream(dev)
@@ -324,7 +399,11 @@ class Engine:
                     t = xs[j]
                     for k in range(i - j):
                         q = "%s.fuse_layers.%d.%d.%d" % (prefix, i, j, k)
-                        t = self.gn_conv(t, q + ".0", q + ".1", 3, 2, k < i - j - 1, train=train)
+                        grp = self._s2d_share.get(id(t)) if k == 0 else None
+                        if grp is not None and grp["x"] is t:
+                            t = self._gn_conv_s2d_shared(grp, q + ".0", q + ".1", k < i - j - 1, train)
+                        else:
+                            t = self.gn_conv(t, q + ".0", q + ".1", 3, 2, k < i - j - 1, train=train)
                     same.append(t)
             y = ops.fuse_sum(self.new(xs[i]), same, low, relu=True)
             y.relu_out = True

@@ -110,6 +110,10 @@ PROTOTYPES = {
     "rtp_wgrad_s2d_reduce": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _i32, _i32, _vp]),
     "rtp_weight_s2d_expand": (C.c_int, [_vp, _vp, _i32, _i32, _vp]),
     "rtp_weight_s2d_fold": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp]),
+    "rtp_s2d_fold_weights": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),
+    "rtp_s2d_border_bias": (C.c_int, [_vp, P8Struct, _i32, _vp]),
+    "rtp_s2d_box_sums_workspace_bytes": (C.c_int64, [_i32, _i32]),
+    "rtp_s2d_fold_wgrad": (C.c_int, [P8Struct, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "rtp_fuse_sum": (C.c_int, [C.POINTER(FuseDesc), _vp]),
     "rtp_upsample_bwd_workspace_bytes": (C.c_int64, [P8Struct, P8Struct, _i32]),
     "rtp_upsample_bwd": (C.c_int, [P8Struct, P8Struct, _i32, _i32, _vp, _vp]),
@@ -188,7 +192,7 @@ LAUNCHES = {"rtp_pack_ncdhw": 1, "rtp_unpack_ncdhw": 1, "rtp_ingest_pack": 1, "r
             "rtp_dcn_bwd_input": 1, "rtp_dcn_bwd_weight": 1, "rtp_mdcn_fwd": 1, "rtp_mdcn_bwd_input": 1, "rtp_mdcn_bwd_weight": 2, "rtp_adam_step": 2, "rtp_adam_step_dev": 2,
             "rtp_assign_targets": 2, "rtp_wgrad_k3s1": 1, "rtp_wgrad_k3s1_reduce": 1, "rtp_conv_pw": 1, "rtp_gn_apply_s2d": 1, "rtp_gn_bwd_reduce_s2d": 2,
             "rtp_gn_bwd_apply_s2d": 1, "rtp_conv_k3s1_stat_finalize": 1, "rtp_conv_multi": 1, "rtp_gn_stats": 2,
-            "rtp_wgrad_s2d": 1, "rtp_wgrad_s2d_reduce": 1, "rtp_wgrad_pw": 1, "rtp_wgrad_pw_reduce": 1,
+            "rtp_wgrad_s2d": 1, "rtp_wgrad_s2d_reduce": 1, "rtp_s2d_fold_weights": 2, "rtp_s2d_border_bias": 1, "rtp_s2d_fold_wgrad": 2, "rtp_wgrad_pw": 1, "rtp_wgrad_pw_reduce": 1,
             "rtp_npy_probe": 0, "rtp_npy_read_roi_slab": 0}  # host-only file readers
 launch_count = 0
 call_counts = {}  # C-ABI entry point -> number of calls (tests assert which kernel path a shape really took)

@@ -779,6 +779,31 @@ def s2d_fold(dw_s2d, dw, accumulate):
     lib.call("rtp_weight_s2d_fold", dw_s2d.data_ptr(), dw.data_ptr(), dw.shape[0], dw.shape[1], int(accumulate), _stream())
 
 
+USE_S2D_SHARE = not bool(_os.environ.get("RTP_NO_S2D_SHARE"))  # sibling stride-2 convs share one view of xhat (csrc/s2d_shared.cu)
+
+
+def s2d_fold_weights(w, gamma, beta, we, bias_cls):
+    """we [Cout][8*Cin][27] = s2d_expand(W * diag(gamma)); bias_cls [8][Cout] = the beta term per border class."""
+    lib.call("rtp_s2d_fold_weights", w.detach().contiguous().data_ptr(), gamma.data_ptr(), beta.data_ptr(), we.data_ptr(),
+             bias_cls.data_ptr(), w.shape[0], w.shape[1], _stream())
+
+
+def s2d_border_bias(bias_cls, r, Cout):
+    """r (P8, N = 1) = bias_cls[class(pos)] - bias_cls[0]; returns r broadcast over the batch (n_stride = 0) for use as the
+    conv's `res` input."""
+    lib.call("rtp_s2d_border_bias", bias_cls.data_ptr(), r.struct(), Cout, _stream())
+
+
+def s2d_fold_wgrad(dy, dw_xhat, w, gamma, beta, dW, dgamma, dbeta, acc_w, acc_gb):
+    """(dW, dgamma, dbeta) of a gamma/beta-folded stride-2 conv from the weight gradient over xhat (csrc/s2d_shared.cu)."""
+    Cout, Cin = w.shape[0], w.shape[1]
+    ws = workspace(lib.load().rtp_s2d_box_sums_workspace_bytes(dy.N, (Cout + 7) // 8), dy.buf.device, "s2dbox")
+    assert dW.is_contiguous() and dw_xhat.is_contiguous()
+    lib.call("rtp_s2d_fold_wgrad", dy.struct(), dw_xhat.data_ptr(), w.detach().contiguous().data_ptr(), gamma.data_ptr(),
+             beta.data_ptr(), ws.data_ptr(), dW.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), Cout, Cin, int(acc_w), int(acc_gb),
+             _stream())
+
+
 def gn_backward(x, dxn, G, stats, gamma, dgamma, dbeta, acc_params, dx, acc_dx, red=None, s2d=False, add=None):
     """red: the [N][C][2] reductions when the conv that produced dxn already computed them (conv_dgrad(stat=...)).
     s2d: dxn is the gradient of the space-to-depth view of GN(x).
@@ -791,7 +816,8 @@ def gn_backward(x, dxn, G, stats, gamma, dgamma, dbeta, acc_params, dx, acc_dx, 
         lib.call("rtp_gn_bwd_reduce" + sfx, x.struct(), dxn.struct(), x.C, G, stats.data_ptr(), red.data_ptr(),
                  gn_ws(x).data_ptr(), _stream())
     lib.call("rtp_gn_bwd_apply" + sfx, x.struct(), dxn.struct(), x.C, G, stats.data_ptr(), red.data_ptr(), gamma.data_ptr(),
-             dgamma.data_ptr(), dbeta.data_ptr(), int(acc_params), dx.struct() if dx is not None else lib.NULL_P8,
+             dgamma.data_ptr() if dgamma is not None else None, dbeta.data_ptr() if dbeta is not None else None,
+             int(acc_params), dx.struct() if dx is not None else lib.NULL_P8,
              int(acc_dx), int(x.relu_out), add.struct() if add is not None else lib.NULL_P8, _stream())
     # bytes: (reduction pass: x + dxn) + (apply pass: x + dxn read, dx written [+ read when accumulating] [+ add read])
     nb = (0 if key[3] else 2) + (0 if dx is None else 3 + (1 if acc_dx else 0) + (1 if add is not None else 0))

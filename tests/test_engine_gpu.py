@@ -252,3 +252,48 @@ def test_shared_conv_branch_of_the_head():
     assert cos >= min(0.97, bcos - 0.01), (cos, bcos)
     for k in ("pose_head.shared_conv.0.weight", "pose_head.shared_conv.0.bias", "pose_head.shared_conv.1.weight"):
         assert k in out["grads"] and float(out["grads"][k].abs().sum()) > 0, k
+
+
+def test_sibling_stride2_convs_share_one_normalised_view(monkeypatch):
+    """The stride-2 fuse convs out of branch 0 of an HR module (2 in stage 3, 3 in stage 4) read ONE space-to-depth view of
+    xhat with their GroupNorm affine folded into the conv (csrc/s2d_shared.cu): forward, every parameter gradient (incl. the
+    folded gamma / beta of those GroupNorms, which come out of the weight gradient) and dL/dx agree with the per-conv path and
+    with the fp32 oracle.  synth weights: beta != 0, so the border-class bias is exercised."""
+    from rtpose_b200 import lib, ops
+    cfg, grid, batch = "hr3d_one_hm_doppler", (8, 32, 48), 2
+    monkeypatch.setattr(ops, "S2D_MIN_VOXELS", 0)
+    x, poses, tgt = G.make_example(cfg, batch, grid, seed=211)
+    sd = O.synth_state_dict(cfg, seed=3)
+    outs = {}
+    for share in (True, False):
+        monkeypatch.setattr(ops, "USE_S2D_SHARE", share)
+        eng, params = build_engine(cfg, sd)
+        lib.call_counts.clear()
+        outs[share], _, _ = run_engine(eng, params, x, tgt)
+        n_fold = lib.call_counts.get("rtp_s2d_fold_wgrad", 0)
+        assert n_fold == (5 if share else 0), n_fold
+        assert lib.call_counts.get("rtp_gn_apply_s2d", 0) > 0
+    a, b = outs[True], outs[False]
+    r_hm, r_reg, r_loss, r_grads = oracle_run(x, sd, cfg, tgt, False)
+    b_hm, b_reg, b_loss, b_grads = oracle_run(x, sd, cfg, tgt, True)
+    for name, r, au in (("hm", r_hm, b_hm), ("reg", r_reg, b_reg)):
+        spread = max((au - r).abs().max().item(), 0.02 * r.std().item())
+        e = (a[name] - r).abs().max().item()
+        print("%s: shared-view path max err %.4g (per-conv path %.4g, autocast %.4g)" % (name, e, (b[name] - r).abs().max().item(), spread))
+        assert e <= 2.0 * spread, (name, e, spread)
+    assert abs(a["loss"][0].item() - r_loss) <= 1.5e-2 * abs(r_loss)
+    rel, cos = grad_report(a["grads"], r_grads)
+    rel_b, cos_b = grad_report(b["grads"], r_grads)
+    brel, bcos = grad_report(b_grads, r_grads)
+    print("grad vs oracle: shared cosine %.5f rel-L2 median %.3g | per-conv %.5f %.3g | autocast %.5f %.3g" %
+          (cos, np.median(rel), cos_b, np.median(rel_b), bcos, np.median(brel)))
+    assert set(a["grads"]) >= set(r_grads)
+    assert cos >= min(0.97, bcos - 0.01) and np.median(rel) <= 1.5 * np.median(brel)
+    # the parameters whose gradients take the new route, one by one against the oracle (yardstick: the per-conv path)
+    for k in sorted(r_grads):
+        if ".fuse_layers." in k and k.split(".fuse_layers.")[1].split(".")[1:3] == ["0", "0"]:
+            r = r_grads[k].double().flatten()
+            ea = float((a["grads"][k].double().flatten() - r).norm() / r.norm())
+            eb = float((b["grads"][k].double().flatten() - r).norm() / r.norm())
+            print("  %-60s rel-L2 shared %.3g per-conv %.3g" % (k, ea, eb))
+            assert ea <= max(2.0 * eb, 0.05), (k, ea, eb)

@@ -599,6 +599,74 @@ def test_stride2_conv_through_space_to_depth_view(ctx, case):
     close(dx5.to_ncdhw(), dx.to_ncdhw().cpu() + bf(extra), tol=2 * BF16_ULP, what="s2d dx + add")
 
 
+@pytest.mark.parametrize("case", [(2, 32, 32, (8, 20, 24)), (1, 32, 32, (2, 64, 10))], ids=str)
+def test_sibling_stride2_convs_with_the_groupnorm_affine_folded_in(ctx, case):
+    """Two `GroupNorm -> conv3x3x3 stride 2` layers with different (gamma, beta, W) reading the same x (the fuse layers out
+    of branch 0, hr3d.py:159-203) computed from ONE space-to-depth view of xhat with the affine folded into each conv
+    (csrc/s2d_shared.cu), against torch: outputs (one with ReLU), dW, dgamma, dbeta of both and the summed dL/dx."""
+    from rtpose_b200 import ops
+    from rtpose_b200.p8 import P8
+    N, Cin, Cout, grid = case
+    hg = tuple(g // 2 for g in grid)
+    x = rnd(N, Cin, *grid, seed=180).requires_grad_(True)
+    ws = [rnd(Cout, Cin, 3, 3, 3, seed=181 + k, scale=0.1).requires_grad_(True) for k in range(2)]
+    gammas = [(1.0 + 0.2 * rnd(Cin, seed=183 + k)).requires_grad_(True) for k in range(2)]
+    betas = [(0.3 * rnd(Cin, seed=185 + k)).requires_grad_(True) for k in range(2)]
+    dys = [rnd(N, Cout, *hg, seed=187 + k) for k in range(2)]
+    relus = [True, False]
+    y_refs = []
+    for k in range(2):
+        xn = F.group_norm(x, 8, gammas[k], betas[k], eps=1e-5)
+        y = F.conv3d(bf(xn.detach()) + (xn - xn.detach()), ws[k], stride=2, padding=1)
+        if relus[k]:
+            y = F.relu(y)
+        y_refs.append(y)
+    sum((y * d).sum() for y, d in zip(y_refs, dys)).backward()
+
+    ops.S2D_MIN_VOXELS = 0
+    xp = to_p8(x.detach())
+    stats = ops.gn_stats(xp, 8)
+    ones, zeros = torch.ones(Cin, device="cuda"), torch.zeros(Cin, device="cuda")
+    V = ops.gn_apply_s2d(xp, 8, stats, ones, zeros, P8(N, 8 * Cin, *hg))
+    dV = P8(N, 8 * Cin, *hg)
+    masks = [ops.s2d_tap_mask(par, False) for par in range(8)]
+    for k in range(2):
+        wc, gc, bc = ws[k].detach().cuda(), gammas[k].detach().cuda(), betas[k].detach().cuda()
+        we = torch.empty((Cout, 8 * Cin, 3, 3, 3), device="cuda")
+        bias_cls = torch.empty((8, Cout), device="cuda")
+        ops.s2d_fold_weights(wc, gc, bc, we, bias_cls)
+        r1 = P8(1, Cout, *hg)
+        ops.s2d_border_bias(bias_cls, r1, Cout)
+        rb = P8(N, Cout, *hg, buf=r1.buf, offset=r1.offset, n_stride=0, c_stride=r1.c_stride)
+        y = ops.conv_forward(ctx, V, we, 1, P8(N, Cout, *hg), bias=bias_cls[0], relu=relus[k], res=rb, key=("sib", case, k),
+                             version=0, tap_mask=masks)
+        torch.cuda.synchronize()
+        # bias classes against a direct evaluation: conv of the constant beta field with zero padding
+        bfield = F.conv3d(betas[k].detach().view(1, Cin, 1, 1, 1).expand(1, Cin, *grid), ws[k].detach(), stride=2, padding=1)[0]
+        for cls in range(8):
+            z, yy, xx = (0 if cls & 4 else 1), (0 if cls & 1 else 1), (0 if cls & 2 else 1)
+            if z >= hg[0] or yy >= hg[1] or xx >= hg[2]:
+                continue  # this class has no output position on such a thin grid
+            close(bias_cls[cls], bfield[:, z, yy, xx], tol=1e-4, what="border-class bias %d" % cls)
+        close(y.to_ncdhw(), y_refs[k], tol=1.5 * BF16_ULP, what="sibling %d forward" % k)
+        # backward: dy w.r.t. the pre-ReLU output
+        dy = dys[k] * (y_refs[k].detach() > 0).float() if relus[k] else dys[k]
+        dyp = to_p8(dy)
+        dwp = torch.empty_like(wc)
+        ops.conv_wgrad_s2d(V, dyp, Cin, dwp, accumulate=False)
+        gw, gg, gb = (torch.full(t.shape, 3.0, device="cuda") for t in (wc, gc, bc))
+        ops.s2d_fold_wgrad(dyp, dwp, wc, gc, bc, gw, gg, gb, False, False)
+        ops.conv_dgrad(ctx, dyp, we, 1, dV, accumulate=k > 0, key=("sib", case, k), version=0, s2d_cin=Cin)
+        torch.cuda.synchronize()
+        close(gw, ws[k].grad, tol=5e-3, what="sibling %d dW" % k)
+        close(gg, gammas[k].grad, tol=2e-2, what="sibling %d dgamma" % k)
+        close(gb, betas[k].grad, tol=2e-2, what="sibling %d dbeta" % k)
+    dx = P8(N, Cin, *grid)
+    ops.gn_backward(xp, dV, 8, stats, ones, None, None, False, dx, False, s2d=True)
+    torch.cuda.synchronize()
+    close(dx.to_ncdhw(), x.grad, tol=2e-2, what="summed dL/dx through the shared view")
+
+
 def test_fused_launch_variants_match_their_multi_launch_forms(ctx):
     """rtp_gn_stats == rtp_gn_sums + rtp_gn_finalize and rtp_conv_multi == one rtp_conv per parity class, bit for bit."""
     from rtpose_b200 import lib, ops
