@@ -258,7 +258,7 @@ def build_params(cfg, device):
     return params, grads, flat, gflat
 
 
-EW = {"gn_apply", "gn_backward", "fuse_sum", "upsample_bwd", "grad_add"}  # element-wise families: they record algorithmic BYTES
+EW = {"gn_apply", "gn_backward", "fuse_sum", "upsample_bwd", "grad_add", "conat"}  # element-wise families: they record algorithmic BYTES
 TENSOR = {"conv_generic", "conv_k3s1", "conv_pw", "wgrad_generic", "wgrad_k3s1", "wgrad_s2d", "wgrad_pw"}
 
 

@@ -315,6 +315,27 @@ typedef struct {
   int32_t relu;
 } rtp_fuse_desc;
 int rtp_fuse_sum(const rtp_fuse_desc* d, void* stream);
+
+/* The final concat + 1x1 conv of HRNet3D as ONE streaming GEMM (csrc/conat.cu):
+ *   out = [relu]( W * cat(x0, up(low[0]), up(low[1]), up(low[2])) + bias ),   up = trilinear, align_corners=True
+ * replaces: `x = torch.cat([x0, F.interpolate(x1..x3, size, mode='trilinear', align_corners=True)], 1); final_conv(x)`
+ * (det3d/models/backbones/hrnet3d.py:37-42).  The chunks of x0 reach shared memory by bulk copies, the chunks of the
+ * upsampled branches are interpolated into the UMMA A operand by the kernel; the concat is never materialised.
+ * w: rtp_weight_pack(mode 0) of the whole [Cout][K] weight, K = c_x0 + sum c_low (each a multiple of 16, cat order).
+ * Supported when rtp_conat_supported() returns 1 (Cout <= 128, weights + two operand stages + blend rows fit shared
+ * memory, padded row length Y + 2 >= 43); callers fall back to per-branch rtp_conv_pw + rtp_fuse_sum otherwise. */
+typedef struct {
+  rtp_p8 x0, out;
+  rtp_p8 low[3];
+  int32_t n_low;      /* 1..3 */
+  int32_t c_x0;       /* channels taken from x0 */
+  int32_t c_low[3];   /* channels taken from each low term */
+  const void* w;      /* packed weights [K/8][NP][8] bf16 */
+  const float* bias;  /* [NP] fp32 or NULL */
+  int32_t K, NP, out_c8, relu;
+} rtp_conat_desc;
+int rtp_conat_supported(const rtp_conat_desc* d);
+int rtp_conat_fwd(const rtp_conat_desc* d, void* stream);
 /* dlow (=|+=) transpose-of-trilinear-upsample applied to dout, as three separable 1-D gather passes (y, x, z;
  * deterministic); workspace >= rtp_upsample_bwd_workspace_bytes(dout, dlow, C), 16-byte aligned */
 int64_t rtp_upsample_bwd_workspace_bytes(rtp_p8 dout, rtp_p8 dlow, int32_t C);

@@ -145,7 +145,7 @@ class SlicedAllReduce:
         cur = torch.cuda.current_stream(self.flat.device)
         self.stream.wait_stream(cur)
         for key, st in ops._side.items():           # weight gradients queued so far
-            if key.split("/")[0] == str(self.flat.device):
+            if key[0] == str(self.flat.device):
                 self.stream.wait_stream(st["stream"])
         eng = getattr(self, "engine", None)
         for st in list(self.extra_streams) + (list(eng._bstreams.values()) if eng is not None else []):

@@ -342,10 +342,11 @@ class Engine:
         # stream: they accumulate into the shared input gradients in program order.)
         par = self.parallel_fuse and self.parallel_branches and len(idx) > 1
         self._s2d_share = {}
-        sib = ["%s.fuse_layers.%d.0.0" % (prefix, i) for i in idx if i > 0]
-        if ops.USE_S2D_SHARE and len(sib) >= 2 and all(ops.s2d_eligible(xs[0], self.p[q + ".1.weight"]) for q in sib):
-            # the stride-2 fuse convs out of branch 0 share one view of xhat (issued here, before the streams fork)
-            self._s2d_share[id(xs[0])] = self._s2d_share_prepare(xs[0], len(sib))
+        for j in range(nb - 1):
+            sib = ["%s.fuse_layers.%d.%d.0" % (prefix, i, j) for i in idx if i > j]
+            if ops.USE_S2D_SHARE and len(sib) >= 2 and all(ops.s2d_eligible(xs[j], self.p[q + ".1.weight"]) for q in sib):
+                # the stride-2 fuse convs out of branch j share one view of xhat (issued here, before the streams fork)
+                self._s2d_share[id(xs[j])] = self._s2d_share_prepare(xs[j], len(sib))
         if par:
             dev = xs[0].buf.device
             main = torch.cuda.current_stream(dev)
@@ -501,12 +502,16 @@ class Engine:
         # trilinear interpolation commute); avoids materialising the concat.
         w, b = self.p[self.pb + "final_conv.weight"], self.p[self.pb + "final_conv.bias"]
         terms, c0 = [], 0
+        f = ops.conat_forward(self.packs, ys, w, b, self.new(ys[0], C=w.shape[0]))  # one GEMM, concat assembled in shared memory
         for y in ys:
-            t = self.new(y, C=w.shape[0])
-            ops.conv_forward(self.packs, y, w, 1, t, ci0=c0, ci_n=y.C)
+            t = None
+            if f is None:
+                t = self.new(y, C=w.shape[0])
+                ops.conv_forward(self.packs, y, w, 1, t, ci0=c0, ci_n=y.C)
             terms.append((y, t, c0))
             c0 += y.C
-        f = ops.fuse_sum(self.new(ys[0], C=w.shape[0]), [terms[0][1]], [t for _, t, _ in terms[1:]], bias=b)
+        if f is None:
+            f = ops.fuse_sum(self.new(ys[0], C=w.shape[0]), [terms[0][1]], [t for _, t, _ in terms[1:]], bias=b)
         if train:
             def bwd():
                 g = self._g(f)
@@ -521,7 +526,7 @@ class Engine:
                     if i == 0:
                         gt = g
                     else:
-                        gt = self.new(t)
+                        gt = self.new(y, C=w.shape[0])
                         ops.upsample_bwd(g, gt)
                     ops.conv_wgrad_async(y, gt, 1, 1, gw, accumulate=accw, ci0=ci0)
                     gy, acc = self._grad_of(y)

@@ -49,6 +49,12 @@ class FuseDesc(C.Structure):
                 ("same", P8Struct * 4), ("low", P8Struct * 3), ("bias", C.c_void_p), ("relu", C.c_int32)]
 
 
+class ConatDesc(C.Structure):
+    _fields_ = [("x0", P8Struct), ("out", P8Struct), ("low", P8Struct * 3), ("n_low", C.c_int32), ("c_x0", C.c_int32),
+                ("c_low", C.c_int32 * 3), ("w", C.c_void_p), ("bias", C.c_void_p), ("K", C.c_int32), ("NP", C.c_int32),
+                ("out_c8", C.c_int32), ("relu", C.c_int32)]
+
+
 class NpyInfo(C.Structure):
     _fields_ = [("ndim", C.c_int32), ("elem_bytes", C.c_int32), ("fortran_order", C.c_int32), ("reserved_", C.c_int32),
                 ("shape", C.c_int64 * 8), ("data_offset", C.c_int64), ("file_bytes", C.c_int64), ("descr", C.c_char * 16)]
@@ -115,6 +121,8 @@ PROTOTYPES = {
     "rtp_s2d_box_sums_workspace_bytes": (C.c_int64, [_i32, _i32]),
     "rtp_s2d_fold_wgrad": (C.c_int, [P8Struct, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "rtp_fuse_sum": (C.c_int, [C.POINTER(FuseDesc), _vp]),
+    "rtp_conat_supported": (C.c_int, [C.POINTER(ConatDesc)]),
+    "rtp_conat_fwd": (C.c_int, [C.POINTER(ConatDesc), _vp]),
     "rtp_upsample_bwd_workspace_bytes": (C.c_int64, [P8Struct, P8Struct, _i32]),
     "rtp_upsample_bwd": (C.c_int, [P8Struct, P8Struct, _i32, _i32, _vp, _vp]),
     "rtp_grad_add": (C.c_int, [P8Struct, P8Struct, P8Struct, _i32, _i32, _vp]),
@@ -193,6 +201,7 @@ LAUNCHES = {"rtp_pack_ncdhw": 1, "rtp_unpack_ncdhw": 1, "rtp_ingest_pack": 1, "r
             "rtp_assign_targets": 2, "rtp_wgrad_k3s1": 1, "rtp_wgrad_k3s1_reduce": 1, "rtp_conv_pw": 1, "rtp_gn_apply_s2d": 1, "rtp_gn_bwd_reduce_s2d": 2,
             "rtp_gn_bwd_apply_s2d": 1, "rtp_conv_k3s1_stat_finalize": 1, "rtp_conv_multi": 1, "rtp_gn_stats": 2,
             "rtp_wgrad_s2d": 1, "rtp_wgrad_s2d_reduce": 1, "rtp_s2d_fold_weights": 2, "rtp_s2d_border_bias": 1, "rtp_s2d_fold_wgrad": 2, "rtp_wgrad_pw": 1, "rtp_wgrad_pw_reduce": 1,
+            "rtp_conat_fwd": 1, "rtp_conat_supported": 0, "rtp_s2d_box_sums_workspace_bytes": 0,
             "rtp_npy_probe": 0, "rtp_npy_read_roi_slab": 0}  # host-only file readers
 launch_count = 0
 call_counts = {}  # C-ABI entry point -> number of calls (tests assert which kernel path a shape really took)

@@ -544,11 +544,19 @@ _side = {}
 LANE = 0  # engines that run concurrently on different streams (half-batch lanes) each get their own weight-gradient stream
 
 
+WGRAD_STREAM_PER_ORIGIN = not bool(_os.environ.get("RTP_ONE_WGRAD_STREAM"))
+
+
 def _side_stream(device):
-    key = "%s/%d" % (device, LANE)
+    """Weight-gradient side stream for work forked from the CURRENT stream: one per origin stream (the main stream and each
+    branch stream get their own), so the small low-resolution weight gradients of a side branch neither queue behind the
+    full-resolution ones nor make them wait for that branch's dY (one shared side stream serialised all of them: with the
+    weight gradients skipped the step is 4.8 ms shorter, i.e. they were almost entirely exposed)."""
+    origin = _stream() if WGRAD_STREAM_PER_ORIGIN else 0
+    key = (str(device), LANE, origin)
     st = _side.get(key)
     if st is None:
-        st = {"stream": named_stream(device, "wgrad%d" % LANE), "busy": False, "events": []}
+        st = {"stream": named_stream(device, "wgrad%d/%x" % (LANE, origin)), "busy": False, "events": []}
         _side[key] = st
     return st
 
@@ -556,7 +564,7 @@ def _side_stream(device):
 def join_wgrad(device=None):
     """Makes the current stream wait for every weight gradient queued on the side stream(s)."""
     for key, st in _side.items():
-        if st["busy"] and key.endswith("/%d" % LANE) and (device is None or key.split("/")[0] == str(device)):
+        if st["busy"] and key[1] == LANE and (device is None or key[0] == str(device)):
             torch.cuda.current_stream(st["stream"].device).wait_stream(st["stream"])
             st["busy"] = False
 
@@ -665,7 +673,7 @@ def gn_apply(x, G, stats, gamma, beta, out):
     return out
 
 
-S2D_MIN_VOXELS = int(_os.environ.get("RTP_S2D_MIN_VOXELS", 1 << 20))
+S2D_MIN_VOXELS = int(_os.environ.get("RTP_S2D_MIN_VOXELS", 1 << 18))
 S2D_DGRAD_PAIR = not bool(_os.environ.get("RTP_NO_PAIR"))
 USE_WGRAD_PW = not bool(_os.environ.get("RTP_NO_WGRAD_PW"))    # streaming 1x1 weight gradient (csrc/wgrad_pw.cu)
 USE_WGRAD_S2D = not bool(_os.environ.get("RTP_NO_WGRAD_S2D"))  # plane-streaming weight gradient over the s2d view (csrc/wgrad_s2d.cu)
@@ -839,6 +847,41 @@ def fuse_sum(out, same, low, bias=None, relu=False):
     ev = _prof_begin(key)
     lib.call("rtp_fuse_sum", C.byref(d), _stream())
     _prof_end(key, ev, _tbytes(out) * (1 + len(same)) + sum(_tbytes(t, out.C) for t in low))
+    return out
+
+
+USE_CONAT = not bool(_os.environ.get("RTP_NO_CONAT"))  # final concat + 1x1 conv as one GEMM with an interpolated A operand (csrc/conat.cu)
+
+
+def conat_forward(packs, ys, w, bias, out, relu=False):
+    """out = [relu](conv1x1(cat(ys[0], up(ys[1]), ...), w) + bias) in ONE launch (rtp_conat_fwd), or None when the shape is
+    not supported (the caller then uses per-branch 1x1 convs + fuse_sum)."""
+    if not USE_CONAT or not (2 <= len(ys) <= 4) or w.shape[2] != 1:
+        return None
+    Cout, Cin = w.shape[0], w.shape[1]
+    if sum(y.C for y in ys) != Cin or any(y.C % 16 for y in ys) or Cout % 16:
+        return None
+    x0 = ys[0]
+    if not (_dense_planes(x0) and _dense_planes(out) and x0.grid == out.grid):
+        return None
+    d = lib.ConatDesc()
+    d.x0, d.out = x0.struct(), out.struct()
+    d.n_low, d.c_x0 = len(ys) - 1, x0.C
+    for j, y in enumerate(ys[1:]):
+        d.low[j] = y.struct()
+        d.c_low[j] = y.C
+    d.K, d.NP, d.out_c8, d.relu = Cin, Cout, Cout // 8, int(relu)
+    if lib.load().rtp_conat_supported(C.byref(d)) != 1:
+        return None
+    wp, KP, NP = packs.get(w, 0)
+    assert (KP, NP) == (Cin, Cout)
+    d.w = wp.data_ptr()
+    b = pad_bias(bias, NP)
+    d.bias = b.data_ptr() if b is not None else None
+    key = ("conat", Cin, Cout, 1, 1, 1, (out.Z, out.X, out.Y))
+    ev = _prof_begin(key)
+    lib.call("rtp_conat_fwd", C.byref(d), _stream())
+    _prof_end(key, ev, _tbytes(x0) + _tbytes(out) + sum(_tbytes(y) for y in ys[1:]))  # algorithmic BYTES (HBM-bound)
     return out
 
 

@@ -271,7 +271,8 @@ def test_sibling_stride2_convs_share_one_normalised_view(monkeypatch):
         lib.call_counts.clear()
         outs[share], _, _ = run_engine(eng, params, x, tgt)
         n_fold = lib.call_counts.get("rtp_s2d_fold_wgrad", 0)
-        assert n_fold == (5 if share else 0), n_fold
+        # branch 0 feeds 2 (stage 3) + 3 (stage 4) stride-2 fuse convs, branch 1 two more in stage 4 (when its grid is eligible)
+        assert n_fold in ((5, 7) if share else (0,)), n_fold
         assert lib.call_counts.get("rtp_gn_apply_s2d", 0) > 0
     a, b = outs[True], outs[False]
     r_hm, r_reg, r_loss, r_grads = oracle_run(x, sd, cfg, tgt, False)
@@ -291,7 +292,7 @@ def test_sibling_stride2_convs_share_one_normalised_view(monkeypatch):
     assert cos >= min(0.97, bcos - 0.01) and np.median(rel) <= 1.5 * np.median(brel)
     # the parameters whose gradients take the new route, one by one against the oracle (yardstick: the per-conv path)
     for k in sorted(r_grads):
-        if ".fuse_layers." in k and k.split(".fuse_layers.")[1].split(".")[1:3] == ["0", "0"]:
+        if ".fuse_layers." in k and k.split(".fuse_layers.")[1].split(".")[1:3] in (["0", "0"], ["1", "0"]):
             r = r_grads[k].double().flatten()
             ea = float((a["grads"][k].double().flatten() - r).norm() / r.norm())
             eb = float((b["grads"][k].double().flatten() - r).norm() / r.norm())

@@ -667,6 +667,65 @@ def test_sibling_stride2_convs_with_the_groupnorm_affine_folded_in(ctx, case):
     close(dx.to_ncdhw(), x.grad, tol=2e-2, what="summed dL/dx through the shared view")
 
 
+CONAT_CASES = [
+    # N, grid (Z, Y, X), channels of the four branches, Cout
+    (2, (8, 48, 24), (32, 32, 64, 64), 128),
+    (1, (16, 64, 160), (32, 32, 64, 64), 128),   # the BASELINE grid
+    (3, (4, 44, 10), (16, 32), 48),              # two branches, Cout not a multiple of 32, coarsest z extent 2
+]
+
+
+@pytest.mark.parametrize("case", CONAT_CASES, ids=str)
+def test_final_concat_conv_as_one_gemm(ctx, case):
+    """cat(x0, trilinear-upsampled x1..x3) -> 1x1 conv + bias (backbones/hrnet3d.py:37-42) in one launch with the concat
+    assembled in shared memory (csrc/conat.cu), against torch (F.interpolate align_corners=True + cat + conv3d) and against
+    the per-branch route (1x1 convs + fuse_sum) it replaces."""
+    from rtpose_b200 import ops
+    from rtpose_b200.p8 import P8
+    N, grid, chans, Cout = case
+    xs = []
+    for j, c in enumerate(chans):
+        g = tuple(max(1, v >> j) for v in grid)
+        xs.append(rnd(N, c, *g, seed=300 + j).cuda())
+    w = rnd(Cout, sum(chans), 1, 1, 1, seed=310, scale=0.1).cuda()
+    b = rnd(Cout, seed=311).cuda()
+    cat = torch.cat([xs[0]] + [F.interpolate(x, size=grid, mode="trilinear", align_corners=True) for x in xs[1:]], 1)
+    ref = F.conv3d(cat, w, b)
+    ys = [P8.from_ncdhw(x) for x in xs]
+    out = ops.conat_forward(ctx, ys, w, b, P8(N, Cout, *grid))
+    assert out is not None, "shape not taken by rtp_conat_fwd"
+    torch.cuda.synchronize()
+    close(out.to_ncdhw(), ref, tol=1.5 * BF16_ULP, what="concat + 1x1 conv in one GEMM")
+    # pads of the output stay zero (ring positions are computed but never stored)
+    full = out.buf[out.offset:out.offset + out.N * out.n_stride].view(N, out.C8, grid[0], grid[2] + 2, grid[1] + 2, 8).float()
+    assert float(full[:, :, :, 0].abs().sum()) == 0 and float(full[:, :, :, :, 0].abs().sum()) == 0
+    assert float(full[:, :, :, -1].abs().sum()) == 0 and float(full[:, :, :, :, -1].abs().sum()) == 0
+    # the route it replaces
+    terms, c0 = [], 0
+    for y in ys:
+        t = P8(N, Cout, *y.grid)
+        ops.conv_forward(ctx, y, w, 1, t, ci0=c0, ci_n=y.C)
+        terms.append(t)
+        c0 += y.C
+    old = ops.fuse_sum(P8(N, Cout, *grid), [terms[0]], terms[1:], bias=b)
+    torch.cuda.synchronize()
+    e_new = (out.to_ncdhw() - ref).abs().max().item()
+    e_old = (old.to_ncdhw() - ref).abs().max().item()
+    print("max err vs torch: one-GEMM %.4g, per-branch convs + fuse_sum %.4g (ref max %.3g)" % (e_new, e_old, ref.abs().max().item()))
+    assert e_new <= 1.5 * e_old + 1e-3
+
+
+def test_final_concat_conv_falls_back_on_unsupported_shapes(ctx):
+    from rtpose_b200 import ops
+    from rtpose_b200.p8 import P8
+    ys = [P8(1, 32, 8, 16, 24), P8(1, 32, 4, 8, 12)]   # rows of 18 padded positions: a tile would span > 4 rows
+    w = torch.zeros(64, 64, 1, 1, 1, device="cuda")
+    assert ops.conat_forward(ctx, ys, w, None, P8(1, 64, 8, 16, 24)) is None
+    ys = [P8(1, 64, 8, 48, 24), P8(1, 128, 4, 24, 12), P8(1, 128, 2, 12, 6), P8(1, 64, 1, 6, 3)]  # feat64: weights exceed shared memory
+    w = torch.zeros(256, 384, 1, 1, 1, device="cuda")
+    assert ops.conat_forward(ctx, ys, w, None, P8(1, 256, 8, 48, 24)) is None
+
+
 def test_fused_launch_variants_match_their_multi_launch_forms(ctx):
     """rtp_gn_stats == rtp_gn_sums + rtp_gn_finalize and rtp_conv_multi == one rtp_conv per parity class, bit for bit."""
     from rtpose_b200 import lib, ops
