@@ -144,9 +144,8 @@ class SlicedAllReduce:
         from . import ops
         cur = torch.cuda.current_stream(self.flat.device)
         self.stream.wait_stream(cur)
-        for key, st in ops._side.items():           # weight gradients queued so far
-            if key[0] == str(self.flat.device):
-                self.stream.wait_stream(st["stream"])
+        for st in ops.wgrad_streams(self.flat.device):   # weight gradients (and their split-K reductions) queued so far
+            self.stream.wait_stream(st)
         eng = getattr(self, "engine", None)
         for st in list(self.extra_streams) + (list(eng._bstreams.values()) if eng is not None else []):
             self.stream.wait_stream(st)             # branch streams (GroupNorm parameter gradients of side branches)

@@ -527,13 +527,13 @@ def _wgrad_k3s1(x, dy, outs):
                 hn = (co_total - h) if (co_total - h) <= 48 else 32  # 9 accumulators x NP columns must fit 512
                 dyg = dy.channels(nn + h, hn)
                 NP = ceil_to(hn, 16)
-                ws = workspace(L.rtp_wgrad_k3s1_workspace_bytes(NP, num_sms()), dev, "wgrad3")
+                ws, done = _split_ws("wgrad3", L.rtp_wgrad_k3s1_workspace_bytes(NP, num_sms()), dev)
                 key = ("wgrad_k3s1", 32, hn, 27, 1, 1, (x.Z, x.X, x.Y))
                 ev = _prof_begin(key)
                 lib.call("rtp_wgrad_k3s1", xg.struct(), dyg.struct(), NP, zero.data_ptr(), ws.data_ptr(), C.byref(nsplit), _stream())
                 _prof_end(key, ev, 2.0 * x.N * x.voxels * 32 * hn * 27)
-                lib.call("rtp_wgrad_k3s1_reduce", ws.data_ptr(), nsplit.value, NP, gw[h:].data_ptr(), gw.shape[1], hn, 0,
-                         c0 + gi * 32, int(acc), _stream())
+                done(lambda ws=ws, ns=nsplit.value, NP=NP, gw=gw, h=h, hn=hn, c=c0 + gi * 32, acc=acc: lib.call(
+                    "rtp_wgrad_k3s1_reduce", ws.data_ptr(), ns, NP, gw[h:].data_ptr(), gw.shape[1], hn, 0, c, int(acc), _stream()))
                 h += hn
 
 
@@ -565,8 +565,58 @@ def join_wgrad(device=None):
     """Makes the current stream wait for every weight gradient queued on the side stream(s)."""
     for key, st in _side.items():
         if st["busy"] and key[1] == LANE and (device is None or key[0] == str(device)):
-            torch.cuda.current_stream(st["stream"].device).wait_stream(st["stream"])
+            cur = torch.cuda.current_stream(st["stream"].device)
+            cur.wait_stream(st["stream"])
+            if st.get("rstream") is not None:
+                cur.wait_stream(st["rstream"])
             st["busy"] = False
+            st["ring"] = {}  # everything is joined: no workspace of the ring is still being reduced
+
+
+def wgrad_streams(device):
+    """Every stream weight-gradient work of `device` may be queued on (side streams and their reduction streams)."""
+    out = []
+    for key, st in _side.items():
+        if key[0] == str(device):
+            out.append(st["stream"])
+            if st.get("rstream") is not None:
+                out.append(st["rstream"])
+    return out
+
+
+_cur_side = None  # state of the weight-gradient side stream the running code was forked onto (conv_wgrad_async / on_wgrad_stream)
+REDUCE_STREAM = bool(_os.environ.get("RTP_REDUCE_STREAM"))  # opt-in: measured SLOWER (20.52 vs 20.32 ms per step) — the main chain is the critical path
+
+
+def _split_ws(tag, nbytes, dev):
+    """Split-K workspace for a weight-gradient launch plus `done(fn)`, which issues the reduction fn().  On a weight-gradient
+    side stream the workspaces alternate between two buffers and the (tiny, latency-bound) reductions go to a companion
+    stream, so the next weight-gradient kernel starts right behind the previous one instead of behind its reduction; a
+    buffer is reused only after the reduction that read it (event).  Elsewhere: one buffer, reduction in stream order.
+    (Experiment, off by default: letting the weight-gradient stream run ahead takes SMs from the main chain and the step
+    gets longer, profiles/r02_ab_runs.txt.)"""
+    st = _cur_side
+    if st is None or not REDUCE_STREAM:
+        return workspace(nbytes, dev, tag), (lambda fn: fn())
+    ring = st.setdefault("ring", {}).setdefault(tag, {"i": 0, "ev": [None, None]})
+    i = ring["i"]
+    ring["i"] = i ^ 1
+    cur = torch.cuda.current_stream(dev)
+    if ring["ev"][i] is not None:
+        cur.wait_event(ring["ev"][i])
+    ws = workspace(nbytes, dev, "%s#%d" % (tag, i))
+
+    def done(fn):
+        if st.get("rstream") is None:
+            st["rstream"] = named_stream(dev, "wreduce/%x" % st["stream"].cuda_stream)
+        r = st["rstream"]
+        r.wait_stream(cur)
+        with torch.cuda.stream(r):
+            fn()
+        ev = torch.cuda.Event()
+        ev.record(r)
+        ring["ev"][i] = ev
+    return ws, done
 
 
 def conv_wgrad_async(x, dy, k, stride, dW, accumulate=False, ci0=0, n0=0, more=(), then=None):
@@ -582,13 +632,18 @@ def conv_wgrad_async(x, dy, k, stride, dW, accumulate=False, ci0=0, n0=0, more=(
         if then is not None:
             then()
         return None
+    global _cur_side
     st = _side_stream(dev)
     st["stream"].wait_stream(torch.cuda.current_stream(dev))
     st["busy"] = True
     with torch.cuda.stream(st["stream"]):
-        conv_wgrad(x, dy, k, stride, dW, accumulate, ci0, n0, more)
-        if then is not None:
-            then()
+        _cur_side = st
+        try:
+            conv_wgrad(x, dy, k, stride, dW, accumulate, ci0, n0, more)
+            if then is not None:
+                then()
+        finally:
+            _cur_side = None
     return None
 
 
@@ -608,7 +663,7 @@ def conv_wgrad(x, dy, k, stride, dW, accumulate=False, ci0=0, n0=0, more=(), tap
         # streaming GEMM over the padded positions (csrc/wgrad_pw.cu): M = dY channels, N = X channels
         L = lib.load()
         dev = x.buf.device
-        ws = workspace(L.rtp_wgrad_pw_workspace_bytes(ci_n, num_sms()), dev, "wgradpw")
+        ws, done = _split_ws("wgradpw", L.rtp_wgrad_pw_workspace_bytes(ci_n, num_sms()), dev)
         zero = _zero_page(4096, dev)
         nsplit = C.c_int32(0)
         key = ("wgrad_pw", ci_n, dy.C, 1, 1, 1, (dy.Z, dy.X, dy.Y))
@@ -616,8 +671,8 @@ def conv_wgrad(x, dy, k, stride, dW, accumulate=False, ci0=0, n0=0, more=(), tap
         lib.call("rtp_wgrad_pw", x.struct(), dy.struct(), ci_n, zero.data_ptr(), ws.data_ptr(), C.byref(nsplit), _stream())
         _prof_end(key, ev, 2.0 * dy.N * dy.voxels * ci_n * dy.C)
         assert dW.is_contiguous()
-        lib.call("rtp_wgrad_pw_reduce", ws.data_ptr(), nsplit.value, ci_n, dW.data_ptr(), dW.shape[1], dW.shape[0], ci0, int(accumulate),
-                 _stream())
+        done(lambda: lib.call("rtp_wgrad_pw_reduce", ws.data_ptr(), nsplit.value, ci_n, dW.data_ptr(), dW.shape[1], dW.shape[0], ci0,
+                              int(accumulate), _stream()))
         return
     Cin8 = ceil_to(ci_n, 8)
     NP = ceil_to(dy.C, 16)
@@ -636,16 +691,19 @@ def conv_wgrad(x, dy, k, stride, dW, accumulate=False, ci0=0, n0=0, more=(), tap
     groups = (nblocks + per_cta - 1) // per_cta
     nsplit = max(1, min(ntiles, (2 * num_sms()) // groups))
     d.nsplit = nsplit
-    ws = workspace(lib.load().rtp_wgrad_workspace_bytes(Cin8, NP, len(taps), nsplit), x.buf.device, "wgrad")
+    ws, done = _split_ws("wgrad", lib.load().rtp_wgrad_workspace_bytes(Cin8, NP, len(taps), nsplit), x.buf.device)
     d.workspace = ws.data_ptr()
     key = ("wgrad_generic", ci_n, dy.C, len(taps), stride, 1, (dy.Z, dy.X, dy.Y))
     ev = _prof_begin(key)
     lib.call("rtp_wgrad", C.byref(d), _stream())
     _prof_end(key, ev, 2.0 * rows * ci_n * dy.C * len(taps))
-    for gw, acc, c0, nn in ((dW, accumulate, ci0, n0),) + tuple(more):
-        assert gw.is_contiguous()
-        lib.call("rtp_wgrad_reduce", ws.data_ptr(), nsplit, Cin8, NP, len(taps), gw.data_ptr(), gw.shape[1], gw.shape[0],
-                 nn, c0, ci_n, int(acc), _stream())
+
+    def reduce_all():
+        for gw, acc, c0, nn in ((dW, accumulate, ci0, n0),) + tuple(more):
+            assert gw.is_contiguous()
+            lib.call("rtp_wgrad_reduce", ws.data_ptr(), nsplit, Cin8, NP, len(taps), gw.data_ptr(), gw.shape[1], gw.shape[0],
+                     nn, c0, ci_n, int(acc), _stream())
+    done(reduce_all)
 
 
 # ------------------------------------------------------------------------------------------------ GroupNorm
@@ -760,11 +818,16 @@ def on_wgrad_stream(x, fn):
         return
     if not ASYNC_WGRAD:
         return fn()
+    global _cur_side
     st = _side_stream(dev)
     st["stream"].wait_stream(torch.cuda.current_stream(dev))
     st["busy"] = True
     with torch.cuda.stream(st["stream"]):
-        fn()
+        _cur_side = st
+        try:
+            fn()
+        finally:
+            _cur_side = None
 
 
 def gn_apply_s2d(x, G, stats, gamma, beta, out):
