@@ -433,6 +433,23 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     launches = launches_per_step * args.steps if use_graph else lib.launch_count
     ms = e0.elapsed_time(e1) / args.steps
+    if args.timeline:
+        # diagnostic only (never a bench value): CUPTI kernel records of two replayed steps -> per-kernel (stream, start,
+        # duration); tools/timeline_report.py turns them into busy / idle / overlap figures
+        from torch.profiler import profile, ProfilerActivity
+        with profile(activities=[ProfilerActivity.CUDA]) as tp:
+            for _ in range(2):
+                step()
+            torch.cuda.synchronize()
+        rows = [{"name": e.name, "stream": getattr(e, "stream", None) if hasattr(e, "stream") else None,
+                 "ts": e.time_range.start, "dur": e.time_range.end - e.time_range.start} for e in tp.events()
+                if str(e.device_type).endswith("CUDA")]
+        with open(args.timeline, "w") as f:
+            json.dump(rows, f)
+        try:
+            tp.export_chrome_trace(args.timeline + ".trace.json")
+        except Exception as ex:
+            print("bench: chrome trace export failed: %r" % (ex,), file=sys.stderr)
     # ---- per-kernel durations for the roofline: the same step, issued eagerly with the weight gradients in-stream so
     #      that every CUDA-event pair brackets exactly one kernel running alone (in the timed region kernels of the
     #      wgrad side stream overlap the main stream, and event timing inside a replayed graph is not available)
@@ -874,6 +891,7 @@ def main():
     ap.add_argument("--serial-branches", action="store_true", help="run the HR-module branches one after the other on one stream")
     ap.add_argument("--sync-wgrad", action="store_true", help="run weight gradients in-stream (no side stream)")
     ap.add_argument("--no-extras", action="store_true", help="skip e2e / cpu_baseline / inference legs")
+    ap.add_argument("--timeline", default=None, help="diagnostic: write the CUPTI kernel timeline of two replayed steps to this JSON file")
     ap.add_argument("--no-optimizer", action="store_true", help="time forward+backward only (no fused clip+Adam step)")
     ap.add_argument("--dcn-head", action="store_true", help="configs[4]: the deformable head (dcn_head='fold_z') on the det3d-style model")
     ap.add_argument("--late-allreduce", action="store_true", help="N > 1: one all-reduce after backward instead of overlapped slices (A/B)")

@@ -621,6 +621,8 @@ extern "C" int rtp_fuse_sum(const rtp_fuse_desc* d, void* stream) {
   RTP_LAUNCH_CHECK();
 }
 
+int rtp_upsample_bwd_yx_mma(const rtp_p8& dout, const rtp_p8& t2, int C8, void* stream);  // upsample_mma.cu
+
 extern "C" int64_t rtp_upsample_bwd_workspace_bytes(rtp_p8 dout, rtp_p8 dlow, int32_t C) {
   // two intermediates: [Z][X][Yl] and [Z][Xl][Yl] (P8, padded planes)
   const int64_t C8 = ceil_div(C, 8);
@@ -652,7 +654,14 @@ extern "C" int rtp_upsample_bwd(rtp_p8 dout, rtp_p8 dlow, int32_t C, int32_t acc
   // rows a tile can need: hi(l1) - lo(l0) + 1 <= (kTXL + 1) / scale + 3 in exact arithmetic; one more for fp32 rounding
   const int nrows_max = sxh > 0.f ? (int)ceilf((float)(kTXL + 1) / sxh) + 4 : 0;
   const size_t smem = (size_t)nrows_max * dlow.Y * 32;
-  if (!no_fused && sxh > 0.f && dlow.Y > 1 && dout.Y > 1 && smem <= 96 * 1024) {
+  int mma_taken = 0;
+  if (!no_fused && sxh > 0.f && dlow.Y > 1 && dout.Y > 1) {
+    // y reduction on the tensor cores, x reduction thread-local (upsample_mma.cu); 0 = shape not supported
+    mma_taken = rtp_upsample_bwd_yx_mma(dout, t2, C8, stream);
+    if (mma_taken < 0) return -1;
+  }
+  if (mma_taken) {
+  } else if (!no_fused && sxh > 0.f && dlow.Y > 1 && dout.Y > 1 && smem <= 96 * 1024) {
     static size_t configured_dev[RTP_MAX_DEVICES];  /* the opt-in is per device */
   size_t& configured = configured_dev[rtp_current_device()];
     if (smem > configured) {

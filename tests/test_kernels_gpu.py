@@ -225,6 +225,42 @@ def test_fuse_sum_and_upsample_bwd():
         close(d.to_ncdhw(), 2 * u.grad, tol=2 * BF16_ULP, what="upsample bwd acc")
 
 
+UPBWD_MMA_CASES = [
+    # (N, C, full grid (Z, Y, X), low grid): Y % 16 == 0 and Yl <= 32 -> upsample_mma.cu (y reduction on the tensor cores)
+    (2, 16, (4, 64, 40), (2, 32, 20)),   # ratio 2: two 16-row blocks of yl, four k16 steps, banded weights
+    (2, 16, (4, 64, 40), (1, 16, 10)),   # ratio 4 (one z plane at low resolution)
+    (1, 24, (2, 64, 56), (2, 8, 7)),     # ratio 8, three channel chunks
+    (2, 8, (2, 32, 24), (1, 16, 12)),    # half -> quarter resolution: two k16 steps
+    (1, 8, (3, 48, 17), (2, 20, 9)),     # odd extents, three k16 steps, non-integer ratio
+    (1, 8, (2, 16, 160), (2, 8, 80)),    # long x extent: several row chunks per unit, rolling accumulators across chunks
+]
+
+
+@pytest.mark.parametrize("case", UPBWD_MMA_CASES, ids=str)
+def test_upsample_bwd_tensor_core_path(case):
+    """rtp_upsample_bwd with the y reduction on mma.sync and the thread-local x reduction (csrc/upsample_mma.cu) against
+    autograd of F.interpolate (trilinear, align_corners=True); fixed summation order; accumulate mode."""
+    from rtpose_b200 import ops
+    from rtpose_b200.p8 import P8
+    N, C, hi, lo = case
+    u = rnd(N, C, *lo, seed=31).requires_grad_(True)
+    up = F.interpolate(u, size=hi, mode="trilinear", align_corners=True)
+    g = rnd(N, C, *hi, seed=32)
+    up.backward(g)
+    gp = to_p8(g)
+    d = P8(N, C, *lo)
+    ops.upsample_bwd(gp, d)
+    torch.cuda.synchronize()
+    close(d.to_ncdhw(), u.grad, what="upsample bwd (mma) %s -> %s" % (hi, lo))
+    first = d.to_ncdhw().clone()
+    ops.upsample_bwd(gp, d)  # fixed summation order: run-to-run identical
+    torch.cuda.synchronize()
+    assert torch.equal(first, d.to_ncdhw())
+    ops.upsample_bwd(gp, d, accumulate=True)
+    torch.cuda.synchronize()
+    close(d.to_ncdhw(), 2 * u.grad, tol=2 * BF16_ULP, what="upsample bwd (mma) accumulate")
+
+
 def test_grad_add_channel_sum_stem():
     from rtpose_b200 import lib, ops
     from rtpose_b200.p8 import P8, _stream
