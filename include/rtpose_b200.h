@@ -139,6 +139,16 @@ int rtp_weight_pack_k3s1(const float* w, void* dst_bf16, int32_t Cout, int32_t C
  * per-group packs of the space-to-depth dgrad, without materialising the slice. */
 int rtp_weight_pack_k3s1_window(const float* w, void* dst_bf16, int32_t Cout, int32_t Cin_total, int32_t ci0, int32_t ci_n,
                                 int32_t KP, int32_t NPo, int32_t transpose_flip, void* stream);
+/* All weight packs of a training step in one launch (the optimizer rewrites every weight, so every pack is rebuilt each
+ * step: ops.PackedWeights.refresh_async).  jobs_dev: device array; kind 0 = rtp_weight_pack (flag = mode, ntaps), kind 1 =
+ * rtp_weight_pack_k3s1[_window] (NP = NPo, flag = transpose_flip); block0 / nblocks: the job's range of 256-thread blocks,
+ * ascending and contiguous from 0; total_blocks = their sum. */
+typedef struct {
+  const void* w;
+  void* dst;
+  int32_t kind, Cout, Cin_total, ntaps, ci0, ci_n, KP, NP, flag, block0, nblocks, reserved;
+} rtp_pack_job;
+int rtp_weight_pack_batch(const rtp_pack_job* jobs_dev, int32_t njobs, int32_t total_blocks, void* stream);
 typedef struct {
   rtp_p8 in, out, res, mask;
   const void* w;

@@ -224,10 +224,10 @@ extern "C" int rtp_ingest_pack(const void* raw_f16, int32_t N, int32_t D, int32_
 // ---------------------------------------------------------------------------------------------- weights
 // w fp32 [Cout][Cin][ntaps] -> dst bf16 [tap][KP/8][NP][8]
 //   mode 0: k = ci - ci0 (ci in [ci0, ci0+ci_n)), n = co ;  mode 1: k = co, n = ci - ci0
-__global__ void weight_pack_kernel(const float* __restrict__ w, bf16* __restrict__ dst, int Cout, int Cin, int ntaps,
-                                   int ci0, int ci_n, int KP, int NP, int mode) {
+__device__ __forceinline__ void weight_pack_elems(const float* __restrict__ w, bf16* __restrict__ dst, int Cout, int Cin, int ntaps,
+                                                  int ci0, int ci_n, int KP, int NP, int mode, int64_t first, int64_t stride) {
   const int64_t total = (int64_t)ntaps * KP * NP;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+  for (int64_t i = first; i < total; i += stride) {
     const int k8 = i & 7;
     int64_t r = i >> 3;
     const int n = r % NP;
@@ -241,6 +241,11 @@ __global__ void weight_pack_kernel(const float* __restrict__ w, bf16* __restrict
     if (co < Cout && ci < ci_n) v = w[((int64_t)co * Cin + (ci0 + ci)) * ntaps + tap];
     dst[i] = __float2bfloat16(v);
   }
+}
+__global__ void weight_pack_kernel(const float* __restrict__ w, bf16* __restrict__ dst, int Cout, int Cin, int ntaps,
+                                   int ci0, int ci_n, int KP, int NP, int mode) {
+  weight_pack_elems(w, dst, Cout, Cin, ntaps, ci0, ci_n, KP, NP, mode, blockIdx.x * (int64_t)blockDim.x + threadIdx.x,
+                    (int64_t)gridDim.x * blockDim.x);
 }
 extern "C" int rtp_weight_pack(const float* w, void* dst_bf16, int32_t Cout, int32_t Cin, int32_t ntaps, int32_t ci0,
                                int32_t ci_n, int32_t KP, int32_t NP, int32_t mode, void* stream) {
@@ -260,11 +265,11 @@ extern "C" int rtp_weight_pack(const float* w, void* dst_bf16, int32_t Cout, int
 // transpose_flip = 1 builds the dgrad operand: K = Cout, N = Cin, taps mirrored.
 // (Cin_total, ci0): the pack may cover a window [ci0, ci0 + Cin) of the weight's input channels (a group of the
 // space-to-depth dgrad) without the caller materialising the slice.
-__global__ void weight_pack_k3s1_kernel(const float* __restrict__ w, bf16* __restrict__ dst, int Cout, int Cin, int KP,
-                                        int NPo, int tf, int Cin_total, int ci0) {
+__device__ __forceinline__ void weight_pack_k3s1_elems(const float* __restrict__ w, bf16* __restrict__ dst, int Cout, int Cin, int KP,
+                                                       int NPo, int tf, int Cin_total, int ci0, int64_t first, int64_t stride) {
   const int N3 = 3 * NPo;
   const int64_t total = (int64_t)9 * KP * N3;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+  for (int64_t i = first; i < total; i += stride) {
     const int k8 = i & 7;
     int64_t r = i >> 3;
     const int n = r % N3;
@@ -281,6 +286,27 @@ __global__ void weight_pack_k3s1_kernel(const float* __restrict__ w, bf16* __res
     dst[i] = __float2bfloat16(v);
   }
 }
+__global__ void weight_pack_k3s1_kernel(const float* __restrict__ w, bf16* __restrict__ dst, int Cout, int Cin, int KP,
+                                        int NPo, int tf, int Cin_total, int ci0) {
+  weight_pack_k3s1_elems(w, dst, Cout, Cin, KP, NPo, tf, Cin_total, ci0, blockIdx.x * (int64_t)blockDim.x + threadIdx.x,
+                         (int64_t)gridDim.x * blockDim.x);
+}
+// Every pack of a training step in ONE launch: block b serves the job whose block range [block0, block0 + nblocks) holds b
+// (binary search over the table).  ~130 separate 2-us launches formed a 0.34 ms serial chain in front of the first conv.
+__global__ void __launch_bounds__(256) weight_pack_batch_kernel(const rtp_pack_job* __restrict__ jobs, int njobs) {
+  int lo = 0, hi = njobs - 1;
+  const int b = blockIdx.x;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (jobs[mid].block0 <= b) lo = mid; else hi = mid - 1;
+  }
+  const rtp_pack_job j = jobs[lo];
+  const int64_t first = (int64_t)(b - j.block0) * 256 + threadIdx.x, stride = (int64_t)j.nblocks * 256;
+  if (j.kind == 0)
+    weight_pack_elems((const float*)j.w, (bf16*)j.dst, j.Cout, j.Cin_total, j.ntaps, j.ci0, j.ci_n, j.KP, j.NP, j.flag, first, stride);
+  else
+    weight_pack_k3s1_elems((const float*)j.w, (bf16*)j.dst, j.Cout, j.ci_n, j.KP, j.NP, j.flag, j.Cin_total, j.ci0, first, stride);
+}
 static int weight_pack_k3s1_launch(const float* w, void* dst_bf16, int Cout, int Cin, int KP, int NPo, int transpose_flip,
                                    int Cin_total, int ci0, void* stream) {
   RTP_CHECK_ARG(w && dst_bf16, "rtp_weight_pack_k3s1: null pointer");
@@ -291,6 +317,11 @@ static int weight_pack_k3s1_launch(const float* w, void* dst_bf16, int Cout, int
   const int64_t total = (int64_t)9 * KP * 3 * NPo;
   weight_pack_k3s1_kernel<<<ceil_div(total, 256) > 1024 ? 1024 : ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(
       w, (bf16*)dst_bf16, Cout, Cin, KP, NPo, transpose_flip, Cin_total, ci0);
+  RTP_LAUNCH_CHECK();
+}
+extern "C" int rtp_weight_pack_batch(const rtp_pack_job* jobs_dev, int32_t njobs, int32_t total_blocks, void* stream) {
+  RTP_CHECK_ARG(jobs_dev && njobs > 0 && total_blocks > 0, "rtp_weight_pack_batch: bad arguments");
+  weight_pack_batch_kernel<<<total_blocks, 256, 0, (cudaStream_t)stream>>>(jobs_dev, njobs);
   RTP_LAUNCH_CHECK();
 }
 extern "C" int rtp_weight_pack_k3s1(const float* w, void* dst_bf16, int32_t Cout, int32_t Cin, int32_t KP, int32_t NPo,

@@ -139,66 +139,74 @@ __global__ void __launch_bounds__(256) box_sums_partial_kernel(P8 dy, float* __r
   }
 }
 
-// one block: S = sum of the partials, T by inclusion-exclusion, then dW / dgamma / dbeta (see the file header)
-__global__ void __launch_bounds__(256) fold_wgrad_kernel(const float* __restrict__ dwp, const float* __restrict__ w,
-                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                         const float* __restrict__ partial, int N, int C8dy, float* __restrict__ dw,
-                                                         float* __restrict__ dgamma, float* __restrict__ dbeta, int Cout, int Cin,
-                                                         int acc_w, int acc_gb) {
-  extern __shared__ float fw_smem[];  // S[Cout][8], T[Cout][27]
-  float* S = fw_smem;
-  float* T = fw_smem + Cout * 8;
-  for (int i = threadIdx.x; i < Cout * 8; i += 256) {
-    const int co = i >> 3, a = i & 7;
-    const int c8 = co >> 3, j = co & 7;
+// One block per output channel co: S[co][A] = fixed-order sum of the box-sum partials (warp A, fp64), T[co][tap] by
+// inclusion-exclusion (also written to Tg for the gamma / beta kernel), then dW[co][:][:] (see the file header).  (A single
+// 256-thread block did all of this in 116 us per launch, on the weight-gradient stream of every shared stride-2 conv.)
+__global__ void __launch_bounds__(256) fold_wgrad_dw_kernel(const float* __restrict__ dwp, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, const float* __restrict__ partial, int N,
+                                                            int C8dy, float* __restrict__ dw, float* __restrict__ Tg, int Cin,
+                                                            int acc_w) {
+  __shared__ float S[8], T[27];
+  const int co = blockIdx.x, c8 = co >> 3, j = co & 7;
+  const int a = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  {
     double s = 0;
-    for (int n = 0; n < N; ++n)
-      for (int slab = 0; slab < kBoxSlabs; ++slab) s += partial[(((size_t)n * C8dy + c8) * kBoxSlabs + slab) * 64 + a * 8 + j];
-    S[i] = (float)s;
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < Cout * 27; i += 256) {
-    const int co = i / 27, k = i % 27;
-    const int kz = k / 9, ky = (k / 3) % 3, kx = k % 3;
-    const int a = (kz == 0 ? 4 : 0) | (kx == 0 ? 2 : 0) | (ky == 0 ? 1 : 0);  // axes on which the tap needs o >= 1
-    float t = 0.f;
-    for (int b = 0; b < 8; ++b) {
-      if ((b & a) != b) continue;
-      const float v = S[co * 8 + b];
-      t += (__popc(b) & 1) ? -v : v;
-    }
-    T[i] = t;
-  }
-  __syncthreads();
-  const int total = Cout * Cin * 27;
-  for (int i = threadIdx.x; i < total; i += 256) {
-    const int k = i % 27, r = i / 27;
-    const int ci = r % Cin, co = r / Cin;
-    const float v = gamma[ci] * dwp[i] + beta[ci] * T[co * 27 + k];
-    dw[i] = acc_w ? dw[i] + v : v;
-  }
-  // eight lanes per input channel (co = sub, sub + 8, ...), combined with a fixed xor tree
-  const int sub = threadIdx.x & 7;
-  for (int ci0 = 0; ci0 < Cin; ci0 += 32) {
-    const int ci = ci0 + ((int)threadIdx.x >> 3);
-    double g = 0, b = 0;
-    if (ci < Cin) {
-      for (int co = sub; co < Cout; co += 8)
-        for (int k = 0; k < 27; ++k) {
-          const float wv = w[((int64_t)co * Cin + ci) * 27 + k];
-          g += (double)wv * (double)dwp[((int64_t)co * Cin + ci) * 27 + k];
-          b += (double)wv * (double)T[co * 27 + k];
-        }
+    const int total = N * kBoxSlabs;  // (n, slab) pairs, lane-strided, then a fixed xor tree
+    for (int i = lane; i < total; i += 32) {
+      const int n = i / kBoxSlabs, slab = i - n * kBoxSlabs;
+      s += partial[(((size_t)n * C8dy + c8) * kBoxSlabs + slab) * 64 + a * 8 + j];
     }
 #pragma unroll
-    for (int o = 4; o > 0; o >>= 1) {
-      g += __shfl_xor_sync(0xffffffffu, g, o);
-      b += __shfl_xor_sync(0xffffffffu, b, o);
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) S[a] = (float)s;
+  }
+  __syncthreads();
+  if (threadIdx.x < 27) {
+    const int k = threadIdx.x;
+    const int kz = k / 9, ky = (k / 3) % 3, kx = k % 3;
+    const int m = (kz == 0 ? 4 : 0) | (kx == 0 ? 2 : 0) | (ky == 0 ? 1 : 0);  // axes on which the tap needs o >= 1
+    float t = 0.f;
+    for (int b = 0; b < 8; ++b) {
+      if ((b & m) != b) continue;
+      const float v = S[b];
+      t += (__popc(b) & 1) ? -v : v;
     }
-    if (sub == 0 && ci < Cin) {
-      dgamma[ci] = acc_gb ? dgamma[ci] + (float)g : (float)g;
-      dbeta[ci] = acc_gb ? dbeta[ci] + (float)b : (float)b;
-    }
+    T[k] = t;
+    Tg[co * 27 + k] = t;
+  }
+  __syncthreads();
+  const int total = Cin * 27;
+  const size_t base = (size_t)co * total;
+  for (int i = threadIdx.x; i < total; i += 256) {
+    const int k = i % 27, ci = i / 27;
+    const float v = gamma[ci] * dwp[base + i] + beta[ci] * T[k];
+    dw[base + i] = acc_w ? dw[base + i] + v : v;
+  }
+}
+
+// dgamma[ci] / dbeta[ci]: eight lanes per input channel (co = sub, sub + 8, ...), combined with a fixed xor tree; 32 ci per block
+__global__ void __launch_bounds__(256) fold_wgrad_gb_kernel(const float* __restrict__ dwp, const float* __restrict__ w,
+                                                            const float* __restrict__ Tg, float* __restrict__ dgamma,
+                                                            float* __restrict__ dbeta, int Cout, int Cin, int acc_gb) {
+  const int sub = threadIdx.x & 7;
+  const int ci = blockIdx.x * 32 + ((int)threadIdx.x >> 3);
+  double g = 0, b = 0;
+  if (ci < Cin) {
+    for (int co = sub; co < Cout; co += 8)
+      for (int k = 0; k < 27; ++k) {
+        const float wv = w[((int64_t)co * Cin + ci) * 27 + k];
+        g += (double)wv * (double)dwp[((int64_t)co * Cin + ci) * 27 + k];
+        b += (double)wv * (double)Tg[co * 27 + k];
+      }
+  }
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) {
+    g += __shfl_xor_sync(0xffffffffu, g, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+  if (sub == 0 && ci < Cin) {
+    dgamma[ci] = acc_gb ? dgamma[ci] + (float)g : (float)g;
+    dbeta[ci] = acc_gb ? dbeta[ci] + (float)b : (float)b;
   }
 }
 
@@ -223,7 +231,8 @@ extern "C" int rtp_s2d_border_bias(const float* bias_cls, rtp_p8 r, int32_t C, v
   RTP_LAUNCH_CHECK();
 }
 
-extern "C" int64_t rtp_s2d_box_sums_workspace_bytes(int32_t N, int32_t C8) { return (int64_t)N * C8 * kBoxSlabs * 64 * 4; }
+// box-sum partials [N][C8][kBoxSlabs][64], then T[Cout <= 256][27]
+extern "C" int64_t rtp_s2d_box_sums_workspace_bytes(int32_t N, int32_t C8) { return ((int64_t)N * C8 * kBoxSlabs * 64 + 256 * 27) * 4; }
 
 extern "C" int rtp_s2d_fold_wgrad(rtp_p8 dy, const float* dw_xhat, const float* w, const float* gamma, const float* beta,
                                   float* workspace, float* dW, float* dgamma, float* dbeta, int32_t Cout, int32_t Cin,
@@ -233,8 +242,8 @@ extern "C" int rtp_s2d_fold_wgrad(rtp_p8 dy, const float* dw_xhat, const float* 
   P8 t(dy);
   t.C8 = ceil_div(Cout, 8);
   box_sums_partial_kernel<<<dim3(kBoxSlabs, t.C8, t.N), 256, 0, (cudaStream_t)stream>>>(t, workspace);
-  const size_t smem = (size_t)Cout * (8 + 27) * sizeof(float);
-  fold_wgrad_kernel<<<1, 256, smem, (cudaStream_t)stream>>>(dw_xhat, w, gamma, beta, workspace, t.N, t.C8, dW, dgamma, dbeta, Cout,
-                                                           Cin, accumulate_w, accumulate_gb);
+  float* Tg = workspace + (size_t)t.N * t.C8 * kBoxSlabs * 64;
+  fold_wgrad_dw_kernel<<<Cout, 256, 0, (cudaStream_t)stream>>>(dw_xhat, gamma, beta, workspace, t.N, t.C8, dW, Tg, Cin, accumulate_w);
+  fold_wgrad_gb_kernel<<<ceil_div(Cin, 32), 256, 0, (cudaStream_t)stream>>>(dw_xhat, w, Tg, dgamma, dbeta, Cout, Cin, accumulate_gb);
   RTP_LAUNCH_CHECK();
 }

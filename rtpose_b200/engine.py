@@ -518,7 +518,7 @@ class Engine:
                 if g is None:
                     return
                 gb, accb = self._pgrad(self.pb + "final_conv.bias")
-                ops.channel_sum(g, gb, accumulate=accb)
+                ops.on_aux_stream(g, lambda: ops.channel_sum(g, gb, accumulate=accb))
                 gw, accw = self._pgrad(self.pb + "final_conv.weight")
                 if not accw:
                     pass  # every input-channel slice is written below exactly once
@@ -565,7 +565,7 @@ class Engine:
                     gw, acc = self._pgrad(q + name + ".2.weight")
                     ops.conv_wgrad_async(tv, o.grad, 3, 1, gw, accumulate=acc)
                     gb, accb = self._pgrad(q + name + ".2.bias")
-                    ops.channel_sum(o.grad, gb, accumulate=accb)
+                    ops.on_aux_stream(o.grad, lambda o=o, gb=gb, accb=accb: ops.channel_sum(o.grad, gb, accumulate=accb))
                     dy = o.grad
                     if dy.C8 == 1 and dy.n_stride >= 2 * dy.c_stride:  # gradient with a zeroed spare chunk (loss())
                         dy = P8(dy.N, 16, dy.Z, dy.Y, dy.X, buf=dy.buf, offset=dy.offset, n_stride=dy.n_stride,
@@ -576,7 +576,7 @@ class Engine:
                 ops.conv_wgrad_async(f, tg, 3, 1, gw_r, accumulate=acc_r, n0=0, more=((gw_h, acc_h, 0, hc),))
                 for name, c0 in (("reg", 0), ("hm", hc)):
                     gb, accb = self._pgrad(q + name + ".0.bias")
-                    ops.channel_sum(tg.channels(c0, hc), gb, accumulate=accb)
+                    ops.on_aux_stream(tg, lambda c0=c0, gb=gb, accb=accb: ops.channel_sum(tg.channels(c0, hc), gb, accumulate=accb))
                 gf, accf = self._grad_of(f)
                 ops.conv_dgrad(self.packs, tg, w0, 1, gf, mask=f if f.relu_out else None, accumulate=accf, key=wkey,
                                version=wver)

@@ -55,6 +55,12 @@ class ConatDesc(C.Structure):
                 ("out_c8", C.c_int32), ("relu", C.c_int32)]
 
 
+class PackJob(C.Structure):  # rtp_pack_job
+    _fields_ = [("w", C.c_void_p), ("dst", C.c_void_p), ("kind", C.c_int32), ("Cout", C.c_int32), ("Cin_total", C.c_int32),
+                ("ntaps", C.c_int32), ("ci0", C.c_int32), ("ci_n", C.c_int32), ("KP", C.c_int32), ("NP", C.c_int32),
+                ("flag", C.c_int32), ("block0", C.c_int32), ("nblocks", C.c_int32), ("reserved", C.c_int32)]
+
+
 class NpyInfo(C.Structure):
     _fields_ = [("ndim", C.c_int32), ("elem_bytes", C.c_int32), ("fortran_order", C.c_int32), ("reserved_", C.c_int32),
                 ("shape", C.c_int64 * 8), ("data_offset", C.c_int64), ("file_bytes", C.c_int64), ("descr", C.c_char * 16)]
@@ -77,6 +83,7 @@ PROTOTYPES = {
     "rtp_weight_pack": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "rtp_conv": (C.c_int, [C.POINTER(ConvDesc), _vp]),
     "rtp_conv_multi": (C.c_int, [C.POINTER(ConvDesc), _i32, _vp]),
+    "rtp_weight_pack_batch": (C.c_int, [_vp, _i32, _i32, _vp]),
     "rtp_weight_pack_k3s1": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "rtp_weight_pack_k3s1_window": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "rtp_conv_k3s1": (C.c_int, [C.POINTER(ConvK3S1Desc), _vp]),
@@ -193,14 +200,14 @@ def require_device():
 
 # kernels launched per C-ABI call (for the bench's `gpu_launches` claim)
 LAUNCHES = {"rtp_pack_ncdhw": 1, "rtp_unpack_ncdhw": 1, "rtp_ingest_pack": 1, "rtp_weight_pack": 1,
-            "rtp_weight_pack_k3s1": 1, "rtp_weight_pack_k3s1_window": 1, "rtp_conv": 1, "rtp_conv_k3s1": 1, "rtp_wgrad": 1, "rtp_wgrad_reduce": 1,
+            "rtp_weight_pack_k3s1": 1, "rtp_weight_pack_k3s1_window": 1, "rtp_weight_pack_batch": 1, "rtp_conv": 1, "rtp_conv_k3s1": 1, "rtp_wgrad": 1, "rtp_wgrad_reduce": 1,
             "rtp_gn_sums": 2, "rtp_gn_finalize": 1, "rtp_gn_apply": 1, "rtp_gn_bwd_reduce": 2, "rtp_gn_bwd_apply": 1,
             "rtp_fuse_sum": 1, "rtp_upsample_bwd": 2, "rtp_grad_add": 1, "rtp_channel_sum": 2, "rtp_stem_fwd": 1,
             "rtp_stem_bwd": 2, "rtp_head_loss": 2, "rtp_decode": 1, "rtp_scale_f32": 1, "rtp_dcn_fwd": 1,
             "rtp_dcn_bwd_input": 1, "rtp_dcn_bwd_weight": 1, "rtp_mdcn_fwd": 1, "rtp_mdcn_bwd_input": 1, "rtp_mdcn_bwd_weight": 2, "rtp_adam_step": 2, "rtp_adam_step_dev": 2,
             "rtp_assign_targets": 2, "rtp_wgrad_k3s1": 1, "rtp_wgrad_k3s1_reduce": 1, "rtp_conv_pw": 1, "rtp_gn_apply_s2d": 1, "rtp_gn_bwd_reduce_s2d": 2,
             "rtp_gn_bwd_apply_s2d": 1, "rtp_conv_k3s1_stat_finalize": 1, "rtp_conv_multi": 1, "rtp_gn_stats": 2,
-            "rtp_wgrad_s2d": 1, "rtp_wgrad_s2d_reduce": 1, "rtp_s2d_fold_weights": 2, "rtp_s2d_border_bias": 1, "rtp_s2d_fold_wgrad": 2, "rtp_wgrad_pw": 1, "rtp_wgrad_pw_reduce": 1,
+            "rtp_wgrad_s2d": 1, "rtp_wgrad_s2d_reduce": 1, "rtp_s2d_fold_weights": 2, "rtp_s2d_border_bias": 1, "rtp_s2d_fold_wgrad": 3, "rtp_wgrad_pw": 1, "rtp_wgrad_pw_reduce": 1,
             "rtp_conat_fwd": 1, "rtp_conat_supported": 0, "rtp_s2d_box_sums_workspace_bytes": 0,
             "rtp_npy_probe": 0, "rtp_npy_read_roi_slab": 0}  # host-only file readers
 launch_count = 0

@@ -2,6 +2,7 @@
 workspace and activation-buffer pooling.  Everything here launches on torch's current CUDA stream.
 """
 import ctypes as C
+import os as _os
 
 import torch
 
@@ -118,6 +119,8 @@ class PackedWeights:
 
     def __init__(self):
         self.cache = {}      # key -> (version, packed value, weakref to the source weight, repack(w) or None)
+        self.jobs = {}       # key -> job of the batched repack (entries with a live, contiguous source weight)
+        self._batch = None   # (signature, device job table, njobs, total blocks) of the last refresh_async()
         self._side = None    # stream of a refresh_async() still to be joined by the first consumer
 
     def _lookup(self, key, w, ver, explicit):
@@ -131,7 +134,7 @@ class PackedWeights:
         same = explicit or (ref is not None and ref() is w)
         return (val if (same and hver == ver and hver is not None) else None), val
 
-    def _store(self, key, w, ver, val, explicit, repack):
+    def _store(self, key, w, ver, val, explicit, repack, job=None):
         import weakref
         ref = None
         if not explicit:
@@ -140,6 +143,10 @@ class PackedWeights:
             except TypeError:
                 ref = None
         self.cache[key] = (ver, val, ref, repack if ref is not None else None)
+        if ref is not None and job is not None and w.is_contiguous():
+            self.jobs[key] = job  # (kind, dst tensor, Cout, Cin_total, ntaps, ci0, ci_n, KP, NP, flag): rtp_weight_pack_batch
+        else:
+            self.jobs.pop(key, None)
 
     def get(self, w, mode, ci0=0, ci_n=None, key=None, version=None):
         Cout, Cin = w.shape[0], w.shape[1]
@@ -162,7 +169,7 @@ class PackedWeights:
             lib.call("rtp_weight_pack", wc.data_ptr(), dst.data_ptr(), Cout, Cin, ntaps, ci0, ci_n, KP, NP, mode, _stream())
         repack(w)
         val = (dst, KP, NP)
-        self._store(key, w, ver, val, explicit, repack)
+        self._store(key, w, ver, val, explicit, repack, (0, dst, Cout, Cin, ntaps, ci0, ci_n, KP, NP, mode))
         return val
 
     def get_k3s1(self, w, K, NPo, transpose_flip, key=None, version=None, ci_window=None):
@@ -186,7 +193,8 @@ class PackedWeights:
             lib.call("rtp_weight_pack_k3s1", wc.data_ptr(), dst.data_ptr(), shape[0], shape[1], K, NPo,
                      int(bool(transpose_flip)), _stream())
         repack(w)
-        self._store(key, w, ver, dst, explicit, repack)
+        cw = ci_window if ci_window is not None else (0, shape[1])
+        self._store(key, w, ver, dst, explicit, repack, (1, dst, shape[0], shape[1], 27, cw[0], cw[1], K, NPo, int(bool(transpose_flip))))
         return dst
 
     def refresh_async(self):
@@ -195,12 +203,14 @@ class PackedWeights:
         lazily, one small kernel at a time, in front of each conv.  Entries built from per-step temporaries (explicit
         keys) are only invalidated."""
         dev = None
+        live = []
         for k in list(self.cache):
             ver, val, ref, repack = self.cache[k]
             w = ref() if ref is not None else None
             if repack is None or w is None:
                 if ref is not None and w is None:
                     del self.cache[k]          # the source tensor is gone
+                    self.jobs.pop(k, None)
                 else:
                     self.cache[k] = (None, val, ref, repack)
                 continue
@@ -210,11 +220,42 @@ class PackedWeights:
                 if _pack_stream is None or _pack_stream.device != dev:
                     _pack_stream = named_stream(dev, "pack")
                 _pack_stream.wait_stream(torch.cuda.current_stream(dev))
-            with torch.cuda.stream(_pack_stream):
-                repack(w)
+            live.append((k, w, repack))
             self.cache[k] = (w._version, val, ref, repack)
-        if dev is not None:
-            self._side = _pack_stream
+        if dev is None:
+            return
+        with torch.cuda.stream(_pack_stream):
+            single = live
+            if BATCH_PACKS:
+                batched = [(k, w) for k, w, _ in live if k in self.jobs]
+                if batched and self._launch_batch(batched, dev):
+                    single = [e for e in live if e[0] not in self.jobs]
+            for _, w, repack in single:
+                repack(w)
+        self._side = _pack_stream
+
+    def _launch_batch(self, batched, dev):
+        """One rtp_weight_pack_batch launch for every (key, weight) of `batched`; the device job table is rebuilt only when
+        the set of jobs (pointers, shapes) changes — never during a stream capture (then the caller repacks one by one)."""
+        import ctypes as C
+        sig = tuple((k, w.data_ptr(), self.jobs[k][1].data_ptr()) for k, w in batched)
+        if self._batch is None or self._batch[0] != sig:
+            if torch.cuda.is_current_stream_capturing():
+                return False
+            table = (lib.PackJob * len(batched))()
+            b0 = 0
+            for j, (k, w) in zip(table, batched):
+                kind, dst, Cout, Cin_total, ntaps, ci0, ci_n, KP, NP, flag = self.jobs[k]
+                total = (ntaps * KP * NP) if kind == 0 else (9 * KP * 3 * NP)
+                nb = max(1, min(64, (total + 2047) // 2048))  # >= 8 elements per thread: ~2400 blocks for the whole network
+                j.w, j.dst, j.kind, j.Cout, j.Cin_total, j.ntaps = w.data_ptr(), dst.data_ptr(), kind, Cout, Cin_total, ntaps
+                j.ci0, j.ci_n, j.KP, j.NP, j.flag, j.block0, j.nblocks = ci0, ci_n, KP, NP, flag, b0, nb
+                b0 += nb
+            host = torch.frombuffer(bytearray(bytes(table)), dtype=torch.uint8)
+            self._batch = (sig, host.to(dev), len(batched), b0)
+        _, tab, n, nblocks = self._batch
+        lib.call("rtp_weight_pack_batch", tab.data_ptr(), n, nblocks, _stream())
+        return True
 
     def invalidate(self):
         """Forces a repack on next use (weights are repacked once per optimizer step in training)."""
@@ -224,6 +265,7 @@ class PackedWeights:
 
 
 _pack_stream = None
+BATCH_PACKS = not bool(_os.environ.get("RTP_NO_BATCH_PACKS"))  # A/B switch: one launch for all packs of a step
 
 
 PROFILE = None  # when a dict: key -> list of (start_event, end_event, algorithmic_flops); used by bench.py
@@ -547,16 +589,16 @@ LANE = 0  # engines that run concurrently on different streams (half-batch lanes
 WGRAD_STREAM_PER_ORIGIN = not bool(_os.environ.get("RTP_ONE_WGRAD_STREAM"))
 
 
-def _side_stream(device):
+def _side_stream(device, kind="wgrad"):
     """Weight-gradient side stream for work forked from the CURRENT stream: one per origin stream (the main stream and each
     branch stream get their own), so the small low-resolution weight gradients of a side branch neither queue behind the
     full-resolution ones nor make them wait for that branch's dY (one shared side stream serialised all of them: with the
     weight gradients skipped the step is 4.8 ms shorter, i.e. they were almost entirely exposed)."""
     origin = _stream() if WGRAD_STREAM_PER_ORIGIN else 0
-    key = (str(device), LANE, origin)
+    key = (str(device), LANE, origin, kind)
     st = _side.get(key)
     if st is None:
-        st = {"stream": named_stream(device, "wgrad%d/%x" % (LANE, origin)), "busy": False, "events": []}
+        st = {"stream": named_stream(device, "%s%d/%x" % (kind, LANE, origin)), "busy": False, "events": []}
         _side[key] = st
     return st
 
@@ -828,6 +870,23 @@ def on_wgrad_stream(x, fn):
             fn()
         finally:
             _cur_side = None
+
+
+def on_aux_stream(x, fn):
+    """Runs fn() on the auxiliary parameter-gradient stream (ordered after the current stream; joined by join_wgrad): the
+    HBM-bound bias-gradient channel sums, which nothing in backward depends on, then run beside the tensor-bound
+    weight-gradient kernels instead of in front of the next dgrad of the main chain."""
+    dev = x.buf.device
+    if not ASYNC_WGRAD or not AUX_STREAM:
+        return fn()
+    st = _side_stream(dev, "aux")
+    st["stream"].wait_stream(torch.cuda.current_stream(dev))
+    st["busy"] = True
+    with torch.cuda.stream(st["stream"]):
+        fn()
+
+
+AUX_STREAM = bool(_os.environ.get("RTP_AUX_STREAM"))  # opt-in: measured slightly SLOWER (19.85 vs 19.75 ms per step) — the sums stretch the weight-gradient kernels they run beside
 
 
 def gn_apply_s2d(x, G, stats, gamma, beta, out):

@@ -253,9 +253,10 @@ int main(int argc, char** argv) {
   if (rtp_npy_probe("/nonexistent/cube.npy", &info) >= 0) return 11;
   if (strstr(rtp_last_error(), "cannot open") == NULL) return 12;
   if (rtp_npy_probe(argv[1], &info) != 0) return 13;
-  printf("%d %lld %lld %lld %s %d %d %d %d %d %d %d\n", info.ndim, (long long)info.shape[0], (long long)info.shape[1],
+  printf("%d %lld %lld %lld %s %d %d %d %d %d %d %d %d %d\n", info.ndim, (long long)info.shape[0], (long long)info.shape[1],
          (long long)info.shape[2], info.descr, (int)sizeof(rtp_p8), (int)sizeof(rtp_conv_desc), (int)sizeof(rtp_npy_info),
-         (int)sizeof(rtp_conv_k3s1_desc), (int)sizeof(rtp_wgrad_desc), (int)sizeof(rtp_fuse_desc), (int)sizeof(rtp_conat_desc));
+         (int)sizeof(rtp_conv_k3s1_desc), (int)sizeof(rtp_wgrad_desc), (int)sizeof(rtp_fuse_desc), (int)sizeof(rtp_conat_desc),
+         (int)sizeof(rtp_pack_job), (int)offsetof(rtp_pack_job, block0));
   printf("%d %d %d %d %d %d %d %d %d %d %d %d %d %d %d %d %d %d\n", (int)offsetof(rtp_conv_desc, w), (int)offsetof(rtp_conv_desc, Cin),
          (int)offsetof(rtp_conv_desc, ntaps), (int)offsetof(rtp_conv_desc, tz), (int)offsetof(rtp_conv_desc, wt),
          (int)offsetof(rtp_conv_desc, RZ), (int)offsetof(rtp_conv_desc, accumulate), (int)offsetof(rtp_conv_k3s1_desc, stat_mode),
@@ -289,7 +290,8 @@ int main(int argc, char** argv) {
     # the ctypes mirrors in rtpose_b200/lib.py have the C compiler's struct sizes (field order, padding)
     import ctypes as C
     assert [int(v) for v in out[5:]] == [C.sizeof(lib.P8Struct), C.sizeof(lib.ConvDesc), C.sizeof(lib.NpyInfo),
-                                         C.sizeof(lib.ConvK3S1Desc), C.sizeof(lib.WgradDesc), C.sizeof(lib.FuseDesc), C.sizeof(lib.ConatDesc)]
+                                         C.sizeof(lib.ConvK3S1Desc), C.sizeof(lib.WgradDesc), C.sizeof(lib.FuseDesc), C.sizeof(lib.ConatDesc),
+                                         C.sizeof(lib.PackJob), lib.PackJob.block0.offset]
 
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference/det3d"), reason="reference tree not present (GPU box)")

@@ -261,6 +261,34 @@ def test_upsample_bwd_tensor_core_path(case):
     close(d.to_ncdhw(), 2 * u.grad, tol=2 * BF16_ULP, what="upsample bwd (mma) accumulate")
 
 
+def test_batched_weight_packs_match_single_launches():
+    """PackedWeights.refresh_async rebuilds every pack with ONE rtp_weight_pack_batch launch: bit-identical to the per-weight
+    launches (generic packs of both modes with an input-channel slice, k3s1 packs plain / transposed / windowed)."""
+    from rtpose_b200 import ops
+    ws = [torch.randn(40, 24, 3, 3, 3, device="cuda"), torch.randn(128, 32, 1, 1, 1, device="cuda"),
+          torch.randn(32, 32, 3, 3, 3, device="cuda"), torch.randn(64, 128, 3, 3, 3, device="cuda")]
+
+    def build(pk):
+        return [pk.get(ws[0], 0)[0], pk.get(ws[0], 1, ci0=8, ci_n=16)[0], pk.get(ws[1], 0)[0], pk.get(ws[1], 1)[0],
+                pk.get_k3s1(ws[2], 32, 32, False), pk.get_k3s1(ws[2], 32, 32, True),
+                pk.get_k3s1(ws[3], 64, 32, True, ci_window=(32, 32)), pk.get_k3s1(ws[3], 128, 64, False)]
+    pk = ops.PackedWeights()
+    packs = build(pk)
+    before = [p.clone() for p in packs]
+    for w in ws:
+        w.mul_(-1.5)  # in place: same storage, new version (what the optimizer does)
+    pk.refresh_async()
+    got = build(pk)  # joins the pack stream; every entry is current again, nothing is repacked here
+    torch.cuda.synchronize()
+    assert pk._batch is not None and pk._batch[2] == len(packs)
+    assert all(g.data_ptr() == p.data_ptr() for g, p in zip(got, packs))
+    ref = build(ops.PackedWeights())  # fresh cache: one launch per pack
+    torch.cuda.synchronize()
+    for g, r, b in zip(got, ref, before):
+        assert torch.equal(g, r)
+        assert not torch.equal(g, b)
+
+
 def test_grad_add_channel_sum_stem():
     from rtpose_b200 import lib, ops
     from rtpose_b200.p8 import P8, _stream
