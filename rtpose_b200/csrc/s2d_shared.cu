@@ -115,10 +115,14 @@ __global__ void __launch_bounds__(256) box_sums_partial_kernel(P8 dy, float* __r
       unpack8(ldg16(base + dy.voxel(z, x, y)), f);
       const int zero = (z == 0 ? 4 : 0) | (x == 0 ? 2 : 0) | (y == 0 ? 1 : 0);
 #pragma unroll
-      for (int a = 0; a < 8; ++a) {
-        if ((a & zero) == a) {
+      for (int j = 0; j < 8; ++j) acc[0][j] += f[j];
+      if (zero) {  // voxels on a low face only (64 predicated adds per vector for everyone cost 81 us per launch)
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[a][j] += f[j];
+        for (int a = 1; a < 8; ++a) {
+          if ((a & zero) == a) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[a][j] += f[j];
+          }
         }
       }
     }
@@ -184,27 +188,26 @@ __global__ void __launch_bounds__(256) fold_wgrad_dw_kernel(const float* __restr
   }
 }
 
-// dgamma[ci] / dbeta[ci]: eight lanes per input channel (co = sub, sub + 8, ...), combined with a fixed xor tree; 32 ci per block
+// dgamma[ci] / dbeta[ci]: one warp per input channel, lane-strided over the Cout * 27 products (fp64), fixed xor tree
 __global__ void __launch_bounds__(256) fold_wgrad_gb_kernel(const float* __restrict__ dwp, const float* __restrict__ w,
                                                             const float* __restrict__ Tg, float* __restrict__ dgamma,
                                                             float* __restrict__ dbeta, int Cout, int Cin, int acc_gb) {
-  const int sub = threadIdx.x & 7;
-  const int ci = blockIdx.x * 32 + ((int)threadIdx.x >> 3);
+  const int lane = threadIdx.x & 31;
+  const int ci = blockIdx.x * 8 + ((int)threadIdx.x >> 5);
+  if (ci >= Cin) return;
   double g = 0, b = 0;
-  if (ci < Cin) {
-    for (int co = sub; co < Cout; co += 8)
-      for (int k = 0; k < 27; ++k) {
-        const float wv = w[((int64_t)co * Cin + ci) * 27 + k];
-        g += (double)wv * (double)dwp[((int64_t)co * Cin + ci) * 27 + k];
-        b += (double)wv * (double)Tg[co * 27 + k];
-      }
+  for (int i = lane; i < Cout * 27; i += 32) {
+    const int co = i / 27, k = i - co * 27;
+    const float wv = w[((int64_t)co * Cin + ci) * 27 + k];
+    g += (double)wv * (double)dwp[((int64_t)co * Cin + ci) * 27 + k];
+    b += (double)wv * (double)Tg[i];
   }
 #pragma unroll
-  for (int o = 4; o > 0; o >>= 1) {
+  for (int o = 16; o > 0; o >>= 1) {
     g += __shfl_xor_sync(0xffffffffu, g, o);
     b += __shfl_xor_sync(0xffffffffu, b, o);
   }
-  if (sub == 0 && ci < Cin) {
+  if (lane == 0) {
     dgamma[ci] = acc_gb ? dgamma[ci] + (float)g : (float)g;
     dbeta[ci] = acc_gb ? dbeta[ci] + (float)b : (float)b;
   }
@@ -244,6 +247,6 @@ extern "C" int rtp_s2d_fold_wgrad(rtp_p8 dy, const float* dw_xhat, const float* 
   box_sums_partial_kernel<<<dim3(kBoxSlabs, t.C8, t.N), 256, 0, (cudaStream_t)stream>>>(t, workspace);
   float* Tg = workspace + (size_t)t.N * t.C8 * kBoxSlabs * 64;
   fold_wgrad_dw_kernel<<<Cout, 256, 0, (cudaStream_t)stream>>>(dw_xhat, gamma, beta, workspace, t.N, t.C8, dW, Tg, Cin, accumulate_w);
-  fold_wgrad_gb_kernel<<<ceil_div(Cin, 32), 256, 0, (cudaStream_t)stream>>>(dw_xhat, w, Tg, dgamma, dbeta, Cout, Cin, accumulate_gb);
+  fold_wgrad_gb_kernel<<<ceil_div(Cin, 8), 256, 0, (cudaStream_t)stream>>>(dw_xhat, w, Tg, dgamma, dbeta, Cout, Cin, accumulate_gb);
   RTP_LAUNCH_CHECK();
 }

@@ -63,6 +63,7 @@ __device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], 
 struct UBM {
   P8 in, out;
   int C8, ntx, txl, nunits, nks;  // x segments per plane, low-resolution x positions per segment, k16 steps per row
+  int nolo;                       // experiment (RTP_UPBWD_NOLO=1): skip the low-part products (bf16 weights)
   uint32_t stage_bytes;
 };
 
@@ -203,7 +204,7 @@ __global__ void __launch_bounds__(kWarps * 32) upsample_bwd_yx_mma_kernel(const 
           for (int ks = 0; ks < 4; ++ks) {
             if (nz & (1u << (mt * 4 + ks))) {
               mma_bf16(d[mt], ah[mt][ks], b[ks >> 1][(ks & 1) * 2], b[ks >> 1][(ks & 1) * 2 + 1]);
-              mma_bf16(d[mt], al[mt][ks], b[ks >> 1][(ks & 1) * 2], b[ks >> 1][(ks & 1) * 2 + 1]);
+              if (!p.nolo) mma_bf16(d[mt], al[mt][ks], b[ks >> 1][(ks & 1) * 2], b[ks >> 1][(ks & 1) * 2 + 1]);
             }
           }
         }
@@ -251,6 +252,8 @@ int rtp_upsample_bwd_yx_mma(const rtp_p8& dout, const rtp_p8& t2, int C8, void* 
   k.out = P8(t2);
   k.C8 = C8;
   k.nks = Y / 16;
+  static const bool nolo = getenv("RTP_UPBWD_NOLO") != nullptr;
+  k.nolo = nolo ? 1 : 0;
   static int nsm = 0;
   if (!nsm) {
     int dev = 0;
