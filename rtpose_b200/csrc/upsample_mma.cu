@@ -63,15 +63,14 @@ __device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], 
 struct UBM {
   P8 in, out;
   int C8, ntx, txl, nunits, nks;  // x segments per plane, low-resolution x positions per segment, k16 steps per row
-  int nolo;                       // experiment (RTP_UPBWD_NOLO=1): skip the low-part products (bf16 weights)
   uint32_t stage_bytes;
 };
 
 constexpr int kStages = 3;  // chunks of kRows full-resolution rows in flight per warp
 constexpr int kRows = 8;
 
-// NMT = 16-row blocks of the low-resolution y extent (1: Yl <= 16, 2: Yl <= 32); Y <= 64, Y % 16 == 0
-template <int NMT>
+// NMT = 16-row blocks of the low-resolution y extent (1: Yl <= 16, 2: Yl <= 32); NKS = Y / 16 k16 steps per row (Y <= 64)
+template <int NMT, int NKS>
 __global__ void __launch_bounds__(kWarps * 32) upsample_bwd_yx_mma_kernel(const __grid_constant__ UBM p) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t bar_full[kWarps][kStages];
@@ -89,20 +88,20 @@ __global__ void __launch_bounds__(kWarps * 32) upsample_bwd_yx_mma_kernel(const 
   }
   __syncwarp();
 
-  // A fragments of the interpolation matrix Wy[yl][y] (row-major m16 x k16 per (mt, ks)), high and low bf16 parts
-  uint32_t ah[NMT][4][4], al[NMT][4][4];
-  uint32_t nz = 0;  // bit mt*4+ks: the block has a non-zero weight somewhere (warp-uniform)
+  // A fragments of the interpolation matrix Wy[yl][y] (row-major m16 x k16 per (mt, ks)), high and low bf16 parts.  Blocks
+  // outside the band of the matrix are all-zero and are multiplied anyway: straight-line code lets the independent
+  // accumulation chains of two rows interleave (per-block branches cost more than the four extra MMAs of the 2x case).
+  uint32_t ah[NMT][NKS][4], al[NMT][NKS][4];
 #pragma unroll
   for (int mt = 0; mt < NMT; ++mt)
 #pragma unroll
-    for (int ks = 0; ks < 4; ++ks) {
-      bool any = false;
+    for (int ks = 0; ks < NKS; ++ks)
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int yl = mt * 16 + g + (i & 1) * 8;
         const int d0 = ks * 16 + 2 * q + (i >> 1) * 8;
         float w0 = 0.f, w1 = 0.f;
-        if (yl < Yl && ks < p.nks) {
+        if (yl < Yl) {
           w0 = d0 < Y ? hat_weight_(d0, yl, sy) : 0.f;
           w1 = d0 + 1 < Y ? hat_weight_(d0 + 1, yl, sy) : 0.f;
         }
@@ -111,10 +110,7 @@ __global__ void __launch_bounds__(kWarps * 32) upsample_bwd_yx_mma_kernel(const 
         const float2 hf = __bfloat1622float2(hb);
         ah[mt][ks][i] = h;
         al[mt][ks][i] = pack_bf16x2(w0 - hf.x, w1 - hf.y);
-        any |= (w0 != 0.f) | (w1 != 0.f);
       }
-      if (__any_sync(0xffffffffu, any)) nz |= 1u << (mt * 4 + ks);
-    }
 
   const int wglobal = blockIdx.x * kWarps + warp, wtotal = gridDim.x * kWarps;
   const uint32_t row_bytes = (uint32_t)p.in.Yp * 16u;
@@ -167,73 +163,91 @@ __global__ void __launch_bounds__(kWarps * 32) upsample_bwd_yx_mma_kernel(const 
     const Unit u = unit_geom(t);
     bf16* out_row0 = p.out.ptr + (int64_t)u.n * p.out.n_stride + (int64_t)u.c8 * p.out.c_stride + p.out.voxel(u.z, 0, 0) + 2 * q;
     const int64_t out_xstride = (int64_t)p.out.Yp * 8;
-    auto flush = [&](int xl, const float (&acc)[NMT][4]) {
-      if (xl < u.xl0 || xl > u.xl1) return;
-      bf16* o = out_row0 + (int64_t)xl * out_xstride;
-#pragma unroll
-      for (int mt = 0; mt < NMT; ++mt)
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int yl = mt * 16 + g + h * 8;
-          if (yl < Yl) *reinterpret_cast<uint32_t*>(o + yl * 8) = pack_bf16x2(acc[mt][2 * h], acc[mt][2 * h + 1]);
-        }
-    };
-    float acc0[NMT][4], acc1[NMT][4];
+    // x reduction state: a full-resolution row contributes to the low-resolution rows xl = a and a + 1; they accumulate in
+    // the even / odd set according to the parity of xl, so advancing a re-uses the registers without moving them
+    float accE[NMT][4], accO[NMT][4];
 #pragma unroll
     for (int mt = 0; mt < NMT; ++mt)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) acc0[mt][i] = acc1[mt][i] = 0.f;
-    int a = (int)(sx * (float)u.r0);  // xl of acc0; acc1 belongs to a + 1
+      for (int i = 0; i < 4; ++i) accE[mt][i] = accO[mt][i] = 0.f;
+    auto flush = [&](int xl, float (&acc)[NMT][4]) {  // store row xl if this unit owns it, then reset the set
+      if (xl >= u.xl0 && xl <= u.xl1) {
+        bf16* o = out_row0 + (int64_t)xl * out_xstride;
+#pragma unroll
+        for (int mt = 0; mt < NMT; ++mt)
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int yl = mt * 16 + g + h * 8;
+            if (yl < Yl) *reinterpret_cast<uint32_t*>(o + yl * 8) = pack_bf16x2(acc[mt][2 * h], acc[mt][2 * h + 1]);
+          }
+      }
+#pragma unroll
+      for (int mt = 0; mt < NMT; ++mt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[mt][i] = 0.f;
+    };
+    int a = (int)(sx * (float)u.r0);
+    // y reduction of one staged row on the tensor cores: separate chains for the high and low weight parts
+    auto yreduce = [&](uint32_t row_s, float (&d)[NMT][4]) {
+      uint32_t b[2][4] = {{0u, 0u, 0u, 0u}, {0u, 0u, 0u, 0u}};
+      ldmatrix_x4_trans(row_s, b[0]);                      // y 0..31: k16 steps 0, 1
+      if (NKS > 2) ldmatrix_x4_trans(row_s + 512u, b[1]);  // y 32..63: k16 steps 2, 3
+      float dl[NMT][4];
+#pragma unroll
+      for (int mt = 0; mt < NMT; ++mt) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) d[mt][i] = dl[mt][i] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < NKS; ++ks) {
+          mma_bf16(d[mt], ah[mt][ks], b[ks >> 1][(ks & 1) * 2], b[ks >> 1][(ks & 1) * 2 + 1]);
+          mma_bf16(dl[mt], al[mt][ks], b[ks >> 1][(ks & 1) * 2], b[ks >> 1][(ks & 1) * 2 + 1]);
+        }
+      }
+#pragma unroll
+      for (int mt = 0; mt < NMT; ++mt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) d[mt][i] += dl[mt][i];
+    };
+    auto xreduce = [&](int r, const float (&d)[NMT][4]) {
+      const int i0 = (int)(sx * (float)r);
+      if (i0 != a) {  // i0 == a + 1 (scale <= 1): row a is complete
+        if (a & 1) flush(a, accO); else flush(a, accE);
+        a = i0;
+      }
+      const float wa = hat_weight_(r, a, sx), wb = hat_weight_(r, a + 1, sx);
+      const float wE = (a & 1) ? wb : wa, wO = (a & 1) ? wa : wb;
+#pragma unroll
+      for (int mt = 0; mt < NMT; ++mt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          accE[mt][i] = fmaf(wE, d[mt][i], accE[mt][i]);
+          accO[mt][i] = fmaf(wO, d[mt][i], accO[mt][i]);
+        }
+    };
     for (int row0 = 0; row0 < u.nrows; row0 += kRows, ++cnt) {
       const int s = cnt % kStages;
       const int rows = min(kRows, u.nrows - row0);
       mbar_wait(&bar_full[warp][s], (cnt / kStages) & 1);
       const uint32_t stage_s = ring_s + (uint32_t)s * p.stage_bytes + (uint32_t)lane * 16u;
-#pragma unroll 2
-      for (int rr = 0; rr < rows; ++rr) {
-        // ---- y reduction of one full-resolution row on the tensor cores
-        uint32_t b[2][4] = {{0u, 0u, 0u, 0u}, {0u, 0u, 0u, 0u}};
-        ldmatrix_x4_trans(stage_s + (uint32_t)rr * row_bytes, b[0]);                        // y 0..31: k16 steps 0, 1
-        if (p.nks > 2) ldmatrix_x4_trans(stage_s + (uint32_t)rr * row_bytes + 512u, b[1]);  // y 32..63: k16 steps 2, 3
-        float d[NMT][4];
-#pragma unroll
-        for (int mt = 0; mt < NMT; ++mt) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) d[mt][i] = 0.f;
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            if (nz & (1u << (mt * 4 + ks))) {
-              mma_bf16(d[mt], ah[mt][ks], b[ks >> 1][(ks & 1) * 2], b[ks >> 1][(ks & 1) * 2 + 1]);
-              if (!p.nolo) mma_bf16(d[mt], al[mt][ks], b[ks >> 1][(ks & 1) * 2], b[ks >> 1][(ks & 1) * 2 + 1]);
-            }
-          }
-        }
-        // ---- x reduction, thread-local: row r contributes to xl = i0 and i0 + 1
-        const int r = u.r0 + row0 + rr;
-        const int i0 = (int)(sx * (float)r);
-        if (i0 != a) {  // i0 == a + 1 (scale <= 1): row a is complete
-          flush(a, acc0);
-#pragma unroll
-          for (int mt = 0; mt < NMT; ++mt)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) { acc0[mt][i] = acc1[mt][i]; acc1[mt][i] = 0.f; }
-          a = i0;
-        }
-        const float w0 = hat_weight_(r, a, sx), w1 = hat_weight_(r, a + 1, sx);
-#pragma unroll
-        for (int mt = 0; mt < NMT; ++mt)
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            acc0[mt][i] = fmaf(w0, d[mt][i], acc0[mt][i]);
-            acc1[mt][i] = fmaf(w1, d[mt][i], acc1[mt][i]);
-          }
+      const int rbase = u.r0 + row0;
+      int rr = 0;
+      for (; rr + 1 < rows; rr += 2) {  // two rows at a time: their MMA chains are independent
+        float d0[NMT][4], d1[NMT][4];
+        yreduce(stage_s + (uint32_t)rr * row_bytes, d0);
+        yreduce(stage_s + (uint32_t)(rr + 1) * row_bytes, d1);
+        xreduce(rbase + rr, d0);
+        xreduce(rbase + rr + 1, d1);
+      }
+      if (rr < rows) {
+        float d0[NMT][4];
+        yreduce(stage_s + (uint32_t)rr * row_bytes, d0);
+        xreduce(rbase + rr, d0);
       }
       // the stage has been consumed (every ldmatrix fed an mma issued above): refill it kStages chunks ahead
       __syncwarp();
       produce(s);
     }
-    flush(a, acc0);
-    flush(a + 1, acc1);
+    if (a & 1) { flush(a, accO); flush(a + 1, accE); } else { flush(a, accE); flush(a + 1, accO); }
   }
 }
 
@@ -252,23 +266,29 @@ int rtp_upsample_bwd_yx_mma(const rtp_p8& dout, const rtp_p8& t2, int C8, void* 
   k.out = P8(t2);
   k.C8 = C8;
   k.nks = Y / 16;
-  static const bool nolo = getenv("RTP_UPBWD_NOLO") != nullptr;
-  k.nolo = nolo ? 1 : 0;
   static int nsm = 0;
   if (!nsm) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
   }
-  // a unit = one x segment of a (sample, chunk, z) plane, streamed kRows rows at a time; a segment re-reads ~1 / scale halo
-  // rows, so segments are as long as load balance allows (>= 6 units per warp when the tensor is large enough)
+  // a unit = one x segment of a (sample, chunk, z) plane, streamed kRows rows at a time.  A segment of txl outputs re-reads
+  // ~1 / scale halo rows (efficiency txl / (txl + 1)); the warps take units round-robin, so the last round should be full
+  // (efficiency rounds / ceil(rounds)): pick the segment count with the best product
   const int64_t planes = (int64_t)dout.N * C8 * dout.Z;
   const int64_t wtotal = (int64_t)nsm * 2 * kWarps;
-  int ntx = (int)((6 * wtotal + planes - 1) / planes);
-  const int ntx_max = Xl / 4 > 1 ? Xl / 4 : 1;
-  if (ntx > ntx_max) ntx = ntx_max;
-  if (ntx < 1) ntx = 1;
-  k.txl = ceil_div(Xl, ntx);
+  const int ntx_max = Xl / 2 > 1 ? Xl / 2 : 1;
+  int best_ntx = 1;
+  double best = -1.0;
+  for (int ntx = 1; ntx <= ntx_max; ++ntx) {
+    const int txl = ceil_div(Xl, ntx);
+    const int ntx_eff = ceil_div(Xl, txl);
+    const double rounds = (double)(ntx_eff * planes) / (double)wtotal;
+    const double balance = rounds / (double)(int64_t)(rounds + 0.999999);
+    const double score = balance * ((double)txl / (double)(txl + 1));
+    if (score > best + 1e-9) { best = score; best_ntx = ntx_eff; }
+  }
+  k.txl = ceil_div(Xl, best_ntx);
   k.ntx = ceil_div(Xl, k.txl);
   const int64_t nunits = (int64_t)k.ntx * planes;
   if (nunits > 0x7fffffff) return 0;
@@ -279,17 +299,20 @@ int rtp_upsample_bwd_yx_mma(const rtp_p8& dout, const rtp_p8& t2, int C8, void* 
   const size_t smem = (size_t)kWarps * kStages * k.stage_bytes + 1024;
   (void)sx;
   const int nmt = Yl > 16 ? 2 : 1;
-  static size_t configured_dev[2][RTP_MAX_DEVICES];  /* the opt-in is per device */
-  size_t& configured = configured_dev[nmt - 1][rtp_current_device()];
+  using Kern = void (*)(const UBM);
+  static const Kern kerns[2][4] = {
+      {upsample_bwd_yx_mma_kernel<1, 1>, upsample_bwd_yx_mma_kernel<1, 2>, upsample_bwd_yx_mma_kernel<1, 3>, upsample_bwd_yx_mma_kernel<1, 4>},
+      {upsample_bwd_yx_mma_kernel<2, 1>, upsample_bwd_yx_mma_kernel<2, 2>, upsample_bwd_yx_mma_kernel<2, 3>, upsample_bwd_yx_mma_kernel<2, 4>}};
+  const Kern kern = kerns[nmt - 1][k.nks - 1];
+  static size_t configured_dev[2][4][RTP_MAX_DEVICES];  /* the opt-in is per device */
+  size_t& configured = configured_dev[nmt - 1][k.nks - 1][rtp_current_device()];
   if (smem > configured) {
-    cudaError_t e = nmt == 2 ? cudaFuncSetAttribute(upsample_bwd_yx_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                             : cudaFuncSetAttribute(upsample_bwd_yx_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { rtp_set_error("rtp_upsample_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -1; }
     configured = smem;
   }
   const int want = ceil_div(k.nunits, kWarps);
   const int grid = want < 2 * nsm ? want : 2 * nsm;
-  if (nmt == 2) upsample_bwd_yx_mma_kernel<2><<<grid, kWarps * 32, smem, (cudaStream_t)stream>>>(k);
-  else upsample_bwd_yx_mma_kernel<1><<<grid, kWarps * 32, smem, (cudaStream_t)stream>>>(k);
+  kern<<<grid, kWarps * 32, smem, (cudaStream_t)stream>>>(k);
   return 1;
 }

@@ -806,20 +806,28 @@ def conv_wgrad_s2d(xs, dy, Cin, dW, accumulate=False):
     Cin8 = ceil_to(Cin, 8)
     NP = ceil_to(dy.C, 16)
     L = lib.load()
+    # the plane-streaming kernel holds 6 accumulators [128 x 2 NP] in TMEM: NP = 32; wider outputs go out as 32-channel slices
+    # of dY (dW rows [32 h, 32 h + 32)), each re-reading the L2-resident view
+    nslice = NP // 32 if (NP > 32 and dy.C % 32 == 0 and dW.shape[0] == dy.C) else 1
+    NPs = 32 if nslice > 1 else NP
     if (USE_WGRAD_S2D and Cin == 32 and xs.C8 == 32 and dy.c_stride == xs.c_stride and dy.C8 * 8 >= NP
             and xs.c_stride == xs.Z * (xs.X + 2) * (xs.Y + 2) * 8 and dW.shape[0] <= NP
-            and L.rtp_wgrad_s2d_supported(Cin, NP, xs.Z, xs.X, xs.Y)):
+            and L.rtp_wgrad_s2d_supported(Cin, NPs, xs.Z, xs.X, xs.Y)):
         # plane-streaming kernel: X staged once per plane, the 27 (parity, offset) pairs are descriptor shifts / N halves
         dev = xs.buf.device
-        ws = workspace(L.rtp_wgrad_s2d_workspace_bytes(NP, num_sms()), dev, "wgrads2d")
+        ws = workspace(L.rtp_wgrad_s2d_workspace_bytes(NPs, num_sms()), dev, "wgrads2d")
         zero = _zero_page(4096, dev)
-        nsplit = C.c_int32(0)
-        key = ("wgrad_s2d", Cin, dy.C, 27, 2, 1, (dy.Z, dy.X, dy.Y))
-        ev = _prof_begin(key)
-        lib.call("rtp_wgrad_s2d", xs.struct(), dy.struct(), Cin, NP, zero.data_ptr(), ws.data_ptr(), C.byref(nsplit), _stream())
-        _prof_end(key, ev, 2.0 * dy.N * dy.voxels * Cin * dy.C * 27)
         assert dW.is_contiguous()
-        lib.call("rtp_wgrad_s2d_reduce", ws.data_ptr(), nsplit.value, Cin, NP, dW.data_ptr(), dW.shape[0], int(accumulate), _stream())
+        for h in range(nslice):
+            dyh = dy if nslice == 1 else dy.channels(32 * h, 32)
+            dWh = dW if nslice == 1 else dW[32 * h:32 * h + 32]
+            nsplit = C.c_int32(0)
+            key = ("wgrad_s2d", Cin, dyh.C, 27, 2, 1, (dy.Z, dy.X, dy.Y))
+            ev = _prof_begin(key)
+            lib.call("rtp_wgrad_s2d", xs.struct(), dyh.struct(), Cin, NPs, zero.data_ptr(), ws.data_ptr(), C.byref(nsplit), _stream())
+            _prof_end(key, ev, 2.0 * dy.N * dy.voxels * Cin * dyh.C * 27)
+            lib.call("rtp_wgrad_s2d_reduce", ws.data_ptr(), nsplit.value, Cin, NPs, dWh.data_ptr(), dWh.shape[0], int(accumulate),
+                     _stream())
         return
     d = lib.WgradDesc()
     d.x, d.dy = xs.struct(), dy.struct()

@@ -883,6 +883,44 @@ def test_full_size_linearity_properties(ctx):
     assert float(yh.abs().sum()) == float(patch.abs().sum())
 
 
+def test_wgrad_s2d_wide_output_as_channel_slices():
+    """Stride-2 conv 32 -> 64 through the space-to-depth view: the plane-streaming weight gradient takes dY in 32-channel
+    slices (dW rows [32 h, 32 h + 32)); against the gather kernel on the plain tensor and against itself with the slicing
+    switched off (generic kernel over the view)."""
+    from rtpose_b200 import ops
+    from rtpose_b200.p8 import P8
+    N, Cin, Cout, grid, og = 4, 32, 64, (8, 32, 48), (4, 16, 24)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = P8.from_ncdhw(torch.randn(N, Cin, *grid, device="cuda", generator=g))
+    dy = P8.from_ncdhw(torch.randn(N, Cout, *og, device="cuda", generator=g))
+    gamma, beta = torch.ones(Cin, device="cuda"), torch.zeros(Cin, device="cuda")
+    st = ops.gn_stats(x, 8)
+    xn = ops.gn_apply(x, 8, st, gamma, beta, P8(N, Cin, *grid))
+    xs = ops.gn_apply_s2d(x, 8, st, gamma, beta, P8(N, 8 * Cin, *og))
+    gw_s, gw_v, gw_g = (torch.zeros(Cout, Cin, 3, 3, 3, device="cuda") for _ in range(3))
+    lib_calls = []
+    real = ops.lib.call
+    ops.lib.call = lambda name, *a: (lib_calls.append(name), real(name, *a))[1]
+    try:
+        ops.conv_wgrad_s2d(xs, dy, Cin, gw_s)
+    finally:
+        ops.lib.call = real
+    assert lib_calls.count("rtp_wgrad_s2d") == 2, lib_calls
+    old = ops.USE_WGRAD_S2D
+    ops.USE_WGRAD_S2D = False
+    try:
+        ops.conv_wgrad_s2d(xs, dy, Cin, gw_v)
+    finally:
+        ops.USE_WGRAD_S2D = old
+    ops.conv_wgrad(xn, dy, 3, 2, gw_g)
+    torch.cuda.synchronize()
+    close(gw_s, gw_g, tol=1e-3, what="sliced s2d wgrad vs gather kernel")
+    close(gw_s, gw_v, tol=1e-4, what="sliced s2d wgrad vs generic kernel over the view")
+    ops.conv_wgrad_s2d(xs, dy, Cin, gw_s, accumulate=True)
+    torch.cuda.synchronize()
+    close(gw_s, 2 * gw_g, tol=1e-3, what="sliced s2d wgrad, accumulate")
+
+
 def test_full_size_stride2_s2d_agrees_with_gather_kernels(ctx):
     """At the BASELINE shape the stride-2 exchange conv is computed twice with independent kernels — through the
     space-to-depth view (plane-streaming conv, masked taps, paired dgrad launches, view wgrad) and with the gather
