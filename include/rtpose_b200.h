@@ -44,6 +44,10 @@ const char* rtp_last_error(void);
 int rtp_version(void);
 /* 1 if a device with compute capability 10.x is current, else 0 (kernels are sm_100a-only). */
 int rtp_device_ok(void);
+/* Device-wide L1 / shared-memory preference for the current device (cudaDeviceSetCacheConfig): 1 = prefer shared memory, so
+ * that the streaming kernels can become resident beside the large-shared-memory persistent kernels (an SM's split only changes
+ * when it is idle); 0 = no preference.  Call once per device before launching (lib.setup_device). */
+int rtp_set_shared_carveout(int32_t prefer_shared);
 
 /* ---- layout conversion at the det3d API boundary -------------------------------------------------------
  * replaces: the NCDHW fp32 tensors that flow between reference modules (radar_pose_net.py:26-46). */

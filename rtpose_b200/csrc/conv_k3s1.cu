@@ -690,3 +690,7 @@ extern "C" int rtp_conv_k3s1_stat_finalize(const float* stat_ws, int32_t nctas, 
   stat_finalize_kernel<<<N, 256, 0, (cudaStream_t)stream>>>(stat_ws, nctas, N, C, G, (double)voxels, eps, stats_in, out, mode);
   RTP_LAUNCH_CHECK();
 }
+
+int rtp_k3s1_set_carveout(int pct) {  // see rtp_set_shared_carveout (layout.cu)
+  return (int)cudaFuncSetAttribute((const void*)stat_finalize_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+}

@@ -23,6 +23,33 @@ extern "C" int rtp_device_ok(void) {
   return p.major == 10 ? 1 : 0;
 }
 
+// The L1 / shared-memory split of an SM can only change while the SM is idle, so a kernel that prefers a different split
+// than the resident one waits for the SM to drain: the small GroupNorm / reduction kernels (default preference: L1) could
+// not start beside the persistent weight-gradient CTAs (196 KB of shared memory), and the main chain stalled behind every
+// side-stream weight gradient (bench --timeline: stat_finalize, 4 us of work, started 150 us late).  With one device-wide
+// preference every kernel of the process runs under the same (maximum shared memory) split.
+int rtp_norm_set_carveout(int pct);        // norm.cu
+int rtp_k3s1_set_carveout(int pct);        // conv_k3s1.cu
+int rtp_wgrad_k3s1_set_carveout(int pct);  // wgrad_k3s1.cu
+extern "C" int rtp_set_shared_carveout(int32_t mode) {
+  cudaError_t e = cudaSuccess;
+  if (mode == 1) {  // device-wide preference
+    e = cudaDeviceSetCacheConfig(cudaFuncCachePreferShared);
+  } else if (mode == 2) {  // only the streaming GroupNorm / finalize / reduce kernels of the main chain
+    int r = rtp_norm_set_carveout(cudaSharedmemCarveoutMaxShared);
+    if (!r) r = rtp_k3s1_set_carveout(cudaSharedmemCarveoutMaxShared);
+    if (!r) r = rtp_wgrad_k3s1_set_carveout(cudaSharedmemCarveoutMaxShared);
+    e = (cudaError_t)r;
+  } else {
+    e = cudaDeviceSetCacheConfig(cudaFuncCachePreferNone);
+  }
+  if (e != cudaSuccess) {
+    rtp_set_error("rtp_set_shared_carveout: %s", cudaGetErrorString(e));
+    return (int)e;
+  }
+  return 0;
+}
+
 // ---------------------------------------------------------------------------------------------- pack / unpack
 // One block: (n, chunk, z, 32-wide x tile, 32-wide y tile); 8 channels x 32 y x 32 x staged in smem so that
 // both the NCDHW side (x fastest) and the P8 side (y fastest, 16 B per voxel) are coalesced.

@@ -312,3 +312,7 @@ extern "C" int rtp_wgrad_k3s1_reduce(const float* workspace, int32_t nsplit, int
                                                                                   n0, ci0, accumulate);
   RTP_LAUNCH_CHECK();
 }
+
+int rtp_wgrad_k3s1_set_carveout(int pct) {  // see rtp_set_shared_carveout (layout.cu)
+  return (int)cudaFuncSetAttribute((const void*)wgrad_k3s1_reduce_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+}

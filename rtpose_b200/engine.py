@@ -40,6 +40,8 @@ class Engine:
         if arch not in ARCH:
             raise KeyError("unknown backbone_cfg %r (supported: %s)" % (arch, sorted(ARCH)))
         self.in_ch, self.ch = ARCH[arch]
+        if torch.cuda.is_available():
+            lib.setup_device()  # device-wide shared-memory preference (lib.setup_device)
         self.fuse = final_fuse
         self.p = params
         self.pb, self.ph = prefix_backbone, prefix_head
