@@ -28,15 +28,15 @@ extern "C" int rtp_device_ok(void) {
 // not start beside the persistent weight-gradient CTAs (196 KB of shared memory), and the main chain stalled behind every
 // side-stream weight gradient (bench --timeline: stat_finalize, 4 us of work, started 150 us late).  With one device-wide
 // preference every kernel of the process runs under the same (maximum shared memory) split.
-int rtp_norm_set_carveout(int pct);        // norm.cu
+int rtp_norm_set_carveout(int pct, int backward_only);  // norm.cu
 int rtp_k3s1_set_carveout(int pct);        // conv_k3s1.cu
 int rtp_wgrad_k3s1_set_carveout(int pct);  // wgrad_k3s1.cu
 extern "C" int rtp_set_shared_carveout(int32_t mode) {
   cudaError_t e = cudaSuccess;
   if (mode == 1) {  // device-wide preference
     e = cudaDeviceSetCacheConfig(cudaFuncCachePreferShared);
-  } else if (mode == 2) {  // only the streaming GroupNorm / finalize / reduce kernels of the main chain
-    int r = rtp_norm_set_carveout(cudaSharedmemCarveoutMaxShared);
+  } else if (mode == 2 || mode == 3) {  // 2: the streaming GroupNorm / finalize / reduce kernels; 3: only GroupNorm backward apply + the finalizers
+    int r = rtp_norm_set_carveout(cudaSharedmemCarveoutMaxShared, mode == 3);
     if (!r) r = rtp_k3s1_set_carveout(cudaSharedmemCarveoutMaxShared);
     if (!r) r = rtp_wgrad_k3s1_set_carveout(cudaSharedmemCarveoutMaxShared);
     e = (cudaError_t)r;

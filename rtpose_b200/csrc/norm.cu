@@ -738,19 +738,21 @@ extern "C" int rtp_channel_sum(rtp_p8 x, int32_t C, float* out, int32_t accumula
 
 // Targeted L1 / shared-memory preference (see rtp_set_shared_carveout, layout.cu): the streaming GroupNorm kernels get the
 // maximum-shared split so that they can become resident beside the persistent weight-gradient / conv CTAs.
-int rtp_norm_set_carveout(int pct) {
+int rtp_norm_set_carveout(int pct, int backward_only) {
   cudaError_t e = cudaSuccess;
   auto set = [&](const void* f) {
     const cudaError_t r = cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
     if (r != cudaSuccess) e = r;
   };
-  set((const void*)gn_sums_partial_kernel);
+  if (!backward_only) {
+    set((const void*)gn_sums_partial_kernel);
+    set((const void*)gn_apply_kernel<false>);
+    set((const void*)gn_apply_kernel<true>);
+    set((const void*)gn_bwd_partial_kernel<false>);
+    set((const void*)gn_bwd_partial_kernel<true>);
+  }
   set((const void*)gn_sums_final_kernel);
   set((const void*)gn_finalize_kernel);
-  set((const void*)gn_apply_kernel<false>);
-  set((const void*)gn_apply_kernel<true>);
-  set((const void*)gn_bwd_partial_kernel<false>);
-  set((const void*)gn_bwd_partial_kernel<true>);
   set((const void*)gn_param_grad_kernel);
   set((const void*)gn_bwd_apply_kernel<false, false>);
   set((const void*)gn_bwd_apply_kernel<false, true>);
