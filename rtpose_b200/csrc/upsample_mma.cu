@@ -66,12 +66,15 @@ struct UBM {
   uint32_t stage_bytes;
 };
 
-constexpr int kStages = 3;  // chunks of kRows full-resolution rows in flight per warp
+// chunks of kRows full-resolution rows in flight per warp: 3 for the one-block kernels (96 registers, 2 CTAs per SM); the
+// two-block kernel (Yl > 16, 161 registers, issue-bound at 8 warps per SM) runs 3 CTAs per SM with 2 stages (-7 %)
+constexpr int stages_of(int nmt) { return nmt == 2 ? 2 : 3; }
 constexpr int kRows = 8;
 
 // NMT = 16-row blocks of the low-resolution y extent (1: Yl <= 16, 2: Yl <= 32); NKS = Y / 16 k16 steps per row (Y <= 64)
 template <int NMT, int NKS>
 __global__ void __launch_bounds__(kWarps * 32) upsample_bwd_yx_mma_kernel(const __grid_constant__ UBM p) {
+  constexpr int kStages = stages_of(NMT);
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t bar_full[kWarps][kStages];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -276,7 +279,14 @@ int rtp_upsample_bwd_yx_mma(const rtp_p8& dout, const rtp_p8& t2, int C8, void* 
   // ~1 / scale halo rows (efficiency txl / (txl + 1)); the warps take units round-robin, so the last round should be full
   // (efficiency rounds / ceil(rounds)): pick the segment count with the best product
   const int64_t planes = (int64_t)dout.N * C8 * dout.Z;
-  const int64_t wtotal = (int64_t)nsm * 2 * kWarps;
+  const uint32_t row_bytes0 = (uint32_t)(Y + 2) * 16u;
+  const int kStages = stages_of(Yl > 16 ? 2 : 1);
+  const size_t smem0 = (size_t)kWarps * kStages * (((uint32_t)kRows * row_bytes0 + 127u) & ~127u) + 1024;
+  int cta_per_sm = (int)((227 * 1024) / (smem0 + 1024));  // + 1 KB the system reserves per CTA
+  const int reg_cap = Yl > 16 ? 3 : 4;                    // 161 / 96 registers x 128 threads
+  if (cta_per_sm > reg_cap) cta_per_sm = reg_cap;
+  if (cta_per_sm < 1) cta_per_sm = 1;
+  const int64_t wtotal = (int64_t)nsm * cta_per_sm * kWarps;
   const int ntx_max = Xl / 2 > 1 ? Xl / 2 : 1;
   int best_ntx = 1;
   double best = -1.0;
@@ -312,7 +322,7 @@ int rtp_upsample_bwd_yx_mma(const rtp_p8& dout, const rtp_p8& t2, int C8, void* 
     configured = smem;
   }
   const int want = ceil_div(k.nunits, kWarps);
-  const int grid = want < 2 * nsm ? want : 2 * nsm;
+  const int grid = want < cta_per_sm * nsm ? want : cta_per_sm * nsm;
   kern<<<grid, kWarps * 32, smem, (cudaStream_t)stream>>>(k);
   return 1;
 }
