@@ -583,6 +583,8 @@ bool same_geom(const rtp_p8& a, const rtp_p8& b) { return a.N == b.N && a.Z == b
 
 }  // namespace
 
+int rtp_fuse_sum_mma(const rtp_fuse_desc* d, void* stream);  // fuse_mma.cu
+
 extern "C" int rtp_fuse_sum(const rtp_fuse_desc* d, void* stream) {
   RTP_CHECK_ARG(d && d->out.ptr, "rtp_fuse_sum: null argument");
   RTP_CHECK_ARG(d->n_same >= 0 && d->n_same <= 4 && d->n_low >= 0 && d->n_low <= 3 && d->n_same + d->n_low >= 1,
@@ -598,6 +600,12 @@ extern "C" int rtp_fuse_sum(const rtp_fuse_desc* d, void* stream) {
   for (int i = 0; i < d->n_low; ++i) {
     RTP_CHECK_ARG(d->low[i].ptr && d->low[i].N == d->out.N && d->low[i].C8 >= C8, "rtp_fuse_sum: low[%d] mismatch", i);
     k.low[i] = P8(d->low[i]);
+  }
+  {
+    // y interpolation on the tensor cores (fuse_mma.cu); 0 = shape not supported
+    const int r = rtp_fuse_sum_mma(d, stream);
+    if (r < 0) return -1;
+    if (r > 0) RTP_LAUNCH_CHECK();
   }
   const int64_t V = (int64_t)d->out.Z * d->out.X * d->out.Y;
   bool rows_ok = d->n_low > 0;

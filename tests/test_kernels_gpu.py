@@ -225,6 +225,50 @@ def test_fuse_sum_and_upsample_bwd():
         close(d.to_ncdhw(), 2 * u.grad, tol=2 * BF16_ULP, what="upsample bwd acc")
 
 
+FUSE_MMA_CASES = [
+    # (N, C, full grid (Z, Y, X), low grids, n_same): Y % 16 == 0, Yl <= 32 -> fuse_mma.cu (y interpolation on the tensor cores)
+    (2, 16, (4, 64, 40), [(2, 32, 20), (1, 16, 10), (1, 8, 5)], 1),   # the full-resolution exchange: ratios 2 / 4 / 8
+    (1, 24, (4, 64, 40), [(2, 32, 20), (1, 16, 10)], 2),              # two same-resolution terms, three channel chunks
+    (2, 8, (2, 32, 24), [(1, 16, 12)], 3),                            # half resolution, one low term, three same terms
+    (1, 8, (3, 48, 17), [(2, 20, 9), (1, 7, 3)], 1),                  # odd extents, non-integer ratios, three row blocks
+    (1, 8, (2, 16, 70), [(1, 8, 35), (1, 1, 1)], 1),                  # long x extent (several units per plane), a 1x1x1 term
+]
+
+
+@pytest.mark.parametrize("case", FUSE_MMA_CASES, ids=str)
+def test_fuse_sum_tensor_core_path(case):
+    """rtp_fuse_sum with the y interpolation on mma.sync (csrc/fuse_mma.cu, opt-in) against F.interpolate (trilinear,
+    align_corners=True) + sum + bias + ReLU in fp32; run-to-run identical; the CUDA-core kernels agree to bf16 round-off."""
+    from rtpose_b200 import ops
+    from rtpose_b200.p8 import P8
+    N, C, hi, lows, n_same = case
+    same = [rnd(N, C, *hi, seed=40 + i) for i in range(n_same)]
+    low = [rnd(N, C, *g, seed=50 + i) for i, g in enumerate(lows)]
+    bias = rnd(C, seed=60)
+    pre = sum(same) + bias.view(1, C, 1, 1, 1)
+    for u in low:
+        pre = pre + F.interpolate(u, size=hi, mode="trilinear", align_corners=True)
+    ref = F.relu(pre)
+    import os
+    base = ops.fuse_sum(P8(N, C, *hi), [to_p8(t) for t in same], [to_p8(u) for u in low], bias=bias.cuda(), relu=True)
+    os.environ["RTP_FUSE_MMA"] = "1"  # the tensor-core kernel is opt-in (measured slower than the tile kernel)
+    try:
+        out = ops.fuse_sum(P8(N, C, *hi), [to_p8(t) for t in same], [to_p8(u) for u in low], bias=bias.cuda(), relu=True)
+        torch.cuda.synchronize()
+        close(out.to_ncdhw(), ref, tol=1.5 * BF16_ULP, what="fuse_sum (mma) %s" % (case,))
+        first = out.to_ncdhw().clone()
+        out2 = ops.fuse_sum(P8(N, C, *hi), [to_p8(t) for t in same], [to_p8(u) for u in low], bias=bias.cuda(), relu=True)
+        torch.cuda.synchronize()
+        assert torch.equal(first, out2.to_ncdhw())
+        # without ReLU / bias
+        out3 = ops.fuse_sum(P8(N, C, *hi), [to_p8(t) for t in same], [to_p8(u) for u in low])
+        torch.cuda.synchronize()
+        close(out3.to_ncdhw(), pre - bias.view(1, C, 1, 1, 1), tol=1.5 * BF16_ULP, what="fuse_sum (mma), plain")
+    finally:
+        del os.environ["RTP_FUSE_MMA"]
+    close(first, base.to_ncdhw(), tol=1.5 * BF16_ULP, what="tensor-core vs CUDA-core fuse_sum")
+
+
 UPBWD_MMA_CASES = [
     # (N, C, full grid (Z, Y, X), low grid): Y % 16 == 0 and Yl <= 32 -> upsample_mma.cu (y reduction on the tensor cores)
     (2, 16, (4, 64, 40), (2, 32, 20)),   # ratio 2: two 16-row blocks of yl, four k16 steps, banded weights
