@@ -359,7 +359,7 @@ def run_ours(args, rank, world, local_rank):
     # N > 1: the flat gradient buffer is all-reduced in 3 slices on a communication stream, each launched as soon as
     # backward has issued the slice's last gradient; the mean comes from seeding backward with 1/world
     sar = None
-    if world > 1 and not args.late_allreduce:
+    if world > 1 and args.overlap_allreduce and not args.late_allreduce:
         from rtpose_b200 import spec as _spec  # noqa: F401
         sar = rdist.SlicedAllReduce(gflat, [(k, v.numel()) for k, v in params.items()], world=world,
                                     fractions=(0.5, 0.35, 0.15)).attach(eng)
@@ -488,7 +488,7 @@ def run_ours(args, rank, world, local_rank):
             "config": dict(workload_config(cfg, B, world, D), **{
                        "l2": "inputs+activations per step >> 126 MB L2 (no explicit flush needed)",
                        "allreduce": (None if world == 1 else ("3 slices overlapped with backward on a communication stream" if sar is not None
-                                                              else "one flat all-reduce after backward")),
+                                                              else "one flat all-reduce after backward (overlapped slices measured slower: --overlap-allreduce)")),
                        "cuda_graph": use_graph, "wgrad_side_stream": bool(ops.ASYNC_WGRAD), "branch_streams": bool(eng.parallel_branches),
                        "targets": "assigned on the device from resident fp64 skeletons every step (rtp_assign_targets)",
                        "optimizer": ("fused clip(35) + decoupled wd + Adam, one-cycle lr (rtp_adam_step) inside the timed region"
@@ -896,7 +896,10 @@ def main():
     ap.add_argument("--timeline", default=None, help="diagnostic: write the CUPTI kernel timeline of two replayed steps to this JSON file")
     ap.add_argument("--no-optimizer", action="store_true", help="time forward+backward only (no fused clip+Adam step)")
     ap.add_argument("--dcn-head", action="store_true", help="configs[4]: the deformable head (dcn_head='fold_z') on the det3d-style model")
-    ap.add_argument("--late-allreduce", action="store_true", help="N > 1: one all-reduce after backward instead of overlapped slices (A/B)")
+    ap.add_argument("--late-allreduce", action="store_true", help="N > 1: one all-reduce after backward (the default since the end of round 2; kept for old command lines)")
+    ap.add_argument("--overlap-allreduce", action="store_true",
+                    help="N > 1: all-reduce in 3 slices on a communication stream while backward runs (A/B: measured SLOWER, 20.24 vs 19.31 ms at N = 2 — "
+                         "the NCCL kernels hold SMs the persistent one-CTA-per-SM conv kernels need)")
     ap.add_argument("--ref-gpu-probe", action="store_true", help="time the unmodified reference on this GPU through stock PyTorch (informative)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
