@@ -281,6 +281,14 @@ int64_t rtp_wgrad_pw_workspace_bytes(int32_t Cin, int32_t nsm);
 int rtp_wgrad_pw(rtp_p8 x, rtp_p8 dy, int32_t Cin, const void* zero_page, float* workspace, int32_t* nsplit_out, void* stream);
 int rtp_wgrad_pw_reduce(const float* workspace, int32_t nsplit, int32_t Cin, float* dW, int32_t Cin_total, int32_t co_n,
                         int32_t ci0, int32_t accumulate, void* stream);
+/* The same with the conv's bias gradient for free: one more GEMM N chunk is fed from ones_page (device, 128 positions x 8
+ * bf16 channels, channel 0 = 1.0), whose product is sum over positions of dY; rtp_wgrad_pw_bias_reduce writes dW as above and
+ * dbias[co] (= or +=).  replaces: autograd's bias gradient of final_conv (hrnet3d.py:20) — a separate pass over dY before. */
+int64_t rtp_wgrad_pw_bias_workspace_bytes(int32_t Cin, int32_t nsm);
+int rtp_wgrad_pw_bias(rtp_p8 x, rtp_p8 dy, int32_t Cin, const void* zero_page, const void* ones_page, float* workspace,
+                      int32_t* nsplit_out, void* stream);
+int rtp_wgrad_pw_bias_reduce(const float* workspace, int32_t nsplit, int32_t Cin, float* dW, int32_t Cin_total, int32_t co_n,
+                             int32_t ci0, int32_t accumulate, float* dbias, int32_t accumulate_bias, void* stream);
 /* Weight gradient of the stride-2 conv straight from the view, plane-streaming (csrc/wgrad_s2d.cu): xs = s2d view of the
  * normalised input (8*Cin/8 chunks), dy = gradient of the conv output (same grid as the view), Cin = 32.  One persistent
  * CTA per SM writes an fp32 partial [nsplit][6][128][2*NP]; rtp_wgrad_s2d_reduce sums them in a fixed order into

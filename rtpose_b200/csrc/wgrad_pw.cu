@@ -23,7 +23,9 @@ constexpr int kMaxStages = 4;
 struct WPW {
   P8 x, dy;
   const bf16* zero_page;  // >= 2048 bytes of zeros (dY chunks beyond its channel count)
-  int NX;                 // X channels padded to 16 (GEMM N)
+  const bf16* ones_page;  // 128 positions x 8 channels with channel 0 = 1 (the bias-gradient column), or nullptr
+  int bias_chunk;         // N chunk fed from ones_page (column 8 * bias_chunk of the result = sum over positions of dY), -1: none
+  int NX;                 // X channels (+ the bias chunk) padded to 16 (GEMM N)
   int P16;                // whole 16-position groups per (sample, chunk) volume
   int ntile, nunits, nstages;
   uint32_t a_bytes, b_bytes, stage_bytes;
@@ -67,7 +69,8 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_pw_kernel(const __grid_cons
           bulk_g2s(dst + (size_t)i * 2048, src, 2048, &bar_full[s]);
         } else {
           const int c = i - 16;
-          const bf16* src = c < p.x.C8 ? p.x.ptr + (int64_t)n * p.x.n_stride + (int64_t)c * p.x.c_stride + q0 : p.zero_page;
+          const bf16* src = c < p.x.C8 ? p.x.ptr + (int64_t)n * p.x.n_stride + (int64_t)c * p.x.c_stride + q0
+                                       : (c == p.bias_chunk ? p.ones_page : p.zero_page);
           bulk_g2s(dst + p.a_bytes + (size_t)c * 2048, src, 2048, &bar_full[s]);
         }
       }
@@ -130,10 +133,13 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_pw_kernel(const __grid_cons
 }
 
 // partial[split][co][ci] -> dW[co][ci0 + ci]
+// (bias_col >= 0: item co_n * ci_n + co is dbias[co] = column bias_col of row co, the product with the ones channel)
 __global__ void __launch_bounds__(256) wgrad_pw_reduce_kernel(const float* __restrict__ partial, int nsplit, int NX, float* __restrict__ dW,
-                                                              int Cin_total, int co_n, int ci0, int ci_n, int accumulate) {
+                                                              int Cin_total, int co_n, int ci0, int ci_n, int accumulate,
+                                                              float* __restrict__ dbias, int bias_col, int accumulate_bias) {
   __shared__ float sh[8][33];
-  const int total = co_n * ci_n;
+  const int nw = co_n * ci_n;
+  const int total = nw + (bias_col >= 0 ? co_n : 0);
   const int o = threadIdx.x & 31, sl = threadIdx.x >> 5;
   const size_t sstride = (size_t)128 * NX;
   for (int base = blockIdx.x * 32; base < total; base += gridDim.x * 32) {
@@ -141,8 +147,13 @@ __global__ void __launch_bounds__(256) wgrad_pw_reduce_kernel(const float* __res
     float acc = 0.f;
     int co = 0, ci = 0;
     if (i < total) {
-      ci = i % ci_n;
-      co = i / ci_n;
+      if (i < nw) {
+        ci = i % ci_n;
+        co = i / ci_n;
+      } else {
+        ci = bias_col;
+        co = i - nw;
+      }
       const float* src = partial + (size_t)co * NX + ci;
       for (int s = sl; s < nsplit; s += 8) acc += src[s * sstride];
     }
@@ -152,8 +163,12 @@ __global__ void __launch_bounds__(256) wgrad_pw_reduce_kernel(const float* __res
       float t = 0.f;
 #pragma unroll
       for (int l = 0; l < 8; ++l) t += sh[l][o];
-      float* d = dW + (int64_t)co * Cin_total + ci0 + ci;
-      *d = accumulate ? *d + t : t;
+      if (i < nw) {
+        float* d = dW + (int64_t)co * Cin_total + ci0 + ci;
+        *d = accumulate ? *d + t : t;
+      } else {
+        dbias[co] = accumulate_bias ? dbias[co] + t : t;
+      }
     }
     __syncthreads();
   }
@@ -165,10 +180,12 @@ extern "C" int rtp_wgrad_pw_supported(int32_t Cin, int32_t Cout, int32_t Z, int3
   // M = 128 dY-channel rows; N = X channels (16..256); the final pad row (Y + 2 positions) must cover the skipped tail
   return (Cin >= 8 && Cin <= 256 && Cout >= 1 && Cout <= 128 && Y + 2 >= 16 && Z >= 1 && X >= 1) ? 1 : 0;
 }
-extern "C" int64_t rtp_wgrad_pw_workspace_bytes(int32_t Cin, int32_t nsm) { return (int64_t)nsm * 128 * ((Cin + 15) / 16 * 16) * 4; }
+static int nx_of(int Cin, int with_bias) { return ((Cin + 7) / 8 * 8 + (with_bias ? 8 : 0) + 15) / 16 * 16; }
+extern "C" int64_t rtp_wgrad_pw_workspace_bytes(int32_t Cin, int32_t nsm) { return (int64_t)nsm * 128 * nx_of(Cin, 0) * 4; }
+extern "C" int64_t rtp_wgrad_pw_bias_workspace_bytes(int32_t Cin, int32_t nsm) { return (int64_t)nsm * 128 * nx_of(Cin, 1) * 4; }
 
-extern "C" int rtp_wgrad_pw(rtp_p8 x, rtp_p8 dy, int32_t Cin, const void* zero_page, float* workspace, int32_t* nsplit_out,
-                            void* stream) {
+static int wgrad_pw_launch(rtp_p8 x, rtp_p8 dy, int32_t Cin, const void* zero_page, const void* ones_page, float* workspace,
+                           int32_t* nsplit_out, void* stream) {
   RTP_CHECK_ARG(x.ptr && dy.ptr && zero_page && workspace && nsplit_out, "rtp_wgrad_pw: null argument");
   RTP_CHECK_ARG(x.N == dy.N && x.Z == dy.Z && x.X == dy.X && x.Y == dy.Y, "rtp_wgrad_pw: geometry mismatch");
   RTP_CHECK_ARG(Cin <= x.C8 * 8 && rtp_wgrad_pw_supported(Cin, dy.C8 * 8 > 128 ? 129 : 128, x.Z, x.X, x.Y) && dy.C8 <= 16,
@@ -178,7 +195,10 @@ extern "C" int rtp_wgrad_pw(rtp_p8 x, rtp_p8 dy, int32_t Cin, const void* zero_p
   WPW k;
   k.x = P8(x); k.dy = P8(dy); k.zero_page = (const bf16*)zero_page;
   k.x.C8 = (Cin + 7) / 8;
-  k.NX = (Cin + 15) / 16 * 16;
+  k.ones_page = (const bf16*)ones_page;
+  k.bias_chunk = ones_page ? k.x.C8 : -1;
+  k.NX = nx_of(Cin, ones_page != nullptr);
+  RTP_CHECK_ARG(k.NX <= 256, "rtp_wgrad_pw: too many X channels");
   k.P16 = (int)(vol / 16);
   k.ntile = (k.P16 + 7) / 8;
   k.nunits = x.N * k.ntile;
@@ -209,13 +229,35 @@ extern "C" int rtp_wgrad_pw(rtp_p8 x, rtp_p8 dy, int32_t Cin, const void* zero_p
   RTP_LAUNCH_CHECK();
 }
 
-extern "C" int rtp_wgrad_pw_reduce(const float* workspace, int32_t nsplit, int32_t Cin, float* dW, int32_t Cin_total, int32_t co_n,
-                                   int32_t ci0, int32_t accumulate, void* stream) {
+extern "C" int rtp_wgrad_pw(rtp_p8 x, rtp_p8 dy, int32_t Cin, const void* zero_page, float* workspace, int32_t* nsplit_out,
+                            void* stream) {
+  return wgrad_pw_launch(x, dy, Cin, zero_page, nullptr, workspace, nsplit_out, stream);
+}
+// The same launch with one more N chunk fed from `ones_page` (128 positions x 8 channels, channel 0 = 1): the product with it
+// is sum over positions of dY = the conv's bias gradient, taken out by rtp_wgrad_pw_bias_reduce — dY is not read again for it.
+extern "C" int rtp_wgrad_pw_bias(rtp_p8 x, rtp_p8 dy, int32_t Cin, const void* zero_page, const void* ones_page, float* workspace,
+                                 int32_t* nsplit_out, void* stream) {
+  RTP_CHECK_ARG(ones_page, "rtp_wgrad_pw_bias: null ones page");
+  return wgrad_pw_launch(x, dy, Cin, zero_page, ones_page, workspace, nsplit_out, stream);
+}
+
+static int wgrad_pw_reduce_launch(const float* workspace, int nsplit, int Cin, float* dW, int Cin_total, int co_n, int ci0,
+                                  int accumulate, float* dbias, int accumulate_bias, void* stream) {
   RTP_CHECK_ARG(workspace && dW && nsplit >= 1 && co_n >= 1 && co_n <= 128 && ci0 >= 0 && ci0 + Cin <= Cin_total,
                 "rtp_wgrad_pw_reduce: bad args");
-  const int NX = (Cin + 15) / 16 * 16;
-  const int total = co_n * Cin;
+  const int NX = nx_of(Cin, dbias != nullptr);
+  const int total = co_n * Cin + (dbias ? co_n : 0);
   wgrad_pw_reduce_kernel<<<ceil_div(total, 32), 256, 0, (cudaStream_t)stream>>>(workspace, nsplit, NX, dW, Cin_total, co_n, ci0, Cin,
-                                                                                 accumulate);
+                                                                                 accumulate, dbias, dbias ? (Cin + 7) / 8 * 8 : -1,
+                                                                                 accumulate_bias);
   RTP_LAUNCH_CHECK();
+}
+extern "C" int rtp_wgrad_pw_reduce(const float* workspace, int32_t nsplit, int32_t Cin, float* dW, int32_t Cin_total, int32_t co_n,
+                                   int32_t ci0, int32_t accumulate, void* stream) {
+  return wgrad_pw_reduce_launch(workspace, nsplit, Cin, dW, Cin_total, co_n, ci0, accumulate, nullptr, 0, stream);
+}
+extern "C" int rtp_wgrad_pw_bias_reduce(const float* workspace, int32_t nsplit, int32_t Cin, float* dW, int32_t Cin_total, int32_t co_n,
+                                        int32_t ci0, int32_t accumulate, float* dbias, int32_t accumulate_bias, void* stream) {
+  RTP_CHECK_ARG(dbias, "rtp_wgrad_pw_bias_reduce: null dbias");
+  return wgrad_pw_reduce_launch(workspace, nsplit, Cin, dW, Cin_total, co_n, ci0, accumulate, dbias, accumulate_bias, stream);
 }

@@ -520,7 +520,6 @@ class Engine:
                 if g is None:
                     return
                 gb, accb = self._pgrad(self.pb + "final_conv.bias")
-                ops.on_aux_stream(g, lambda: ops.channel_sum(g, gb, accumulate=accb))
                 gw, accw = self._pgrad(self.pb + "final_conv.weight")
                 if not accw:
                     pass  # every input-channel slice is written below exactly once
@@ -530,7 +529,9 @@ class Engine:
                     else:
                         gt = self.new(y, C=w.shape[0])
                         ops.upsample_bwd(g, gt)
-                    ops.conv_wgrad_async(y, gt, 1, 1, gw, accumulate=accw, ci0=ci0)
+                    # the bias gradient (sum of g over positions) rides in the full-resolution term's weight gradient as a
+                    # ones channel of its GEMM N: g is not read once more for it (a 0.17 ms channel_sum pass before)
+                    ops.conv_wgrad_async(y, gt, 1, 1, gw, accumulate=accw, ci0=ci0, bias_grad=(gb, accb) if i == 0 else None)
                     gy, acc = self._grad_of(y)
                     ops.conv_dgrad(self.packs, gt, w, 1, gy, mask=y if y.relu_out else None, accumulate=acc, ci0=ci0,
                                    ci_n=y.C)

@@ -661,7 +661,7 @@ def _split_ws(tag, nbytes, dev):
     return ws, done
 
 
-def conv_wgrad_async(x, dy, k, stride, dW, accumulate=False, ci0=0, n0=0, more=(), then=None):
+def conv_wgrad_async(x, dy, k, stride, dW, accumulate=False, ci0=0, n0=0, more=(), then=None, bias_grad=None):
     """conv_wgrad queued on a side stream, ordered after everything issued so far on the current stream.  The caller
     keeps x, dy and dW alive and untouched until join_wgrad() (the engine's buffers live until the end of the step).
     `then()` is called right after, on the same stream (post-processing of dW).  Falls back to the in-stream call when
@@ -670,7 +670,7 @@ def conv_wgrad_async(x, dy, k, stride, dW, accumulate=False, ci0=0, n0=0, more=(
     if _SKIP_WGRAD:  # timing experiments only (RTP_SKIP_WGRAD=1): how much of the step the weight gradients cost net
         return None
     if not ASYNC_WGRAD:
-        conv_wgrad(x, dy, k, stride, dW, accumulate, ci0, n0, more)
+        conv_wgrad(x, dy, k, stride, dW, accumulate, ci0, n0, more, bias_grad=bias_grad)
         if then is not None:
             then()
         return None
@@ -681,7 +681,7 @@ def conv_wgrad_async(x, dy, k, stride, dW, accumulate=False, ci0=0, n0=0, more=(
     with torch.cuda.stream(st["stream"]):
         _cur_side = st
         try:
-            conv_wgrad(x, dy, k, stride, dW, accumulate, ci0, n0, more)
+            conv_wgrad(x, dy, k, stride, dW, accumulate, ci0, n0, more, bias_grad=bias_grad)
             if then is not None:
                 then()
         finally:
@@ -689,10 +689,32 @@ def conv_wgrad_async(x, dy, k, stride, dW, accumulate=False, ci0=0, n0=0, more=(
     return None
 
 
-def conv_wgrad(x, dy, k, stride, dW, accumulate=False, ci0=0, n0=0, more=(), taps=None):
+def _ones_page(device):
+    """128 positions x 8 bf16 channels with channel 0 = 1: the extra GEMM N chunk of rtp_wgrad_pw_bias."""
+    z = _ones_pages.get(str(device))
+    if z is None:
+        z = torch.zeros((128, 8), dtype=torch.bfloat16, device=device)
+        z[:, 0] = 1.0
+        _ones_pages[str(device)] = z
+    return z
+
+
+_ones_pages = {}
+USE_WGRAD_PW_BIAS = not bool(_os.environ.get("RTP_NO_WGRAD_PW_BIAS"))  # A/B switch
+
+
+def conv_wgrad(x, dy, k, stride, dW, accumulate=False, ci0=0, n0=0, more=(), taps=None, bias_grad=None):
     """dW[:, ci0:ci0+x.C] (=|+=) wgrad(x, dy[:, n0:n0+dW.shape[0]]).  x: forward input (P8), dy: P8 gradient.
     `more`: further (dW, accumulate, ci0, n0) outputs reduced from the same split-K workspace.
-    `taps`: explicit (tz, tx, ty) list instead of the k^3 stencil (the DCN sample volume keeps its taps on the z axis)."""
+    `taps`: explicit (tz, tx, ty) list instead of the k^3 stencil (the DCN sample volume keeps its taps on the z axis).
+    `bias_grad` = (db fp32 [Cout], accumulate): also db (=|+=) sum over positions of dy — inside the streaming 1x1 kernel when it
+    takes the shape (a ones channel in the GEMM N), else by a channel_sum pass."""
+    if bias_grad is not None and not (USE_WGRAD_PW_BIAS and taps is None and USE_WGRAD_PW and k == 1 and stride == 1 and not more
+                                      and n0 == 0 and dy.C <= 128 and dy.C8 <= 16 and x.grid == dy.grid and _dense_planes(x)
+                                      and _dense_planes(dy) and dW.shape[0] <= dy.C8 * 8 and dW.shape[0] == bias_grad[0].numel()
+                                      and x.C + 8 <= 256 and lib.load().rtp_wgrad_pw_supported(x.C, dy.C, x.Z, x.X, x.Y)):
+        channel_sum(dy, bias_grad[0], accumulate=bias_grad[1])
+        bias_grad = None
     outs = ((dW, accumulate, ci0, n0),) + tuple(more)
     if (taps is None and USE_WGRAD_K3S1 and k == 3 and stride == 1 and x.C % 32 == 0 and x.c_stride == x.Z * (x.X + 2) * (x.Y + 2) * 8
             and dy.c_stride == x.c_stride and all(o[3] % 8 == 0 for o in outs)
@@ -705,14 +727,24 @@ def conv_wgrad(x, dy, k, stride, dW, accumulate=False, ci0=0, n0=0, more=(), tap
         # streaming GEMM over the padded positions (csrc/wgrad_pw.cu): M = dY channels, N = X channels
         L = lib.load()
         dev = x.buf.device
-        ws, done = _split_ws("wgradpw", L.rtp_wgrad_pw_workspace_bytes(ci_n, num_sms()), dev)
         zero = _zero_page(4096, dev)
         nsplit = C.c_int32(0)
         key = ("wgrad_pw", ci_n, dy.C, 1, 1, 1, (dy.Z, dy.X, dy.Y))
+        assert dW.is_contiguous()
+        if bias_grad is not None:
+            db, accb = bias_grad
+            ws, done = _split_ws("wgradpw", L.rtp_wgrad_pw_bias_workspace_bytes(ci_n, num_sms()), dev)
+            ev = _prof_begin(key)
+            lib.call("rtp_wgrad_pw_bias", x.struct(), dy.struct(), ci_n, zero.data_ptr(), _ones_page(dev).data_ptr(), ws.data_ptr(),
+                     C.byref(nsplit), _stream())
+            _prof_end(key, ev, 2.0 * dy.N * dy.voxels * ci_n * dy.C)
+            done(lambda: lib.call("rtp_wgrad_pw_bias_reduce", ws.data_ptr(), nsplit.value, ci_n, dW.data_ptr(), dW.shape[1], dW.shape[0],
+                                  ci0, int(accumulate), db.data_ptr(), int(accb), _stream()))
+            return
+        ws, done = _split_ws("wgradpw", L.rtp_wgrad_pw_workspace_bytes(ci_n, num_sms()), dev)
         ev = _prof_begin(key)
         lib.call("rtp_wgrad_pw", x.struct(), dy.struct(), ci_n, zero.data_ptr(), ws.data_ptr(), C.byref(nsplit), _stream())
         _prof_end(key, ev, 2.0 * dy.N * dy.voxels * ci_n * dy.C)
-        assert dW.is_contiguous()
         done(lambda: lib.call("rtp_wgrad_pw_reduce", ws.data_ptr(), nsplit.value, ci_n, dW.data_ptr(), dW.shape[1], dW.shape[0], ci0,
                               int(accumulate), _stream()))
         return

@@ -1041,3 +1041,17 @@ def test_pointwise_wgrad_streaming_kernel(case):
     ops.conv_wgrad(xp, dyp, 1, 1, got)
     torch.cuda.synchronize()
     close(got, ref, tol=2e-5, what="streaming vs gather 1x1 wgrad (same bf16 operands)")
+    # bias gradient as a ones channel of the same GEMM (rtp_wgrad_pw_bias): dW unchanged, db = sum over positions of dy
+    lib.call_counts.clear()
+    got_b = torch.zeros((Cout, Cin, 1, 1, 1), device="cuda")
+    db = torch.full((Cout,), 5.0, device="cuda")
+    ops.conv_wgrad(xp, dyp, 1, 1, got_b, bias_grad=(db, False))
+    torch.cuda.synchronize()
+    assert lib.call_counts.get("rtp_wgrad_pw_bias", 0) == 1 and lib.call_counts.get("rtp_channel_sum", 0) == 0
+    assert torch.equal(got_b, got)
+    want_db = dy.sum((0, 2, 3, 4))
+    close(db, want_db, tol=1e-4, what="bias gradient from the ones channel")
+    ops.conv_wgrad(xp, dyp, 1, 1, got_b, accumulate=True, bias_grad=(db, True))
+    torch.cuda.synchronize()
+    close(db, 2 * want_db, tol=1e-4, what="bias gradient, accumulated")
+    close(got_b, 2 * got, tol=1e-6, what="dW accumulated beside the bias column")
