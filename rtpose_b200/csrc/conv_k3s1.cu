@@ -54,6 +54,9 @@ struct K3 {
   int ntile;       // 128-position tiles per plane
   int ZC, nzc;     // output planes per z-chunk, z-chunks
   int nunits;
+  // LANES = 1, one z-chunk: the units of the last, partly filled round (index >= split_from) are issued as two half-depth units
+  // each (output planes [0, split_zh) and [split_zh, Z)), so that round costs (Z/2 + 1) / Z of a full one
+  int split_from, split_zh;
   int nstages;
   uint32_t stage_bytes, wbuf_bytes, wtap_bytes, wtap_stride;  // per-pass weight slice: 9 copies of wtap_bytes
   long long* dbg;  // optional [grid][8] cycle counters (RTP_K3S1_DEBUG): MMA-warp wait/issue breakdown
@@ -107,15 +110,24 @@ __global__ void __launch_bounds__(LANES == 2 ? RTP_K3S1_DUAL_BOUND : kThreads, 1
   fence_after_sync();
   const uint32_t tmem = tmem_base_s + (uint32_t)L * 256u;  // lane L accumulates in its own 256 columns
 
-  auto decode = [&](int u, int& n, int& zc, int& tile) {
-    tile = u % p.ntile;
-    const int r = u / p.ntile;
+  auto decode = [&](int u, int& n, int& zo0, int& zo1, int& tile) {
     if constexpr (LANES == 2) {  // a unit is (sample, tile); the z-chunk is the lane
-      zc = L;
-      n = r;
-    } else {
-      zc = r % p.nzc;
+      tile = u % p.ntile;
+      n = u / p.ntile;
+      zo0 = L * p.ZC;
+      zo1 = min(Z, zo0 + p.ZC);
+    } else if (u < p.split_from) {
+      tile = u % p.ntile;
+      const int r = u / p.ntile;
       n = r / p.nzc;
+      zo0 = (r % p.nzc) * p.ZC;
+      zo1 = min(Z, zo0 + p.ZC);
+    } else {  // half-depth units of the last round (nzc == 1)
+      const int h = u - p.split_from, uu = p.split_from + (h >> 1);
+      tile = uu % p.ntile;
+      n = uu / p.ntile;
+      zo0 = (h & 1) ? p.split_zh : 0;
+      zo1 = (h & 1) ? Z : p.split_zh;
     }
   };
 
@@ -127,9 +139,8 @@ __global__ void __launch_bounds__(LANES == 2 ? RTP_K3S1_DUAL_BOUND : kThreads, 1
       uint32_t it = 0, wit = 0;
       bool w_loaded = false;
       for (int u = blockIdx.x; u < p.nunits; u += gridDim.x) {
-        int n, zc, tile;
-        decode(u, n, zc, tile);
-        const int zo0 = zc * p.ZC, zo1 = min(Z, zo0 + p.ZC);
+        int n, zo0, zo1, tile;
+        decode(u, n, zo0, zo1, tile);
         const int iz0 = max(0, zo0 - 1), iz1 = min(Z, zo1 + 1);
         const int64_t qoff = ((int64_t)tile * 128 - 1) * 8;  // first staged position = q0 - Yp - 1, q0 = Yp + tile*128
         const bf16* in_n = p.in.ptr + (int64_t)n * p.in.n_stride + qoff;
@@ -184,9 +195,8 @@ __global__ void __launch_bounds__(LANES == 2 ? RTP_K3S1_DUAL_BOUND : kThreads, 1
       const uint32_t stage0 = smem_u32(stages), wbase0 = smem_u32(wbuf);
       auto mk_desc = [](uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; };
       for (int u = blockIdx.x; u < p.nunits; u += gridDim.x) {
-        int n, zc, tile;
-        decode(u, n, zc, tile);
-        const int zo0 = zc * p.ZC, zo1 = min(Z, zo0 + p.ZC);
+        int n, zo0, zo1, tile;
+        decode(u, n, zo0, zo1, tile);
         const int iz0 = max(0, zo0 - 1), iz1 = min(Z, zo1 + 1);
         for (int g = 0; g < p.npass; ++g) {
           if (p.npass > 1 || !w_ready) {
@@ -297,9 +307,8 @@ __global__ void __launch_bounds__(LANES == 2 ? RTP_K3S1_DUAL_BOUND : kThreads, 1
       pre_ring = reinterpret_cast<uint4*>(smem + p.pre_off) + (size_t)(L * 128 + r) * 8;  // [2 buffers][4 chunks]
     }
     for (int u = blockIdx.x; u < p.nunits; u += gridDim.x) {
-      int n, zc, tile;
-      decode(u, n, zc, tile);
-      const int zo0 = zc * p.ZC, zo1 = min(Z, zo0 + p.ZC);
+      int n, zo0, zo1, tile;
+      decode(u, n, zo0, zo1, tile);
       const int q = Yp + tile * 128 + r;            // in-plane linear position (padded coordinates)
       const int xp = q / Yp, yp = q - xp * Yp;
       const bool ok = xp >= 1 && xp <= p.out.X && yp >= 1 && yp <= p.out.Y;
@@ -620,6 +629,23 @@ extern "C" int rtp_conv_k3s1(const rtp_conv_k3s1_desc* d, void* stream) {
   k.has_res = d->res.ptr != nullptr; k.has_mask = d->mask.ptr != nullptr;
   k.KG = pl.KG; k.npass = pl.npass; k.PW = pl.PW; k.ntile = pl.ntile; k.ZC = pl.ZC; k.nzc = pl.nzc;
   k.nunits = plan_units(pl, d->in.N);
+  static int nsm = 0;
+  if (!nsm) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+  }
+  k.split_from = 0x7fffffff;
+  k.split_zh = 0;
+  static const bool no_split = getenv("RTP_NO_TAIL_SPLIT") != nullptr;  // A/B switch
+  if (!no_split && pl.lanes == 1 && pl.nzc == 1 && d->in.Z >= 4 && d->in.Z % 2 == 0) {
+    const int rem = k.nunits % nsm;
+    if (k.nunits > nsm && rem > 0 && 2 * rem <= nsm) {  // e.g. 352 units on 148 SMs: 296 full + 112 half-depth units
+      k.split_from = k.nunits - rem;
+      k.split_zh = d->in.Z / 2;
+      k.nunits += rem;
+    }
+  }
   k.nstages = pl.nstages; k.stage_bytes = pl.stage_bytes; k.wbuf_bytes = pl.wbuf_bytes;
   k.pre_off = pl.lanes == 2 ? pl.pre_off : 0;
   k.wtap_bytes = (uint32_t)(pl.KG / 8) * k.N3 * 16;          // one tap's [KG/8][N3][8] slice
@@ -653,12 +679,6 @@ extern "C" int rtp_conv_k3s1(const rtp_conv_k3s1_desc* d, void* stream) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
     if (e != cudaSuccess) { rtp_set_error("rtp_conv_k3s1: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
     configured[ki] = pl.smem;
-  }
-  static int nsm = 0;
-  if (!nsm) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
   }
   const int grid = k.nunits < nsm ? k.nunits : nsm;
   kern<<<grid, pl.lanes == 2 ? kThreads2 : kThreads, pl.smem, (cudaStream_t)stream>>>(k);

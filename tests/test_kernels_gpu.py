@@ -518,6 +518,38 @@ def test_conv_k3s1_forward_and_dgrad(ctx, case):
         close(dx2.to_ncdhw(), base + x.grad * (mask > 0), tol=2 * BF16_ULP, what="k3s1 dgrad mask+acc")
 
 
+def test_conv_k3s1_tail_split_half_depth_units(ctx):
+    """Single-lane conv_k3s1 whose unit count leaves a partly filled last round (the half-resolution 64 -> 64 convs of the
+    bench: 16 samples x 22 tiles = 352 units on 148 SMs): the units of that round run as two half-depth units each.  Forward
+    (bias, ReLU, residual) and dgrad (mask, accumulate) against torch on the GPU."""
+    from rtpose_b200 import lib, ops
+    from rtpose_b200.p8 import P8
+    N, Cin, Cout, grid = 16, 64, 64, (8, 32, 80)
+    nsm = ops.num_sms()
+    ntile = ((grid[2]) * (grid[1] + 2) + 127) // 128
+    assert N * ntile > nsm and 0 < (N * ntile) % nsm <= nsm // 2, "shape no longer produces a short last round on this GPU"
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = bf(torch.randn(N, Cin, *grid, device="cuda", generator=g)).requires_grad_(True)
+    w = bf(torch.randn(Cout, Cin, 3, 3, 3, device="cuda", generator=g) * (Cin * 27) ** -0.5).requires_grad_(True)
+    b = bf(torch.randn(Cout, device="cuda", generator=g))
+    res = bf(torch.randn(N, Cout, *grid, device="cuda", generator=g))
+    pre = F.conv3d(x, w, b, padding=1)
+    ref = F.relu(pre + res)
+    xp = P8.from_ncdhw(x.detach())
+    out = P8(N, Cout, *grid)
+    ops.conv_forward(ctx, xp, w.detach(), 1, out, bias=b, relu=True, res=P8.from_ncdhw(res))
+    torch.cuda.synchronize()
+    close(out.to_ncdhw(), ref, what="k3s1 fwd with half-depth tail units")
+    dy = bf(torch.randn(N, Cout, *grid, device="cuda", generator=g))
+    pre.backward(dy)
+    mask = bf(torch.randn(N, Cin, *grid, device="cuda", generator=g))
+    base = bf(torch.randn(N, Cin, *grid, device="cuda", generator=g))
+    dx = P8.from_ncdhw(base)
+    ops.conv_dgrad(ctx, P8.from_ncdhw(dy), w.detach(), 1, dx, mask=P8.from_ncdhw(mask), accumulate=True)
+    torch.cuda.synchronize()
+    close(dx.to_ncdhw(), base + x.grad * (mask > 0), tol=2 * BF16_ULP, what="k3s1 dgrad with half-depth tail units")
+
+
 def test_generic_path_still_used_when_fast_path_disabled(ctx):
     from rtpose_b200 import ops
     from rtpose_b200.p8 import P8
