@@ -110,12 +110,21 @@ __global__ void __launch_bounds__(LANES == 2 ? RTP_K3S1_DUAL_BOUND : kThreads, 1
   fence_after_sync();
   const uint32_t tmem = tmem_base_s + (uint32_t)L * 256u;  // lane L accumulates in its own 256 columns
 
-  auto decode = [&](int u, int& n, int& zo0, int& zo1, int& tile) {
+  // returns false when this lane has nothing to do in unit u (LANES = 2, split last round: one lane per CTA)
+  auto decode = [&](int u, int& n, int& zo0, int& zo1, int& tile) -> bool {
     if constexpr (LANES == 2) {  // a unit is (sample, tile); the z-chunk is the lane
-      tile = u % p.ntile;
-      n = u / p.ntile;
+      int uu = u;
+      bool active = true;
+      if (u >= p.split_from) {  // last round: unit uu is shared by two CTAs, each running ONE lane with the tensor pipe to itself
+        const int h = u - p.split_from;
+        uu = p.split_from + (h >> 1);
+        active = (h & 1) == L;
+      }
+      tile = uu % p.ntile;
+      n = uu / p.ntile;
       zo0 = L * p.ZC;
       zo1 = min(Z, zo0 + p.ZC);
+      return active;
     } else if (u < p.split_from) {
       tile = u % p.ntile;
       const int r = u / p.ntile;
@@ -129,6 +138,7 @@ __global__ void __launch_bounds__(LANES == 2 ? RTP_K3S1_DUAL_BOUND : kThreads, 1
       zo0 = (h & 1) ? p.split_zh : 0;
       zo1 = (h & 1) ? Z : p.split_zh;
     }
+    return true;
   };
 
   if (role == 0) {
@@ -140,7 +150,7 @@ __global__ void __launch_bounds__(LANES == 2 ? RTP_K3S1_DUAL_BOUND : kThreads, 1
       bool w_loaded = false;
       for (int u = blockIdx.x; u < p.nunits; u += gridDim.x) {
         int n, zo0, zo1, tile;
-        decode(u, n, zo0, zo1, tile);
+        if (!decode(u, n, zo0, zo1, tile)) continue;
         const int iz0 = max(0, zo0 - 1), iz1 = min(Z, zo1 + 1);
         const int64_t qoff = ((int64_t)tile * 128 - 1) * 8;  // first staged position = q0 - Yp - 1, q0 = Yp + tile*128
         const bf16* in_n = p.in.ptr + (int64_t)n * p.in.n_stride + qoff;
@@ -196,7 +206,7 @@ __global__ void __launch_bounds__(LANES == 2 ? RTP_K3S1_DUAL_BOUND : kThreads, 1
       auto mk_desc = [](uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; };
       for (int u = blockIdx.x; u < p.nunits; u += gridDim.x) {
         int n, zo0, zo1, tile;
-        decode(u, n, zo0, zo1, tile);
+        if (!decode(u, n, zo0, zo1, tile)) continue;
         const int iz0 = max(0, zo0 - 1), iz1 = min(Z, zo1 + 1);
         for (int g = 0; g < p.npass; ++g) {
           if (p.npass > 1 || !w_ready) {
@@ -308,7 +318,7 @@ __global__ void __launch_bounds__(LANES == 2 ? RTP_K3S1_DUAL_BOUND : kThreads, 1
     }
     for (int u = blockIdx.x; u < p.nunits; u += gridDim.x) {
       int n, zo0, zo1, tile;
-      decode(u, n, zo0, zo1, tile);
+      if (!decode(u, n, zo0, zo1, tile)) continue;
       const int q = Yp + tile * 128 + r;            // in-plane linear position (padded coordinates)
       const int xp = q / Yp, yp = q - xp * Yp;
       const bool ok = xp >= 1 && xp <= p.out.X && yp >= 1 && yp <= p.out.Y;
@@ -638,9 +648,10 @@ extern "C" int rtp_conv_k3s1(const rtp_conv_k3s1_desc* d, void* stream) {
   k.split_from = 0x7fffffff;
   k.split_zh = 0;
   static const bool no_split = getenv("RTP_NO_TAIL_SPLIT") != nullptr;  // A/B switch
-  if (!no_split && pl.lanes == 1 && pl.nzc == 1 && d->in.Z >= 4 && d->in.Z % 2 == 0) {
+  if (!no_split && ((pl.lanes == 1 && pl.nzc == 1 && d->in.Z >= 4 && d->in.Z % 2 == 0) || pl.lanes == 2)) {
+    // lanes == 2: the two z-chunk lanes of a last-round unit go to two CTAs (a lone lane has the tensor pipe to itself)
     const int rem = k.nunits % nsm;
-    if (k.nunits > nsm && rem > 0 && 2 * rem <= nsm) {  // e.g. 352 units on 148 SMs: 296 full + 112 half-depth units
+    if (k.nunits > nsm && rem > 0 && 2 * rem <= nsm) {  // e.g. 352 units on 148 SMs: 296 full + 112 half units
       k.split_from = k.nunits - rem;
       k.split_zh = d->in.Z / 2;
       k.nunits += rem;

@@ -518,13 +518,15 @@ def test_conv_k3s1_forward_and_dgrad(ctx, case):
         close(dx2.to_ncdhw(), base + x.grad * (mask > 0), tol=2 * BF16_ULP, what="k3s1 dgrad mask+acc")
 
 
-def test_conv_k3s1_tail_split_half_depth_units(ctx):
-    """Single-lane conv_k3s1 whose unit count leaves a partly filled last round (the half-resolution 64 -> 64 convs of the
-    bench: 16 samples x 22 tiles = 352 units on 148 SMs): the units of that round run as two half-depth units each.  Forward
-    (bias, ReLU, residual) and dgrad (mask, accumulate) against torch on the GPU."""
+@pytest.mark.parametrize("chan", [64, 32], ids=["single_lane_64", "dual_lane_32"])
+def test_conv_k3s1_tail_split_half_depth_units(ctx, chan):
+    """conv_k3s1 whose unit count leaves a partly filled last round (the half-resolution convs of the bench: 16 samples x 22
+    tiles = 352 units on 148 SMs): the units of that round run as two half units each — half the output planes (single lane,
+    64 channels) or one z-chunk lane per CTA (dual lane, 32 channels).  Forward (bias, ReLU, residual) and dgrad (mask,
+    accumulate) against torch on the GPU; the fused GroupNorm statistics of the dual-lane kernel against a separate pass."""
     from rtpose_b200 import lib, ops
     from rtpose_b200.p8 import P8
-    N, Cin, Cout, grid = 16, 64, 64, (8, 32, 80)
+    N, Cin, Cout, grid = 16, chan, chan, (8, 32, 80)
     nsm = ops.num_sms()
     ntile = ((grid[2]) * (grid[1] + 2) + 127) // 128
     assert N * ntile > nsm and 0 < (N * ntile) % nsm <= nsm // 2, "shape no longer produces a short last round on this GPU"
@@ -548,6 +550,13 @@ def test_conv_k3s1_tail_split_half_depth_units(ctx):
     ops.conv_dgrad(ctx, P8.from_ncdhw(dy), w.detach(), 1, dx, mask=P8.from_ncdhw(mask), accumulate=True)
     torch.cuda.synchronize()
     close(dx.to_ncdhw(), base + x.grad * (mask > 0), tol=2 * BF16_ULP, what="k3s1 dgrad with half-depth tail units")
+    if chan == 32 and ops.stat_fusable(xp, w.detach(), False):
+        out2 = P8(N, Cout, *grid)
+        _, st = ops.conv_forward(ctx, xp, w.detach(), 1, out2, bias=b, relu=True, res=P8.from_ncdhw(res), stat=("stats", 8, 1e-5))
+        want = ops.gn_stats(out2, 8)
+        torch.cuda.synchronize()
+        assert torch.equal(out2.to_ncdhw(), out.to_ncdhw())
+        close(st, want, tol=1e-4, what="fused statistics with split tail units")
 
 
 def test_generic_path_still_used_when_fast_path_disabled(ctx):
