@@ -323,6 +323,17 @@ int rtp_s2d_fold_wgrad(rtp_p8 dy, const float* dw_xhat, const float* w, const fl
                        float* dW, float* dgamma, float* dbeta, int32_t Cout, int32_t Cin, int32_t accumulate_w,
                        int32_t accumulate_gb, void* stream);
 
+/* Backward of the regression branch's last conv from the SPARSE loss gradient (csrc/head_sparse.cu).  CenterHead.loss gathers
+ * the regression output at the target voxels only (center_head.py:244-270), so d_reg — written by rtp_head_loss — is zero
+ * except at the <= M voxels ind[n][0..M) of each sample (reference flat index z*Y*X + y*X + x).  Computes, without touching the
+ * rest of the volume: dt = [t_in > 0] * conv_transpose(d_reg, w) (dt is zero-filled first; Cin channels), dW (= or +=) and
+ * db (= or +=) of the conv y = conv3x3x3(t_in, w) + b, w fp32 [R][Cin][3][3][3].  M <= 64, R <= 64.
+ * replaces: autograd through SepHead's last Conv (center_head.py:95-104) for the `reg` branch. */
+int64_t rtp_reg_head_bwd_sparse_workspace_bytes(int32_t N, int32_t M);
+int rtp_reg_head_bwd_sparse(rtp_p8 d_reg, rtp_p8 t_in, const int64_t* ind, int32_t M, const float* w, int32_t R, int32_t Cin,
+                            rtp_p8 dt, float* dW, int32_t accumulate_w, float* db, int32_t accumulate_b, void* workspace,
+                            void* stream);
+
 /* ---- branch exchange ---------------------------------------------------------------------------------------
  * replaces: the fuse sum of HighResolutionModule.forward (hr_util/hr3d.py:213-227) and the upsample+cat of
  * HRNet3D.forward (hrnet3d.py:37-42): out = [relu]( sum_i same[i] + sum_j trilinear_up(low[j]) + bias ),

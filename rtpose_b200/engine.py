@@ -65,6 +65,7 @@ class Engine:
         self._last_touch, self._closure_idx = {}, -1
         self._grad_groups, self._on_ready, self._milestones = None, None, None
         self._s2d_share, self._s2d_scratch, self._unit_affine = {}, {}, {}
+        self._reg_sparse = None  # (reg.grad, ind) of the last loss() call: lets head.bwd take the sparse path
         self.generation = 0  # bumped by begin(): a backward job checks that the tape it recorded is still the live one
 
     # ------------------------------------------------------------------ helpers
@@ -564,7 +565,16 @@ class Engine:
                 if hm.grad is None or reg.grad is None:
                     return
                 tg = self.new(t)
+                sp = self._reg_sparse
+                self._reg_sparse = None
                 for name, tv, o, c0 in (("reg", t_reg, reg, 0), ("hm", t_hm, hm, hc)):
+                    if (name == "reg" and sp is not None and sp[0] is reg.grad and ops.reg_sparse_supported(p[q + "reg.2.weight"], sp[1])):
+                        # the loss touches `reg` at the target voxels only: its gradient is zero elsewhere, and the whole
+                        # backward of reg.2 (dgrad, weight and bias gradients) is a few hundred voxel neighbourhoods
+                        gw, acc = self._pgrad(q + "reg.2.weight")
+                        gb, accb = self._pgrad(q + "reg.2.bias")
+                        ops.reg_head_bwd_sparse(reg.grad, tv, sp[1], p[q + "reg.2.weight"], tg.channels(c0, hc), gw, acc, gb, accb)
+                        continue
                     gw, acc = self._pgrad(q + name + ".2.weight")
                     ops.conv_wgrad_async(tv, o.grad, 3, 1, gw, accumulate=acc)
                     gb, accb = self._pgrad(q + name + ".2.bias")
@@ -623,6 +633,7 @@ class Engine:
             else:
                 hm.grad = self.new(hm)
             reg.grad = self.new(reg)
+            self._reg_sparse = (reg.grad, ind)  # the regression gradient is non-zero at the target voxels only (head.bwd)
             dh, dr = hm.grad.struct(), reg.grad.struct()
         else:
             dh = dr = lib.NULL_P8

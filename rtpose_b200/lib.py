@@ -118,6 +118,8 @@ PROTOTYPES = {
     "rtp_wgrad_pw_workspace_bytes": (C.c_int64, [_i32, _i32]),
     "rtp_wgrad_pw": (C.c_int, [P8Struct, P8Struct, _i32, _vp, _vp, C.POINTER(C.c_int32), _vp]),
     "rtp_wgrad_pw_reduce": (C.c_int, [_vp, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _vp]),
+    "rtp_reg_head_bwd_sparse_workspace_bytes": (C.c_int64, [_i32, _i32]),
+    "rtp_reg_head_bwd_sparse": (C.c_int, [P8Struct, P8Struct, _vp, _i32, _vp, _i32, _i32, P8Struct, _vp, _i32, _vp, _i32, _vp, _vp]),
     "rtp_wgrad_pw_bias_workspace_bytes": (C.c_int64, [_i32, _i32]),
     "rtp_wgrad_pw_bias": (C.c_int, [P8Struct, P8Struct, _i32, _vp, _vp, _vp, C.POINTER(C.c_int32), _vp]),
     "rtp_wgrad_pw_bias_reduce": (C.c_int, [_vp, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),
@@ -232,7 +234,8 @@ LAUNCHES = {"rtp_pack_ncdhw": 1, "rtp_unpack_ncdhw": 1, "rtp_ingest_pack": 1, "r
             "rtp_gn_bwd_apply_s2d": 1, "rtp_conv_k3s1_stat_finalize": 1, "rtp_conv_multi": 1, "rtp_gn_stats": 2,
             "rtp_wgrad_s2d": 1, "rtp_wgrad_s2d_reduce": 1, "rtp_s2d_fold_weights": 2, "rtp_s2d_border_bias": 1, "rtp_s2d_fold_wgrad": 3, "rtp_wgrad_pw": 1, "rtp_wgrad_pw_reduce": 1, "rtp_wgrad_pw_bias": 1, "rtp_wgrad_pw_bias_reduce": 1, "rtp_wgrad_pw_bias_workspace_bytes": 0,
             "rtp_conat_fwd": 1, "rtp_conat_supported": 0, "rtp_s2d_box_sums_workspace_bytes": 0,
-            "rtp_npy_probe": 0, "rtp_npy_read_roi_slab": 0, "rtp_set_shared_carveout": 0}  # host-only file readers
+            "rtp_npy_probe": 0, "rtp_npy_read_roi_slab": 0, "rtp_set_shared_carveout": 0, "rtp_reg_head_bwd_sparse": 3,
+            "rtp_reg_head_bwd_sparse_workspace_bytes": 0}  # host-only file readers
 launch_count = 0
 call_counts = {}  # C-ABI entry point -> number of calls (tests assert which kernel path a shape really took)
 

@@ -1063,5 +1063,25 @@ def grad_add(src, dst, mask=None, accumulate=False):
     _prof_end(key, ev, _tbytes(dst) * (2 + (1 if mask is not None else 0) + (1 if accumulate else 0)))
 
 
+USE_SPARSE_REG = not bool(_os.environ.get("RTP_NO_SPARSE_REG"))  # A/B switch: rtp_reg_head_bwd_sparse
+
+
+def reg_head_bwd_sparse(d_reg, t_in, ind, w, dt, dW, acc_w, db, acc_b):
+    """Backward of the regression branch's last 3x3x3 conv from the sparse loss gradient (csrc/head_sparse.cu)."""
+    L = lib.load()
+    N, M = ind.shape
+    R, Cin = w.shape[0], w.shape[1]
+    ws = workspace(L.rtp_reg_head_bwd_sparse_workspace_bytes(N, M), d_reg.buf.device, "regsp")
+    wc = w.detach()
+    assert wc.is_contiguous() and dW.is_contiguous() and ind.dtype == torch.int64 and ind.is_contiguous()
+    lib.call("rtp_reg_head_bwd_sparse", d_reg.struct(), t_in.struct(), ind.data_ptr(), M, wc.data_ptr(), R, Cin, dt.struct(),
+             dW.data_ptr(), int(acc_w), db.data_ptr(), int(acc_b), ws.data_ptr(), _stream())
+
+
+def reg_sparse_supported(w, ind):
+    return (USE_SPARSE_REG and w.dim() == 5 and tuple(w.shape[2:]) == (3, 3, 3) and w.shape[0] <= 64 and ind is not None
+            and ind.dim() == 2 and ind.shape[1] <= 64 and ind.dtype == torch.int64)
+
+
 def channel_sum(x, out, accumulate=False):
     lib.call("rtp_channel_sum", x.struct(), x.C, out.data_ptr(), int(accumulate), gn_ws(x).data_ptr(), _stream())

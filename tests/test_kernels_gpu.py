@@ -333,6 +333,59 @@ def test_batched_weight_packs_match_single_launches():
         assert not torch.equal(g, b)
 
 
+def test_sparse_regression_head_backward_matches_dense(ctx):
+    """rtp_reg_head_bwd_sparse (backward of the regression branch's last conv from the loss gradient, which is non-zero at
+    the target voxels only) against the dense kernels on the same tensors: input gradient with the ReLU mask, weight and bias
+    gradients; targets on the volume border, duplicate targets, adjacent targets (overlapping neighbourhoods), accumulate."""
+    from rtpose_b200 import ops
+    from rtpose_b200.p8 import P8
+    N, Cin, R, grid, M = 3, 32, 45, (6, 16, 24), 15
+    Z, Y, X = grid
+    g = torch.Generator().manual_seed(9)
+    t_in = bf(torch.randn(N, Cin, *grid, generator=g))           # hidden activations (sign = ReLU gate)
+    w = bf(torch.randn(R, Cin, 3, 3, 3, generator=g) * 0.05).cuda()
+    zz = torch.randint(0, Z, (N, M), generator=g); yy = torch.randint(0, Y, (N, M), generator=g); xx = torch.randint(0, X, (N, M), generator=g)
+    zz[0, 0], yy[0, 0], xx[0, 0] = 0, 0, 0                        # corner
+    zz[0, 1], yy[0, 1], xx[0, 1] = Z - 1, Y - 1, X - 1            # opposite corner
+    zz[1, 1], yy[1, 1], xx[1, 1] = zz[1, 0], yy[1, 0], xx[1, 0]   # duplicate voxel
+    zz[2, 1], yy[2, 1], xx[2, 1] = zz[2, 0], yy[2, 0], min(int(xx[2, 0]) + 1, X - 1)  # neighbours
+    ind = (zz * Y * X + yy * X + xx).to(torch.int64)
+    dyd = torch.zeros(N, R, *grid)
+    vals = bf(torch.randn(N, M, R, generator=g))
+    for n in range(N):
+        for j in range(M):
+            dyd[n, :, zz[n, j], yy[n, j], xx[n, j]] = vals[n, j]    # duplicates: last write wins (the tensor is the source of truth)
+    dyp, tp = to_p8(dyd), to_p8(t_in)
+    # dense reference with the repo's own kernels
+    dW_d, db_d = torch.zeros(R, Cin, 3, 3, 3, device="cuda"), torch.zeros(R, device="cuda")
+    ops.conv_wgrad(tp, dyp, 3, 1, dW_d)
+    ops.channel_sum(dyp, db_d)
+    dt_d = P8(N, Cin, *grid)
+    ops.conv_dgrad(ctx, dyp, w, 1, dt_d, mask=tp)
+    # sparse
+    dW_s, db_s = torch.full((R, Cin, 3, 3, 3), 7.0, device="cuda"), torch.full((R,), 7.0, device="cuda")
+    wide = P8(N, 2 * Cin, *grid)
+    wide.buf.fill_(1.0)                                           # garbage that the zero-fill must remove
+    dt_s = wide.channels(Cin, Cin)                                # a channel view, like the merged head gradient
+    ops.reg_head_bwd_sparse(dyp, tp, ind.cuda(), w, dt_s, dW_s, False, db_s, False)
+    torch.cuda.synchronize()
+    close(dt_s.to_ncdhw(), dt_d.to_ncdhw(), tol=1e-2, what="sparse vs dense dgrad of the regression head")
+    close(dW_s, dW_d, tol=1e-3, what="sparse vs dense weight gradient")
+    close(db_s, db_d, tol=1e-4, what="sparse vs dense bias gradient")
+    # against fp32 autograd as well
+    xr = t_in.clone().requires_grad_(True)
+    wr = w.cpu().clone().requires_grad_(True)
+    br = torch.zeros(R, requires_grad=True)
+    F.conv3d(xr, wr, br, padding=1).backward(dyd)
+    close(dt_s.to_ncdhw(), xr.grad * (t_in > 0), what="sparse dgrad vs autograd")
+    close(dW_s, wr.grad, tol=1e-3, what="sparse wgrad vs autograd")
+    close(db_s, br.grad, tol=1e-4, what="sparse bias gradient vs autograd")
+    ops.reg_head_bwd_sparse(dyp, tp, ind.cuda(), w, dt_s, dW_s, True, db_s, True)
+    torch.cuda.synchronize()
+    close(dW_s, 2 * wr.grad, tol=1e-3, what="sparse wgrad accumulate")
+    close(db_s, 2 * br.grad, tol=1e-4, what="sparse bias accumulate")
+
+
 def test_grad_add_channel_sum_stem():
     from rtpose_b200 import lib, ops
     from rtpose_b200.p8 import P8, _stream
