@@ -174,8 +174,19 @@ typedef struct {
   int32_t use_tap_mask, tap_mask_groups;
   uint16_t tap_mask[8];
   void* debug; /* tools only (tools/dbg_k3s1.py): [grid][8] int64 cycle counters of the MMA warp; NULL otherwise */
+  /* optional list of the (sample, 128-position tile) units to process (rtp_active_units): device int32 unit ids u = n * ntile +
+   * tile and their count; units not listed are skipped — with accumulate = 1 that leaves the existing output untouched, which
+   * is exact when the input is known to be zero around them (the regression half of the head gradient).  NULL = all units. */
+  const int32_t* unit_list;
+  const int32_t* unit_count;
 } rtp_conv_k3s1_desc;
 int rtp_conv_k3s1(const rtp_conv_k3s1_desc* d, void* stream);
+/* Units (n, tile) — tile = 128 consecutive in-plane positions of the padded plane, the unit of rtp_conv_k3s1 / rtp_wgrad_k3s1 —
+ * that contain a voxel within `radius` (in x and y; every z belongs to a unit) of one of the voxels ind[n][0..M) (reference flat
+ * index z*Y*X + y*X + x).  unit_list: int32 [N * ntile] (ascending ids, first *unit_count valid), ntile = ceil(X*(Y+2)/128).
+ * One small launch; deterministic order. */
+int rtp_active_units(const int64_t* ind, int32_t N, int32_t M, int32_t Z, int32_t X, int32_t Y, int32_t radius, int32_t* unit_list,
+                     int32_t* unit_count, void* stream);
 /* dynamic shared memory the kernel would use for this shape, or -1 when the shape is not supported (callers
  * then use rtp_conv) */
 int64_t rtp_conv_k3s1_smem_bytes(int32_t Cin, int32_t NPo, int32_t Z, int32_t X, int32_t Y);
@@ -230,6 +241,9 @@ int64_t rtp_wgrad_k3s1_workspace_bytes(int32_t NP, int32_t nsm);
 int64_t rtp_wgrad_k3s1_zero_bytes(int32_t Y);
 int rtp_wgrad_k3s1(rtp_p8 x, rtp_p8 dy, int32_t NP, const void* zero_page, float* workspace, int32_t* nsplit_out,
                    void* stream);
+/* The same over the listed units only (rtp_active_units; exact when dy is zero in every other unit). */
+int rtp_wgrad_k3s1_units(rtp_p8 x, rtp_p8 dy, int32_t NP, const void* zero_page, float* workspace, int32_t* nsplit_out,
+                         const int32_t* unit_list, const int32_t* unit_count, void* stream);
 int rtp_wgrad_k3s1_reduce(const float* workspace, int32_t nsplit, int32_t NP, float* dW, int32_t Cin_total,
                           int32_t co_n, int32_t n0, int32_t ci0, int32_t accumulate, void* stream);
 

@@ -57,6 +57,8 @@ struct K3 {
   // LANES = 1, one z-chunk: the units of the last, partly filled round (index >= split_from) are issued as two half-depth units
   // each (output planes [0, split_zh) and [split_zh, Z)), so that round costs (Z/2 + 1) / Z of a full one
   int split_from, split_zh;
+  const int* unit_list;   // optional: the unit ids to process (rtp_active_units) and their count, else all nunits
+  const int* unit_count;
   int nstages;
   uint32_t stage_bytes, wbuf_bytes, wtap_bytes, wtap_stride;  // per-pass weight slice: 9 copies of wtap_bytes
   long long* dbg;  // optional [grid][8] cycle counters (RTP_K3S1_DEBUG): MMA-warp wait/issue breakdown
@@ -111,6 +113,7 @@ __global__ void __launch_bounds__(LANES == 2 ? RTP_K3S1_DUAL_BOUND : kThreads, 1
   const uint32_t tmem = tmem_base_s + (uint32_t)L * 256u;  // lane L accumulates in its own 256 columns
 
   // returns false when this lane has nothing to do in unit u (LANES = 2, split last round: one lane per CTA)
+  const int nloop = p.unit_list ? __ldg(p.unit_count) : p.nunits;
   auto decode = [&](int u, int& n, int& zo0, int& zo1, int& tile) -> bool {
     if constexpr (LANES == 2) {  // a unit is (sample, tile); the z-chunk is the lane
       int uu = u;
@@ -148,7 +151,8 @@ __global__ void __launch_bounds__(LANES == 2 ? RTP_K3S1_DUAL_BOUND : kThreads, 1
     {
       uint32_t it = 0, wit = 0;
       bool w_loaded = false;
-      for (int u = blockIdx.x; u < p.nunits; u += gridDim.x) {
+      for (int ku = blockIdx.x; ku < nloop; ku += gridDim.x) {
+        const int u = p.unit_list ? p.unit_list[ku] : ku;
         int n, zo0, zo1, tile;
         if (!decode(u, n, zo0, zo1, tile)) continue;
         const int iz0 = max(0, zo0 - 1), iz1 = min(Z, zo1 + 1);
@@ -204,7 +208,8 @@ __global__ void __launch_bounds__(LANES == 2 ? RTP_K3S1_DUAL_BOUND : kThreads, 1
       const uint32_t a_k16 = 2u * p.PW, b_k16 = 2u * p.N3, b_tap16 = p.wtap_bytes >> 4;
       const uint32_t stage0 = smem_u32(stages), wbase0 = smem_u32(wbuf);
       auto mk_desc = [](uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; };
-      for (int u = blockIdx.x; u < p.nunits; u += gridDim.x) {
+      for (int ku = blockIdx.x; ku < nloop; ku += gridDim.x) {
+        const int u = p.unit_list ? p.unit_list[ku] : ku;
         int n, zo0, zo1, tile;
         if (!decode(u, n, zo0, zo1, tile)) continue;
         const int iz0 = max(0, zo0 - 1), iz1 = min(Z, zo1 + 1);
@@ -316,7 +321,8 @@ __global__ void __launch_bounds__(LANES == 2 ? RTP_K3S1_DUAL_BOUND : kThreads, 1
       use_ring = p.pre_off != 0 && (STAT == 2 || p.has_res);
       pre_ring = reinterpret_cast<uint4*>(smem + p.pre_off) + (size_t)(L * 128 + r) * 8;  // [2 buffers][4 chunks]
     }
-    for (int u = blockIdx.x; u < p.nunits; u += gridDim.x) {
+    for (int ku = blockIdx.x; ku < nloop; ku += gridDim.x) {
+        const int u = p.unit_list ? p.unit_list[ku] : ku;
       int n, zo0, zo1, tile;
       if (!decode(u, n, zo0, zo1, tile)) continue;
       const int q = Yp + tile * 128 + r;            // in-plane linear position (padded coordinates)
@@ -647,8 +653,13 @@ extern "C" int rtp_conv_k3s1(const rtp_conv_k3s1_desc* d, void* stream) {
   }
   k.split_from = 0x7fffffff;
   k.split_zh = 0;
+  k.unit_list = d->unit_list;
+  k.unit_count = d->unit_count;
+  if (d->unit_list) {
+    RTP_CHECK_ARG(d->unit_count && (pl.lanes == 2 || pl.nzc == 1), "rtp_conv_k3s1: a unit list needs one z-chunk per unit");
+  }
   static const bool no_split = getenv("RTP_NO_TAIL_SPLIT") != nullptr;  // A/B switch
-  if (!no_split && ((pl.lanes == 1 && pl.nzc == 1 && d->in.Z >= 4 && d->in.Z % 2 == 0) || pl.lanes == 2)) {
+  if (!no_split && !d->unit_list && ((pl.lanes == 1 && pl.nzc == 1 && d->in.Z >= 4 && d->in.Z % 2 == 0) || pl.lanes == 2)) {
     // lanes == 2: the two z-chunk lanes of a last-round unit go to two CTAs (a lone lane has the tensor pipe to itself)
     const int rem = k.nunits % nsm;
     if (k.nunits > nsm && rem > 0 && 2 * rem <= nsm) {  // e.g. 352 units on 148 SMs: 296 full + 112 half units
@@ -724,4 +735,46 @@ extern "C" int rtp_conv_k3s1_stat_finalize(const float* stat_ws, int32_t nctas, 
 
 int rtp_k3s1_set_carveout(int pct) {  // see rtp_set_shared_carveout (layout.cu)
   return (int)cudaFuncSetAttribute((const void*)stat_finalize_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+}
+
+namespace {
+// one block: flags in shared memory, then an ordered compaction by thread 0 (a few thousand units at most)
+__global__ void __launch_bounds__(1024) active_units_kernel(const int64_t* __restrict__ ind, int N, int M, int X, int Y, int radius,
+                                                            int ntile, int* __restrict__ list, int* __restrict__ count) {
+  extern __shared__ int au_flags[];
+  const int total = N * ntile, Yp = Y + 2;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) au_flags[i] = 0;
+  __syncthreads();
+  const int side = 2 * radius + 1;
+  const int items = N * M * side * side;
+  const int64_t YX = (int64_t)Y * X;
+  for (int i = threadIdx.x; i < items; i += blockDim.x) {
+    const int dy = i % side - radius, dx = (i / side) % side - radius;
+    const int j = i / (side * side);  // n * M + target
+    const int64_t id = ind[j];
+    const int r = (int)(id % YX);
+    const int y = r / X + dy, x = r % X + dx;
+    if (x < 0 || x >= X || y < 0 || y >= Y) continue;
+    const int q = (x + 1) * Yp + (y + 1);
+    au_flags[(j / M) * ntile + (q - Yp) / 128] = 1;  // benign race: every writer stores 1
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int c = 0;
+    for (int i = 0; i < total; ++i)
+      if (au_flags[i]) list[c++] = i;
+    *count = c;
+  }
+}
+}  // namespace
+
+extern "C" int rtp_active_units(const int64_t* ind, int32_t N, int32_t M, int32_t Z, int32_t X, int32_t Y, int32_t radius,
+                                int32_t* unit_list, int32_t* unit_count, void* stream) {
+  RTP_CHECK_ARG(ind && unit_list && unit_count && N >= 1 && M >= 1 && Z >= 1 && X >= 1 && Y >= 1 && radius >= 0 && radius <= 8,
+                "rtp_active_units: bad arguments");
+  const int ntile = (X * (Y + 2) + 127) / 128;
+  RTP_CHECK_ARG((int64_t)N * ntile <= 11000, "rtp_active_units: too many units for one block's shared memory");
+  active_units_kernel<<<1, 1024, (size_t)N * ntile * sizeof(int), (cudaStream_t)stream>>>(ind, N, M, X, Y, radius, ntile, unit_list,
+                                                                                          unit_count);
+  RTP_LAUNCH_CHECK();
 }

@@ -36,6 +36,8 @@ struct WG3 {
   const bf16* zero_page;  // >= 2048 bytes of zeros (stands in for the dY planes z = -1 and z = Z)
   int NP;                 // dY channels padded to 16
   int ntile, nunits;
+  const int* unit_list;   // optional: the unit ids to process (rtp_active_units) and their count, else all nunits
+  const int* unit_count;
   int nstages;            // X stages (one step each)
   int R;                  // dY ring slots (+2 mirror slots behind them)
   int valid_pos;          // X*Yp: positions past this in the last tile are skipped in whole k16 steps
@@ -66,13 +68,15 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_k3s1_kernel(const __grid_co
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem = tmem_base_s;
-  const bool has_work = (int)blockIdx.x < p.nunits;
+  const int nloop = p.unit_list ? __ldg(p.unit_count) : p.nunits;
+  const bool has_work = (int)blockIdx.x < nloop;
 
   if (warp == 0) {
     // producer warp: lane 0 runs the barrier protocol, then all lanes issue the step's bulk copies in parallel
     uint32_t it = 0, gbase = 0;  // CTA-local step counter / plane counter at the start of the unit
     const int nch = p.NP / 8;
-    for (int u = blockIdx.x; u < p.nunits; u += gridDim.x, gbase += ZP) {
+    for (int ku = blockIdx.x; ku < nloop; ku += gridDim.x, gbase += ZP) {
+      const int u = p.unit_list ? p.unit_list[ku] : ku;
       const int tile = u % p.ntile, n = u / p.ntile;
       const int64_t q0 = (int64_t)Yp + (int64_t)tile * 128;
       const bf16* xn = p.x.ptr + (int64_t)n * p.x.n_stride + (q0 - 1 - Yp) * 8;
@@ -132,7 +136,8 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_k3s1_kernel(const __grid_co
     const uint32_t idesc = idesc_bf16(128, N3, 1, 1);
     const uint32_t a_hi = p.a_sbo | (1u << 14), b_hi = 128u | (1u << 14);
     const uint32_t smem0 = smem_u32(smem), ring0 = smem_u32(ring);
-    for (int u = blockIdx.x; u < p.nunits; u += gridDim.x, gbase += ZP) {
+    for (int ku = blockIdx.x; ku < nloop; ku += gridDim.x, gbase += ZP) {
+      const int u = p.unit_list ? p.unit_list[ku] : ku;
       const int tile = u % p.ntile;
       int nk16 = (p.valid_pos - tile * 128 + 15) / 16;  // whole 16-position K steps inside the plane
       nk16 = nk16 > 8 ? 8 : nk16;
@@ -266,8 +271,8 @@ extern "C" int rtp_wgrad_k3s1_supported(int32_t Cin, int32_t NP, int32_t Z, int3
   return plan(NP, Y, S, R, span, xs, sb, smem) && Z >= 1 && X >= 1 ? 1 : 0;
 }
 
-extern "C" int rtp_wgrad_k3s1(rtp_p8 x, rtp_p8 dy, int32_t NP, const void* zero_page, float* workspace, int32_t* nsplit_out,
-                              void* stream) {
+static int wgrad_k3s1_launch(rtp_p8 x, rtp_p8 dy, int32_t NP, const void* zero_page, float* workspace, int32_t* nsplit_out,
+                             const int32_t* unit_list, const int32_t* unit_count, void* stream) {
   RTP_CHECK_ARG(x.ptr && dy.ptr && zero_page && workspace && nsplit_out, "rtp_wgrad_k3s1: null argument");
   RTP_CHECK_ARG(x.N == dy.N && x.Z == dy.Z && x.X == dy.X && x.Y == dy.Y, "rtp_wgrad_k3s1: geometry mismatch");
   RTP_CHECK_ARG(x.C8 >= 4 && rtp_wgrad_k3s1_supported(32, NP, x.Z, x.X, x.Y), "rtp_wgrad_k3s1: unsupported shape NP=%d", NP);
@@ -283,6 +288,8 @@ extern "C" int rtp_wgrad_k3s1(rtp_p8 x, rtp_p8 dy, int32_t NP, const void* zero_
   k.ntile = (k.valid_pos + 127) / 128;
   k.nunits = x.N * k.ntile;
   k.partial = workspace;
+  k.unit_list = unit_list;
+  k.unit_count = unit_count;
   k.dbg = rtp_wgrad_k3s1_dbg;
   static int nsm = 0;
   if (!nsm) {
@@ -301,6 +308,16 @@ extern "C" int rtp_wgrad_k3s1(rtp_p8 x, rtp_p8 dy, int32_t NP, const void* zero_
   }
   wgrad_k3s1_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(k);
   RTP_LAUNCH_CHECK();
+}
+
+extern "C" int rtp_wgrad_k3s1(rtp_p8 x, rtp_p8 dy, int32_t NP, const void* zero_page, float* workspace, int32_t* nsplit_out,
+                              void* stream) {
+  return wgrad_k3s1_launch(x, dy, NP, zero_page, workspace, nsplit_out, nullptr, nullptr, stream);
+}
+extern "C" int rtp_wgrad_k3s1_units(rtp_p8 x, rtp_p8 dy, int32_t NP, const void* zero_page, float* workspace, int32_t* nsplit_out,
+                                    const int32_t* unit_list, const int32_t* unit_count, void* stream) {
+  RTP_CHECK_ARG(unit_list && unit_count, "rtp_wgrad_k3s1_units: null unit list");
+  return wgrad_k3s1_launch(x, dy, NP, zero_page, workspace, nsplit_out, unit_list, unit_count, stream);
 }
 
 extern "C" int rtp_wgrad_k3s1_reduce(const float* workspace, int32_t nsplit, int32_t NP, float* dW, int32_t Cin_total,

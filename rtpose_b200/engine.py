@@ -567,8 +567,10 @@ class Engine:
                 tg = self.new(t)
                 sp = self._reg_sparse
                 self._reg_sparse = None
+                reg_sparse = False
                 for name, tv, o, c0 in (("reg", t_reg, reg, 0), ("hm", t_hm, hm, hc)):
                     if (name == "reg" and sp is not None and sp[0] is reg.grad and ops.reg_sparse_supported(p[q + "reg.2.weight"], sp[1])):
+                        reg_sparse = True
                         # the loss touches `reg` at the target voxels only: its gradient is zero elsewhere, and the whole
                         # backward of reg.2 (dgrad, weight and bias gradients) is a few hundred voxel neighbourhoods
                         gw, acc = self._pgrad(q + "reg.2.weight")
@@ -586,13 +588,28 @@ class Engine:
                     ops.conv_dgrad(self.packs, dy, p[q + name + ".2.weight"], 1, tg.channels(c0, hc), mask=tv)
                 gw_r, acc_r = self._pgrad(q + "reg.0.weight")
                 gw_h, acc_h = self._pgrad(q + "hm.0.weight")
-                ops.conv_wgrad_async(f, tg, 3, 1, gw_r, accumulate=acc_r, n0=0, more=((gw_h, acc_h, 0, hc),))
+                # With the sparse regression gradient, the regression half of tg is non-zero only within one voxel of a target:
+                # the two halves of the merged conv go out separately, and the regression half's weight gradient / dgrad visit
+                # only the (sample, tile) units around the targets (within 1 / 2 voxels in the plane).
+                split = (reg_sparse and ops.USE_SPARSE_UNITS and hc == 32 and f.C % 32 == 0 and f.C > 80
+                         and ops.k3s1_eligible(tg.channels(0, hc), 32, 32))
+                if split:
+                    u1 = ops.active_units(sp[1], f, 1, "r1")
+                    u2 = ops.active_units(sp[1], f, 2, "r2")
+                    ops.conv_wgrad_async(f, tg.channels(hc, hc), 3, 1, gw_h, accumulate=acc_h)
+                    ops.conv_wgrad_async(f, tg.channels(0, hc), 3, 1, gw_r, accumulate=acc_r, units=u1)
+                else:
+                    ops.conv_wgrad_async(f, tg, 3, 1, gw_r, accumulate=acc_r, n0=0, more=((gw_h, acc_h, 0, hc),))
                 for name, c0 in (("reg", 0), ("hm", hc)):
                     gb, accb = self._pgrad(q + name + ".0.bias")
                     ops.on_aux_stream(tg, lambda c0=c0, gb=gb, accb=accb: ops.channel_sum(tg.channels(c0, hc), gb, accumulate=accb))
                 gf, accf = self._grad_of(f)
-                ops.conv_dgrad(self.packs, tg, w0, 1, gf, mask=f if f.relu_out else None, accumulate=accf, key=wkey,
-                               version=wver)
+                fmask = f if f.relu_out else None
+                if split:
+                    ops.conv_dgrad(self.packs, tg.channels(hc, hc), p[q + "hm.0.weight"], 1, gf, mask=fmask, accumulate=accf)
+                    ops.conv_dgrad(self.packs, tg.channels(0, hc), p[q + "reg.0.weight"], 1, gf, mask=fmask, accumulate=True, units=u2)
+                else:
+                    ops.conv_dgrad(self.packs, tg, w0, 1, gf, mask=fmask, accumulate=accf, key=wkey, version=wver)
                 self._wrote(f)
             self.tape.append(bwd)
         return hm, reg

@@ -34,7 +34,7 @@ class ConvK3S1Desc(C.Structure):
                 ("bias", C.c_void_p), ("Cin", C.c_int32), ("NPo", C.c_int32), ("out_c8", C.c_int32),
                 ("relu", C.c_int32), ("accumulate", C.c_int32), ("stat_mode", C.c_int32), ("stat_aux", P8Struct),
                 ("stat_ws", C.c_void_p), ("use_tap_mask", C.c_int32), ("tap_mask_groups", C.c_int32), ("tap_mask", C.c_uint16 * 8),
-                ("debug", C.c_void_p)]
+                ("debug", C.c_void_p), ("unit_list", C.c_void_p), ("unit_count", C.c_void_p)]
 
 
 class WgradDesc(C.Structure):
@@ -101,6 +101,8 @@ PROTOTYPES = {
     "rtp_wgrad_k3s1_workspace_bytes": (C.c_int64, [_i32, _i32]),
     "rtp_wgrad_k3s1_zero_bytes": (C.c_int64, [_i32]),
     "rtp_wgrad_k3s1": (C.c_int, [P8Struct, P8Struct, _i32, _vp, _vp, C.POINTER(_i32), _vp]),
+    "rtp_wgrad_k3s1_units": (C.c_int, [P8Struct, P8Struct, _i32, _vp, _vp, C.POINTER(_i32), _vp, _vp, _vp]),
+    "rtp_active_units": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "rtp_wgrad_k3s1_reduce": (C.c_int, [_vp, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "rtp_gn_workspace_bytes": (C.c_int64, [_i32, _i32]),
     "rtp_gn_sums": (C.c_int, [P8Struct, _i32, _vp, _vp, _vp]),
@@ -234,7 +236,7 @@ LAUNCHES = {"rtp_pack_ncdhw": 1, "rtp_unpack_ncdhw": 1, "rtp_ingest_pack": 1, "r
             "rtp_gn_bwd_apply_s2d": 1, "rtp_conv_k3s1_stat_finalize": 1, "rtp_conv_multi": 1, "rtp_gn_stats": 2,
             "rtp_wgrad_s2d": 1, "rtp_wgrad_s2d_reduce": 1, "rtp_s2d_fold_weights": 2, "rtp_s2d_border_bias": 1, "rtp_s2d_fold_wgrad": 3, "rtp_wgrad_pw": 1, "rtp_wgrad_pw_reduce": 1, "rtp_wgrad_pw_bias": 1, "rtp_wgrad_pw_bias_reduce": 1, "rtp_wgrad_pw_bias_workspace_bytes": 0,
             "rtp_conat_fwd": 1, "rtp_conat_supported": 0, "rtp_s2d_box_sums_workspace_bytes": 0,
-            "rtp_npy_probe": 0, "rtp_npy_read_roi_slab": 0, "rtp_set_shared_carveout": 0, "rtp_reg_head_bwd_sparse": 3,
+            "rtp_npy_probe": 0, "rtp_npy_read_roi_slab": 0, "rtp_set_shared_carveout": 0, "rtp_reg_head_bwd_sparse": 3, "rtp_active_units": 1, "rtp_wgrad_k3s1_units": 1,
             "rtp_reg_head_bwd_sparse_workspace_bytes": 0}  # host-only file readers
 launch_count = 0
 call_counts = {}  # C-ABI entry point -> number of calls (tests assert which kernel path a shape really took)

@@ -406,7 +406,7 @@ def s2d_tap_mask(par, flipped):
 
 
 def conv_k3s1(packs, x, w, out, transpose_flip, bias=None, relu=False, res=None, mask=None, accumulate=False, key=None,
-              version=None, stat=None, tap_mask=None, ci_window=None):
+              version=None, stat=None, tap_mask=None, ci_window=None, units=None):
     """Plane-streaming 3x3x3 s1 conv (forward: transpose_flip=False; dgrad: True).
     stat: None | ("stats", G, eps) -> returns (out, stats[N][G][2]) of the stored result (GroupNorm forward)
                | ("red", G, x_gn, stats) -> returns (out, red[N][C][2]) (GroupNorm backward reductions, out = dL/dxn)."""
@@ -425,6 +425,7 @@ def conv_k3s1(packs, x, w, out, transpose_flip, bias=None, relu=False, res=None,
     d.Cin, d.NPo, d.out_c8 = K, NPo, out.C8
     d.relu, d.accumulate = int(relu), int(accumulate)
     d.debug = None
+    d.unit_list, d.unit_count = (units[0].data_ptr(), units[1].data_ptr()) if units is not None else (None, None)
     d.stat_mode, d.stat_ws = 0, None
     d.use_tap_mask = 0
     if tap_mask is not None:  # list of per-K-group in-plane tap masks (structurally sparse weights)
@@ -487,12 +488,12 @@ def conv_forward(packs, x, w, stride, out, bias=None, relu=False, res=None, ci0=
 
 
 def conv_dgrad(packs, dy, w, stride, dx, mask=None, accumulate=False, ci0=0, ci_n=None, key=None, version=None, stat=None,
-               s2d_cin=None):
+               s2d_cin=None, units=None):
     """dx (=|+=) conv_transpose(dy, w) [* (mask > 0)]; dx has the forward input's geometry.
     stat (only when stat_fusable(dy, w, True) and stride 1): see conv_k3s1; the return value becomes (dx, red)."""
     k = w.shape[2]
     if k == 3 and stride == 1 and ci0 == 0 and ci_n is None and k3s1_eligible(dy, ceil_to(w.shape[0], 16), ceil_to(w.shape[1], 16)):
-        return conv_k3s1(packs, dy, w, dx, True, mask=mask, accumulate=accumulate, key=key, version=version, stat=stat)
+        return conv_k3s1(packs, dy, w, dx, True, mask=mask, accumulate=accumulate, key=key, version=version, stat=stat, units=units)
     assert stat is None, "fused statistics need the plane-streaming kernel (check stat_fusable first)"
     if (k == 3 and stride == 1 and ci0 == 0 and ci_n is None and w.shape[1] > 80 and w.shape[1] % 32 == 0
             and k3s1_eligible(dy, ceil_to(w.shape[0], 16), 32)):
@@ -513,8 +514,9 @@ def conv_dgrad(packs, dy, w, stride, dx, mask=None, accumulate=False, ci0=0, ci_
             conv_k3s1(packs, dy, w, dx.channels(g * gs, gs), True,
                       mask=mask.channels(g * gs, gs) if mask is not None else None, accumulate=accumulate,
                       key=(key if key is not None else w.data_ptr(), "dgrad_group", gs, g),
-                      version=version if version is not None else w._version, tap_mask=tm, ci_window=(g * gs, gs))
+                      version=version if version is not None else w._version, tap_mask=tm, ci_window=(g * gs, gs), units=units)
         return dx
+    assert units is None, "a unit list needs the plane-streaming kernel"
     wp, KP, NP = packs.get(w, 1, ci0, ci_n, key, version)
     real = (w.shape[0], ci_n if ci_n is not None else w.shape[1])
     if k == 1 and stride == 1 and USE_PW and pw_eligible(dy, dx, KP, NP):
@@ -554,8 +556,9 @@ def _zero_page(nbytes, device):
     return z
 
 
-def _wgrad_k3s1(x, dy, outs):
-    """Plane-streaming wgrad: loops 32-channel input groups x (<= 48)-channel dY groups; outs = [(dW, acc, ci0, n0)]."""
+def _wgrad_k3s1(x, dy, outs, units=None):
+    """Plane-streaming wgrad: loops 32-channel input groups x (<= 48)-channel dY groups; outs = [(dW, acc, ci0, n0)].
+    units = (list, count) from active_units(): only those (sample, tile) units are visited (dy is zero in all the others)."""
     L = lib.load()
     dev = x.buf.device
     zero = _zero_page(L.rtp_wgrad_k3s1_zero_bytes(x.Y), dev)
@@ -572,7 +575,11 @@ def _wgrad_k3s1(x, dy, outs):
                 ws, done = _split_ws("wgrad3", L.rtp_wgrad_k3s1_workspace_bytes(NP, num_sms()), dev)
                 key = ("wgrad_k3s1", 32, hn, 27, 1, 1, (x.Z, x.X, x.Y))
                 ev = _prof_begin(key)
-                lib.call("rtp_wgrad_k3s1", xg.struct(), dyg.struct(), NP, zero.data_ptr(), ws.data_ptr(), C.byref(nsplit), _stream())
+                if units is not None:
+                    lib.call("rtp_wgrad_k3s1_units", xg.struct(), dyg.struct(), NP, zero.data_ptr(), ws.data_ptr(), C.byref(nsplit),
+                             units[0].data_ptr(), units[1].data_ptr(), _stream())
+                else:
+                    lib.call("rtp_wgrad_k3s1", xg.struct(), dyg.struct(), NP, zero.data_ptr(), ws.data_ptr(), C.byref(nsplit), _stream())
                 _prof_end(key, ev, 2.0 * x.N * x.voxels * 32 * hn * 27)
                 done(lambda ws=ws, ns=nsplit.value, NP=NP, gw=gw, h=h, hn=hn, c=c0 + gi * 32, acc=acc: lib.call(
                     "rtp_wgrad_k3s1_reduce", ws.data_ptr(), ns, NP, gw[h:].data_ptr(), gw.shape[1], hn, 0, c, int(acc), _stream()))
@@ -661,7 +668,7 @@ def _split_ws(tag, nbytes, dev):
     return ws, done
 
 
-def conv_wgrad_async(x, dy, k, stride, dW, accumulate=False, ci0=0, n0=0, more=(), then=None, bias_grad=None):
+def conv_wgrad_async(x, dy, k, stride, dW, accumulate=False, ci0=0, n0=0, more=(), then=None, bias_grad=None, units=None):
     """conv_wgrad queued on a side stream, ordered after everything issued so far on the current stream.  The caller
     keeps x, dy and dW alive and untouched until join_wgrad() (the engine's buffers live until the end of the step).
     `then()` is called right after, on the same stream (post-processing of dW).  Falls back to the in-stream call when
@@ -670,7 +677,7 @@ def conv_wgrad_async(x, dy, k, stride, dW, accumulate=False, ci0=0, n0=0, more=(
     if _SKIP_WGRAD:  # timing experiments only (RTP_SKIP_WGRAD=1): how much of the step the weight gradients cost net
         return None
     if not ASYNC_WGRAD:
-        conv_wgrad(x, dy, k, stride, dW, accumulate, ci0, n0, more, bias_grad=bias_grad)
+        conv_wgrad(x, dy, k, stride, dW, accumulate, ci0, n0, more, bias_grad=bias_grad, units=units)
         if then is not None:
             then()
         return None
@@ -681,7 +688,7 @@ def conv_wgrad_async(x, dy, k, stride, dW, accumulate=False, ci0=0, n0=0, more=(
     with torch.cuda.stream(st["stream"]):
         _cur_side = st
         try:
-            conv_wgrad(x, dy, k, stride, dW, accumulate, ci0, n0, more, bias_grad=bias_grad)
+            conv_wgrad(x, dy, k, stride, dW, accumulate, ci0, n0, more, bias_grad=bias_grad, units=units)
             if then is not None:
                 then()
         finally:
@@ -703,7 +710,7 @@ _ones_pages = {}
 USE_WGRAD_PW_BIAS = not bool(_os.environ.get("RTP_NO_WGRAD_PW_BIAS"))  # A/B switch
 
 
-def conv_wgrad(x, dy, k, stride, dW, accumulate=False, ci0=0, n0=0, more=(), taps=None, bias_grad=None):
+def conv_wgrad(x, dy, k, stride, dW, accumulate=False, ci0=0, n0=0, more=(), taps=None, bias_grad=None, units=None):
     """dW[:, ci0:ci0+x.C] (=|+=) wgrad(x, dy[:, n0:n0+dW.shape[0]]).  x: forward input (P8), dy: P8 gradient.
     `more`: further (dW, accumulate, ci0, n0) outputs reduced from the same split-K workspace.
     `taps`: explicit (tz, tx, ty) list instead of the k^3 stencil (the DCN sample volume keeps its taps on the z axis).
@@ -719,7 +726,8 @@ def conv_wgrad(x, dy, k, stride, dW, accumulate=False, ci0=0, n0=0, more=(), tap
     if (taps is None and USE_WGRAD_K3S1 and k == 3 and stride == 1 and x.C % 32 == 0 and x.c_stride == x.Z * (x.X + 2) * (x.Y + 2) * 8
             and dy.c_stride == x.c_stride and all(o[3] % 8 == 0 for o in outs)
             and lib.load().rtp_wgrad_k3s1_supported(32, 32, x.Z, x.X, x.Y)):
-        return _wgrad_k3s1(x, dy, outs)
+        return _wgrad_k3s1(x, dy, outs, units)
+    assert units is None, "a unit list needs the plane-streaming weight-gradient kernel"
     ci_n = x.C
     if (taps is None and USE_WGRAD_PW and k == 1 and stride == 1 and not more and n0 == 0 and dy.C <= 128 and dy.C8 <= 16
             and x.grid == dy.grid and _dense_planes(x) and _dense_planes(dy) and dW.shape[0] <= dy.C8 * 8
@@ -1064,6 +1072,19 @@ def grad_add(src, dst, mask=None, accumulate=False):
 
 
 USE_SPARSE_REG = not bool(_os.environ.get("RTP_NO_SPARSE_REG"))  # A/B switch: rtp_reg_head_bwd_sparse
+USE_SPARSE_UNITS = not bool(_os.environ.get("RTP_NO_SPARSE_UNITS"))  # A/B switch: unit lists for the regression half of the head
+
+
+def active_units(ind, like, radius, tag):
+    """(unit list int32 [N * ntile], count int32 [1]) of the (sample, 128-position tile) units of `like`'s grid that contain a
+    voxel within `radius` (x, y) of a target voxel ind[n][m] — the units conv_k3s1 / wgrad_k3s1 have to visit when their input
+    is zero everywhere else (rtp_active_units).  The buffers belong to (tag, stream) and are reused every step."""
+    N, M = ind.shape
+    ntile = (like.X * (like.Y + 2) + 127) // 128
+    buf = workspace(4 * (N * ntile + 4), like.buf.device, "units_" + tag).view(torch.int32)
+    lst, cnt = buf[:N * ntile], buf[N * ntile:N * ntile + 1]
+    lib.call("rtp_active_units", ind.data_ptr(), N, M, like.Z, like.X, like.Y, radius, lst.data_ptr(), cnt.data_ptr(), _stream())
+    return lst, cnt
 
 
 def reg_head_bwd_sparse(d_reg, t_in, ind, w, dt, dW, acc_w, db, acc_b):

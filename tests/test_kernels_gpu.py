@@ -386,6 +386,66 @@ def test_sparse_regression_head_backward_matches_dense(ctx):
     close(db_s, 2 * br.grad, tol=1e-4, what="sparse bias accumulate")
 
 
+def test_unit_lists_for_sparse_operands(ctx):
+    """rtp_active_units + the unit-list variants of conv_k3s1 (dgrad, accumulate) and wgrad_k3s1: with a gradient that is
+    non-zero only within one voxel of a few target voxels, visiting only the listed (sample, tile) units gives the dense
+    result — the dgrad needs the tiles within 2 voxels (x, y) of a target, the weight gradient those within 1."""
+    from rtpose_b200 import lib, ops
+    from rtpose_b200.p8 import P8
+    N, C, Cx, grid, M = 4, 32, 128, (6, 64, 160), 5
+    Z, Y, X = grid
+    g = torch.Generator().manual_seed(13)
+    zz = torch.randint(0, Z, (N, M), generator=g); yy = torch.randint(0, Y, (N, M), generator=g); xx = torch.randint(0, X, (N, M), generator=g)
+    zz[0, 0], yy[0, 0], xx[0, 0] = 0, 0, 0
+    zz[1, 0], yy[1, 0], xx[1, 0] = Z - 1, Y - 1, X - 1
+    ind = (zz * Y * X + yy * X + xx).to(torch.int64).cuda()
+    dy = torch.zeros(N, C, *grid)
+    for n in range(N):
+        for j in range(M):
+            z0, z1 = max(0, int(zz[n, j]) - 1), min(Z, int(zz[n, j]) + 2)
+            y0, y1 = max(0, int(yy[n, j]) - 1), min(Y, int(yy[n, j]) + 2)
+            x0, x1 = max(0, int(xx[n, j]) - 1), min(X, int(xx[n, j]) + 2)
+            dy[n, :, z0:z1, y0:y1, x0:x1] = bf(torch.randn(C, z1 - z0, y1 - y0, x1 - x0, generator=g))
+    dyp = to_p8(dy)
+    xin = to_p8(rnd(N, Cx, *grid, seed=14))
+    w = bf(torch.randn(C, Cx, 3, 3, 3, generator=g) * 0.05).cuda()   # conv Cx -> C; dgrad: dy (C) -> dx (Cx)
+    like = P8(N, Cx, *grid)
+    u1 = ops.active_units(ind, like, 1, "t1")
+    u2 = ops.active_units(ind, like, 2, "t2")
+    torch.cuda.synchronize()
+    ntile = (X * (Y + 2) + 127) // 128
+    n1, n2 = int(u1[1][0]), int(u2[1][0])
+    assert 0 < n1 <= n2 < N * ntile // 2, (n1, n2, N * ntile)
+    l2 = u2[0][:n2].cpu()
+    assert bool((l2[1:] > l2[:-1]).all())
+    # every voxel within 2 of a target lies in a listed unit
+    Yp = Y + 2
+    listed = set(l2.tolist())
+    for n in range(N):
+        for j in range(M):
+            for dxv in range(-2, 3):
+                for dyv in range(-2, 3):
+                    x, y = int(xx[n, j]) + dxv, int(yy[n, j]) + dyv
+                    if 0 <= x < X and 0 <= y < Y:
+                        assert n * ntile + ((x + 1) * Yp + (y + 1) - Yp) // 128 in listed
+    dense = P8(N, Cx, *grid)
+    ops.conv_dgrad(ctx, dyp, w, 1, dense)
+    base = rnd(N, Cx, *grid, seed=15)
+    viau = to_p8(base)
+    ops.conv_dgrad(ctx, dyp, w, 1, viau, accumulate=True, units=u2)
+    torch.cuda.synchronize()
+    close(viau.to_ncdhw(), bf(base).cuda() + dense.to_ncdhw(), tol=2 * BF16_ULP, what="dgrad over the listed units (accumulate)")
+    far = (dense.to_ncdhw() == 0)
+    assert torch.equal(viau.to_ncdhw()[far], bf(base).cuda()[far])  # untouched where the dense result is exactly zero
+    dW_d, dW_u = torch.zeros(C, Cx, 3, 3, 3, device="cuda"), torch.zeros(C, Cx, 3, 3, 3, device="cuda")
+    ops.conv_wgrad(xin, dyp, 3, 1, dW_d)
+    lib.call_counts.clear()
+    ops.conv_wgrad(xin, dyp, 3, 1, dW_u, units=u1)
+    torch.cuda.synchronize()
+    assert lib.call_counts.get("rtp_wgrad_k3s1_units", 0) == Cx // 32
+    close(dW_u, dW_d, tol=1e-5, what="weight gradient over the listed units")
+
+
 def test_grad_add_channel_sum_stem():
     from rtpose_b200 import lib, ops
     from rtpose_b200.p8 import P8, _stream
