@@ -371,7 +371,9 @@ def run_ours(args, rank, world, local_rank):
         lib.call("rtp_ingest_pack", raw.data_ptr(), B, D, RAW_SHAPE[0], RAW_SHAPE[1], RAW_SHAPE[2], ROI0[0], ROI0[1], ROI0[2],
                  float(a), float(b - a), 1 if norm is not None else 0, xin.struct(), None, _stream())
         tgt = targets.assign_device(poses, GRID, one_hm=(ncls == 1), min_radius=2 if ncls == 1 else 1)
-        hm, rg = eng.forward(xin, True)
+        # the loss gathers the regression output at the target voxels only: the engine evaluates (and back-propagates) the
+        # regression branch of the head around them (Engine.forward, reg_targets)
+        hm, rg = eng.forward(xin, True, reg_targets=tgt["ind"])
         out = eng.loss(hm, rg, tgt["hm"], tgt["ind"], tgt["mask"], tgt["cat"], tgt["anno_pose"],
                        grad_scale=(1.0 / world) if sar is not None else 1.0)
         eng.backward(grads)

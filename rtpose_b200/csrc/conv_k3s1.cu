@@ -113,7 +113,15 @@ __global__ void __launch_bounds__(LANES == 2 ? RTP_K3S1_DUAL_BOUND : kThreads, 1
   const uint32_t tmem = tmem_base_s + (uint32_t)L * 256u;  // lane L accumulates in its own 256 columns
 
   // returns false when this lane has nothing to do in unit u (LANES = 2, split last round: one lane per CTA)
-  const int nloop = p.unit_list ? __ldg(p.unit_count) : p.nunits;
+  // with a unit list, entry b = n * ntile + tile stands for all z-chunks of that (sample, tile)
+  const int zmul = (LANES == 1 && p.unit_list) ? p.nzc : 1;
+  const int nloop = p.unit_list ? __ldg(p.unit_count) * zmul : p.nunits;
+  auto unit_of = [&](int ku) {
+    if (!p.unit_list) return ku;
+    if (zmul == 1) return p.unit_list[ku];
+    const int b = p.unit_list[ku / zmul], zc = ku - (ku / zmul) * zmul;
+    return ((b / p.ntile) * p.nzc + zc) * p.ntile + b % p.ntile;
+  };
   auto decode = [&](int u, int& n, int& zo0, int& zo1, int& tile) -> bool {
     if constexpr (LANES == 2) {  // a unit is (sample, tile); the z-chunk is the lane
       int uu = u;
@@ -152,7 +160,7 @@ __global__ void __launch_bounds__(LANES == 2 ? RTP_K3S1_DUAL_BOUND : kThreads, 1
       uint32_t it = 0, wit = 0;
       bool w_loaded = false;
       for (int ku = blockIdx.x; ku < nloop; ku += gridDim.x) {
-        const int u = p.unit_list ? p.unit_list[ku] : ku;
+        const int u = unit_of(ku);
         int n, zo0, zo1, tile;
         if (!decode(u, n, zo0, zo1, tile)) continue;
         const int iz0 = max(0, zo0 - 1), iz1 = min(Z, zo1 + 1);
@@ -209,7 +217,7 @@ __global__ void __launch_bounds__(LANES == 2 ? RTP_K3S1_DUAL_BOUND : kThreads, 1
       const uint32_t stage0 = smem_u32(stages), wbase0 = smem_u32(wbuf);
       auto mk_desc = [](uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; };
       for (int ku = blockIdx.x; ku < nloop; ku += gridDim.x) {
-        const int u = p.unit_list ? p.unit_list[ku] : ku;
+        const int u = unit_of(ku);
         int n, zo0, zo1, tile;
         if (!decode(u, n, zo0, zo1, tile)) continue;
         const int iz0 = max(0, zo0 - 1), iz1 = min(Z, zo1 + 1);
@@ -322,7 +330,7 @@ __global__ void __launch_bounds__(LANES == 2 ? RTP_K3S1_DUAL_BOUND : kThreads, 1
       pre_ring = reinterpret_cast<uint4*>(smem + p.pre_off) + (size_t)(L * 128 + r) * 8;  // [2 buffers][4 chunks]
     }
     for (int ku = blockIdx.x; ku < nloop; ku += gridDim.x) {
-        const int u = p.unit_list ? p.unit_list[ku] : ku;
+        const int u = unit_of(ku);
       int n, zo0, zo1, tile;
       if (!decode(u, n, zo0, zo1, tile)) continue;
       const int q = Yp + tile * 128 + r;            // in-plane linear position (padded coordinates)
@@ -655,9 +663,7 @@ extern "C" int rtp_conv_k3s1(const rtp_conv_k3s1_desc* d, void* stream) {
   k.split_zh = 0;
   k.unit_list = d->unit_list;
   k.unit_count = d->unit_count;
-  if (d->unit_list) {
-    RTP_CHECK_ARG(d->unit_count && (pl.lanes == 2 || pl.nzc == 1), "rtp_conv_k3s1: a unit list needs one z-chunk per unit");
-  }
+  if (d->unit_list) RTP_CHECK_ARG(d->unit_count != nullptr, "rtp_conv_k3s1: unit_list without unit_count");
   static const bool no_split = getenv("RTP_NO_TAIL_SPLIT") != nullptr;  // A/B switch
   if (!no_split && !d->unit_list && ((pl.lanes == 1 && pl.nzc == 1 && d->in.Z >= 4 && d->in.Z % 2 == 0) || pl.lanes == 2)) {
     // lanes == 2: the two z-chunk lanes of a last-round unit go to two CTAs (a lone lane has the tensor pipe to itself)

@@ -234,9 +234,11 @@ class _StepJob(_ParamJob):
         if self.graph_state is not None:
             return self._run_graphed()
         e = self.engine
-        hm, reg = e.forward(_as_p8(self.x), self.train)
+        tgt = self._targets()
+        # training: the loss reads the regression map at tgt[1] (ind) only (Engine.forward, reg_targets)
+        hm, reg = e.forward(_as_p8(self.x), self.train, reg_targets=tgt[1] if self.train else None)
         self.gen = e.generation
-        return e.loss(hm, reg, *self._targets(), with_grad=self.train)
+        return e.loss(hm, reg, *tgt, with_grad=self.train)
 
     def _run_graphed(self):
         from .graph import StepGraph
@@ -249,7 +251,7 @@ class _StepJob(_ParamJob):
 
             def body():
                 e.packs.refresh_async()  # the optimizer rewrites the weights between replays: repack inside the graph
-                hm, reg = e.forward(_as_p8(st["x"]), True)
+                hm, reg = e.forward(_as_p8(st["x"]), True, reg_targets=st["tgt"][1])
                 out = e.loss(hm, reg, *st["tgt"], with_grad=True)
                 st["touched"] = e.backward(st["views"])
                 return out

@@ -540,7 +540,7 @@ class Engine:
             self.tape.append(bwd)
         return f
 
-    def head(self, f, train):
+    def head(self, f, train, reg_targets=None):
         """CenterHead.forward + SepHead.forward (pose_heads/center_head.py:232-238, :66-109); reg.0 and hm.0 read the
         same input and are merged into one N=64 GEMM."""
         p, ph = self.p, self.ph
@@ -553,12 +553,27 @@ class Engine:
         wkey = ("merged_head", p[q + "reg.0.weight"].data_ptr(), p[q + "hm.0.weight"].data_ptr())
         wver = (p[q + "reg.0.weight"]._version, p[q + "hm.0.weight"]._version)
         t = self.new(f, C=2 * hc)
-        ops.conv_forward(self.packs, f, w0, 1, t, bias=b0, relu=True, key=wkey, version=wver)
-        t.relu_out = True
         t_reg, t_hm = t.channels(0, hc), t.channels(hc, hc)
         reg = self.new(f, C=self.R)
         hm = self.new(f, C=self.ncls)
-        ops.conv_forward(self.packs, t_reg, p[q + "reg.2.weight"], 1, reg, bias=p[q + "reg.2.bias"])
+        # Training with known targets: the loss reads `reg` at the target voxels only, so the regression branch (reg.0 half of
+        # the merged conv, reg.2) is evaluated on the units around them: within 1 voxel for the hidden layer (the 3x3x3 input
+        # neighbourhood of a target), the target's own tile for reg.2.  The backward pass then MUST take the sparse paths.
+        sparse_fwd = (train and reg_targets is not None and ops.USE_SPARSE_FWD and ops.USE_SPARSE_UNITS and hc == 32
+                      and f.C % 32 == 0 and f.C > 80 and ops.reg_sparse_supported(p[q + "reg.2.weight"], reg_targets)
+                      and ops.k3s1_eligible(f, f.C, 32) and ops.k3s1_eligible(t_reg, 32, 32)
+                      and ops.k3s1_eligible(t_reg, 32, (self.R + 15) // 16 * 16))
+        if sparse_fwd:
+            u0 = ops.active_units(reg_targets, f, 0, "f0")
+            u1 = ops.active_units(reg_targets, f, 1, "f1")
+            ops.conv_forward(self.packs, f, p[q + "hm.0.weight"], 1, t_hm, bias=p[q + "hm.0.bias"], relu=True)
+            ops.conv_forward(self.packs, f, p[q + "reg.0.weight"], 1, t_reg, bias=p[q + "reg.0.bias"], relu=True, units=u1)
+            ops.conv_forward(self.packs, t_reg, p[q + "reg.2.weight"], 1, reg, bias=p[q + "reg.2.bias"], units=u0)
+        else:
+            ops.conv_forward(self.packs, f, w0, 1, t, bias=b0, relu=True, key=wkey, version=wver)
+            ops.conv_forward(self.packs, t_reg, p[q + "reg.2.weight"], 1, reg, bias=p[q + "reg.2.bias"])
+        t.relu_out = True
+        t_reg.relu_out = t_hm.relu_out = True
         ops.conv_forward(self.packs, t_hm, p[q + "hm.2.weight"], 1, hm, bias=p[q + "hm.2.bias"])
         if train:
             def bwd():
@@ -568,6 +583,9 @@ class Engine:
                 sp = self._reg_sparse
                 self._reg_sparse = None
                 reg_sparse = False
+                if sparse_fwd and not (sp is not None and sp[0] is reg.grad and sp[1] is reg_targets):
+                    raise lib.RtpError("forward(reg_targets=...) evaluated the regression branch around those targets only: "
+                                       "loss() must be called with the same `ind` tensor before backward()")
                 for name, tv, o, c0 in (("reg", t_reg, reg, 0), ("hm", t_hm, hm, hc)):
                     if (name == "reg" and sp is not None and sp[0] is reg.grad and ops.reg_sparse_supported(p[q + "reg.2.weight"], sp[1])):
                         reg_sparse = True
@@ -593,6 +611,7 @@ class Engine:
                 # only the (sample, tile) units around the targets (within 1 / 2 voxels in the plane).
                 split = (reg_sparse and ops.USE_SPARSE_UNITS and hc == 32 and f.C % 32 == 0 and f.C > 80
                          and ops.k3s1_eligible(tg.channels(0, hc), 32, 32))
+                assert split or not sparse_fwd
                 if split:
                     u1 = ops.active_units(sp[1], f, 1, "r1")
                     u2 = ops.active_units(sp[1], f, 2, "r2")
@@ -622,15 +641,19 @@ class Engine:
         self.stats_cache = {}
         self._touched = set()
 
-    def forward(self, x, train):
-        """x: P8 input cube [N, in_ch, Z, Y, X].  Returns (hm, reg) raw head outputs as P8 tensors."""
+    def forward(self, x, train, reg_targets=None):
+        """x: P8 input cube [N, in_ch, Z, Y, X].  Returns (hm, reg) raw head outputs as P8 tensors.
+        reg_targets (training only): the int64 [N][M] target voxel indices the loss will gather the regression output at
+        (CenterHead.loss, center_head.py:244-270).  When given, the regression branch of the head is evaluated only on the
+        (sample, tile) units that contain those voxels — `reg` is then DEFINED ONLY THERE — and loss() / backward() must be
+        called with the same indices (they take the matching sparse backward path)."""
         if x.buf.device.index != torch.cuda.current_device():
             # every launch goes to the CURRENT device's current stream (p8._stream): one process per GPU, or select the
             # device with torch.cuda.device(...) around the call
             raise lib.RtpError("input lives on %s but the current CUDA device is %d" % (x.buf.device, torch.cuda.current_device()))
         self.begin()
         f = self.backbone(x, train)
-        return self.head(f, train)
+        return self.head(f, train, reg_targets)
 
     def loss(self, hm, reg, tgt_hm, ind, mask, cat, anno, with_grad=True, grad_scale=1.0):
         """CenterHead.loss (center_head.py:244-270).  Returns a device fp32 tensor

@@ -469,14 +469,15 @@ def stat_fusable(x, w, transpose_flip):
 
 
 def conv_forward(packs, x, w, stride, out, bias=None, relu=False, res=None, ci0=0, ci_n=None, key=None, version=None,
-                 stat=None, tap_mask=None):
+                 stat=None, tap_mask=None, units=None):
     """y = conv3d(x[:, ci0:ci0+ci_n], w[:, ci0:ci0+ci_n], stride, padding=k//2) (+bias)(+res)(relu).
     stat (only when stat_fusable(x, w, False) and stride 1): see conv_k3s1; the return value becomes (y, stats)."""
     k = w.shape[2]
     if k == 3 and stride == 1 and ci0 == 0 and ci_n is None and k3s1_eligible(x, ceil_to(w.shape[1], 16), ceil_to(w.shape[0], 16)):
         return conv_k3s1(packs, x, w, out, False, bias=bias, relu=relu, res=res, key=key, version=version, stat=stat,
-                         tap_mask=tap_mask)
+                         tap_mask=tap_mask, units=units)
     assert stat is None, "fused statistics need the plane-streaming kernel (check stat_fusable first)"
+    assert units is None, "a unit list needs the plane-streaming kernel"
     if k == 1 and stride == 1 and res is None and USE_PW:
         wp, KP, NP = packs.get(w, 0, ci0, ci_n, key, version)
         if pw_eligible(x, out, KP, NP):
@@ -1073,6 +1074,7 @@ def grad_add(src, dst, mask=None, accumulate=False):
 
 USE_SPARSE_REG = not bool(_os.environ.get("RTP_NO_SPARSE_REG"))  # A/B switch: rtp_reg_head_bwd_sparse
 USE_SPARSE_UNITS = not bool(_os.environ.get("RTP_NO_SPARSE_UNITS"))  # A/B switch: unit lists for the regression half of the head
+USE_SPARSE_FWD = not bool(_os.environ.get("RTP_NO_SPARSE_FWD"))  # A/B switch: training forward of the regression branch on the listed units only
 
 
 def active_units(ind, like, radius, tag):

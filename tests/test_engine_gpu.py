@@ -198,6 +198,55 @@ def test_stream_schedules_are_bitwise_equivalent():
             assert torch.equal(out["grads"][k], ref["grads"][k]), k
 
 
+@pytest.mark.parametrize("grid,batch", [((8, 16, 24), 2), ((16, 64, 160), 2)], ids=["small", "full_grid"])
+def test_regression_branch_evaluated_around_the_targets_only(grid, batch):
+    """Engine.forward(reg_targets=ind): in training the loss gathers the regression map at the target voxels only, so the
+    regression branch of the head runs on the (sample, tile) units around them (forward AND backward).  Loss and every
+    parameter gradient must agree with the dense evaluation; the regression map must agree at the target voxels; switching
+    the sparse paths off (RTP_NO_SPARSE_* at import time) is the dense evaluation used as the reference here."""
+    from rtpose_b200 import ops
+    from rtpose_b200.p8 import P8
+    cfg = "hr3d_one_hm_doppler"
+    x, poses, tgt = G.make_example(cfg, batch, grid, seed=21)
+    eng, params = build_engine(cfg)
+
+    def run(sparse):
+        xp = P8.from_ncdhw(torch.from_numpy(x).cuda())
+        ind = tgt["ind"].cuda()
+        old = (ops.USE_SPARSE_REG, ops.USE_SPARSE_UNITS, ops.USE_SPARSE_FWD)
+        if not sparse:
+            ops.USE_SPARSE_REG = ops.USE_SPARSE_UNITS = ops.USE_SPARSE_FWD = False
+        try:
+            hm, reg = eng.forward(xp, True, reg_targets=ind if sparse else None)
+            loss = eng.loss(hm, reg, tgt["hm"].cuda(), ind, tgt["mask"].cuda(), tgt["cat"].cuda(), tgt["anno_pose"].cuda())
+            grads = {k: torch.zeros_like(v) for k, v in params.items()}
+            touched = eng.backward(grads)
+        finally:
+            ops.USE_SPARSE_REG, ops.USE_SPARSE_UNITS, ops.USE_SPARSE_FWD = old
+        torch.cuda.synchronize()
+        return hm.to_ncdhw().cpu(), reg.to_ncdhw().cpu(), loss.cpu(), {k: grads[k].cpu() for k in touched}
+
+    hm_d, reg_d, loss_d, g_d = run(False)
+    hm_s, reg_s, loss_s, g_s = run(True)
+    # (the heat-map half of the merged head conv is its own launch in the sparse evaluation: same operands, another
+    # accumulation grouping — equal to fp32 round-off before the bf16 store)
+    assert float((hm_s - hm_d).abs().max()) <= 2.0 ** -7 * float(hm_d.abs().max())
+    assert float((hm_s != hm_d).float().mean()) < 0.02
+    Z, Y, X = grid
+    ind = tgt["ind"]
+    for n in range(batch):
+        for j in range(ind.shape[1]):
+            i = int(ind[n, j])
+            z, y, xx = i // (Y * X), (i % (Y * X)) // X, i % X
+            assert float((reg_s[n, :, z, y, xx] - reg_d[n, :, z, y, xx]).abs().max()) <= 2.0 ** -7 * float(reg_d.abs().max()), (n, j)
+    assert torch.allclose(loss_s, loss_d, rtol=2e-3, atol=1e-5), (loss_s, loss_d)
+    assert set(g_s) == set(g_d)
+    for k in g_d:
+        den = float(g_d[k].norm()) + 1e-12
+        rel = float((g_s[k] - g_d[k]).norm()) / den
+        assert rel <= 2e-2, (k, rel)   # bf16 round-off of the re-grouped head convs propagates through the whole backward pass
+
+
 def test_gradient_ready_notifications_follow_the_tape():
     """Engine.set_grad_groups: after the first (learning) backward pass every group is reported exactly once per pass, in
     backward order (tail of the flat buffer first), and only after its last gradient has been issued — the hook the
