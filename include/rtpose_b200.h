@@ -347,6 +347,13 @@ int64_t rtp_reg_head_bwd_sparse_workspace_bytes(int32_t N, int32_t M);
 int rtp_reg_head_bwd_sparse(rtp_p8 d_reg, rtp_p8 t_in, const int64_t* ind, int32_t M, const float* w, int32_t R, int32_t Cin,
                             rtp_p8 dt, float* dW, int32_t accumulate_w, float* db, int32_t accumulate_b, void* workspace,
                             void* stream);
+/* The same for a dt whose first ceil(Cin / 8) chunks are ALREADY zero (rtp_zero_chunks issued earlier, e.g. on a side stream
+ * beside the head's convolutions): skips the zero-fill, which otherwise sits at the serial start of the backward pass. */
+int rtp_reg_head_bwd_sparse_prezeroed(rtp_p8 d_reg, rtp_p8 t_in, const int64_t* ind, int32_t M, const float* w, int32_t R, int32_t Cin,
+                            rtp_p8 dt, float* dW, int32_t accumulate_w, float* db, int32_t accumulate_b, void* workspace,
+                            void* stream);
+/* Zero-fills all t.C8 chunk volumes of every sample of a P8 tensor / channel view (pad ring included; chunk volumes must be dense). */
+int rtp_zero_chunks(rtp_p8 t, void* stream);
 
 /* ---- branch exchange ---------------------------------------------------------------------------------------
  * replaces: the fuse sum of HighResolutionModule.forward (hr_util/hr3d.py:213-227) and the upsample+cat of
@@ -410,6 +417,15 @@ int rtp_head_loss(rtp_p8 hm, rtp_p8 reg, int32_t ncls, int32_t R, const float* t
                   const uint8_t* mask, const int64_t* cat, const float* anno, int32_t M, float weight,
                   const float* code_weights, float grad_scale, float* out, rtp_p8 d_hm, rtp_p8 d_reg,
                   void* workspace, void* stream);
+/* The same with options.  Chunks of d_hm behind the ceil(ncls / 8) class chunks (d_hm.C8 larger than that: a K-padding chunk for
+ * the tensor-core dgrad that follows) are zero-filled in the same pass.  flags & RTP_LOSS_SPARSE_DREG: d_reg is written (cleared,
+ * then accumulated) at the N * M target voxels ind[n][m] only and left untouched everywhere else — for a consumer that reads it
+ * there only (rtp_reg_head_bwd_sparse); saves the dense zero-fill of the R-channel gradient. */
+#define RTP_LOSS_SPARSE_DREG 1
+int rtp_head_loss_flags(rtp_p8 hm, rtp_p8 reg, int32_t ncls, int32_t R, const float* tgt_hm, const int64_t* ind,
+                        const uint8_t* mask, const int64_t* cat, const float* anno, int32_t M, float weight,
+                        const float* code_weights, float grad_scale, float* out, rtp_p8 d_hm, rtp_p8 d_reg,
+                        int32_t flags, void* workspace, void* stream);
 
 /* ---- keypoint decode -------------------------------------------------------------------------------------------
  * replaces: CenterHead.predict + post_processing (center_head.py:272-360): per (sample, class) arg-max of

@@ -744,7 +744,7 @@ int rtp_k3s1_set_carveout(int pct) {  // see rtp_set_shared_carveout (layout.cu)
 }
 
 namespace {
-// one block: flags in shared memory, then an ordered compaction by thread 0 (a few thousand units at most)
+// one block of 1024 threads: flags in shared memory, then an ordered compaction (a few thousand units at most)
 __global__ void __launch_bounds__(1024) active_units_kernel(const int64_t* __restrict__ ind, int N, int M, int X, int Y, int radius,
                                                             int ntile, int* __restrict__ list, int* __restrict__ count) {
   extern __shared__ int au_flags[];
@@ -765,12 +765,37 @@ __global__ void __launch_bounds__(1024) active_units_kernel(const int64_t* __res
     au_flags[(j / M) * ntile + (q - Yp) / 128] = 1;  // benign race: every writer stores 1
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    int c = 0;
-    for (int i = 0; i < total; ++i)
-      if (au_flags[i]) list[c++] = i;
-    *count = c;
+  // ordered compaction: thread t owns the flags [t * per, (t + 1) * per); block-wide exclusive scan of the per-thread counts
+  // (one thread walking all flags took 17 us at the bench shape, four times per step on the critical path)
+  __shared__ int au_warp[32];
+  const int per = (total + (int)blockDim.x - 1) / (int)blockDim.x;
+  const int b0 = min(total, (int)threadIdx.x * per), b1 = min(total, b0 + per);
+  int c = 0;
+  for (int i = b0; i < b1; ++i) c += au_flags[i] != 0;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int incl = c;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
   }
+  if (lane == 31) au_warp[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    const int v = lane < (int)(blockDim.x >> 5) ? au_warp[lane] : 0;
+    int sc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int u = __shfl_up_sync(0xffffffffu, sc, o);
+      if (lane >= o) sc += u;
+    }
+    au_warp[lane] = sc - v;  // exclusive prefix of the warp totals
+    if (lane == 31) *count = sc;
+  }
+  __syncthreads();
+  int pos = au_warp[wid] + incl - c;
+  for (int i = b0; i < b1; ++i)
+    if (au_flags[i]) list[pos++] = i;
 }
 }  // namespace
 

@@ -35,13 +35,25 @@ __global__ void __launch_bounds__(256) adam_step_kernel(float* __restrict__ p, c
                                                         const float* __restrict__ hyper, const float* __restrict__ partial,
                                                         float* __restrict__ norm_out) {
   __shared__ float s_coef;
+  __shared__ double s_tot[256];
   if (hyper) {
     lr = hyper[0]; beta1 = hyper[1]; beta2 = hyper[2]; eps = hyper[3]; wd = hyper[4]; bias1 = hyper[5]; bias2_sqrt = hyper[6];
     max_norm = hyper[7];
   }
+  // every block reduces the kNormBlocks partial sums itself, in a fixed order (strided per thread, then a tree): deterministic,
+  // identical in all blocks (one thread adding them one by one put ~10 us in front of every block's update loop)
+  {
+    double t = 0;
+    for (int i = threadIdx.x; i < kNormBlocks; i += 256) t += partial[i];
+    s_tot[threadIdx.x] = t;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+      if ((int)threadIdx.x < s) s_tot[threadIdx.x] += s_tot[threadIdx.x + s];
+      __syncthreads();
+    }
+  }
   if (threadIdx.x == 0) {
-    double tot = 0;
-    for (int i = 0; i < kNormBlocks; ++i) tot += partial[i];  // fixed order: deterministic
+    const double tot = s_tot[0];
     const float norm = (float)sqrt(tot);
     float coef = max_norm > 0.f ? max_norm / (norm + 1e-6f) : 1.f;  // torch.nn.utils.clip_grad_norm_
     s_coef = coef < 1.f ? coef : 1.f;

@@ -65,7 +65,8 @@ class Engine:
         self._last_touch, self._closure_idx = {}, -1
         self._grad_groups, self._on_ready, self._milestones = None, None, None
         self._s2d_share, self._s2d_scratch, self._unit_affine = {}, {}, {}
-        self._reg_sparse = None  # (reg.grad, ind) of the last loss() call: lets head.bwd take the sparse path
+        self._reg_sparse = None  # (reg.grad, ind, sparse_only) of the last loss() call: lets head.bwd take the sparse path
+        self._reg_out = self._reg2_weight = None  # the training head's regression output and last conv weight (head -> loss)
         self.generation = 0  # bumped by begin(): a backward job checks that the tape it recorded is still the live one
 
     # ------------------------------------------------------------------ helpers
@@ -556,6 +557,7 @@ class Engine:
         t_reg, t_hm = t.channels(0, hc), t.channels(hc, hc)
         reg = self.new(f, C=self.R)
         hm = self.new(f, C=self.ncls)
+        self._reg_out, self._reg2_weight = (reg, p[q + "reg.2.weight"]) if train else (None, None)  # see loss()
         # Training with known targets: the loss reads `reg` at the target voxels only, so the regression branch (reg.0 half of
         # the merged conv, reg.2) is evaluated on the units around them: within 1 voxel for the hidden layer (the 3x3x3 input
         # neighbourhood of a target), the target's own tile for reg.2.  The backward pass then MUST take the sparse paths.
@@ -563,9 +565,16 @@ class Engine:
                       and f.C % 32 == 0 and f.C > 80 and ops.reg_sparse_supported(p[q + "reg.2.weight"], reg_targets)
                       and ops.k3s1_eligible(f, f.C, 32) and ops.k3s1_eligible(t_reg, 32, 32)
                       and ops.k3s1_eligible(t_reg, 32, (self.R + 15) // 16 * 16))
+        fwd_units = {}
+        tg_pre = tg_ready = None
+        if sparse_fwd and ops.USE_PREZERO:
+            # the hidden layer's gradient buffer is taken now, and its regression half (written around the targets only by the
+            # backward pass) is zero-filled on a side stream beside the head convolutions below
+            tg_pre = self.new(t)
+            tg_ready = ops.prezero(tg_pre.channels(0, hc))
         if sparse_fwd:
             u0 = ops.active_units(reg_targets, f, 0, "f0")
-            u1 = ops.active_units(reg_targets, f, 1, "f1")
+            u1 = fwd_units[1] = ops.active_units(reg_targets, f, 1, "f1")
             ops.conv_forward(self.packs, f, p[q + "hm.0.weight"], 1, t_hm, bias=p[q + "hm.0.bias"], relu=True)
             ops.conv_forward(self.packs, f, p[q + "reg.0.weight"], 1, t_reg, bias=p[q + "reg.0.bias"], relu=True, units=u1)
             ops.conv_forward(self.packs, t_reg, p[q + "reg.2.weight"], 1, reg, bias=p[q + "reg.2.bias"], units=u0)
@@ -579,7 +588,7 @@ class Engine:
             def bwd():
                 if hm.grad is None or reg.grad is None:
                     return
-                tg = self.new(t)
+                tg = tg_pre if tg_pre is not None else self.new(t)
                 sp = self._reg_sparse
                 self._reg_sparse = None
                 reg_sparse = False
@@ -593,7 +602,10 @@ class Engine:
                         # backward of reg.2 (dgrad, weight and bias gradients) is a few hundred voxel neighbourhoods
                         gw, acc = self._pgrad(q + "reg.2.weight")
                         gb, accb = self._pgrad(q + "reg.2.bias")
-                        ops.reg_head_bwd_sparse(reg.grad, tv, sp[1], p[q + "reg.2.weight"], tg.channels(c0, hc), gw, acc, gb, accb)
+                        if tg_ready is not None:
+                            torch.cuda.current_stream(f.buf.device).wait_event(tg_ready)
+                        ops.reg_head_bwd_sparse(reg.grad, tv, sp[1], p[q + "reg.2.weight"], tg.channels(c0, hc), gw, acc, gb, accb,
+                                                prezeroed=tg_pre is not None)
                         continue
                     gw, acc = self._pgrad(q + name + ".2.weight")
                     ops.conv_wgrad_async(tv, o.grad, 3, 1, gw, accumulate=acc)
@@ -604,6 +616,8 @@ class Engine:
                         dy = P8(dy.N, 16, dy.Z, dy.Y, dy.X, buf=dy.buf, offset=dy.offset, n_stride=dy.n_stride,
                                 c_stride=dy.c_stride)
                     ops.conv_dgrad(self.packs, dy, p[q + name + ".2.weight"], 1, tg.channels(c0, hc), mask=tv)
+                if sp is not None and sp[0] is reg.grad and sp[2] and not reg_sparse:
+                    raise lib.RtpError("loss() left the regression gradient undefined away from the targets, but the dense backward ran")
                 gw_r, acc_r = self._pgrad(q + "reg.0.weight")
                 gw_h, acc_h = self._pgrad(q + "hm.0.weight")
                 # With the sparse regression gradient, the regression half of tg is non-zero only within one voxel of a target:
@@ -613,7 +627,8 @@ class Engine:
                          and ops.k3s1_eligible(tg.channels(0, hc), 32, 32))
                 assert split or not sparse_fwd
                 if split:
-                    u1 = ops.active_units(sp[1], f, 1, "r1")
+                    # (the forward pass listed the radius-1 units of the same targets already: sp[1] is reg_targets, checked above)
+                    u1 = fwd_units[1] if sparse_fwd else ops.active_units(sp[1], f, 1, "r1")
                     u2 = ops.active_units(sp[1], f, 2, "r2")
                     ops.conv_wgrad_async(f, tg.channels(hc, hc), 3, 1, gw_h, accumulate=acc_h)
                     ops.conv_wgrad_async(f, tg.channels(0, hc), 3, 1, gw_r, accumulate=acc_r, units=u1)
@@ -636,6 +651,7 @@ class Engine:
     # ------------------------------------------------------------------ entry points
     def begin(self):
         self.generation += 1
+        ops.join_wgrad()  # side-stream work of a pass that was never back-propagated (e.g. the head's gradient pre-fill)
         self.pool.release_all()
         self.tape = []
         self.stats_cache = {}
@@ -663,24 +679,32 @@ class Engine:
             self._cw = torch.tensor(self.code_weights, dtype=torch.float32, device=dev)
         out = torch.empty(4 + self.R, dtype=torch.float32, device=dev)
         ws = ops.workspace(lib.load().rtp_head_loss_workspace_bytes(hm.N, self.ncls, hm.Z, hm.Y, hm.X), dev, "loss")
+        flags = 0
         if with_grad:
             if hm.C8 == 1:
                 # one spare, zeroed 8-channel chunk behind the heat-map gradient: the dgrad of hm.2 can then run on the
-                # plane-streaming kernel (K = 16) instead of the generic one (see head.bwd)
+                # plane-streaming kernel (K = 16) instead of the generic one (see head.bwd); the loss kernel zero-fills it
                 wide = self.new(hm, C=16)
-                wide.channels(8, 8).zero_()
                 hm.grad = wide.channels(0, hm.C)
+                dh = wide.struct()
             else:
                 hm.grad = self.new(hm)
+                dh = hm.grad.struct()
             reg.grad = self.new(reg)
-            self._reg_sparse = (reg.grad, ind)  # the regression gradient is non-zero at the target voxels only (head.bwd)
-            dh, dr = hm.grad.struct(), reg.grad.struct()
+            # The regression gradient is non-zero at the target voxels only.  When head.bwd is going to read it there only
+            # (rtp_reg_head_bwd_sparse), the loss kernel does not zero-fill the rest of it (third entry: head.bwd checks it).
+            w2 = self._reg2_weight
+            sparse_only = bool(ops.USE_SPARSE_DREG and w2 is not None and reg is self._reg_out and ops.reg_sparse_supported(w2, ind))
+            self._reg_sparse = (reg.grad, ind, sparse_only)
+            if sparse_only:
+                flags |= lib.RTP_LOSS_SPARSE_DREG
+            dr = reg.grad.struct()
         else:
             dh = dr = lib.NULL_P8
         M = ind.shape[1]
-        lib.call("rtp_head_loss", hm.struct(), reg.struct(), self.ncls, self.R, tgt_hm.data_ptr(), ind.data_ptr(),
+        lib.call("rtp_head_loss_flags", hm.struct(), reg.struct(), self.ncls, self.R, tgt_hm.data_ptr(), ind.data_ptr(),
                  mask.data_ptr(), cat.data_ptr(), anno.data_ptr(), M, self.loss_weight, self._cw.data_ptr(),
-                 float(grad_scale), out.data_ptr(), dh, dr, ws.data_ptr(), _stream())
+                 float(grad_scale), out.data_ptr(), dh, dr, flags, ws.data_ptr(), _stream())
         return out
 
     def backward(self, grads):

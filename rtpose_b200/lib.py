@@ -18,6 +18,7 @@ class P8Struct(C.Structure):
 
 
 NULL_P8 = P8Struct(None, 0, 0, 0, 0, 0, 0, 0)
+RTP_LOSS_SPARSE_DREG = 1  # include/rtpose_b200.h
 
 
 class ConvDesc(C.Structure):
@@ -122,6 +123,9 @@ PROTOTYPES = {
     "rtp_wgrad_pw_reduce": (C.c_int, [_vp, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _vp]),
     "rtp_reg_head_bwd_sparse_workspace_bytes": (C.c_int64, [_i32, _i32]),
     "rtp_reg_head_bwd_sparse": (C.c_int, [P8Struct, P8Struct, _vp, _i32, _vp, _i32, _i32, P8Struct, _vp, _i32, _vp, _i32, _vp, _vp]),
+    "rtp_reg_head_bwd_sparse_prezeroed": (C.c_int, [P8Struct, P8Struct, _vp, _i32, _vp, _i32, _i32, P8Struct, _vp, _i32, _vp, _i32, _vp,
+                                                    _vp]),
+    "rtp_zero_chunks": (C.c_int, [P8Struct, _vp]),
     "rtp_wgrad_pw_bias_workspace_bytes": (C.c_int64, [_i32, _i32]),
     "rtp_wgrad_pw_bias": (C.c_int, [P8Struct, P8Struct, _i32, _vp, _vp, _vp, C.POINTER(C.c_int32), _vp]),
     "rtp_wgrad_pw_bias_reduce": (C.c_int, [_vp, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),
@@ -147,6 +151,8 @@ PROTOTYPES = {
     "rtp_head_loss_workspace_bytes": (C.c_int64, [_i32, _i32, _i32, _i32, _i32]),
     "rtp_head_loss": (C.c_int, [P8Struct, P8Struct, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _f32, _vp, _f32, _vp,
                                 P8Struct, P8Struct, _vp, _vp]),
+    "rtp_head_loss_flags": (C.c_int, [P8Struct, P8Struct, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _f32, _vp, _f32, _vp,
+                                      P8Struct, P8Struct, _i32, _vp, _vp]),
     "rtp_decode": (C.c_int, [P8Struct, P8Struct, _i32, _i32, C.POINTER(_f32), C.POINTER(_f32), _vp, _vp, _vp, _vp]),
     "rtp_dcn_fwd": (C.c_int, [_vp, _vp, _vp, _vp] + [_i32] * 11 + [_vp]),
     "rtp_dcn_bwd_input": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp] + [_i32] * 11 + [_vp]),
@@ -230,13 +236,13 @@ LAUNCHES = {"rtp_pack_ncdhw": 1, "rtp_unpack_ncdhw": 1, "rtp_ingest_pack": 1, "r
             "rtp_weight_pack_k3s1": 1, "rtp_weight_pack_k3s1_window": 1, "rtp_weight_pack_batch": 1, "rtp_conv": 1, "rtp_conv_k3s1": 1, "rtp_wgrad": 1, "rtp_wgrad_reduce": 1,
             "rtp_gn_sums": 2, "rtp_gn_finalize": 1, "rtp_gn_apply": 1, "rtp_gn_bwd_reduce": 2, "rtp_gn_bwd_apply": 1,
             "rtp_fuse_sum": 1, "rtp_upsample_bwd": 2, "rtp_grad_add": 1, "rtp_channel_sum": 2, "rtp_stem_fwd": 1,
-            "rtp_stem_bwd": 2, "rtp_head_loss": 2, "rtp_decode": 1, "rtp_scale_f32": 1, "rtp_dcn_fwd": 1,
+            "rtp_stem_bwd": 2, "rtp_head_loss": 2, "rtp_head_loss_flags": 2, "rtp_decode": 1, "rtp_scale_f32": 1, "rtp_dcn_fwd": 1,
             "rtp_dcn_bwd_input": 1, "rtp_dcn_bwd_weight": 1, "rtp_mdcn_fwd": 1, "rtp_mdcn_bwd_input": 1, "rtp_mdcn_bwd_weight": 2, "rtp_adam_step": 2, "rtp_adam_step_dev": 2,
             "rtp_assign_targets": 2, "rtp_wgrad_k3s1": 1, "rtp_wgrad_k3s1_reduce": 1, "rtp_conv_pw": 1, "rtp_gn_apply_s2d": 1, "rtp_gn_bwd_reduce_s2d": 2,
             "rtp_gn_bwd_apply_s2d": 1, "rtp_conv_k3s1_stat_finalize": 1, "rtp_conv_multi": 1, "rtp_gn_stats": 2,
             "rtp_wgrad_s2d": 1, "rtp_wgrad_s2d_reduce": 1, "rtp_s2d_fold_weights": 2, "rtp_s2d_border_bias": 1, "rtp_s2d_fold_wgrad": 3, "rtp_wgrad_pw": 1, "rtp_wgrad_pw_reduce": 1, "rtp_wgrad_pw_bias": 1, "rtp_wgrad_pw_bias_reduce": 1, "rtp_wgrad_pw_bias_workspace_bytes": 0,
             "rtp_conat_fwd": 1, "rtp_conat_supported": 0, "rtp_s2d_box_sums_workspace_bytes": 0,
-            "rtp_npy_probe": 0, "rtp_npy_read_roi_slab": 0, "rtp_set_shared_carveout": 0, "rtp_reg_head_bwd_sparse": 3, "rtp_active_units": 1, "rtp_wgrad_k3s1_units": 1,
+            "rtp_npy_probe": 0, "rtp_npy_read_roi_slab": 0, "rtp_set_shared_carveout": 0, "rtp_reg_head_bwd_sparse": 3, "rtp_reg_head_bwd_sparse_prezeroed": 2, "rtp_zero_chunks": 1, "rtp_active_units": 1, "rtp_wgrad_k3s1_units": 1,
             "rtp_reg_head_bwd_sparse_workspace_bytes": 0}  # host-only file readers
 launch_count = 0
 call_counts = {}  # C-ABI entry point -> number of calls (tests assert which kernel path a shape really took)

@@ -1074,6 +1074,7 @@ def grad_add(src, dst, mask=None, accumulate=False):
 
 USE_SPARSE_REG = not bool(_os.environ.get("RTP_NO_SPARSE_REG"))  # A/B switch: rtp_reg_head_bwd_sparse
 USE_SPARSE_UNITS = not bool(_os.environ.get("RTP_NO_SPARSE_UNITS"))  # A/B switch: unit lists for the regression half of the head
+USE_SPARSE_DREG = not bool(_os.environ.get("RTP_NO_SPARSE_DREG"))  # A/B switch: the loss writes d_reg at the target voxels only
 USE_SPARSE_FWD = not bool(_os.environ.get("RTP_NO_SPARSE_FWD"))  # A/B switch: training forward of the regression branch on the listed units only
 
 
@@ -1089,15 +1090,39 @@ def active_units(ind, like, radius, tag):
     return lst, cnt
 
 
-def reg_head_bwd_sparse(d_reg, t_in, ind, w, dt, dW, acc_w, db, acc_b):
-    """Backward of the regression branch's last 3x3x3 conv from the sparse loss gradient (csrc/head_sparse.cu)."""
+USE_PREZERO = not bool(_os.environ.get("RTP_NO_PREZERO"))  # A/B switch: zero-fill of the hidden regression gradient beside the head convs
+
+
+def prezero(x):
+    """Zero-fills the chunk volumes of x on a side stream forked from the current one (rtp_zero_chunks) and returns the event
+    to wait for before x is used (None when the fill was issued in line).  Engine.head uses it for the regression half of the
+    head's hidden gradient: an HBM-bound fill that otherwise sits between the loss and the first backward kernel now runs
+    beside the tensor-bound head convolutions of the forward pass."""
+    dev = x.buf.device
+    if not ASYNC_WGRAD:
+        lib.call("rtp_zero_chunks", x.struct(), _stream())
+        return None
+    st = _side_stream(dev, "zero")
+    st["stream"].wait_stream(torch.cuda.current_stream(dev))
+    st["busy"] = True
+    with torch.cuda.stream(st["stream"]):
+        lib.call("rtp_zero_chunks", x.struct(), _stream())
+        ev = torch.cuda.Event()
+        ev.record(st["stream"])
+    return ev
+
+
+def reg_head_bwd_sparse(d_reg, t_in, ind, w, dt, dW, acc_w, db, acc_b, prezeroed=False):
+    """Backward of the regression branch's last 3x3x3 conv from the sparse loss gradient (csrc/head_sparse.cu).
+    prezeroed: dt's chunks are zero already (prezero above)."""
     L = lib.load()
     N, M = ind.shape
     R, Cin = w.shape[0], w.shape[1]
     ws = workspace(L.rtp_reg_head_bwd_sparse_workspace_bytes(N, M), d_reg.buf.device, "regsp")
     wc = w.detach()
     assert wc.is_contiguous() and dW.is_contiguous() and ind.dtype == torch.int64 and ind.is_contiguous()
-    lib.call("rtp_reg_head_bwd_sparse", d_reg.struct(), t_in.struct(), ind.data_ptr(), M, wc.data_ptr(), R, Cin, dt.struct(),
+    lib.call("rtp_reg_head_bwd_sparse_prezeroed" if prezeroed else "rtp_reg_head_bwd_sparse", d_reg.struct(), t_in.struct(),
+             ind.data_ptr(), M, wc.data_ptr(), R, Cin, dt.struct(),
              dW.data_ptr(), int(acc_w), db.data_ptr(), int(acc_b), ws.data_ptr(), _stream())
 
 

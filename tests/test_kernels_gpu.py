@@ -558,6 +558,51 @@ def test_head_loss_and_decode(one_hm):
             assert abs(score[n, c].item() - kp[4]) <= 1e-6
 
 
+def test_head_loss_flags_sparse_regression_gradient_and_spare_chunk():
+    """rtp_head_loss_flags: with RTP_LOSS_SPARSE_DREG the regression gradient is cleared + accumulated at the target voxels only
+    (identical there to the dense call, untouched elsewhere), and chunks of d_hm behind the class chunks are zero-filled."""
+    from oracle import hrpose_oracle as O
+    from rtpose_b200 import lib, ops
+    from rtpose_b200.p8 import P8
+    grid, N, ncls, R = (8, 16, 24), 3, 15, 3
+    rs = np.random.RandomState(6)
+    tgt = O.batch_targets([O.synth_pose(rs, grid) for _ in range(N)], grid, False)
+    tgt = {k: v.cuda() for k, v in tgt.items()}
+    tgt["ind"][1, 3] = tgt["ind"][1, 2]   # two targets (classes 2 and 3) of a sample on one voxel: their regression gradients add up
+    tgt["mask"][1, 2:4] = 1
+    tgt["mask"][2, 5] = 0                 # a masked-out target: contributes nothing, its voxel still gets a defined (zero) gradient
+    hp, rp = to_p8(bf(rnd(N, ncls, *grid, seed=32) * 0.5 - 2.0)), to_p8(rnd(N, R, *grid, seed=33))
+    cw = torch.ones(R, device="cuda")
+    M = tgt["ind"].shape[1]
+    ws = torch.empty(lib.load().rtp_head_loss_workspace_bytes(N, ncls, *grid), dtype=torch.uint8, device="cuda")
+
+    def run(flags, fill):
+        d_hm, d_reg = P8(N, 24, *grid), P8(N, R, *grid)
+        d_hm.buf.fill_(fill)
+        d_reg.buf.fill_(fill)
+        out = torch.empty(4 + R, device="cuda")
+        lib.call("rtp_head_loss_flags", hp.struct(), rp.struct(), ncls, R, tgt["hm"].data_ptr(), tgt["ind"].data_ptr(),
+                 tgt["mask"].data_ptr(), tgt["cat"].data_ptr(), tgt["anno_pose"].data_ptr(), M, 0.5, cw.data_ptr(), 1.0,
+                 out.data_ptr(), d_hm.struct(), d_reg.struct(), flags, ws.data_ptr(), ops._stream())
+        torch.cuda.synchronize()
+        return out.cpu(), d_hm.to_ncdhw().cpu(), d_reg.to_ncdhw().cpu()
+
+    o_d, hm_d, reg_d = run(0, 7.0)
+    o_s, hm_s, reg_s = run(lib.RTP_LOSS_SPARSE_DREG, 7.0)
+    assert torch.equal(o_d, o_s)
+    assert torch.equal(hm_d, hm_s)
+    assert float(hm_d[:, 15:].abs().max()) == 0.0         # class padding (channel 15) and the spare chunk (16..23)
+    assert float(hm_d[:, :15].abs().max()) > 0.0
+    Z, Y, X = grid
+    at_target = torch.zeros(N, Z * Y * X, dtype=torch.bool)
+    at_target.scatter_(1, tgt["ind"].cpu(), True)
+    at_target = at_target.view(N, 1, Z, Y, X).expand(N, R, Z, Y, X)
+    assert torch.equal(reg_s[at_target], reg_d[at_target])
+    assert float(reg_d[at_target].abs().max()) > 0.0
+    assert bool((reg_s[~at_target] == 7.0).all())          # untouched away from the targets
+    assert float(reg_d[~at_target].abs().max()) == 0.0     # the dense call zero-fills
+
+
 def test_decode_tie_breaks_to_lowest_reference_index():
     from rtpose_b200.engine import Engine
     grid, N = (4, 6, 10), 2
