@@ -33,6 +33,10 @@ def _adjacent_cat(a, b):
     return torch.cat([a, b], 0).contiguous()
 
 
+FUSE_PRIORITY = int(os.environ.get("RTP_FUSE_PRIO", "-2"))  # stream priority of the side fuse outputs (0: the branch streams, as before)
+FUSE_LONGEST_FIRST = not bool(os.environ.get("RTP_NO_FUSE_ORDER"))  # A/B switch: issue the side fuse outputs longest chain first
+
+
 class Engine:
     def __init__(self, arch, final_fuse, params, reg_channels, num_classes, loss_weight, code_weights,
                  prefix_backbone="backbone.", prefix_head="pose_head."):
@@ -357,7 +361,7 @@ class Engine:
             for x in xs:  # statistics every fuse conv may ask for, computed once, before the fork
                 if self._stats_get(x) is None:
                     self._stats_put(x, ops.gn_stats(x, 8 if x.C >= 8 else 1))
-            used = {i: self._branch_stream(i, dev) for i in idx if i > 0}
+            used = {i: self._fuse_stream(i, dev) for i in idx if i > 0}
             for st in used.values():  # fork everything first: a later wait_stream(main) would also wait for output 0
                 st.wait_stream(main)
             if train and self.parallel_fuse_bwd:  # runs LAST among the fuse closures in backward
@@ -367,17 +371,30 @@ class Engine:
                         cur.wait_stream(st)
                 self.tape.append(join_bwd)
         self._fuse_closures = []
-        for i in idx:
+        # Issue order: output 0, then the side outputs with the LONGEST stride-2 chain first (their first convs all want the
+        # whole GPU and run one after the other: the chain with the most stages behind it should not be the last to start).
+        # The backward closures and the fuse_sum closures keep the order of `idx` (gradient accumulation order unchanged).
+        order = [i for i in idx if i == 0] + sorted((i for i in idx if i > 0), reverse=True) if par and FUSE_LONGEST_FIRST else idx
+        ys, segs, fcl = {}, {}, {}
+        base = len(self.tape)
+        for i in order:
             st = used.get(i) if par else None
-            t0 = len(self.tape)
+            t0, f0 = len(self.tape), len(self._fuse_closures)
             with (torch.cuda.stream(st) if st is not None else contextlib.nullcontext()):
-                y = self._fuse_output(xs, prefix, nb, i, train)
+                ys[i] = self._fuse_output(xs, prefix, nb, i, train)
             if st is not None and train and self.parallel_fuse_bwd:
                 # backward of output i's fuse layers on the same stream; accumulation into the shared input gradients
                 # is chained in program order by _grad_of / _wrote
                 for k in range(t0, len(self.tape)):
                     self.tape[k] = self._on_stream(self.tape[k], st)
-            outs.append(y)
+            segs[i], fcl[i] = self.tape[t0:], self._fuse_closures[f0:]
+            del self.tape[t0:]
+            del self._fuse_closures[f0:]
+        assert len(self.tape) == base
+        for i in idx:
+            self.tape.extend(segs[i])
+            self._fuse_closures.extend(fcl[i])
+            outs.append(ys[i])
         self.tape.extend(self._fuse_closures)
         self._fuse_closures = []
         if par:
@@ -418,6 +435,19 @@ class Engine:
                 # first GroupNorm backward into xs[i] comes, and rides in it (_defer_add)
                 self._fuse_closures.append(self._fuse_bwd(y, same, low))
             return y
+
+    def _fuse_stream(self, i, device):
+        """Stream of fuse output i >= 1.  Its priority is HIGHER than the main (capture) stream's: the stride-2 chains of the side
+        outputs are sequences of small latency-bound kernels that end the module's critical path, while output 0's fuse_sum on
+        the main stream is one long kernel of ~10^4 blocks — at equal or lower priority the chains' kernels queued behind all
+        of its blocks (0.27 ms of a nearly empty GPU per module, profiles/r02_timeline_step.txt)."""
+        if FUSE_PRIORITY == 0:
+            return self._branch_stream(i, device)
+        st = self._bstreams.get(("fuse", i, str(device)))
+        if st is None:
+            st = ops.named_stream(device, "fuse%d/%d" % (ops.LANE, i), priority=FUSE_PRIORITY)
+            self._bstreams[("fuse", i, str(device))] = st
+        return st
 
     def _branch_stream(self, b, device):
         st = self._bstreams.get((b, str(device)))
