@@ -34,6 +34,7 @@ def _adjacent_cat(a, b):
 
 
 FUSE_PRIORITY = int(os.environ.get("RTP_FUSE_PRIO", "-2"))  # stream priority of the side fuse outputs (0: the branch streams, as before)
+BRANCH_PRIORITY = int(os.environ.get("RTP_BRANCH_PRIO", "-1"))  # stream priority of the side branches b >= 1 (res blocks): the capture stream's, not below it
 FUSE_LONGEST_FIRST = not bool(os.environ.get("RTP_NO_FUSE_ORDER"))  # A/B switch: issue the side fuse outputs longest chain first
 
 
@@ -452,7 +453,8 @@ class Engine:
     def _branch_stream(self, b, device):
         st = self._bstreams.get((b, str(device)))
         if st is None:
-            st = ops.named_stream(device, "branch%d/%d" % (ops.LANE, b))  # shared by all engines of the process (see ops.named_stream)
+            # shared by all engines of the process (see ops.named_stream)
+            st = ops.named_stream(device, "branch%d/%d" % (ops.LANE, b), priority=BRANCH_PRIORITY)
             self._bstreams[(b, str(device))] = st
         return st
 
