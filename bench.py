@@ -259,7 +259,7 @@ def build_params(cfg, device):
 
 
 EW = {"gn_apply", "gn_backward", "fuse_sum", "upsample_bwd", "grad_add", "conat"}  # element-wise families: they record algorithmic BYTES
-TENSOR = {"conv_generic", "conv_k3s1", "conv_pw", "wgrad_generic", "wgrad_k3s1", "wgrad_s2d", "wgrad_pw"}
+TENSOR = {"conv_generic", "conv_k3s1", "conv_pw", "wgrad_generic", "wgrad_k3s1", "wgrad_s2d", "wgrad_pw", "conv_k3s1_units", "wgrad_k3s1_units"}
 
 
 def ncu_traffic(kname, key, batch):
@@ -303,12 +303,14 @@ def summarize_profile(prof, total_ms, nprof, batch, timing_note):
     if fam:
         for key, (tt, n, fl) in sorted(fam.items(), key=lambda kv: -kv[1][0])[:16]:
             top.append({"kernel": key[0], "cin": key[1], "cout": key[2], "taps": key[3], "is_os": [key[4], key[5]], "rows": list(key[6]),
-                        "launches": n, "ms_total": round(tt, 3), "tflops": round(fl / (tt * 1e-3) / 1e12, 1)})
+                        "launches": n, "ms_total": round(tt, 3), "tflops": round(fl / (tt * 1e-3) / 1e12, 1) if fl > 0 else None})
+            if fl <= 0:
+                top[-1]["note"] = "restricted to a device-side unit list (the tiles around the targets): no algorithmic FLOPs claimed"
         by_kernel = {}
         for key, (tt, n, fl) in fam.items():
             a = by_kernel.setdefault(key[0], [0.0, 0, 0.0])
             a[0] += tt; a[1] += n; a[2] += fl
-        kname = max(by_kernel, key=lambda k: by_kernel[k][0])
+        kname = max((k for k in by_kernel if by_kernel[k][2] > 0), key=lambda k: by_kernel[k][0])
         key, (tt, n, fl) = max(((k, v) for k, v in fam.items() if k[0] == kname), key=lambda kv: kv[1][0])
         ach = fl / (tt * 1e-3) / 1e12
         traffic, tsrc = ncu_traffic(kname, key, batch)
@@ -318,7 +320,8 @@ def summarize_profile(prof, total_ms, nprof, batch, timing_note):
                 "algorithmic_flops_per_launch": fl / n, "avg_launch_ms": tt / n, "share_of_step": by_kernel[kname][0] / total_ms,
                 "traffic": traffic, "traffic_source": tsrc, "timing": timing_note,
                 "hbm_bound_kernels": hbm_kernels, "hbm_peak_GBps": hbm_peak,
-                "all_tensor_kernels": {k: {"tflops": round(v[2] / (v[0] * 1e-3) / 1e12, 1), "frac_of_burst": round(v[2] / (v[0] * 1e-3) / 1e12 / pk_burst, 3),
+                "all_tensor_kernels": {k: {"tflops": round(v[2] / (v[0] * 1e-3) / 1e12, 1) if v[2] > 0 else None,
+                                           "frac_of_burst": round(v[2] / (v[0] * 1e-3) / 1e12 / pk_burst, 3) if v[2] > 0 else None,
                                            "ms_per_step": round(v[0] / nprof, 3), "share_of_step": round(v[0] / total_ms, 3)} for k, v in by_kernel.items()}}
     return roof, top
 
@@ -493,10 +496,15 @@ def run_ours(args, rank, world, local_rank):
                                                               else "one flat all-reduce after backward (overlapped slices measured slower: --overlap-allreduce)")),
                        "cuda_graph": use_graph, "wgrad_side_stream": bool(ops.ASYNC_WGRAD), "branch_streams": bool(eng.parallel_branches),
                        "targets": "assigned on the device from resident fp64 skeletons every step (rtp_assign_targets)",
+                       "head_regression_branch": ("training: forward and backward on the (sample, tile) units around the target voxels only — "
+                                                  "CenterHead.loss gathers the regression map there and nowhere else, so loss and all "
+                                                  "gradients equal the dense evaluation (A/B: RTP_NO_SPARSE_FWD / _UNITS / _REG=1)"),
                        "optimizer": ("fused clip(35) + decoupled wd + Adam, one-cycle lr (rtp_adam_step) inside the timed region"
                                      if opt is not None else "none (--no-optimizer)")}),
             "model_tflops": 3 * gf_fwd * 1e9 * value / 1e12, "model_flops_frac_of_peak": 3 * gf_fwd * 1e9 * value / 1e12 / world / pk_burst,
             "model_flops_frac_of_sustained_peak": 3 * gf_fwd * 1e9 * value / 1e12 / world / pk_sust,
+            "model_tflops_is": "3 x the reference model's dense forward FLOPs x frames/s (MFU convention: the work the reference performs per frame; "
+                               "the sparse regression branch executes fewer tensor FLOPs than that)",
             "loss": float(out[0]), "gpu_launches": launches, "host_issue_ms_per_step": round(host_issue_ms, 2), "clocks": sampler.summary(), "roofline": roof, "top_kernels": top}
 
     if not args.no_extras:

@@ -438,11 +438,13 @@ def conv_k3s1(packs, x, w, out, transpose_flip, bias=None, relu=False, res=None,
         d.stat_mode, d.stat_ws = (1 if stat[0] == "stats" else 2), sws.data_ptr()
         if stat[0] == "red":
             d.stat_aux = stat[2].struct()
-    pkey = ("conv_k3s1", Cin if not transpose_flip else Cout, Cout if not transpose_flip else Cin, 27, 1, 1,
-            (x.Z, x.X, x.Y))
+    # (launches restricted to a unit list are their own profile family: their work depends on the device-side unit count, so
+    # no algorithmic FLOPs are claimed for them and they do not dilute the dense launches' figures)
+    pkey = ("conv_k3s1" if units is None else "conv_k3s1_units", Cin if not transpose_flip else Cout,
+            Cout if not transpose_flip else Cin, 27, 1, 1, (x.Z, x.X, x.Y))
     ev = _prof_begin(pkey)
     lib.call("rtp_conv_k3s1", C.byref(d), _stream())
-    _prof_end(pkey, ev, 2.0 * x.N * x.voxels * Cin * Cout * 27)
+    _prof_end(pkey, ev, 2.0 * x.N * x.voxels * Cin * Cout * 27 if units is None else 0.0)
     if stat is None:
         return out
     nct = L.rtp_conv_k3s1_num_ctas(K, NPo, x.N, x.Z, x.X, x.Y)
@@ -574,14 +576,14 @@ def _wgrad_k3s1(x, dy, outs, units=None):
                 dyg = dy.channels(nn + h, hn)
                 NP = ceil_to(hn, 16)
                 ws, done = _split_ws("wgrad3", L.rtp_wgrad_k3s1_workspace_bytes(NP, num_sms()), dev)
-                key = ("wgrad_k3s1", 32, hn, 27, 1, 1, (x.Z, x.X, x.Y))
+                key = ("wgrad_k3s1" if units is None else "wgrad_k3s1_units", 32, hn, 27, 1, 1, (x.Z, x.X, x.Y))
                 ev = _prof_begin(key)
                 if units is not None:
                     lib.call("rtp_wgrad_k3s1_units", xg.struct(), dyg.struct(), NP, zero.data_ptr(), ws.data_ptr(), C.byref(nsplit),
                              units[0].data_ptr(), units[1].data_ptr(), _stream())
                 else:
                     lib.call("rtp_wgrad_k3s1", xg.struct(), dyg.struct(), NP, zero.data_ptr(), ws.data_ptr(), C.byref(nsplit), _stream())
-                _prof_end(key, ev, 2.0 * x.N * x.voxels * 32 * hn * 27)
+                _prof_end(key, ev, 2.0 * x.N * x.voxels * 32 * hn * 27 if units is None else 0.0)
                 done(lambda ws=ws, ns=nsplit.value, NP=NP, gw=gw, h=h, hn=hn, c=c0 + gi * 32, acc=acc: lib.call(
                     "rtp_wgrad_k3s1_reduce", ws.data_ptr(), ns, NP, gw[h:].data_ptr(), gw.shape[1], hn, 0, c, int(acc), _stream()))
                 h += hn
