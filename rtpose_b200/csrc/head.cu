@@ -2,7 +2,8 @@
 // arg-max keypoint decode.  HBM-bound: each reads the heatmap once.
 //
 // Algorithmic bytes per frame: loss = hm bf16 (2 B x 8-channel vector per voxel) + target fp32 (4 B per class
-// voxel) read, d_hm written, d_reg zero-filled; decode = hm read once + one regression row.
+// voxel) read, d_hm written (+ a zero-filled K-padding chunk when the caller hands one over), d_reg zero-filled unless the
+// caller consumes it at the target voxels only (RTP_LOSS_SPARSE_DREG); decode = hm read once + one regression row.
 #include "common.cuh"
 
 namespace {
